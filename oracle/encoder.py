@@ -1,0 +1,97 @@
+"""numpy restatement of ``TempME.forward`` -- TEST INFRASTRUCTURE ONLY.
+
+Follows /root/reference/models/explainer.py line by line (eval mode: every Dropout is the
+identity).  ``dtype=np.float32`` mirrors the reference's arithmetic type; ``dtype=np.float64``
+is the arbiter used to decide which of two fp32 results is closer to the exact value.
+
+Parity status: PINNED against the unmodified reference module (run on CPU with a
+``torch_scatter`` stand-in) by tests/golden/make_golden.py -> tests/golden/encoder_*.npz.
+
+``params`` uses the reference's ``state_dict`` names:
+  event_conv.lin_event.{weight,bias}, event_conv.MLP.{0,2}.{weight,bias},
+  attention.{W1,W2}.{weight,bias}, attention.MLP.{0,3}.{weight,bias},
+  MLP.{0,3,5}.{weight,bias}, time_encoder.{basis_freq,phase}
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _lin(x, p, name, dt):
+    # nn.Linear: x @ W^T + b
+    return x @ p[name + ".weight"].astype(dt).T + p[name + ".bias"].astype(dt)
+
+
+def time_encode(ts, p, dt):
+    """TimeEncode.forward, explainer.py:51-59: cos(ts * basis_freq + phase)."""
+    m = ts[..., None] * p["time_encoder.basis_freq"].astype(dt)
+    m = m + p["time_encoder.phase"].astype(dt)
+    return np.cos(m)
+
+
+def event_gcn(ev, src, tgt, p, dt):
+    """event_gcn.forward, explainer.py:85-96."""
+    event = _lin(ev, p, "event_conv.lin_event", dt)
+    msg = np.maximum(tgt + event, 0)
+    h = np.maximum(_lin(src + msg, p, "event_conv.MLP.0", dt), 0)
+    return _lin(h, p, "event_conv.MLP.2", dt)
+
+
+def temporal_attention(feat, time_idx, cut_time, p, dt, use_temporal=True):
+    """TemporalAwareAttention.forward, explainer.py:789-846 (Attention.forward :25-43 when not use_temporal)."""
+    src = feat[:, :, 2, :]                      # [B, W, 2H]   :799
+    tgt = feat[:, :, 0:2, :]                    # [B, W, 2, 2H] :800
+    Wp = _lin(src, p, "attention.W1", dt)       # :806
+    Wq = _lin(tgt, p, "attention.W2", dt)       # :807
+    scores = np.einsum("bwd,bwkd->bwk", Wp, Wq)  # bmm, :808
+    if use_temporal:
+        sel = time_idx[:, :, :2]                # :820
+        td = np.abs(cut_time[:, None, None] - sel)          # :826
+        std = td.astype(np.float64).std(ddof=1) if td.size > 1 else np.float64("nan")   # torch .std() is unbiased, :828
+        tw = np.exp(-td / (dt(std) + dt(1e-6)))
+        scores = scores * (dt(1.0) - dt(0.3) + dt(0.3) * tw)    # :835-836
+    scores = scores - scores.max(-1, keepdims=True)
+    e = np.exp(scores)
+    alpha = e / e.sum(-1, keepdims=True)        # softmax :839
+    out = np.einsum("bwk,bwkd->bwd", alpha, Wq)  # bmm :841
+    out = src + out                             # :842
+    h = np.maximum(_lin(out, p, "attention.MLP.0", dt), 0)
+    last = "attention.MLP.3" if "attention.MLP.3.weight" in p else "attention.MLP.2"   # Attention.MLP has no Dropout, :18
+    return _lin(h, p, last, dt)                 # [B, W, H]
+
+
+def forward(p, node_feat, edge_feat, walks, cut_time, edge_identify, dtype=np.float32,
+            use_temporal=True, if_cat=True, return_hidden=False):
+    """TempME.forward, explainer.py:174-201.
+
+    walks = (node_idx [B,W,6], edge_idx [B,W,3], time_idx [B,W,3], cat_feat [B,W,1] or [B,W], _)
+    """
+    dt = dtype
+    node_idx, edge_idx, time_idx, cat_feat = walks[0], walks[1], walks[2], walks[3]
+    node_feat = np.asarray(node_feat).astype(dt); edge_feat = np.asarray(edge_feat).astype(dt)
+    # timestamps and cut times go through .float() first (:325, :814-816)
+    t32 = np.asarray(time_idx).astype(np.float32)
+    cut32 = np.asarray(cut_time).astype(np.float32)
+    edge_features = edge_feat[np.asarray(edge_idx).astype(np.int64)]            # :332-338
+    edge_count = np.asarray(edge_identify).astype(np.float32).astype(dt)        # :177
+    delta = (t32[:, :, 2:3] - t32)                                               # :326 (fp32 subtraction)
+    B, W = delta.shape[:2]
+    time_features = time_encode(delta.astype(dt), p, dt)                         # :328-329
+    ev = np.concatenate([edge_features, edge_count, time_features], axis=-1)    # :179
+    nid = np.asarray(node_idx).astype(np.int64)
+    srcf = node_feat[nid[:, :, [0, 2, 4]]]                                       # :348-351
+    tgtf = node_feat[nid[:, :, [1, 3, 5]]]
+    up_src = event_gcn(ev, srcf, tgtf, p, dt)                                    # :182
+    up_tgt = event_gcn(ev, tgtf, srcf, p, dt)                                    # :184
+    feat = np.concatenate([up_src, up_tgt], axis=-1)                             # :185
+    h = temporal_attention(feat, t32.astype(dt), cut32.astype(dt), p, dt, use_temporal)   # :190-193
+    if if_cat:
+        cat = np.asarray(cat_feat).astype(np.int64).reshape(B, W)
+        onehot = np.eye(12, dtype=dt)[cat]                                       # :308-315
+        h = np.concatenate([h, onehot], axis=-1)                                 # :197
+    z = np.maximum(_lin(h, p, "MLP.0", dt), 0)
+    z = np.maximum(_lin(z, p, "MLP.3", dt), 0)
+    z = _lin(z, p, "MLP.5", dt)
+    out = 1.0 / (1.0 + np.exp(-z))                                               # :200
+    out = out.astype(dt)
+    return (out, h) if return_hidden else out
