@@ -1,0 +1,171 @@
+/*
+ * tempme_b200.h -- C ABI of libtempme_b200.so, the B200 (sm_100a) implementation of TempME's
+ * data-parallel hot path: time-ordered neighbour lookup, retrospective 3-event motif walk
+ * sampling, event anonymisation / motif-class histogram, edge-identity counts and the
+ * TimeEncode + motif-encoder scorer.
+ *
+ * The reference (dharunm236/TempME) is pure Python and has no FFI layer; its "plugin API" is the
+ * duck-typed NeighborFinder / TempME surface.  Each entry point below names the reference
+ * function it replaces (file:line relative to the reference root); tempme_b200/ (Python, ctypes)
+ * mirrors the reference classes on top of these calls, and INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns TM_OK (0) or a negative tm_status; tm_last_error() gives the text
+ *    (thread-local); no C++ exception crosses the boundary;
+ *  - pointers named d_* are DEVICE pointers on the graph's device, h_* are HOST pointers;
+ *  - every launch goes to the cudaStream_t passed as `stream` (0 = legacy default stream) and is
+ *    asynchronous; the library never synchronises the device on the hot path;
+ *  - graph handles are immutable after creation: concurrent readers are safe;
+ *  - a data-dependent failure that the reference reports as an exception (IndexError for an
+ *    e_idx that is not in a node's list, utils/graph.py:134-135) is reported through the
+ *    optional d_err word: 0 = fine, otherwise 1 + index of the smallest failing row.
+ */
+#ifndef TEMPME_B200_H
+#define TEMPME_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    TM_OK = 0,
+    TM_ERR_ARG = -1,         /* bad argument (null pointer, negative size, unsupported fan-out) */
+    TM_ERR_CUDA = -2,        /* a CUDA runtime call failed; see tm_last_error() */
+    TM_ERR_NOMEM = -3,
+    TM_ERR_NODE_RANGE = -4,  /* node id outside [0, n_nodes) in the adjacency entries */
+    TM_ERR_EDGE_TABLE = -5,  /* an edge id is negative or occurs in the lists of more than two nodes */
+    TM_ERR_UNSUPPORTED = -6
+} tm_status;
+
+typedef struct tm_graph tm_graph;
+typedef void *tm_stream; /* cudaStream_t */
+
+/* e_idx value meaning "this row has no e_idx: cut by time" (the e_idx_l=None call of the reference) */
+#define TM_EIDX_NONE INT32_MIN
+/* stage ids of the draw contract (DESIGN.md "RNG") */
+#define TM_STAGE_STEP2 16u
+#define TM_STAGE_STEP3 17u
+#define TM_MAX_STEP2_FANOUT 32
+
+int tm_version(void);
+const char *tm_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph: replaces NeighborFinder.__init__ / init_off_set / get_ts2idx (utils/graph.py:13-101).
+ * Input is the flattened adj_list: entry j belongs to the list of node h_entry_node[j]; entries
+ * of one node appear in insertion order.  Per node the entries are stably sorted by timestamp
+ * (graph.py:48) into a device-resident CSR; nodeedge2idx is materialised as a per-edge table.
+ * ------------------------------------------------------------------------------------------ */
+int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t *h_entry_node,
+                    const int32_t *h_entry_nbr, const int32_t *h_entry_eidx, const double *h_entry_ts,
+                    int device, tm_graph **out);
+/* Same, from an event list: event k is appended to src's list and then to dst's list
+ * (the callers' loop, temp_exp_main.py:135-144 / utils/null_model.py:55-64). */
+int tm_graph_create_from_events(int64_t n_nodes, int64_t n_events, const int32_t *h_src, const int32_t *h_dst,
+                                const int32_t *h_eidx, const double *h_ts, int device, tm_graph **out);
+void tm_graph_destroy(tm_graph *g);
+int tm_graph_sizes(const tm_graph *g, int64_t *n_nodes, int64_t *n_entries, int64_t *max_eidx, int64_t *device_bytes);
+/* Public attribute surface of NeighborFinder (off_set_l, node_idx_l, edge_idx_l, node_ts_l; graph.py:22-27) */
+int tm_graph_export(const tm_graph *g, int64_t *h_off, int32_t *h_nbr, int32_t *h_eidx, double *h_ts);
+/* nodeedge2idx as a table: h_tab[e] = {node_a, node_b, cut_a, cut_b} (-1 = absent), e in [0, max_eidx] */
+int tm_graph_export_edge_table(const tm_graph *g, int32_t *h_tab);
+
+/* find_before (utils/graph.py:103-146) for R rows: window = [d_start[i], d_start[i] + d_cut[i]).
+ * d_cut_time may be NULL when every row carries an e_idx; d_eidx may be NULL (all rows cut by time). */
+int tm_find_before_batch(const tm_graph *g, int64_t R, const int32_t *d_node, const double *d_cut_time,
+                         const int32_t *d_eidx, int64_t *d_start, int32_t *d_cut, int32_t *d_err, tm_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Draws.  index = (r64 * L) >> 64 with r64 from Philox4x32-10(key = seed, ctr = (slot >> 1,
+ * row_lo, row_hi, stage)), low or high 64-bit half by slot & 1; row = row_offset(...) + local row.
+ * If d_inject is non-NULL the draws are taken from it instead (d_inject[row_local * fanout + slot],
+ * already reduced to [0, L)): the mode used to replay indices recorded from the reference's own
+ * MT19937 stream.
+ * ------------------------------------------------------------------------------------------ */
+
+/* get_temporal_neighbor (utils/graph.py:197-231), uniform branch: n sorted draws per non-empty
+ * window.  Outputs [R, n]: node (i32), eidx (i32), ts (f32).  stage = hop level. */
+int tm_sample_hop(const tm_graph *g, int64_t R, const int32_t *d_node, const double *d_cut_time,
+                  const int32_t *d_eidx, int n, uint64_t seed, uint32_t stage, uint64_t row_offset,
+                  const uint32_t *d_inject, int32_t *d_o_node, int32_t *d_o_eidx, float *d_o_ts,
+                  int32_t *d_err, tm_stream stream);
+
+/* find_k_walks = get_next_step + get_final_step (utils/graph.py:265-476).
+ * d_root [B]; d_h1_* [B, n] (first-hop record).  W = n * N2 walks per root, walk w = i1 * N2 + j.
+ * Outputs: d_o_nodes [B, W, 6] = [src3,tgt3,src2,tgt2,src1,tgt1]; d_o_eidx [B, W, 3] = [e3,e2,e1];
+ * d_o_t [B, W, 3] = [t3,t2,t1]; optional d_o_anony [B, W, 3] = [1, c, t]; optional d_o_cat [B*W]
+ * = category id 0..11 in the order of processed/data_preprocess.py:171; optional histograms
+ * (accumulated, not zeroed): d_hist_null[12] in the key order of utils/null_model.py:90 and
+ * d_hist_prep[12] in the data_preprocess order; optional d_scanned[1] accumulates the number of
+ * prefix entries the neighbour-id filter of cases 1/2 had to inspect.
+ * row_offset = global index of the first root (RNG rows are row_offset*n + i and row_offset*W + i). */
+int tm_sample_walks(const tm_graph *g, int64_t B, int n, int N2, const int32_t *d_root,
+                    const int32_t *d_h1_node, const int32_t *d_h1_eidx, const float *d_h1_ts,
+                    uint64_t seed, uint64_t row_offset, const uint32_t *d_inject2, const uint32_t *d_inject3,
+                    int32_t *d_o_nodes, int32_t *d_o_eidx, float *d_o_t, int32_t *d_o_anony, uint8_t *d_o_cat,
+                    unsigned long long *d_hist_null, unsigned long long *d_hist_prep,
+                    unsigned long long *d_scanned, tm_stream stream);
+
+/* statistic (utils/null_model.py:75-82) / marginal (processed/data_preprocess.py:148-208) on
+ * anonymised rows [count, 3]: accumulates both 12-bin histograms, optionally writes category ids.
+ * A row that is none of the 12 classes (KeyError in the reference) sets d_err. */
+int tm_class_hist(int64_t count, const int32_t *d_anony, unsigned long long *d_hist_null,
+                  unsigned long long *d_hist_prep, uint8_t *d_o_cat, int32_t *d_err, tm_stream stream);
+
+/* new_edge_info (processed/data_preprocess.py:327-343): d_eidx [B, W, 3] -> d_out [B, W, 3, 3] (f32) */
+int tm_edge_identity(int64_t B, int64_t W, const int32_t *d_eidx, float *d_out, tm_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Encoder / scorer: TempME.forward (models/explainer.py:174-201) in eval mode.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t node_dim;     /* D  = base.n_feat_th.shape[1] = time_dim   explainer.py:107-109 */
+    int32_t edge_dim;     /* Ed = base.e_feat_th.shape[1]              explainer.py:108 */
+    int32_t hid_dim;      /* H                                          explainer.py:111 */
+    int32_t use_temporal; /* TemporalAwareAttention (1) or Attention (0) explainer.py:121 */
+    int32_t if_cat;       /* one-hot category features                 explainer.py:116,195-197 */
+} tm_encoder_desc;
+
+/* Host pointers to the reference's parameters (nn.Linear layout: weight [out, in] row-major). */
+typedef struct {
+    const float *lin_event_w, *lin_event_b; /* event_conv.lin_event  [D, Ed+3+D]   explainer.py:82 */
+    const float *gcn0_w, *gcn0_b;           /* event_conv.MLP.0      [H, D]        :84 */
+    const float *gcn2_w, *gcn2_b;           /* event_conv.MLP.2      [H, H] */
+    const float *att_w1_w, *att_w1_b;       /* attention.W1          [2H, 2H]      :772 */
+    const float *att_w2_w, *att_w2_b;       /* attention.W2          [2H, 2H]      :773 */
+    const float *att_mlp0_w, *att_mlp0_b;   /* attention.MLP.0       [H, 2H]       :776-781 */
+    const float *att_mlp3_w, *att_mlp3_b;   /* attention.MLP.3 (.2)  [H, H] */
+    const float *mlp0_w, *mlp0_b;           /* MLP.0                 [M, M], M = H + 12 (or H)   :123-125 */
+    const float *mlp3_w, *mlp3_b;           /* MLP.3                 [H, M] */
+    const float *mlp5_w, *mlp5_b;           /* MLP.5                 [1, H] */
+    const float *basis_freq, *phase;        /* time_encoder          [D], [D]      :49-50 */
+} tm_encoder_params;
+
+/* Size in floats of the packed device weight blob, and the packer (host -> host blob; the caller
+ * uploads it once and keeps it resident). */
+int64_t tm_encoder_blob_floats(const tm_encoder_desc *desc);
+int tm_encoder_pack(const tm_encoder_desc *desc, const tm_encoder_params *params, float *h_blob);
+/* Workspace (floats) tm_encode_score needs for B roots in groups of `group` roots. */
+int64_t tm_encoder_workspace_floats(const tm_encoder_desc *desc, int64_t B, int64_t W, int64_t group);
+
+/* Scores for B roots x W walks.  `group` = roots per reference batch: the temporal attention
+ * normalises by the unbiased std of |cut_time - t| over a whole batch [group, W, 2]
+ * (explainer.py:826-828), so scores depend on the batch a root is scored with.
+ * d_nodes [B,W,6] i32, d_eidx [B,W,3] i32, d_t [B,W,3] f32, d_cat [B*W] u8, d_cut_time [B] f32,
+ * d_edge_identity [B,W,3,3] f32, feature tables row-major f32.  d_scores [B*W] f32. */
+int tm_encode_score(const tm_encoder_desc *desc, const float *d_blob, int64_t B, int64_t W, int64_t group,
+                    const int32_t *d_nodes, const int32_t *d_eidx, const float *d_t, const uint8_t *d_cat,
+                    const float *d_cut_time, const float *d_edge_identity,
+                    const float *d_node_feat, int64_t n_node_rows, const float *d_edge_feat, int64_t n_edge_rows,
+                    float *d_workspace, float *d_scores, int device, tm_stream stream);
+
+/* Launch counter: number of kernels this library has launched in this process (bench gpu_launches). */
+uint64_t tm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEMPME_B200_H */

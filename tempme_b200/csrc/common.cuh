@@ -1,0 +1,135 @@
+// Shared device/host helpers of libtempme_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/tempme_b200.h"
+
+namespace tmb {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define TM_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            tmb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return TM_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define TM_LAUNCH_CHECK()                                                                      \
+    do {                                                                                       \
+        tmb::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess) {                                                              \
+            tmb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return TM_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+// One CSR entry: 16 bytes so that a sampled neighbour costs one 128-bit load (one sector).
+struct __align__(16) Entry {
+    int32_t nbr;
+    int32_t eidx;
+    double ts;
+};
+
+// Device view of the graph (all pointers device memory, immutable after build).
+struct GraphView {
+    int64_t n_nodes;
+    int64_t n_entries;
+    int64_t max_eidx;
+    const int64_t *off;   // [n_nodes + 1]
+    const Entry *entry;   // [n_entries]  time-sorted per node
+    const int32_t *nbr;   // [n_entries]  neighbour ids only: 4 B/entry stream for the id filter of step 3
+    const int4 *etab;     // [max_eidx + 1] {node_a, node_b, cut_a, cut_b}: nodeedge2idx as a table
+};
+
+}  // namespace tm
+
+struct tm_graph {
+    tmb::GraphView v;
+    int device;
+    int64_t device_bytes;
+};
+
+namespace tmb {
+
+// ---------------- Philox4x32-10 (counter-based; DESIGN.md "RNG") ----------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                                        uint32_t c2, uint32_t c3, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ uint64_t draw_index(uint64_t seed, uint32_t stage, uint64_t row, uint32_t slot, uint64_t L) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), slot >> 1, (uint32_t)row, (uint32_t)(row >> 32), stage, o);
+    const uint64_t r = (slot & 1) ? ((uint64_t)o[3] << 32 | o[2]) : ((uint64_t)o[1] << 32 | o[0]);
+    return __umul64hi(r, L);
+}
+
+// d_err protocol: 0 = fine, otherwise 1 + smallest failing row
+__device__ __forceinline__ void report_row_error(int32_t *err, int64_t row) {
+    if (!err) return;
+    const int32_t val = (int32_t)min(row + 1, (int64_t)INT32_MAX);
+    int32_t old = *((volatile int32_t *)err);
+    while (old == 0 || val < old) {
+        const int32_t prev = atomicCAS(err, old, val);
+        if (prev == old) break;
+        old = prev;
+    }
+}
+
+__device__ __forceinline__ Entry load_entry(const Entry *p) {
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(p));
+    Entry e;
+    e.nbr = v.x; e.eidx = v.y;
+    e.ts = __longlong_as_double(((long long)(uint32_t)v.w << 32) | (uint32_t)v.z);
+    return e;
+}
+
+// nodeedge2idx[node].get(e): -1 when absent (None)
+__device__ __forceinline__ int64_t dict_get(const GraphView &g, int64_t node, int32_t e) {
+    if (e < 0 || (int64_t)e > g.max_eidx) return -1;
+    const int4 t = __ldg(g.etab + e);
+    if (node == t.x) return t.z;
+    if (node == t.y) return t.w;
+    return -1;
+}
+
+// bisect_left_adapt (utils/graph.py:511-530) as a warp-cooperative 33-ary search on the float64
+// timestamps of one node: first index i in [0, len) with ts[i] >= x.  All 32 lanes must call.
+__device__ __forceinline__ int64_t warp_lower_bound(const Entry *base, int64_t len, double x, int lane) {
+    int64_t lo = 0, hi = len;
+    while (hi - lo > 32) {
+        const int64_t span = hi - lo;
+        const int64_t pos = lo + ((int64_t)(lane + 1) * span) / 33;  // lo < pos < hi, increasing in lane
+        const double v = __ldg(&base[pos].ts);
+        const unsigned b = __ballot_sync(0xffffffffu, v < x);       // sorted -> lanes [0, cnt) are true
+        const int cnt = __popc(b);
+        const int64_t plo = lo + ((int64_t)cnt * span) / 33;        // pivot of lane cnt-1
+        const int64_t phi = lo + ((int64_t)(cnt + 1) * span) / 33;  // pivot of lane cnt
+        if (cnt > 0) lo = plo + 1;
+        if (cnt < 32) hi = phi;
+    }
+    const int64_t pos = lo + lane;
+    const bool lt = pos < hi && __ldg(&base[pos].ts) < x;
+    return lo + __popc(__ballot_sync(0xffffffffu, lt));
+}
+
+}  // namespace tm

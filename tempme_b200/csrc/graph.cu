@@ -1,0 +1,221 @@
+// Graph build + find_before.  Replaces NeighborFinder.__init__/init_off_set/get_ts2idx/find_before
+// (reference utils/graph.py:13-146).  The build is a one-time host pass (counting sort by node,
+// stable per-node sort by timestamp, literal emulation of get_ts2idx into a per-edge table),
+// followed by one upload; every query after that runs on the device.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tmb {
+
+static thread_local std::string t_err;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err = buf;
+}
+
+// find_before, utils/graph.py:103-146.  One warp per row so that the time cut is the
+// warp-cooperative search; e_idx rows cost one 16-byte table load.
+__global__ void find_before_kernel(GraphView g, int64_t R, const int32_t *__restrict__ node,
+                                   const double *__restrict__ cut_time, const int32_t *__restrict__ eidx,
+                                   int64_t *__restrict__ o_start, int32_t *__restrict__ o_cut, int32_t *err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= R) return;
+    const int64_t v = node[row];
+    if (v < 0 || v >= g.n_nodes) {
+        if (lane == 0) { o_start[row] = 0; o_cut[row] = 0; report_row_error(err, row); }
+        return;
+    }
+    const int64_t s = __ldg(g.off + v), len = __ldg(g.off + v + 1) - s;
+    const int32_t e = eidx ? eidx[row] : TM_EIDX_NONE;
+    int64_t c;
+    if (e == TM_EIDX_NONE) c = warp_lower_bound(g.entry + s, len, cut_time ? cut_time[row] : 0.0, lane);   // graph.py:129
+    else if (v > 0) {                                                                       // graph.py:133
+        c = dict_get(g, v, e);
+        if (c < 0) { c = 0; if (lane == 0) report_row_error(err, row); }   // IndexError, graph.py:134-135
+    } else c = 0;
+    if (lane == 0) { o_start[row] = s; o_cut[row] = (int32_t)c; }
+}
+
+}  // namespace tm
+
+using namespace tmb;
+
+extern "C" int tm_version(void) { return 100; }
+extern "C" const char *tm_last_error(void) { return tmb::t_err.c_str(); }
+extern "C" uint64_t tm_launch_count(void) { return tmb::g_launches.load(); }
+
+static inline int32_t slice_len(int64_t c, int64_t len) {  // python a[:c] on a list of length len
+    if (c < 0) { c += len; if (c < 0) c = 0; }
+    if (c > len) c = len;
+    return (int32_t)c;
+}
+
+extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t *h_node, const int32_t *h_nbr,
+                               const int32_t *h_eidx, const double *h_ts, int device, tm_graph **out) {
+    if (!out || n_nodes < 0 || n_entries < 0 || (n_entries > 0 && (!h_node || !h_nbr || !h_eidx || !h_ts))) {
+        set_error("tm_graph_create: bad argument");
+        return TM_ERR_ARG;
+    }
+    if (n_entries >= (int64_t)INT32_MAX) { set_error("tm_graph_create: more than 2^31-1 entries"); return TM_ERR_UNSUPPORTED; }
+    std::vector<int64_t> off(n_nodes + 1, 0);
+    int64_t max_e = -1;
+    for (int64_t j = 0; j < n_entries; ++j) {
+        const int32_t v = h_node[j];
+        if (v < 0 || v >= n_nodes) { set_error("entry %lld: node %d outside [0, %lld)", (long long)j, v, (long long)n_nodes); return TM_ERR_NODE_RANGE; }
+        if (h_eidx[j] < 0) { set_error("entry %lld: negative edge id %d", (long long)j, h_eidx[j]); return TM_ERR_EDGE_TABLE; }
+        max_e = std::max<int64_t>(max_e, h_eidx[j]);
+        off[v + 1]++;
+    }
+    for (int64_t v = 0; v < n_nodes; ++v) off[v + 1] += off[v];
+    // stable counting sort by node (keeps insertion order inside each list)
+    std::vector<Entry> ent(n_entries);
+    {
+        std::vector<int64_t> fill(off.begin(), off.end() - 1);
+        for (int64_t j = 0; j < n_entries; ++j) {
+            Entry &e = ent[fill[h_node[j]]++];
+            e.nbr = h_nbr[j]; e.eidx = h_eidx[j]; e.ts = h_ts[j];
+        }
+    }
+    // sorted(curr, key=lambda x: x[2]) -- stable, graph.py:48
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t v = 0; v < n_nodes; ++v) {
+        Entry *b = ent.data() + off[v], *e = ent.data() + off[v + 1];
+        auto lt = [](const Entry &x, const Entry &y) { return x.ts < y.ts; };
+        if (!std::is_sorted(b, e, lt)) std::stable_sort(b, e, lt);
+    }
+    // nodeedge2idx as a table: claim the (edge, node) slots (sequential: two nodes share one row)
+    std::vector<int4> etab(max_e + 1, make_int4(-1, -1, -1, -1));
+    for (int64_t v = 0; v < n_nodes; ++v)
+        for (int64_t p = off[v]; p < off[v + 1]; ++p) {
+            int4 &t = etab[ent[p].eidx];
+            if (t.x == (int32_t)v || t.y == (int32_t)v) continue;
+            if (t.x == -1) t.x = (int32_t)v;
+            else if (t.y == -1) t.y = (int32_t)v;
+            else { set_error("edge id %d occurs in the lists of more than two nodes", ent[p].eidx); return TM_ERR_EDGE_TABLE; }
+        }
+    // get_ts2idx, graph.py:77-101, emulated literally; each node only touches its own table words
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t v = 0; v < n_nodes; ++v) {
+        const int64_t s = off[v], len = off[v + 1] - s;
+        auto slot = [&](int32_t e) -> int32_t & { int4 &t = etab[e]; return t.x == (int32_t)v ? t.z : t.w; };
+        int64_t tie_lo = -1, tie_n = 0;
+        double last_ts = -1.0;                                                    // :82
+        for (int64_t i = 0; i < len; ++i) {
+            const double t = ent[s + i].ts;
+            slot(ent[s + i].eidx) = (int32_t)i;                                   // :85
+            if (t == last_ts) { if (tie_n == 0) { tie_lo = i - 1; tie_n = 2; } else tie_n++; }   // :87-91
+            if (!(t == last_ts) && tie_n > 0) {                                   // :93-98
+                for (int64_t j = 0; j < tie_n; ++j) slot(ent[s + tie_lo + j].eidx) -= (int32_t)j;
+                tie_n = 0;
+            }
+            last_ts = t;
+        }
+        for (int64_t i = 0; i < len; ++i) { int32_t &c = slot(ent[s + i].eidx); c = slice_len(c, len); }  // [:cut] semantics
+    }
+    std::vector<int32_t> nbr(n_entries);
+    for (int64_t p = 0; p < n_entries; ++p) nbr[p] = ent[p].nbr;
+
+    TM_CUDA(cudaSetDevice(device));
+    tm_graph *g = new tm_graph();
+    g->device = device;
+    void *d_off = nullptr, *d_ent = nullptr, *d_nbr = nullptr, *d_tab = nullptr;
+    const size_t b_off = sizeof(int64_t) * (n_nodes + 1), b_ent = sizeof(Entry) * std::max<int64_t>(n_entries, 1),
+                 b_nbr = sizeof(int32_t) * std::max<int64_t>(n_entries, 1), b_tab = sizeof(int4) * std::max<int64_t>(max_e + 1, 1);
+    cudaError_t ce = cudaMalloc(&d_off, b_off);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_ent, b_ent);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_nbr, b_nbr);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_tab, b_tab);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d_off, off.data(), b_off, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && n_entries) ce = cudaMemcpy(d_ent, ent.data(), sizeof(Entry) * n_entries, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && n_entries) ce = cudaMemcpy(d_nbr, nbr.data(), sizeof(int32_t) * n_entries, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && max_e >= 0) ce = cudaMemcpy(d_tab, etab.data(), sizeof(int4) * (max_e + 1), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        set_error("graph upload failed: %s", cudaGetErrorString(ce));
+        cudaFree(d_off); cudaFree(d_ent); cudaFree(d_nbr); cudaFree(d_tab);
+        delete g;
+        return ce == cudaErrorMemoryAllocation ? TM_ERR_NOMEM : TM_ERR_CUDA;
+    }
+    g->v.n_nodes = n_nodes; g->v.n_entries = n_entries; g->v.max_eidx = max_e;
+    g->v.off = (const int64_t *)d_off; g->v.entry = (const Entry *)d_ent; g->v.nbr = (const int32_t *)d_nbr; g->v.etab = (const int4 *)d_tab;
+    g->device_bytes = (int64_t)(b_off + b_ent + b_nbr + b_tab);
+    *out = g;
+    return TM_OK;
+}
+
+extern "C" int tm_graph_create_from_events(int64_t n_nodes, int64_t n_events, const int32_t *h_src, const int32_t *h_dst,
+                                           const int32_t *h_eidx, const double *h_ts, int device, tm_graph **out) {
+    if (n_events < 0 || (n_events > 0 && (!h_src || !h_dst || !h_eidx || !h_ts))) { set_error("tm_graph_create_from_events: bad argument"); return TM_ERR_ARG; }
+    std::vector<int32_t> node(2 * n_events), nbr(2 * n_events), e(2 * n_events);
+    std::vector<double> t(2 * n_events);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n_events; ++k) {   // adj[src].append((dst,e,t)); adj[dst].append((src,e,t))
+        node[2 * k] = h_src[k]; nbr[2 * k] = h_dst[k];
+        node[2 * k + 1] = h_dst[k]; nbr[2 * k + 1] = h_src[k];
+        e[2 * k] = e[2 * k + 1] = h_eidx[k];
+        t[2 * k] = t[2 * k + 1] = h_ts[k];
+    }
+    return tm_graph_create(n_nodes, 2 * n_events, node.data(), nbr.data(), e.data(), t.data(), device, out);
+}
+
+extern "C" void tm_graph_destroy(tm_graph *g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    cudaFree((void *)g->v.off); cudaFree((void *)g->v.entry); cudaFree((void *)g->v.nbr); cudaFree((void *)g->v.etab);
+    delete g;
+}
+
+extern "C" int tm_graph_sizes(const tm_graph *g, int64_t *n_nodes, int64_t *n_entries, int64_t *max_eidx, int64_t *device_bytes) {
+    if (!g) { set_error("tm_graph_sizes: null graph"); return TM_ERR_ARG; }
+    if (n_nodes) *n_nodes = g->v.n_nodes;
+    if (n_entries) *n_entries = g->v.n_entries;
+    if (max_eidx) *max_eidx = g->v.max_eidx;
+    if (device_bytes) *device_bytes = g->device_bytes;
+    return TM_OK;
+}
+
+extern "C" int tm_graph_export(const tm_graph *g, int64_t *h_off, int32_t *h_nbr, int32_t *h_eidx, double *h_ts) {
+    if (!g) { set_error("tm_graph_export: null graph"); return TM_ERR_ARG; }
+    TM_CUDA(cudaSetDevice(g->device));
+    if (h_off) TM_CUDA(cudaMemcpy(h_off, g->v.off, sizeof(int64_t) * (g->v.n_nodes + 1), cudaMemcpyDeviceToHost));
+    if ((h_nbr || h_eidx || h_ts) && g->v.n_entries) {
+        std::vector<Entry> ent(g->v.n_entries);
+        TM_CUDA(cudaMemcpy(ent.data(), g->v.entry, sizeof(Entry) * g->v.n_entries, cudaMemcpyDeviceToHost));
+        for (int64_t p = 0; p < g->v.n_entries; ++p) {
+            if (h_nbr) h_nbr[p] = ent[p].nbr;
+            if (h_eidx) h_eidx[p] = ent[p].eidx;
+            if (h_ts) h_ts[p] = ent[p].ts;
+        }
+    }
+    return TM_OK;
+}
+
+extern "C" int tm_graph_export_edge_table(const tm_graph *g, int32_t *h_tab) {
+    if (!g || !h_tab) { set_error("tm_graph_export_edge_table: bad argument"); return TM_ERR_ARG; }
+    TM_CUDA(cudaSetDevice(g->device));
+    if (g->v.max_eidx >= 0) TM_CUDA(cudaMemcpy(h_tab, g->v.etab, sizeof(int4) * (g->v.max_eidx + 1), cudaMemcpyDeviceToHost));
+    return TM_OK;
+}
+
+extern "C" int tm_find_before_batch(const tm_graph *g, int64_t R, const int32_t *d_node, const double *d_cut_time,
+                                    const int32_t *d_eidx, int64_t *d_start, int32_t *d_cut, int32_t *d_err, tm_stream stream) {
+    if (!g || R < 0 || (R > 0 && (!d_node || !d_start || !d_cut || (!d_cut_time && !d_eidx)))) { set_error("tm_find_before_batch: bad argument"); return TM_ERR_ARG; }
+    if (R == 0) return TM_OK;
+    TM_CUDA(cudaSetDevice(g->device));
+    const int threads = 256;
+    const int64_t blocks = (R * 32 + threads - 1) / threads;
+    find_before_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(g->v, R, d_node, d_cut_time, d_eidx, d_start, d_cut, d_err);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}

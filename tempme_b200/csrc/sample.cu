@@ -1,0 +1,328 @@
+// Sampling kernels: temporal neighbour sampling (get_temporal_neighbor), the fused 3-event walk
+// sampler (get_next_step + get_final_step + anonymisation class), motif-class histograms and
+// edge-identity counts.  Reference: utils/graph.py:197-476, utils/null_model.py:75-82,
+// processed/data_preprocess.py:148-208,327-343.  One warp per query row everywhere: the row's
+// windows are found with one or two 16-byte table loads, draws are counter-based (no state), the
+// gathers are 128-bit loads of whole CSR entries, and the neighbour-id filter of step 3 streams
+// the 4-byte id array with ballot/popc.
+#include "common.cuh"
+
+namespace tmb {
+
+constexpr int kWarpsPerBlock = 8;
+
+// prep-order category id (processed/data_preprocess.py:171) of anonymised row [1, c, t]
+__device__ __forceinline__ int class_prep(int c, int t) {
+    // c: 2 -> "1,2,t", 3 -> "1,3,t", 1 -> "1,1,t"
+    const unsigned m2 = 0x2103u, m3 = 0x5647u, m1 = 0x89abu;  // nibble t of each = id
+    const unsigned m = c == 2 ? m2 : (c == 3 ? m3 : m1);
+    return (int)((m >> (4 * t)) & 0xfu);
+}
+// 0-based position of a prep-order id in the null-model key order (utils/null_model.py:90)
+__constant__ int kPrepToNull[12] = {1, 3, 2, 0, 5, 6, 7, 4, 11, 10, 9, 8};
+
+// ---------------------------------------------------------------------------------------------
+// get_temporal_neighbor, utils/graph.py:197-231 (uniform / bias == 0 branch)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_hop_kernel(GraphView g, int64_t R, const int32_t *__restrict__ node, const double *__restrict__ cut_time,
+                  const int32_t *__restrict__ eidx, int n, uint64_t seed, uint32_t stage, uint64_t row_offset,
+                  const uint32_t *__restrict__ inject, int32_t *__restrict__ o_node, int32_t *__restrict__ o_eidx,
+                  float *__restrict__ o_ts, int32_t *err) {
+    extern __shared__ uint32_t sh_draw[];  // [kWarpsPerBlock][n]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+    if (row >= R) return;
+    uint32_t *d = sh_draw + (size_t)warp * n;
+    const int64_t v = node[row];
+    int64_t s = 0, c = 0;
+    if (v < 0 || v >= g.n_nodes) {
+        if (lane == 0) report_row_error(err, row);
+    } else {
+        s = __ldg(g.off + v);
+        const int64_t len = __ldg(g.off + v + 1) - s;
+        const int32_t e = eidx ? eidx[row] : TM_EIDX_NONE;
+        if (e == TM_EIDX_NONE) c = warp_lower_bound(g.entry + s, len, cut_time ? cut_time[row] : 0.0, lane);
+        else if (v > 0) {
+            c = dict_get(g, v, e);
+            if (c < 0) { c = 0; if (lane == 0) report_row_error(err, row); }
+        }
+    }
+    const int64_t ob = row * n;
+    if (c == 0) {  // no previous neighbours: padding row, no draw consumed (graph.py:214-215)
+        for (int k = lane; k < n; k += 32) { o_node[ob + k] = 0; o_eidx[ob + k] = 0; o_ts[ob + k] = 0.f; }
+        return;
+    }
+    for (int k = lane; k < n; k += 32) {
+        uint64_t x;
+        if (inject) {
+            x = inject[ob + k];
+            if (x >= (uint64_t)c) { x = c - 1; report_row_error(err, row); }
+        } else x = draw_index(seed, stage, row_offset + row, k, (uint64_t)c);
+        d[k] = (uint32_t)x;
+    }
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {  // np.sort of the sampled indices (graph.py:218) by rank
+        const uint32_t mine = d[k];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) { const uint32_t x = d[j]; rank += (x < mine) || (x == mine && j < k); }
+        const Entry en = load_entry(g.entry + s + mine);
+        o_node[ob + rank] = en.nbr; o_eidx[ob + rank] = en.eidx; o_ts[ob + rank] = (float)en.ts;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp-cooperative filtered prefix scans for get_final_step cases 1/2 (graph.py:358-371,398-411)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t warp_count_match(const int32_t *__restrict__ p, int64_t len, int32_t a, int32_t b, int lane) {
+    int64_t cnt = 0;
+    for (int64_t base = 0; base < len; base += 128) {
+        int32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int64_t i = base + u * 32 + lane; v[u] = i < len ? __ldg(p + i) : -1; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cnt += __popc(__ballot_sync(0xffffffffu, v[u] >= 0 && (v[u] == a || v[u] == b)));
+    }
+    return cnt;
+}
+// position of the k-th (0-based) matching entry
+__device__ __forceinline__ int64_t warp_select_match(const int32_t *__restrict__ p, int64_t len, int32_t a, int32_t b, int64_t k, int lane) {
+    int64_t seen = 0;
+    for (int64_t base = 0; base < len; base += 32) {
+        const int64_t i = base + lane;
+        const int32_t v = i < len ? __ldg(p + i) : -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, v >= 0 && (v == a || v == b));
+        const int c = __popc(bal);
+        if (seen + c > k) return base + __fns(bal, 0, (int)(k - seen) + 1);
+        seen += c;
+    }
+    return len - 1;  // unreachable when k < count
+}
+
+// ---------------------------------------------------------------------------------------------
+// find_k_walks = get_next_step (graph.py:308-333) + get_final_step (:335-476), one warp per
+// first-hop slot; lane j holds walk j of that slot.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__restrict__ root,
+                    const int32_t *__restrict__ h1_node, const int32_t *__restrict__ h1_eidx, const float *__restrict__ h1_ts,
+                    uint64_t seed, uint64_t row_offset, const uint32_t *__restrict__ inj2, const uint32_t *__restrict__ inj3,
+                    int32_t *__restrict__ o_nodes, int32_t *__restrict__ o_eidx, float *__restrict__ o_t,
+                    int32_t *__restrict__ o_anony, uint8_t *__restrict__ o_cat,
+                    unsigned long long *hist_null, unsigned long long *hist_prep, unsigned long long *scanned) {
+    __shared__ unsigned int sh_hist[12];
+    __shared__ unsigned long long sh_scan;
+    if (threadIdx.x < 12) sh_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sh_scan = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r2 = (int64_t)blockIdx.x * kWarpsPerBlock + warp;  // loop variable i of get_next_step
+    if (r2 < B * n) {
+        const int64_t W = (int64_t)n * N2;
+        const int64_t b = r2 / n;
+        const int64_t s1 = root[b], t1n = h1_node[r2];
+        const int32_t e1 = h1_eidx[r2];
+        const float t1 = h1_ts[r2];
+        auto in_range = [&](int64_t v) { return v >= 0 && v < g.n_nodes; };
+        // ---- step 2: find_before_walk([root, nbr], e_idx=e1): node 0 -> 0, missing key -> 0 (graph.py:174-176)
+        int64_t c_a = 0, c_b = 0, s_a = 0, s_b = 0;
+        {
+            int4 t = make_int4(-1, -1, -1, -1);
+            if (e1 >= 0 && (int64_t)e1 <= g.max_eidx) t = __ldg(g.etab + e1);
+            if (s1 > 0 && in_range(s1)) { s_a = __ldg(g.off + s1); c_a = s1 == t.x ? t.z : (s1 == t.y ? t.w : 0); }
+            if (t1n > 0 && in_range(t1n)) { s_b = __ldg(g.off + t1n); c_b = t1n == t.x ? t.z : (t1n == t.y ? t.w : 0); }
+        }
+        const int64_t L = c_a + c_b;
+        int64_t src2 = 0, tgt2 = 0; int32_t e2 = 0; float t2 = 0.f;
+        if (L > 0) {
+            uint64_t dr = 0;
+            if (lane < N2) dr = inj2 ? min((uint64_t)inj2[r2 * N2 + lane], (uint64_t)L - 1) : draw_index(seed, TM_STAGE_STEP2, row_offset * n + r2, lane, (uint64_t)L);
+            int rank = 0;
+            for (int j = 0; j < N2; ++j) { const uint64_t x = __shfl_sync(0xffffffffu, dr, j); rank += (x < dr) || (x == dr && j < lane); }
+            uint64_t sd = 0;
+            for (int j = 0; j < N2; ++j) {  // np.sort (graph.py:328): lane k takes the draw of rank k
+                const uint64_t x = __shfl_sync(0xffffffffu, dr, j);
+                const int rk = __shfl_sync(0xffffffffu, rank, j);
+                if (rk == lane) sd = x;
+            }
+            if (lane < N2) {
+                const bool from_a = (int64_t)sd < c_a;
+                const Entry en = load_entry(g.entry + (from_a ? s_a + (int64_t)sd : s_b + ((int64_t)sd - c_a)));
+                src2 = from_a ? s1 : t1n; tgt2 = en.nbr; e2 = en.eidx; t2 = (float)en.ts;   // graph.py:329-332
+            }
+        }
+        // ---- step 3: get_final_step, walks of this slot one after the other, warp-cooperative
+        int64_t my_src3 = 0, my_tgt3 = 0; int32_t my_e3 = 0; float my_t3 = 0.f; int my_tc = 0, my_code = 1;
+        unsigned long long scan_acc = 0;
+        for (int jj = 0; jj < N2; ++jj) {
+            const int64_t s2 = __shfl_sync(0xffffffffu, src2, jj), t2n = __shfl_sync(0xffffffffu, tgt2, jj);
+            const int32_t ee2 = __shfl_sync(0xffffffffu, e2, jj);
+            int64_t A, Bn; int32_t fa1, fa2, fb; int code;
+            if (s1 == s2 && t1n != t2n) { A = s1; Bn = t2n; fa1 = (int32_t)t1n; fa2 = (int32_t)t2n; fb = (int32_t)t1n; code = 2; }       // :355
+            else if (t1n == s2 && s1 != t2n) { A = t1n; Bn = t2n; fa1 = (int32_t)s1; fa2 = (int32_t)t2n; fb = (int32_t)s1; code = 3; }  // :395
+            else { A = t1n; Bn = t2n; fa1 = fa2 = fb = -1; code = 1; }                                                                     // :436
+            // cut = nodeedge2idx[x].get(e2) if x > 0 else 0; None -> whole list (graph.py:357-358)
+            int64_t cA = 0, cB = 0, sA = 0, sB = 0;
+            {
+                int4 t = make_int4(-1, -1, -1, -1);
+                if (ee2 >= 0 && (int64_t)ee2 <= g.max_eidx) t = __ldg(g.etab + ee2);
+                if (A > 0 && in_range(A)) { sA = __ldg(g.off + A); cA = A == t.x ? t.z : (A == t.y ? t.w : __ldg(g.off + A + 1) - sA); }
+                if (Bn > 0 && in_range(Bn)) { sB = __ldg(g.off + Bn); cB = Bn == t.x ? t.z : (Bn == t.y ? t.w : __ldg(g.off + Bn + 1) - sB); }
+            }
+            int64_t nA, nB;
+            if (code == 1) { nA = cA; nB = cB; }
+            else {
+                nA = warp_count_match(g.nbr + sA, cA, fa1, fa2, lane);
+                nB = warp_count_match(g.nbr + sB, cB, fb, fb, lane);
+                scan_acc += (unsigned long long)(cA + cB);
+            }
+            int64_t src3 = 0, tgt3 = 0; int32_t e3 = 0; float t3 = 0.f; int tc = 0;
+            if (nA + nB > 0) {
+                const int64_t w = r2 * N2 + jj;
+                int64_t k = inj3 ? (int64_t)min((uint64_t)inj3[w], (uint64_t)(nA + nB) - 1)
+                                 : (int64_t)draw_index(seed, TM_STAGE_STEP3, row_offset * W + w, 0, (uint64_t)(nA + nB));
+                int64_t p;
+                if (k < nA) { src3 = A; p = sA + (code == 1 ? k : warp_select_match(g.nbr + sA, cA, fa1, fa2, k, lane)); }
+                else { k -= nA; src3 = Bn; p = sB + (code == 1 ? k : warp_select_match(g.nbr + sB, cB, fb, fb, k, lane)); }
+                const Entry en = load_entry(g.entry + p);
+                tgt3 = en.nbr; e3 = en.eidx; t3 = (float)en.ts;
+                if (code == 2) tc = (src3 == s1 && tgt3 == t1n) ? 1 : (src3 == s1 && tgt3 == t2n) ? 2 : (src3 == t1n && tgt3 == t2n) ? 3 : 0;      // :386-393
+                else if (code == 3) tc = (src3 == t1n && tgt3 == s1) ? 1 : (src3 == t1n && tgt3 == t2n) ? 3 : (src3 == t2n && tgt3 == s1) ? 2 : 0; // :427-434
+                else tc = (src3 == s1 && tgt3 != t1n) ? 3 : (src3 == t1n && tgt3 != s1) ? 2 : (src3 == s1 && tgt3 == t1n) ? 1 : (src3 == t1n && tgt3 == s1) ? 1 : 0;  // :464-473
+            }
+            if (lane == jj) { my_src3 = src3; my_tgt3 = tgt3; my_e3 = e3; my_t3 = t3; my_tc = tc; my_code = code; }
+        }
+        if (lane < N2) {
+            const int64_t w = r2 * N2 + lane;
+            int2 *on = reinterpret_cast<int2 *>(o_nodes + w * 6);   // [src3,tgt3,src2,tgt2,src1,tgt1], graph.py:303
+            on[0] = make_int2((int32_t)my_src3, (int32_t)my_tgt3);
+            on[1] = make_int2((int32_t)src2, (int32_t)tgt2);
+            on[2] = make_int2((int32_t)s1, (int32_t)t1n);
+            o_eidx[w * 3 + 0] = my_e3; o_eidx[w * 3 + 1] = e2; o_eidx[w * 3 + 2] = e1;     // :304
+            o_t[w * 3 + 0] = my_t3; o_t[w * 3 + 1] = t2; o_t[w * 3 + 2] = t1;               // :305
+            if (o_anony) { o_anony[w * 3 + 0] = 1; o_anony[w * 3 + 1] = my_code; o_anony[w * 3 + 2] = my_tc; }
+            const int cls = class_prep(my_code, my_tc);
+            if (o_cat) o_cat[w] = (uint8_t)cls;
+            if (hist_null || hist_prep) atomicAdd(&sh_hist[cls], 1u);
+        }
+        if (scanned && lane == 0 && scan_acc) atomicAdd(&sh_scan, scan_acc);
+    }
+    __syncthreads();
+    if (threadIdx.x < 12 && sh_hist[threadIdx.x]) {
+        if (hist_prep) atomicAdd(hist_prep + threadIdx.x, (unsigned long long)sh_hist[threadIdx.x]);
+        if (hist_null) atomicAdd(hist_null + kPrepToNull[threadIdx.x], (unsigned long long)sh_hist[threadIdx.x]);
+    }
+    if (threadIdx.x == 0 && scanned && sh_scan) atomicAdd(scanned, sh_scan);
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistic (utils/null_model.py:75-82) / marginal ids (processed/data_preprocess.py:171-208)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+class_hist_kernel(int64_t count, const int32_t *__restrict__ anony, unsigned long long *hist_null,
+                  unsigned long long *hist_prep, uint8_t *__restrict__ o_cat, int32_t *err) {
+    __shared__ unsigned int sh_hist[12];
+    if (threadIdx.x < 12) sh_hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a0 = anony[3 * i], c = anony[3 * i + 1], t = anony[3 * i + 2];
+        const bool ok = a0 == 1 && c >= 1 && c <= 3 && t >= 0 && t <= 3;
+        if (!ok) { report_row_error(err, i); if (o_cat) o_cat[i] = 255; continue; }   // KeyError in the reference
+        const int cls = class_prep(c, t);
+        if (o_cat) o_cat[i] = (uint8_t)cls;
+        // warp-aggregated: one shared-memory atomic per distinct class per warp
+        const unsigned peers = __match_any_sync(__activemask(), cls);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh_hist[cls], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < 12 && sh_hist[threadIdx.x]) {
+        if (hist_prep) atomicAdd(hist_prep + threadIdx.x, (unsigned long long)sh_hist[threadIdx.x]);
+        if (hist_null) atomicAdd(hist_null + kPrepToNull[threadIdx.x], (unsigned long long)sh_hist[threadIdx.x]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// new_edge_info (processed/data_preprocess.py:327-343): one block per root, ids staged in smem
+// ---------------------------------------------------------------------------------------------
+__global__ void edge_identity_kernel(int64_t B, int W, const int32_t *__restrict__ eidx, float *__restrict__ out) {
+    extern __shared__ int32_t sh_ids[];  // [W * 3]
+    const int64_t b = blockIdx.x;
+    const int n3 = W * 3;
+    const int32_t *src = eidx + b * n3;
+    for (int i = threadIdx.x; i < n3; i += blockDim.x) sh_ids[i] = src[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n3; i += blockDim.x) {
+        const int32_t id = sh_ids[i];
+        int c0 = 0, c1 = 0, c2 = 0;
+        for (int m = 0; m < W; ++m) {  // every thread reads the same word: shared-memory broadcast
+            c0 += sh_ids[3 * m] == id; c1 += sh_ids[3 * m + 1] == id; c2 += sh_ids[3 * m + 2] == id;
+        }
+        float *o = out + (b * n3 + i) * 3;
+        o[0] = (float)c0; o[1] = (float)c1; o[2] = (float)c2;
+    }
+}
+
+}  // namespace tm
+
+using namespace tmb;
+
+extern "C" int tm_sample_hop(const tm_graph *g, int64_t R, const int32_t *d_node, const double *d_cut_time,
+                             const int32_t *d_eidx, int n, uint64_t seed, uint32_t stage, uint64_t row_offset,
+                             const uint32_t *d_inject, int32_t *d_o_node, int32_t *d_o_eidx, float *d_o_ts,
+                             int32_t *d_err, tm_stream stream) {
+    if (!g || R < 0 || n <= 0 || (R > 0 && (!d_node || !d_o_node || !d_o_eidx || !d_o_ts || (!d_cut_time && !d_eidx)))) {
+        set_error("tm_sample_hop: bad argument");
+        return TM_ERR_ARG;
+    }
+    const size_t smem = sizeof(uint32_t) * kWarpsPerBlock * (size_t)n;
+    if (smem > 48 * 1024) { set_error("tm_sample_hop: fan-out %d too large (max %d)", n, 48 * 1024 / 4 / kWarpsPerBlock); return TM_ERR_UNSUPPORTED; }
+    if (R == 0) return TM_OK;
+    TM_CUDA(cudaSetDevice(g->device));
+    const int64_t blocks = (R + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    sample_hop_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+        g->v, R, d_node, d_cut_time, d_eidx, n, seed, stage, row_offset, d_inject, d_o_node, d_o_eidx, d_o_ts, d_err);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}
+
+extern "C" int tm_sample_walks(const tm_graph *g, int64_t B, int n, int N2, const int32_t *d_root,
+                               const int32_t *d_h1_node, const int32_t *d_h1_eidx, const float *d_h1_ts,
+                               uint64_t seed, uint64_t row_offset, const uint32_t *d_inject2, const uint32_t *d_inject3,
+                               int32_t *d_o_nodes, int32_t *d_o_eidx, float *d_o_t, int32_t *d_o_anony, uint8_t *d_o_cat,
+                               unsigned long long *d_hist_null, unsigned long long *d_hist_prep,
+                               unsigned long long *d_scanned, tm_stream stream) {
+    if (!g || B < 0 || n <= 0 || N2 <= 0 || (B > 0 && (!d_root || !d_h1_node || !d_h1_eidx || !d_h1_ts || !d_o_nodes || !d_o_eidx || !d_o_t))) {
+        set_error("tm_sample_walks: bad argument");
+        return TM_ERR_ARG;
+    }
+    if (N2 > TM_MAX_STEP2_FANOUT) { set_error("tm_sample_walks: step-2 fan-out %d > %d", N2, TM_MAX_STEP2_FANOUT); return TM_ERR_UNSUPPORTED; }
+    if (B == 0) return TM_OK;
+    TM_CUDA(cudaSetDevice(g->device));
+    const int64_t rows = B * n, blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    sample_walks_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        g->v, B, n, N2, d_root, d_h1_node, d_h1_eidx, d_h1_ts, seed, row_offset, d_inject2, d_inject3,
+        d_o_nodes, d_o_eidx, d_o_t, d_o_anony, d_o_cat, d_hist_null, d_hist_prep, d_scanned);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}
+
+extern "C" int tm_class_hist(int64_t count, const int32_t *d_anony, unsigned long long *d_hist_null,
+                             unsigned long long *d_hist_prep, uint8_t *d_o_cat, int32_t *d_err, tm_stream stream) {
+    if (count < 0 || (count > 0 && !d_anony)) { set_error("tm_class_hist: bad argument"); return TM_ERR_ARG; }
+    if (count == 0) return TM_OK;
+    const int64_t blocks = std::min<int64_t>((count + 255) / 256, 148 * 8);
+    class_hist_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(count, d_anony, d_hist_null, d_hist_prep, d_o_cat, d_err);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}
+
+extern "C" int tm_edge_identity(int64_t B, int64_t W, const int32_t *d_eidx, float *d_out, tm_stream stream) {
+    if (B < 0 || W <= 0 || (B > 0 && (!d_eidx || !d_out))) { set_error("tm_edge_identity: bad argument"); return TM_ERR_ARG; }
+    const size_t smem = sizeof(int32_t) * 3 * (size_t)W;
+    if (smem > 48 * 1024) { set_error("tm_edge_identity: %lld walks per root exceed the shared-memory window", (long long)W); return TM_ERR_UNSUPPORTED; }
+    if (B == 0) return TM_OK;
+    const int threads = (int)std::min<int64_t>(1024, ((3 * W + 31) / 32) * 32);
+    edge_identity_kernel<<<(unsigned)B, threads, smem, (cudaStream_t)stream>>>(B, (int)W, d_eidx, d_out);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}

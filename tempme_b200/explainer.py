@@ -1,0 +1,194 @@
+"""``TempME`` with the reference's constructor, parameter names and ``forward`` contract
+(reference models/explainer.py:99-201), scoring motifs with the fused sm_100a kernel of
+libtempme_b200 (``tm_encode_score``).
+
+The sub-module / parameter names equal the reference's so a reference
+``state_dict`` loads with ``load_state_dict`` and ours loads into the reference class.  The fused
+kernel implements eval-mode ``forward``; training (autograd, dropout) is outside the hot path and
+is not built (DESIGN.md "out of scope").
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ._lib import EncoderDesc, EncoderParams, check, lib, ptr
+
+
+class TimeEncode(nn.Module):
+    """Parameters of the reference TimeEncode (explainer.py:45-50): basis_freq = 1/10^linspace(0,9,D), phase = 0."""
+
+    def __init__(self, expand_dim):
+        super().__init__()
+        self.time_dim = expand_dim
+        self.basis_freq = nn.Parameter(torch.from_numpy(1 / 10 ** np.linspace(0, 9, expand_dim)).float())
+        self.phase = nn.Parameter(torch.zeros(expand_dim).float())
+
+
+class _EventGCN(nn.Module):  # parameter container for event_gcn (explainer.py:79-84)
+    def __init__(self, event_dim, node_dim, hid_dim):
+        super().__init__()
+        self.lin_event = nn.Linear(event_dim, node_dim)
+        self.relu = nn.ReLU()
+        self.MLP = nn.Sequential(nn.Linear(node_dim, hid_dim), nn.ReLU(), nn.Linear(hid_dim, hid_dim))
+
+
+class _Attention(nn.Module):  # Attention (explainer.py:12-23)
+    def __init__(self, input_dim, hid_dim):
+        super().__init__()
+        self.hidden_size = hid_dim
+        self.W1 = nn.Linear(input_dim, input_dim)
+        self.W2 = nn.Linear(input_dim, input_dim)
+        self.MLP = nn.Sequential(nn.Linear(input_dim, hid_dim), nn.ReLU(), nn.Linear(hid_dim, hid_dim))
+        nn.init.xavier_uniform_(self.W2.weight.data)
+        self.W2.bias.data.fill_(0.1)
+
+
+class _TemporalAwareAttention(nn.Module):  # TemporalAwareAttention (explainer.py:768-787)
+    def __init__(self, input_dim, hid_dim, dropout_p=0.1):
+        super().__init__()
+        self.hidden_size = hid_dim
+        self.W1 = nn.Linear(input_dim, input_dim)
+        self.W2 = nn.Linear(input_dim, input_dim)
+        self.W_time = nn.Linear(1, input_dim)
+        self.dropout = nn.Dropout(dropout_p)
+        self.MLP = nn.Sequential(nn.Linear(input_dim, hid_dim), nn.ReLU(), nn.Dropout(dropout_p), nn.Linear(hid_dim, hid_dim))
+        nn.init.xavier_uniform_(self.W2.weight.data)
+        self.W2.bias.data.fill_(0.1)
+        nn.init.xavier_uniform_(self.W_time.weight.data)
+
+
+class _MergeLayer(nn.Module):  # _MergeLayer (explainer.py:62-69)
+    def __init__(self, input_dim, hid_dim):
+        super().__init__()
+        self.fc1 = nn.Linear(2 * input_dim, hid_dim)
+        self.fc2 = nn.Linear(hid_dim, 1)
+        nn.init.xavier_normal_(self.fc1.weight)
+        nn.init.xavier_normal_(self.fc2.weight)
+        self.act = nn.ReLU()
+
+
+class TempME(nn.Module):
+    def __init__(self, base, base_model_type, data, out_dim, hid_dim, prior="empirical", temp=0.07,
+                 if_cat_feature=True, dropout_p=0.1, device=None, use_temporal_guidance=True,
+                 use_dependency_aware_sampling=True, null_model=None, batch_group=None):
+        super().__init__()
+        self.node_dim = base.n_feat_th.shape[1]
+        self.edge_dim = base.e_feat_th.shape[1]
+        self.time_dim = self.node_dim
+        self.out_dim = out_dim
+        self.hid_dim = hid_dim
+        self.base_type = base_model_type
+        self.dropout_p = dropout_p
+        self.temp = temp
+        self.prior = prior
+        self.if_cat = if_cat_feature
+        self.dropout = nn.Dropout(dropout_p)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.event_dim = self.edge_dim + self.time_dim + 3
+        self.event_conv = _EventGCN(self.event_dim, self.node_dim, self.hid_dim)
+        self.use_temporal_guidance = use_temporal_guidance
+        self.attention = (_TemporalAwareAttention if use_temporal_guidance else _Attention)(2 * self.hid_dim, self.hid_dim)
+        self.mlp_dim = self.hid_dim + 12 if self.if_cat else self.hid_dim
+        self.MLP = nn.Sequential(nn.Linear(self.mlp_dim, self.mlp_dim), nn.ReLU(), nn.Dropout(self.dropout_p),
+                                 nn.Linear(self.mlp_dim, self.hid_dim), nn.ReLU(), nn.Linear(self.hid_dim, 1))
+        self.final_linear = nn.Linear(2 * self.hid_dim, self.hid_dim)
+        self.node_emd_dim = self.hid_dim + 12 + self.node_dim if self.if_cat else self.hid_dim + self.node_dim
+        self.affinity_score = _MergeLayer(self.node_emd_dim, self.node_emd_dim)
+        self.edge_raw_embed = base.edge_raw_features
+        self.node_raw_embed = base.node_raw_features
+        self.time_encoder = TimeEncode(expand_dim=self.time_dim)
+        if null_model is None:
+            from .null_model import get_null_distribution
+            null_model = get_null_distribution(data_name=data)
+        self.null_model = null_model
+        num_nodes = base.n_feat_th.shape[0]
+        self.node_degree = torch.ones(num_nodes, device=self.device)
+        self.use_dependency_aware_sampling = use_dependency_aware_sampling
+        if use_dependency_aware_sampling:  # parameters of the edge-level modules (explainer.py:141-171), unused by forward
+            self.edge_dependency_gcn = nn.Sequential(
+                nn.Linear(self.edge_dim + self.time_dim, self.hid_dim), nn.ReLU(), nn.Dropout(dropout_p * 1.5),
+                nn.Linear(self.hid_dim, self.hid_dim // 2), nn.ReLU(), nn.Dropout(dropout_p), nn.Linear(self.hid_dim // 2, 1))
+            self.edge_importance_attention = nn.MultiheadAttention(embed_dim=self.hid_dim, num_heads=4, dropout=dropout_p, batch_first=True)
+            self.edge_to_node_transform = nn.Sequential(nn.Linear(self.edge_dim, self.hid_dim), nn.ReLU(), nn.Linear(self.hid_dim, self.hid_dim))
+            self.gumbel_temperature = 1.0
+            self.min_gumbel_temperature = 0.5
+            self.gumbel_anneal_rate = 0.003
+        # ---- device-side state of the fused scorer
+        self.batch_group = batch_group          # roots per reference batch; None = the whole call is one batch
+        self._desc = EncoderDesc(self.node_dim, self.edge_dim, self.hid_dim, int(bool(use_temporal_guidance)), int(bool(self.if_cat)))
+        self._blob = None
+        self._blob_key = None
+        self._ws = None
+
+    # ------------------------------------------------------------------ weights -> packed device blob
+    def _forward_params(self):
+        a3 = self.attention.MLP[3] if self.use_temporal_guidance else self.attention.MLP[2]
+        return [self.event_conv.lin_event.weight, self.event_conv.lin_event.bias,
+                self.event_conv.MLP[0].weight, self.event_conv.MLP[0].bias, self.event_conv.MLP[2].weight, self.event_conv.MLP[2].bias,
+                self.attention.W1.weight, self.attention.W1.bias, self.attention.W2.weight, self.attention.W2.bias,
+                self.attention.MLP[0].weight, self.attention.MLP[0].bias, a3.weight, a3.bias,
+                self.MLP[0].weight, self.MLP[0].bias, self.MLP[3].weight, self.MLP[3].bias, self.MLP[5].weight, self.MLP[5].bias,
+                self.time_encoder.basis_freq, self.time_encoder.phase]
+
+    def packed_weights(self):
+        ps = self._forward_params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._blob is None or key != self._blob_key:
+            host = [p.detach().to("cpu", torch.float32).contiguous() for p in ps]
+            prm = EncoderParams(*[C.c_void_p(h.data_ptr()) for h in host])
+            n = lib().tm_encoder_blob_floats(C.byref(self._desc))
+            blob = torch.empty(n, dtype=torch.float32)
+            check(lib().tm_encoder_pack(C.byref(self._desc), C.byref(prm), ptr(blob)), "tm_encoder_pack")
+            self._blob = blob.to(self.device)
+            self._blob_key = key
+        return self._blob
+
+    def _tables(self):
+        nf = self.node_raw_embed.weight if hasattr(self.node_raw_embed, "weight") else self.node_raw_embed
+        ef = self.edge_raw_embed.weight if hasattr(self.edge_raw_embed, "weight") else self.edge_raw_embed
+        if nf.device != self.device or nf.dtype != torch.float32 or not nf.is_contiguous():
+            nf = nf.detach().to(self.device, torch.float32).contiguous()
+        if ef.device != self.device or ef.dtype != torch.float32 or not ef.is_contiguous():
+            ef = ef.detach().to(self.device, torch.float32).contiguous()
+        return nf, ef
+
+    def _t(self, a, dtype):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ forward (explainer.py:174-201)
+    def score_device(self, nodes, eidx, t, cat, cut_time, edge_identity, group=None):
+        """All arguments CUDA tensors: nodes i32 [B,W,6], eidx i32 [B,W,3], t f32 [B,W,3], cat u8 [B,W],
+        cut_time f32 [B], edge_identity f32 [B,W,3,3] -> scores f32 [B,W]."""
+        B, W = nodes.shape[0], nodes.shape[1]
+        group = int(group or self.batch_group or max(B, 1))
+        blob = self.packed_weights()
+        nf, ef = self._tables()
+        nws = lib().tm_encoder_workspace_floats(C.byref(self._desc), B, W, group)
+        if self._ws is None or self._ws.numel() < nws:
+            self._ws = torch.empty(max(nws, 1024), dtype=torch.float32, device=self.device)
+        scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(lib().tm_encode_score(C.byref(self._desc), ptr(blob), B, W, group, ptr(nodes), ptr(eidx), ptr(t), ptr(cat),
+                                    ptr(cut_time), ptr(edge_identity), ptr(nf), nf.shape[0], ptr(ef), ef.shape[0],
+                                    ptr(self._ws), ptr(scores), self.device.index, st), "tm_encode_score")
+        return scores
+
+    def forward(self, walks, cut_time_l, edge_identify):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("tempme_b200.TempME.forward is the eval-mode scorer; call .eval() / torch.no_grad() "
+                                      "(training the explainer is outside the B200 hot path)")
+        node_idx, edge_idx, time_idx, cat_feat, _ = walks
+        nodes = self._t(node_idx, torch.int32)
+        eidx = self._t(edge_idx, torch.int32)
+        t = self._t(time_idx, torch.float32)                              # .float(), explainer.py:325
+        B, W = nodes.shape[0], nodes.shape[1]
+        cat = self._t(cat_feat, torch.uint8).view(B, W) if self.if_cat else None
+        cut = self._t(cut_time_l, torch.float32)                          # .float(), explainer.py:816
+        eid = self._t(edge_identify, torch.float32)                       # .float(), explainer.py:177
+        return self.score_device(nodes, eidx, t, cat, cut, eid).view(B, W, 1)

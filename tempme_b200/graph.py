@@ -1,0 +1,313 @@
+"""``NeighborFinder`` with the reference's Python surface (reference utils/graph.py:12-476) on top of
+the device-resident CSR of libtempme_b200.
+
+Host API (numpy in, numpy out, reference dtypes/shapes): ``find_before``, ``get_temporal_neighbor``,
+``find_k_hop``, ``find_k_walks``, ``get_next_step``/``get_final_step`` are not re-exposed separately
+(the walk sampler is one fused kernel); see DESIGN.md.  Device API (torch CUDA tensors in/out, no
+host round trip): ``sample_hop_device``, ``find_k_hop_device``, ``find_k_walks_device``.
+
+Randomness: the reference draws from numpy's global MT19937 stream.  Here every top-level sampling
+call number ``c`` uses the counter-based Philox stream keyed by ``seed + c`` (DESIGN.md "RNG"), so
+results do not depend on how queries are split across GPUs; ``inject=`` replays recorded indices.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TM_EIDX_NONE, check, lib, ptr
+
+PRECISION = 5
+
+
+def _flatten_adj_list(adj_list):
+    """adj_list: List[List[(nbr, eidx, ts)]] -> entry arrays in insertion order."""
+    lens = np.fromiter((len(a) for a in adj_list), dtype=np.int64, count=len(adj_list))
+    total = int(lens.sum())
+    node = np.repeat(np.arange(len(adj_list), dtype=np.int32), lens)
+    nbr = np.empty(total, np.int32); eidx = np.empty(total, np.int32); ts = np.empty(total, np.float64)
+    p = 0
+    for a in adj_list:
+        if a:
+            arr = np.asarray(a, dtype=np.float64)          # ids are exact in float64 up to 2^53
+            k = len(a)
+            nbr[p:p + k] = arr[:, 0]; eidx[p:p + k] = arr[:, 1]; ts[p:p + k] = arr[:, 2]
+            p += k
+    return node, nbr, eidx, ts
+
+
+class NeighborFinder:
+    def __init__(self, adj_list, bias=0, ts_precision=PRECISION, use_cache=False, sample_method='multinomial',
+                 device=None, seed=None, _entries=None):
+        if not math.isclose(bias, 0) or sample_method != 'multinomial':
+            # the reference's callers never leave the defaults; those branches are not built
+            raise NotImplementedError("tempme_b200.NeighborFinder supports bias=0, sample_method='multinomial' only")
+        if not torch.cuda.is_available():
+            raise RuntimeError("tempme_b200.NeighborFinder needs a CUDA device (no CPU fallback)")
+        self.bias = bias
+        self.ts_precision = ts_precision
+        self.use_cache = use_cache
+        self.cache = {}
+        self.sample_method = sample_method
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        n_nodes, (node, nbr, eidx, ts) = (len(adj_list), _flatten_adj_list(adj_list)) if _entries is None else _entries
+        h = C.c_void_p()
+        check(lib().tm_graph_create(n_nodes, len(node), ptr(node), ptr(nbr), ptr(eidx), ptr(ts), dev.index, C.byref(h)),
+              "tm_graph_create")
+        self._h = h
+        self.n_nodes = n_nodes
+        self.n_entries = len(node)
+        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self.calls = 0
+        self._host = None
+        self._dict = None
+        self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_events(cls, n_nodes, src, dst, eidx, ts, device=None, seed=None):
+        """Graph of an event list; equals NeighborFinder(adj_list) for the adj_list the reference's
+        callers build (each event appended to both endpoints, temp_exp_main.py:135-144)."""
+        src = np.asarray(src); dst = np.asarray(dst)
+        m = len(src)
+        node = np.empty(2 * m, np.int32); nbr = np.empty(2 * m, np.int32)
+        node[0::2] = src; node[1::2] = dst; nbr[0::2] = dst; nbr[1::2] = src
+        e = np.repeat(np.asarray(eidx).astype(np.int32), 2)
+        t = np.repeat(np.asarray(ts).astype(np.float64), 2)
+        return cls(None, device=device, seed=seed, _entries=(int(n_nodes), (node, nbr, e, t)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and _lib._lib is not None:
+            _lib._lib.tm_graph_destroy(h)
+            self._h = None
+
+    def device_bytes(self):
+        v = [C.c_int64() for _ in range(4)]
+        check(lib().tm_graph_sizes(self._h, *[C.byref(x) for x in v]), "tm_graph_sizes")
+        return v[3].value
+
+    # ------------------------------------------------------------------ reference attribute surface
+    def _export(self):
+        if self._host is None:
+            off = np.zeros(self.n_nodes + 1, np.int64)
+            nbr = np.zeros(self.n_entries, np.int32); e = np.zeros(self.n_entries, np.int32)
+            ts = np.zeros(self.n_entries, np.float64)
+            check(lib().tm_graph_export(self._h, ptr(off), ptr(nbr), ptr(e), ptr(ts)), "tm_graph_export")
+            self._host = (off, nbr.astype(np.int64), e.astype(np.int64), ts)
+        return self._host
+
+    @property
+    def off_set_l(self):
+        return self._export()[0]
+
+    @property
+    def node_idx_l(self):
+        return self._export()[1]
+
+    @property
+    def edge_idx_l(self):
+        return self._export()[2]
+
+    @property
+    def node_ts_l(self):
+        return self._export()[3]
+
+    @property
+    def binary_prob_l(self):
+        # compute_binary_prob with bias == 0 (graph.py:68-75): exp(0)/cumsum(1) = 1/(position+1)
+        off = self.off_set_l
+        pos = np.arange(self.n_entries) - np.repeat(off[:-1], np.diff(off))
+        return 1.0 / (pos + 1.0)
+
+    def edge_table(self):
+        v = [C.c_int64() for _ in range(4)]
+        check(lib().tm_graph_sizes(self._h, *[C.byref(x) for x in v]), "tm_graph_sizes")
+        tab = np.full((v[2].value + 1, 4), -1, np.int32)
+        check(lib().tm_graph_export_edge_table(self._h, ptr(tab)), "tm_graph_export_edge_table")
+        return tab
+
+    @property
+    def nodeedge2idx(self):
+        """{node: {e_idx: cut}} rebuilt from the device edge table (graph.py:56,77-101).  Values are the
+        effective prefix lengths, i.e. already passed through python's ``[:cut]`` slice semantics."""
+        if self._dict is None:
+            d = {v: {} for v in range(self.n_nodes)}
+            tab = self.edge_table()
+            for e in np.nonzero(tab[:, 0] >= 0)[0]:
+                a, b, ca, cb = tab[e]
+                d[int(a)][int(e)] = int(ca)
+                if b >= 0:
+                    d[int(b)][int(e)] = int(cb)
+            self._dict = d
+        return self._dict
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, a, dtype):
+        if a is None:
+            return None
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(np.asarray(a)), device="cpu").to(dtype).to(self.device, non_blocking=True)
+
+    def _next_seed(self, seed):
+        if seed is not None:
+            return int(seed) & (2 ** 64 - 1)
+        s = (self.seed + self.calls) & (2 ** 64 - 1)
+        self.calls += 1
+        return s
+
+    def _raise_if_err(self, what):
+        row = int(self._err.item())
+        if row:
+            self._err.zero_()
+            raise IndexError(f"{what}: e_idx not found in edge list (or node id out of range) at row {row - 1}")
+
+    # ------------------------------------------------------------------ find_before (graph.py:103-146)
+    def find_before_batch_device(self, node, cut_time=None, e_idx=None):
+        node = self._dev(node, torch.int32)
+        R = node.numel()
+        ct = self._dev(cut_time, torch.float64)
+        e = self._dev(e_idx, torch.int32)
+        start = torch.empty(R, dtype=torch.int64, device=self.device)
+        cut = torch.empty(R, dtype=torch.int32, device=self.device)
+        check(lib().tm_find_before_batch(self._h, R, ptr(node), ptr(ct), ptr(e), ptr(start), ptr(cut), ptr(self._err),
+                                         self._stream()), "tm_find_before_batch")
+        return start, cut
+
+    def find_before(self, src_idx, cut_time, e_idx=None, return_binary_prob=False):
+        """Returns views into the exported CSR arrays, like the reference."""
+        start, cut = self.find_before_batch_device([int(src_idx)], [float(cut_time)] if e_idx is None else None,
+                                                   None if e_idx is None else [int(e_idx)])
+        s, c = int(start.item()), int(cut.item())
+        row = int(self._err.item())
+        if row:
+            self._err.zero_()
+            raise IndexError('e_idx {} not found in edge list of {}'.format(e_idx, src_idx))
+        off, nbr, e, ts = self._export()
+        prob = self.binary_prob_l[s:s + c] if return_binary_prob else None
+        return nbr[s:s + c], e[s:s + c], ts[s:s + c], prob
+
+    # ------------------------------------------------------------------ get_temporal_neighbor (graph.py:197-231)
+    def sample_hop_device(self, node, cut_time, num_neighbor, e_idx=None, seed=0, stage=0, row_offset=0, inject=None):
+        node = self._dev(node, torch.int32)
+        R = node.numel()
+        ct = self._dev(cut_time, torch.float64) if cut_time is not None else None
+        e = self._dev(e_idx, torch.int32)
+        inj = self._dev(inject, torch.int64).to(torch.int32) if inject is not None else None
+        o_node = torch.empty((R, num_neighbor), dtype=torch.int32, device=self.device)
+        o_eidx = torch.empty_like(o_node)
+        o_ts = torch.empty((R, num_neighbor), dtype=torch.float32, device=self.device)
+        check(lib().tm_sample_hop(self._h, R, ptr(node), ptr(ct), ptr(e), int(num_neighbor), seed, stage, row_offset,
+                                  ptr(inj), ptr(o_node), ptr(o_eidx), ptr(o_ts), ptr(self._err), self._stream()),
+              "tm_sample_hop")
+        return o_node, o_eidx, o_ts
+
+    def get_temporal_neighbor(self, src_idx_l, cut_time_l, num_neighbor, e_idx_l=None, seed=None, row_offset=0, inject=None):
+        assert (len(src_idx_l) == len(cut_time_l))
+        s = self._next_seed(seed)
+        ct = None if e_idx_l is not None else cut_time_l
+        o = self.sample_hop_device(src_idx_l, ct, num_neighbor, e_idx_l, s, 0, row_offset, inject)
+        out = tuple(x.cpu().numpy() for x in o)
+        self._raise_if_err("get_temporal_neighbor")
+        return out
+
+    # ------------------------------------------------------------------ find_k_hop (graph.py:233-262)
+    def find_k_hop_device(self, k, src_idx_l, cut_time_l, num_neighbors, e_idx_l=None, seed=None, row_offset=0, inject=None):
+        """inject: optional list (one per hop) of recorded index arrays."""
+        if k == 0:
+            return ([], [], [])
+        s = self._next_seed(seed)
+        n = int(num_neighbors)
+        B = len(src_idx_l)
+        ct = None if e_idx_l is not None else cut_time_l
+        x, y, z = self.sample_hop_device(src_idx_l, ct, n, e_idx_l, s, 0, row_offset, inject[0] if inject else None)
+        recs = ([x], [y], [z])
+        for layer in range(1, k):
+            pn, pe = recs[0][-1].reshape(-1), recs[1][-1].reshape(-1)
+            # deeper hops look the window up by e_idx; the (float32) time is unused (graph.py:247-250)
+            x, y, z = self.sample_hop_device(pn, None, n, pe, s, layer, row_offset * (n ** layer),
+                                             inject[layer] if inject else None)
+            for r, v in zip(recs, (x, y, z)):
+                r.append(v.view(B, -1))
+        return recs
+
+    def find_k_hop(self, k, src_idx_l, cut_time_l, num_neighbors, e_idx_l=None, seed=None, row_offset=0, inject=None):
+        recs = self.find_k_hop_device(k, src_idx_l, cut_time_l, num_neighbors, e_idx_l, seed, row_offset, inject)
+        out = tuple([t.cpu().numpy() for t in r] for r in recs)
+        self._raise_if_err("find_k_hop")
+        return out
+
+    # ------------------------------------------------------------------ find_k_walks (graph.py:265-476)
+    def find_k_walks_device(self, degree, src_idx_l, num_neighbors, subgraph_src, seed=None, row_offset=0,
+                            inject2=None, inject3=None, want_anony=True, want_cat=True, hist_null=None, hist_prep=None,
+                            scanned=None):
+        s = self._next_seed(seed)
+        root = self._dev(src_idx_l, torch.int32)
+        B = root.numel()
+        n, N2 = int(degree), int(num_neighbors)
+        h1n = self._dev(subgraph_src[0][0], torch.int32); h1e = self._dev(subgraph_src[1][0], torch.int32)
+        h1t = self._dev(subgraph_src[2][0], torch.float32)
+        assert h1n.shape == (B, n)
+        W = n * N2
+        dev = self.device
+        nodes = torch.empty((B, W, 6), dtype=torch.int32, device=dev)
+        eidx = torch.empty((B, W, 3), dtype=torch.int32, device=dev)
+        t = torch.empty((B, W, 3), dtype=torch.float32, device=dev)
+        anony = torch.empty((B, W, 3), dtype=torch.int32, device=dev) if want_anony else None
+        cat = torch.empty((B, W), dtype=torch.uint8, device=dev) if want_cat else None
+        i2 = self._dev(inject2, torch.int64).to(torch.int32) if inject2 is not None else None
+        i3 = self._dev(inject3, torch.int64).to(torch.int32) if inject3 is not None else None
+        check(lib().tm_sample_walks(self._h, B, n, N2, ptr(root), ptr(h1n), ptr(h1e), ptr(h1t), s, row_offset,
+                                    ptr(i2), ptr(i3), ptr(nodes), ptr(eidx), ptr(t), ptr(anony), ptr(cat),
+                                    ptr(hist_null), ptr(hist_prep), ptr(scanned), self._stream()), "tm_sample_walks")
+        return nodes, eidx, t, anony, cat
+
+    def find_k_walks(self, degree, src_idx_l, num_neighbors, subgraph_src, seed=None, row_offset=0, inject2=None, inject3=None):
+        nodes, eidx, t, anony, _ = self.find_k_walks_device(degree, src_idx_l, num_neighbors, subgraph_src, seed, row_offset,
+                                                            inject2, inject3, want_cat=False)
+        node_dtype = np.result_type(np.asarray(src_idx_l).dtype, np.int32)   # np.stack of the int64 roots with int32 hops, graph.py:303
+        return (nodes.cpu().numpy().astype(node_dtype), eidx.cpu().numpy(), t.cpu().numpy(), anony.cpu().numpy())
+
+
+# ---------------------------------------------------------------------- class ids / histograms / edge identity
+def class_hist_device(anony, want_cat=True):
+    """statistic (utils/null_model.py:75-82) + marginal ids (processed/data_preprocess.py:171-208) on device."""
+    a = anony.contiguous().view(-1, 3)
+    dev = a.device
+    hn = torch.zeros(12, dtype=torch.int64, device=dev); hp = torch.zeros(12, dtype=torch.int64, device=dev)
+    cat = torch.empty(a.shape[0], dtype=torch.uint8, device=dev) if want_cat else None
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        check(lib().tm_class_hist(a.shape[0], ptr(a), ptr(hn), ptr(hp), ptr(cat), ptr(err), st), "tm_class_hist")
+    return hn, hp, (cat.view(anony.shape[:-1]) if want_cat else None), err
+
+
+def edge_identity_device(eidx):
+    """new_edge_info (processed/data_preprocess.py:327-343): [B, W, 3] int32 -> [B, W, 3, 3] float32."""
+    e = eidx.contiguous()
+    B, W, _ = e.shape
+    out = torch.empty((B, W, 3, 3), dtype=torch.float32, device=e.device)
+    st = C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream)
+    with torch.cuda.device(e.device):
+        check(lib().tm_edge_identity(B, W, ptr(e), ptr(out), st), "tm_edge_identity")
+    return out
+
+
+def new_edge_info(edge_ids):
+    """Host-array front end with the reference's signature/dtype (float64 [bsz, n_walks, 3, 3])."""
+    e = torch.as_tensor(np.ascontiguousarray(edge_ids)).to(torch.int32).cuda()
+    return edge_identity_device(e).cpu().numpy().astype(np.float64)

@@ -1,0 +1,79 @@
+"""Device-resident motif pipeline: the whole hot path for a batch of query events without leaving
+the GPU -- first-hop lookup/sampling, 3-event walks + anonymisation class + histogram, edge-identity
+counts and the fused TempME scorer.  This is what bench.py times; the pieces are the same C-ABI calls
+the reference-facing classes (NeighborFinder, TempME) make.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import TM_EIDX_NONE
+from .graph import edge_identity_device
+
+
+class MotifPipeline:
+    """roots = (src, tgt, bgd) of every query event, as processed/data_preprocess.py:106-134 does per event;
+    ``group`` = events per reference batch (temp_exp_main.py --bs, default 100): the explainer is called
+    once per root type per batch, so the attention's batch-global std runs over [group, W, 2]."""
+
+    def __init__(self, finder, explainer, n, N2, group=100, seed=0):
+        self.finder, self.explainer = finder, explainer
+        self.n, self.N2, self.W, self.group = int(n), int(N2), int(n) * int(N2), int(group)
+        self.seed = int(seed)
+        self.device = finder.device
+        self.hist_null = torch.zeros(12, dtype=torch.int64, device=self.device)
+        self.hist_prep = torch.zeros(12, dtype=torch.int64, device=self.device)
+        self.scanned = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    def _layout(self, Q):
+        g = self.group if Q >= self.group else Q
+        if g == 0 or Q % g:
+            raise ValueError(f"{Q} query events are not a whole number of reference batches of {self.group}")
+        return Q // g, g
+
+    def stage_queries(self, src, dst, fake, ts, eidx):
+        """Host arrays -> device tensors of 3Q rows laid out batch-major, [n_batches, 3 (src|tgt|bgd), group]:
+        the global row index of a root therefore does not depend on how whole batches are split over GPUs."""
+        dev = self.device
+        Q = len(src)
+        nb, g = self._layout(Q)
+        def lay(a, b, c, dt):
+            x = np.stack([np.asarray(a).reshape(nb, g), np.asarray(b).reshape(nb, g), np.asarray(c).reshape(nb, g)], axis=1)
+            return torch.as_tensor(np.ascontiguousarray(x.astype(dt))).to(dev, non_blocking=True).view(-1)
+        roots = lay(src, dst, fake, np.int32)
+        e = lay(eidx, eidx, np.full(Q, TM_EIDX_NONE, np.int64), np.int32)           # bgd roots are cut by time
+        cut64 = lay(ts, ts, ts, np.float64)
+        return roots, e, cut64
+
+    def run_device(self, roots, e, cut64, row_offset=0, want_walks=False, timers=None):
+        """roots/e/cut64: [3Q] device tensors in the stage_queries layout; row_offset = global index of the first
+        root row (3 * events before this shard).  Returns scores [3Q, W] in the same row order."""
+        f, n, N2, W = self.finder, self.n, self.N2, self.W
+        R = roots.numel()
+        g = self.group if R >= 3 * self.group else R // 3
+        def mark(name):
+            if timers is not None:
+                ev = torch.cuda.Event(enable_timing=True); ev.record(); timers.append((name, ev))
+        mark("start")
+        h1 = f.sample_hop_device(roots, cut64, n, e, seed=self.seed, stage=0, row_offset=row_offset)
+        mark("sample_hop")
+        nodes, eidx, t, _, cat = f.find_k_walks_device(n, roots, N2, ([h1[0]], [h1[1]], [h1[2]]), seed=self.seed + 1,
+                                                       row_offset=row_offset, want_anony=False, want_cat=True,
+                                                       hist_null=self.hist_null, hist_prep=self.hist_prep, scanned=self.scanned)
+        mark("sample_walks")
+        eid = edge_identity_device(eidx)
+        mark("edge_identity")
+        scores = self.explainer.score_device(nodes, eidx, t, cat, cut64.to(torch.float32), eid, group=max(g, 1))
+        mark("encode")
+        return (scores, (nodes, eidx, t, cat, eid)) if want_walks else scores
+
+    def unstage_scores(self, scores, Q):
+        """[3Q, W] in batch-major row order -> [3, Q, W] (src | tgt | bgd)."""
+        nb, g = self._layout(Q)
+        return scores.view(nb, 3, g, self.W).permute(1, 0, 2, 3).reshape(3, Q, self.W)
+
+    def run_host(self, src, dst, fake, ts, eidx, row_offset=0):
+        """End-to-end call with host buffers: H2D of the queries, the device pipeline, D2H of the scores."""
+        roots, e, cut64 = self.stage_queries(src, dst, fake, ts, eidx)
+        return self.unstage_scores(self.run_device(roots, e, cut64, row_offset), len(src)).cpu().numpy()

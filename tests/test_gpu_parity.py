@@ -1,0 +1,322 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI via
+tempme_b200's reference-facing classes, against (a) the committed golden vectors produced by the
+unmodified reference and (b) the CPU oracle on seeded inputs.  Integer / index outputs and copied
+float32 timestamps are compared bit-exactly; fp32 scores within rtol 1e-5 (the north_star tolerance).
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROOTS = ("src", "tgt", "bgd")
+
+
+@pytest.fixture(scope="module")
+def tm():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import tempme_b200
+    return tempme_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import oracle
+    return oracle
+
+
+def finder_of(tm, g, upto=None, seed=0):
+    s = slice(None, upto)
+    return tm.NeighborFinder.from_events(int(g["n_nodes"]), g["src"][s].astype(np.int64), g["dst"][s].astype(np.int64),
+                                         g["eidx"][s], g["ts"][s].astype(np.float64), seed=seed)
+
+
+def assert_sub(g, prefix, sub):
+    for name, rec in zip(("node", "eidx", "ts"), sub):
+        for l, a in enumerate(rec):
+            ref = g[f"{prefix}_hop{l}_{name}"]
+            assert a.shape == ref.shape and a.dtype == (np.float32 if name == "ts" else np.int32)
+            assert (a == ref).all(), f"{prefix} hop{l} {name}"
+
+
+def assert_walks(g, prefix, walks):
+    for name, a in zip(("nodes", "eidx", "t", "anony"), walks):
+        ref = g[f"{prefix}_w_{name}"]
+        assert a.shape == ref.shape, (a.shape, ref.shape)
+        assert (a == ref).all(), f"{prefix} walks {name}"
+
+
+# ------------------------------------------------------------------------------------------ graph
+def test_tie_star_csr_and_cuts(tm, golden):
+    g = golden("tie_star")
+    f = finder_of(tm, g)
+    assert (f.off_set_l == g["off"]).all() and (f.node_idx_l == g["nbr"]).all()
+    assert (f.edge_idx_l == g["e"]).all() and (f.node_ts_l == g["t"]).all()
+    d = f.nodeedge2idx
+    for v, e, val in g["dict"]:
+        assert d[int(v)][int(e)] == val
+    assert [d[1][k] for k in range(1, 7)] == [0, 1, 1, 1, 4, 5]
+    for v, e, n in g["fb_eidx"]:
+        assert len(f.find_before(int(v), 3.0, e_idx=int(e))[0]) == n
+    for v, t, n in g["fb_time"]:
+        nb, ee, ts, _ = f.find_before(int(v), float(t))
+        assert len(nb) == int(n) and (ts < t).all()
+    with pytest.raises(IndexError):
+        f.find_before(1, 3.0, e_idx=99)
+    assert len(f.find_before(0, 3.0, e_idx=1)[0]) == 0                 # node 0 -> cut 0 (graph.py:133)
+
+
+@pytest.mark.parametrize("name", ["rand_small", "rand_bigts", "uslegis"])
+def test_golden_csr_hops_walks(tm, orc, golden, name):
+    g = golden(name)
+    f = finder_of(tm, g)
+    if "off" in g:
+        assert (f.off_set_l == g["off"]).all() and (f.node_idx_l == g["nbr"]).all()
+        assert (f.edge_idx_l == g["e"]).all() and (f.node_ts_l == g["t"]).all()
+        d = f.nodeedge2idx
+        for v, e, val in g["dict"]:
+            L = g["off"][v + 1] - g["off"][v]
+            eff = max(0, L + val) if val < 0 else min(val, L)
+            assert d[int(v)][int(e)] == eff
+    q, n, N2, seed = g["q"], int(g["n"]), int(g["N2"]), int(g["base_seed"])
+    ts = g["ts"].astype(np.float64)
+    call = 0
+    for r in ROOTS:
+        roots = {"src": g["src"][q], "tgt": g["dst"][q], "bgd": g["fake"]}[r].astype(np.int64)
+        e = None if r == "bgd" else g["eidx"][q]
+        sub = f.find_k_hop(2, roots, ts[q], n, e, seed=seed + call)
+        assert_sub(g, r, sub)
+        walks = f.find_k_walks(n, roots, N2, sub, seed=seed + call + 1)
+        assert walks[0].dtype == np.int64
+        assert_walks(g, r, walks)
+        call += 2
+        if f"{r}_edge_identity" in g:
+            ei = tm.new_edge_info(walks[1])
+            assert ei.dtype == np.float64 and (ei == g[f"{r}_edge_identity"]).all()
+        if f"{r}_cat" in g:
+            an = torch.as_tensor(walks[3]).cuda()
+            hn, hp, cat, err = tm.class_hist_device(an)
+            assert int(err.item()) == 0 and (cat.cpu().numpy() == g[f"{r}_cat"]).all()
+            assert (hn.cpu().numpy() == orc.class_hist_null(walks[3])).all()
+            assert (hp.cpu().numpy() == orc.class_ids_prep(walks[3])[1]).all()
+
+
+def test_shard_offset_wide_fanout_and_call_counter(tm, golden):
+    g = golden("rand_small")
+    f = finder_of(tm, g, seed=77)
+    q, n, N2 = g["q"], int(g["n"]), int(g["N2"])
+    ts = g["ts"]
+    sub = f.find_k_hop(2, g["src"][q][24:], ts[q][24:], n, g["eidx"][q][24:], seed=77, row_offset=24)
+    assert_sub(g, "shard1", sub)
+    walks = f.find_k_walks(n, g["src"][q][24:], N2, sub, seed=78, row_offset=24)
+    assert_walks(g, "shard1", walks)
+    assert (sub[0][1] == g["src_hop1_node"][24:]).all() and (walks[0] == g["src_w_nodes"][24:]).all()
+    sub = f.find_k_hop(1, g["dst"][q], ts[q], 40, g["eidx"][q], seed=5)
+    assert_sub(g, "wide", sub)
+    assert_walks(g, "wide", f.find_k_walks(40, g["dst"][q], 1, sub, seed=6))
+    # implicit seeds: call number c uses seed + c, exactly how the golden run numbered its calls
+    f2 = finder_of(tm, g, seed=77)
+    sub = f2.find_k_hop(2, g["src"][q], ts[q], n, g["eidx"][q])
+    assert_sub(g, "src", sub)
+    assert_walks(g, "src", f2.find_k_walks(n, g["src"][q], N2, sub))
+
+
+def test_train_finder_missing_eidx(tm, golden):
+    g = golden("rand_bigts")
+    f = finder_of(tm, g, int(g["n_train"]))
+    q, n, N2 = g["q"], int(g["n"]), int(g["N2"])
+    with pytest.raises(IndexError):
+        f.find_k_hop(1, g["src"][q], g["ts"][q], n, g["eidx"][q])
+    with pytest.raises(IndexError):
+        f.find_before(int(g["src"][q][0]), float(g["ts"][q][0]), e_idx=int(g["eidx"][q][0]))
+    sub = f.find_k_hop(2, g["src"][q], g["ts"][q], n, None, seed=9 + 6)
+    assert_sub(g, "train", sub)
+    assert_walks(g, "train", f.find_k_walks(n, g["src"][q], N2, sub, seed=9 + 7))
+
+
+def test_null_model_distribution_golden(tm, golden):
+    g = golden("nullmodel")
+    f = finder_of(tm, g, seed=int(g["base_seed"]))
+    ti = g["test_idx"]
+    dist = tm.pre_processing(f, None, g["src"][ti].astype(np.int64), g["dst"][ti].astype(np.int64),
+                             g["ts"][ti].astype(np.float64), g["eidx"][ti], int(g["n"]), fakes=g["fakes"])
+    assert list(dist.keys()) == list(range(1, 13))
+    assert np.array_equal(np.array([dist[k] for k in range(1, 13)]), g["dist"])
+
+
+def test_empty_and_edge_inputs(tm, golden):
+    g = golden("rand_small")
+    f = finder_of(tm, g)
+    e = np.zeros(0, np.int64)
+    sub = f.find_k_hop(2, e, e.astype(np.float64), 5, e)
+    assert sub[0][0].shape == (0, 5) and sub[0][1].shape == (0, 25)
+    w = f.find_k_walks(5, e, 3, sub)
+    assert w[0].shape == (0, 15, 6) and w[3].shape == (0, 15, 3)
+    # a root with no history gives an all-padding row and [1, 3, 0] motifs (graph.py:214-215, 395-435)
+    sub = f.find_k_hop(1, np.array([1]), np.array([-5.0]), 4, None, seed=1)
+    assert (sub[0][0] == 0).all() and (sub[2][0] == 0).all()
+    w = f.find_k_walks(4, np.array([1]), 2, sub, seed=2)
+    assert (w[0][..., :4] == 0).all() and (w[3] == np.array([1, 3, 0])).all()
+    # graph without any event
+    f0 = tm.NeighborFinder([[] for _ in range(4)])
+    sub = f0.find_k_hop(1, np.array([1, 2]), np.array([1.0, 2.0]), 3, None)
+    assert (sub[0][0] == 0).all()
+    with pytest.raises(NotImplementedError):
+        tm.NeighborFinder([[]], bias=1.0)
+    with pytest.raises(NotImplementedError):
+        f.find_k_walks(4, np.array([1]), 33, f.find_k_hop(1, np.array([1]), np.array([5.0]), 4, None))
+
+
+# ------------------------------------------------------------------------------------------ vs oracle, seeded
+def synth_graph(seed, N, E, tmax, zipf=1.0, lo=1):
+    rng = np.random.default_rng(seed)
+    p = 1.0 / np.arange(1, N - lo + 1) ** zipf
+    p /= p.sum()
+    src = rng.choice(np.arange(lo, N), E, p=p); dst = rng.choice(np.arange(lo, N), E, p=p)
+    ts = np.sort(rng.integers(0, tmax, E)).astype(np.float64)
+    return src, dst, np.arange(1, E + 1), ts
+
+
+@pytest.mark.parametrize("seed,N,E,tmax,n,N2", [(1, 185, 60000, 10 ** 7, 30, 1), (2, 3000, 80000, 50000, 20, 3), (3, 500, 30000, 40, 20, 5)])
+def test_oracle_parity_seeded(tm, orc, seed, N, E, tmax, n, N2):
+    src, dst, eidx, ts = synth_graph(seed, N, E, tmax)
+    f = tm.NeighborFinder.from_events(N, src, dst, eidx, ts)
+    og = orc.OracleGraph.from_events(N, src, dst, eidx, ts)
+    off, nbr, e, t = og.export()
+    assert (f.off_set_l == off).all() and (f.node_idx_l == nbr).all() and (f.edge_idx_l == e).all() and (f.node_ts_l == t).all()
+    rng = np.random.default_rng(seed + 100)
+    q = rng.choice(np.arange(E // 2, E), 600, replace=False)
+    # find_before, both modes, straight through the batch call
+    fake = rng.integers(1, N, len(q))
+    s_o, c_o = og.find_before_batch(src[q], None, eidx[q])
+    s_d, c_d = f.find_before_batch_device(src[q], None, eidx[q])
+    assert (s_d.cpu().numpy() == s_o).all() and (c_d.cpu().numpy() == c_o).all()
+    s_o, c_o = og.find_before_batch(fake, ts[q], None)
+    s_d, c_d = f.find_before_batch_device(fake, ts[q], None)
+    assert (s_d.cpu().numpy() == s_o).all() and (c_d.cpu().numpy() == c_o).all()
+    for roots, ee, sd in ((src[q], eidx[q], 11), (dst[q], eidx[q], 12), (fake, None, 13)):
+        sub = f.find_k_hop(2, roots, ts[q], n, ee, seed=sd, row_offset=7)
+        osub = og.find_k_hop(2, roots, ts[q], n, ee, seed=sd, row_offset=7)
+        for a, b in zip(sub, osub):
+            for x, y in zip(a, b):
+                assert x.dtype == y.dtype and (x == y).all()
+        scanned = torch.zeros(1, dtype=torch.int64, device="cuda")
+        nodes, we, wt, anony, cat = f.find_k_walks_device(n, roots, N2, sub, seed=sd + 50, row_offset=7, scanned=scanned)
+        on, oe, ot, oa, osc = og.sample_walks(roots, osub[0][0], osub[1][0], osub[2][0], N2, seed=sd + 50, row_offset=7, want_scanned=True)
+        assert (nodes.cpu().numpy() == on).all() and (we.cpu().numpy() == oe).all()
+        assert (wt.cpu().numpy() == ot).all() and (anony.cpu().numpy() == oa).all()
+        assert (cat.cpu().numpy() == orc.class_ids_prep(oa)[0]).all()
+        assert int(scanned.item()) == int(osc.sum())
+        assert (tm.edge_identity_device(we).cpu().numpy() == orc.edge_identity(oe)).all()
+        # size-independent properties: sampled first-hop timestamps ascend per row and precede the cut
+        t0 = sub[2][0]
+        assert (np.diff(t0, axis=1) >= 0).all()
+        if ee is None:
+            assert (t0.astype(np.float64)[sub[0][0] > 0] < np.repeat(ts[q], n).reshape(-1, n)[sub[0][0] > 0] + 1.0).all()
+
+
+def test_injected_draws_replay(tm, orc):
+    """INJECTED mode: indices recorded elsewhere (here: from the oracle's Philox run) reproduce the sample."""
+    src, dst, eidx, ts = synth_graph(5, 300, 20000, 5000)
+    f = tm.NeighborFinder.from_events(300, src, dst, eidx, ts)
+    og = orc.OracleGraph.from_events(300, src, dst, eidx, ts)
+    q = np.arange(15000, 15200)
+    n = 12
+    s, c = og.find_before_batch(src[q], None, eidx[q])
+    rec = np.zeros((len(q), n), np.int64)
+    for i in range(len(q)):
+        for k in range(n):
+            rec[i, k] = orc.draw_index(99, 0, i, k, int(c[i])) if c[i] else 0
+    a = f.find_k_hop(1, src[q], ts[q], n, eidx[q], inject=[rec], seed=12345)   # seed ignored when injecting
+    b = og.find_k_hop(1, src[q], ts[q], n, eidx[q], seed=99)
+    for x, y in zip(a, b):
+        assert (x[0] == y[0]).all()
+
+
+# ------------------------------------------------------------------------------------------ encoder
+class _Base:
+    def __init__(self, nfeat, efeat):
+        self.n_feat_th = torch.as_tensor(nfeat).cuda(); self.e_feat_th = torch.as_tensor(efeat).cuda()
+        self.node_raw_features = torch.nn.Embedding.from_pretrained(self.n_feat_th, padding_idx=0, freeze=True)
+        self.edge_raw_features = torch.nn.Embedding.from_pretrained(self.e_feat_th, padding_idx=0, freeze=True)
+
+
+def explainer_from_golden(tm, g):
+    base = _Base(g["node_feat"], g["edge_feat"])
+    m = tm.TempME(base, "tgn", "unit", out_dim=40, hid_dim=64, device="cuda", use_temporal_guidance=bool(g["use_temporal"]),
+                  null_model={k: 1 / 12 for k in range(1, 13)})
+    sd = {k[2:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("p:")}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected                       # every reference parameter name exists in our module
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("tag", ["d172", "d32", "d32_plainattn"])
+def test_encoder_golden(tm, golden, tag):
+    g = golden("encoder_" + tag)
+    m = explainer_from_golden(tm, g)
+    walks = (g["w_nodes"].astype(np.int64), g["w_eidx"].astype(np.int64), g["w_t"].astype(np.float64),
+             g["w_cat"].astype(np.int64)[..., None], None)
+    with torch.no_grad():
+        out = m(walks, g["cut_time"], g["edge_identity"].astype(np.float64))
+    assert out.shape == g["score"].shape and out.dtype == torch.float32
+    np.testing.assert_allclose(out.cpu().numpy(), g["score"], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("D,Ed", [(32, 32), (172, 172), (100, 7)])
+def test_encoder_vs_oracle_larger(tm, orc, D, Ed):
+    """Scores for many roots in reference batches of 100 (ragged last batch) vs the numpy oracle."""
+    from oracle import encoder as orc_enc
+    rng = np.random.default_rng(D)
+    src, dst, eidx, ts = synth_graph(7, 400, 30000, 10 ** 6)
+    f = tm.NeighborFinder.from_events(400, src, dst, eidx, ts)
+    q = np.arange(20000, 20250)
+    n, N2 = 10, 3
+    sub = f.find_k_hop_device(1, src[q], ts[q], n, eidx[q], seed=3)
+    nodes, we, wt, anony, cat = f.find_k_walks_device(n, src[q], N2, sub, seed=4)
+    eid = tm.edge_identity_device(we)
+    nfeat = rng.standard_normal((400, D)).astype(np.float32); efeat = rng.standard_normal((30001, Ed)).astype(np.float32)
+    nfeat[0] = 0; efeat[0] = 0
+    torch.manual_seed(D)
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, 64, device="cuda", null_model={}).cuda().eval()
+    with torch.no_grad():
+        m.time_encoder.phase.normal_(0, 0.1)
+    cut = torch.as_tensor(ts[q].astype(np.float32)).cuda()
+    scores = m.score_device(nodes, we, wt, cat, cut, eid, group=100).cpu().numpy()
+    p = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    for s in range(0, len(q), 100):
+        sl = slice(s, s + 100)
+        walks = (nodes[sl].cpu().numpy(), we[sl].cpu().numpy(), wt[sl].cpu().numpy(), cat[sl].cpu().numpy(), None)
+        ref = orc_enc.forward(p, nfeat, efeat, walks, ts[q][sl], eid[sl].cpu().numpy())
+        np.testing.assert_allclose(scores[sl], ref[..., 0], rtol=1e-5, atol=0)
+
+
+def test_pipeline_matches_piecewise(tm, orc):
+    """MotifPipeline (the bench path) == the reference-facing calls made one by one."""
+    src, dst, eidx, ts = synth_graph(9, 185, 40000, 10 ** 7)
+    f = tm.NeighborFinder.from_events(185, src, dst, eidx, ts)
+    rng = np.random.default_rng(1)
+    nfeat = rng.standard_normal((185, 32)).astype(np.float32); efeat = rng.standard_normal((40001, 32)).astype(np.float32)
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, 64, device="cuda", null_model={}).cuda().eval()
+    q = np.arange(30000, 30200)
+    fake = rng.integers(1, 185, len(q))
+    pipe = tm.MotifPipeline(f, m, 30, 1, group=100, seed=42)
+    scores = pipe.run_host(src[q], dst[q], fake, ts[q], eidx[q])
+    assert scores.shape == (3, 200, 30)
+    assert int(pipe.hist_null.sum().item()) == 3 * 200 * 30 == int(pipe.hist_prep.sum().item())
+    og = orc.OracleGraph.from_events(185, src, dst, eidx, ts)
+    hist = np.zeros(12, np.int64)
+    for b in range(2):                                   # reference batches of 100 events
+        sl = slice(100 * b, 100 * b + 100)
+        for k, (roots, ee) in enumerate(((src[q], eidx[q]), (dst[q], eidx[q]), (fake, None))):
+            off = b * 300 + k * 100                      # batch-major global row of the first root
+            osub = og.find_k_hop(1, roots[sl], ts[q][sl], 30, None if ee is None else ee[sl], seed=42, row_offset=off)
+            on, oe, ot, oa = og.sample_walks(roots[sl], osub[0][0], osub[1][0], osub[2][0], 1, seed=43, row_offset=off)
+            hist += orc.class_hist_null(oa)
+            cat = orc.class_ids_prep(oa)[0]
+            walks = (on.astype(np.int64), oe.astype(np.int64), ot.astype(np.float64), cat[..., None].astype(np.int64), None)
+            with torch.no_grad():
+                ref = m(walks, ts[q][sl], orc.edge_identity(oe))
+            np.testing.assert_allclose(scores[k, sl], ref[..., 0].cpu().numpy(), rtol=1e-6, atol=0)
+    assert (pipe.hist_null.cpu().numpy() == hist).all()
