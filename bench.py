@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- temporal motifs sampled+encoded per second on N B200s of one node.
+
+A step = one pass of the hot path over one batch of Q query events per GPU: 3Q roots (src, tgt, bgd)
+-> first-hop lookup/sampling -> 3-event walks + anonymisation class + histogram -> edge-identity counts
+-> fused TempME scorer (eval, fp32), i.e. 3*Q*W motifs.  Default workload: BASELINE.json configs[1]
+(synthetic Enron-shaped graph, TGN base, 30 walks/query).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1..cfg5] [--events Q]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # the CPU port of the reference path (oracle/) on the host cores
+
+Prints ONE JSON line (rank 0).  `value` is measured with the queries already resident in HBM (CUDA events,
+max over ranks); `e2e` goes through MotifPipeline.run_host with pinned host buffers (H2D + D2H inside the
+timed region).  oracle/ is used here only for the cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "temporal_motifs_sampled_and_encoded_per_sec"
+UNIT = "motifs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--events", type=int, default=0, help="query events per GPU per step (multiple of --group)")
+    ap.add_argument("--group", type=int, default=100, help="events per reference batch (temp_exp_main.py --bs)")
+    ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (cfg5 smoke runs)")
+    ap.add_argument("--cpu-events", type=int, default=0, help="query events of the bounded CPU sample (0 = auto, ~15 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def encoder_flops(D, Ed, H=64):
+    """Algorithmic FLOPs per motif, lin_event counted once."""
+    ev, M = Ed + D + 3, H + 12
+    return 3 * 2 * ev * D + 6 * 2 * (D * H + H * H) + 3 * 2 * (2 * H) ** 2 + 2 * (2 * H * H + H * H) + 2 * (M * M + M * H + H)
+
+
+def default_events(cfg):
+    return {"cfg1": 2000, "cfg2": 16000, "cfg3": 4000, "cfg4": 4000, "cfg5": 16000}[cfg]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tensor=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="measured (MEASURED_PEAKS.json; bf16 sustained)")
+    return dict(hbm=6650.0, tensor=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------- CPU port (oracle)
+class CpuPort:
+    """The reference's path restated on the CPU (oracle/): C + OpenMP for lookup/sampling/anonymisation/edge
+    identity, numpy (BLAS threads) for TempME.forward.  Checker/baseline only."""
+
+    def __init__(self, graph, nfeat, efeat, params, n, N2, group, D, Ed):
+        import oracle
+        from oracle import encoder as enc
+        self.oracle, self.enc = oracle, enc
+        self.og = oracle.OracleGraph.from_events(graph["n_nodes"], graph["src"], graph["dst"], graph["eidx"], graph["ts"])
+        self.nfeat, self.efeat, self.params = nfeat, efeat, params
+        self.n, self.N2, self.group = n, N2, group
+
+    def step(self, src, dst, fake, ts, eidx, seed=0):
+        o, n, N2 = self.oracle, self.n, self.N2
+        motifs = 0
+        for roots, e in ((src, eidx), (dst, eidx), (fake, None)):
+            sub = self.og.find_k_hop(1, roots, ts, n, e, seed=seed)
+            nodes, we, wt, anony = self.og.sample_walks(roots, sub[0][0], sub[1][0], sub[2][0], N2, seed=seed + 1)
+            cat, _ = o.class_ids_prep(anony)
+            o.class_hist_null(anony)
+            eid = o.edge_identity(we)
+            for s in range(0, len(roots), self.group):
+                sl = slice(s, s + self.group)
+                self.enc.forward(self.params, self.nfeat, self.efeat, (nodes[sl], we[sl], wt[sl], cat[sl], None), ts[sl], eid[sl])
+            motifs += nodes.shape[0] * nodes.shape[1]
+        return motifs
+
+
+def random_params(D, Ed, H=64, seed=0):
+    """Default-init weights of the reference modules' shapes (torch.manual_seed(seed) nn.Linear inits)."""
+    import torch
+    torch.manual_seed(seed)
+    M, ev = H + 12, Ed + D + 3
+    shapes = {"event_conv.lin_event": (D, ev), "event_conv.MLP.0": (H, D), "event_conv.MLP.2": (H, H), "attention.W1": (2 * H, 2 * H),
+              "attention.W2": (2 * H, 2 * H), "attention.MLP.0": (H, 2 * H), "attention.MLP.3": (H, H), "MLP.0": (M, M), "MLP.3": (H, M), "MLP.5": (1, H)}
+    p = {}
+    for k, (o, i) in shapes.items():
+        lin = torch.nn.Linear(i, o)
+        p[k + ".weight"] = lin.weight.detach().numpy(); p[k + ".bias"] = lin.bias.detach().numpy()
+    p["time_encoder.basis_freq"] = (1 / 10 ** np.linspace(0, 9, D)).astype(np.float32)
+    p["time_encoder.phase"] = np.zeros(D, np.float32)
+    return p
+
+
+def cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def time_cpu_port(port, graph, rng, group, budget_s=15.0, events=0):
+    from tempme_b200 import synth
+    q = synth.make_queries(graph, rng, group)
+    t0 = time.perf_counter(); m = port.step(*q); t_cal = time.perf_counter() - t0       # calibration (also warms caches)
+    if not events:
+        events = int(min(5000, max(group, budget_s / max(t_cal, 1e-3) * group)) // group * group)
+    q = synth.make_queries(graph, rng, events)
+    t0 = time.perf_counter(); m = port.step(*q); dt = time.perf_counter() - t0
+    return m / dt, events, m, dt
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tempme_b200 import synth
+    sh = synth.SHAPES[args.workload]
+    graph = synth.make_graph(args.workload, args.scale if args.workload == "cfg5" else 1.0)
+    if args.workload == "cfg5" and args.scale >= 0.5:
+        graph = synth.make_graph("cfg5", 0.01)      # the CPU path cannot hold the 100M-event adjacency: 1 % subsample, same law
+    nfeat, efeat = synth.make_features(args.workload, graph["n_nodes"], len(graph["src"]))
+    port = CpuPort(graph, nfeat.numpy(), efeat.numpy(), random_params(sh["D"], sh["Ed"]), sh["n"], sh["N2"], args.group, sh["D"], sh["Ed"])
+    rng = np.random.default_rng(7)
+    ev = args.cpu_events or 2 * args.group
+    for _ in range(args.warmup):
+        port.step(*synth.make_queries(graph, rng, args.group))
+    qs = [synth.make_queries(graph, rng, ev) for _ in range(args.steps)]
+    t0 = time.perf_counter()
+    motifs = sum(port.step(*q) for q in qs)
+    dt = time.perf_counter() - t0
+    v = motifs / dt
+    sample = f"{ev} query events/step ({motifs // args.steps} motifs) of {args.workload}, CPU port of the reference path (oracle/: C+OpenMP sampling, numpy fp32 encoder)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"{args.workload}: {sh['desc']}", "events_per_step": ev, "walks_per_root": sh["n"] * sh["N2"]},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tempme_b200 as tm
+    from tempme_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sh = synth.SHAPES[args.workload]
+    n, N2, D, Ed = sh["n"], sh["N2"], sh["D"], sh["Ed"]
+    W = n * N2
+    Q = args.events or default_events(args.workload)
+    Q = max(args.group, Q // args.group * args.group)
+    graph = synth.make_graph(args.workload, args.scale)
+    E = len(graph["src"])
+    t0 = time.perf_counter()
+    finder = tm.NeighborFinder.from_events(graph["n_nodes"], graph["src"], graph["dst"], graph["eidx"], graph["ts"], device=dev, seed=1234)
+    build_s = time.perf_counter() - t0
+    nfeat, efeat = synth.make_features(args.workload, graph["n_nodes"], E, device=dev)
+
+    class Base:
+        n_feat_th = nfeat.to(dev); e_feat_th = efeat.to(dev)
+        node_raw_features = torch.nn.Embedding.from_pretrained(n_feat_th, padding_idx=0, freeze=True)
+        edge_raw_features = torch.nn.Embedding.from_pretrained(e_feat_th, padding_idx=0, freeze=True)
+
+    params = random_params(D, Ed)
+    model = tm.TempME(Base(), "tgn", args.workload, 40, 64, device=dev, null_model={}).to(dev).eval()
+    model.load_state_dict({k: torch.as_tensor(v) for k, v in params.items()}, strict=False)
+    pipe = tm.MotifPipeline(finder, model, n, N2, group=args.group, seed=99)
+
+    # query sets: a fresh batch per step, different per rank; global row offset = rank's first root row (weak scaling)
+    rng = np.random.default_rng(1000 + rank)
+    total = args.warmup + args.steps
+    host_q = [synth.make_queries(graph, rng, Q) for _ in range(total)]
+    dev_q = [pipe.stage_queries(*q) for q in host_q]
+    row_off = rank * 3 * Q
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    gathered = torch.empty((world, 3 * Q, W), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(i, timers=None):
+        scores = pipe.run_device(*dev_q[i], row_offset=row_off, timers=timers)
+        if world > 1:       # the path's only exchanges: 12-bin histogram all-reduce + score gather
+            dist.all_reduce(pipe.hist_null)
+            dist.all_gather_into_tensor(gathered, scores)
+        return scores
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    pipe.hist_null.zero_(); pipe.hist_prep.zero_(); pipe.scanned.zero_()
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = tm.launch_count()
+    stage_ms = {}
+    t_dev = 0.0
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    last = None
+    for k in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (not timed)
+        timers = []
+        last = step(args.warmup + k, timers)
+        end = torch.cuda.Event(enable_timing=True); end.record()
+        end.synchronize()
+        t_dev += timers[0][1].elapsed_time(end)
+        for (_, a), (name, b) in zip(timers[:-1], timers[1:]):
+            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    launches = tm.launch_count() - launches0
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    ln = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ln)
+    t_ms = float(t.item())
+    motifs_step = 3 * Q * W
+    value = world * motifs_step * args.steps / (t_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (stage durations from CUDA events inside the timed region)
+    S_total = int(pipe.scanned.item())
+    scores_f, walks = pipe.run_device(*dev_q[-1], row_offset=row_off, want_walks=True)
+    e3_frac = float((walks[1][..., 0] != 0).float().mean().item())
+    M = motifs_step
+    deg = 2.0 * E / max(graph["n_nodes"] - 1, 1)
+    alg_bytes = {
+        "sample_hop": 3 * Q * (16 + (2 * 16 + 8 * float(np.ceil(np.log2(deg + 1)))) / 3 + 28 * n),
+        "sample_walks": 3 * Q * n * (32 + 16 * N2) + M * (32 + 16 * e3_frac + 49) + 4.0 * S_total / args.steps,
+        "edge_identity": M * 48.0,
+        "encode": M * (4.0 * (6 * D + 3 * Ed) + 85 + 4),
+    }
+    flops = {"encode": M * float(encoder_flops(D, Ed))}
+    pk = peaks()
+    top = max(stage_ms, key=stage_ms.get)
+    dur_s = stage_ms[top] / args.steps * 1e-3
+    kern = {"sample_hop": "sample_hop_kernel", "sample_walks": "sample_walks_kernel", "edge_identity": "edge_identity_kernel", "encode": "encode_kernel"}[top]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"{args.workload}:{kern}")
+    if top == "encode":
+        ach = flops["encode"] / dur_s / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": traffic}
+    else:
+        ach = alg_bytes[top] / dur_s / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic}
+    roof.update(kernel=kern, peak_source=pk["source"], share_of_step=stage_ms[top] / sum(stage_ms.values()),
+                stage_ms_per_step={k: v / args.steps for k, v in stage_ms.items()},
+                algorithmic_bytes_per_motif={k: v / M for k, v in alg_bytes.items()}, hbm_gbs_all_stages=sum(alg_bytes.values()) / (t_ms / args.steps * 1e-3) / 1e9)
+
+    # ---- end to end through the public host API: pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        pinned = []
+        for q in host_q:
+            pinned.append(tuple(torch.as_tensor(np.ascontiguousarray(a)).pin_memory().numpy() for a in q))
+        for i in range(args.warmup):
+            pipe.run_host(*pinned[i], row_offset=row_off)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            out = pipe.run_host(*pinned[args.warmup + k], row_offset=row_off)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * motifs_step * args.steps / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": 3 * Q * (4 + 4 + 8), "d2h_bytes_per_step": int(out.nbytes)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        g_cpu = graph if args.workload != "cfg5" or args.scale < 0.5 else synth.make_graph("cfg5", 0.01)
+        nf_c, ef_c = (nfeat, efeat) if g_cpu is graph else synth.make_features("cfg5", g_cpu["n_nodes"], len(g_cpu["src"]))
+        port = CpuPort(g_cpu, nf_c.cpu().numpy(), ef_c.cpu().numpy(), params, n, N2, args.group, D, Ed)
+        v, ev, m, dt = time_cpu_port(port, g_cpu, np.random.default_rng(5), args.group, events=args.cpu_events)
+        cpu = {"value": v, "unit": UNIT, "cores": cores(), "kind": "port",
+               "sample": f"{ev} query events ({m} motifs, {dt:.1f} s) of the same workload through oracle/ (C+OpenMP sampling, numpy fp32 encoder)"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {sh['desc']}", "events_per_gpu_per_step": Q, "roots_per_event": 3, "walks_per_root": W,
+                       "motifs_per_step_per_gpu": motifs_step, "reference_batch": args.group, "node_dim": D, "edge_dim": Ed, "hid_dim": 64,
+                       "parallelism": f"query-sharded x{world}, graph replicated", "l2": "flushed between timed steps (256 MiB memset)",
+                       "graph_build_s": build_s, "graph_device_bytes": finder.device_bytes()},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(ln.item()), "clocks": clk,
+            "wall_s_timed_region": wall}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

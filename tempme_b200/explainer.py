@@ -87,7 +87,12 @@ class TempME(nn.Module):
         self.prior = prior
         self.if_cat = if_cat_feature
         self.dropout = nn.Dropout(dropout_p)
-        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise RuntimeError("tempme_b200.TempME scores on a CUDA device (no CPU fallback)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
         self.event_dim = self.edge_dim + self.time_dim + 3
         self.event_conv = _EventGCN(self.event_dim, self.node_dim, self.hid_dim)
         self.use_temporal_guidance = use_temporal_guidance

@@ -241,7 +241,7 @@ class NeighborFinder:
             x, y, z = self.sample_hop_device(pn, None, n, pe, s, layer, row_offset * (n ** layer),
                                              inject[layer] if inject else None)
             for r, v in zip(recs, (x, y, z)):
-                r.append(v.view(B, -1))
+                r.append(v.view(B, n ** (layer + 1)))
         return recs
 
     def find_k_hop(self, k, src_idx_l, cut_time_l, num_neighbors, e_idx_l=None, seed=None, row_offset=0, inject=None):
