@@ -47,7 +47,7 @@ struct GraphView {
     int64_t max_eidx;
     const int64_t *off;   // [n_nodes + 1]
     const Entry *entry;   // [n_entries]  time-sorted per node
-    const int32_t *nbr;   // [n_entries]  neighbour ids only: 4 B/entry stream for the id filter of step 3
+    const uint64_t *skey; // [n_entries]  per node: (nbr << 32 | position) sorted -- secondary index for the id filter of step 3
     const int4 *etab;     // [max_eidx + 1] {node_a, node_b, cut_a, cut_b}: nodeedge2idx as a table
 };
 

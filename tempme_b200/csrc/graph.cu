@@ -124,22 +124,28 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
         }
         for (int64_t i = 0; i < len; ++i) { int32_t &c = slot(ent[s + i].eidx); c = slice_len(c, len); }  // [:cut] semantics
     }
-    std::vector<int32_t> nbr(n_entries);
-    for (int64_t p = 0; p < n_entries; ++p) nbr[p] = ent[p].nbr;
+    // secondary index: per node the keys (nbr << 32 | position) sorted, i.e. positions grouped by neighbour id
+    std::vector<uint64_t> skey(n_entries);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t v = 0; v < n_nodes; ++v) {
+        const int64_t s = off[v], len = off[v + 1] - s;
+        for (int64_t i = 0; i < len; ++i) skey[s + i] = (uint64_t)(uint32_t)ent[s + i].nbr << 32 | (uint64_t)i;
+        std::sort(skey.begin() + s, skey.begin() + s + len);
+    }
 
     TM_CUDA(cudaSetDevice(device));
     tm_graph *g = new tm_graph();
     g->device = device;
     void *d_off = nullptr, *d_ent = nullptr, *d_nbr = nullptr, *d_tab = nullptr;
     const size_t b_off = sizeof(int64_t) * (n_nodes + 1), b_ent = sizeof(Entry) * std::max<int64_t>(n_entries, 1),
-                 b_nbr = sizeof(int32_t) * std::max<int64_t>(n_entries, 1), b_tab = sizeof(int4) * std::max<int64_t>(max_e + 1, 1);
+                 b_nbr = sizeof(uint64_t) * std::max<int64_t>(n_entries, 1), b_tab = sizeof(int4) * std::max<int64_t>(max_e + 1, 1);
     cudaError_t ce = cudaMalloc(&d_off, b_off);
     if (ce == cudaSuccess) ce = cudaMalloc(&d_ent, b_ent);
     if (ce == cudaSuccess) ce = cudaMalloc(&d_nbr, b_nbr);
     if (ce == cudaSuccess) ce = cudaMalloc(&d_tab, b_tab);
     if (ce == cudaSuccess) ce = cudaMemcpy(d_off, off.data(), b_off, cudaMemcpyHostToDevice);
     if (ce == cudaSuccess && n_entries) ce = cudaMemcpy(d_ent, ent.data(), sizeof(Entry) * n_entries, cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess && n_entries) ce = cudaMemcpy(d_nbr, nbr.data(), sizeof(int32_t) * n_entries, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && n_entries) ce = cudaMemcpy(d_nbr, skey.data(), sizeof(uint64_t) * n_entries, cudaMemcpyHostToDevice);
     if (ce == cudaSuccess && max_e >= 0) ce = cudaMemcpy(d_tab, etab.data(), sizeof(int4) * (max_e + 1), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) {
         set_error("graph upload failed: %s", cudaGetErrorString(ce));
@@ -148,7 +154,7 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
         return ce == cudaErrorMemoryAllocation ? TM_ERR_NOMEM : TM_ERR_CUDA;
     }
     g->v.n_nodes = n_nodes; g->v.n_entries = n_entries; g->v.max_eidx = max_e;
-    g->v.off = (const int64_t *)d_off; g->v.entry = (const Entry *)d_ent; g->v.nbr = (const int32_t *)d_nbr; g->v.etab = (const int4 *)d_tab;
+    g->v.off = (const int64_t *)d_off; g->v.entry = (const Entry *)d_ent; g->v.skey = (const uint64_t *)d_nbr; g->v.etab = (const int4 *)d_tab;
     g->device_bytes = (int64_t)(b_off + b_ent + b_nbr + b_tab);
     *out = g;
     return TM_OK;
@@ -172,7 +178,7 @@ extern "C" int tm_graph_create_from_events(int64_t n_nodes, int64_t n_events, co
 extern "C" void tm_graph_destroy(tm_graph *g) {
     if (!g) return;
     cudaSetDevice(g->device);
-    cudaFree((void *)g->v.off); cudaFree((void *)g->v.entry); cudaFree((void *)g->v.nbr); cudaFree((void *)g->v.etab);
+    cudaFree((void *)g->v.off); cudaFree((void *)g->v.entry); cudaFree((void *)g->v.skey); cudaFree((void *)g->v.etab);
     delete g;
 }
 

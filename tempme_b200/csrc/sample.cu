@@ -1,10 +1,10 @@
 // Sampling kernels: temporal neighbour sampling (get_temporal_neighbor), the fused 3-event walk
 // sampler (get_next_step + get_final_step + anonymisation class), motif-class histograms and
 // edge-identity counts.  Reference: utils/graph.py:197-476, utils/null_model.py:75-82,
-// processed/data_preprocess.py:148-208,327-343.  One warp per query row everywhere: the row's
+// processed/data_preprocess.py:148-208,327-343.  One warp per hop row, one thread per walk slot: the row's
 // windows are found with one or two 16-byte table loads, draws are counter-based (no state), the
-// gathers are 128-bit loads of whole CSR entries, and the neighbour-id filter of step 3 streams
-// the 4-byte id array with ballot/popc.
+// gathers are 128-bit loads of whole CSR entries, and the neighbour-id filter of step 3 is a key-range
+// lookup in a per-node (neighbour, position)-sorted secondary index instead of an O(prefix) scan.
 #include "common.cuh"
 
 namespace tmb {
@@ -72,38 +72,44 @@ sample_hop_kernel(GraphView g, int64_t R, const int32_t *__restrict__ node, cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// warp-cooperative filtered prefix scans for get_final_step cases 1/2 (graph.py:358-371,398-411)
+// Neighbour-id filter of get_final_step cases 1/2 (graph.py:358-371,398-411) without the O(prefix)
+// scan: skey[] holds, per node, (nbr << 32 | position) sorted, so "entries of prefix(v, cut) whose
+// neighbour is x" is the key range [(x,0), (x,cut)) and the k-th of them (in position order) is one load.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int64_t warp_count_match(const int32_t *__restrict__ p, int64_t len, int32_t a, int32_t b, int lane) {
-    int64_t cnt = 0;
-    for (int64_t base = 0; base < len; base += 128) {
-        int32_t v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int64_t i = base + u * 32 + lane; v[u] = i < len ? __ldg(p + i) : -1; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) cnt += __popc(__ballot_sync(0xffffffffu, v[u] >= 0 && (v[u] == a || v[u] == b)));
+__device__ __forceinline__ int64_t key_lower_bound(const uint64_t *__restrict__ k, int64_t lo, int64_t hi, uint64_t key) {
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(k + mid) < key) lo = mid + 1; else hi = mid;
     }
-    return cnt;
+    return lo;
 }
-// position of the k-th (0-based) matching entry
-__device__ __forceinline__ int64_t warp_select_match(const int32_t *__restrict__ p, int64_t len, int32_t a, int32_t b, int64_t k, int lane) {
-    int64_t seen = 0;
-    for (int64_t base = 0; base < len; base += 32) {
-        const int64_t i = base + lane;
-        const int32_t v = i < len ? __ldg(p + i) : -1;
-        const unsigned bal = __ballot_sync(0xffffffffu, v >= 0 && (v == a || v == b));
-        const int c = __popc(bal);
-        if (seen + c > k) return base + __fns(bal, 0, (int)(k - seen) + 1);
-        seen += c;
+struct IdRange { int64_t base, cnt; };   // skey[base .. base+cnt) = positions (< cut) of neighbour x, ascending
+__device__ __forceinline__ IdRange id_prefix(const uint64_t *__restrict__ k, int64_t len, int64_t cut, int32_t x) {
+    IdRange r;
+    const uint64_t hi_key = (uint64_t)(uint32_t)x << 32;
+    r.base = key_lower_bound(k, 0, len, hi_key);
+    r.cnt = cut > 0 ? key_lower_bound(k, r.base, len, hi_key | (uint64_t)cut) - r.base : 0;
+    return r;
+}
+// position of the element of merged rank kk in the union of two ascending position lists (all positions distinct)
+__device__ __forceinline__ int64_t select_union(const uint64_t *__restrict__ k, IdRange a, IdRange b, int64_t kk) {
+    int64_t lo = max((int64_t)0, kk - b.cnt), hi = min(kk, a.cnt);
+    while (lo < hi) {   // lo = how many of the kk smaller elements come from a
+        const int64_t mid = (lo + hi) >> 1;
+        if ((uint32_t)__ldg(k + a.base + mid) < (uint32_t)__ldg(k + b.base + (kk - mid - 1))) lo = mid + 1; else hi = mid;
     }
-    return len - 1;  // unreachable when k < count
+    const uint32_t pa = lo < a.cnt ? (uint32_t)__ldg(k + a.base + lo) : 0xffffffffu;
+    const uint32_t pb = kk - lo < b.cnt ? (uint32_t)__ldg(k + b.base + (kk - lo)) : 0xffffffffu;
+    return (int64_t)min(pa, pb);
 }
 
 // ---------------------------------------------------------------------------------------------
-// find_k_walks = get_next_step (graph.py:308-333) + get_final_step (:335-476), one warp per
-// first-hop slot; lane j holds walk j of that slot.
+// find_k_walks = get_next_step (graph.py:308-333) + get_final_step (:335-476).  One THREAD per
+// first-hop slot (it owns the N2 walks of that slot): every step is a short chain of dependent
+// 16-byte loads, so the latency is hidden by thread-level parallelism (>100k slots in flight).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int CAP>
+__global__ void __launch_bounds__(256)
 sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__restrict__ root,
                     const int32_t *__restrict__ h1_node, const int32_t *__restrict__ h1_eidx, const float *__restrict__ h1_ts,
                     uint64_t seed, uint64_t row_offset, const uint32_t *__restrict__ inj2, const uint32_t *__restrict__ inj3,
@@ -115,8 +121,7 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
     if (threadIdx.x < 12) sh_hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) sh_scan = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t r2 = (int64_t)blockIdx.x * kWarpsPerBlock + warp;  // loop variable i of get_next_step
+    const int64_t r2 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // loop variable i of get_next_step
     if (r2 < B * n) {
         const int64_t W = (int64_t)n * N2;
         const int64_t b = r2 / n;
@@ -133,79 +138,78 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
             if (t1n > 0 && in_range(t1n)) { s_b = __ldg(g.off + t1n); c_b = t1n == t.x ? t.z : (t1n == t.y ? t.w : 0); }
         }
         const int64_t L = c_a + c_b;
-        int64_t src2 = 0, tgt2 = 0; int32_t e2 = 0; float t2 = 0.f;
+        uint64_t d[CAP];
         if (L > 0) {
-            uint64_t dr = 0;
-            if (lane < N2) dr = inj2 ? min((uint64_t)inj2[r2 * N2 + lane], (uint64_t)L - 1) : draw_index(seed, TM_STAGE_STEP2, row_offset * n + r2, lane, (uint64_t)L);
-            int rank = 0;
-            for (int j = 0; j < N2; ++j) { const uint64_t x = __shfl_sync(0xffffffffu, dr, j); rank += (x < dr) || (x == dr && j < lane); }
-            uint64_t sd = 0;
-            for (int j = 0; j < N2; ++j) {  // np.sort (graph.py:328): lane k takes the draw of rank k
-                const uint64_t x = __shfl_sync(0xffffffffu, dr, j);
-                const int rk = __shfl_sync(0xffffffffu, rank, j);
-                if (rk == lane) sd = x;
-            }
-            if (lane < N2) {
-                const bool from_a = (int64_t)sd < c_a;
-                const Entry en = load_entry(g.entry + (from_a ? s_a + (int64_t)sd : s_b + ((int64_t)sd - c_a)));
-                src2 = from_a ? s1 : t1n; tgt2 = en.nbr; e2 = en.eidx; t2 = (float)en.ts;   // graph.py:329-332
-            }
+#pragma unroll
+            for (int j = 0; j < CAP; ++j)
+                if (j < N2) d[j] = inj2 ? min((uint64_t)inj2[r2 * N2 + j], (uint64_t)L - 1) : draw_index(seed, TM_STAGE_STEP2, row_offset * n + r2, j, (uint64_t)L);
+#pragma unroll
+            for (int i = 1; i < CAP; ++i)      // np.sort (graph.py:328): insertion sort of <= CAP draws
+                if (i < N2) {
+                    const uint64_t v = d[i];
+                    int j = i - 1;
+                    while (j >= 0 && d[j] > v) { d[j + 1] = d[j]; --j; }
+                    d[j + 1] = v;
+                }
         }
-        // ---- step 3: get_final_step, walks of this slot one after the other, warp-cooperative
-        int64_t my_src3 = 0, my_tgt3 = 0; int32_t my_e3 = 0; float my_t3 = 0.f; int my_tc = 0, my_code = 1;
         unsigned long long scan_acc = 0;
         for (int jj = 0; jj < N2; ++jj) {
-            const int64_t s2 = __shfl_sync(0xffffffffu, src2, jj), t2n = __shfl_sync(0xffffffffu, tgt2, jj);
-            const int32_t ee2 = __shfl_sync(0xffffffffu, e2, jj);
+            int64_t s2 = 0, t2n = 0; int32_t e2 = 0; float t2 = 0.f;
+            if (L > 0) {
+                const int64_t sd = (int64_t)d[jj];
+                const bool from_a = sd < c_a;
+                const Entry en = load_entry(g.entry + (from_a ? s_a + sd : s_b + (sd - c_a)));
+                s2 = from_a ? s1 : t1n; t2n = en.nbr; e2 = en.eidx; t2 = (float)en.ts;   // graph.py:329-332
+            }
+            // ---- step 3: get_final_step for walk w
             int64_t A, Bn; int32_t fa1, fa2, fb; int code;
             if (s1 == s2 && t1n != t2n) { A = s1; Bn = t2n; fa1 = (int32_t)t1n; fa2 = (int32_t)t2n; fb = (int32_t)t1n; code = 2; }       // :355
             else if (t1n == s2 && s1 != t2n) { A = t1n; Bn = t2n; fa1 = (int32_t)s1; fa2 = (int32_t)t2n; fb = (int32_t)s1; code = 3; }  // :395
             else { A = t1n; Bn = t2n; fa1 = fa2 = fb = -1; code = 1; }                                                                     // :436
             // cut = nodeedge2idx[x].get(e2) if x > 0 else 0; None -> whole list (graph.py:357-358)
-            int64_t cA = 0, cB = 0, sA = 0, sB = 0;
+            int64_t cA = 0, cB = 0, sA = 0, sB = 0, lenA = 0, lenB = 0;
             {
                 int4 t = make_int4(-1, -1, -1, -1);
-                if (ee2 >= 0 && (int64_t)ee2 <= g.max_eidx) t = __ldg(g.etab + ee2);
-                if (A > 0 && in_range(A)) { sA = __ldg(g.off + A); cA = A == t.x ? t.z : (A == t.y ? t.w : __ldg(g.off + A + 1) - sA); }
-                if (Bn > 0 && in_range(Bn)) { sB = __ldg(g.off + Bn); cB = Bn == t.x ? t.z : (Bn == t.y ? t.w : __ldg(g.off + Bn + 1) - sB); }
+                if (e2 >= 0 && (int64_t)e2 <= g.max_eidx) t = __ldg(g.etab + e2);
+                if (A > 0 && in_range(A)) { sA = __ldg(g.off + A); lenA = __ldg(g.off + A + 1) - sA; cA = A == t.x ? t.z : (A == t.y ? t.w : lenA); }
+                if (Bn > 0 && in_range(Bn)) { sB = __ldg(g.off + Bn); lenB = __ldg(g.off + Bn + 1) - sB; cB = Bn == t.x ? t.z : (Bn == t.y ? t.w : lenB); }
             }
             int64_t nA, nB;
+            IdRange ra1 = {0, 0}, ra2 = {0, 0}, rb = {0, 0};
             if (code == 1) { nA = cA; nB = cB; }
             else {
-                nA = warp_count_match(g.nbr + sA, cA, fa1, fa2, lane);
-                nB = warp_count_match(g.nbr + sB, cB, fb, fb, lane);
+                ra1 = id_prefix(g.skey + sA, lenA, cA, fa1);
+                if (fa2 != fa1) ra2 = id_prefix(g.skey + sA, lenA, cA, fa2);
+                rb = id_prefix(g.skey + sB, lenB, cB, fb);
+                nA = ra1.cnt + ra2.cnt; nB = rb.cnt;
                 scan_acc += (unsigned long long)(cA + cB);
             }
             int64_t src3 = 0, tgt3 = 0; int32_t e3 = 0; float t3 = 0.f; int tc = 0;
+            const int64_t w = r2 * N2 + jj;
             if (nA + nB > 0) {
-                const int64_t w = r2 * N2 + jj;
                 int64_t k = inj3 ? (int64_t)min((uint64_t)inj3[w], (uint64_t)(nA + nB) - 1)
                                  : (int64_t)draw_index(seed, TM_STAGE_STEP3, row_offset * W + w, 0, (uint64_t)(nA + nB));
                 int64_t p;
-                if (k < nA) { src3 = A; p = sA + (code == 1 ? k : warp_select_match(g.nbr + sA, cA, fa1, fa2, k, lane)); }
-                else { k -= nA; src3 = Bn; p = sB + (code == 1 ? k : warp_select_match(g.nbr + sB, cB, fb, fb, k, lane)); }
+                if (k < nA) { src3 = A; p = sA + (code == 1 ? k : select_union(g.skey + sA, ra1, ra2, k)); }
+                else { k -= nA; src3 = Bn; p = sB + (code == 1 ? k : (int64_t)(uint32_t)__ldg(g.skey + sB + rb.base + k)); }
                 const Entry en = load_entry(g.entry + p);
                 tgt3 = en.nbr; e3 = en.eidx; t3 = (float)en.ts;
                 if (code == 2) tc = (src3 == s1 && tgt3 == t1n) ? 1 : (src3 == s1 && tgt3 == t2n) ? 2 : (src3 == t1n && tgt3 == t2n) ? 3 : 0;      // :386-393
                 else if (code == 3) tc = (src3 == t1n && tgt3 == s1) ? 1 : (src3 == t1n && tgt3 == t2n) ? 3 : (src3 == t2n && tgt3 == s1) ? 2 : 0; // :427-434
                 else tc = (src3 == s1 && tgt3 != t1n) ? 3 : (src3 == t1n && tgt3 != s1) ? 2 : (src3 == s1 && tgt3 == t1n) ? 1 : (src3 == t1n && tgt3 == s1) ? 1 : 0;  // :464-473
             }
-            if (lane == jj) { my_src3 = src3; my_tgt3 = tgt3; my_e3 = e3; my_t3 = t3; my_tc = tc; my_code = code; }
-        }
-        if (lane < N2) {
-            const int64_t w = r2 * N2 + lane;
             int2 *on = reinterpret_cast<int2 *>(o_nodes + w * 6);   // [src3,tgt3,src2,tgt2,src1,tgt1], graph.py:303
-            on[0] = make_int2((int32_t)my_src3, (int32_t)my_tgt3);
-            on[1] = make_int2((int32_t)src2, (int32_t)tgt2);
+            on[0] = make_int2((int32_t)src3, (int32_t)tgt3);
+            on[1] = make_int2((int32_t)s2, (int32_t)t2n);
             on[2] = make_int2((int32_t)s1, (int32_t)t1n);
-            o_eidx[w * 3 + 0] = my_e3; o_eidx[w * 3 + 1] = e2; o_eidx[w * 3 + 2] = e1;     // :304
-            o_t[w * 3 + 0] = my_t3; o_t[w * 3 + 1] = t2; o_t[w * 3 + 2] = t1;               // :305
-            if (o_anony) { o_anony[w * 3 + 0] = 1; o_anony[w * 3 + 1] = my_code; o_anony[w * 3 + 2] = my_tc; }
-            const int cls = class_prep(my_code, my_tc);
+            o_eidx[w * 3 + 0] = e3; o_eidx[w * 3 + 1] = e2; o_eidx[w * 3 + 2] = e1;     // :304
+            o_t[w * 3 + 0] = t3; o_t[w * 3 + 1] = t2; o_t[w * 3 + 2] = t1;               // :305
+            if (o_anony) { o_anony[w * 3 + 0] = 1; o_anony[w * 3 + 1] = code; o_anony[w * 3 + 2] = tc; }
+            const int cls = class_prep(code, tc);
             if (o_cat) o_cat[w] = (uint8_t)cls;
             if (hist_null || hist_prep) atomicAdd(&sh_hist[cls], 1u);
         }
-        if (scanned && lane == 0 && scan_acc) atomicAdd(&sh_scan, scan_acc);
+        if (scanned && scan_acc) atomicAdd(&sh_scan, scan_acc);
     }
     __syncthreads();
     if (threadIdx.x < 12 && sh_hist[threadIdx.x]) {
@@ -298,10 +302,12 @@ extern "C" int tm_sample_walks(const tm_graph *g, int64_t B, int n, int N2, cons
     if (N2 > TM_MAX_STEP2_FANOUT) { set_error("tm_sample_walks: step-2 fan-out %d > %d", N2, TM_MAX_STEP2_FANOUT); return TM_ERR_UNSUPPORTED; }
     if (B == 0) return TM_OK;
     TM_CUDA(cudaSetDevice(g->device));
-    const int64_t rows = B * n, blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    sample_walks_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        g->v, B, n, N2, d_root, d_h1_node, d_h1_eidx, d_h1_ts, seed, row_offset, d_inject2, d_inject3,
-        d_o_nodes, d_o_eidx, d_o_t, d_o_anony, d_o_cat, d_hist_null, d_hist_prep, d_scanned);
+    const int64_t rows = B * n, blocks = (rows + 255) / 256;
+#define TM_WALKS(CAP) sample_walks_kernel<CAP><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                           \
+        g->v, B, n, N2, d_root, d_h1_node, d_h1_eidx, d_h1_ts, seed, row_offset, d_inject2, d_inject3,                        \
+        d_o_nodes, d_o_eidx, d_o_t, d_o_anony, d_o_cat, d_hist_null, d_hist_prep, d_scanned)
+    if (N2 == 1) TM_WALKS(1); else if (N2 <= 4) TM_WALKS(4); else if (N2 <= 8) TM_WALKS(8); else TM_WALKS(TM_MAX_STEP2_FANOUT);
+#undef TM_WALKS
     TM_LAUNCH_CHECK();
     return TM_OK;
 }
