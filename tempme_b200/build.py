@@ -7,8 +7,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["graph.cu", "sample.cu", "encoder.cu"]
-HEADERS = ["common.cuh", os.path.join("..", "..", "include", "tempme_b200.h")]
+SOURCES = ["graph.cu", "sample.cu", "encoder.cu", "encoder_tc.cu"]
+HEADERS = ["common.cuh", "tc.cuh", os.path.join("..", "..", "include", "tempme_b200.h")]
 LIB = os.path.join(CSRC, "libtempme_b200.so")
 
 
