@@ -33,6 +33,15 @@ extern std::atomic<uint64_t> g_launches;
         }                                                                                      \
     } while (0)
 
+// tensor-core scorer (encoder_tc.cu)
+int64_t tc_blob_floats(const tm_encoder_desc &d);
+int tc_pack(const tm_encoder_desc &d, const tm_encoder_params &p, float *blob);
+int64_t tc_slab_motifs();
+int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
+                    const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
+                    int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
+                    int device, cudaStream_t st);
+
 // One CSR entry: 16 bytes so that a sampled neighbour costs one 128-bit load (one sector).
 struct __align__(16) Entry {
     int32_t nbr;

@@ -6,6 +6,7 @@
 // Arithmetic is fp32 throughout (the reference's type); TimeEncode keeps the reference's
 // mul-then-add rounding (no FMA contraction) and the accurate cosf because its arguments reach 1e8.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -267,12 +268,12 @@ encode_kernel(const EncLayout L, const float *__restrict__ blob, const EncArgs a
 
 using namespace tmb;
 
-extern "C" int64_t tm_encoder_blob_floats(const tm_encoder_desc *desc) { return desc ? make_layout(*desc).total : -1; }
+extern "C" int64_t tm_encoder_blob_floats(const tm_encoder_desc *desc) { return desc ? make_layout(*desc).total + tc_blob_floats(*desc) : -1; }
 
 extern "C" int64_t tm_encoder_workspace_floats(const tm_encoder_desc *desc, int64_t B, int64_t W, int64_t group) {
-    (void)W;
     if (!desc || B < 0 || group <= 0) return -1;
-    return std::max<int64_t>(32, (B + group - 1) / group);
+    const int64_t n_std = (std::max<int64_t>(32, (B + group - 1) / group) + 31) & ~(int64_t)31;   // per-batch std, then the F slab (16-byte aligned)
+    return n_std + std::min<int64_t>(tc_slab_motifs(), std::max<int64_t>(B * W, 1)) * 3 * 2 * desc->hid_dim;
 }
 
 extern "C" int tm_encoder_pack(const tm_encoder_desc *desc, const tm_encoder_params *p, float *h_blob) {
@@ -293,7 +294,7 @@ extern "C" int tm_encoder_pack(const tm_encoder_desc *desc, const tm_encoder_par
               put(L.m5, p->mlp5_w, p->mlp5_b) && p->basis_freq && p->phase;
     if (!ok) { set_error("tm_encoder_pack: a parameter pointer is null"); return TM_ERR_ARG; }
     for (int k = 0; k < L.D; ++k) { h_blob[L.freq + k] = p->basis_freq[k]; h_blob[L.phase + k] = p->phase[k]; }
-    return TM_OK;
+    return tc_pack(*desc, *p, h_blob + L.total);     // second half of the blob: pre-split, pre-tiled tcgen05 operands
 }
 
 // shared-memory floats one tile of T motifs needs (layout of encode_kernel)
@@ -340,6 +341,12 @@ extern "C" int tm_encode_score(const tm_encoder_desc *desc, const float *d_blob,
     if (desc->use_temporal) {
         time_std_kernel<<<(unsigned)n_groups, 256, 0, st>>>(B, W, group, d_t, d_cut_time, d_workspace);
         TM_LAUNCH_CHECK();
+    }
+    const char *which = getenv("TEMPME_ENCODER");     // "ffma" selects the fp32 CUDA-core kernel (A/B validation); default: tcgen05
+    if (!which || strcmp(which, "ffma") != 0) {
+        const int64_t n_std = (std::max<int64_t>(32, n_groups) + 31) & ~(int64_t)31;
+        return tc_encode_score(*desc, d_blob + L.total, B, W, group, d_nodes, d_eidx, d_t, d_cat, d_cut_time, d_edge_identity, d_node_feat,
+                               n_node_rows, d_edge_feat, n_edge_rows, d_workspace, d_workspace + n_std, d_scores, device, st);
     }
     const int64_t cap = (227 * 1024 - 1024) / 4;
     int T = 64;

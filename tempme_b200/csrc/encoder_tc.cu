@@ -1,5 +1,9 @@
 // tcgen05 (5th-gen tensor core) path of the motif scorer: 3xTF32 GEMM chains with TMEM accumulators.
 // This file starts with a self-test GEMM that pins the descriptor / TMEM conventions of tc.cuh on hardware.
+#include <string.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -78,3 +82,464 @@ extern "C" int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, 
     TM_LAUNCH_CHECK();
     return TM_OK;
 }
+
+// =================================================================================================
+// Tensor-core scorer.  Two kernels per slab of motifs:
+//   event_tc_kernel : one CTA = 128 threads = 128 event rows (3 per motif).  lin_event -> event MLP for both
+//                     orientations; writes updated_feature rows F[row][2H] (explainer.py:179-185).
+//   motif_tc_kernel : one CTA = 128 threads = 128 motifs.  W1/W2 projections, temporal attention, attention
+//                     MLP, category one-hot, final MLP, sigmoid (explainer.py:190-200, 789-846).
+// Every Linear is a 3xTF32 tcgen05.mma chain accumulating in TMEM.  Thread t owns row t of the tile = TMEM
+// lane t: the "A-fill" of a layer reads the previous layer's accumulator row from TMEM (or the gathered
+// features), applies bias / activation in fp32 registers, splits into tf32 hi + lo and stores the row into
+// the K-major operand tile in shared memory; weights arrive pre-split and pre-tiled from the packed blob.
+// =================================================================================================
+namespace tmb {
+
+constexpr int kKC = 32;       // K columns per operand chunk
+constexpr int kTcThreads = 128;
+
+struct TcLin { int64_t w, b; int K8, N16; };   // chunk c at w + c * 2 * N16 * kKC floats: [hi tile | lo tile]; bias[N16] at b
+struct TcLayout {
+    int D, Ed, H, M, ev, use_temporal, if_cat;
+    TcLin evt, g0, g2, w1, w2, a0, a3, m0, m3;
+    int64_t w5, b5, freq, phase, total;
+};
+
+__host__ __device__ static inline int r8(int x) { return (x + 7) & ~7; }
+__host__ __device__ static inline int r16(int x) { return (x + 15) & ~15; }
+
+TcLayout make_tc_layout(const tm_encoder_desc &d) {
+    TcLayout L;
+    memset(&L, 0, sizeof L);
+    L.D = d.node_dim; L.Ed = d.edge_dim; L.H = d.hid_dim; L.use_temporal = d.use_temporal; L.if_cat = d.if_cat;
+    L.M = d.if_cat ? d.hid_dim + 12 : d.hid_dim; L.ev = L.Ed + 3 + L.D;
+    int64_t o = 0;
+    auto lin = [&](int K, int N) {
+        TcLin l; l.K8 = r8(K); l.N16 = r16(N);
+        const int nch = (l.K8 + kKC - 1) / kKC;
+        l.w = o; o += (int64_t)nch * 2 * l.N16 * kKC; l.b = o; o += l.N16;
+        return l;
+    };
+    L.evt = lin(L.ev, L.D); L.g0 = lin(L.D, L.H); L.g2 = lin(L.H, L.H);
+    L.w1 = lin(2 * L.H, 2 * L.H); L.w2 = lin(2 * L.H, 2 * L.H); L.a0 = lin(2 * L.H, L.H); L.a3 = lin(L.H, L.H);
+    L.m0 = lin(L.M, L.M); L.m3 = lin(L.M, L.H);
+    L.w5 = o; o += r16(L.H); L.b5 = o; o += 16;
+    L.freq = o; o += r16(L.D); L.phase = o; o += r16(L.D);
+    L.total = (o + 3) & ~(int64_t)3;
+    return L;
+}
+
+// host: nn.Linear weight [N][K] -> per K chunk the [hi | lo] operand tiles in the tc.cuh layout (R = N16 rows)
+void pack_tc_lin(const TcLin &l, int K, int N, const float *w, const float *b, float *blob) {
+    const int nch = (l.K8 + kKC - 1) / kKC;
+    for (int c = 0; c < nch; ++c) {
+        const int kc = std::min(kKC, l.K8 - c * kKC);
+        (void)kc;
+        float *hi = blob + l.w + (int64_t)c * 2 * l.N16 * kKC, *lo = hi + (int64_t)l.N16 * kKC;
+        for (int n = 0; n < N; ++n)
+            for (int kk = 0; kk < kKC && c * kKC + kk < K; ++kk) {
+                const float x = w[(int64_t)n * K + c * kKC + kk];
+                uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u;
+                float h; memcpy(&h, &u, 4);
+                const int64_t off = ((kk >> 2) * (l.N16 * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 3) * 4) / 4;
+                hi[off] = h; lo[off] = x - h;
+            }
+    }
+    for (int n = 0; n < N; ++n) blob[l.b + n] = b[n];
+}
+
+struct TcSmem {
+    uint8_t *a[2][2];   // [m-block][hi, lo]  128 x kKC fp32 tiles
+    uint8_t *b;         // [hi | lo] N16 x kKC
+    uint64_t *mbar;
+};
+
+__device__ __forceinline__ void store_a4(const TcSmem &s, int mb, int row, int k, float4 v) {
+    float4 h, l;
+    tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+    const uint32_t off = tc::tile_off(128, row, k);
+    *reinterpret_cast<float4 *>(s.a[mb][0] + off) = h;
+    *reinterpret_cast<float4 *>(s.a[mb][1] + off) = l;
+}
+
+// One Linear over MB row blocks that share the weight: acc[mb] (TMEM column) = A[mb] * W^T.
+// fill(c, kcols) must write columns [c*kKC, c*kKC + kcols) of every A block for this thread's row.
+template <int MB, typename Fill>
+__device__ __forceinline__ void tc_linear(const TcLin l, const float *__restrict__ blob, const TcSmem &s, uint32_t tmem,
+                                          const int (&acc_col)[MB], Fill fill, uint32_t &phase) {
+    const int t = threadIdx.x;
+    const int nch = (l.K8 + kKC - 1) / kKC;
+    const uint32_t idesc = tc::idesc_tf32(128, l.N16);
+    for (int c = 0; c < nch; ++c) {
+        const int kcols = min(kKC, l.K8 - c * kKC);
+        {   // weight chunk: contiguous [hi | lo] tiles, straight 16-byte copies (L2 resident)
+            const float4 *src = reinterpret_cast<const float4 *>(blob + l.w + (int64_t)c * 2 * l.N16 * kKC);
+            float4 *dst = reinterpret_cast<float4 *>(s.b);
+            const int n4 = 2 * l.N16 * kKC / 4;
+            for (int i = t; i < n4; i += kTcThreads) dst[i] = __ldg(src + i);
+        }
+        fill(c, kcols);
+        tc::fence_smem_to_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (t == 0) {
+            tc::fence_after_sync();
+            const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)l.N16 * 16;
+            const uint32_t b_hi = tc::smem_u32(s.b), b_lo = b_hi + (uint32_t)l.N16 * kKC * 4;
+            for (int ks = 0; ks < kcols / 8; ++ks) {
+                const uint64_t bh = tc::smem_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128), bl = tc::smem_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) {
+                    const uint64_t ah = tc::smem_desc(tc::smem_u32(s.a[mb][0]) + ks * 2 * lbo_a, lbo_a, 128);
+                    const uint64_t al = tc::smem_desc(tc::smem_u32(s.a[mb][1]) + ks * 2 * lbo_a, lbo_a, 128);
+                    tc::mma_tf32(tmem + acc_col[mb], ah, bh, idesc, (c | ks) != 0);
+                    tc::mma_tf32(tmem + acc_col[mb], al, bh, idesc, 1);
+                    tc::mma_tf32(tmem + acc_col[mb], ah, bl, idesc, 1);
+                }
+            }
+            tc::mma_commit(s.mbar);
+        }
+        tc::mbar_wait(s.mbar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+    }
+}
+
+struct TcArgs {
+    int64_t n_motifs, W, group, m_begin;     // this launch scores motifs [m_begin, m_begin + slab)
+    int64_t slab;
+    const int32_t *nodes, *eidx;
+    const float *t;
+    const uint8_t *cat;
+    const float *cut, *eid, *node_feat, *edge_feat, *std_;
+    int64_t n_node_rows, n_edge_rows;
+    float *F;                                // [3 * slab][2H] updated_feature rows of the slab
+    float *scores;
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ void tc_carve(uint8_t *smem, TcSmem &s, int n16_max) {
+    s.a[0][0] = smem; s.a[0][1] = smem + 128 * kKC * 4; s.a[1][0] = smem + 2 * 128 * kKC * 4; s.a[1][1] = smem + 3 * 128 * kKC * 4;
+    s.b = smem + 4 * 128 * kKC * 4;
+    (void)n16_max;
+}
+
+// ---------------------------------------------------------------------------------------------
+// event kernel: rows r = 3 * motif + position of the slab
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads)
+event_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    TcSmem s; tc_carve(smem, s, 0); s.mbar = &mbar;
+    const int t = threadIdx.x, warp = t >> 5;
+    if (t == 0) tc::mbar_init(&mbar, 1);
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, a.tmem_cols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot, lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t phase = 0;
+    const int H = L.H, D = L.D, Ed = L.Ed;
+    const int colZ = 0, colE = 2 * H, colF = 2 * H;      // Z [0,2H) ; E [2H, 2H + r16(D)) ; F aliases E (dead by then)
+    const int64_t n_rows = 3 * min(a.slab, a.n_motifs - a.m_begin);
+    const float *__restrict__ freq = blob + L.freq, *__restrict__ phs = blob + L.phase;
+
+    for (int64_t tile = blockIdx.x; tile * 128 < n_rows; tile += gridDim.x) {
+        const int64_t r = tile * 128 + t;
+        const bool live = r < n_rows;
+        const int64_t gm = a.m_begin + (live ? r / 3 : 0);
+        const int pos = live ? (int)(r % 3) : 0;
+        int64_t e = 0, ns = 0, nt = 0; float dt = 0.f;
+        if (live) {
+            e = a.eidx[gm * 3 + pos]; ns = a.nodes[gm * 6 + 2 * pos]; nt = a.nodes[gm * 6 + 2 * pos + 1];
+            dt = __fsub_rn(a.t[gm * 3 + 2], a.t[gm * 3 + pos]);                       // explainer.py:326
+        }
+        const bool e_ok = live && e >= 0 && e < a.n_edge_rows, s_ok = live && ns >= 0 && ns < a.n_node_rows, t_ok = live && nt >= 0 && nt < a.n_node_rows;
+        const float *ef = a.edge_feat + e * Ed, *sf = a.node_feat + ns * D, *tf = a.node_feat + nt * D;
+        const float *ei = a.eid ? a.eid + gm * 9 + pos * 3 : nullptr;
+        auto xval = [&](int j) -> float {                                              // event_features column j (:179)
+            if (j < Ed) return e_ok ? __ldg(ef + j) : 0.f;
+            if (j < Ed + 3) return (live && ei) ? __ldg(ei + (j - Ed)) : 0.f;
+            if (j < L.ev) { const int k = j - Ed - 3; return live ? cosf(__fadd_rn(__fmul_rn(dt, __ldg(freq + k)), __ldg(phs + k))) : 0.f; }
+            return 0.f;
+        };
+        // ---- lin_event (:93)
+        { const int acc[1] = {colE};
+          tc_linear<1>(L.evt, blob, s, tmem, acc, [&](int c, int kcols) {
+              for (int k = 0; k < kcols; k += 4) { const int j = c * kKC + k; store_a4(s, 0, t, k, make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3))); }
+          }, phase); }
+        // ---- event_conv.MLP.0 on src + relu(tgt + event) and tgt + relu(src + event) (:94-95,182-184)
+        { const int acc[2] = {colZ, colZ + H};
+          tc_linear<2>(L.g0, blob, s, tmem, acc, [&](int c, int kcols) {
+              for (int k0 = 0; k0 < kcols; k0 += 16) {
+                  float ev[16];
+                  tc::tmem_ld16(tmem + lane_base + colE + c * kKC + k0, ev);
+#pragma unroll
+                  for (int k = 0; k < 16; k += 4) {
+                      if (k0 + k >= kcols) break;
+                      float hs[4], hg[4];
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) {
+                          const int j = c * kKC + k0 + k + i;
+                          const float e_ = j < D ? ev[k + i] + __ldg(blob + L.evt.b + j) : 0.f;
+                          const float s_ = (j < D && s_ok) ? __ldg(sf + j) : 0.f, g_ = (j < D && t_ok) ? __ldg(tf + j) : 0.f;
+                          hs[i] = j < D ? s_ + fmaxf(g_ + e_, 0.f) : 0.f;
+                          hg[i] = j < D ? g_ + fmaxf(s_ + e_, 0.f) : 0.f;
+                      }
+                      store_a4(s, 0, t, k0 + k, make_float4(hs[0], hs[1], hs[2], hs[3]));
+                      store_a4(s, 1, t, k0 + k, make_float4(hg[0], hg[1], hg[2], hg[3]));
+                  }
+              }
+          }, phase); }
+        // ---- event_conv.MLP.2 (:84)
+        { const int acc[2] = {colF, colF + H};
+          tc_linear<2>(L.g2, blob, s, tmem, acc, [&](int c, int kcols) {
+#pragma unroll
+              for (int mb = 0; mb < 2; ++mb)
+                  for (int k0 = 0; k0 < kcols; k0 += 16) {
+                      float z[16];
+                      tc::tmem_ld16(tmem + lane_base + colZ + mb * H + c * kKC + k0, z);
+#pragma unroll
+                      for (int k = 0; k < 16; k += 4) {
+                          float v[4];
+#pragma unroll
+                          for (int i = 0; i < 4; ++i) v[i] = fmaxf(z[k + i] + __ldg(blob + L.g0.b + c * kKC + k0 + k + i), 0.f);
+                          store_a4(s, mb, t, k0 + k, make_float4(v[0], v[1], v[2], v[3]));
+                      }
+                  }
+          }, phase); }
+        // ---- updated_feature row = [MLP(src side) | MLP(tgt side)] (:185); tcgen05.ld stays warp-uniform
+        {
+            float *fo = a.F + (live ? r : 0) * (2 * H);
+            for (int c0 = 0; c0 < 2 * H; c0 += 16) {
+                float v[16];
+                tc::tmem_ld16(tmem + lane_base + colF + c0, v);
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float *bb = blob + L.g2.b + ((c0 + i) & (H - 1));
+                        *reinterpret_cast<float4 *>(fo + c0 + i) = make_float4(v[i] + __ldg(bb), v[i + 1] + __ldg(bb + 1), v[i + 2] + __ldg(bb + 2), v[i + 3] + __ldg(bb + 3));
+                    }
+                }
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();            // all TMEM reads of this tile done before the next tile's MMAs overwrite it
+        tc::fence_after_sync();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// motif kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads)
+motif_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    TcSmem s; tc_carve(smem, s, 0); s.mbar = &mbar;
+    const int t = threadIdx.x, warp = t >> 5;
+    if (t == 0) tc::mbar_init(&mbar, 1);
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot, lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t phase = 0;
+    const int H = L.H, H2 = 2 * L.H;
+    const int colP = 0, colQ0 = H2, colQ1 = 2 * H2, colA1 = 3 * H2, colA2 = 3 * H2 + H;     // 3*2H + 2H = 512 columns at H = 64
+    const int colM0 = 0, colM1 = H2;                                                           // reuse after the attention
+    const int64_t n_m = min(a.slab, a.n_motifs - a.m_begin);
+
+    for (int64_t tile = blockIdx.x; tile * 128 < n_m; tile += gridDim.x) {
+        const int64_t ml = tile * 128 + t;           // motif index inside the slab
+        const bool live = ml < n_m;
+        const int64_t gm = a.m_begin + (live ? ml : 0);
+        const float *f0 = a.F + (live ? ml : 0) * 3 * H2, *f1 = f0 + H2, *f2 = f1 + H2;
+        auto load4 = [&](const float *p) { return live ? __ldg(reinterpret_cast<const float4 *>(p)) : make_float4(0.f, 0.f, 0.f, 0.f); };
+        // ---- Wp = W1 f2 ; Wq_k = W2 f_k (:806-807)
+        { const int acc[1] = {colP};
+          tc_linear<1>(L.w1, blob, s, tmem, acc, [&](int c, int kcols) {
+              for (int k = 0; k < kcols; k += 4) store_a4(s, 0, t, k, load4(f2 + c * kKC + k));
+          }, phase); }
+        { const int acc[2] = {colQ0, colQ1};
+          tc_linear<2>(L.w2, blob, s, tmem, acc, [&](int c, int kcols) {
+              for (int k = 0; k < kcols; k += 4) { store_a4(s, 0, t, k, load4(f0 + c * kKC + k)); store_a4(s, 1, t, k, load4(f1 + c * kKC + k)); }
+          }, phase); }
+        // ---- scores, temporal weighting, softmax (:808-839)
+        float s0 = 0.f, s1 = 0.f;
+        for (int c0 = 0; c0 < H2; c0 += 16) {
+            float p[16], q0[16], q1[16];
+            tc::tmem_ld16(tmem + lane_base + colP + c0, p); tc::tmem_ld16(tmem + lane_base + colQ0 + c0, q0); tc::tmem_ld16(tmem + lane_base + colQ1 + c0, q1);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float pb = p[i] + __ldg(blob + L.w1.b + c0 + i), b2 = __ldg(blob + L.w2.b + c0 + i);
+                s0 = fmaf(pb, q0[i] + b2, s0); s1 = fmaf(pb, q1[i] + b2, s1);
+            }
+        }
+        if (L.use_temporal && live) {
+            const int64_t b = gm / a.W;
+            const float cut = a.cut[b], sd = __fadd_rn(a.std_[b / a.group], 1e-6f);
+            const float d0 = fabsf(__fsub_rn(cut, a.t[gm * 3 + 0])), d1 = fabsf(__fsub_rn(cut, a.t[gm * 3 + 1]));
+            s0 = __fmul_rn(s0, __fadd_rn(0.7f, __fmul_rn(0.3f, expf(__fdiv_rn(-d0, sd)))));      // :828,836
+            s1 = __fmul_rn(s1, __fadd_rn(0.7f, __fmul_rn(0.3f, expf(__fdiv_rn(-d1, sd)))));
+        }
+        const float mx = fmaxf(s0, s1), e0 = expf(s0 - mx), e1 = expf(s1 - mx);
+        const float al0 = e0 / (e0 + e1), al1 = e1 / (e0 + e1);
+        // ---- attention.MLP.0 on f2 + sum_k alpha_k Wq_k (:841-843)
+        { const int acc[1] = {colA1};
+          tc_linear<1>(L.a0, blob, s, tmem, acc, [&](int c, int kcols) {
+              for (int k0 = 0; k0 < kcols; k0 += 16) {
+                  float q0[16], q1[16];
+                  tc::tmem_ld16(tmem + lane_base + colQ0 + c * kKC + k0, q0); tc::tmem_ld16(tmem + lane_base + colQ1 + c * kKC + k0, q1);
+#pragma unroll
+                  for (int k = 0; k < 16; k += 4) {
+                      const float4 f = load4(f2 + c * kKC + k0 + k);
+                      const float fv[4] = {f.x, f.y, f.z, f.w};
+                      float o[4];
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) { const float b2 = __ldg(blob + L.w2.b + c * kKC + k0 + k + i); o[i] = fv[i] + fmaf(al0, q0[k + i] + b2, al1 * (q1[k + i] + b2)); }
+                      store_a4(s, 0, t, k0 + k, make_float4(o[0], o[1], o[2], o[3]));
+                  }
+              }
+          }, phase); }
+        // ---- attention.MLP.3
+        { const int acc[1] = {colA2};
+          tc_linear<1>(L.a3, blob, s, tmem, acc, [&](int c, int kcols) {
+              for (int k0 = 0; k0 < kcols; k0 += 16) {
+                  float z[16];
+                  tc::tmem_ld16(tmem + lane_base + colA1 + c * kKC + k0, z);
+#pragma unroll
+                  for (int k = 0; k < 16; k += 4) {
+                      float v[4];
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) v[i] = fmaxf(z[k + i] + __ldg(blob + L.a0.b + c * kKC + k0 + k + i), 0.f);
+                      store_a4(s, 0, t, k0 + k, make_float4(v[0], v[1], v[2], v[3]));
+                  }
+              }
+          }, phase); }
+        // ---- MLP.0 on [attention out | one-hot(category)] (:195-200)
+        const int cat = (L.if_cat && live && a.cat) ? (int)a.cat[gm] : -1;
+        { const int acc[1] = {colM0};
+          tc_linear<1>(L.m0, blob, s, tmem, acc, [&](int c, int kcols) {
+              for (int k0 = 0; k0 < kcols; k0 += 16) {
+                  float z[16];
+                  tc::tmem_ld16(tmem + lane_base + colA2 + min(c * kKC + k0, H - 16), z);   // columns >= H come from the one-hot
+#pragma unroll
+                  for (int k = 0; k < 16; k += 4) {
+                      if (k0 + k >= kcols) break;
+                      float v[4];
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) {
+                          const int j = c * kKC + k0 + k + i;
+                          v[i] = j < H ? z[k + i] + __ldg(blob + L.a3.b + j) : (j - H == cat ? 1.f : 0.f);
+                      }
+                      store_a4(s, 0, t, k0 + k, make_float4(v[0], v[1], v[2], v[3]));
+                  }
+              }
+          }, phase); }
+        // ---- MLP.3
+        { const int acc[1] = {colM1};
+          tc_linear<1>(L.m3, blob, s, tmem, acc, [&](int c, int kcols) {
+              for (int k0 = 0; k0 < kcols; k0 += 16) {
+                  float z[16];
+                  tc::tmem_ld16(tmem + lane_base + colM0 + c * kKC + k0, z);
+#pragma unroll
+                  for (int k = 0; k < 16; k += 4) {
+                      if (k0 + k >= kcols) break;
+                      float v[4];
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) { const int j = c * kKC + k0 + k + i; v[i] = j < L.M ? fmaxf(z[k + i] + __ldg(blob + L.m0.b + j), 0.f) : 0.f; }
+                      store_a4(s, 0, t, k0 + k, make_float4(v[0], v[1], v[2], v[3]));
+                  }
+              }
+          }, phase); }
+        // ---- MLP.5 + sigmoid
+        float z5 = 0.f;
+        for (int c0 = 0; c0 < H; c0 += 16) {
+            float z[16];
+            tc::tmem_ld16(tmem + lane_base + colM1 + c0, z);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z5 = fmaf(fmaxf(z[i] + __ldg(blob + L.m3.b + c0 + i), 0.f), __ldg(blob + L.w5 + c0 + i), z5);
+        }
+        if (live) a.scores[gm] = 1.f / (1.f + expf(-(z5 + __ldg(blob + L.b5))));
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tmb
+
+using namespace tmb;
+
+namespace tmb {
+
+int64_t tc_blob_floats(const tm_encoder_desc &d) { return make_tc_layout(d).total; }
+
+int tc_pack(const tm_encoder_desc &d, const tm_encoder_params &p, float *blob) {
+    const TcLayout L = make_tc_layout(d);
+    memset(blob, 0, sizeof(float) * L.total);
+    const int H = L.H, D = L.D, M = L.M;
+    pack_tc_lin(L.evt, L.ev, D, p.lin_event_w, p.lin_event_b, blob);
+    pack_tc_lin(L.g0, D, H, p.gcn0_w, p.gcn0_b, blob);
+    pack_tc_lin(L.g2, H, H, p.gcn2_w, p.gcn2_b, blob);
+    pack_tc_lin(L.w1, 2 * H, 2 * H, p.att_w1_w, p.att_w1_b, blob);
+    pack_tc_lin(L.w2, 2 * H, 2 * H, p.att_w2_w, p.att_w2_b, blob);
+    pack_tc_lin(L.a0, 2 * H, H, p.att_mlp0_w, p.att_mlp0_b, blob);
+    pack_tc_lin(L.a3, H, H, p.att_mlp3_w, p.att_mlp3_b, blob);
+    pack_tc_lin(L.m0, M, M, p.mlp0_w, p.mlp0_b, blob);
+    pack_tc_lin(L.m3, M, H, p.mlp3_w, p.mlp3_b, blob);
+    for (int k = 0; k < H; ++k) blob[L.w5 + k] = p.mlp5_w[k];
+    blob[L.b5] = p.mlp5_b[0];
+    for (int k = 0; k < D; ++k) { blob[L.freq + k] = p.basis_freq[k]; blob[L.phase + k] = p.phase[k]; }
+    return TM_OK;
+}
+
+int64_t tc_slab_motifs() { return 48 * 1024; }     // F slab = 48k motifs * 1.5 KB = 72 MB: stays in the 126 MB L2 between the two kernels
+
+// std_ = per-batch std (already computed); F = workspace for one slab
+int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
+                    const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
+                    int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
+                    int device, cudaStream_t st) {
+    const TcLayout L = make_tc_layout(d);
+    const int n16 = std::max(r16(L.D), 2 * L.H);
+    const size_t smem = (size_t)4 * 128 * kKC * 4 + (size_t)2 * n16 * kKC * 4;
+    uint32_t cols_e = 32;
+    while ((int)cols_e < 2 * L.H + std::max(r16(L.D), 2 * L.H)) cols_e <<= 1;
+    static bool attr_set[64] = {false};
+    if (device < 64 && !attr_set[device]) {
+        TM_CUDA(cudaFuncSetAttribute(event_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TM_CUDA(cudaFuncSetAttribute(motif_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[device] = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    TcArgs a;
+    a.n_motifs = B * W; a.W = W; a.group = group; a.slab = tc_slab_motifs(); a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
+    a.eid = eid; a.node_feat = node_feat; a.edge_feat = edge_feat; a.std_ = std_; a.n_node_rows = n_node_rows; a.n_edge_rows = n_edge_rows;
+    a.F = F; a.scores = scores; a.tmem_cols = cols_e;
+    const int ctas_e = cols_e <= 256 ? 2 : 1;
+    for (int64_t m0 = 0; m0 < a.n_motifs; m0 += a.slab) {
+        a.m_begin = m0;
+        const int64_t nm = std::min(a.slab, a.n_motifs - m0);
+        const int64_t tiles_e = (3 * nm + 127) / 128, tiles_m = (nm + 127) / 128;
+        event_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem, st>>>(L, d_blob_tc, a);
+        TM_LAUNCH_CHECK();
+        motif_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_m, sms), kTcThreads, smem, st>>>(L, d_blob_tc, a);
+        TM_LAUNCH_CHECK();
+    }
+    return TM_OK;
+}
+
+}  // namespace tmb
