@@ -97,7 +97,7 @@ extern "C" int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, 
 namespace tmb {
 
 constexpr int kKC = 32;       // K columns per operand chunk
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;   // 128 rows x 2 column halves
 
 struct TcLin { int64_t w, b; int K8, N16; };   // chunk c at w + c * 2 * N16 * kKC floats: [hi tile | lo tile]; bias[N16] at b
 struct TcLayout {
@@ -149,59 +149,68 @@ void pack_tc_lin(const TcLin &l, int K, int N, const float *w, const float *b, f
     for (int n = 0; n < N; ++n) blob[l.b + n] = b[n];
 }
 
-struct TcSmem {
-    uint8_t *a[2][2];   // [m-block][hi, lo]  128 x kKC fp32 tiles
-    uint8_t *b;         // [hi | lo] N16 x kKC
-    uint64_t *mbar;
+// the static per-tile sequence of weight chunks of one kernel (streamed by TMA, double buffered)
+struct ChunkTab { int n; int64_t off[40]; int bytes[40]; };
+
+struct TcCtx {
+    uint8_t *a[2][2];      // [m-block][hi, lo]  128 x kKC fp32 operand tiles
+    uint8_t *b[2];         // double-buffered weight chunk [hi | lo]
+    uint64_t *mma_bar, *b_bar;   // b_bar[2]
+    uint32_t mma_phase;
+    int64_t seq, total;    // running chunk counter of this CTA / chunks it will consume in total
+    const float *blob;
 };
 
-__device__ __forceinline__ void store_a4(const TcSmem &s, int mb, int row, int k, float4 v) {
+__device__ __forceinline__ void tc_prefetch(const TcCtx &x, const ChunkTab &tab, int64_t seq) {   // thread 0 only
+    const int i = (int)(seq % tab.n), buf = (int)(seq & 1);
+    tc::mbar_expect_tx(x.b_bar + buf, (uint32_t)tab.bytes[i]);
+    tc::tma_load_1d(x.b[buf], x.blob + tab.off[i], (uint32_t)tab.bytes[i], x.b_bar + buf);
+}
+
+__device__ __forceinline__ void store_a4(const TcCtx &x, int mb, int row, int k, float4 v) {
     float4 h, l;
     tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
     const uint32_t off = tc::tile_off(128, row, k);
-    *reinterpret_cast<float4 *>(s.a[mb][0] + off) = h;
-    *reinterpret_cast<float4 *>(s.a[mb][1] + off) = l;
+    *reinterpret_cast<float4 *>(x.a[mb][0] + off) = h;
+    *reinterpret_cast<float4 *>(x.a[mb][1] + off) = l;
 }
 
-// One Linear over MB row blocks that share the weight: acc[mb] (TMEM column) = A[mb] * W^T.
-// fill(c, kcols) must write columns [c*kKC, c*kKC + kcols) of every A block for this thread's row.
+// One Linear over MB row blocks that share the weight: acc[mb] (TMEM column) = A[mb] * W^T, K streamed in chunks
+// of kKC columns.  fill(c, kcols) writes this thread's share of columns [c*kKC, c*kKC + kcols) of every A block.
 template <int MB, typename Fill>
-__device__ __forceinline__ void tc_linear(const TcLin l, const float *__restrict__ blob, const TcSmem &s, uint32_t tmem,
-                                          const int (&acc_col)[MB], Fill fill, uint32_t &phase) {
+__device__ __forceinline__ void tc_linear(const TcLin l, TcCtx &x, const ChunkTab &tab, uint32_t tmem, const int (&acc_col)[MB], Fill fill) {
     const int t = threadIdx.x;
     const int nch = (l.K8 + kKC - 1) / kKC;
     const uint32_t idesc = tc::idesc_tf32(128, l.N16);
     for (int c = 0; c < nch; ++c) {
         const int kcols = min(kKC, l.K8 - c * kKC);
-        {   // weight chunk: contiguous [hi | lo] tiles, straight 16-byte copies (L2 resident)
-            const float4 *src = reinterpret_cast<const float4 *>(blob + l.w + (int64_t)c * 2 * l.N16 * kKC);
-            float4 *dst = reinterpret_cast<float4 *>(s.b);
-            const int n4 = 2 * l.N16 * kKC / 4;
-            for (int i = t; i < n4; i += kTcThreads) dst[i] = __ldg(src + i);
-        }
+        if (t == 0 && x.seq + 1 < x.total) tc_prefetch(x, tab, x.seq + 1);    // its buffer was released by the MMA wait of chunk seq-1
         fill(c, kcols);
         tc::fence_smem_to_async();
         tc::fence_before_sync();
         __syncthreads();
         if (t == 0) {
+            const int buf = (int)(x.seq & 1);
+            tc::mbar_wait(x.b_bar + buf, (uint32_t)((x.seq >> 1) & 1));           // weight chunk has landed (TMA)
             tc::fence_after_sync();
             const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)l.N16 * 16;
-            const uint32_t b_hi = tc::smem_u32(s.b), b_lo = b_hi + (uint32_t)l.N16 * kKC * 4;
+            const uint32_t b_hi = tc::smem_u32(x.b[buf]), b_lo = b_hi + (uint32_t)l.N16 * kKC * 4;
             for (int ks = 0; ks < kcols / 8; ++ks) {
                 const uint64_t bh = tc::smem_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128), bl = tc::smem_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
 #pragma unroll
                 for (int mb = 0; mb < MB; ++mb) {
-                    const uint64_t ah = tc::smem_desc(tc::smem_u32(s.a[mb][0]) + ks * 2 * lbo_a, lbo_a, 128);
-                    const uint64_t al = tc::smem_desc(tc::smem_u32(s.a[mb][1]) + ks * 2 * lbo_a, lbo_a, 128);
+                    const uint64_t ah = tc::smem_desc(tc::smem_u32(x.a[mb][0]) + ks * 2 * lbo_a, lbo_a, 128);
+                    const uint64_t al = tc::smem_desc(tc::smem_u32(x.a[mb][1]) + ks * 2 * lbo_a, lbo_a, 128);
                     tc::mma_tf32(tmem + acc_col[mb], ah, bh, idesc, (c | ks) != 0);
                     tc::mma_tf32(tmem + acc_col[mb], al, bh, idesc, 1);
                     tc::mma_tf32(tmem + acc_col[mb], ah, bl, idesc, 1);
                 }
             }
-            tc::mma_commit(s.mbar);
+            tc::mma_commit(x.mma_bar);
         }
-        tc::mbar_wait(s.mbar, phase);
-        phase ^= 1;
+        tc::mbar_wait(x.mma_bar, x.mma_phase);
+        x.mma_phase ^= 1;
+        x.seq++;
         tc::fence_after_sync();
     }
 }
@@ -217,38 +226,48 @@ struct TcArgs {
     float *F;                                // [3 * slab][2H] updated_feature rows of the slab
     float *scores;
     uint32_t tmem_cols;
+    int b_bytes;                             // bytes of one weight-chunk buffer
 };
 
-__device__ __forceinline__ void tc_carve(uint8_t *smem, TcSmem &s, int n16_max) {
-    s.a[0][0] = smem; s.a[0][1] = smem + 128 * kKC * 4; s.a[1][0] = smem + 2 * 128 * kKC * 4; s.a[1][1] = smem + 3 * 128 * kKC * 4;
-    s.b = smem + 4 * 128 * kKC * 4;
-    (void)n16_max;
-}
-
-// ---------------------------------------------------------------------------------------------
-// event kernel: rows r = 3 * motif + position of the slab
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads)
-event_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t tmem_slot;
-    TcSmem s; tc_carve(smem, s, 0); s.mbar = &mbar;
-    const int t = threadIdx.x, warp = t >> 5;
-    if (t == 0) tc::mbar_init(&mbar, 1);
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, a.tmem_cols);
+__device__ __forceinline__ void tc_setup(uint8_t *smem, TcCtx &x, const TcArgs &a, int mb, uint64_t *bars, uint32_t *tmem_slot,
+                                         uint32_t tmem_cols, const float *blob) {
+    uint8_t *p = smem;
+    for (int m = 0; m < 2; ++m)
+        for (int h = 0; h < 2; ++h) { x.a[m][h] = p; if (m < mb) p += 128 * kKC * 4; }
+    x.b[0] = p; x.b[1] = p + a.b_bytes;
+    x.mma_bar = bars; x.b_bar = bars + 1;
+    x.mma_phase = 0; x.seq = 0; x.blob = blob;
+    if (threadIdx.x == 0) { tc::mbar_init(bars, 1); tc::mbar_init(bars + 1, 1); tc::mbar_init(bars + 2, 1); }
+    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem = tmem_slot, lane_base = (uint32_t)(warp * 32) << 16;
-    uint32_t phase = 0;
+}
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// ---------------------------------------------------------------------------------------------
+// event kernel: 256 threads = 128 event rows x 2 column halves; rows r = 3 * motif + position of the slab
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads)
+event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ blob, const TcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[3];
+    __shared__ uint32_t tmem_slot;
+    TcCtx x;
+    tc_setup(smem, x, a, 2, bars, &tmem_slot, a.tmem_cols, blob);
+    const int t = threadIdx.x, warp = t >> 5, row = t & 127, half = t >> 7, kb = 16 * half;
+    const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int H = L.H, D = L.D, Ed = L.Ed;
     const int colZ = 0, colE = 2 * H, colF = 2 * H;      // Z [0,2H) ; E [2H, 2H + r16(D)) ; F aliases E (dead by then)
     const int64_t n_rows = 3 * min(a.slab, a.n_motifs - a.m_begin);
+    const int64_t n_tiles = (n_rows + 127) / 128;
+    x.total = ((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * tab.n;
+    if (t == 0 && x.total > 0) tc_prefetch(x, tab, 0);
     const float *__restrict__ freq = blob + L.freq, *__restrict__ phs = blob + L.phase;
 
-    for (int64_t tile = blockIdx.x; tile * 128 < n_rows; tile += gridDim.x) {
-        const int64_t r = tile * 128 + t;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t r = tile * 128 + row;
         const bool live = r < n_rows;
         const int64_t gm = a.m_begin + (live ? r / 3 : 0);
         const int pos = live ? (int)(r % 3) : 0;
@@ -268,60 +287,58 @@ event_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         };
         // ---- lin_event (:93)
         { const int acc[1] = {colE};
-          tc_linear<1>(L.evt, blob, s, tmem, acc, [&](int c, int kcols) {
-              for (int k = 0; k < kcols; k += 4) { const int j = c * kKC + k; store_a4(s, 0, t, k, make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3))); }
-          }, phase); }
+          tc_linear<1>(L.evt, x, tab, tmem, acc, [&](int c, int kcols) {
+              for (int k = kb; k < min(kb + 16, kcols); k += 4) { const int j = c * kKC + k; store_a4(x, 0, row, k, make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3))); }
+          }); }
         // ---- event_conv.MLP.0 on src + relu(tgt + event) and tgt + relu(src + event) (:94-95,182-184)
         { const int acc[2] = {colZ, colZ + H};
-          tc_linear<2>(L.g0, blob, s, tmem, acc, [&](int c, int kcols) {
-              for (int k0 = 0; k0 < kcols; k0 += 16) {
+          tc_linear<2>(L.g0, x, tab, tmem, acc, [&](int c, int kcols) {
+              if (kb < kcols) {
                   float ev[16];
-                  tc::tmem_ld16(tmem + lane_base + colE + c * kKC + k0, ev);
+                  tc::tmem_ld16(tmem + lane_base + colE + c * kKC + kb, ev);
 #pragma unroll
                   for (int k = 0; k < 16; k += 4) {
-                      if (k0 + k >= kcols) break;
+                      if (kb + k >= kcols) break;
                       float hs[4], hg[4];
 #pragma unroll
                       for (int i = 0; i < 4; ++i) {
-                          const int j = c * kKC + k0 + k + i;
+                          const int j = c * kKC + kb + k + i;
                           const float e_ = j < D ? ev[k + i] + __ldg(blob + L.evt.b + j) : 0.f;
                           const float s_ = (j < D && s_ok) ? __ldg(sf + j) : 0.f, g_ = (j < D && t_ok) ? __ldg(tf + j) : 0.f;
                           hs[i] = j < D ? s_ + fmaxf(g_ + e_, 0.f) : 0.f;
                           hg[i] = j < D ? g_ + fmaxf(s_ + e_, 0.f) : 0.f;
                       }
-                      store_a4(s, 0, t, k0 + k, make_float4(hs[0], hs[1], hs[2], hs[3]));
-                      store_a4(s, 1, t, k0 + k, make_float4(hg[0], hg[1], hg[2], hg[3]));
+                      store_a4(x, 0, row, kb + k, make_float4(hs[0], hs[1], hs[2], hs[3]));
+                      store_a4(x, 1, row, kb + k, make_float4(hg[0], hg[1], hg[2], hg[3]));
                   }
               }
-          }, phase); }
+          }); }
         // ---- event_conv.MLP.2 (:84)
         { const int acc[2] = {colF, colF + H};
-          tc_linear<2>(L.g2, blob, s, tmem, acc, [&](int c, int kcols) {
+          tc_linear<2>(L.g2, x, tab, tmem, acc, [&](int c, int kcols) {
+              (void)kcols;
 #pragma unroll
-              for (int mb = 0; mb < 2; ++mb)
-                  for (int k0 = 0; k0 < kcols; k0 += 16) {
-                      float z[16];
-                      tc::tmem_ld16(tmem + lane_base + colZ + mb * H + c * kKC + k0, z);
+              for (int mb = 0; mb < 2; ++mb) {
+                  float z[16];
+                  tc::tmem_ld16(tmem + lane_base + colZ + mb * H + c * kKC + kb, z);
 #pragma unroll
-                      for (int k = 0; k < 16; k += 4) {
-                          float v[4];
-#pragma unroll
-                          for (int i = 0; i < 4; ++i) v[i] = fmaxf(z[k + i] + __ldg(blob + L.g0.b + c * kKC + k0 + k + i), 0.f);
-                          store_a4(s, mb, t, k0 + k, make_float4(v[0], v[1], v[2], v[3]));
-                      }
+                  for (int k = 0; k < 16; k += 4) {
+                      const float4 bb = ldg4(blob + L.g0.b + c * kKC + kb + k);
+                      store_a4(x, mb, row, kb + k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
                   }
-          }, phase); }
-        // ---- updated_feature row = [MLP(src side) | MLP(tgt side)] (:185); tcgen05.ld stays warp-uniform
+              }
+          }); }
+        // ---- updated_feature row = [MLP(src side) | MLP(tgt side)] (:185): half h stores columns [h*H, h*H + H)
         {
-            float *fo = a.F + (live ? r : 0) * (2 * H);
-            for (int c0 = 0; c0 < 2 * H; c0 += 16) {
+            float *fo = a.F + (live ? r : 0) * (2 * H) + half * H;
+            for (int c0 = 0; c0 < H; c0 += 16) {
                 float v[16];
-                tc::tmem_ld16(tmem + lane_base + colF + c0, v);
+                tc::tmem_ld16(tmem + lane_base + colF + half * H + c0, v);
                 if (live) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
-                        const float *bb = blob + L.g2.b + ((c0 + i) & (H - 1));
-                        *reinterpret_cast<float4 *>(fo + c0 + i) = make_float4(v[i] + __ldg(bb), v[i + 1] + __ldg(bb + 1), v[i + 2] + __ldg(bb + 2), v[i + 3] + __ldg(bb + 3));
+                        const float4 bb = ldg4(blob + L.g2.b + c0 + i);
+                        *reinterpret_cast<float4 *>(fo + c0 + i) = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
                     }
                 }
             }
@@ -336,53 +353,68 @@ event_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 }
 
 // ---------------------------------------------------------------------------------------------
-// motif kernel
+// motif kernel: 256 threads = 128 motifs x 2 column halves.  TMEM: X = [0, 2H), Y = [2H, 4H).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads)
-motif_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
+motif_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ blob, const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t bars[3];
     __shared__ uint32_t tmem_slot;
-    TcSmem s; tc_carve(smem, s, 0); s.mbar = &mbar;
-    const int t = threadIdx.x, warp = t >> 5;
-    if (t == 0) tc::mbar_init(&mbar, 1);
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem = tmem_slot, lane_base = (uint32_t)(warp * 32) << 16;
-    uint32_t phase = 0;
+    __shared__ float part[2][128];
+    TcCtx x;
+    tc_setup(smem, x, a, 1, bars, &tmem_slot, a.tmem_cols, blob);
+    const int t = threadIdx.x, warp = t >> 5, row = t & 127, half = t >> 7, kb = 16 * half;
+    const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int H = L.H, H2 = 2 * L.H;
-    const int colP = 0, colQ0 = H2, colQ1 = 2 * H2, colA1 = 3 * H2, colA2 = 3 * H2 + H;     // 3*2H + 2H = 512 columns at H = 64
-    const int colM0 = 0, colM1 = H2;                                                           // reuse after the attention
+    const int colX = 0, colY = H2, colA1 = 0, colA2 = H, colM0 = H2, colM1 = 0;
     const int64_t n_m = min(a.slab, a.n_motifs - a.m_begin);
+    const int64_t n_tiles = (n_m + 127) / 128;
+    x.total = ((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * tab.n;
+    if (t == 0 && x.total > 0) tc_prefetch(x, tab, 0);
+    auto both_halves = [&](float v) {      // sum of the two column-half partials of every row
+        part[half][row] = v;
+        __syncthreads();
+        const float s_ = part[0][row] + part[1][row];
+        __syncthreads();
+        return s_;
+    };
 
-    for (int64_t tile = blockIdx.x; tile * 128 < n_m; tile += gridDim.x) {
-        const int64_t ml = tile * 128 + t;           // motif index inside the slab
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t ml = tile * 128 + row;         // motif index inside the slab
         const bool live = ml < n_m;
         const int64_t gm = a.m_begin + (live ? ml : 0);
         const float *f0 = a.F + (live ? ml : 0) * 3 * H2, *f1 = f0 + H2, *f2 = f1 + H2;
-        auto load4 = [&](const float *p) { return live ? __ldg(reinterpret_cast<const float4 *>(p)) : make_float4(0.f, 0.f, 0.f, 0.f); };
-        // ---- Wp = W1 f2 ; Wq_k = W2 f_k (:806-807)
-        { const int acc[1] = {colP};
-          tc_linear<1>(L.w1, blob, s, tmem, acc, [&](int c, int kcols) {
-              for (int k = 0; k < kcols; k += 4) store_a4(s, 0, t, k, load4(f2 + c * kKC + k));
-          }, phase); }
-        { const int acc[2] = {colQ0, colQ1};
-          tc_linear<2>(L.w2, blob, s, tmem, acc, [&](int c, int kcols) {
-              for (int k = 0; k < kcols; k += 4) { store_a4(s, 0, t, k, load4(f0 + c * kKC + k)); store_a4(s, 1, t, k, load4(f1 + c * kKC + k)); }
-          }, phase); }
-        // ---- scores, temporal weighting, softmax (:808-839)
-        float s0 = 0.f, s1 = 0.f;
-        for (int c0 = 0; c0 < H2; c0 += 16) {
-            float p[16], q0[16], q1[16];
-            tc::tmem_ld16(tmem + lane_base + colP + c0, p); tc::tmem_ld16(tmem + lane_base + colQ0 + c0, q0); tc::tmem_ld16(tmem + lane_base + colQ1 + c0, q1);
+        auto load4 = [&](const float *p) { return live ? ldg4(p) : make_float4(0.f, 0.f, 0.f, 0.f); };
+        // dot over this thread's column half of (X + b1) . (Y + b2)
+        auto score_half = [&]() {
+            float sc = 0.f;
+            for (int c0 = half * H; c0 < half * H + H; c0 += 16) {
+                float p[16], q[16];
+                tc::tmem_ld16(tmem + lane_base + colX + c0, p); tc::tmem_ld16(tmem + lane_base + colY + c0, q);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float pb = p[i] + __ldg(blob + L.w1.b + c0 + i), b2 = __ldg(blob + L.w2.b + c0 + i);
-                s0 = fmaf(pb, q0[i] + b2, s0); s1 = fmaf(pb, q1[i] + b2, s1);
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b1 = ldg4(blob + L.w1.b + c0 + i), b2 = ldg4(blob + L.w2.b + c0 + i);
+                    sc = fmaf(p[i] + b1.x, q[i] + b2.x, sc); sc = fmaf(p[i + 1] + b1.y, q[i + 1] + b2.y, sc);
+                    sc = fmaf(p[i + 2] + b1.z, q[i + 2] + b2.z, sc); sc = fmaf(p[i + 3] + b1.w, q[i + 3] + b2.w, sc);
+                }
             }
-        }
+            return sc;
+        };
+        // ---- Wp = W1 f2 -> X ; Wq_0 = W2 f_0 -> Y ; score_0 ; Wq_1 = W2 f_1 -> Y ; score_1 (:806-808)
+        { const int acc[1] = {colX};
+          tc_linear<1>(L.w1, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
+              for (int k = kb; k < kb + 16; k += 4) store_a4(x, 0, row, k, load4(f2 + c * kKC + k)); }); }
+        { const int acc[1] = {colY};
+          tc_linear<1>(L.w2, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
+              for (int k = kb; k < kb + 16; k += 4) store_a4(x, 0, row, k, load4(f0 + c * kKC + k)); }); }
+        float s0 = both_halves(score_half());
+        tc::fence_before_sync(); __syncthreads(); tc::fence_after_sync();        // Y is about to be overwritten
+        { const int acc[1] = {colY};
+          tc_linear<1>(L.w2, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
+              for (int k = kb; k < kb + 16; k += 4) store_a4(x, 0, row, k, load4(f1 + c * kKC + k)); }); }
+        float s1 = both_halves(score_half());
+        tc::fence_before_sync(); __syncthreads(); tc::fence_after_sync();
+        // ---- temporal weighting + softmax (:811-839)
         if (L.use_temporal && live) {
             const int64_t b = gm / a.W;
             const float cut = a.cut[b], sd = __fadd_rn(a.std_[b / a.group], 1e-6f);
@@ -392,90 +424,82 @@ motif_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         }
         const float mx = fmaxf(s0, s1), e0 = expf(s0 - mx), e1 = expf(s1 - mx);
         const float al0 = e0 / (e0 + e1), al1 = e1 / (e0 + e1);
-        // ---- attention.MLP.0 on f2 + sum_k alpha_k Wq_k (:841-843)
+        // ---- sum_k alpha_k (W2 f_k + b2) = W2 (alpha_0 f_0 + alpha_1 f_1) + b2 since alpha sums to one -> Y (:841)
+        { const int acc[1] = {colY};
+          tc_linear<1>(L.w2, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
+              for (int k = kb; k < kb + 16; k += 4) {
+                  const float4 u = load4(f0 + c * kKC + k), v = load4(f1 + c * kKC + k);
+                  store_a4(x, 0, row, k, make_float4(fmaf(al0, u.x, al1 * v.x), fmaf(al0, u.y, al1 * v.y), fmaf(al0, u.z, al1 * v.z), fmaf(al0, u.w, al1 * v.w)));
+              } }); }
+        // ---- attention.MLP.0 on f2 + (Y + b2) -> A1 (:842-843)
         { const int acc[1] = {colA1};
-          tc_linear<1>(L.a0, blob, s, tmem, acc, [&](int c, int kcols) {
-              for (int k0 = 0; k0 < kcols; k0 += 16) {
-                  float q0[16], q1[16];
-                  tc::tmem_ld16(tmem + lane_base + colQ0 + c * kKC + k0, q0); tc::tmem_ld16(tmem + lane_base + colQ1 + c * kKC + k0, q1);
+          tc_linear<1>(L.a0, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
+              float q[16];
+              tc::tmem_ld16(tmem + lane_base + colY + c * kKC + kb, q);
 #pragma unroll
-                  for (int k = 0; k < 16; k += 4) {
-                      const float4 f = load4(f2 + c * kKC + k0 + k);
-                      const float fv[4] = {f.x, f.y, f.z, f.w};
-                      float o[4];
-#pragma unroll
-                      for (int i = 0; i < 4; ++i) { const float b2 = __ldg(blob + L.w2.b + c * kKC + k0 + k + i); o[i] = fv[i] + fmaf(al0, q0[k + i] + b2, al1 * (q1[k + i] + b2)); }
-                      store_a4(s, 0, t, k0 + k, make_float4(o[0], o[1], o[2], o[3]));
-                  }
-              }
-          }, phase); }
-        // ---- attention.MLP.3
+              for (int k = 0; k < 16; k += 4) {
+                  const float4 f = load4(f2 + c * kKC + kb + k), b2 = ldg4(blob + L.w2.b + c * kKC + kb + k);
+                  store_a4(x, 0, row, kb + k, make_float4(f.x + (q[k] + b2.x), f.y + (q[k + 1] + b2.y), f.z + (q[k + 2] + b2.z), f.w + (q[k + 3] + b2.w)));
+              } }); }
+        // ---- attention.MLP.3 -> A2
         { const int acc[1] = {colA2};
-          tc_linear<1>(L.a3, blob, s, tmem, acc, [&](int c, int kcols) {
-              for (int k0 = 0; k0 < kcols; k0 += 16) {
-                  float z[16];
-                  tc::tmem_ld16(tmem + lane_base + colA1 + c * kKC + k0, z);
+          tc_linear<1>(L.a3, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
+              float z[16];
+              tc::tmem_ld16(tmem + lane_base + colA1 + c * kKC + kb, z);
 #pragma unroll
-                  for (int k = 0; k < 16; k += 4) {
-                      float v[4];
-#pragma unroll
-                      for (int i = 0; i < 4; ++i) v[i] = fmaxf(z[k + i] + __ldg(blob + L.a0.b + c * kKC + k0 + k + i), 0.f);
-                      store_a4(s, 0, t, k0 + k, make_float4(v[0], v[1], v[2], v[3]));
-                  }
-              }
-          }, phase); }
-        // ---- MLP.0 on [attention out | one-hot(category)] (:195-200)
+              for (int k = 0; k < 16; k += 4) {
+                  const float4 bb = ldg4(blob + L.a0.b + c * kKC + kb + k);
+                  store_a4(x, 0, row, kb + k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
+              } }); }
+        // ---- MLP.0 on [attention out | one-hot(category)] -> M0 (:195-200)
         const int cat = (L.if_cat && live && a.cat) ? (int)a.cat[gm] : -1;
         { const int acc[1] = {colM0};
-          tc_linear<1>(L.m0, blob, s, tmem, acc, [&](int c, int kcols) {
-              for (int k0 = 0; k0 < kcols; k0 += 16) {
+          tc_linear<1>(L.m0, x, tab, tmem, acc, [&](int c, int kcols) {
+              if (kb < kcols) {
                   float z[16];
-                  tc::tmem_ld16(tmem + lane_base + colA2 + min(c * kKC + k0, H - 16), z);   // columns >= H come from the one-hot
+                  tc::tmem_ld16(tmem + lane_base + colA2 + min(c * kKC + kb, H - 16), z);   // columns >= H come from the one-hot
 #pragma unroll
                   for (int k = 0; k < 16; k += 4) {
-                      if (k0 + k >= kcols) break;
                       float v[4];
 #pragma unroll
                       for (int i = 0; i < 4; ++i) {
-                          const int j = c * kKC + k0 + k + i;
+                          const int j = c * kKC + kb + k + i;
                           v[i] = j < H ? z[k + i] + __ldg(blob + L.a3.b + j) : (j - H == cat ? 1.f : 0.f);
                       }
-                      store_a4(s, 0, t, k0 + k, make_float4(v[0], v[1], v[2], v[3]));
+                      store_a4(x, 0, row, kb + k, make_float4(v[0], v[1], v[2], v[3]));
                   }
-              }
-          }, phase); }
-        // ---- MLP.3
+              } }); }
+        // ---- MLP.3 -> M1
         { const int acc[1] = {colM1};
-          tc_linear<1>(L.m3, blob, s, tmem, acc, [&](int c, int kcols) {
-              for (int k0 = 0; k0 < kcols; k0 += 16) {
+          tc_linear<1>(L.m3, x, tab, tmem, acc, [&](int c, int kcols) {
+              if (kb < kcols) {
                   float z[16];
-                  tc::tmem_ld16(tmem + lane_base + colM0 + c * kKC + k0, z);
+                  tc::tmem_ld16(tmem + lane_base + colM0 + c * kKC + kb, z);
 #pragma unroll
                   for (int k = 0; k < 16; k += 4) {
-                      if (k0 + k >= kcols) break;
                       float v[4];
 #pragma unroll
-                      for (int i = 0; i < 4; ++i) { const int j = c * kKC + k0 + k + i; v[i] = j < L.M ? fmaxf(z[k + i] + __ldg(blob + L.m0.b + j), 0.f) : 0.f; }
-                      store_a4(s, 0, t, k0 + k, make_float4(v[0], v[1], v[2], v[3]));
+                      for (int i = 0; i < 4; ++i) { const int j = c * kKC + kb + k + i; v[i] = j < L.M ? fmaxf(z[k + i] + __ldg(blob + L.m0.b + j), 0.f) : 0.f; }
+                      store_a4(x, 0, row, kb + k, make_float4(v[0], v[1], v[2], v[3]));
                   }
-              }
-          }, phase); }
+              } }); }
         // ---- MLP.5 + sigmoid
         float z5 = 0.f;
-        for (int c0 = 0; c0 < H; c0 += 16) {
+        for (int c0 = half * (H / 2); c0 < half * (H / 2) + H / 2; c0 += 16) {
             float z[16];
             tc::tmem_ld16(tmem + lane_base + colM1 + c0, z);
 #pragma unroll
             for (int i = 0; i < 16; ++i) z5 = fmaf(fmaxf(z[i] + __ldg(blob + L.m3.b + c0 + i), 0.f), __ldg(blob + L.w5 + c0 + i), z5);
         }
-        if (live) a.scores[gm] = 1.f / (1.f + expf(-(z5 + __ldg(blob + L.b5))));
+        z5 = both_halves(z5);
+        if (live && half == 0) a.scores[gm] = 1.f / (1.f + expf(-(z5 + __ldg(blob + L.b5))));
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+    if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
 }
 
 }  // namespace tmb
@@ -513,14 +537,24 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
                     int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
                     int device, cudaStream_t st) {
     const TcLayout L = make_tc_layout(d);
-    const int n16 = std::max(r16(L.D), 2 * L.H);
-    const size_t smem = (size_t)4 * 128 * kKC * 4 + (size_t)2 * n16 * kKC * 4;
-    uint32_t cols_e = 32;
+    ChunkTab te, tm;
+    te.n = tm.n = 0;
+    auto push = [](ChunkTab &tab, const TcLin &l) {
+        const int nch = (l.K8 + kKC - 1) / kKC;
+        for (int c = 0; c < nch; ++c) { tab.off[tab.n] = l.w + (int64_t)c * 2 * l.N16 * kKC; tab.bytes[tab.n] = 2 * l.N16 * kKC * 4; tab.n++; }
+    };
+    push(te, L.evt); push(te, L.g0); push(te, L.g2);
+    push(tm, L.w1); push(tm, L.w2); push(tm, L.w2); push(tm, L.w2); push(tm, L.a0); push(tm, L.a3); push(tm, L.m0); push(tm, L.m3);
+    if (te.n > 40 || tm.n > 40) { set_error("tc_encode_score: feature dims need more than 40 weight chunks"); return TM_ERR_UNSUPPORTED; }
+    const int bb_e = 2 * std::max(r16(L.D), L.H) * kKC * 4, bb_m = 2 * std::max(2 * L.H, r16(L.M)) * kKC * 4;
+    const size_t smem_e = (size_t)4 * 128 * kKC * 4 + 2 * (size_t)bb_e, smem_m = (size_t)2 * 128 * kKC * 4 + 2 * (size_t)bb_m;
+    uint32_t cols_e = 32, cols_m = 32;
     while ((int)cols_e < 2 * L.H + std::max(r16(L.D), 2 * L.H)) cols_e <<= 1;
+    while ((int)cols_m < 4 * L.H) cols_m <<= 1;
     static bool attr_set[64] = {false};
     if (device < 64 && !attr_set[device]) {
-        TM_CUDA(cudaFuncSetAttribute(event_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TM_CUDA(cudaFuncSetAttribute(motif_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TM_CUDA(cudaFuncSetAttribute(event_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TM_CUDA(cudaFuncSetAttribute(motif_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[device] = true;
     }
     int sms = 148;
@@ -528,15 +562,17 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     TcArgs a;
     a.n_motifs = B * W; a.W = W; a.group = group; a.slab = tc_slab_motifs(); a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
     a.eid = eid; a.node_feat = node_feat; a.edge_feat = edge_feat; a.std_ = std_; a.n_node_rows = n_node_rows; a.n_edge_rows = n_edge_rows;
-    a.F = F; a.scores = scores; a.tmem_cols = cols_e;
-    const int ctas_e = cols_e <= 256 ? 2 : 1;
+    a.F = F; a.scores = scores;
+    const int ctas_e = (cols_e <= 256 && smem_e <= 110 * 1024) ? 2 : 1, ctas_m = (cols_m <= 256 && smem_m <= 110 * 1024) ? 2 : 1;
     for (int64_t m0 = 0; m0 < a.n_motifs; m0 += a.slab) {
         a.m_begin = m0;
         const int64_t nm = std::min(a.slab, a.n_motifs - m0);
         const int64_t tiles_e = (3 * nm + 127) / 128, tiles_m = (nm + 127) / 128;
-        event_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem, st>>>(L, d_blob_tc, a);
+        a.tmem_cols = cols_e; a.b_bytes = bb_e;
+        event_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem_e, st>>>(L, te, d_blob_tc, a);
         TM_LAUNCH_CHECK();
-        motif_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_m, sms), kTcThreads, smem, st>>>(L, d_blob_tc, a);
+        a.tmem_cols = cols_m; a.b_bytes = bb_m;
+        motif_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_m, (int64_t)sms * ctas_m), kTcThreads, smem_m, st>>>(L, tm, d_blob_tc, a);
         TM_LAUNCH_CHECK();
     }
     return TM_OK;

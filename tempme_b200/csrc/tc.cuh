@@ -53,6 +53,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
         :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16); completes on the mbarrier
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
 // TMEM allocation: one full warp; ncols power of two in [32, 512]; address lands in *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(slot)), "r"(ncols) : "memory");
