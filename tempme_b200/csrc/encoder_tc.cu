@@ -1,8 +1,10 @@
 // tcgen05 (5th-gen tensor core) path of the motif scorer: 3xTF32 GEMM chains with TMEM accumulators.
 // This file starts with a self-test GEMM that pins the descriptor / TMEM conventions of tc.cuh on hardware.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -85,25 +87,29 @@ extern "C" int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, 
 
 // =================================================================================================
 // Tensor-core scorer.  Two kernels per slab of motifs:
-//   event_tc_kernel : one CTA = 128 threads = 128 event rows (3 per motif).  lin_event -> event MLP for both
-//                     orientations; writes updated_feature rows F[row][2H] (explainer.py:179-185).
-//   motif_tc_kernel : one CTA = 128 threads = 128 motifs.  W1/W2 projections, temporal attention, attention
-//                     MLP, category one-hot, final MLP, sigmoid (explainer.py:190-200, 789-846).
-// Every Linear is a 3xTF32 tcgen05.mma chain accumulating in TMEM.  Thread t owns row t of the tile = TMEM
-// lane t: the "A-fill" of a layer reads the previous layer's accumulator row from TMEM (or the gathered
-// features), applies bias / activation in fp32 registers, splits into tf32 hi + lo and stores the row into
-// the K-major operand tile in shared memory; weights arrive pre-split and pre-tiled from the packed blob.
+//   event_tc_kernel : one CTA = 256 threads = 128 event rows (3 per motif) x 2 column halves.  lin_event -> event
+//                     MLP for both orientations; writes updated_feature rows (explainer.py:179-185) as 16 KB
+//                     [128 motifs x 32 columns] slabs, one per (motif tile, position, column chunk).
+//   motif_tc_kernel : one CTA = 128 motifs x 2 column halves.  W1/W2 projections, temporal attention, attention
+//                     MLP, category one-hot, final MLP, sigmoid (explainer.py:190-200, 789-846); its operand rows
+//                     arrive as TMA bulk copies of those slabs.
+// Every Linear is a 3xTF32 tcgen05.mma chain accumulating in TMEM.  Thread (row, half) owns half of the columns
+// of row `row` of the tile = TMEM lane `row`: the "A-fill" of a layer reads the previous layer's accumulator row
+// from TMEM (or the gathered features), applies bias / activation in fp32 registers, splits into tf32 hi + lo and
+// stores into the K-major operand tile in shared memory; weights arrive pre-split and pre-tiled by TMA.
 // =================================================================================================
 namespace tmb {
 
-constexpr int kKC = 32;       // K columns per operand chunk
+constexpr int kKC = 32;           // K columns per operand chunk
 constexpr int kTcThreads = 256;   // 128 rows x 2 column halves
+constexpr int kSlabFloats = 128 * kKC;
 
-struct TcLin { int64_t w, b; int K8, N16; };   // chunk c at w + c * 2 * N16 * kKC floats: [hi tile | lo tile]; bias[N16] at b
+struct TcLin { int64_t w; int b, K8, N16; };   // chunk c at w + c * 2 * N16 * kKC floats: [hi tile | lo tile]; bias at cst[b]
 struct TcLayout {
     int D, Ed, H, M, ev, use_temporal, if_cat;
     TcLin evt, g0, g2, w1, w2, a0, a3, m0, m3;
-    int64_t w5, b5, freq, phase, total;
+    int w5, b5, freq, phase, n_cst;     // offsets inside the constant block (biases, MLP.5, TimeEncode parameters)
+    int64_t cst, total;
 };
 
 __host__ __device__ static inline int r8(int x) { return (x + 7) & ~7; }
@@ -115,27 +121,26 @@ TcLayout make_tc_layout(const tm_encoder_desc &d) {
     L.D = d.node_dim; L.Ed = d.edge_dim; L.H = d.hid_dim; L.use_temporal = d.use_temporal; L.if_cat = d.if_cat;
     L.M = d.if_cat ? d.hid_dim + 12 : d.hid_dim; L.ev = L.Ed + 3 + L.D;
     int64_t o = 0;
+    int co = 0;
     auto lin = [&](int K, int N) {
         TcLin l; l.K8 = r8(K); l.N16 = r16(N);
         const int nch = (l.K8 + kKC - 1) / kKC;
-        l.w = o; o += (int64_t)nch * 2 * l.N16 * kKC; l.b = o; o += l.N16;
+        l.w = o; o += (int64_t)nch * 2 * l.N16 * kKC; l.b = co; co += l.N16;
         return l;
     };
     L.evt = lin(L.ev, L.D); L.g0 = lin(L.D, L.H); L.g2 = lin(L.H, L.H);
     L.w1 = lin(2 * L.H, 2 * L.H); L.w2 = lin(2 * L.H, 2 * L.H); L.a0 = lin(2 * L.H, L.H); L.a3 = lin(L.H, L.H);
     L.m0 = lin(L.M, L.M); L.m3 = lin(L.M, L.H);
-    L.w5 = o; o += r16(L.H); L.b5 = o; o += 16;
-    L.freq = o; o += r16(L.D); L.phase = o; o += r16(L.D);
-    L.total = (o + 3) & ~(int64_t)3;
+    L.w5 = co; co += r16(L.H); L.b5 = co; co += 16;
+    L.freq = co; co += r16(L.D); L.phase = co; co += r16(L.D);
+    L.n_cst = co; L.cst = o; L.total = o + co;
     return L;
 }
 
 // host: nn.Linear weight [N][K] -> per K chunk the [hi | lo] operand tiles in the tc.cuh layout (R = N16 rows)
-void pack_tc_lin(const TcLin &l, int K, int N, const float *w, const float *b, float *blob) {
+void pack_tc_lin(const TcLayout &L, const TcLin &l, int K, int N, const float *w, const float *b, float *blob) {
     const int nch = (l.K8 + kKC - 1) / kKC;
     for (int c = 0; c < nch; ++c) {
-        const int kc = std::min(kKC, l.K8 - c * kKC);
-        (void)kc;
         float *hi = blob + l.w + (int64_t)c * 2 * l.N16 * kKC, *lo = hi + (int64_t)l.N16 * kKC;
         for (int n = 0; n < N; ++n)
             for (int kk = 0; kk < kKC && c * kKC + kk < K; ++kk) {
@@ -146,25 +151,39 @@ void pack_tc_lin(const TcLin &l, int K, int N, const float *w, const float *b, f
                 hi[off] = h; lo[off] = x - h;
             }
     }
-    for (int n = 0; n < N; ++n) blob[l.b + n] = b[n];
+    for (int n = 0; n < N; ++n) blob[L.cst + l.b + n] = b[n];
 }
 
-// the static per-tile sequence of weight chunks of one kernel (streamed by TMA, double buffered)
+// static per-tile schedules: weight chunks (TMA, global -> smem) and, for the motif kernel, the updated_feature
+// slabs a round's A-fill reads (TMA into the staging buffer one round ahead)
 struct ChunkTab { int n; int64_t off[40]; int bytes[40]; };
+struct StageTab { int8_t ns[40]; int8_t pos[40][2]; int8_t ch[40][2]; };
 
 struct TcCtx {
     uint8_t *a[2][2];      // [m-block][hi, lo]  128 x kKC fp32 operand tiles
-    uint8_t *b[2];         // double-buffered weight chunk [hi | lo]
-    uint64_t *mma_bar, *b_bar;   // b_bar[2]
-    uint32_t mma_phase;
+    uint8_t *b[2];         // weight chunk buffer(s) [hi | lo]
+    float *stage;          // 2 slabs of updated_feature columns (motif kernel)
+    const float *cst;      // constant block in shared memory
+    uint64_t *mma_bar, *b_bar, *s_bar;
+    uint32_t mma_phase, s_phase;
+    int nbuf, ri;          // weight buffers (1 or 2); round index inside the tile
+    long long *dbg;        // optional per-chunk timestamps of CTA 0 (TEMPME_TC_TIMING), 6 slots per chunk
     int64_t seq, total;    // running chunk counter of this CTA / chunks it will consume in total
-    const float *blob;
+    const float *blob, *F;
 };
 
-__device__ __forceinline__ void tc_prefetch(const TcCtx &x, const ChunkTab &tab, int64_t seq) {   // thread 0 only
-    const int i = (int)(seq % tab.n), buf = (int)(seq & 1);
+__device__ __forceinline__ void tc_prefetch_b(const TcCtx &x, const ChunkTab &tab, int64_t seq) {   // thread 0 only
+    const int i = (int)(seq % tab.n), buf = x.nbuf == 2 ? (int)(seq & 1) : 0;
     tc::mbar_expect_tx(x.b_bar + buf, (uint32_t)tab.bytes[i]);
     tc::tma_load_1d(x.b[buf], x.blob + tab.off[i], (uint32_t)tab.bytes[i], x.b_bar + buf);
+}
+__device__ __forceinline__ void tc_prefetch_stage(const TcCtx &x, const ChunkTab &tab, const StageTab &st, int64_t seq) {   // thread 0 only
+    const int i = (int)(seq % tab.n), ns = st.ns[i];
+    if (!ns) return;
+    const int64_t tile = blockIdx.x + (seq / tab.n) * gridDim.x;
+    tc::mbar_expect_tx(x.s_bar, (uint32_t)(ns * kSlabFloats * 4));
+    for (int k = 0; k < ns; ++k)
+        tc::tma_load_1d(x.stage + k * kSlabFloats, x.F + ((tile * 3 + st.pos[i][k]) * 4 + st.ch[i][k]) * kSlabFloats, kSlabFloats * 4, x.s_bar);
 }
 
 __device__ __forceinline__ void store_a4(const TcCtx &x, int mb, int row, int k, float4 v) {
@@ -174,24 +193,34 @@ __device__ __forceinline__ void store_a4(const TcCtx &x, int mb, int row, int k,
     *reinterpret_cast<float4 *>(x.a[mb][0] + off) = h;
     *reinterpret_cast<float4 *>(x.a[mb][1] + off) = l;
 }
+// updated_feature slab element (row, k): 128-byte rows with the 16-byte pieces XOR-swizzled by the row (bank spread)
+__device__ __forceinline__ int slab_off(int row, int k) { return row * kKC + ((((k >> 2) ^ (row & 7)) << 2) | (k & 3)); }
 
 // One Linear over MB row blocks that share the weight: acc[mb] (TMEM column) = A[mb] * W^T, K streamed in chunks
 // of kKC columns.  fill(c, kcols) writes this thread's share of columns [c*kKC, c*kKC + kcols) of every A block.
 template <int MB, typename Fill>
-__device__ __forceinline__ void tc_linear(const TcLin l, TcCtx &x, const ChunkTab &tab, uint32_t tmem, const int (&acc_col)[MB], Fill fill) {
+__device__ __forceinline__ void tc_linear(const TcLin l, TcCtx &x, const ChunkTab &tab, const StageTab *st, uint32_t tmem,
+                                          const int (&acc_col)[MB], Fill fill) {
     const int t = threadIdx.x;
     const int nch = (l.K8 + kKC - 1) / kKC;
     const uint32_t idesc = tc::idesc_tf32(128, l.N16);
     for (int c = 0; c < nch; ++c) {
         const int kcols = min(kKC, l.K8 - c * kKC);
-        if (t == 0 && x.seq + 1 < x.total) tc_prefetch(x, tab, x.seq + 1);    // its buffer was released by the MMA wait of chunk seq-1
+        const bool tim = x.dbg && blockIdx.x == 0 && t == 0 && x.seq < 64;
+        if (tim) x.dbg[x.seq * 6 + 0] = clock64();
+        if (x.nbuf == 2 && t == 0 && x.seq + 1 < x.total) tc_prefetch_b(x, tab, x.seq + 1);   // buffer released by the MMA wait of chunk seq-1
+        if (st && st->ns[x.ri]) { tc::mbar_wait(x.s_bar, x.s_phase); x.s_phase ^= 1; }        // this round's slabs have landed
         fill(c, kcols);
+        if (tim) x.dbg[x.seq * 6 + 1] = clock64();
         tc::fence_smem_to_async();
         tc::fence_before_sync();
         __syncthreads();
         if (t == 0) {
-            const int buf = (int)(x.seq & 1);
-            tc::mbar_wait(x.b_bar + buf, (uint32_t)((x.seq >> 1) & 1));           // weight chunk has landed (TMA)
+            if (st && x.seq + 1 < x.total) tc_prefetch_stage(x, tab, *st, x.seq + 1);         // staging buffer is free again
+            const int buf = x.nbuf == 2 ? (int)(x.seq & 1) : 0;
+            if (tim) x.dbg[x.seq * 6 + 2] = clock64();
+            tc::mbar_wait(x.b_bar + buf, (uint32_t)((x.nbuf == 2 ? (x.seq >> 1) : x.seq) & 1));   // weight chunk has landed (TMA)
+            if (tim) x.dbg[x.seq * 6 + 3] = clock64();
             tc::fence_after_sync();
             const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)l.N16 * 16;
             const uint32_t b_hi = tc::smem_u32(x.b[buf]), b_lo = b_hi + (uint32_t)l.N16 * kKC * 4;
@@ -207,10 +236,14 @@ __device__ __forceinline__ void tc_linear(const TcLin l, TcCtx &x, const ChunkTa
                 }
             }
             tc::mma_commit(x.mma_bar);
+            if (tim) x.dbg[x.seq * 6 + 4] = clock64();
         }
         tc::mbar_wait(x.mma_bar, x.mma_phase);
+        if (tim) x.dbg[x.seq * 6 + 5] = clock64();
         x.mma_phase ^= 1;
+        if (x.nbuf == 1 && t == 0 && x.seq + 1 < x.total) tc_prefetch_b(x, tab, x.seq + 1);   // single buffer: refill right after the MMA released it
         x.seq++;
+        x.ri = x.ri + 1 == tab.n ? 0 : x.ri + 1;
         tc::fence_after_sync();
     }
 }
@@ -223,39 +256,61 @@ struct TcArgs {
     const uint8_t *cat;
     const float *cut, *eid, *node_feat, *edge_feat, *std_;
     int64_t n_node_rows, n_edge_rows;
-    float *F;                                // [3 * slab][2H] updated_feature rows of the slab
+    float *F;                                // updated_feature slabs of the slab of motifs: [tile][pos][chunk][128][kKC]
     float *scores;
     uint32_t tmem_cols;
-    int b_bytes;                             // bytes of one weight-chunk buffer
+    int b_bytes, nbuf;                       // bytes of one weight-chunk buffer, number of buffers
+    long long *dbg;
 };
 
-__device__ __forceinline__ void tc_setup(uint8_t *smem, TcCtx &x, const TcArgs &a, int mb, uint64_t *bars, uint32_t *tmem_slot,
-                                         uint32_t tmem_cols, const float *blob) {
+__device__ __forceinline__ void tc_setup(uint8_t *smem, TcCtx &x, const TcLayout &L, const TcArgs &a, int mb, bool stage, uint64_t *bars,
+                                         uint32_t *tmem_slot, const float *blob) {
     uint8_t *p = smem;
     for (int m = 0; m < 2; ++m)
         for (int h = 0; h < 2; ++h) { x.a[m][h] = p; if (m < mb) p += 128 * kKC * 4; }
-    x.b[0] = p; x.b[1] = p + a.b_bytes;
-    x.mma_bar = bars; x.b_bar = bars + 1;
-    x.mma_phase = 0; x.seq = 0; x.blob = blob;
-    if (threadIdx.x == 0) { tc::mbar_init(bars, 1); tc::mbar_init(bars + 1, 1); tc::mbar_init(bars + 2, 1); }
-    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
+    x.b[0] = p; p += a.b_bytes; x.b[1] = p; if (a.nbuf == 2) p += a.b_bytes;
+    x.stage = reinterpret_cast<float *>(p); if (stage) p += 2 * kSlabFloats * 4;
+    float *cst = reinterpret_cast<float *>(p);
+    x.cst = cst;
+    x.mma_bar = bars; x.b_bar = bars + 1; x.s_bar = bars + 3;
+    x.mma_phase = 0; x.s_phase = 0; x.seq = 0; x.ri = 0; x.nbuf = a.nbuf; x.blob = blob; x.F = a.F; x.dbg = a.dbg;
+    for (int i = threadIdx.x; i < L.n_cst; i += blockDim.x) cst[i] = __ldg(blob + L.cst + i);
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) tc::mbar_init(bars + i, 1); }
+    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc(tmem_slot, a.tmem_cols);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
 }
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+// cos(x) for the TimeEncode arguments (up to ~1e8 and beyond): beyond the library's fast range the argument is
+// reduced in float64 with a two-term pi/2 (FMA Cody-Waite; exact to ~1e-16 for |x| < 1e15), then the short
+// sin/cos kernels run on |r| <= pi/4.  Result within ~1 ulp of the exact cosine of the fp32 argument, like cosf.
+__device__ __forceinline__ float cos_accurate(float x) {
+    const float ax = fabsf(x);
+    if (ax <= 105615.0f || !(ax < 1.0e15f)) return cosf(x);
+    const double xd = (double)x;
+    const double q = rint(xd * 0.63661977236758134308);
+    double r = fma(-q, 1.5707963267948966192, xd);
+    r = fma(-q, 6.123233995736766036e-17, r);
+    float sn, cs;
+    sincosf((float)r, &sn, &cs);
+    const int n = (int)((long long)q & 3);
+    return n == 0 ? cs : n == 1 ? -sn : n == 2 ? -cs : sn;
+}
 
 // ---------------------------------------------------------------------------------------------
-// event kernel: 256 threads = 128 event rows x 2 column halves; rows r = 3 * motif + position of the slab
+// event kernel: rows r = 3 * motif + position of the slab
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads)
 event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ blob, const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[3];
+    __shared__ __align__(8) uint64_t bars[4];
     __shared__ uint32_t tmem_slot;
     TcCtx x;
-    tc_setup(smem, x, a, 2, bars, &tmem_slot, a.tmem_cols, blob);
+    tc_setup(smem, x, L, a, 2, false, bars, &tmem_slot, blob);
     const int t = threadIdx.x, warp = t >> 5, row = t & 127, half = t >> 7, kb = 16 * half;
     const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int H = L.H, D = L.D, Ed = L.Ed;
@@ -263,14 +318,15 @@ event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
     const int64_t n_rows = 3 * min(a.slab, a.n_motifs - a.m_begin);
     const int64_t n_tiles = (n_rows + 127) / 128;
     x.total = ((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * tab.n;
-    if (t == 0 && x.total > 0) tc_prefetch(x, tab, 0);
-    const float *__restrict__ freq = blob + L.freq, *__restrict__ phs = blob + L.phase;
+    if (t == 0 && x.total > 0) tc_prefetch_b(x, tab, 0);
+    const float *cst = x.cst;
+    const bool ed_vec = (Ed & 3) == 0, d_vec = (D & 3) == 0;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t r = tile * 128 + row;
         const bool live = r < n_rows;
-        const int64_t gm = a.m_begin + (live ? r / 3 : 0);
-        const int pos = live ? (int)(r % 3) : 0;
+        const int64_t ml = live ? r / 3 : 0, gm = a.m_begin + ml;
+        const int pos = live ? (int)(r - 3 * ml) : 0;
         int64_t e = 0, ns = 0, nt = 0; float dt = 0.f;
         if (live) {
             e = a.eidx[gm * 3 + pos]; ns = a.nodes[gm * 6 + 2 * pos]; nt = a.nodes[gm * 6 + 2 * pos + 1];
@@ -282,18 +338,39 @@ event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
         auto xval = [&](int j) -> float {                                              // event_features column j (:179)
             if (j < Ed) return e_ok ? __ldg(ef + j) : 0.f;
             if (j < Ed + 3) return (live && ei) ? __ldg(ei + (j - Ed)) : 0.f;
-            if (j < L.ev) { const int k = j - Ed - 3; return live ? cosf(__fadd_rn(__fmul_rn(dt, __ldg(freq + k)), __ldg(phs + k))) : 0.f; }
+            if (j < L.ev) { const int k = j - Ed - 3; return live ? cos_accurate(__fadd_rn(__fmul_rn(dt, cst[L.freq + k]), cst[L.phase + k])) : 0.f; }   // :55-58
             return 0.f;
         };
         // ---- lin_event (:93)
         { const int acc[1] = {colE};
-          tc_linear<1>(L.evt, x, tab, tmem, acc, [&](int c, int kcols) {
-              for (int k = kb; k < min(kb + 16, kcols); k += 4) { const int j = c * kKC + k; store_a4(x, 0, row, k, make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3))); }
+          tc_linear<1>(L.evt, x, tab, nullptr, tmem, acc, [&](int c, int kcols) {
+              float4 v[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                  const int k = kb + 4 * g, j = c * kKC + k;
+                  if (k >= kcols) { v[g] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+                  if (ed_vec && j + 3 < Ed) v[g] = e_ok ? ldg4(ef + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  else v[g] = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g) if (kb + 4 * g < kcols) store_a4(x, 0, row, kb + 4 * g, v[g]);
           }); }
         // ---- event_conv.MLP.0 on src + relu(tgt + event) and tgt + relu(src + event) (:94-95,182-184)
         { const int acc[2] = {colZ, colZ + H};
-          tc_linear<2>(L.g0, x, tab, tmem, acc, [&](int c, int kcols) {
+          tc_linear<2>(L.g0, x, tab, nullptr, tmem, acc, [&](int c, int kcols) {
               if (kb < kcols) {
+                  float sv[16], gv[16];
+#pragma unroll
+                  for (int k = 0; k < 16; k += 4) {       // issue the gathers first (explainer.py:348-351)
+                      const int j = c * kKC + kb + k;
+                      if (d_vec && j + 3 < D) {
+                          const float4 s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f), g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                          sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
+                      } else {
+#pragma unroll
+                          for (int i = 0; i < 4; ++i) { sv[k + i] = (j + i < D && s_ok) ? __ldg(sf + j + i) : 0.f; gv[k + i] = (j + i < D && t_ok) ? __ldg(tf + j + i) : 0.f; }
+                      }
+                  }
                   float ev[16];
                   tc::tmem_ld16(tmem + lane_base + colE + c * kKC + kb, ev);
 #pragma unroll
@@ -303,10 +380,9 @@ event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
 #pragma unroll
                       for (int i = 0; i < 4; ++i) {
                           const int j = c * kKC + kb + k + i;
-                          const float e_ = j < D ? ev[k + i] + __ldg(blob + L.evt.b + j) : 0.f;
-                          const float s_ = (j < D && s_ok) ? __ldg(sf + j) : 0.f, g_ = (j < D && t_ok) ? __ldg(tf + j) : 0.f;
-                          hs[i] = j < D ? s_ + fmaxf(g_ + e_, 0.f) : 0.f;
-                          hg[i] = j < D ? g_ + fmaxf(s_ + e_, 0.f) : 0.f;
+                          const float e_ = j < D ? ev[k + i] + cst[L.evt.b + j] : 0.f;
+                          hs[i] = j < D ? sv[k + i] + fmaxf(gv[k + i] + e_, 0.f) : 0.f;
+                          hg[i] = j < D ? gv[k + i] + fmaxf(sv[k + i] + e_, 0.f) : 0.f;
                       }
                       store_a4(x, 0, row, kb + k, make_float4(hs[0], hs[1], hs[2], hs[3]));
                       store_a4(x, 1, row, kb + k, make_float4(hg[0], hg[1], hg[2], hg[3]));
@@ -315,7 +391,7 @@ event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
           }); }
         // ---- event_conv.MLP.2 (:84)
         { const int acc[2] = {colF, colF + H};
-          tc_linear<2>(L.g2, x, tab, tmem, acc, [&](int c, int kcols) {
+          tc_linear<2>(L.g2, x, tab, nullptr, tmem, acc, [&](int c, int kcols) {
               (void)kcols;
 #pragma unroll
               for (int mb = 0; mb < 2; ++mb) {
@@ -323,22 +399,25 @@ event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
                   tc::tmem_ld16(tmem + lane_base + colZ + mb * H + c * kKC + kb, z);
 #pragma unroll
                   for (int k = 0; k < 16; k += 4) {
-                      const float4 bb = ldg4(blob + L.g0.b + c * kKC + kb + k);
+                      const float4 bb = lds4(cst + L.g0.b + c * kKC + kb + k);
                       store_a4(x, mb, row, kb + k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
                   }
               }
           }); }
-        // ---- updated_feature row = [MLP(src side) | MLP(tgt side)] (:185): half h stores columns [h*H, h*H + H)
+        // ---- updated_feature row = [MLP(src side) | MLP(tgt side)] (:185): half h owns columns [h*H, h*H + H), i.e.
+        //      column chunks 2h and 2h+1 of the (motif tile, position) slabs
         {
-            float *fo = a.F + (live ? r : 0) * (2 * H) + half * H;
+            const int mrow = (int)(ml & 127);
+            float *fo = a.F + (((ml >> 7) * 3 + pos) * 4 + 2 * half) * kSlabFloats;
             for (int c0 = 0; c0 < H; c0 += 16) {
                 float v[16];
                 tc::tmem_ld16(tmem + lane_base + colF + half * H + c0, v);
                 if (live) {
+                    float *fc = fo + (c0 >> 5) * kSlabFloats;
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
-                        const float4 bb = ldg4(blob + L.g2.b + c0 + i);
-                        *reinterpret_cast<float4 *>(fo + c0 + i) = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
+                        const float4 bb = lds4(cst + L.g2.b + c0 + i);
+                        *reinterpret_cast<float4 *>(fc + slab_off(mrow, (c0 & 31) + i)) = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
                     }
                 }
             }
@@ -356,13 +435,13 @@ event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
 // motif kernel: 256 threads = 128 motifs x 2 column halves.  TMEM: X = [0, 2H), Y = [2H, 4H).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads)
-motif_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ blob, const TcArgs a) {
+motif_tc_kernel(const TcLayout L, const ChunkTab tab, const StageTab stab, const float *__restrict__ blob, const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[3];
+    __shared__ __align__(8) uint64_t bars[4];
     __shared__ uint32_t tmem_slot;
     __shared__ float part[2][128];
     TcCtx x;
-    tc_setup(smem, x, a, 1, bars, &tmem_slot, a.tmem_cols, blob);
+    tc_setup(smem, x, L, a, 1, true, bars, &tmem_slot, blob);
     const int t = threadIdx.x, warp = t >> 5, row = t & 127, half = t >> 7, kb = 16 * half;
     const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int H = L.H, H2 = 2 * L.H;
@@ -370,7 +449,9 @@ motif_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
     const int64_t n_m = min(a.slab, a.n_motifs - a.m_begin);
     const int64_t n_tiles = (n_m + 127) / 128;
     x.total = ((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * tab.n;
-    if (t == 0 && x.total > 0) tc_prefetch(x, tab, 0);
+    if (t == 0 && x.total > 0) { tc_prefetch_b(x, tab, 0); tc_prefetch_stage(x, tab, stab, 0); }
+    const float *cst = x.cst;
+    const float *sg0 = x.stage, *sg1 = x.stage + kSlabFloats;
     auto both_halves = [&](float v) {      // sum of the two column-half partials of every row
         part[half][row] = v;
         __syncthreads();
@@ -383,8 +464,6 @@ motif_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
         const int64_t ml = tile * 128 + row;         // motif index inside the slab
         const bool live = ml < n_m;
         const int64_t gm = a.m_begin + (live ? ml : 0);
-        const float *f0 = a.F + (live ? ml : 0) * 3 * H2, *f1 = f0 + H2, *f2 = f1 + H2;
-        auto load4 = [&](const float *p) { return live ? ldg4(p) : make_float4(0.f, 0.f, 0.f, 0.f); };
         // dot over this thread's column half of (X + b1) . (Y + b2)
         auto score_half = [&]() {
             float sc = 0.f;
@@ -393,25 +472,22 @@ motif_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
                 tc::tmem_ld16(tmem + lane_base + colX + c0, p); tc::tmem_ld16(tmem + lane_base + colY + c0, q);
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
-                    const float4 b1 = ldg4(blob + L.w1.b + c0 + i), b2 = ldg4(blob + L.w2.b + c0 + i);
+                    const float4 b1 = lds4(cst + L.w1.b + c0 + i), b2 = lds4(cst + L.w2.b + c0 + i);
                     sc = fmaf(p[i] + b1.x, q[i] + b2.x, sc); sc = fmaf(p[i + 1] + b1.y, q[i + 1] + b2.y, sc);
                     sc = fmaf(p[i + 2] + b1.z, q[i + 2] + b2.z, sc); sc = fmaf(p[i + 3] + b1.w, q[i + 3] + b2.w, sc);
                 }
             }
             return sc;
         };
+        auto copy_slab = [&](int c, int kcols) { (void)c; (void)kcols;      // A row = the staged updated_feature columns
+#pragma unroll
+            for (int k = kb; k < kb + 16; k += 4) store_a4(x, 0, row, k, lds4(sg0 + slab_off(row, k))); };
         // ---- Wp = W1 f2 -> X ; Wq_0 = W2 f_0 -> Y ; score_0 ; Wq_1 = W2 f_1 -> Y ; score_1 (:806-808)
-        { const int acc[1] = {colX};
-          tc_linear<1>(L.w1, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
-              for (int k = kb; k < kb + 16; k += 4) store_a4(x, 0, row, k, load4(f2 + c * kKC + k)); }); }
-        { const int acc[1] = {colY};
-          tc_linear<1>(L.w2, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
-              for (int k = kb; k < kb + 16; k += 4) store_a4(x, 0, row, k, load4(f0 + c * kKC + k)); }); }
+        { const int acc[1] = {colX}; tc_linear<1>(L.w1, x, tab, &stab, tmem, acc, copy_slab); }
+        { const int acc[1] = {colY}; tc_linear<1>(L.w2, x, tab, &stab, tmem, acc, copy_slab); }
         float s0 = both_halves(score_half());
         tc::fence_before_sync(); __syncthreads(); tc::fence_after_sync();        // Y is about to be overwritten
-        { const int acc[1] = {colY};
-          tc_linear<1>(L.w2, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
-              for (int k = kb; k < kb + 16; k += 4) store_a4(x, 0, row, k, load4(f1 + c * kKC + k)); }); }
+        { const int acc[1] = {colY}; tc_linear<1>(L.w2, x, tab, &stab, tmem, acc, copy_slab); }
         float s1 = both_halves(score_half());
         tc::fence_before_sync(); __syncthreads(); tc::fence_after_sync();
         // ---- temporal weighting + softmax (:811-839)
@@ -426,35 +502,36 @@ motif_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
         const float al0 = e0 / (e0 + e1), al1 = e1 / (e0 + e1);
         // ---- sum_k alpha_k (W2 f_k + b2) = W2 (alpha_0 f_0 + alpha_1 f_1) + b2 since alpha sums to one -> Y (:841)
         { const int acc[1] = {colY};
-          tc_linear<1>(L.w2, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
+          tc_linear<1>(L.w2, x, tab, &stab, tmem, acc, [&](int c, int kcols) { (void)c; (void)kcols;
+#pragma unroll
               for (int k = kb; k < kb + 16; k += 4) {
-                  const float4 u = load4(f0 + c * kKC + k), v = load4(f1 + c * kKC + k);
+                  const float4 u = lds4(sg0 + slab_off(row, k)), v = lds4(sg1 + slab_off(row, k));
                   store_a4(x, 0, row, k, make_float4(fmaf(al0, u.x, al1 * v.x), fmaf(al0, u.y, al1 * v.y), fmaf(al0, u.z, al1 * v.z), fmaf(al0, u.w, al1 * v.w)));
               } }); }
         // ---- attention.MLP.0 on f2 + (Y + b2) -> A1 (:842-843)
         { const int acc[1] = {colA1};
-          tc_linear<1>(L.a0, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
+          tc_linear<1>(L.a0, x, tab, &stab, tmem, acc, [&](int c, int kcols) { (void)kcols;
               float q[16];
               tc::tmem_ld16(tmem + lane_base + colY + c * kKC + kb, q);
 #pragma unroll
               for (int k = 0; k < 16; k += 4) {
-                  const float4 f = load4(f2 + c * kKC + kb + k), b2 = ldg4(blob + L.w2.b + c * kKC + kb + k);
+                  const float4 f = lds4(sg0 + slab_off(row, kb + k)), b2 = lds4(cst + L.w2.b + c * kKC + kb + k);
                   store_a4(x, 0, row, kb + k, make_float4(f.x + (q[k] + b2.x), f.y + (q[k + 1] + b2.y), f.z + (q[k + 2] + b2.z), f.w + (q[k + 3] + b2.w)));
               } }); }
         // ---- attention.MLP.3 -> A2
         { const int acc[1] = {colA2};
-          tc_linear<1>(L.a3, x, tab, tmem, acc, [&](int c, int kcols) { (void)kcols;
+          tc_linear<1>(L.a3, x, tab, &stab, tmem, acc, [&](int c, int kcols) { (void)kcols;
               float z[16];
               tc::tmem_ld16(tmem + lane_base + colA1 + c * kKC + kb, z);
 #pragma unroll
               for (int k = 0; k < 16; k += 4) {
-                  const float4 bb = ldg4(blob + L.a0.b + c * kKC + kb + k);
+                  const float4 bb = lds4(cst + L.a0.b + c * kKC + kb + k);
                   store_a4(x, 0, row, kb + k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
               } }); }
         // ---- MLP.0 on [attention out | one-hot(category)] -> M0 (:195-200)
         const int cat = (L.if_cat && live && a.cat) ? (int)a.cat[gm] : -1;
         { const int acc[1] = {colM0};
-          tc_linear<1>(L.m0, x, tab, tmem, acc, [&](int c, int kcols) {
+          tc_linear<1>(L.m0, x, tab, &stab, tmem, acc, [&](int c, int kcols) {
               if (kb < kcols) {
                   float z[16];
                   tc::tmem_ld16(tmem + lane_base + colA2 + min(c * kKC + kb, H - 16), z);   // columns >= H come from the one-hot
@@ -464,14 +541,14 @@ motif_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
 #pragma unroll
                       for (int i = 0; i < 4; ++i) {
                           const int j = c * kKC + kb + k + i;
-                          v[i] = j < H ? z[k + i] + __ldg(blob + L.a3.b + j) : (j - H == cat ? 1.f : 0.f);
+                          v[i] = j < H ? z[k + i] + cst[L.a3.b + j] : (j - H == cat ? 1.f : 0.f);
                       }
                       store_a4(x, 0, row, kb + k, make_float4(v[0], v[1], v[2], v[3]));
                   }
               } }); }
         // ---- MLP.3 -> M1
         { const int acc[1] = {colM1};
-          tc_linear<1>(L.m3, x, tab, tmem, acc, [&](int c, int kcols) {
+          tc_linear<1>(L.m3, x, tab, &stab, tmem, acc, [&](int c, int kcols) {
               if (kb < kcols) {
                   float z[16];
                   tc::tmem_ld16(tmem + lane_base + colM0 + c * kKC + kb, z);
@@ -479,7 +556,7 @@ motif_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
                   for (int k = 0; k < 16; k += 4) {
                       float v[4];
 #pragma unroll
-                      for (int i = 0; i < 4; ++i) { const int j = c * kKC + kb + k + i; v[i] = j < L.M ? fmaxf(z[k + i] + __ldg(blob + L.m0.b + j), 0.f) : 0.f; }
+                      for (int i = 0; i < 4; ++i) { const int j = c * kKC + kb + k + i; v[i] = j < L.M ? fmaxf(z[k + i] + cst[L.m0.b + j], 0.f) : 0.f; }
                       store_a4(x, 0, row, kb + k, make_float4(v[0], v[1], v[2], v[3]));
                   }
               } }); }
@@ -489,10 +566,10 @@ motif_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
             float z[16];
             tc::tmem_ld16(tmem + lane_base + colM1 + c0, z);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) z5 = fmaf(fmaxf(z[i] + __ldg(blob + L.m3.b + c0 + i), 0.f), __ldg(blob + L.w5 + c0 + i), z5);
+            for (int i = 0; i < 16; ++i) z5 = fmaf(fmaxf(z[i] + cst[L.m3.b + c0 + i], 0.f), cst[L.w5 + c0 + i], z5);
         }
         z5 = both_halves(z5);
-        if (live && half == 0) a.scores[gm] = 1.f / (1.f + expf(-(z5 + __ldg(blob + L.b5))));
+        if (live && half == 0) a.scores[gm] = 1.f / (1.f + expf(-(z5 + cst[L.b5])));
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
@@ -514,22 +591,36 @@ int tc_pack(const tm_encoder_desc &d, const tm_encoder_params &p, float *blob) {
     const TcLayout L = make_tc_layout(d);
     memset(blob, 0, sizeof(float) * L.total);
     const int H = L.H, D = L.D, M = L.M;
-    pack_tc_lin(L.evt, L.ev, D, p.lin_event_w, p.lin_event_b, blob);
-    pack_tc_lin(L.g0, D, H, p.gcn0_w, p.gcn0_b, blob);
-    pack_tc_lin(L.g2, H, H, p.gcn2_w, p.gcn2_b, blob);
-    pack_tc_lin(L.w1, 2 * H, 2 * H, p.att_w1_w, p.att_w1_b, blob);
-    pack_tc_lin(L.w2, 2 * H, 2 * H, p.att_w2_w, p.att_w2_b, blob);
-    pack_tc_lin(L.a0, 2 * H, H, p.att_mlp0_w, p.att_mlp0_b, blob);
-    pack_tc_lin(L.a3, H, H, p.att_mlp3_w, p.att_mlp3_b, blob);
-    pack_tc_lin(L.m0, M, M, p.mlp0_w, p.mlp0_b, blob);
-    pack_tc_lin(L.m3, M, H, p.mlp3_w, p.mlp3_b, blob);
-    for (int k = 0; k < H; ++k) blob[L.w5 + k] = p.mlp5_w[k];
-    blob[L.b5] = p.mlp5_b[0];
-    for (int k = 0; k < D; ++k) { blob[L.freq + k] = p.basis_freq[k]; blob[L.phase + k] = p.phase[k]; }
+    pack_tc_lin(L, L.evt, L.ev, D, p.lin_event_w, p.lin_event_b, blob);
+    pack_tc_lin(L, L.g0, D, H, p.gcn0_w, p.gcn0_b, blob);
+    pack_tc_lin(L, L.g2, H, H, p.gcn2_w, p.gcn2_b, blob);
+    pack_tc_lin(L, L.w1, 2 * H, 2 * H, p.att_w1_w, p.att_w1_b, blob);
+    pack_tc_lin(L, L.w2, 2 * H, 2 * H, p.att_w2_w, p.att_w2_b, blob);
+    pack_tc_lin(L, L.a0, 2 * H, H, p.att_mlp0_w, p.att_mlp0_b, blob);
+    pack_tc_lin(L, L.a3, H, H, p.att_mlp3_w, p.att_mlp3_b, blob);
+    pack_tc_lin(L, L.m0, M, M, p.mlp0_w, p.mlp0_b, blob);
+    pack_tc_lin(L, L.m3, M, H, p.mlp3_w, p.mlp3_b, blob);
+    float *cst = blob + L.cst;
+    for (int k = 0; k < H; ++k) cst[L.w5 + k] = p.mlp5_w[k];
+    cst[L.b5] = p.mlp5_b[0];
+    for (int k = 0; k < D; ++k) { cst[L.freq + k] = p.basis_freq[k]; cst[L.phase + k] = p.phase[k]; }
     return TM_OK;
 }
 
-int64_t tc_slab_motifs() { return 48 * 1024; }     // F slab = 48k motifs * 1.5 KB = 72 MB: stays in the 126 MB L2 between the two kernels
+// Motifs per slab: a whole number of waves of the motif kernel (2 CTAs per SM x 128 motifs), small enough that the
+// slab's updated_feature rows (1.5 KB per motif) stay in the 126 MB L2 between the event and the motif kernel.
+int64_t tc_slab_motifs() {
+    static int64_t v = 0;
+    if (!v) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const char *e = getenv("TEMPME_TC_SLAB_WAVES");
+        const int waves = e ? std::max(1, atoi(e)) : 1;
+        v = (int64_t)sms * 2 * 128 * waves;
+    }
+    return v;
+}
 
 // std_ = per-batch std (already computed); F = workspace for one slab
 int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
@@ -537,17 +628,29 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
                     int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
                     int device, cudaStream_t st) {
     const TcLayout L = make_tc_layout(d);
+    if (L.H != 64) { set_error("tc_encode_score: hid_dim must be 64"); return TM_ERR_UNSUPPORTED; }
     ChunkTab te, tm;
+    StageTab stg;
+    memset(&stg, 0, sizeof stg);
     te.n = tm.n = 0;
-    auto push = [](ChunkTab &tab, const TcLin &l) {
+    auto push = [&](ChunkTab &tab, const TcLin &l, int npos, int p0, int p1) {
         const int nch = (l.K8 + kKC - 1) / kKC;
-        for (int c = 0; c < nch; ++c) { tab.off[tab.n] = l.w + (int64_t)c * 2 * l.N16 * kKC; tab.bytes[tab.n] = 2 * l.N16 * kKC * 4; tab.n++; }
+        for (int c = 0; c < nch; ++c) {
+            tab.off[tab.n] = l.w + (int64_t)c * 2 * l.N16 * kKC; tab.bytes[tab.n] = 2 * l.N16 * kKC * 4;
+            if (&tab == &tm) { stg.ns[tab.n] = (int8_t)npos; stg.pos[tab.n][0] = (int8_t)p0; stg.pos[tab.n][1] = (int8_t)p1; stg.ch[tab.n][0] = stg.ch[tab.n][1] = (int8_t)c; }
+            tab.n++;
+        }
     };
-    push(te, L.evt); push(te, L.g0); push(te, L.g2);
-    push(tm, L.w1); push(tm, L.w2); push(tm, L.w2); push(tm, L.w2); push(tm, L.a0); push(tm, L.a3); push(tm, L.m0); push(tm, L.m3);
-    if (te.n > 40 || tm.n > 40) { set_error("tc_encode_score: feature dims need more than 40 weight chunks"); return TM_ERR_UNSUPPORTED; }
+    const int n_evt = (L.evt.K8 + kKC - 1) / kKC + (L.g0.K8 + kKC - 1) / kKC + 2;
+    if (n_evt > 40) { set_error("tc_encode_score: feature dims need more than 40 weight chunks"); return TM_ERR_UNSUPPORTED; }
+    push(te, L.evt, 0, 0, 0); push(te, L.g0, 0, 0, 0); push(te, L.g2, 0, 0, 0);
+    push(tm, L.w1, 1, 2, 0); push(tm, L.w2, 1, 0, 0); push(tm, L.w2, 1, 1, 0); push(tm, L.w2, 2, 0, 1); push(tm, L.a0, 1, 2, 0);
+    push(tm, L.a3, 0, 0, 0); push(tm, L.m0, 0, 0, 0); push(tm, L.m3, 0, 0, 0);
     const int bb_e = 2 * std::max(r16(L.D), L.H) * kKC * 4, bb_m = 2 * std::max(2 * L.H, r16(L.M)) * kKC * 4;
-    const size_t smem_e = (size_t)4 * 128 * kKC * 4 + 2 * (size_t)bb_e, smem_m = (size_t)2 * 128 * kKC * 4 + 2 * (size_t)bb_m;
+    const size_t cst_b = (size_t)((L.n_cst + 31) & ~31) * 4;
+    const int nbuf_e = 2, nbuf_m = 1;
+    const size_t smem_e = (size_t)4 * 128 * kKC * 4 + (size_t)nbuf_e * bb_e + cst_b;
+    const size_t smem_m = (size_t)2 * 128 * kKC * 4 + (size_t)nbuf_m * bb_m + (size_t)2 * kSlabFloats * 4 + cst_b;
     uint32_t cols_e = 32, cols_m = 32;
     while ((int)cols_e < 2 * L.H + std::max(r16(L.D), 2 * L.H)) cols_e <<= 1;
     while ((int)cols_m < 4 * L.H) cols_m <<= 1;
@@ -562,18 +665,34 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     TcArgs a;
     a.n_motifs = B * W; a.W = W; a.group = group; a.slab = tc_slab_motifs(); a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
     a.eid = eid; a.node_feat = node_feat; a.edge_feat = edge_feat; a.std_ = std_; a.n_node_rows = n_node_rows; a.n_edge_rows = n_edge_rows;
-    a.F = F; a.scores = scores;
+    a.F = F; a.scores = scores; a.dbg = nullptr;
+    static long long *dbg_buf = nullptr;
+    const char *tim_env = getenv("TEMPME_TC_TIMING");
+    if (tim_env && !dbg_buf) cudaMalloc(&dbg_buf, 2 * 64 * 6 * sizeof(long long));
     const int ctas_e = (cols_e <= 256 && smem_e <= 110 * 1024) ? 2 : 1, ctas_m = (cols_m <= 256 && smem_m <= 110 * 1024) ? 2 : 1;
     for (int64_t m0 = 0; m0 < a.n_motifs; m0 += a.slab) {
         a.m_begin = m0;
         const int64_t nm = std::min(a.slab, a.n_motifs - m0);
         const int64_t tiles_e = (3 * nm + 127) / 128, tiles_m = (nm + 127) / 128;
-        a.tmem_cols = cols_e; a.b_bytes = bb_e;
+        a.tmem_cols = cols_e; a.b_bytes = bb_e; a.nbuf = nbuf_e; a.dbg = (tim_env && m0 == 0) ? dbg_buf : nullptr;
         event_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem_e, st>>>(L, te, d_blob_tc, a);
         TM_LAUNCH_CHECK();
-        a.tmem_cols = cols_m; a.b_bytes = bb_m;
-        motif_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_m, (int64_t)sms * ctas_m), kTcThreads, smem_m, st>>>(L, tm, d_blob_tc, a);
+        a.tmem_cols = cols_m; a.b_bytes = bb_m; a.nbuf = nbuf_m; a.dbg = (tim_env && m0 == 0) ? dbg_buf + 64 * 6 : nullptr;
+        motif_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_m, (int64_t)sms * ctas_m), kTcThreads, smem_m, st>>>(L, tm, stg, d_blob_tc, a);
         TM_LAUNCH_CHECK();
+    }
+    if (tim_env) {      // diagnostic only: dump the phase timeline of CTA 0 of the first slab
+        cudaStreamSynchronize(st);
+        std::vector<long long> h(2 * 64 * 6);
+        cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        for (int k = 0; k < 2; ++k) {
+            const int n = std::min(k ? tm.n : te.n, 64);
+            fprintf(stderr, "[tc timing] %s kernel, CTA 0, first tile: chunk: fill | sync | tma-wait | mma-issue | mma-done   (cycles)\n", k ? "motif" : "event");
+            for (int c = 0; c < n; ++c) {
+                const long long *dd = h.data() + (k * 64 + c) * 6;
+                fprintf(stderr, "  %2d: %6lld %6lld %6lld %6lld %6lld   round %6lld\n", c, dd[1] - dd[0], dd[2] - dd[1], dd[3] - dd[2], dd[4] - dd[3], dd[5] - dd[4], dd[5] - dd[0]);
+            }
+        }
     }
     return TM_OK;
 }
