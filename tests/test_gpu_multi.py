@@ -1,0 +1,61 @@
+"""GPU (needs >= 2 devices; skipped otherwise): query sharding over NCCL gives the same scores and histogram as
+one GPU (draws are keyed by global row; whole reference batches per rank)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    import tempme_b200 as tm
+    from tempme_b200 import synth
+    from tempme_b200.dist import ShardedPipeline
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    g = synth.make_graph("cfg2", scale=0.2)
+    f = tm.NeighborFinder.from_events(g["n_nodes"], g["src"], g["dst"], g["eidx"], g["ts"], device=dev, seed=5)
+    nfeat, efeat = synth.make_features("cfg2", g["n_nodes"], len(g["src"]))
+
+    class Base:
+        n_feat_th = nfeat.to(dev); e_feat_th = efeat.to(dev)
+        node_raw_features = torch.nn.Embedding.from_pretrained(n_feat_th, padding_idx=0, freeze=True)
+        edge_raw_features = torch.nn.Embedding.from_pretrained(e_feat_th, padding_idx=0, freeze=True)
+
+    torch.manual_seed(0)
+    m = tm.TempME(Base(), "tgn", "unit", 40, 64, device=dev, null_model={}).to(dev).eval()
+    q = synth.make_queries(g, np.random.default_rng(3), 500)       # 5 reference batches of 100: a 3 + 2 split
+    pipe = tm.MotifPipeline(f, m, 30, 1, group=100, seed=11)
+    scores, hist = ShardedPipeline(pipe).run(*q)
+    ok = 1
+    if rank == 0:
+        single = tm.MotifPipeline(f, m, 30, 1, group=100, seed=11)
+        ref = single.run_host(*q)
+        ok = int(np.array_equal(scores, ref) and torch.equal(hist, single.hist_null))
+        ret.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharding_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1
