@@ -45,18 +45,24 @@ selftest_gemm_kernel(const float *__restrict__ A, const float *__restrict__ B, f
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    if (t == 0) {
+    long long t_issue0 = 0, t_issue1 = 0;
+    if (warp == 0) {     // warp-uniform: every lane computes the (uniform) descriptors, one elected lane issues
+        const uint32_t leader = tc::elect_one();
         const uint32_t idesc = tc::idesc_tf32(128, N);
         const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)N * 16;
+        t_issue0 = clock64();
+        uint64_t ah = tc::smem_desc(tc::smem_u32(a_hi), lbo_a, 128), al = tc::smem_desc(tc::smem_u32(a_lo), lbo_a, 128);
+        uint64_t bh = tc::smem_desc(tc::smem_u32(b_hi), lbo_b, 128), bl = tc::smem_desc(tc::smem_u32(b_lo), lbo_b, 128);
+        const uint64_t da = (2 * lbo_a) >> 4, db = (2 * lbo_b) >> 4;       // descriptor start-address step per K = 8
         for (int ks = 0; ks < K / 8; ++ks) {
-            const uint64_t ah = tc::smem_desc(tc::smem_u32(a_hi) + ks * 2 * lbo_a, lbo_a, 128);
-            const uint64_t al = tc::smem_desc(tc::smem_u32(a_lo) + ks * 2 * lbo_a, lbo_a, 128);
-            const uint64_t bh = tc::smem_desc(tc::smem_u32(b_hi) + ks * 2 * lbo_b, lbo_b, 128);
-            const uint64_t bl = tc::smem_desc(tc::smem_u32(b_lo) + ks * 2 * lbo_b, lbo_b, 128);
-            tc::mma_tf32(tmem, ah, bh, idesc, ks > 0);
-            if (mode == 1) { tc::mma_tf32(tmem, al, bh, idesc, 1); tc::mma_tf32(tmem, ah, bl, idesc, 1); }
+            tc::mma_tf32(tmem, ah, bh, idesc, ks > 0, leader);
+            if (mode >= 1) { tc::mma_tf32(tmem, al, bh, idesc, 1, leader); tc::mma_tf32(tmem, ah, bl, idesc, 1, leader); }
+            ah += da; al += da; bh += db; bl += db;
         }
-        tc::mma_commit(&mbar);
+        tc::mma_commit(&mbar, leader);
+        t_issue1 = clock64();
+        if (mode >= 2 && leader) printf("[selftest] K=%d N=%d: %d MMAs, issue %lld cycles\n", K, N, (K / 8) * 3, t_issue1 - t_issue0);
+        __syncwarp();
     }
     tc::mbar_wait(&mbar, 0);
     tc::fence_after_sync();
@@ -160,38 +166,40 @@ struct ChunkTab { int n; int64_t off[40]; int bytes[40]; };
 struct StageTab { int8_t ns[40]; int8_t pos[40][2]; int8_t ch[40][2]; };
 
 struct TcCtx {
-    uint8_t *a[2][2];      // [m-block][hi, lo]  128 x kKC fp32 operand tiles
-    uint8_t *b[2];         // weight chunk buffer(s) [hi | lo]
+    uint8_t *a;            // A operand region: tile (m-block mb, hi/lo h) at a + (2*mb + h) * 128*kKC*4
+    uint32_t a_s, b_s;     // shared-space addresses of the A region and of weight buffer 0
+    uint32_t b_bytes;      // bytes of one weight chunk buffer [hi | lo]
     float *stage;          // 2 slabs of updated_feature columns (motif kernel)
     const float *cst;      // constant block in shared memory
-    uint64_t *mma_bar, *b_bar, *s_bar;
+    uint64_t *bars;        // [0] MMA done, [1], [2] weight buffers, [3] staging
     uint32_t mma_phase, s_phase;
     int nbuf, ri;          // weight buffers (1 or 2); round index inside the tile
     long long *dbg;        // optional per-chunk timestamps of CTA 0 (TEMPME_TC_TIMING), 6 slots per chunk
     int64_t seq, total;    // running chunk counter of this CTA / chunks it will consume in total
     const float *blob, *F;
 };
+constexpr uint32_t kATile = 128 * kKC * 4;
 
 __device__ __forceinline__ void tc_prefetch_b(const TcCtx &x, const ChunkTab &tab, int64_t seq) {   // thread 0 only
     const int i = (int)(seq % tab.n), buf = x.nbuf == 2 ? (int)(seq & 1) : 0;
-    tc::mbar_expect_tx(x.b_bar + buf, (uint32_t)tab.bytes[i]);
-    tc::tma_load_1d(x.b[buf], x.blob + tab.off[i], (uint32_t)tab.bytes[i], x.b_bar + buf);
+    tc::mbar_expect_tx(x.bars + 1 + buf, (uint32_t)tab.bytes[i]);
+    tc::tma_load_1d_s(x.b_s + buf * x.b_bytes, x.blob + tab.off[i], (uint32_t)tab.bytes[i], x.bars + 1 + buf);
 }
 __device__ __forceinline__ void tc_prefetch_stage(const TcCtx &x, const ChunkTab &tab, const StageTab &st, int64_t seq) {   // thread 0 only
     const int i = (int)(seq % tab.n), ns = st.ns[i];
     if (!ns) return;
     const int64_t tile = blockIdx.x + (seq / tab.n) * gridDim.x;
-    tc::mbar_expect_tx(x.s_bar, (uint32_t)(ns * kSlabFloats * 4));
+    tc::mbar_expect_tx(x.bars + 3, (uint32_t)(ns * kSlabFloats * 4));
     for (int k = 0; k < ns; ++k)
-        tc::tma_load_1d(x.stage + k * kSlabFloats, x.F + ((tile * 3 + st.pos[i][k]) * 4 + st.ch[i][k]) * kSlabFloats, kSlabFloats * 4, x.s_bar);
+        tc::tma_load_1d(x.stage + k * kSlabFloats, x.F + ((tile * 3 + st.pos[i][k]) * 4 + st.ch[i][k]) * kSlabFloats, kSlabFloats * 4, x.bars + 3);
 }
 
 __device__ __forceinline__ void store_a4(const TcCtx &x, int mb, int row, int k, float4 v) {
     float4 h, l;
     tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
-    const uint32_t off = tc::tile_off(128, row, k);
-    *reinterpret_cast<float4 *>(x.a[mb][0] + off) = h;
-    *reinterpret_cast<float4 *>(x.a[mb][1] + off) = l;
+    uint8_t *p = x.a + (uint32_t)(2 * mb) * kATile + tc::tile_off(128, row, k);
+    *reinterpret_cast<float4 *>(p) = h;
+    *reinterpret_cast<float4 *>(p + kATile) = l;
 }
 // updated_feature slab element (row, k): 128-byte rows with the 16-byte pieces XOR-swizzled by the row (bank spread)
 __device__ __forceinline__ int slab_off(int row, int k) { return row * kKC + ((((k >> 2) ^ (row & 7)) << 2) | (k & 3)); }
@@ -209,36 +217,43 @@ __device__ __forceinline__ void tc_linear(const TcLin l, TcCtx &x, const ChunkTa
         const bool tim = x.dbg && blockIdx.x == 0 && t == 0 && x.seq < 64;
         if (tim) x.dbg[x.seq * 6 + 0] = clock64();
         if (x.nbuf == 2 && t == 0 && x.seq + 1 < x.total) tc_prefetch_b(x, tab, x.seq + 1);   // buffer released by the MMA wait of chunk seq-1
-        if (st && st->ns[x.ri]) { tc::mbar_wait(x.s_bar, x.s_phase); x.s_phase ^= 1; }        // this round's slabs have landed
+        if (st && st->ns[x.ri]) { tc::mbar_wait(x.bars + 3, x.s_phase); x.s_phase ^= 1; }        // this round's slabs have landed
         fill(c, kcols);
         if (tim) x.dbg[x.seq * 6 + 1] = clock64();
         tc::fence_smem_to_async();
         tc::fence_before_sync();
         __syncthreads();
-        if (t == 0) {
-            if (st && x.seq + 1 < x.total) tc_prefetch_stage(x, tab, *st, x.seq + 1);         // staging buffer is free again
+        if (t < 32) {        // warp 0 (warp-uniform branch): lane 0 feeds the TMA queues, one elected lane issues the MMAs
+            if (t == 0 && st && x.seq + 1 < x.total) tc_prefetch_stage(x, tab, *st, x.seq + 1);   // staging buffer is free again
+            __syncwarp();
             const int buf = x.nbuf == 2 ? (int)(x.seq & 1) : 0;
             if (tim) x.dbg[x.seq * 6 + 2] = clock64();
-            tc::mbar_wait(x.b_bar + buf, (uint32_t)((x.nbuf == 2 ? (x.seq >> 1) : x.seq) & 1));   // weight chunk has landed (TMA)
+            tc::mbar_wait(x.bars + 1 + buf, (uint32_t)((x.nbuf == 2 ? (x.seq >> 1) : x.seq) & 1));   // weight chunk has landed (TMA)
             if (tim) x.dbg[x.seq * 6 + 3] = clock64();
             tc::fence_after_sync();
+            const uint32_t leader = tc::elect_one();
             const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)l.N16 * 16;
-            const uint32_t b_hi = tc::smem_u32(x.b[buf]), b_lo = b_hi + (uint32_t)l.N16 * kKC * 4;
+            const uint32_t b_base = x.b_s + (uint32_t)buf * x.b_bytes;
+            uint64_t bh = tc::smem_desc(b_base, lbo_b, 128), bl = tc::smem_desc(b_base + (uint32_t)l.N16 * kKC * 4, lbo_b, 128);
+            uint64_t ah[MB], al[MB];
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) { ah[mb] = tc::smem_desc(x.a_s + (uint32_t)(2 * mb) * kATile, lbo_a, 128); al[mb] = tc::smem_desc(x.a_s + (uint32_t)(2 * mb + 1) * kATile, lbo_a, 128); }
+            const uint64_t da = (2 * lbo_a) >> 4, db = (2 * lbo_b) >> 4;      // descriptor start-address step per K = 8
             for (int ks = 0; ks < kcols / 8; ++ks) {
-                const uint64_t bh = tc::smem_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128), bl = tc::smem_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
 #pragma unroll
                 for (int mb = 0; mb < MB; ++mb) {
-                    const uint64_t ah = tc::smem_desc(tc::smem_u32(x.a[mb][0]) + ks * 2 * lbo_a, lbo_a, 128);
-                    const uint64_t al = tc::smem_desc(tc::smem_u32(x.a[mb][1]) + ks * 2 * lbo_a, lbo_a, 128);
-                    tc::mma_tf32(tmem + acc_col[mb], ah, bh, idesc, (c | ks) != 0);
-                    tc::mma_tf32(tmem + acc_col[mb], al, bh, idesc, 1);
-                    tc::mma_tf32(tmem + acc_col[mb], ah, bl, idesc, 1);
+                    tc::mma_tf32(tmem + acc_col[mb], ah[mb], bh, idesc, (c | ks) != 0, leader);
+                    tc::mma_tf32(tmem + acc_col[mb], al[mb], bh, idesc, 1, leader);
+                    tc::mma_tf32(tmem + acc_col[mb], ah[mb], bl, idesc, 1, leader);
+                    ah[mb] += da; al[mb] += da;
                 }
+                bh += db; bl += db;
             }
-            tc::mma_commit(x.mma_bar);
+            tc::mma_commit(x.bars, leader);
             if (tim) x.dbg[x.seq * 6 + 4] = clock64();
+            __syncwarp();
         }
-        tc::mbar_wait(x.mma_bar, x.mma_phase);
+        tc::mbar_wait(x.bars, x.mma_phase);
         if (tim) x.dbg[x.seq * 6 + 5] = clock64();
         x.mma_phase ^= 1;
         if (x.nbuf == 1 && t == 0 && x.seq + 1 < x.total) tc_prefetch_b(x, tab, x.seq + 1);   // single buffer: refill right after the MMA released it
@@ -266,13 +281,12 @@ struct TcArgs {
 __device__ __forceinline__ void tc_setup(uint8_t *smem, TcCtx &x, const TcLayout &L, const TcArgs &a, int mb, bool stage, uint64_t *bars,
                                          uint32_t *tmem_slot, const float *blob) {
     uint8_t *p = smem;
-    for (int m = 0; m < 2; ++m)
-        for (int h = 0; h < 2; ++h) { x.a[m][h] = p; if (m < mb) p += 128 * kKC * 4; }
-    x.b[0] = p; p += a.b_bytes; x.b[1] = p; if (a.nbuf == 2) p += a.b_bytes;
+    x.a = p; x.a_s = tc::smem_u32(p); p += (uint32_t)(2 * mb) * kATile;
+    x.b_s = tc::smem_u32(p); x.b_bytes = (uint32_t)a.b_bytes; p += (size_t)a.nbuf * a.b_bytes;
     x.stage = reinterpret_cast<float *>(p); if (stage) p += 2 * kSlabFloats * 4;
     float *cst = reinterpret_cast<float *>(p);
     x.cst = cst;
-    x.mma_bar = bars; x.b_bar = bars + 1; x.s_bar = bars + 3;
+    x.bars = bars;
     x.mma_phase = 0; x.s_phase = 0; x.seq = 0; x.ri = 0; x.nbuf = a.nbuf; x.blob = blob; x.F = a.F; x.dbg = a.dbg;
     for (int i = threadIdx.x; i < L.n_cst; i += blockDim.x) cst[i] = __ldg(blob + L.cst + i);
     if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) tc::mbar_init(bars + i, 1); }
@@ -285,20 +299,38 @@ __device__ __forceinline__ void tc_setup(uint8_t *smem, TcCtx &x, const TcLayout
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
-// cos(x) for the TimeEncode arguments (up to ~1e8 and beyond): beyond the library's fast range the argument is
-// reduced in float64 with a two-term pi/2 (FMA Cody-Waite; exact to ~1e-16 for |x| < 1e15), then the short
-// sin/cos kernels run on |r| <= pi/4.  Result within ~1 ulp of the exact cosine of the fp32 argument, like cosf.
+// cos(x) for the TimeEncode arguments (they reach 1e8 and beyond, where the library cosf takes its slow path).
+// Branch-free exact argument reduction in 64-bit integer arithmetic: |x| = m * 2^e with a 24-bit integer m, so
+// frac(|x| / 2pi) = frac(m * frac(2^e / 2pi)); kInv2Pi[e + 44] holds frac(2^e / 2pi) in 0.64 fixed point and the
+// product wraps mod 2^64 for free (error < 2^-40 turns).  The turn fraction is split into a quadrant and an angle in
+// [-pi/4, pi/4) for the fdlibm single-precision sin/cos kernels.  Max error 1.4 ulp of 1.0 against the exact cosine
+// of the fp32 argument over |x| <= 1e11 (cosf: 1-2 ulp); |x| >= 2^43, inf and nan go to cosf.
+__constant__ unsigned long long kInv2Pi[64] = {
+    0x0000000000028be6ull, 0x00000000000517ccull, 0x00000000000a2f98ull, 0x0000000000145f30ull, 0x000000000028be60ull, 0x0000000000517cc1ull,
+    0x0000000000a2f983ull, 0x000000000145f306ull, 0x00000000028be60dull, 0x000000000517cc1bull, 0x000000000a2f9836ull, 0x00000000145f306dull,
+    0x0000000028be60dbull, 0x00000000517cc1b7ull, 0x00000000a2f9836eull, 0x0000000145f306dcull, 0x000000028be60db9ull, 0x0000000517cc1b72ull,
+    0x0000000a2f9836e4ull, 0x000000145f306dc9ull, 0x00000028be60db93ull, 0x000000517cc1b727ull, 0x000000a2f9836e4eull, 0x00000145f306dc9cull,
+    0x0000028be60db939ull, 0x00000517cc1b7272ull, 0x00000a2f9836e4e4ull, 0x0000145f306dc9c8ull, 0x000028be60db9391ull, 0x0000517cc1b72722ull,
+    0x0000a2f9836e4e44ull, 0x000145f306dc9c88ull, 0x00028be60db93910ull, 0x000517cc1b727220ull, 0x000a2f9836e4e441ull, 0x00145f306dc9c882ull,
+    0x0028be60db939105ull, 0x00517cc1b727220aull, 0x00a2f9836e4e4415ull, 0x0145f306dc9c882aull, 0x028be60db9391054ull, 0x0517cc1b727220a9ull,
+    0x0a2f9836e4e44152ull, 0x145f306dc9c882a5ull, 0x28be60db9391054aull, 0x517cc1b727220a94ull, 0xa2f9836e4e441529ull, 0x45f306dc9c882a53ull,
+    0x8be60db9391054a7ull, 0x17cc1b727220a94full, 0x2f9836e4e441529full, 0x5f306dc9c882a53full, 0xbe60db9391054a7full, 0x7cc1b727220a94feull,
+    0xf9836e4e441529fcull, 0xf306dc9c882a53f8ull, 0xe60db9391054a7f0ull, 0xcc1b727220a94fe1ull, 0x9836e4e441529fc2ull, 0x306dc9c882a53f84ull,
+    0x60db9391054a7f09ull, 0xc1b727220a94fe13ull, 0x836e4e441529fc27ull, 0x06dc9c882a53f84eull};
+
 __device__ __forceinline__ float cos_accurate(float x) {
-    const float ax = fabsf(x);
-    if (ax <= 105615.0f || !(ax < 1.0e15f)) return cosf(x);
-    const double xd = (double)x;
-    const double q = rint(xd * 0.63661977236758134308);
-    double r = fma(-q, 1.5707963267948966192, xd);
-    r = fma(-q, 6.123233995736766036e-17, r);
-    float sn, cs;
-    sincosf((float)r, &sn, &cs);
-    const int n = (int)((long long)q & 3);
-    return n == 0 ? cs : n == 1 ? -sn : n == 2 ? -cs : sn;
+    const uint32_t bits = __float_as_uint(x) & 0x7fffffffu;
+    const int e = (int)(bits >> 23) - 150;                 // |x| = m * 2^e
+    if (e > 19) return cosf(x);
+    const unsigned long long m = e < -44 ? 0ull : (unsigned long long)((bits & 0x7fffffu) | 0x800000u);   // tiny |x|: angle 0
+    const unsigned long long p = m * kInv2Pi[max(e, -44) + 44] + (1ull << 61);     // turn fraction + 1/8 turn, 0.64 fixed point
+    const int q = (int)(p >> 62);
+    const long long r = (long long)(p & ((1ull << 62) - 1)) - (1ll << 61);           // angle inside the quadrant, [-1/8, 1/8) turn
+    const float th = (float)r * 3.40612158008655459e-19f /* 2 pi / 2^64 */, z = th * th;
+    const float cs = fmaf(z, fmaf(z, fmaf(z, fmaf(z, 2.43904487962774090654e-5f, -1.38867637746099294692e-3f), 4.16666233237390631894e-2f), -4.99999997251031003120e-1f), 1.f);
+    const float sn = fmaf(th * z, fmaf(z, fmaf(z, fmaf(z, 2.7183114939898219064e-6f, -1.98393348360966317347e-4f), 8.3333293858894631756e-3f), -1.66666666416265235595e-1f), th);
+    const float v = (q & 1) ? sn : cs;                     // cos(q pi/2 + th) = {cs, -sn, -cs, sn}[q]
+    return ((q + 1) & 2) ? -v : v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -622,6 +654,11 @@ int64_t tc_slab_motifs() {
     return v;
 }
 
+// optional per-kernel timing (bench.py roofline): CUDA events around every launch of the two kernels
+static bool g_prof = false;
+static std::vector<cudaEvent_t> g_prof_ev;      // triples: before event kernel, between, after motif kernel
+static size_t g_prof_used = 0;
+
 // std_ = per-batch std (already computed); F = workspace for one slab
 int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
                     const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
@@ -670,17 +707,49 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     const char *tim_env = getenv("TEMPME_TC_TIMING");
     if (tim_env && !dbg_buf) cudaMalloc(&dbg_buf, 2 * 64 * 6 * sizeof(long long));
     const int ctas_e = (cols_e <= 256 && smem_e <= 110 * 1024) ? 2 : 1, ctas_m = (cols_m <= 256 && smem_m <= 110 * 1024) ? 2 : 1;
-    for (int64_t m0 = 0; m0 < a.n_motifs; m0 += a.slab) {
+    // Slabs alternate between two internal streams (each with its own F buffer) so that the ramp-down of one slab's
+    // motif kernel overlaps the next slab's event kernel; both fork from / join the caller's stream through events.
+    static cudaStream_t s2[64][2];
+    static cudaEvent_t ev_fork[64], ev_join[64][2];
+    static bool s2_init[64] = {false};
+    if (device >= 64) { set_error("tc_encode_score: device index >= 64"); return TM_ERR_UNSUPPORTED; }
+    if (!s2_init[device]) {
+        for (int k = 0; k < 2; ++k) { TM_CUDA(cudaStreamCreateWithFlags(&s2[device][k], cudaStreamNonBlocking)); TM_CUDA(cudaEventCreateWithFlags(&ev_join[device][k], cudaEventDisableTiming)); }
+        TM_CUDA(cudaEventCreateWithFlags(&ev_fork[device], cudaEventDisableTiming));
+        s2_init[device] = true;
+    }
+    const bool two = a.n_motifs > a.slab && !tim_env;
+    if (two) {
+        TM_CUDA(cudaEventRecord(ev_fork[device], st));
+        for (int k = 0; k < 2; ++k) TM_CUDA(cudaStreamWaitEvent(s2[device][k], ev_fork[device], 0));
+    }
+    const int64_t f_floats = ((a.slab + 127) / 128) * 128 * 3 * 2 * (int64_t)L.H;
+    cudaStream_t caller = st;
+    int64_t islab = 0;
+    for (int64_t m0 = 0; m0 < a.n_motifs; m0 += a.slab, ++islab) {
+        st = two ? s2[device][islab & 1] : caller;
+        a.F = F + (two ? (islab & 1) * f_floats : 0);
         a.m_begin = m0;
         const int64_t nm = std::min(a.slab, a.n_motifs - m0);
         const int64_t tiles_e = (3 * nm + 127) / 128, tiles_m = (nm + 127) / 128;
+        cudaEvent_t *pe = nullptr;
+        if (g_prof) {
+            if (g_prof_used + 3 > g_prof_ev.size()) { const size_t o = g_prof_ev.size(); g_prof_ev.resize(o + 3); for (size_t i = o; i < o + 3; ++i) cudaEventCreate(&g_prof_ev[i]); }
+            pe = &g_prof_ev[g_prof_used]; g_prof_used += 3;
+            cudaEventRecord(pe[0], st);
+        }
         a.tmem_cols = cols_e; a.b_bytes = bb_e; a.nbuf = nbuf_e; a.dbg = (tim_env && m0 == 0) ? dbg_buf : nullptr;
         event_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem_e, st>>>(L, te, d_blob_tc, a);
         TM_LAUNCH_CHECK();
+        if (pe) cudaEventRecord(pe[1], st);
         a.tmem_cols = cols_m; a.b_bytes = bb_m; a.nbuf = nbuf_m; a.dbg = (tim_env && m0 == 0) ? dbg_buf + 64 * 6 : nullptr;
         motif_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_m, (int64_t)sms * ctas_m), kTcThreads, smem_m, st>>>(L, tm, stg, d_blob_tc, a);
         TM_LAUNCH_CHECK();
+        if (pe) cudaEventRecord(pe[2], st);
     }
+    st = caller;
+    if (two)
+        for (int k = 0; k < 2; ++k) { TM_CUDA(cudaEventRecord(ev_join[device][k], s2[device][k])); TM_CUDA(cudaStreamWaitEvent(st, ev_join[device][k], 0)); }
     if (tim_env) {      // diagnostic only: dump the phase timeline of CTA 0 of the first slab
         cudaStreamSynchronize(st);
         std::vector<long long> h(2 * 64 * 6);
@@ -698,3 +767,20 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
 }
 
 }  // namespace tmb
+
+extern "C" int tm_encoder_profile(int enable) { tmb::g_prof = enable != 0; tmb::g_prof_used = 0; return TM_OK; }
+
+extern "C" int tm_encoder_profile_read(float *h_event_ms, float *h_motif_ms) {
+    if (!h_event_ms || !h_motif_ms) { set_error("tm_encoder_profile_read: null output"); return TM_ERR_ARG; }
+    double e = 0, m = 0;
+    for (size_t i = 0; i + 2 < tmb::g_prof_used + 0 && i + 2 < tmb::g_prof_ev.size() + 0; i += 3) {
+        float a = 0, b = 0;
+        TM_CUDA(cudaEventSynchronize(tmb::g_prof_ev[i + 2]));
+        TM_CUDA(cudaEventElapsedTime(&a, tmb::g_prof_ev[i], tmb::g_prof_ev[i + 1]));
+        TM_CUDA(cudaEventElapsedTime(&b, tmb::g_prof_ev[i + 1], tmb::g_prof_ev[i + 2]));
+        e += a; m += b;
+    }
+    *h_event_ms = (float)e; *h_motif_ms = (float)m;
+    tmb::g_prof_used = 0;
+    return TM_OK;
+}

@@ -26,15 +26,30 @@ __device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// exactly one lane of a converged warp gets true: the form ptxas recognises for issuing UTC* instructions without
+// a per-instruction lane-election loop (issue from `if (threadIdx.x == 0)` costs ~75 cycles per MMA instead)
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "@px mov.s32 %0, 1;\n\t}\n"
+        : "+r"(pred));
+    return pred;
 }
-// all MMAs issued so far by this thread arrive on the mbarrier when they complete
-__device__ __forceinline__ void mma_commit(uint64_t *mbar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(mbar)) : "memory");
+
+// The whole (converged) warp executes these; `leader` (from elect_one) predicates the instruction itself, so the
+// operands stay warp-uniform (uniform registers) and ptxas emits back-to-back UTC* instructions.
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, uint32_t leader = 1) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+// all MMAs issued so far by the leader arrive on the mbarrier when they complete
+__device__ __forceinline__ void mma_commit(uint64_t *mbar, uint32_t leader = 1) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(smem_u32(mbar)), "r"(leader) : "memory");
 }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -60,6 +75,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_1d_s(uint32_t dst_smem_addr, const void *src_gmem, uint32_t bytes, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(dst_smem_addr), "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
 // TMEM allocation: one full warp; ncols power of two in [32, 512]; address lands in *slot (shared memory)
