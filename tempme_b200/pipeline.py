@@ -73,7 +73,32 @@ class MotifPipeline:
         nb, g = self._layout(Q)
         return scores.view(nb, 3, g, self.W).permute(1, 0, 2, 3).reshape(3, Q, self.W)
 
+    def _host_buffers(self, Q):
+        """Pinned host staging (inputs [3Q] in the batch-major layout, scores [3, Q, W]) + matching device tensors,
+        allocated once per query count."""
+        if getattr(self, "_hb_q", None) != Q:
+            dev = self.device
+            self._pin_i32 = torch.empty((2, 3 * Q), dtype=torch.int32).pin_memory()      # roots | e_idx
+            self._pin_f64 = torch.empty(3 * Q, dtype=torch.float64).pin_memory()         # cut times
+            self._pin_out = torch.empty((3, Q, self.W), dtype=torch.float32).pin_memory()
+            self._dev_i32 = torch.empty((2, 3 * Q), dtype=torch.int32, device=dev)
+            self._dev_f64 = torch.empty(3 * Q, dtype=torch.float64, device=dev)
+            self._hb_q = Q
+        return self._pin_i32, self._pin_f64, self._pin_out
+
     def run_host(self, src, dst, fake, ts, eidx, row_offset=0):
-        """End-to-end call with host buffers: H2D of the queries, the device pipeline, D2H of the scores."""
-        roots, e, cut64 = self.stage_queries(src, dst, fake, ts, eidx)
-        return self.unstage_scores(self.run_device(roots, e, cut64, row_offset), len(src)).cpu().numpy()
+        """End-to-end call with host buffers: H2D of the queries, the device pipeline, D2H of the scores.
+        Returns a [3, Q, W] float32 array backed by an internal pinned buffer (valid until the next run_host call)."""
+        Q = len(src)
+        nb, g = self._layout(Q)
+        pin_i, pin_t, pin_out = self._host_buffers(Q)
+        r = pin_i[0].numpy().reshape(nb, 3, g); e = pin_i[1].numpy().reshape(nb, 3, g); c = pin_t.numpy().reshape(nb, 3, g)
+        r[:, 0] = np.asarray(src).reshape(nb, g); r[:, 1] = np.asarray(dst).reshape(nb, g); r[:, 2] = np.asarray(fake).reshape(nb, g)
+        e[:, 0] = e[:, 1] = np.asarray(eidx).reshape(nb, g); e[:, 2] = TM_EIDX_NONE                  # bgd roots are cut by time
+        c[:] = np.asarray(ts, np.float64).reshape(nb, 1, g)
+        self._dev_i32.copy_(pin_i, non_blocking=True)
+        self._dev_f64.copy_(pin_t, non_blocking=True)
+        scores = self.run_device(self._dev_i32[0], self._dev_i32[1], self._dev_f64, row_offset)
+        pin_out.copy_(self.unstage_scores(scores, Q), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return pin_out.numpy()
