@@ -126,7 +126,7 @@ def time_cpu_port(port, graph, rng, group, budget_s=15.0, events=0):
     q = synth.make_queries(graph, rng, group)
     t0 = time.perf_counter(); m = port.step(*q); t_cal = time.perf_counter() - t0       # calibration (also warms caches)
     if not events:
-        events = int(min(5000, max(group, budget_s / max(t_cal, 1e-3) * group)) // group * group)
+        events = int(min(20000, max(group, budget_s / max(t_cal, 1e-3) * group)) // group * group)
     q = synth.make_queries(graph, rng, events)
     t0 = time.perf_counter(); m = port.step(*q); dt = time.perf_counter() - t0
     return m / dt, events, m, dt
@@ -325,7 +325,9 @@ def run_ours(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(f"{args.workload}:{kern}")
+        traffic = json.load(open(tp)).get(f"{args.workload}:{top}")
+        if traffic is not None:
+            traffic = traffic * M / 1_440_000          # profiled at 1.44M motifs per step; DRAM bytes scale with the motif count
     if top in flops:
         ach = flops[top] / dur_s / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": traffic}

@@ -215,14 +215,19 @@ __device__ __forceinline__ void tc_linear(const TcLin l, TcCtx &x, const ChunkTa
     for (int c = 0; c < nch; ++c) {
         const int kcols = min(kKC, l.K8 - c * kKC);
         const bool tim = x.dbg && blockIdx.x == 0 && t == 0 && x.seq < 64;
+        const bool tim7 = x.dbg && blockIdx.x == 0 && t == 224 && x.seq < 64;
+        if (tim7) x.dbg[768 + x.seq * 4 + 0] = clock64();
         if (tim) x.dbg[x.seq * 6 + 0] = clock64();
         if (x.nbuf == 2 && t == 0 && x.seq + 1 < x.total) tc_prefetch_b(x, tab, x.seq + 1);   // buffer released by the MMA wait of chunk seq-1
         if (st && st->ns[x.ri]) { tc::mbar_wait(x.bars + 3, x.s_phase); x.s_phase ^= 1; }        // this round's slabs have landed
         fill(c, kcols);
         if (tim) x.dbg[x.seq * 6 + 1] = clock64();
+        if (tim7) x.dbg[768 + x.seq * 4 + 1] = clock64();
         tc::fence_smem_to_async();
+        if (tim7) x.dbg[768 + x.seq * 4 + 2] = clock64();
         tc::fence_before_sync();
         __syncthreads();
+        if (tim7) x.dbg[768 + x.seq * 4 + 3] = clock64();
         if (t < 32) {        // warp 0 (warp-uniform branch): lane 0 feeds the TMA queues, one elected lane issues the MMAs
             if (t == 0 && st && x.seq + 1 < x.total) tc_prefetch_stage(x, tab, *st, x.seq + 1);   // staging buffer is free again
             __syncwarp();
@@ -705,7 +710,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.F = F; a.scores = scores; a.dbg = nullptr;
     static long long *dbg_buf = nullptr;
     const char *tim_env = getenv("TEMPME_TC_TIMING");
-    if (tim_env && !dbg_buf) cudaMalloc(&dbg_buf, 2 * 64 * 6 * sizeof(long long));
+    if (tim_env && !dbg_buf) cudaMalloc(&dbg_buf, (2 * 64 * 6 + 2 * 1024) * sizeof(long long));
     const int ctas_e = (cols_e <= 256 && smem_e <= 110 * 1024) ? 2 : 1, ctas_m = (cols_m <= 256 && smem_m <= 110 * 1024) ? 2 : 1;
     // Slabs alternate between two internal streams (each with its own F buffer) so that the ramp-down of one slab's
     // motif kernel overlaps the next slab's event kernel; both fork from / join the caller's stream through events.
@@ -742,7 +747,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         event_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem_e, st>>>(L, te, d_blob_tc, a);
         TM_LAUNCH_CHECK();
         if (pe) cudaEventRecord(pe[1], st);
-        a.tmem_cols = cols_m; a.b_bytes = bb_m; a.nbuf = nbuf_m; a.dbg = (tim_env && m0 == 0) ? dbg_buf + 64 * 6 : nullptr;
+        a.tmem_cols = cols_m; a.b_bytes = bb_m; a.nbuf = nbuf_m; a.dbg = (tim_env && m0 == 0) ? dbg_buf + 1024 : nullptr;
         motif_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_m, (int64_t)sms * ctas_m), kTcThreads, smem_m, st>>>(L, tm, stg, d_blob_tc, a);
         TM_LAUNCH_CHECK();
         if (pe) cudaEventRecord(pe[2], st);
@@ -752,14 +757,14 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         for (int k = 0; k < 2; ++k) { TM_CUDA(cudaEventRecord(ev_join[device][k], s2[device][k])); TM_CUDA(cudaStreamWaitEvent(st, ev_join[device][k], 0)); }
     if (tim_env) {      // diagnostic only: dump the phase timeline of CTA 0 of the first slab
         cudaStreamSynchronize(st);
-        std::vector<long long> h(2 * 64 * 6);
+        std::vector<long long> h(2 * 64 * 6 + 2 * 1024);
         cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         for (int k = 0; k < 2; ++k) {
             const int n = std::min(k ? tm.n : te.n, 64);
             fprintf(stderr, "[tc timing] %s kernel, CTA 0, first tile: chunk: fill | sync | tma-wait | mma-issue | mma-done   (cycles)\n", k ? "motif" : "event");
             for (int c = 0; c < n; ++c) {
-                const long long *dd = h.data() + (k * 64 + c) * 6;
-                fprintf(stderr, "  %2d: %6lld %6lld %6lld %6lld %6lld   round %6lld\n", c, dd[1] - dd[0], dd[2] - dd[1], dd[3] - dd[2], dd[4] - dd[3], dd[5] - dd[4], dd[5] - dd[0]);
+                const long long *dd = h.data() + k * 1024 + c * 6, *d7 = h.data() + k * 1024 + 768 + c * 4;
+                fprintf(stderr, "  %2d: %6lld %6lld %6lld %6lld %6lld   round %6lld | warp7: start+%lld fill %lld proxy-fence %lld bar %lld\n", c, dd[1] - dd[0], dd[2] - dd[1], dd[3] - dd[2], dd[4] - dd[3], dd[5] - dd[4], dd[5] - dd[0], d7[0] - dd[0], d7[1] - d7[0], d7[2] - d7[1], d7[3] - d7[2]);
             }
         }
     }
