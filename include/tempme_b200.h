@@ -109,6 +109,14 @@ int tm_sample_walks(const tm_graph *g, int64_t B, int n, int N2, const int32_t *
                     unsigned long long *d_hist_null, unsigned long long *d_hist_prep,
                     unsigned long long *d_scanned, tm_stream stream);
 
+/* get_final_step (utils/graph.py:335-476) on its own: R walks whose first two events are given.
+ * d_src1/d_tgt1/d_e1/d_t1 [R] = first event (root, first-hop neighbour, e_idx, time); d_step2 [R, 3] = (src2, tgt2, e2),
+ * d_t2 [R] (may be NULL).  Draw rows are row_offset + i, stage 17.  Outputs as tm_sample_walks with W = 1. */
+int tm_walk_final_step(const tm_graph *g, int64_t R, const int32_t *d_src1, const int32_t *d_tgt1, const int32_t *d_e1,
+                       const float *d_t1, const int32_t *d_step2, const float *d_t2, uint64_t seed, uint64_t row_offset,
+                       const uint32_t *d_inject3, int32_t *d_o_nodes, int32_t *d_o_eidx, float *d_o_t, int32_t *d_o_anony,
+                       tm_stream stream);
+
 /* statistic (utils/null_model.py:75-82) / marginal (processed/data_preprocess.py:148-208) on
  * anonymised rows [count, 3]: accumulates both 12-bin histograms, optionally writes category ids.
  * A row that is none of the 12 classes (KeyError in the reference) sets d_err. */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "tm_sample_hop": (C.c_int, [_p, _i64, _p, _p, _p, C.c_int, _u64, C.c_uint32, _u64, _p, _p, _p, _p, _p, _p]),
     "tm_sample_walks": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, _p, _p, _p, _u64, _u64, _p, _p,
                                   _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "tm_walk_final_step": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _u64, _u64, _p, _p, _p, _p, _p, _p]),
     "tm_class_hist": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p]),
     "tm_edge_identity": (C.c_int, [_i64, _i64, _p, _p, _p]),
     "tm_encoder_blob_floats": (_i64, [C.POINTER(EncoderDesc)]),

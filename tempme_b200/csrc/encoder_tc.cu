@@ -739,9 +739,10 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         const int64_t tiles_e = (3 * nm + 127) / 128, tiles_m = (nm + 127) / 128;
         cudaEvent_t *pe = nullptr;
         if (g_prof) {
-            if (g_prof_used + 3 > g_prof_ev.size()) { const size_t o = g_prof_ev.size(); g_prof_ev.resize(o + 3); for (size_t i = o; i < o + 3; ++i) cudaEventCreate(&g_prof_ev[i]); }
-            pe = &g_prof_ev[g_prof_used]; g_prof_used += 3;
-            cudaEventRecord(pe[0], st);
+            if (g_prof_used + 3 <= g_prof_ev.size()) {        // pool is created by tm_encoder_profile(1); when exhausted, stop recording
+                pe = &g_prof_ev[g_prof_used]; g_prof_used += 3;
+                cudaEventRecord(pe[0], st);
+            }
         }
         a.tmem_cols = cols_e; a.b_bytes = bb_e; a.nbuf = nbuf_e; a.dbg = (tim_env && m0 == 0) ? dbg_buf : nullptr;
         event_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem_e, st>>>(L, te, d_blob_tc, a);
@@ -773,7 +774,15 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
 
 }  // namespace tmb
 
-extern "C" int tm_encoder_profile(int enable) { tmb::g_prof = enable != 0; tmb::g_prof_used = 0; return TM_OK; }
+extern "C" int tm_encoder_profile(int enable) {
+    tmb::g_prof = enable != 0;
+    tmb::g_prof_used = 0;
+    if (enable && tmb::g_prof_ev.empty()) {          // event pool, created outside any timed region
+        tmb::g_prof_ev.resize(3 * 4096);
+        for (auto &e : tmb::g_prof_ev) TM_CUDA(cudaEventCreate(&e));
+    }
+    return TM_OK;
+}
 
 extern "C" int tm_encoder_profile_read(float *h_event_ms, float *h_motif_ms) {
     if (!h_event_ms || !h_motif_ms) { set_error("tm_encoder_profile_read: null output"); return TM_ERR_ARG; }

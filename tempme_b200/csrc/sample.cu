@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(256)
 sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__restrict__ root,
                     const int32_t *__restrict__ h1_node, const int32_t *__restrict__ h1_eidx, const float *__restrict__ h1_ts,
                     uint64_t seed, uint64_t row_offset, const uint32_t *__restrict__ inj2, const uint32_t *__restrict__ inj3,
+                    const int32_t *__restrict__ pre2,   // optional [B*n*N2][3] = given (src2, tgt2, e2): get_final_step on its own
+                    const float *__restrict__ pre2_t,
                     int32_t *__restrict__ o_nodes, int32_t *__restrict__ o_eidx, float *__restrict__ o_t,
                     int32_t *__restrict__ o_anony, uint8_t *__restrict__ o_cat,
                     unsigned long long *hist_null, unsigned long long *hist_prep, unsigned long long *scanned) {
@@ -137,7 +139,7 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
             if (s1 > 0 && in_range(s1)) { s_a = __ldg(g.off + s1); c_a = s1 == t.x ? t.z : (s1 == t.y ? t.w : 0); }
             if (t1n > 0 && in_range(t1n)) { s_b = __ldg(g.off + t1n); c_b = t1n == t.x ? t.z : (t1n == t.y ? t.w : 0); }
         }
-        const int64_t L = c_a + c_b;
+        const int64_t L = pre2 ? 0 : c_a + c_b;
         uint64_t d[CAP];
         if (L > 0) {
 #pragma unroll
@@ -155,7 +157,10 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
         unsigned long long scan_acc = 0;
         for (int jj = 0; jj < N2; ++jj) {
             int64_t s2 = 0, t2n = 0; int32_t e2 = 0; float t2 = 0.f;
-            if (L > 0) {
+            if (pre2) {
+                const int64_t w2 = r2 * N2 + jj;
+                s2 = pre2[w2 * 3]; t2n = pre2[w2 * 3 + 1]; e2 = pre2[w2 * 3 + 2]; t2 = pre2_t ? pre2_t[w2] : 0.f;
+            } else if (L > 0) {
                 const int64_t sd = (int64_t)d[jj];
                 const bool from_a = sd < c_a;
                 const Entry en = load_entry(g.entry + (from_a ? s_a + sd : s_b + (sd - c_a)));
@@ -289,12 +294,13 @@ extern "C" int tm_sample_hop(const tm_graph *g, int64_t R, const int32_t *d_node
     return TM_OK;
 }
 
-extern "C" int tm_sample_walks(const tm_graph *g, int64_t B, int n, int N2, const int32_t *d_root,
-                               const int32_t *d_h1_node, const int32_t *d_h1_eidx, const float *d_h1_ts,
-                               uint64_t seed, uint64_t row_offset, const uint32_t *d_inject2, const uint32_t *d_inject3,
-                               int32_t *d_o_nodes, int32_t *d_o_eidx, float *d_o_t, int32_t *d_o_anony, uint8_t *d_o_cat,
-                               unsigned long long *d_hist_null, unsigned long long *d_hist_prep,
-                               unsigned long long *d_scanned, tm_stream stream) {
+static int walks_impl(const tm_graph *g, int64_t B, int n, int N2, const int32_t *d_root,
+                      const int32_t *d_h1_node, const int32_t *d_h1_eidx, const float *d_h1_ts,
+                      uint64_t seed, uint64_t row_offset, const uint32_t *d_inject2, const uint32_t *d_inject3,
+                      const int32_t *d_pre2, const float *d_pre2_t,
+                      int32_t *d_o_nodes, int32_t *d_o_eidx, float *d_o_t, int32_t *d_o_anony, uint8_t *d_o_cat,
+                      unsigned long long *d_hist_null, unsigned long long *d_hist_prep,
+                      unsigned long long *d_scanned, tm_stream stream) {
     if (!g || B < 0 || n <= 0 || N2 <= 0 || (B > 0 && (!d_root || !d_h1_node || !d_h1_eidx || !d_h1_ts || !d_o_nodes || !d_o_eidx || !d_o_t))) {
         set_error("tm_sample_walks: bad argument");
         return TM_ERR_ARG;
@@ -304,12 +310,32 @@ extern "C" int tm_sample_walks(const tm_graph *g, int64_t B, int n, int N2, cons
     TM_CUDA(cudaSetDevice(g->device));
     const int64_t rows = B * n, blocks = (rows + 255) / 256;
 #define TM_WALKS(CAP) sample_walks_kernel<CAP><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                           \
-        g->v, B, n, N2, d_root, d_h1_node, d_h1_eidx, d_h1_ts, seed, row_offset, d_inject2, d_inject3,                        \
+        g->v, B, n, N2, d_root, d_h1_node, d_h1_eidx, d_h1_ts, seed, row_offset, d_inject2, d_inject3, d_pre2, d_pre2_t,     \
         d_o_nodes, d_o_eidx, d_o_t, d_o_anony, d_o_cat, d_hist_null, d_hist_prep, d_scanned)
     if (N2 == 1) TM_WALKS(1); else if (N2 <= 4) TM_WALKS(4); else if (N2 <= 8) TM_WALKS(8); else TM_WALKS(TM_MAX_STEP2_FANOUT);
 #undef TM_WALKS
     TM_LAUNCH_CHECK();
     return TM_OK;
+}
+
+extern "C" int tm_sample_walks(const tm_graph *g, int64_t B, int n, int N2, const int32_t *d_root,
+                               const int32_t *d_h1_node, const int32_t *d_h1_eidx, const float *d_h1_ts,
+                               uint64_t seed, uint64_t row_offset, const uint32_t *d_inject2, const uint32_t *d_inject3,
+                               int32_t *d_o_nodes, int32_t *d_o_eidx, float *d_o_t, int32_t *d_o_anony, uint8_t *d_o_cat,
+                               unsigned long long *d_hist_null, unsigned long long *d_hist_prep,
+                               unsigned long long *d_scanned, tm_stream stream) {
+    return walks_impl(g, B, n, N2, d_root, d_h1_node, d_h1_eidx, d_h1_ts, seed, row_offset, d_inject2, d_inject3, nullptr, nullptr,
+                      d_o_nodes, d_o_eidx, d_o_t, d_o_anony, d_o_cat, d_hist_null, d_hist_prep, d_scanned, stream);
+}
+
+extern "C" int tm_walk_final_step(const tm_graph *g, int64_t R, const int32_t *d_src1, const int32_t *d_tgt1, const int32_t *d_e1,
+                                  const float *d_t1, const int32_t *d_step2, const float *d_t2, uint64_t seed, uint64_t row_offset,
+                                  const uint32_t *d_inject3, int32_t *d_o_nodes, int32_t *d_o_eidx, float *d_o_t, int32_t *d_o_anony,
+                                  tm_stream stream) {
+    if (!d_step2) { set_error("tm_walk_final_step: d_step2 is required"); return TM_ERR_ARG; }
+    // one root per walk (n = N2 = 1): row i of get_final_step is walk i
+    return walks_impl(g, R, 1, 1, d_src1, d_tgt1, d_e1, d_t1, seed, row_offset, nullptr, d_inject3, d_step2, d_t2,
+                      d_o_nodes, d_o_eidx, d_o_t, d_o_anony, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int tm_class_hist(int64_t count, const int32_t *d_anony, unsigned long long *d_hist_null,

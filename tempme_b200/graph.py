@@ -2,8 +2,8 @@
 the device-resident CSR of libtempme_b200.
 
 Host API (numpy in, numpy out, reference dtypes/shapes): ``find_before``, ``get_temporal_neighbor``,
-``find_k_hop``, ``find_k_walks``, ``get_next_step``/``get_final_step`` are not re-exposed separately
-(the walk sampler is one fused kernel); see DESIGN.md.  Device API (torch CUDA tensors in/out, no
+``find_k_hop``, ``find_k_walks``, ``find_before_walk``, ``get_next_step`` and ``get_final_step`` (the last two are
+views of the one fused walk kernel: step 2 alone / step 3 on given second events).  Device API (torch CUDA tensors in/out, no
 host round trip): ``sample_hop_device``, ``find_k_hop_device``, ``find_k_walks_device``.
 
 Randomness: the reference draws from numpy's global MT19937 stream.  Here every top-level sampling
@@ -280,6 +280,49 @@ class NeighborFinder:
                                                             inject2, inject3, want_cat=False)
         node_dtype = np.result_type(np.asarray(src_idx_l).dtype, np.int32)   # np.stack of the int64 roots with int32 hops, graph.py:303
         return (nodes.cpu().numpy().astype(node_dtype), eidx.cpu().numpy(), t.cpu().numpy(), anony.cpu().numpy())
+
+
+    # ------------------------------------------------------------------ the pieces of find_k_walks, reference signatures
+    def find_before_walk(self, src_idx_list, cut_time, e_idx=None, return_binary_prob=False):
+        """graph.py:149-194: concatenated prefixes of the given nodes; with e_idx a missing key counts as 0 (:174-176)."""
+        nodes = [int(v) for v in src_idx_list]
+        start, cut = self.find_before_batch_device(nodes, [float(cut_time)] * len(nodes) if e_idx is None else None,
+                                                   None if e_idx is None else [int(e_idx)] * len(nodes))
+        st, ct = start.cpu().numpy(), cut.cpu().numpy()
+        self._err.zero_()                                   # "not found" is not an error here
+        off, nbr, e, ts = self._export()
+        sl = [slice(int(a), int(a) + int(c)) for a, c in zip(st, ct)]
+        source = np.concatenate([np.full(int(c), v, dtype=np.int64) for v, c in zip(nodes, ct)]) if nodes else np.zeros(0, np.int64)
+        prob = np.concatenate([self.binary_prob_l[x] for x in sl]) if return_binary_prob else None
+        return (source, np.concatenate([nbr[x] for x in sl]), np.concatenate([e[x] for x in sl]), np.concatenate([ts[x] for x in sl]), prob)
+
+    def get_next_step(self, src_idx_l, cut_time_l, num_neighbor, degree, e_idx_l=None, source_id=None, seed=None, row_offset=0):
+        """graph.py:308-333 -> (src2, tgt2, e2, t2), each [B*degree, num_neighbor]."""
+        if e_idx_l is None:
+            raise NotImplementedError("get_next_step without e_idx_l (time cut) is not built: find_k_walks always passes e_idx")
+        assert len(src_idx_l) == len(cut_time_l) == len(source_id) * degree
+        B = len(source_id)
+        sub = ([np.asarray(src_idx_l).reshape(B, degree)], [np.asarray(e_idx_l).reshape(B, degree)],
+               [np.asarray(cut_time_l, dtype=np.float32).reshape(B, degree)])
+        nodes, eidx, t, _, _ = self.find_k_walks_device(degree, source_id, num_neighbor, sub, seed, row_offset, want_anony=False, want_cat=False)
+        R = B * degree
+        return (nodes[..., 2].reshape(R, -1).cpu().numpy(), nodes[..., 3].reshape(R, -1).cpu().numpy(),
+                eidx[..., 1].reshape(R, -1).cpu().numpy(), t[..., 1].reshape(R, -1).cpu().numpy())
+
+    def get_final_step(self, n_id_src_1, n_id_tgt_1, n_id_src_2, n_id_tgt_2, e_id_1, e_id_2, t_id_1, t_id_2, seed=None, row_offset=0, inject=None):
+        """graph.py:335-476 -> (src3, tgt3, e3, t3 [R], anony [R, 3]) for walks whose first two events are given."""
+        s = self._next_seed(seed)
+        dev = self.device
+        s1 = self._dev(np.asarray(n_id_src_1).reshape(-1), torch.int32); R = s1.numel()
+        t1n = self._dev(np.asarray(n_id_tgt_1).reshape(-1), torch.int32); e1 = self._dev(np.asarray(e_id_1).reshape(-1), torch.int32)
+        t1 = self._dev(np.asarray(t_id_1).reshape(-1), torch.float32); t2 = self._dev(np.asarray(t_id_2).reshape(-1), torch.float32)
+        step2 = torch.stack([self._dev(np.asarray(a).reshape(-1), torch.int32) for a in (n_id_src_2, n_id_tgt_2, e_id_2)], dim=1).contiguous()
+        nodes = torch.empty((R, 6), dtype=torch.int32, device=dev); eidx = torch.empty((R, 3), dtype=torch.int32, device=dev)
+        t = torch.empty((R, 3), dtype=torch.float32, device=dev); anony = torch.empty((R, 3), dtype=torch.int32, device=dev)
+        inj = self._dev(inject, torch.int64).to(torch.int32) if inject is not None else None
+        check(lib().tm_walk_final_step(self._h, R, ptr(s1), ptr(t1n), ptr(e1), ptr(t1), ptr(step2), ptr(t2), s, row_offset, ptr(inj),
+                                       ptr(nodes), ptr(eidx), ptr(t), ptr(anony), self._stream()), "tm_walk_final_step")
+        return (nodes[:, 0].cpu().numpy(), nodes[:, 1].cpu().numpy(), eidx[:, 0].cpu().numpy(), t[:, 0].cpu().numpy(), anony.cpu().numpy())
 
 
 # ---------------------------------------------------------------------- class ids / histograms / edge identity

@@ -9,6 +9,7 @@ pulled out of that file with ``ast`` at run time and executed as they are.
 Fixtures:
   tie_star.npz     SURVEY App. A.2 example: CSR arrays, nodeedge2idx values, find_before windows
   rand_small.npz   40-node multigraph with ties, self-loops and a real node 0: k-hop + walks (+offset shard)
+  native_rng.npz   the reference driven by its own numpy MT19937 stream, with the draws it consumed recorded
   rand_bigts.npz   timestamps ~1e8 (float32 != float64), train/full split: e_idx missing from a finder
   uslegis.npz      the bundled processed/ml_uslegis_sampled events + reference outputs on test queries
   nullmodel.npz    utils/null_model.py pre_processing on an endpoint-shuffled copy (class histogram)
@@ -114,6 +115,33 @@ def gen_rand_small():
         pack_sub("wide", sub, out); pack_walks("wide", walks, out)
     out["src_edge_identity"] = new_edge_info(out["src_w_eidx"].astype(int))
     np.savez_compressed(os.path.join(HERE, "rand_small.npz"), **out)
+
+
+def gen_native_rng():
+    """The reference with its OWN numpy MT19937 stream (np.random.seed(12345)); the draws are only recorded."""
+    rng = np.random.default_rng(21)
+    N, E = 50, 1200
+    src = rng.integers(0, N, E); dst = rng.integers(0, N, E)
+    ts = np.sort(rng.integers(0, 300, E)).astype(np.float64)
+    eidx = np.arange(1, E + 1)
+    nf = rg.NeighborFinder(refshim.adj_list_from_events(N, src, dst, eidx, ts))
+    q = np.arange(E - 400, E - 1)[::7][:40]
+    fake = rng.integers(0, N, len(q))
+    n, N2 = 9, 3
+    out = dict(n_nodes=N, src=src, dst=dst, eidx=eidx, ts=ts, q=q, fake=fake, n=n, N2=N2)
+    np.random.seed(12345)
+    for name, roots, e in (("src", src[q], eidx[q]), ("bgd", fake, None)):
+        rec = refshim.DrawRecorder()
+        with rec.patched():
+            sub = nf.find_k_hop(2, roots, ts[q], n, e_idx_l=e)
+            walks = nf.find_k_walks(n, roots, N2, sub)
+        pack_sub(name, sub, out); pack_walks(name, walks, out)
+        B = len(q)
+        out[f"{name}_inj_hop0"] = rec.dense(("get_temporal_neighbor", 0), B, n)
+        out[f"{name}_inj_hop1"] = rec.dense(("get_temporal_neighbor", 1), B * n, n)
+        out[f"{name}_inj_step2"] = rec.dense(("get_next_step", 0), B * n, N2)
+        out[f"{name}_inj_step3"] = rec.dense(("get_final_step", 0), B * n * N2, 1)
+    np.savez_compressed(os.path.join(HERE, "native_rng.npz"), **out)
 
 
 def gen_rand_bigts():
@@ -250,6 +278,7 @@ def gen_encoder(tag, walks5, edge_identity, cut_time, n_nodes, n_edges, D, Ed, s
 def main():
     gen_tie_star()
     gen_rand_small()
+    gen_native_rng()
     big = gen_rand_bigts()
     us = gen_uslegis()
     gen_nullmodel()

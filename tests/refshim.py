@@ -143,3 +143,38 @@ def adj_list_from_events(n_nodes, src, dst, eidx, ts):
         adj[int(s)].append((int(d), int(e), float(t)))
         adj[int(d)].append((int(s), int(e), float(t)))
     return adj
+
+
+class DrawRecorder:
+    """Leaves the reference's own MT19937 stream in place and only RECORDS what numpy.random.randint returned to
+    the sampling loops: {(function, hop level): {row i: raw draws}}.  Feeding these arrays back through the CUDA
+    path's INJECTED mode must reproduce the reference's outputs bit for bit."""
+
+    def __init__(self):
+        self._real = np.random.randint
+        self.log = {}
+
+    def randint(self, low, high=None, size=None, dtype=int):
+        out = self._real(low, high, size, dtype)
+        f = sys._getframe(1)
+        name = f.f_code.co_name
+        if name in ("get_temporal_neighbor", "get_next_step", "get_final_step"):
+            level = 0
+            if name == "get_temporal_neighbor" and f.f_back is not None and f.f_back.f_code.co_name == "find_k_hop":
+                level = f.f_back.f_locals.get("layer_i", 0)
+            self.log.setdefault((name, level), {})[int(f.f_locals["i"])] = np.array(out, dtype=np.int64).reshape(-1)
+        return out
+
+    @contextlib.contextmanager
+    def patched(self):
+        np.random.randint = self.randint
+        try:
+            yield self
+        finally:
+            np.random.randint = self._real
+
+    def dense(self, key, rows, width):
+        a = np.zeros((rows, width), np.int64)
+        for i, v in self.log.get(key, {}).items():
+            a[i, :len(v)] = v
+        return a

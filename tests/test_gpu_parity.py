@@ -234,6 +234,87 @@ def test_injected_draws_replay(tm, orc):
         assert (x[0] == y[0]).all()
 
 
+def test_walk_pieces_reference_signatures(tm, golden):
+    """get_next_step / get_final_step / find_before_walk with the reference's signatures reproduce the pieces of the
+    golden find_k_walks run (graph.py:290-296 shows how find_k_walks composes them)."""
+    g = golden("rand_small")
+    f = finder_of(tm, g)
+    q, n, N2 = g["q"], int(g["n"]), int(g["N2"])
+    roots = g["src"][q].astype(np.int64)
+    h1n, h1e, h1t = g["src_hop0_node"], g["src_hop0_eidx"], g["src_hop0_ts"]
+    s2, t2n, e2, t2 = f.get_next_step(h1n.flatten(), h1t.flatten(), N2, n, e_idx_l=h1e.flatten(), source_id=roots, seed=78)
+    wn, we, wt = g["src_w_nodes"], g["src_w_eidx"], g["src_w_t"]
+    B = len(q)
+    assert (s2.reshape(B, -1) == wn[..., 2]).all() and (t2n.reshape(B, -1) == wn[..., 3]).all()
+    assert (e2.reshape(B, -1) == we[..., 1]).all() and (t2.reshape(B, -1) == wt[..., 1]).all()
+    s3, t3n, e3, t3, anony = f.get_final_step(wn[..., 4], wn[..., 5], wn[..., 2], wn[..., 3], we[..., 2], we[..., 1], wt[..., 2], wt[..., 1], seed=78)
+    assert (s3.reshape(B, -1) == wn[..., 0]).all() and (t3n.reshape(B, -1) == wn[..., 1]).all()
+    assert (e3.reshape(B, -1) == we[..., 0]).all() and (t3.reshape(B, -1) == wt[..., 0]).all()
+    assert (anony.reshape(B, -1, 3) == g["src_w_anony"]).all()
+    # find_before_walk: prefixes of [root, neighbour] cut at the first-hop edge; a node that lacks the edge contributes nothing
+    root, nb, e = int(roots[3]), int(h1n[3, 2]), int(h1e[3, 2])
+    src_a, nbr_a, e_a, ts_a, _ = f.find_before_walk([root, nb], 0.0, e_idx=e)
+    d = f.nodeedge2idx
+    ca = d[root].get(e, 0) if root > 0 else 0
+    cb = d[nb].get(e, 0) if nb > 0 else 0
+    assert len(src_a) == ca + cb and (src_a[:ca] == root).all() and (src_a[ca:] == nb).all()
+    off = f.off_set_l
+    assert (e_a[:ca] == f.edge_idx_l[off[root]:off[root] + ca]).all() and (ts_a[ca:] == f.node_ts_l[off[nb]:off[nb] + cb]).all()
+
+
+def test_reference_native_mt19937_replay(tm, golden):
+    """The unmodified reference ran with its OWN numpy MT19937 stream (np.random.seed(12345)); its draws were only
+    recorded.  Feeding them back (INJECTED mode) must reproduce hops, walks and anonymisation bit for bit."""
+    g = golden("native_rng")
+    f = finder_of(tm, g)
+    q, n, N2 = g["q"], int(g["n"]), int(g["N2"])
+    ts = g["ts"].astype(np.float64)
+    for r in ("src", "bgd"):
+        roots = (g["src"][q] if r == "src" else g["fake"]).astype(np.int64)
+        e = g["eidx"][q] if r == "src" else None
+        sub = f.find_k_hop(2, roots, ts[q], n, e, inject=[g[f"{r}_inj_hop0"], g[f"{r}_inj_hop1"]])
+        assert_sub(g, r, sub)
+        walks = f.find_k_walks(n, roots, N2, sub, inject2=g[f"{r}_inj_step2"], inject3=g[f"{r}_inj_step3"])
+        assert_walks(g, r, walks)
+
+
+def test_native_philox_distribution_chi_square(tm, golden):
+    """Native-RNG mode: the 12-class motif histogram under our Philox stream is statistically indistinguishable from
+    the histogram the reference produced with its MT19937 stream (two-sample chi-square, alpha = 1e-3), and the
+    sampled first-hop indices are uniform over their windows."""
+    from scipy import stats
+    g = golden("nullmodel")
+    ref = g["dist"] * 500 * 3 * int(g["n"])                      # counts of the reference run (Philox-contract draws)
+    ti = g["test_idx"]
+    tot = np.zeros(12)
+    for seed in range(40, 48):                                    # 8 independent native runs
+        f = finder_of(tm, g, seed=seed)
+        d = tm.pre_processing(f, None, g["src"][ti].astype(np.int64), g["dst"][ti].astype(np.int64),
+                              g["ts"][ti].astype(np.float64), g["eidx"][ti], int(g["n"]), fakes=g["fakes"])
+        tot += np.array([d[k] for k in range(1, 13)]) * 500 * 3 * int(g["n"])
+    keep = (ref + tot) > 40                                       # pool sparse classes out of the test
+    table = np.stack([ref[keep], tot[keep]])
+    chi2, p, dof, _ = stats.chi2_contingency(table)
+    assert p > 1e-3, (chi2, p, dof)
+    # uniformity of first-hop draws: position / window length ~ U(0,1)
+    src, dst, eidx, ts = synth_graph(4, 60, 40000, 10 ** 6)
+    f = tm.NeighborFinder.from_events(60, src, dst, eidx, ts, seed=3)
+    q = np.arange(30000, 34000)
+    start, cut = f.find_before_batch_device(src[q], None, eidx[q])
+    sub = f.find_k_hop(1, src[q], ts[q], 16, eidx[q])
+    off = f.off_set_l; e_sorted = f.edge_idx_l
+    cutn = cut.cpu().numpy(); st = start.cpu().numpy()
+    u = []
+    for i in range(0, len(q), 7):
+        if cutn[i] < 50:
+            continue
+        win = e_sorted[st[i]:st[i] + cutn[i]]
+        pos = {int(e): k for k, e in enumerate(win)}
+        u += [(pos[int(e)] + 0.5) / cutn[i] for e in sub[1][0][i]]
+    ks = stats.kstest(np.array(u), "uniform")
+    assert ks.pvalue > 1e-3, ks
+
+
 # ------------------------------------------------------------------------------------------ encoder
 class _Base:
     def __init__(self, nfeat, efeat):
