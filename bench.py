@@ -145,7 +145,7 @@ def run_reference(args):
     nfeat, efeat = synth.make_features(args.workload, graph["n_nodes"], len(graph["src"]))
     port = CpuPort(graph, nfeat.numpy(), efeat.numpy(), random_params(sh["D"], sh["Ed"]), sh["n"], sh["N2"], args.group, sh["D"], sh["Ed"])
     rng = np.random.default_rng(7)
-    ev = args.cpu_events or 2 * args.group
+    ev = args.cpu_events or 10 * args.group
     for _ in range(args.warmup):
         port.step(*synth.make_queries(graph, rng, args.group))
     qs = [synth.make_queries(graph, rng, ev) for _ in range(args.steps)]

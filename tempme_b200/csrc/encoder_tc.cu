@@ -37,7 +37,7 @@ selftest_gemm_kernel(const float *__restrict__ A, const float *__restrict__ B, f
             *reinterpret_cast<float4 *>(b_lo + tc::tile_off(N, n, k)) = l;
         }
     uint32_t ncols = 32;
-    while ((int)ncols < N) ncols <<= 1;
+    while ((int)ncols < (mode == 3 ? N + 2 * K : N)) ncols <<= 1;
     if (t == 0) tc::mbar_init(&mbar, 1);
     if (warp == 0) tc::tmem_alloc(&tmem_slot, ncols);
     tc::fence_smem_to_async();
@@ -45,6 +45,18 @@ selftest_gemm_kernel(const float *__restrict__ A, const float *__restrict__ B, f
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
+    if (mode == 3) {       // TS mode: this thread's A row goes to TMEM columns [N, N+K) (hi) and [N+K, N+2K) (lo)
+        for (int k = 0; k < K; k += 16) {
+            float h[16], l[16];
+            for (int i = 0; i < 16; ++i) { const float x = k + i < K ? A[(size_t)t * K + k + i] : 0.f; tc::split_tf32(x, h[i], l[i]); }
+            tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + N + k, h);
+            tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + N + K + k, l);
+        }
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
     long long t_issue0 = 0, t_issue1 = 0;
     if (warp == 0) {     // warp-uniform: every lane computes the (uniform) descriptors, one elected lane issues
         const uint32_t leader = tc::elect_one();
@@ -55,8 +67,14 @@ selftest_gemm_kernel(const float *__restrict__ A, const float *__restrict__ B, f
         uint64_t bh = tc::smem_desc(tc::smem_u32(b_hi), lbo_b, 128), bl = tc::smem_desc(tc::smem_u32(b_lo), lbo_b, 128);
         const uint64_t da = (2 * lbo_a) >> 4, db = (2 * lbo_b) >> 4;       // descriptor start-address step per K = 8
         for (int ks = 0; ks < K / 8; ++ks) {
-            tc::mma_tf32(tmem, ah, bh, idesc, ks > 0, leader);
-            if (mode >= 1) { tc::mma_tf32(tmem, al, bh, idesc, 1, leader); tc::mma_tf32(tmem, ah, bl, idesc, 1, leader); }
+            if (mode == 3) {
+                tc::mma_tf32_ts(tmem, tmem + N + 8 * ks, bh, idesc, ks > 0, leader);
+                tc::mma_tf32_ts(tmem, tmem + N + K + 8 * ks, bh, idesc, 1, leader);
+                tc::mma_tf32_ts(tmem, tmem + N + 8 * ks, bl, idesc, 1, leader);
+            } else {
+                tc::mma_tf32(tmem, ah, bh, idesc, ks > 0, leader);
+                if (mode >= 1) { tc::mma_tf32(tmem, al, bh, idesc, 1, leader); tc::mma_tf32(tmem, ah, bl, idesc, 1, leader); }
+            }
             ah += da; al += da; bh += db; bl += db;
         }
         tc::mma_commit(&mbar, leader);
@@ -82,6 +100,7 @@ selftest_gemm_kernel(const float *__restrict__ A, const float *__restrict__ B, f
 using namespace tmb;
 
 extern "C" int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, int K, int N, int mode, tm_stream stream) {
+    if (mode == 3 && (K % 16 || N + 2 * K > 512)) { set_error("tm_selftest_gemm: TS mode needs K %% 16 == 0 and N + 2K <= 512"); return TM_ERR_ARG; }
     if (!d_A || !d_B || !d_C || K <= 0 || K % 8 || N < 16 || N > 256 || N % 16) { set_error("tm_selftest_gemm: need K %% 8 == 0, 16 <= N <= 256, N %% 16 == 0"); return TM_ERR_ARG; }
     const size_t smem = (size_t)(2 * 128 + 2 * N) * K * 4;
     if (smem > 200 * 1024) { set_error("tm_selftest_gemm: tile too large"); return TM_ERR_UNSUPPORTED; }

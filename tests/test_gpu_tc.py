@@ -28,6 +28,12 @@ def test_selftest_gemm_3xtf32(K, N):
         err = np.abs(out - ref) / scale
         assert np.isfinite(out).all()
         assert err.max() < tol, (mode, err.max())
+    if K % 16 == 0 and N + 2 * K <= 512:      # TS mode: A operand through TMEM (tcgen05.st), same accuracy
+        dC = torch.full((128, N), float("nan"), device="cuda")
+        _lib.check(L.tm_selftest_gemm(_lib.ptr(dA), _lib.ptr(dB), _lib.ptr(dC), K, N, 3, st), "tm_selftest_gemm")
+        torch.cuda.synchronize()
+        ts_out = dC.cpu().numpy().astype(np.float64)
+        assert (np.abs(ts_out - ref) / scale).max() < 2e-6
     # 3xTF32 must be at fp32-sgemm level: compare with the fp32 product
     f32 = (A @ B.T).astype(np.float64)
     assert np.abs(out - ref).max() <= 4 * np.abs(f32 - ref).max() + 1e-6 * scale.max()
