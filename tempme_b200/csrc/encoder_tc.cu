@@ -83,6 +83,7 @@ selftest_gemm_kernel(const float *__restrict__ A, const float *__restrict__ B, f
         __syncwarp();
     }
     tc::mbar_wait(&mbar, 0);
+    if (mode >= 2 && t == 0) printf("[selftest]   mode %d: MMAs complete %lld cycles after issue start\n", mode, clock64() - t_issue0);
     tc::fence_after_sync();
     for (int c = 0; c < N; c += 16) {
         float v[16];
@@ -635,6 +636,265 @@ motif_tc_kernel(const TcLayout L, const ChunkTab tab, const StageTab stab, const
     if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// motif kernel, TS mode, warp specialised.  The A operand lives in TMEM (written with tcgen05.st by the thread
+// that owns the row), so shared memory only carries the weight chunks and the staged updated_feature slabs
+// (112 KB instead of 192 KB per K-chunk round).  One CTA per SM: warps 0-7 (256 threads = 128 motifs x 2 column
+// halves) run the A-fills and the register-level epilogues; warp 8 is the issuer: it feeds the TMA queues (weight
+// ring of 3, staging ring of 2) and issues the MMAs of chunk i as soon as the fill threads have arrived on
+// a_full[i & 1].  The A region is double buffered, so fill(i+1) overlaps MMA(i); fill threads only wait when they
+// need a buffer back (chunk i-2) or read an accumulator (layer boundary).
+// TMEM: X [0,2H) Y [2H,4H) A0 [4H,4H+64) A1 [4H+64,4H+128).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTsThreads = 288;
+struct TsTab { int16_t n16[40], kcols[40], acc[40]; int8_t first[40]; };
+// barriers: [0,1] MMA done per A buffer, [2,3,4] weight ring, [5,6] staging ring, [7,8] A full per buffer
+__device__ __forceinline__ void named_sync_fill() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(tc::smem_u32(mbar)) : "memory"); }
+
+struct TsPipe {
+    float *stage;                   // 2 x 2 slabs
+    uint64_t *bars;
+    int64_t seq, waited;            // chunk counter; all MMAs of chunks < waited are known complete (fill side)
+    int ri;                         // round inside the tile
+    int64_t su_use;                 // staging uses consumed
+};
+
+__device__ __forceinline__ void ts_wait_mma(TsPipe &p, int64_t upto) {        // fill threads: MMAs of chunks < upto complete
+    for (; p.waited < upto; ++p.waited) tc::mbar_wait(p.bars + (p.waited & 1), (uint32_t)((p.waited >> 1) & 1));
+    tc::fence_after_sync();
+}
+
+// fill(c, kcols, sg, v): this thread's 16 columns [c*kKC + kb, +16) of the A row into v[16]; sg = staged slabs of the round
+template <typename Fill>
+__device__ __forceinline__ void ts_linear(const TcLin l, TsPipe &p, const StageTab &st, int n_tab, uint32_t tmem, int colA, uint32_t lane_base, int kb, Fill fill) {
+    const int nch = (l.K8 + kKC - 1) / kKC;
+    for (int c = 0; c < nch; ++c) {
+        const int kcols = min(kKC, l.K8 - c * kKC);
+        const int64_t i = p.seq;
+        if (i >= 2) ts_wait_mma(p, i - 1);                     // chunk i-2 done: A buffer (i & 1) is free
+        const float *sg = p.stage;
+        if (st.ns[p.ri]) {
+            const int sb = (int)(p.su_use & 1);
+            tc::mbar_wait(p.bars + 5 + sb, (uint32_t)((p.su_use >> 1) & 1));      // this round's slabs have landed
+            sg = p.stage + sb * 2 * kSlabFloats;
+            p.su_use++;
+        }
+        if (kb < kcols) {
+            float v[16], h[16], lo[16];
+            fill(c, kcols, sg, v);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) tc::split_tf32(v[k], h[k], lo[k]);
+            const uint32_t a0 = tmem + lane_base + colA + (uint32_t)(i & 1) * 64 + kb;
+            tc::tmem_st16(a0, h);
+            tc::tmem_st16(a0 + 32, lo);
+            tc::tmem_st_wait();
+        }
+        tc::fence_before_sync();
+        mbar_arrive(p.bars + 7 + (i & 1));                     // A buffer full (and the staged slabs consumed)
+        p.seq++;
+        p.ri = p.ri + 1 == n_tab ? 0 : p.ri + 1;
+    }
+}
+
+__global__ void __launch_bounds__(kTsThreads, 1)
+motif_ts_kernel(const TcLayout L, const ChunkTab tab, const StageTab stab, const TsTab tst, const float *__restrict__ blob, const TcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[10];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float part[2][128];
+    const int t = threadIdx.x, warp = t >> 5, row = t & 127, half = (t >> 7) & 1, kb = 16 * half;
+    const uint32_t b_s = tc::smem_u32(smem), b_bytes = (uint32_t)a.b_bytes;
+    float *stage = reinterpret_cast<float *>(smem + 3 * (size_t)a.b_bytes);
+    float *cstw = stage + 4 * kSlabFloats;
+    for (int i = t; i < L.n_cst; i += blockDim.x) cstw[i] = __ldg(blob + L.cst + i);
+    if (t == 0) { for (int i = 0; i < 7; ++i) tc::mbar_init(bars + i, 1); tc::mbar_init(bars + 7, 256); tc::mbar_init(bars + 8, 256); }
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const float *cst = cstw;
+    const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int H = L.H, H2 = 2 * L.H;
+    const int colX = 0, colY = H2, colA = 2 * H2, colA1 = 0, colA2 = H, colM0 = H2, colM1 = 0;
+    const int64_t n_m = min(a.slab, a.n_motifs - a.m_begin);
+    const int64_t n_tiles = (n_m + 127) / 128;
+    const int64_t total = ((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * tab.n;
+
+    if (warp == 8) {
+        // ================= issuer warp: TMA queues + MMA issue =================
+        const int lane = t & 31;
+        int64_t su_issue = 0;
+        auto issue_b = [&](int64_t seq) {        // lane 0
+            const int ci = (int)(seq % tab.n), buf = (int)(seq % 3);
+            tc::mbar_expect_tx(bars + 2 + buf, (uint32_t)tab.bytes[ci]);
+            tc::tma_load_1d_s(b_s + buf * b_bytes, blob + tab.off[ci], (uint32_t)tab.bytes[ci], bars + 2 + buf);
+        };
+        auto issue_stage = [&](int64_t seq) {    // lane 0; stage use number su_issue goes to buffer su_issue & 1
+            const int ci = (int)(seq % tab.n), ns = stab.ns[ci];
+            if (!ns) return;
+            const int buf = (int)(su_issue & 1);
+            const int64_t tile = blockIdx.x + (seq / tab.n) * gridDim.x;
+            tc::mbar_expect_tx(bars + 5 + buf, (uint32_t)(ns * kSlabFloats * 4));
+            for (int k = 0; k < ns; ++k)
+                tc::tma_load_1d(stage + (buf * 2 + k) * kSlabFloats, a.F + ((tile * 3 + stab.pos[ci][k]) * 4 + stab.ch[ci][k]) * kSlabFloats, kSlabFloats * 4, bars + 5 + buf);
+            su_issue++;
+        };
+        if (lane == 0 && total > 0) {            // prime: weights of chunks 0,1 and the staging of the first two staged rounds
+            issue_b(0); if (total > 1) issue_b(1);
+            issue_stage(0); if (total > 1) issue_stage(1);
+        }
+        __syncwarp();
+        for (int64_t i = 0; i < total; ++i) {
+            const int ci = (int)(i % tab.n), buf = (int)(i % 3);
+            const bool tim = a.dbg && blockIdx.x == 0 && lane == 0 && i < 64;
+            if (tim) a.dbg[i * 6 + 0] = clock64();
+            tc::mbar_wait(bars + 7 + (i & 1), (uint32_t)((i >> 1) & 1));          // fill threads have written A(i) (and read their slabs)
+            if (tim) a.dbg[i * 6 + 1] = clock64();
+            if (lane == 0 && i + 2 < total) issue_stage(i + 2);                    // its staging buffer (if any) was consumed two staged rounds ago
+            __syncwarp();
+            tc::mbar_wait(bars + 2 + buf, (uint32_t)((i / 3) & 1));               // weight chunk has landed (TMA)
+            if (tim) a.dbg[i * 6 + 2] = clock64();
+            tc::fence_after_sync();
+            const uint32_t leader = tc::elect_one();
+            const int n16 = tst.n16[ci], kcols = tst.kcols[ci];
+            const uint32_t idesc = tc::idesc_tf32(128, n16);
+            const uint32_t lbo_b = (uint32_t)n16 * 16, b_base = b_s + (uint32_t)buf * b_bytes;
+            uint64_t bh = tc::smem_desc(b_base, lbo_b, 128), bl = tc::smem_desc(b_base + (uint32_t)n16 * kKC * 4, lbo_b, 128);
+            const uint64_t db = (2 * lbo_b) >> 4;
+            const uint32_t a_hi = tmem + colA + (uint32_t)(i & 1) * 64, a_lo = a_hi + 32, d = tmem + tst.acc[ci];
+            for (int ks = 0; ks < kcols / 8; ++ks) {
+                tc::mma_tf32_ts(d, a_hi + 8 * ks, bh, idesc, (uint32_t)(!tst.first[ci] || ks != 0), leader);
+                tc::mma_tf32_ts(d, a_lo + 8 * ks, bh, idesc, 1, leader);
+                tc::mma_tf32_ts(d, a_hi + 8 * ks, bl, idesc, 1, leader);
+                bh += db; bl += db;
+            }
+            tc::mma_commit(bars + (i & 1), leader);
+            if (tim) a.dbg[i * 6 + 3] = clock64();
+            __syncwarp();
+            if (i + 2 < total) {                                                    // weight buffer (i+2) % 3 = (i-1) % 3: free once MMA(i-1) is done
+                if (i >= 1) tc::mbar_wait(bars + ((i - 1) & 1), (uint32_t)(((i - 1) >> 1) & 1));
+                if (tim) a.dbg[i * 6 + 4] = clock64();
+                if (lane == 0) issue_b(i + 2);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= fill / epilogue warps =================
+        TsPipe p;
+        p.stage = stage; p.bars = bars; p.seq = 0; p.waited = 0; p.ri = 0; p.su_use = 0;
+        auto both_halves = [&](float v) {
+            part[half][row] = v;
+            named_sync_fill();
+            const float s_ = part[0][row] + part[1][row];
+            named_sync_fill();
+            return s_;
+        };
+        auto drain = [&]() { ts_wait_mma(p, p.seq); };      // every issued MMA has completed: accumulators readable
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t ml = tile * 128 + row;
+            const bool live = ml < n_m;
+            const int64_t gm = a.m_begin + (live ? ml : 0);
+            auto score_half = [&]() {
+                float sc = 0.f;
+                for (int c0 = half * H; c0 < half * H + H; c0 += 16) {
+                    float pp[16], q[16];
+                    tc::tmem_ld16(tmem + lane_base + colX + c0, pp); tc::tmem_ld16(tmem + lane_base + colY + c0, q);
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 b1 = lds4(cst + L.w1.b + c0 + i), b2 = lds4(cst + L.w2.b + c0 + i);
+                        sc = fmaf(pp[i] + b1.x, q[i] + b2.x, sc); sc = fmaf(pp[i + 1] + b1.y, q[i + 1] + b2.y, sc);
+                        sc = fmaf(pp[i + 2] + b1.z, q[i + 2] + b2.z, sc); sc = fmaf(pp[i + 3] + b1.w, q[i + 3] + b2.w, sc);
+                    }
+                }
+                return sc;
+            };
+            auto copy_slab = [&](int c, int kcols, const float *sg, float *v) { (void)c; (void)kcols;
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) { const float4 f = lds4(sg + slab_off(row, kb + k)); v[k] = f.x; v[k + 1] = f.y; v[k + 2] = f.z; v[k + 3] = f.w; } };
+            // ---- Wp = W1 f2 -> X ; Wq_0 = W2 f_0 -> Y ; score_0 ; Wq_1 = W2 f_1 -> Y ; score_1 (:806-808)
+            ts_linear(L.w1, p, stab, tab.n, tmem, colA, lane_base, kb, copy_slab);
+            ts_linear(L.w2, p, stab, tab.n, tmem, colA, lane_base, kb, copy_slab);
+            drain();
+            float s0 = both_halves(score_half());
+            tc::fence_before_sync(); named_sync_fill(); tc::fence_after_sync();        // Y is about to be overwritten
+            ts_linear(L.w2, p, stab, tab.n, tmem, colA, lane_base, kb, copy_slab);
+            drain();
+            float s1 = both_halves(score_half());
+            tc::fence_before_sync(); named_sync_fill(); tc::fence_after_sync();
+            if (L.use_temporal && live) {                                             // temporal weighting (:811-836)
+                const int64_t b = gm / a.W;
+                const float cut = a.cut[b], sd = __fadd_rn(a.std_[b / a.group], 1e-6f);
+                const float d0 = fabsf(__fsub_rn(cut, a.t[gm * 3 + 0])), d1 = fabsf(__fsub_rn(cut, a.t[gm * 3 + 1]));
+                s0 = __fmul_rn(s0, __fadd_rn(0.7f, __fmul_rn(0.3f, expf(__fdiv_rn(-d0, sd)))));
+                s1 = __fmul_rn(s1, __fadd_rn(0.7f, __fmul_rn(0.3f, expf(__fdiv_rn(-d1, sd)))));
+            }
+            const float mx = fmaxf(s0, s1), e0 = expf(s0 - mx), e1 = expf(s1 - mx);
+            const float al0 = e0 / (e0 + e1), al1 = e1 / (e0 + e1);                  // softmax (:839)
+            // ---- sum_k alpha_k (W2 f_k + b2) = W2 (alpha_0 f_0 + alpha_1 f_1) + b2 -> Y (:841)
+            ts_linear(L.w2, p, stab, tab.n, tmem, colA, lane_base, kb, [&](int c, int kcols, const float *sg, float *v) { (void)c; (void)kcols;
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) {
+                    const float4 u = lds4(sg + slab_off(row, kb + k)), w = lds4(sg + kSlabFloats + slab_off(row, kb + k));
+                    v[k] = fmaf(al0, u.x, al1 * w.x); v[k + 1] = fmaf(al0, u.y, al1 * w.y); v[k + 2] = fmaf(al0, u.z, al1 * w.z); v[k + 3] = fmaf(al0, u.w, al1 * w.w);
+                } });
+            drain();
+            // ---- attention.MLP.0 on f2 + (Y + b2) -> A1 (:842-843)
+            ts_linear(L.a0, p, stab, tab.n, tmem, colA, lane_base, kb, [&](int c, int kcols, const float *sg, float *v) { (void)kcols;
+                float q[16];
+                tc::tmem_ld16(tmem + lane_base + colY + c * kKC + kb, q);
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) {
+                    const float4 f = lds4(sg + slab_off(row, kb + k)), b2 = lds4(cst + L.w2.b + c * kKC + kb + k);
+                    v[k] = f.x + (q[k] + b2.x); v[k + 1] = f.y + (q[k + 1] + b2.y); v[k + 2] = f.z + (q[k + 2] + b2.z); v[k + 3] = f.w + (q[k + 3] + b2.w);
+                } });
+            drain();
+            // ---- attention.MLP.3 -> A2
+            ts_linear(L.a3, p, stab, tab.n, tmem, colA, lane_base, kb, [&](int c, int kcols, const float *sg, float *v) { (void)kcols; (void)sg;
+                float z[16];
+                tc::tmem_ld16(tmem + lane_base + colA1 + c * kKC + kb, z);
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) {
+                    const float4 bb = lds4(cst + L.a0.b + c * kKC + kb + k);
+                    v[k] = fmaxf(z[k] + bb.x, 0.f); v[k + 1] = fmaxf(z[k + 1] + bb.y, 0.f); v[k + 2] = fmaxf(z[k + 2] + bb.z, 0.f); v[k + 3] = fmaxf(z[k + 3] + bb.w, 0.f);
+                } });
+            drain();
+            // ---- MLP.0 on [attention out | one-hot(category)] -> M0 (:195-200)
+            const int cat = (L.if_cat && live && a.cat) ? (int)a.cat[gm] : -1;
+            ts_linear(L.m0, p, stab, tab.n, tmem, colA, lane_base, kb, [&](int c, int kcols, const float *sg, float *v) { (void)kcols; (void)sg;
+                float z[16];
+                tc::tmem_ld16(tmem + lane_base + colA2 + min(c * kKC + kb, H - 16), z);   // columns >= H come from the one-hot
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { const int j = c * kKC + kb + k; v[k] = j < H ? z[k] + cst[L.a3.b + j] : (j - H == cat ? 1.f : 0.f); } });
+            drain();
+            // ---- MLP.3 -> M1
+            ts_linear(L.m3, p, stab, tab.n, tmem, colA, lane_base, kb, [&](int c, int kcols, const float *sg, float *v) { (void)kcols; (void)sg;
+                float z[16];
+                tc::tmem_ld16(tmem + lane_base + colM0 + c * kKC + kb, z);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { const int j = c * kKC + kb + k; v[k] = j < L.M ? fmaxf(z[k] + cst[L.m0.b + j], 0.f) : 0.f; } });
+            drain();
+            // ---- MLP.5 + sigmoid
+            float z5 = 0.f;
+            for (int c0 = half * (H / 2); c0 < half * (H / 2) + H / 2; c0 += 16) {
+                float z[16];
+                tc::tmem_ld16(tmem + lane_base + colM1 + c0, z);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) z5 = fmaf(fmaxf(z[i] + cst[L.m3.b + c0 + i], 0.f), cst[L.w5 + c0 + i], z5);
+            }
+            z5 = both_halves(z5);
+            if (live && half == 0) a.scores[gm] = 1.f / (1.f + expf(-(z5 + cst[L.b5])));
+            tc::fence_before_sync();
+            named_sync_fill();          // all TMEM reads of this tile done before the next tile's MMAs overwrite X
+            tc::fence_after_sync();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace tmb
 
 using namespace tmb;
@@ -712,6 +972,20 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     const int nbuf_e = 2, nbuf_m = 1;
     const size_t smem_e = (size_t)4 * 128 * kKC * 4 + (size_t)nbuf_e * bb_e + cst_b;
     const size_t smem_m = (size_t)2 * 128 * kKC * 4 + (size_t)nbuf_m * bb_m + (size_t)2 * kSlabFloats * 4 + cst_b;
+    TsTab tst;
+    memset(&tst, 0, sizeof tst);
+    {
+        const int H2 = 2 * L.H;
+        int k = 0;
+        auto tsp = [&](const TcLin &l, int acc) {
+            const int nch = (l.K8 + kKC - 1) / kKC;
+            for (int c = 0; c < nch && k < 40; ++c, ++k) { tst.n16[k] = (int16_t)l.N16; tst.kcols[k] = (int16_t)std::min(kKC, l.K8 - c * kKC); tst.acc[k] = (int16_t)acc; tst.first[k] = (int8_t)(c == 0); }
+        };
+        tsp(L.w1, 0); tsp(L.w2, H2); tsp(L.w2, H2); tsp(L.w2, H2); tsp(L.a0, 0); tsp(L.a3, L.H); tsp(L.m0, H2); tsp(L.m3, 0);
+    }
+    const char *ms_env = getenv("TEMPME_TC_MOTIF");          // "ss": both operands from shared memory (2 CTAs/SM); default "ts": A from TMEM
+    const bool use_ts = !(ms_env && strcmp(ms_env, "ss") == 0);
+    const size_t smem_ts = (size_t)3 * bb_m + (size_t)4 * kSlabFloats * 4 + cst_b;
     uint32_t cols_e = 32, cols_m = 32;
     while ((int)cols_e < 2 * L.H + std::max(r16(L.D), 2 * L.H)) cols_e <<= 1;
     while ((int)cols_m < 4 * L.H) cols_m <<= 1;
@@ -719,6 +993,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     if (device < 64 && !attr_set[device]) {
         TM_CUDA(cudaFuncSetAttribute(event_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         TM_CUDA(cudaFuncSetAttribute(motif_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TM_CUDA(cudaFuncSetAttribute(motif_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[device] = true;
     }
     int sms = 148;
@@ -742,7 +1017,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         TM_CUDA(cudaEventCreateWithFlags(&ev_fork[device], cudaEventDisableTiming));
         s2_init[device] = true;
     }
-    const bool two = a.n_motifs > a.slab && !tim_env;
+    const bool two = a.n_motifs > a.slab && !tim_env && !getenv("TEMPME_TC_SERIAL");
     if (two) {
         TM_CUDA(cudaEventRecord(ev_fork[device], st));
         for (int k = 0; k < 2; ++k) TM_CUDA(cudaStreamWaitEvent(s2[device][k], ev_fork[device], 0));
@@ -768,6 +1043,8 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         TM_LAUNCH_CHECK();
         if (pe) cudaEventRecord(pe[1], st);
         a.tmem_cols = cols_m; a.b_bytes = bb_m; a.nbuf = nbuf_m; a.dbg = (tim_env && m0 == 0) ? dbg_buf + 1024 : nullptr;
+        if (use_ts) motif_ts_kernel<<<(unsigned)std::min<int64_t>(tiles_m, (int64_t)sms), kTsThreads, smem_ts, st>>>(L, tm, stg, tst, d_blob_tc, a);
+        else
         motif_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_m, (int64_t)sms * ctas_m), kTcThreads, smem_m, st>>>(L, tm, stg, d_blob_tc, a);
         TM_LAUNCH_CHECK();
         if (pe) cudaEventRecord(pe[2], st);
@@ -782,6 +1059,14 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         for (int k = 0; k < 2; ++k) {
             const int n = std::min(k ? tm.n : te.n, 64);
             fprintf(stderr, "[tc timing] %s kernel, CTA 0, first tile: chunk: fill | sync | tma-wait | mma-issue | mma-done   (cycles)\n", k ? "motif" : "event");
+            if (k && use_ts) {
+                fprintf(stderr, "  (TS kernel, issuer warp) chunk: wait A-full | wait weights | issue+commit | wait MMA(i-1) | period\n");
+                for (int c = 0; c < n; ++c) {
+                    const long long *dd = h.data() + k * 1024 + c * 6, *dn = dd + 6;
+                    fprintf(stderr, "  %2d: %6lld %6lld %6lld %6lld   %6lld\n", c, dd[1] - dd[0], dd[2] - dd[1], dd[3] - dd[2], dd[4] - dd[3], c + 1 < n ? dn[0] - dd[0] : 0);
+                }
+                continue;
+            }
             for (int c = 0; c < n; ++c) {
                 const long long *dd = h.data() + k * 1024 + c * 6, *d7 = h.data() + k * 1024 + 768 + c * 4;
                 fprintf(stderr, "  %2d: %6lld %6lld %6lld %6lld %6lld   round %6lld | warp7: start+%lld fill %lld proxy-fence %lld bar %lld\n", c, dd[1] - dd[0], dd[2] - dd[1], dd[3] - dd[2], dd[4] - dd[3], dd[5] - dd[4], dd[5] - dd[0], d7[0] - dd[0], d7[1] - d7[0], d7[2] - d7[1], d7[3] - d7[2]);
