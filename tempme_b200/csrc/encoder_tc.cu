@@ -129,6 +129,7 @@ namespace tmb {
 constexpr int kKC = 32;           // K columns per operand chunk
 constexpr int kTcThreads = 256;   // 128 rows x 2 column halves
 constexpr int kSlabFloats = 128 * kKC;
+constexpr int kReplicas = 1;      // copies of the packed weights; CTA b streams from copy b % kReplicas (spreads the L2 slices that serve the broadcast)
 
 struct TcLin { int64_t w; int b, K8, N16; };   // chunk c at w + c * 2 * N16 * kKC floats: [hi tile | lo tile]; bias at cst[b]
 struct TcLayout {
@@ -300,6 +301,7 @@ struct TcArgs {
     float *scores;
     uint32_t tmem_cols;
     int b_bytes, nbuf;                       // bytes of one weight-chunk buffer, number of buffers
+    int replicas;                            // weight copies in the blob (CTA b uses copy b % replicas)
     long long *dbg;
 };
 
@@ -362,7 +364,8 @@ __device__ __forceinline__ float cos_accurate(float x) {
 // event kernel: rows r = 3 * motif + position of the slab
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads)
-event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ blob, const TcArgs a) {
+event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ blob0, const TcArgs a) {
+    const float *__restrict__ blob = blob0 + (int64_t)(blockIdx.x % a.replicas) * ((L.total + 31) & ~(int64_t)31);
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[4];
     __shared__ uint32_t tmem_slot;
@@ -492,7 +495,8 @@ event_tc_kernel(const TcLayout L, const ChunkTab tab, const float *__restrict__ 
 // motif kernel: 256 threads = 128 motifs x 2 column halves.  TMEM: X = [0, 2H), Y = [2H, 4H).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads)
-motif_tc_kernel(const TcLayout L, const ChunkTab tab, const StageTab stab, const float *__restrict__ blob, const TcArgs a) {
+motif_tc_kernel(const TcLayout L, const ChunkTab tab, const StageTab stab, const float *__restrict__ blob0, const TcArgs a) {
+    const float *__restrict__ blob = blob0 + (int64_t)(blockIdx.x % a.replicas) * ((L.total + 31) & ~(int64_t)31);
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[4];
     __shared__ uint32_t tmem_slot;
@@ -699,17 +703,18 @@ __device__ __forceinline__ void ts_linear(const TcLin l, TsPipe &p, const StageT
 }
 
 __global__ void __launch_bounds__(kTsThreads, 1)
-motif_ts_kernel(const TcLayout L, const ChunkTab tab, const StageTab stab, const TsTab tst, const float *__restrict__ blob, const TcArgs a) {
+motif_ts_kernel(const TcLayout L, const ChunkTab tab, const StageTab stab, const TsTab tst, const float *__restrict__ blob0, const TcArgs a) {
+    const float *__restrict__ blob = blob0 + (int64_t)(blockIdx.x % a.replicas) * ((L.total + 31) & ~(int64_t)31);
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[10];
+    __shared__ __align__(8) uint64_t bars[16];         // [0,1] MMA done, [5,6] staging, [7,8] A full, [10..13] weight ring
     __shared__ uint32_t tmem_slot;
     __shared__ float part[2][128];
     const int t = threadIdx.x, warp = t >> 5, row = t & 127, half = (t >> 7) & 1, kb = 16 * half;
     const uint32_t b_s = tc::smem_u32(smem), b_bytes = (uint32_t)a.b_bytes;
-    float *stage = reinterpret_cast<float *>(smem + 3 * (size_t)a.b_bytes);
+    float *stage = reinterpret_cast<float *>(smem + 4 * (size_t)a.b_bytes);
     float *cstw = stage + 4 * kSlabFloats;
     for (int i = t; i < L.n_cst; i += blockDim.x) cstw[i] = __ldg(blob + L.cst + i);
-    if (t == 0) { for (int i = 0; i < 7; ++i) tc::mbar_init(bars + i, 1); tc::mbar_init(bars + 7, 256); tc::mbar_init(bars + 8, 256); }
+    if (t == 0) { for (int i = 0; i < 14; ++i) tc::mbar_init(bars + i, 1); tc::mbar_init(bars + 7, 256); tc::mbar_init(bars + 8, 256); }
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
     tc::fence_before_sync();
     __syncthreads();
@@ -724,37 +729,48 @@ motif_ts_kernel(const TcLayout L, const ChunkTab tab, const StageTab stab, const
 
     if (warp == 8) {
         // ================= issuer warp: TMA queues + MMA issue =================
+        // weight ring of kRing buffers (chunk j lives in buffer j % kRing, barrier 10 + j % kRing), filled kRing - 1 chunks ahead;
+        // all round-robin indices are carried incrementally (no 64-bit division in the loop)
+        constexpr int kRing = 4;
         const int lane = t & 31;
-        int64_t su_issue = 0;
-        auto issue_b = [&](int64_t seq) {        // lane 0
-            const int ci = (int)(seq % tab.n), buf = (int)(seq % 3);
-            tc::mbar_expect_tx(bars + 2 + buf, (uint32_t)tab.bytes[ci]);
-            tc::tma_load_1d_s(b_s + buf * b_bytes, blob + tab.off[ci], (uint32_t)tab.bytes[ci], bars + 2 + buf);
+        uint64_t *wbar = bars + 10;
+        int b_ci = 0, b_buf = 0;                 // next weight chunk to request: index in the tile schedule, ring slot
+        int64_t b_seq = 0;
+        int s_ci = 0; int64_t s_seq = 0, s_tile = blockIdx.x, su_issue = 0;     // next staging request
+        auto issue_b = [&]() {                   // whole warp keeps the counters; lane 0 talks to the TMA
+            if (lane == 0) {
+                tc::mbar_expect_tx(wbar + b_buf, (uint32_t)tab.bytes[b_ci]);
+                tc::tma_load_1d_s(b_s + b_buf * b_bytes, blob + tab.off[b_ci], (uint32_t)tab.bytes[b_ci], wbar + b_buf);
+            }
+            __syncwarp();
+            ++b_seq; b_ci = b_ci + 1 == tab.n ? 0 : b_ci + 1; b_buf = b_buf + 1 == kRing ? 0 : b_buf + 1;
         };
-        auto issue_stage = [&](int64_t seq) {    // lane 0; stage use number su_issue goes to buffer su_issue & 1
-            const int ci = (int)(seq % tab.n), ns = stab.ns[ci];
-            if (!ns) return;
-            const int buf = (int)(su_issue & 1);
-            const int64_t tile = blockIdx.x + (seq / tab.n) * gridDim.x;
-            tc::mbar_expect_tx(bars + 5 + buf, (uint32_t)(ns * kSlabFloats * 4));
-            for (int k = 0; k < ns; ++k)
-                tc::tma_load_1d(stage + (buf * 2 + k) * kSlabFloats, a.F + ((tile * 3 + stab.pos[ci][k]) * 4 + stab.ch[ci][k]) * kSlabFloats, kSlabFloats * 4, bars + 5 + buf);
-            su_issue++;
+        auto issue_stage = [&]() {               // staged round number su_issue goes to buffer su_issue & 1
+            const int ns = stab.ns[s_ci];
+            if (ns) {
+                const int buf = (int)(su_issue & 1);
+                if (lane == 0) {
+                    tc::mbar_expect_tx(bars + 5 + buf, (uint32_t)(ns * kSlabFloats * 4));
+                    for (int k = 0; k < ns; ++k)
+                        tc::tma_load_1d(stage + (buf * 2 + k) * kSlabFloats, a.F + ((s_tile * 3 + stab.pos[s_ci][k]) * 4 + stab.ch[s_ci][k]) * kSlabFloats, kSlabFloats * 4, bars + 5 + buf);
+                }
+                __syncwarp();
+                su_issue++;
+            }
+            ++s_seq;
+            if (++s_ci == tab.n) { s_ci = 0; s_tile += gridDim.x; }
         };
-        if (lane == 0 && total > 0) {            // prime: weights of chunks 0,1 and the staging of the first two staged rounds
-            issue_b(0); if (total > 1) issue_b(1);
-            issue_stage(0); if (total > 1) issue_stage(1);
-        }
-        __syncwarp();
+        for (int k = 0; k < kRing - 1 && b_seq < total; ++k) issue_b();       // prime the rings
+        for (int k = 0; k < 2 && s_seq < total; ++k) issue_stage();
+        int ci = 0, buf = 0;
+        uint32_t wpar = 0;                       // parity of ring slot `buf`'s current use
         for (int64_t i = 0; i < total; ++i) {
-            const int ci = (int)(i % tab.n), buf = (int)(i % 3);
             const bool tim = a.dbg && blockIdx.x == 0 && lane == 0 && i < 64;
             if (tim) a.dbg[i * 6 + 0] = clock64();
             tc::mbar_wait(bars + 7 + (i & 1), (uint32_t)((i >> 1) & 1));          // fill threads have written A(i) (and read their slabs)
             if (tim) a.dbg[i * 6 + 1] = clock64();
-            if (lane == 0 && i + 2 < total) issue_stage(i + 2);                    // its staging buffer (if any) was consumed two staged rounds ago
-            __syncwarp();
-            tc::mbar_wait(bars + 2 + buf, (uint32_t)((i / 3) & 1));               // weight chunk has landed (TMA)
+            if (s_seq < total) issue_stage();                                      // staging of round i+2: its buffer was consumed by round i or earlier
+            tc::mbar_wait(wbar + buf, wpar);                                       // weight chunk has landed (TMA)
             if (tim) a.dbg[i * 6 + 2] = clock64();
             tc::fence_after_sync();
             const uint32_t leader = tc::elect_one();
@@ -773,12 +789,13 @@ motif_ts_kernel(const TcLayout L, const ChunkTab tab, const StageTab stab, const
             tc::mma_commit(bars + (i & 1), leader);
             if (tim) a.dbg[i * 6 + 3] = clock64();
             __syncwarp();
-            if (i + 2 < total) {                                                    // weight buffer (i+2) % 3 = (i-1) % 3: free once MMA(i-1) is done
+            if (b_seq < total) {                                                    // ring slot of chunk i-1 is free once MMA(i-1) is done -> chunk i+kRing-1
                 if (i >= 1) tc::mbar_wait(bars + ((i - 1) & 1), (uint32_t)(((i - 1) >> 1) & 1));
                 if (tim) a.dbg[i * 6 + 4] = clock64();
-                if (lane == 0) issue_b(i + 2);
-                __syncwarp();
+                if (i >= 1) issue_b();
             }
+            ci = ci + 1 == tab.n ? 0 : ci + 1;
+            if (++buf == kRing) { buf = 0; wpar ^= 1; }
         }
     } else {
         // ================= fill / epilogue warps =================
@@ -895,17 +912,211 @@ motif_ts_kernel(const TcLayout L, const ChunkTab tab, const StageTab stab, const
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// event kernel, TS mode, warp specialised: 16 fill warps (512 threads = 128 event rows x 4 column quarters) + one
+// issuer warp, one CTA per SM.  Both orientations' A operands live in TMEM, double buffered:
+// TMEM: Z [0,2H)  E/F [2H,4H)  A buffers [4H + 128*b + 64*mb, +64) = hi 32 | lo 32 columns.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEvThreads = 544;
+__device__ __forceinline__ void named_sync_fill512() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+
+struct EvPipe { uint64_t *bars; int64_t seq, waited; };
+__device__ __forceinline__ void ev_wait_mma(EvPipe &p, int64_t upto) {
+    for (; p.waited < upto; ++p.waited) tc::mbar_wait(p.bars + (p.waited & 1), (uint32_t)((p.waited >> 1) & 1));
+    tc::fence_after_sync();
+}
+// fill(c, kcols, v0, v1): this thread's 8 columns [c*kKC + kq, +8) of the A rows of the MB m-blocks
+template <int MB, typename Fill>
+__device__ __forceinline__ void ev_linear(const TcLin l, EvPipe &p, uint32_t tmem, int colA, uint32_t lane_base, int kq, Fill fill) {
+    const int nch = (l.K8 + kKC - 1) / kKC;
+    for (int c = 0; c < nch; ++c) {
+        const int kcols = min(kKC, l.K8 - c * kKC);
+        const int64_t i = p.seq;
+        if (i >= 2) ev_wait_mma(p, i - 1);                     // chunk i-2 done: A buffer (i & 1) is free
+        if (kq < kcols) {
+            float v[MB][8], h[8], lo[8];
+            fill(c, kcols, v);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) tc::split_tf32(v[mb][k], h[k], lo[k]);
+                const uint32_t a0 = tmem + lane_base + colA + (uint32_t)(i & 1) * 128 + mb * 64 + kq;
+                tc::tmem_st8(a0, h);
+                tc::tmem_st8(a0 + 32, lo);
+            }
+            tc::tmem_st_wait();
+        }
+        tc::fence_before_sync();
+        mbar_arrive(p.bars + 5 + (i & 1));
+        p.seq++;
+    }
+}
+
+__global__ void __launch_bounds__(kEvThreads, 1)
+event_ts_kernel(const TcLayout L, const ChunkTab tab, const TsTab tst, const float *__restrict__ blob0, const TcArgs a) {
+    const float *__restrict__ blob = blob0 + (int64_t)(blockIdx.x % a.replicas) * ((L.total + 31) & ~(int64_t)31);
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[8];          // [0,1] MMA done per A buffer, [2,3,4] weight ring, [5,6] A full per buffer
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5, row = t & 127, quarter = (t >> 7) & 3, kq = 8 * quarter;
+    const uint32_t b_s = tc::smem_u32(smem), b_bytes = (uint32_t)a.b_bytes;
+    float *cstw = reinterpret_cast<float *>(smem + 3 * (size_t)a.b_bytes);
+    for (int i = t; i < L.n_cst; i += blockDim.x) cstw[i] = __ldg(blob + L.cst + i);
+    if (t == 0) { for (int i = 0; i < 5; ++i) tc::mbar_init(bars + i, 1); tc::mbar_init(bars + 5, 512); tc::mbar_init(bars + 6, 512); }
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const float *cst = cstw;
+    const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int H = L.H, D = L.D, Ed = L.Ed;
+    const int colZ = 0, colE = 2 * H, colF = 2 * H, colA = 4 * H;
+    const int64_t n_rows = 3 * min(a.slab, a.n_motifs - a.m_begin);
+    const int64_t n_tiles = (n_rows + 127) / 128;
+    const int64_t total = ((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * tab.n;
+
+    if (warp == 16) {
+        // ================= issuer warp =================
+        const int lane = t & 31;
+        auto issue_b = [&](int64_t seq) {
+            const int ci = (int)(seq % tab.n), buf = (int)(seq % 3);
+            tc::mbar_expect_tx(bars + 2 + buf, (uint32_t)tab.bytes[ci]);
+            tc::tma_load_1d_s(b_s + buf * b_bytes, blob + tab.off[ci], (uint32_t)tab.bytes[ci], bars + 2 + buf);
+        };
+        if (lane == 0 && total > 0) { issue_b(0); if (total > 1) issue_b(1); }
+        __syncwarp();
+        for (int64_t i = 0; i < total; ++i) {
+            const int ci = (int)(i % tab.n), buf = (int)(i % 3);
+            tc::mbar_wait(bars + 5 + (i & 1), (uint32_t)((i >> 1) & 1));          // A(i) written
+            tc::mbar_wait(bars + 2 + buf, (uint32_t)((i / 3) & 1));               // weight chunk landed
+            tc::fence_after_sync();
+            const uint32_t leader = tc::elect_one();
+            const int n16 = tst.n16[ci], kcols = tst.kcols[ci], nmb = tst.first[ci] >> 1;     // first: bit 0 = first chunk of the layer, bits 1.. = m-blocks
+            const uint32_t idesc = tc::idesc_tf32(128, n16);
+            const uint32_t lbo_b = (uint32_t)n16 * 16, b_base = b_s + (uint32_t)buf * b_bytes;
+            uint64_t bh = tc::smem_desc(b_base, lbo_b, 128), bl = tc::smem_desc(b_base + (uint32_t)n16 * kKC * 4, lbo_b, 128);
+            const uint64_t db = (2 * lbo_b) >> 4;
+            const uint32_t acc_flag = (uint32_t)(!(tst.first[ci] & 1));
+            for (int ks = 0; ks < kcols / 8; ++ks) {
+                for (int mb = 0; mb < nmb; ++mb) {
+                    const uint32_t a_hi = tmem + colA + (uint32_t)(i & 1) * 128 + mb * 64 + 8 * ks, d = tmem + tst.acc[ci] + mb * H;
+                    tc::mma_tf32_ts(d, a_hi, bh, idesc, acc_flag | (uint32_t)(ks != 0), leader);
+                    tc::mma_tf32_ts(d, a_hi + 32, bh, idesc, 1, leader);
+                    tc::mma_tf32_ts(d, a_hi, bl, idesc, 1, leader);
+                }
+                bh += db; bl += db;
+            }
+            tc::mma_commit(bars + (i & 1), leader);
+            __syncwarp();
+            if (i + 2 < total) {
+                if (i >= 1) tc::mbar_wait(bars + ((i - 1) & 1), (uint32_t)(((i - 1) >> 1) & 1));
+                if (lane == 0) issue_b(i + 2);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= fill / epilogue warps =================
+        EvPipe p; p.bars = bars; p.seq = 0; p.waited = 0;
+        const bool ed_vec = (Ed & 3) == 0, d_vec = (D & 3) == 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t r = tile * 128 + row;
+            const bool live = r < n_rows;
+            const int64_t ml = live ? r / 3 : 0, gm = a.m_begin + ml;
+            const int pos = live ? (int)(r - 3 * ml) : 0;
+            int64_t e = 0, ns = 0, nt = 0; float dt = 0.f;
+            if (live) {
+                e = a.eidx[gm * 3 + pos]; ns = a.nodes[gm * 6 + 2 * pos]; nt = a.nodes[gm * 6 + 2 * pos + 1];
+                dt = __fsub_rn(a.t[gm * 3 + 2], a.t[gm * 3 + pos]);                       // explainer.py:326
+            }
+            const bool e_ok = live && e >= 0 && e < a.n_edge_rows, s_ok = live && ns >= 0 && ns < a.n_node_rows, t_ok = live && nt >= 0 && nt < a.n_node_rows;
+            const float *ef = a.edge_feat + e * Ed, *sf = a.node_feat + ns * D, *tf = a.node_feat + nt * D;
+            const float *ei = a.eid ? a.eid + gm * 9 + pos * 3 : nullptr;
+            auto xval = [&](int j) -> float {                                              // event_features column j (:179)
+                if (j < Ed) return e_ok ? __ldg(ef + j) : 0.f;
+                if (j < Ed + 3) return (live && ei) ? __ldg(ei + (j - Ed)) : 0.f;
+                if (j < L.ev) { const int k = j - Ed - 3; return live ? cos_accurate(__fadd_rn(__fmul_rn(dt, cst[L.freq + k]), cst[L.phase + k])) : 0.f; }   // :55-58
+                return 0.f;
+            };
+            // ---- lin_event (:93) -> E
+            ev_linear<1>(L.evt, p, tmem, colA, lane_base, kq, [&](int c, int kcols, float (*v)[8]) { (void)kcols;
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int j = c * kKC + kq + 4 * g;
+                    float4 x;
+                    if (ed_vec && j + 3 < Ed) x = e_ok ? ldg4(ef + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    else x = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
+                    v[0][4 * g] = x.x; v[0][4 * g + 1] = x.y; v[0][4 * g + 2] = x.z; v[0][4 * g + 3] = x.w;
+                } });
+            ev_wait_mma(p, p.seq);                                   // E complete
+            // ---- event_conv.MLP.0 on src + relu(tgt + event) and tgt + relu(src + event) (:94-95,182-184) -> Z
+            ev_linear<2>(L.g0, p, tmem, colA, lane_base, kq, [&](int c, int kcols, float (*v)[8]) { (void)kcols;
+                float sv[8], gv[8], ev[8];
+#pragma unroll
+                for (int k = 0; k < 8; k += 4) {
+                    const int j = c * kKC + kq + k;
+                    if (d_vec && j + 3 < D) {
+                        const float4 s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f), g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { sv[k + i] = (j + i < D && s_ok) ? __ldg(sf + j + i) : 0.f; gv[k + i] = (j + i < D && t_ok) ? __ldg(tf + j + i) : 0.f; }
+                    }
+                }
+                tc::tmem_ld8(tmem + lane_base + colE + c * kKC + kq, ev);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int j = c * kKC + kq + k;
+                    const float e_ = j < D ? ev[k] + cst[L.evt.b + j] : 0.f;
+                    v[0][k] = j < D ? sv[k] + fmaxf(gv[k] + e_, 0.f) : 0.f;
+                    v[1][k] = j < D ? gv[k] + fmaxf(sv[k] + e_, 0.f) : 0.f;
+                } });
+            ev_wait_mma(p, p.seq);                                   // Z complete
+            // ---- event_conv.MLP.2 (:84) -> F (aliases E, dead)
+            ev_linear<2>(L.g2, p, tmem, colA, lane_base, kq, [&](int c, int kcols, float (*v)[8]) { (void)kcols;
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    float z[8];
+                    tc::tmem_ld8(tmem + lane_base + colZ + mb * H + c * kKC + kq, z);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[mb][k] = fmaxf(z[k] + cst[L.g0.b + c * kKC + kq + k], 0.f);
+                } });
+            ev_wait_mma(p, p.seq);                                   // F complete
+            // ---- updated_feature row (:185): quarter q owns columns [32q, 32q + 32) = column chunk q of the slabs
+            {
+                const int mrow = (int)(ml & 127);
+                float *fc = a.F + (((ml >> 7) * 3 + pos) * 4 + quarter) * kSlabFloats;
+                for (int c0 = 0; c0 < 32; c0 += 8) {
+                    float v[8];
+                    tc::tmem_ld8(tmem + lane_base + colF + quarter * 32 + c0, v);
+                    if (live) {
+                        const float *bb = cst + L.g2.b + ((quarter * 32 + c0) & (H - 1));
+                        *reinterpret_cast<float4 *>(fc + slab_off(mrow, c0)) = make_float4(v[0] + bb[0], v[1] + bb[1], v[2] + bb[2], v[3] + bb[3]);
+                        *reinterpret_cast<float4 *>(fc + slab_off(mrow, c0 + 4)) = make_float4(v[4] + bb[4], v[5] + bb[5], v[6] + bb[6], v[7] + bb[7]);
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            named_sync_fill512();       // all TMEM reads of this tile done before the next tile's MMAs overwrite E
+            tc::fence_after_sync();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace tmb
 
 using namespace tmb;
 
 namespace tmb {
 
-int64_t tc_blob_floats(const tm_encoder_desc &d) { return make_tc_layout(d).total; }
+int64_t tc_blob_floats(const tm_encoder_desc &d) { return ((make_tc_layout(d).total + 31) & ~(int64_t)31) * kReplicas; }
 
 int tc_pack(const tm_encoder_desc &d, const tm_encoder_params &p, float *blob) {
     const TcLayout L = make_tc_layout(d);
-    memset(blob, 0, sizeof(float) * L.total);
+    memset(blob, 0, sizeof(float) * ((L.total + 31) & ~(int64_t)31) * kReplicas);
     const int H = L.H, D = L.D, M = L.M;
     pack_tc_lin(L, L.evt, L.ev, D, p.lin_event_w, p.lin_event_b, blob);
     pack_tc_lin(L, L.g0, D, H, p.gcn0_w, p.gcn0_b, blob);
@@ -920,6 +1131,8 @@ int tc_pack(const tm_encoder_desc &d, const tm_encoder_params &p, float *blob) {
     for (int k = 0; k < H; ++k) cst[L.w5 + k] = p.mlp5_w[k];
     cst[L.b5] = p.mlp5_b[0];
     for (int k = 0; k < D; ++k) { cst[L.freq + k] = p.basis_freq[k]; cst[L.phase + k] = p.phase[k]; }
+    const int64_t stride = (L.total + 31) & ~(int64_t)31;
+    for (int r = 1; r < kReplicas; ++r) memcpy(blob + r * stride, blob, sizeof(float) * L.total);
     return TM_OK;
 }
 
@@ -983,9 +1196,22 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         };
         tsp(L.w1, 0); tsp(L.w2, H2); tsp(L.w2, H2); tsp(L.w2, H2); tsp(L.a0, 0); tsp(L.a3, L.H); tsp(L.m0, H2); tsp(L.m3, 0);
     }
-    const char *ms_env = getenv("TEMPME_TC_MOTIF");          // "ss": both operands from shared memory (2 CTAs/SM); default "ts": A from TMEM
-    const bool use_ts = !(ms_env && strcmp(ms_env, "ss") == 0);
-    const size_t smem_ts = (size_t)3 * bb_m + (size_t)4 * kSlabFloats * 4 + cst_b;
+    TsTab tse;                                                // event kernel chunk table: first = (first chunk of layer) | m-blocks << 1
+    memset(&tse, 0, sizeof tse);
+    {
+        int k = 0;
+        auto tsp = [&](const TcLin &l, int acc, int nmb) {
+            const int nch = (l.K8 + kKC - 1) / kKC;
+            for (int c = 0; c < nch && k < 40; ++c, ++k) { tse.n16[k] = (int16_t)l.N16; tse.kcols[k] = (int16_t)std::min(kKC, l.K8 - c * kKC); tse.acc[k] = (int16_t)acc; tse.first[k] = (int8_t)((c == 0) | (nmb << 1)); }
+        };
+        tsp(L.evt, 2 * L.H, 1); tsp(L.g0, 0, 2); tsp(L.g2, 2 * L.H, 2);
+    }
+    const char *es_env = getenv("TEMPME_TC_EVENT");           // "ts": A operand in TMEM, warp-specialised, 1 CTA/SM (needs D <= 128); default: shared-memory operands, 2 CTAs/SM
+    const bool use_ts_e = es_env && strcmp(es_env, "ts") == 0 && r16(L.D) <= 2 * L.H;
+    const size_t smem_ts_e = (size_t)3 * bb_e + cst_b;
+    const char *ms_env = getenv("TEMPME_TC_MOTIF");          // "ts": A operand in TMEM, warp-specialised, 1 CTA/SM; default: both operands from shared memory, 2 CTAs/SM
+    const bool use_ts = ms_env && strcmp(ms_env, "ts") == 0;
+    const size_t smem_ts = (size_t)4 * bb_m + (size_t)4 * kSlabFloats * 4 + cst_b;
     uint32_t cols_e = 32, cols_m = 32;
     while ((int)cols_e < 2 * L.H + std::max(r16(L.D), 2 * L.H)) cols_e <<= 1;
     while ((int)cols_m < 4 * L.H) cols_m <<= 1;
@@ -994,6 +1220,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         TM_CUDA(cudaFuncSetAttribute(event_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         TM_CUDA(cudaFuncSetAttribute(motif_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         TM_CUDA(cudaFuncSetAttribute(motif_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TM_CUDA(cudaFuncSetAttribute(event_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[device] = true;
     }
     int sms = 148;
@@ -1002,6 +1229,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.n_motifs = B * W; a.W = W; a.group = group; a.slab = tc_slab_motifs(); a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
     a.eid = eid; a.node_feat = node_feat; a.edge_feat = edge_feat; a.std_ = std_; a.n_node_rows = n_node_rows; a.n_edge_rows = n_edge_rows;
     a.F = F; a.scores = scores; a.dbg = nullptr;
+    { const char *re = getenv("TEMPME_TC_REPLICAS"); a.replicas = re ? std::min(kReplicas, std::max(1, atoi(re))) : kReplicas; }
     static long long *dbg_buf = nullptr;
     const char *tim_env = getenv("TEMPME_TC_TIMING");
     if (tim_env && !dbg_buf) cudaMalloc(&dbg_buf, (2 * 64 * 6 + 2 * 1024) * sizeof(long long));
@@ -1039,6 +1267,8 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
             }
         }
         a.tmem_cols = cols_e; a.b_bytes = bb_e; a.nbuf = nbuf_e; a.dbg = (tim_env && m0 == 0) ? dbg_buf : nullptr;
+        if (use_ts_e) event_ts_kernel<<<(unsigned)std::min<int64_t>(tiles_e, (int64_t)sms), kEvThreads, smem_ts_e, st>>>(L, te, tse, d_blob_tc, a);
+        else
         event_tc_kernel<<<(unsigned)std::min<int64_t>(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem_e, st>>>(L, te, d_blob_tc, a);
         TM_LAUNCH_CHECK();
         if (pe) cudaEventRecord(pe[1], st);
