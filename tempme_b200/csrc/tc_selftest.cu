@@ -1,0 +1,112 @@
+// Hardware self-test GEMM of the tcgen05 / TMEM conventions in tc.cuh (descriptor layout, 3xTF32, TS mode).
+// tests/test_gpu_tc.py runs it on the device; the scorer kernels in encoder_tc.cu rely on exactly these conventions.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace tmb {
+
+// C[128 x N] = A[128 x K] * B[N x K]^T, one CTA of 128 threads.  mode 0: single TF32 pass, 1: 3xTF32.
+__global__ void __launch_bounds__(128)
+selftest_gemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C, int K, int N, int mode) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    uint8_t *a_hi = smem, *a_lo = a_hi + 128 * K * 4, *b_hi = a_lo + 128 * K * 4, *b_lo = b_hi + N * K * 4;
+    for (int k = 0; k < K; k += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(A + (size_t)t * K + k);
+        float4 h, l;
+        tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+        if (mode == 0) h = v;
+        *reinterpret_cast<float4 *>(a_hi + tc::tile_off(128, t, k)) = h;
+        *reinterpret_cast<float4 *>(a_lo + tc::tile_off(128, t, k)) = l;
+    }
+    for (int n = t; n < N; n += 128)
+        for (int k = 0; k < K; k += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(B + (size_t)n * K + k);
+            float4 h, l;
+            tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+            if (mode == 0) h = v;
+            *reinterpret_cast<float4 *>(b_hi + tc::tile_off(N, n, k)) = h;
+            *reinterpret_cast<float4 *>(b_lo + tc::tile_off(N, n, k)) = l;
+        }
+    uint32_t ncols = 32;
+    while ((int)ncols < (mode == 3 ? N + 2 * K : N)) ncols <<= 1;
+    if (t == 0) tc::mbar_init(&mbar, 1);
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, ncols);
+    tc::fence_smem_to_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    if (mode == 3) {       // TS mode: this thread's A row goes to TMEM columns [N, N+K) (hi) and [N+K, N+2K) (lo)
+        for (int k = 0; k < K; k += 16) {
+            float h[16], l[16];
+            for (int i = 0; i < 16; ++i) { const float x = k + i < K ? A[(size_t)t * K + k + i] : 0.f; tc::split_tf32(x, h[i], l[i]); }
+            tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + N + k, h);
+            tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + N + K + k, l);
+        }
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
+    long long t_issue0 = 0, t_issue1 = 0;
+    if (warp == 0) {     // warp-uniform: every lane computes the (uniform) descriptors, one elected lane issues
+        const uint32_t leader = tc::elect_one();
+        const uint32_t idesc = tc::idesc_tf32(128, N);
+        const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)N * 16;
+        t_issue0 = clock64();
+        uint64_t ah = tc::smem_desc(tc::smem_u32(a_hi), lbo_a, 128), al = tc::smem_desc(tc::smem_u32(a_lo), lbo_a, 128);
+        uint64_t bh = tc::smem_desc(tc::smem_u32(b_hi), lbo_b, 128), bl = tc::smem_desc(tc::smem_u32(b_lo), lbo_b, 128);
+        const uint64_t da = (2 * lbo_a) >> 4, db = (2 * lbo_b) >> 4;       // descriptor start-address step per K = 8
+        for (int ks = 0; ks < K / 8; ++ks) {
+            if (mode == 3) {
+                tc::mma_tf32_ts(tmem, tmem + N + 8 * ks, bh, idesc, ks > 0, leader);
+                tc::mma_tf32_ts(tmem, tmem + N + K + 8 * ks, bh, idesc, 1, leader);
+                tc::mma_tf32_ts(tmem, tmem + N + 8 * ks, bl, idesc, 1, leader);
+            } else {
+                tc::mma_tf32(tmem, ah, bh, idesc, ks > 0, leader);
+                if (mode >= 1) { tc::mma_tf32(tmem, al, bh, idesc, 1, leader); tc::mma_tf32(tmem, ah, bl, idesc, 1, leader); }
+            }
+            ah += da; al += da; bh += db; bl += db;
+        }
+        tc::mma_commit(&mbar, leader);
+        t_issue1 = clock64();
+        if (mode >= 2 && leader) printf("[selftest] K=%d N=%d: %d MMAs, issue %lld cycles\n", K, N, (K / 8) * 3, t_issue1 - t_issue0);
+        __syncwarp();
+    }
+    tc::mbar_wait(&mbar, 0);
+    if (mode >= 2 && t == 0) printf("[selftest]   mode %d: MMAs complete %lld cycles after issue start\n", mode, clock64() - t_issue0);
+    tc::fence_after_sync();
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) C[(size_t)t * N + c + i] = v[i];
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, ncols);
+}
+
+}  // namespace tmb
+
+using namespace tmb;
+
+extern "C" int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, int K, int N, int mode, tm_stream stream) {
+    if (mode == 3 && (K % 16 || N + 2 * K > 512)) { set_error("tm_selftest_gemm: TS mode needs K %% 16 == 0 and N + 2K <= 512"); return TM_ERR_ARG; }
+    if (!d_A || !d_B || !d_C || K <= 0 || K % 8 || N < 16 || N > 256 || N % 16) { set_error("tm_selftest_gemm: need K %% 8 == 0, 16 <= N <= 256, N %% 16 == 0"); return TM_ERR_ARG; }
+    const size_t smem = (size_t)(2 * 128 + 2 * N) * K * 4;
+    if (smem > 200 * 1024) { set_error("tm_selftest_gemm: tile too large"); return TM_ERR_UNSUPPORTED; }
+    TM_CUDA(cudaFuncSetAttribute(selftest_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selftest_gemm_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(d_A, d_B, d_C, K, N, mode);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}
