@@ -306,7 +306,8 @@ __device__ __forceinline__ float cos_accurate(float x, const uint2 *tab) {
 // TMEM: Zs [0,H)  Zt [H,2H)  E [2H, 2H + D16), or E aliasing Zt when MLP.0 has a single K chunk (D <= 32): E has then
 // been read completely before the MMA that writes Zt is issued, and four CTAs fit the SM's 512 columns.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads)
+template <int kMinCtas>
+__global__ void __launch_bounds__(kTcThreads, kMinCtas)
 event_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2];
@@ -608,7 +609,7 @@ int64_t tc_slab_motifs() {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const char *e = getenv("TEMPME_TC_SLAB_WAVES");
-        const int waves = e ? std::max(1, atoi(e)) : 1;
+        const int waves = e ? std::max(1, atoi(e)) : 4;        // measured on cfg2: 1 -> 422, 2 -> 453, 4 -> 462, 8 -> 453 M motifs/s (launch ramps vs L2 residency of h)
         v = (int64_t)sms * 2 * 128 * waves;
     }
     return v;
@@ -651,17 +652,28 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     int ctas_e = std::min<int>(512 / cols_e, (int)((228 * 1024) / (need_e + 1024 + 64)));
     ctas_e = std::max(1, std::min(ctas_e, ce ? std::max(1, atoi(ce)) : 4));
     const int ctas_m = std::max(1, std::min<int>(512 / cols_m, (int)((228 * 1024) / (need_m + 1024 + 2048))));
+    // the event kernel is compiled for three register budgets (2, 3 and 4 resident CTAs per SM)
+    using EvK = void (*)(const TcLayout, const float *, const TcArgs);
+    static const EvK ev_k[3] = {event_tc_kernel<2>, event_tc_kernel<3>, event_tc_kernel<4>};
     static bool attr_set[64] = {false};
+    static int ev_regs[3] = {0, 0, 0};
     if (!attr_set[device]) {
-        TM_CUDA(cudaFuncSetAttribute(event_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+        for (int v = 0; v < 3; ++v) {
+            TM_CUDA(cudaFuncSetAttribute(ev_k[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+            TM_CUDA(cudaFuncSetAttribute(ev_k[v], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            cudaFuncAttributes fa;
+            TM_CUDA(cudaFuncGetAttributes(&fa, ev_k[v]));
+            ev_regs[v] = fa.numRegs;
+        }
         TM_CUDA(cudaFuncSetAttribute(motif_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+        TM_CUDA(cudaFuncSetAttribute(motif_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[device] = true;
     }
-    {   // registers may allow fewer resident CTAs than shared memory and TMEM do
-        int occ = 0;
-        TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, event_tc_kernel, kTcThreads, need_e));
-        ctas_e = std::max(1, std::min(ctas_e, occ));
-    }
+    auto by_regs = [](int regs) { return 65536 / (((regs + 7) & ~7) * kTcThreads); };      // register file: 64K per SM, allocated in units of 8 per thread
+    const int ev_v = std::min(std::max(ctas_e, 2), 4) - 2;
+    const EvK event_kernel = ev_k[ev_v];
+    ctas_e = std::max(1, std::min(ctas_e, by_regs(ev_regs[ev_v])));
+    if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] event kernel: %d CTAs/SM (%d registers, smem %zu B, %u TMEM columns); motif kernel: %d CTAs/SM (smem %zu B)\n", ctas_e, ev_regs[ev_v], need_e, cols_e, ctas_m, need_m);
     const size_t smem_e = pad_smem(need_e, ctas_e), smem_m = pad_smem(need_m, ctas_m);
     TcArgs a;
     a.n_motifs = B * W; a.W = W; a.group = group; a.slab = tc_slab_motifs(); a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
@@ -701,7 +713,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
             cudaEventRecord(pe[0], st);
         }
         a.tmem_cols = cols_e; a.b_bytes = bb_e;
-        event_tc_kernel<<<balanced(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem_e, st>>>(L, d_blob_tc, a);
+        event_kernel<<<balanced(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem_e, st>>>(L, d_blob_tc, a);
         TM_LAUNCH_CHECK();
         if (pe) cudaEventRecord(pe[1], st);
         a.tmem_cols = cols_m; a.b_bytes = bb_m;
