@@ -12,12 +12,10 @@
 // which halves the multiply-adds per motif and takes the per-tile GEMM rounds from 34 to 17 (D = Ed = 32).  The
 // folded weights are rounded to fp32 once; scores agree with the unfolded fp32 evaluation to ~2e-7 relative.
 //
-//   event_tc_kernel : tile = 128 motifs x one walk position.  lin_event over [edge features | TimeEncode] (the three
-//                     edge-identity columns are added on the CUDA cores; position-2 tiles have dt = 0, so their
-//                     TimeEncode chunks collapse into a bias), then event_conv.MLP.0 + ReLU for the two orientations.
-//                     Writes h as [tile][position][4 column chunks][128 x 32] slabs (16-byte pieces, piece-major).
-//   motif_tc_kernel : tile = 128 motifs.  [S; P] h_2 -> scores -> temporal weights, softmax -> + Q mix -> R -> MLP.3 ->
-//                     MLP.5 + sigmoid.
+// One persistent kernel (score_tc_kernel) takes tiles of 128 motifs through three event passes (lin_event over
+// [edge features | TimeEncode]; the three edge-identity columns are added on the CUDA cores; position-2 rows have
+// dt = 0, so their TimeEncode chunks collapse into a bias; event_conv.MLP.0 + ReLU for the two orientations) and the
+// motif rounds ([S; P] h_2 -> scores -> temporal weights, softmax -> + Q mix -> R -> MLP.3 -> MLP.5 + sigmoid).
 // Thread (row, half) of the 256 owns TMEM lane `row` and 16 of the 32 columns of every K chunk: it reads the previous
 // accumulator row with tcgen05.ld, applies bias / ReLU / mixing in fp32 registers, splits into tf32 hi + lo and stores
 // the K-major operand tile in shared memory; weights arrive pre-split and pre-tiled by 1-D bulk TMA.
@@ -256,7 +254,7 @@ struct TcArgs {
     const uint8_t *cat;
     const float *cut, *eid, *node_feat, *edge_feat, *std_;
     int64_t n_node_rows, n_edge_rows;
-    float *F;                                // h slabs of the slab of motifs: [tile][pos][chunk][piece k/4][128 rows][4]
+    float *F;                                // scratch: per CTA 12 h slabs [position][column chunk][piece k/4][128 rows][4]
     float *scores;
     uint32_t tmem_cols;
     int b_bytes;                             // bytes of the weight-chunk buffer
@@ -302,22 +300,31 @@ __device__ __forceinline__ float cos_accurate(float x, const uint2 *tab) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// event kernel.  Tile id = 3 * motif tile + position; row i of the tile = motif (motif tile) * 128 + i.
-// TMEM: Zs [0,H)  Zt [H,2H)  E [2H, 2H + D16), or E aliasing Zt when MLP.0 has a single K chunk (D <= 32): E has then
-// been read completely before the MMA that writes Zt is issued, and four CTAs fit the SM's 512 columns.
+// score_tc_kernel: one persistent launch scores all motifs.  A CTA (256 threads = 128 motifs x 2 column halves, two
+// CTAs per SM) takes a tile of 128 motifs through
+//   event passes, one per walk position p (row = motif): lin_event -> E, MLP.0 for both orientations -> Zs, Zt,
+//     h_p = relu(. + bias) written to the CTA's private 192 KB scratch (12 [128 x 32] slabs, L2 resident);
+//   motif rounds: [S; P] h_2 -> scores -> temporal weights, softmax -> + Q mix -> R -> MLP.3 -> MLP.5 + sigmoid.
+// While one CTA of the SM is in its (CUDA-core heavy) event passes the other is usually in its (tensor heavy)
+// motif rounds.
+// TMEM (256 columns): event passes Zs [0,H)  Zt [H,2H)  E [2H, 2H + D16), or E aliasing Zt when MLP.0 has a single
+// K chunk (D <= 32): E has then been read completely before the MMA that writes Zt is issued.  Motif rounds:
+// U [0,2H) | Y [2H,3H) (one N = 3H accumulator of the [S; P] rounds), later M0 [0,M16) and M1 [2H,3H).
 // ---------------------------------------------------------------------------------------------
-template <int kMinCtas>
-__global__ void __launch_bounds__(kTcThreads, kMinCtas)
-event_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
+__device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+
+__global__ void __launch_bounds__(kTcThreads, 2)
+score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ float part[2][3][128];
     const int t = threadIdx.x, warp = t >> 5, row = t & 127, half = t >> 7, kb = 16 * half;
     TcCtx x;
     x.a = smem; x.a_s = tc::smem_u32(smem); x.b_s = x.a_s + 2 * kATile; x.bars = bars; x.mma_phase = 0; x.b_phase = 0; x.blob = blob;
-    float *cst = reinterpret_cast<float *>(smem + 2 * kATile + a.b_bytes);
-    uint2 *ctab = reinterpret_cast<uint2 *>(cst + ((L.n_cstE + 3) & ~3));
-    for (int i = t; i < L.n_cstE; i += kTcThreads) cst[i] = __ldg(blob + L.cstE + i);
+    float *cstE = reinterpret_cast<float *>(smem + 2 * kATile + a.b_bytes), *cstM = cstE + L.n_cstE;
+    uint2 *ctab = reinterpret_cast<uint2 *>(cstM + L.n_cstM);
+    for (int i = t; i < L.n_cstE + L.n_cstM; i += kTcThreads) cstE[i] = __ldg(blob + L.cstE + i);      // cstM follows cstE in the blob
     if (t < 64) ctab[t] = make_uint2((uint32_t)kInv2Pi[t], (uint32_t)(kInv2Pi[t] >> 32));
     if (t == 0) { tc::mbar_init(bars, 1); tc::mbar_init(bars + 1, 1); }
     if (warp == 0) tc::tmem_alloc(&tmem_slot, a.tmem_cols);
@@ -326,158 +333,123 @@ event_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
     x.tmem = tmem;
-    const int H = L.H, D = L.D, Ed = L.Ed, nG = L.g0.nch;
-    const int colZ = 0, colE = (nG == 1 && L.D16 <= H) ? H : 2 * H;
-    const int64_t n_m = min(a.slab, a.n_motifs - a.m_begin);
-    const int64_t n_tiles = 3 * ((n_m + 127) / 128);
+    const int H = L.H, H2 = 2 * L.H, D = L.D, Ed = L.Ed, nG = L.g0.nch, nchS = L.sp.nch;
+    const int colZ = 0, colE = (nG == 1 && L.D16 <= H) ? H : H2;
+    const int colU = 0, colY = H2, colM0 = 0, colM1 = H2;
+    const int64_t n_m = a.n_motifs, n_tiles = (n_m + 127) / 128;
     const int bytes_e = (int)chunk_floats(L.evt) * 4, bytes_g = (int)chunk_floats(L.g0) * 4;
+    const int bytes_sp = (int)chunk_floats(L.sp) * 4, bytes_q = (int)chunk_floats(L.q) * 4, bytes_r = (int)chunk_floats(L.r) * 4, bytes_m3 = (int)chunk_floats(L.m3) * 4;
     if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, L.evt.w, bytes_e);
     const bool ed_vec = (Ed & 3) == 0, d_vec = (D & 3) == 0;
-
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t mt = tile / 3;
-        const int pos = (int)(tile - 3 * mt);
-        const int64_t ml = mt * 128 + row;
-        const bool live = ml < n_m, more = tile + gridDim.x < n_tiles;
-        const int64_t gm = a.m_begin + (live ? ml : 0);
-        const int nE = pos == 2 ? L.nch_edge : L.evt.nch;          // position 2: dt = 0, the pure TimeEncode chunks are in the bias
-        int64_t e = 0, ns = 0, nt = 0; float dt = 0.f, ei0 = 0.f, ei1 = 0.f, ei2 = 0.f;
-        if (live) {
-            e = a.eidx[gm * 3 + pos]; ns = a.nodes[gm * 6 + 2 * pos]; nt = a.nodes[gm * 6 + 2 * pos + 1];
-            dt = __fsub_rn(a.t[gm * 3 + 2], a.t[gm * 3 + pos]);                       // explainer.py:326
-            if (a.eid) { const float *ei = a.eid + gm * 9 + pos * 3; ei0 = __ldg(ei); ei1 = __ldg(ei + 1); ei2 = __ldg(ei + 2); }
-        }
-        const bool e_ok = live && e >= 0 && e < a.n_edge_rows, s_ok = live && ns >= 0 && ns < a.n_node_rows, t_ok = live && nt >= 0 && nt < a.n_node_rows;
-        const float *ef = a.edge_feat + e * Ed, *sf = a.node_feat + ns * D, *tf = a.node_feat + nt * D;
-        auto xval = [&](int j) -> float {                                              // [edge features | TimeEncode] column j (:179, :55-58)
-            if (j < Ed) return e_ok ? __ldg(ef + j) : 0.f;
-            const int k = j - Ed;
-            if (k < D) return live ? cos_accurate(__fadd_rn(__fmul_rn(dt, cst[L.e_freq + k]), cst[L.e_phase + k]), ctab) : 0.f;
-            return 0.f;
-        };
-        // ---- lin_event (:93) -> E
-        for (int c = 0; c < nE; ++c) {
-            const int kcols = min(kKC, L.evt.K8 - c * kKC);
-            float4 v[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int k = kb + 4 * g, j = c * kKC + k;
-                if (k >= kcols) { v[g] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
-                if (ed_vec && j + 3 < Ed) v[g] = e_ok ? ldg4(ef + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                else v[g] = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) if (kb + 4 * g < kcols) store_a4(x, row, kb + 4 * g, v[g]);
-            const bool last = c + 1 == nE;
-            tc_mma_round(x, L.D16, kcols, colE, c != 0, last ? L.g0.w : L.evt.w + (int64_t)(c + 1) * chunk_floats(L.evt), last ? bytes_g : bytes_e);
-        }
-        // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
-        const int eb = pos == 2 ? L.e_b2 : L.e_b;
-        for (int o = 0; o < 2; ++o)
-            for (int c = 0; c < nG; ++c) {
-                const int kcols = min(kKC, L.g0.K8 - c * kKC);
-                if (kb < kcols) {
-                    float sv[16], gv[16];
-#pragma unroll
-                    for (int k = 0; k < 16; k += 4) {       // the gathers first (explainer.py:348-351)
-                        const int j = c * kKC + kb + k;
-                        if (d_vec && j + 3 < D) {
-                            const float4 s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f), g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) { sv[k + i] = (j + i < D && s_ok) ? __ldg(sf + j + i) : 0.f; gv[k + i] = (j + i < D && t_ok) ? __ldg(tf + j + i) : 0.f; }
-                        }
-                    }
-                    float evv[16];
-                    tc::tmem_ld16(tmem + lane_base + colE + c * kKC + kb, evv);
-#pragma unroll
-                    for (int k = 0; k < 16; k += 4) {
-                        float z[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int j = c * kKC + kb + k + i;          // j < D16: constants are zero-padded
-                            float e_ = evv[k + i] + cst[eb + j];
-                            e_ = fmaf(cst[L.e_wi + j], ei0, e_); e_ = fmaf(cst[L.e_wi + L.D16 + j], ei1, e_); e_ = fmaf(cst[L.e_wi + 2 * L.D16 + j], ei2, e_);
-                            const float p_ = o ? gv[k + i] : sv[k + i], q_ = o ? sv[k + i] : gv[k + i];
-                            z[i] = (j < D && live) ? p_ + fmaxf(q_ + e_, 0.f) : 0.f;
-                        }
-                        store_a4(x, row, kb + k, make_float4(z[0], z[1], z[2], z[3]));
-                    }
-                }
-                const bool last = c + 1 == nG;
-                int64_t noff; int nbytes;
-                if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
-                else if (o == 0) { noff = L.g0.w; nbytes = bytes_g; }
-                else { noff = L.evt.w; nbytes = more ? bytes_e : 0; }
-                tc_mma_round(x, H, kcols, colZ + o * H, c != 0, noff, nbytes);
-            }
-        // ---- h = relu(MLP.0 + bias): half o owns orientation o = column chunks 2o, 2o+1 of the (motif tile, position) slabs
-        {
-            float *fo = a.F + ((mt * 3 + pos) * 4 + 2 * half) * kSlabFloats + row * 4;
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                float v[16];
-                tc::tmem_ld16(tmem + lane_base + colZ + half * H + c0, v);
-                if (live) {
-                    float *fc = fo + (c0 >> 5) * kSlabFloats + ((c0 & 31) >> 2) * 512;
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const float4 bb = lds4(cst + L.e_g0b + c0 + i);
-                        *reinterpret_cast<float4 *>(fc + (i >> 2) * 512) =
-                            make_float4(fmaxf(v[i] + bb.x, 0.f), fmaxf(v[i + 1] + bb.y, 0.f), fmaxf(v[i + 2] + bb.z, 0.f), fmaxf(v[i + 3] + bb.w, 0.f));
-                    }
-                }
-            }
-        }
-        tc::fence_before_sync();
-        __syncthreads();            // all TMEM reads of this tile done before the next tile's MMAs overwrite it
-        tc::fence_after_sync();
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
-}
-
-// ---------------------------------------------------------------------------------------------
-// motif kernel: 256 threads = 128 motifs x 2 column halves, two CTAs per SM.
-// TMEM: U [0,2H) | Y [2H,3H) (one N = 3H accumulator of the [S; P] rounds), later M0 [0,M16) and M1 [2H,3H).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads, 2)
-motif_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2];
-    __shared__ uint32_t tmem_slot;
-    __shared__ float part[2][3][128];
-    const int t = threadIdx.x, warp = t >> 5, row = t & 127, half = t >> 7, kb = 16 * half;
-    TcCtx x;
-    x.a = smem; x.a_s = tc::smem_u32(smem); x.b_s = x.a_s + 2 * kATile; x.bars = bars; x.mma_phase = 0; x.b_phase = 0; x.blob = blob;
-    float *cst = reinterpret_cast<float *>(smem + 2 * kATile + a.b_bytes);
-    for (int i = t; i < L.n_cstM; i += kTcThreads) cst[i] = __ldg(blob + L.cstM + i);
-    if (t == 0) { tc::mbar_init(bars, 1); tc::mbar_init(bars + 1, 1); }
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, a.tmem_cols);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    x.tmem = tmem;
-    const int H = L.H, H2 = 2 * L.H;
-    const int colU = 0, colY = H2, colM0 = 0, colM1 = H2;
-    const int64_t n_m = min(a.slab, a.n_motifs - a.m_begin);
-    const int64_t n_tiles = (n_m + 127) / 128;
-    const int bytes_sp = (int)chunk_floats(L.sp) * 4, bytes_q = (int)chunk_floats(L.q) * 4, bytes_r = (int)chunk_floats(L.r) * 4, bytes_m3 = (int)chunk_floats(L.m3) * 4;
-    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, L.sp.w, bytes_sp);
+    float *Fs = a.F + (int64_t)blockIdx.x * 12 * kSlabFloats;           // this CTA's h slabs: [position][column chunk][piece k/4][128 rows][4]
+    const float *F0 = Fs, *F1 = Fs + 4 * kSlabFloats, *F2 = Fs + 8 * kSlabFloats;
     // this thread's 16 columns [kb, kb+16) of row `row` of a [128 x 32] slab (four coalesced 16-byte pieces)
     auto ld16 = [&](const float *slab, float *v) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) { const float4 f = ldg4(slab + ((kb >> 2) + g) * 512 + row * 4); v[4 * g] = f.x; v[4 * g + 1] = f.y; v[4 * g + 2] = f.z; v[4 * g + 3] = f.w; }
+        for (int g = 0; g < 4; ++g) { const float4 f = ldcg4(slab + ((kb >> 2) + g) * 512 + row * 4); v[4 * g] = f.x; v[4 * g + 1] = f.y; v[4 * g + 2] = f.z; v[4 * g + 3] = f.w; }
     };
-    const int nchS = L.sp.nch;      // = 2H / 32 column chunks of h
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t ml = tile * 128 + row;
-        const bool live = ml < n_m, more = tile + gridDim.x < n_tiles;
-        const int64_t gm = a.m_begin + (live ? ml : 0);
-        const float *F0 = a.F + (tile * 3 + 0) * 4 * kSlabFloats, *F1 = F0 + 4 * kSlabFloats, *F2 = F1 + 4 * kSlabFloats;
+        const int64_t gm_ = tile * 128 + row;
+        const bool live = gm_ < n_m, more = tile + gridDim.x < n_tiles;
+        const int64_t gm = live ? gm_ : 0;
+        // =========================== event passes ===========================
+#pragma unroll 1
+        for (int pos = 0; pos < 3; ++pos) {
+            const int nE = pos == 2 ? L.nch_edge : L.evt.nch;          // position 2: dt = 0, the pure TimeEncode chunks are in the bias
+            int64_t e = 0, ns = 0, nt = 0; float dt = 0.f, ei0 = 0.f, ei1 = 0.f, ei2 = 0.f;
+            if (live) {
+                e = a.eidx[gm * 3 + pos]; ns = a.nodes[gm * 6 + 2 * pos]; nt = a.nodes[gm * 6 + 2 * pos + 1];
+                dt = __fsub_rn(a.t[gm * 3 + 2], a.t[gm * 3 + pos]);                       // explainer.py:326
+                if (a.eid) { const float *ei = a.eid + gm * 9 + pos * 3; ei0 = __ldg(ei); ei1 = __ldg(ei + 1); ei2 = __ldg(ei + 2); }
+            }
+            const bool e_ok = live && e >= 0 && e < a.n_edge_rows, s_ok = live && ns >= 0 && ns < a.n_node_rows, t_ok = live && nt >= 0 && nt < a.n_node_rows;
+            const float *ef = a.edge_feat + e * Ed, *sf = a.node_feat + ns * D, *tf = a.node_feat + nt * D;
+            auto xval = [&](int j) -> float {                                              // [edge features | TimeEncode] column j (:179, :55-58)
+                if (j < Ed) return e_ok ? __ldg(ef + j) : 0.f;
+                const int k = j - Ed;
+                if (k < D) return live ? cos_accurate(__fadd_rn(__fmul_rn(dt, cstE[L.e_freq + k]), cstE[L.e_phase + k]), ctab) : 0.f;
+                return 0.f;
+            };
+            // ---- lin_event (:93) -> E
+            for (int c = 0; c < nE; ++c) {
+                const int kcols = min(kKC, L.evt.K8 - c * kKC);
+                float4 v[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int k = kb + 4 * g, j = c * kKC + k;
+                    if (k >= kcols) { v[g] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+                    if (ed_vec && j + 3 < Ed) v[g] = e_ok ? ldg4(ef + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    else v[g] = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) if (kb + 4 * g < kcols) store_a4(x, row, kb + 4 * g, v[g]);
+                const bool last = c + 1 == nE;
+                tc_mma_round(x, L.D16, kcols, colE, c != 0, last ? L.g0.w : L.evt.w + (int64_t)(c + 1) * chunk_floats(L.evt), last ? bytes_g : bytes_e);
+            }
+            // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
+            const int eb = pos == 2 ? L.e_b2 : L.e_b;
+#pragma unroll 1
+            for (int o = 0; o < 2; ++o)
+                for (int c = 0; c < nG; ++c) {
+                    const int kcols = min(kKC, L.g0.K8 - c * kKC);
+                    if (kb < kcols) {
+                        float sv[16], gv[16];
+#pragma unroll
+                        for (int k = 0; k < 16; k += 4) {       // the gathers first (explainer.py:348-351)
+                            const int j = c * kKC + kb + k;
+                            if (d_vec && j + 3 < D) {
+                                const float4 s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f), g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) { sv[k + i] = (j + i < D && s_ok) ? __ldg(sf + j + i) : 0.f; gv[k + i] = (j + i < D && t_ok) ? __ldg(tf + j + i) : 0.f; }
+                            }
+                        }
+                        float evv[16];
+                        tc::tmem_ld16(tmem + lane_base + colE + c * kKC + kb, evv);
+#pragma unroll
+                        for (int k = 0; k < 16; k += 4) {
+                            float z[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int j = c * kKC + kb + k + i;          // j < D16: constants are zero-padded
+                                float e_ = evv[k + i] + cstE[eb + j];
+                                e_ = fmaf(cstE[L.e_wi + j], ei0, e_); e_ = fmaf(cstE[L.e_wi + L.D16 + j], ei1, e_); e_ = fmaf(cstE[L.e_wi + 2 * L.D16 + j], ei2, e_);
+                                const float p_ = o ? gv[k + i] : sv[k + i], q_ = o ? sv[k + i] : gv[k + i];
+                                z[i] = (j < D && live) ? p_ + fmaxf(q_ + e_, 0.f) : 0.f;
+                            }
+                            store_a4(x, row, kb + k, make_float4(z[0], z[1], z[2], z[3]));
+                        }
+                    }
+                    const bool last = c + 1 == nG;
+                    int64_t noff; int nbytes;
+                    if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
+                    else if (o == 0) { noff = L.g0.w; nbytes = bytes_g; }
+                    else if (pos < 2) { noff = L.evt.w; nbytes = bytes_e; }
+                    else { noff = L.sp.w; nbytes = bytes_sp; }
+                    tc_mma_round(x, H, kcols, colZ + o * H, c != 0, noff, nbytes);
+                }
+            // ---- h_pos = relu(MLP.0 + bias): half o owns orientation o = column chunks 2o, 2o+1
+            {
+                float *fo = Fs + (pos * 4 + 2 * half) * kSlabFloats + row * 4;
+                for (int c0 = 0; c0 < H; c0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(tmem + lane_base + colZ + half * H + c0, v);
+                    float *fc = fo + (c0 >> 5) * kSlabFloats + ((c0 & 31) >> 2) * 512;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 bb = lds4(cstE + L.e_g0b + c0 + i);
+                        __stcg(reinterpret_cast<float4 *>(fc + (i >> 2) * 512),
+                               make_float4(fmaxf(v[i] + bb.x, 0.f), fmaxf(v[i + 1] + bb.y, 0.f), fmaxf(v[i + 2] + bb.z, 0.f), fmaxf(v[i + 3] + bb.w, 0.f)));
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncthreads();            // TMEM reads done before the next pass overwrites E / Z; the h slabs are visible to the CTA
+            tc::fence_after_sync();
+        }
+        // =========================== motif rounds ===========================
         // ---- [U | Y] = [S; P] h_2 ; r = d . h_2
         float rp = 0.f;
         {
@@ -490,7 +462,7 @@ motif_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 if (c + 1 < nchS) ld16(F2 + (c + 1) * kSlabFloats, nxt);
 #pragma unroll
                 for (int k = 0; k < 16; k += 4) {
-                    const float4 dd = lds4(cst + L.m_d + c * kKC + kb + k);
+                    const float4 dd = lds4(cstM + L.m_d + c * kKC + kb + k);
                     rp = fmaf(dd.x, cur[k], rp); rp = fmaf(dd.y, cur[k + 1], rp); rp = fmaf(dd.z, cur[k + 2], rp); rp = fmaf(dd.w, cur[k + 3], rp);
                     store_a4(x, row, kb + k, make_float4(cur[k], cur[k + 1], cur[k + 2], cur[k + 3]));
                 }
@@ -511,7 +483,7 @@ motif_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 tc::tmem_ld16(tmem + lane_base + colU + (c + cc) * kKC + kb, u);
 #pragma unroll
                 for (int k = 0; k < 16; k += 4) {
-                    const float4 cu = lds4(cst + L.m_cu + (c + cc) * kKC + kb + k);
+                    const float4 cu = lds4(cstM + L.m_cu + (c + cc) * kKC + kb + k);
                     const float u0 = u[k] + cu.x, u1 = u[k + 1] + cu.y, u2 = u[k + 2] + cu.z, u3 = u[k + 3] + cu.w;
                     s0 = fmaf(p0[cc][k], u0, s0); s0 = fmaf(p0[cc][k + 1], u1, s0); s0 = fmaf(p0[cc][k + 2], u2, s0); s0 = fmaf(p0[cc][k + 3], u3, s0);
                     s1 = fmaf(p1[cc][k], u0, s1); s1 = fmaf(p1[cc][k + 1], u1, s1); s1 = fmaf(p1[cc][k + 2], u2, s1); s1 = fmaf(p1[cc][k + 3], u3, s1);
@@ -523,7 +495,7 @@ motif_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         part[half][0][row] = s0; part[half][1][row] = s1; part[half][2][row] = rp;
         __syncthreads();
         {
-            const float r_ = part[0][2][row] + part[1][2][row] + cst[L.m_e];
+            const float r_ = part[0][2][row] + part[1][2][row] + cstM[L.m_e];
             s0 = part[0][0][row] + part[1][0][row] + r_;
             s1 = part[0][1][row] + part[1][1][row] + r_;
         }
@@ -556,7 +528,7 @@ motif_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             tc::tmem_ld16(tmem + lane_base + colY + c * kKC + kb, z);
 #pragma unroll
             for (int k = 0; k < 16; k += 4) {
-                const float4 bb = lds4(cst + L.m_cy + c * kKC + kb + k);
+                const float4 bb = lds4(cstM + L.m_cy + c * kKC + kb + k);
                 store_a4(x, row, kb + k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
             }
             const bool last = c + 1 == L.r.nch;
@@ -578,7 +550,7 @@ motif_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 }
             }
             const bool last = c + 1 == L.m3.nch;
-            tc_mma_round(x, H, kcols, colM1, c != 0, last ? L.sp.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? bytes_sp : 0) : bytes_m3);
+            tc_mma_round(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? bytes_e : 0) : bytes_m3);
         }
         // ---- MLP.5 + sigmoid (:199-200)
         float z5 = 0.f;
@@ -586,48 +558,38 @@ motif_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             float z[16];
             tc::tmem_ld16(tmem + lane_base + colM1 + c0, z);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) z5 = fmaf(fmaxf(z[i] + cst[L.m_m3b + c0 + i], 0.f), cst[L.m_w5 + c0 + i], z5);
+            for (int i = 0; i < 16; ++i) z5 = fmaf(fmaxf(z[i] + cstM[L.m_m3b + c0 + i], 0.f), cstM[L.m_w5 + c0 + i], z5);
         }
         part[half][0][row] = z5;         // the score reduction's reads of part[] ended before the Q rounds' barriers
         tc::fence_before_sync();
-        __syncthreads();                 // also: all TMEM reads of this tile done before the next tile's MMAs overwrite U
+        __syncthreads();                 // also: all TMEM reads of this tile done before the next tile's MMAs overwrite it
         tc::fence_after_sync();
-        if (live && half == 0) a.scores[gm] = 1.f / (1.f + expf(-(part[0][0][row] + part[1][0][row] + cst[L.m_b5])));
-        // next tile's first write to part[] comes after the barriers of its [S; P] rounds
+        if (live && half == 0) a.scores[gm] = 1.f / (1.f + expf(-(part[0][0][row] + part[1][0][row] + cstM[L.m_b5])));
+        // the next write to part[] comes after the barriers of the next tile's rounds
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
 }
 
-// Motifs per slab: a whole number of waves of the motif kernel (2 CTAs per SM x 128 motifs), small enough that the
-// slab's h rows (1.5 KB per motif) stay in the 126 MB L2 between the event and the motif kernel.
+// Motifs whose h rows the workspace holds: two resident CTAs per SM x 128 motifs (tm_encoder_workspace_floats)
 int64_t tc_slab_motifs() {
     static int64_t v = 0;
     if (!v) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const char *e = getenv("TEMPME_TC_SLAB_WAVES");
-        const int waves = e ? std::max(1, atoi(e)) : 4;        // measured on cfg2: 1 -> 422, 2 -> 453, 4 -> 462, 8 -> 453 M motifs/s (launch ramps vs L2 residency of h)
-        v = (int64_t)sms * 2 * 128 * waves;
+        v = (int64_t)sms * 2 * 128;
     }
     return v;
 }
 
-// optional per-kernel timing (bench.py roofline): CUDA events around every launch of the two kernels
+// optional kernel timing (bench.py roofline): CUDA events around the launch
 static bool g_prof = false;
-static std::vector<cudaEvent_t> g_prof_ev;      // triples: before event kernel, between, after motif kernel
+static std::vector<cudaEvent_t> g_prof_ev;      // pairs: before, after
 static size_t g_prof_used = 0;
 
-// dynamic shared memory padded so that at most `ctas` CTAs fit an SM (TMEM columns are not part of the occupancy
-// calculation: a CTA beyond 512 / tmem_cols would spin in tcgen05.alloc while holding its other resources)
-static size_t pad_smem(size_t need, int ctas) {
-    const size_t excl = (size_t)228 * 1024 / (ctas + 1);          // with this much per CTA, ctas + 1 of them do not fit
-    return std::max(need, std::min(excl, (size_t)227 * 1024 - 4096));
-}
-
-// std_ = per-batch std (already computed); F = workspace for two slabs
+// std_ = per-batch std (already computed); F = scratch for the h slabs of the resident CTAs
 int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
                     const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
                     int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
@@ -637,93 +599,42 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     if (device < 0 || device >= 64) { set_error("tc_encode_score: device index out of range"); return TM_ERR_UNSUPPORTED; }
     const int H = L.H;
     const bool alias_e = L.g0.nch == 1 && L.D16 <= H;
-    uint32_t cols_e = 32, cols_m = 32;
-    while ((int)cols_e < (alias_e ? 2 * H : 2 * H + L.D16)) cols_e <<= 1;
-    while ((int)cols_m < 3 * H) cols_m <<= 1;
-    if (cols_e > 512) { set_error("tc_encode_score: node_dim too large for the TMEM layout"); return TM_ERR_UNSUPPORTED; }
-    const int bb_e = (int)std::max(chunk_floats(L.evt), chunk_floats(L.g0)) * 4;
-    const int bb_m = (int)std::max(std::max(chunk_floats(L.sp), chunk_floats(L.q)), std::max(chunk_floats(L.r), chunk_floats(L.m3))) * 4;
-    const size_t need_e = (size_t)2 * kATile + bb_e + (size_t)((L.n_cstE + 3) & ~3) * 4 + 64 * 8;
-    const size_t need_m = (size_t)2 * kATile + bb_m + (size_t)((L.n_cstM + 3) & ~3) * 4;
-    if (need_e > 220 * 1024) { set_error("tc_encode_score: feature dims too large for one weight chunk in shared memory"); return TM_ERR_UNSUPPORTED; }
+    uint32_t cols = 32;
+    while ((int)cols < std::max(3 * H, alias_e ? 2 * H : 2 * H + L.D16)) cols <<= 1;
+    if (cols > 512) { set_error("tc_encode_score: node_dim too large for the TMEM layout"); return TM_ERR_UNSUPPORTED; }
+    int64_t bb = 0;
+    for (const TcLin *l : {&L.evt, &L.g0, &L.sp, &L.q, &L.r, &L.m3}) bb = std::max(bb, chunk_floats(*l) * 4);
+    const size_t need = (size_t)2 * kATile + (size_t)bb + (size_t)(L.n_cstE + L.n_cstM) * 4 + 64 * 8;
+    if (need > 220 * 1024) { set_error("tc_encode_score: feature dims too large for one weight chunk in shared memory"); return TM_ERR_UNSUPPORTED; }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const char *ce = getenv("TEMPME_TC_EVENT_CTAS");
-    int ctas_e = std::min<int>(512 / cols_e, (int)((228 * 1024) / (need_e + 1024 + 64)));
-    ctas_e = std::max(1, std::min(ctas_e, ce ? std::max(1, atoi(ce)) : 4));
-    const int ctas_m = std::max(1, std::min<int>(512 / cols_m, (int)((228 * 1024) / (need_m + 1024 + 2048))));
-    // the event kernel is compiled for three register budgets (2, 3 and 4 resident CTAs per SM)
-    using EvK = void (*)(const TcLayout, const float *, const TcArgs);
-    static const EvK ev_k[3] = {event_tc_kernel<2>, event_tc_kernel<3>, event_tc_kernel<4>};
+    // resident CTAs per SM: TMEM columns and shared memory (registers: __launch_bounds__(256, 2))
+    const int ctas = std::max(1, std::min<int>(2, std::min<int>(512 / cols, (int)((228 * 1024) / (need + 1024 + 4096)))));
+    // dynamic shared memory padded so that no more than `ctas` CTAs fit an SM (TMEM columns are not part of the occupancy
+    // calculation: a CTA beyond 512 / cols would spin in tcgen05.alloc while holding its other resources)
+    const size_t smem = std::max(need, std::min((size_t)228 * 1024 / (ctas + 1), (size_t)227 * 1024 - 4096));
     static bool attr_set[64] = {false};
-    static int ev_regs[3] = {0, 0, 0};
     if (!attr_set[device]) {
-        for (int v = 0; v < 3; ++v) {
-            TM_CUDA(cudaFuncSetAttribute(ev_k[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
-            TM_CUDA(cudaFuncSetAttribute(ev_k[v], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            cudaFuncAttributes fa;
-            TM_CUDA(cudaFuncGetAttributes(&fa, ev_k[v]));
-            ev_regs[v] = fa.numRegs;
-        }
-        TM_CUDA(cudaFuncSetAttribute(motif_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
-        TM_CUDA(cudaFuncSetAttribute(motif_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TM_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+        TM_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[device] = true;
     }
-    auto by_regs = [](int regs) { return 65536 / (((regs + 7) & ~7) * kTcThreads); };      // register file: 64K per SM, allocated in units of 8 per thread
-    const int ev_v = std::min(std::max(ctas_e, 2), 4) - 2;
-    const EvK event_kernel = ev_k[ev_v];
-    ctas_e = std::max(1, std::min(ctas_e, by_regs(ev_regs[ev_v])));
-    if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] event kernel: %d CTAs/SM (%d registers, smem %zu B, %u TMEM columns); motif kernel: %d CTAs/SM (smem %zu B)\n", ctas_e, ev_regs[ev_v], need_e, cols_e, ctas_m, need_m);
-    const size_t smem_e = pad_smem(need_e, ctas_e), smem_m = pad_smem(need_m, ctas_m);
     TcArgs a;
-    a.n_motifs = B * W; a.W = W; a.group = group; a.slab = tc_slab_motifs(); a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
+    a.n_motifs = B * W; a.W = W; a.group = group; a.m_begin = 0; a.slab = 0; a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
     a.eid = eid; a.node_feat = node_feat; a.edge_feat = edge_feat; a.std_ = std_; a.n_node_rows = n_node_rows; a.n_edge_rows = n_edge_rows;
-    a.F = F; a.scores = scores;
-    // Slabs alternate between two internal streams (each with its own F buffer) so that the ramp-down of one slab's
-    // motif kernel overlaps the next slab's event kernel; both fork from / join the caller's stream through events.
-    static cudaStream_t s2[64][2];
-    static cudaEvent_t ev_fork[64], ev_join[64][2];
-    static bool s2_init[64] = {false};
-    if (!s2_init[device]) {
-        for (int k = 0; k < 2; ++k) { TM_CUDA(cudaStreamCreateWithFlags(&s2[device][k], cudaStreamNonBlocking)); TM_CUDA(cudaEventCreateWithFlags(&ev_join[device][k], cudaEventDisableTiming)); }
-        TM_CUDA(cudaEventCreateWithFlags(&ev_fork[device], cudaEventDisableTiming));
-        s2_init[device] = true;
+    a.F = F; a.scores = scores; a.tmem_cols = cols; a.b_bytes = (int)bb;
+    const int64_t tiles = (a.n_motifs + 127) / 128, cap = (int64_t)sms * ctas;
+    const int64_t per_cta = (tiles + cap - 1) / cap;
+    const unsigned grid = (unsigned)((tiles + per_cta - 1) / per_cta);          // every CTA gets the same number of tiles (+-1); grid <= 2 * sms
+    if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] score kernel: %u CTAs (%d per SM), smem %zu B (needs %zu), %u TMEM columns, %lld tiles\n", grid, ctas, smem, need, cols, (long long)tiles);
+    cudaEvent_t *pe = nullptr;
+    if (g_prof && g_prof_used + 2 <= g_prof_ev.size()) {        // pool is created by tm_encoder_profile(1); when exhausted, stop recording
+        pe = &g_prof_ev[g_prof_used]; g_prof_used += 2;
+        cudaEventRecord(pe[0], st);
     }
-    const bool two = a.n_motifs > a.slab && !getenv("TEMPME_TC_SERIAL");
-    if (two) {
-        TM_CUDA(cudaEventRecord(ev_fork[device], st));
-        for (int k = 0; k < 2; ++k) TM_CUDA(cudaStreamWaitEvent(s2[device][k], ev_fork[device], 0));
-    }
-    const int64_t f_floats = ((a.slab + 127) / 128) * 128 * 3 * 2 * (int64_t)H;
-    auto balanced = [](int64_t tiles, int64_t cap) {          // every CTA gets the same number of tiles (+-1)
-        const int64_t rounds = (tiles + cap - 1) / cap;
-        return (unsigned)((tiles + rounds - 1) / rounds);
-    };
-    cudaStream_t caller = st;
-    int64_t islab = 0;
-    for (int64_t m0 = 0; m0 < a.n_motifs; m0 += a.slab, ++islab) {
-        st = two ? s2[device][islab & 1] : caller;
-        a.F = F + (two ? (islab & 1) * f_floats : 0);
-        a.m_begin = m0;
-        const int64_t nm = std::min(a.slab, a.n_motifs - m0);
-        const int64_t tiles_m = (nm + 127) / 128, tiles_e = 3 * tiles_m;
-        cudaEvent_t *pe = nullptr;
-        if (g_prof && g_prof_used + 3 <= g_prof_ev.size()) {        // pool is created by tm_encoder_profile(1); when exhausted, stop recording
-            pe = &g_prof_ev[g_prof_used]; g_prof_used += 3;
-            cudaEventRecord(pe[0], st);
-        }
-        a.tmem_cols = cols_e; a.b_bytes = bb_e;
-        event_kernel<<<balanced(tiles_e, (int64_t)sms * ctas_e), kTcThreads, smem_e, st>>>(L, d_blob_tc, a);
-        TM_LAUNCH_CHECK();
-        if (pe) cudaEventRecord(pe[1], st);
-        a.tmem_cols = cols_m; a.b_bytes = bb_m;
-        motif_tc_kernel<<<balanced(tiles_m, (int64_t)sms * ctas_m), kTcThreads, smem_m, st>>>(L, d_blob_tc, a);
-        TM_LAUNCH_CHECK();
-        if (pe) cudaEventRecord(pe[2], st);
-    }
-    st = caller;
-    if (two)
-        for (int k = 0; k < 2; ++k) { TM_CUDA(cudaEventRecord(ev_join[device][k], s2[device][k])); TM_CUDA(cudaStreamWaitEvent(st, ev_join[device][k], 0)); }
+    score_tc_kernel<<<grid, kTcThreads, smem, st>>>(L, d_blob_tc, a);
+    TM_LAUNCH_CHECK();
+    if (pe) cudaEventRecord(pe[1], st);
     return TM_OK;
 }
 
@@ -733,23 +644,24 @@ extern "C" int tm_encoder_profile(int enable) {
     tmb::g_prof = enable != 0;
     tmb::g_prof_used = 0;
     if (enable && tmb::g_prof_ev.empty()) {          // event pool, created outside any timed region
-        tmb::g_prof_ev.resize(3 * 4096);
+        tmb::g_prof_ev.resize(2 * 4096);
         for (auto &e : tmb::g_prof_ev) TM_CUDA(cudaEventCreate(&e));
     }
     return TM_OK;
 }
 
+// h_event_ms: accumulated milliseconds of score_tc_kernel since the last read; h_motif_ms: 0 (the event-level and the
+// motif-level phases are one kernel)
 extern "C" int tm_encoder_profile_read(float *h_event_ms, float *h_motif_ms) {
     if (!h_event_ms || !h_motif_ms) { tmb::set_error("tm_encoder_profile_read: null output"); return TM_ERR_ARG; }
-    double e = 0, m = 0;
-    for (size_t i = 0; i + 2 < tmb::g_prof_used && i + 2 < tmb::g_prof_ev.size(); i += 3) {
-        float a = 0, b = 0;
-        TM_CUDA(cudaEventSynchronize(tmb::g_prof_ev[i + 2]));
+    double e = 0;
+    for (size_t i = 0; i + 1 < tmb::g_prof_used && i + 1 < tmb::g_prof_ev.size(); i += 2) {
+        float a = 0;
+        TM_CUDA(cudaEventSynchronize(tmb::g_prof_ev[i + 1]));
         TM_CUDA(cudaEventElapsedTime(&a, tmb::g_prof_ev[i], tmb::g_prof_ev[i + 1]));
-        TM_CUDA(cudaEventElapsedTime(&b, tmb::g_prof_ev[i + 1], tmb::g_prof_ev[i + 2]));
-        e += a; m += b;
+        e += a;
     }
-    *h_event_ms = (float)e; *h_motif_ms = (float)m;
+    *h_event_ms = (float)e; *h_motif_ms = 0.f;
     tmb::g_prof_used = 0;
     return TM_OK;
 }
