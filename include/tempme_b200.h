@@ -171,14 +171,19 @@ int tm_encode_score(const tm_encoder_desc *desc, const float *d_blob, int64_t B,
                     float *d_workspace, float *d_scores, int device, tm_stream stream);
 
 /* Per-kernel timing of the tensor-core scorer (CUDA events around every launch of its two kernels on the caller's
- * stream).  tm_encoder_profile(1) starts collecting; tm_encoder_profile_read returns the accumulated milliseconds of
- * the event-level and the motif-level kernel since the last read (synchronises on the recorded events). */
+ * stream).  tm_encoder_profile(1) starts collecting; tm_encoder_profile_read returns in h_event_ms the accumulated
+ * milliseconds of the scorer kernel since the last read (synchronises on the recorded events); h_motif_ms is 0 since the
+ * event-level and the motif-level phases run as one kernel. */
 int tm_encoder_profile(int enable);
 int tm_encoder_profile_read(float *h_event_ms, float *h_motif_ms);
 
 /* Hardware self-test of the tcgen05/TMEM conventions the scorer relies on: C[128,N] = A[128,K] * B[N,K]^T on the
  * tensor cores (mode 0: one TF32 pass, mode 1: 3xTF32 split accumulation).  K % 8 == 0, N % 16 == 0, N <= 256. */
 int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, int K, int N, int mode, tm_stream stream);
+
+/* Self-test of the TimeEncode cosine (reference models/explainer.py:55-58): d_out[i] = cos(d_x[i]) evaluated by the
+ * scorer's device routine (exact integer argument reduction; arguments reach 1e8 and beyond). */
+int tm_selftest_cos(const float *d_x, float *d_out, int64_t n, tm_stream stream);
 
 /* Launch counter: number of kernels this library has launched in this process (bench gpu_launches). */
 uint64_t tm_launch_count(void);

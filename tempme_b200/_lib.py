@@ -55,6 +55,7 @@ SIGNATURES = {
     "tm_encoder_profile": (C.c_int, [C.c_int]),
     "tm_encoder_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tm_selftest_gemm": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p]),
+    "tm_selftest_cos": (C.c_int, [_p, _p, _i64, _p]),
     "tm_encode_score": (C.c_int, [C.POINTER(EncoderDesc), _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p,
                                   _p, _i64, _p, _i64, _p, _p, C.c_int, _p]),
 }

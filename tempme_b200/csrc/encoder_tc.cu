@@ -16,7 +16,7 @@
 // [edge features | TimeEncode]; the three edge-identity columns are added on the CUDA cores; position-2 rows have
 // dt = 0, so their TimeEncode chunks collapse into a bias; event_conv.MLP.0 + ReLU for the two orientations) and the
 // motif rounds ([S; P] h_2 -> scores -> temporal weights, softmax -> + Q mix -> R -> MLP.3 -> MLP.5 + sigmoid).
-// Thread (row, half) of the 256 owns TMEM lane `row` and 16 of the 32 columns of every K chunk: it reads the previous
+// Thread (row, part) owns TMEM lane `row` and CW of the 32 columns of every K chunk (CW = 8: 512 threads): it reads the previous
 // accumulator row with tcgen05.ld, applies bias / ReLU / mixing in fp32 registers, splits into tf32 hi + lo and stores
 // the K-major operand tile in shared memory; weights arrive pre-split and pre-tiled by 1-D bulk TMA.
 #include <math.h>
@@ -28,11 +28,11 @@
 
 #include "common.cuh"
 #include "tc.cuh"
+#include "timeenc.cuh"
 
 namespace tmb {
 
 constexpr int kKC = 32;           // K columns per operand chunk
-constexpr int kTcThreads = 256;   // 128 rows x 2 column halves
 constexpr int kSlabFloats = 128 * kKC;
 constexpr uint32_t kATile = 128 * kKC * 4;
 
@@ -200,6 +200,8 @@ struct TcCtx {
     uint32_t mma_phase, b_phase;
     uint32_t tmem;
     const float *blob;
+    long long *dbg;        // TEMPME_TC_TIMING: thread 0 of CTA 0 stamps 5 clocks per round (entry, after sync, weights landed, MMAs issued, MMAs done)
+    int dbg_i;
 };
 
 __device__ __forceinline__ void tc_request_b(const TcCtx &x, int64_t off, int bytes) {       // one thread
@@ -217,11 +219,15 @@ __device__ __forceinline__ void store_a4(const TcCtx &x, int row, int k, float4 
 
 // fill() has written this thread's share of the A tiles.  next_bytes != 0: weight chunk of the CTA's next round.
 __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d_col, bool accumulate, int64_t next_off, int next_bytes) {
+    const bool tim = x.dbg && threadIdx.x == 0 && x.dbg_i < 128;
+    if (tim) x.dbg[x.dbg_i * 5 + 0] = clock64();
     tc::fence_smem_to_async();
     tc::fence_before_sync();
     __syncthreads();
+    if (tim) x.dbg[x.dbg_i * 5 + 1] = clock64();
     if (threadIdx.x < 32) {          // warp 0 (warp-uniform): one elected lane issues
         tc::mbar_wait(x.bars + 1, x.b_phase);
+        if (tim) x.dbg[x.dbg_i * 5 + 2] = clock64();
         tc::fence_after_sync();
         const uint32_t leader = tc::elect_one();
         const uint32_t idesc = tc::idesc_tf32(128, n16);
@@ -237,14 +243,21 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
             ah += da; al += da; bh += db; bl += db;
         }
         tc::mma_commit(x.bars, leader);
+        if (tim) x.dbg[x.dbg_i * 5 + 3] = clock64();
         __syncwarp();
     }
     x.b_phase ^= 1;
     tc::mbar_wait(x.bars, x.mma_phase);
+    if (tim) x.dbg[x.dbg_i * 5 + 4] = clock64();
+    if (x.dbg) x.dbg_i++;
     x.mma_phase ^= 1;
     tc::fence_after_sync();
     if (threadIdx.x == 0 && next_bytes) tc_request_b(x, next_off, next_bytes);       // the weight buffer is free again
 }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(tc::smem_u32(mbar)) : "memory"); }
+constexpr int kStageRow = 36;     // floats per staged feature row piece: 128 bytes + 16 bytes of padding (conflict-free 16-byte reads down a column of rows)
+constexpr int kStageTable = 128 * kStageRow;
 
 struct TcArgs {
     int64_t n_motifs, W, group, m_begin;     // this launch scores motifs [m_begin, m_begin + slab)
@@ -258,46 +271,13 @@ struct TcArgs {
     float *scores;
     uint32_t tmem_cols;
     int b_bytes;                             // bytes of the weight-chunk buffer
+    int stage_off;                           // byte offset of the node-feature staging (src rows, then tgt rows); 0: gather with plain loads
+    int stage_edge_off;                      // byte offset of the edge-feature staging; 0: gather with plain loads
+    long long *dbg;                          // TEMPME_TC_TIMING: 128 x 5 clock stamps of CTA 0
 };
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-
-// cos(x) for the TimeEncode arguments (they reach 1e8 and beyond, where the library cosf takes its slow path).
-// Exact argument reduction in integer arithmetic: |x| = m * 2^e with a 24-bit integer m, so frac(|x| / 2pi) =
-// frac(m * frac(2^e / 2pi)); kInv2Pi[e + 44] holds frac(2^e / 2pi) in 0.64 fixed point, of which the top 32 bits of the
-// product are kept (error < 2^-32 turn = 1.5e-9 rad).  The turn fraction is split into a quadrant and an angle in
-// [-pi/4, pi/4) for the fdlibm single-precision sin/cos kernels.  Max error ~1.5 ulp of 1.0 against the exact cosine
-// of the fp32 argument over |x| <= 1e11 (cosf: 1-2 ulp); |x| >= 2^43, inf and nan go to cosf.  The table is read from
-// shared memory (a copy of kInv2Pi): lanes index it with different exponents.
-__constant__ unsigned long long kInv2Pi[64] = {
-    0x0000000000028be6ull, 0x00000000000517ccull, 0x00000000000a2f98ull, 0x0000000000145f30ull, 0x000000000028be60ull, 0x0000000000517cc1ull,
-    0x0000000000a2f983ull, 0x000000000145f306ull, 0x00000000028be60dull, 0x000000000517cc1bull, 0x000000000a2f9836ull, 0x00000000145f306dull,
-    0x0000000028be60dbull, 0x00000000517cc1b7ull, 0x00000000a2f9836eull, 0x0000000145f306dcull, 0x000000028be60db9ull, 0x0000000517cc1b72ull,
-    0x0000000a2f9836e4ull, 0x000000145f306dc9ull, 0x00000028be60db93ull, 0x000000517cc1b727ull, 0x000000a2f9836e4eull, 0x00000145f306dc9cull,
-    0x0000028be60db939ull, 0x00000517cc1b7272ull, 0x00000a2f9836e4e4ull, 0x0000145f306dc9c8ull, 0x000028be60db9391ull, 0x0000517cc1b72722ull,
-    0x0000a2f9836e4e44ull, 0x000145f306dc9c88ull, 0x00028be60db93910ull, 0x000517cc1b727220ull, 0x000a2f9836e4e441ull, 0x00145f306dc9c882ull,
-    0x0028be60db939105ull, 0x00517cc1b727220aull, 0x00a2f9836e4e4415ull, 0x0145f306dc9c882aull, 0x028be60db9391054ull, 0x0517cc1b727220a9ull,
-    0x0a2f9836e4e44152ull, 0x145f306dc9c882a5ull, 0x28be60db9391054aull, 0x517cc1b727220a94ull, 0xa2f9836e4e441529ull, 0x45f306dc9c882a53ull,
-    0x8be60db9391054a7ull, 0x17cc1b727220a94full, 0x2f9836e4e441529full, 0x5f306dc9c882a53full, 0xbe60db9391054a7full, 0x7cc1b727220a94feull,
-    0xf9836e4e441529fcull, 0xf306dc9c882a53f8ull, 0xe60db9391054a7f0ull, 0xcc1b727220a94fe1ull, 0x9836e4e441529fc2ull, 0x306dc9c882a53f84ull,
-    0x60db9391054a7f09ull, 0xc1b727220a94fe13ull, 0x836e4e441529fc27ull, 0x06dc9c882a53f84eull};
-
-__device__ __forceinline__ float cos_accurate(float x, const uint2 *tab) {
-    const uint32_t bits = __float_as_uint(x) & 0x7fffffffu;
-    const int e = (int)(bits >> 23) - 150;                 // |x| = m * 2^e
-    if (e > 19) return cosf(x);
-    const uint32_t m = e < -44 ? 0u : ((bits & 0x7fffffu) | 0x800000u);        // tiny |x|: angle 0
-    const uint2 T = tab[max(e, -44) + 44];                 // {low, high} words of frac(2^e / 2pi)
-    const uint32_t fr = m * T.y + __umulhi(m, T.x) + (1u << 29);               // turn fraction + 1/8 turn, 0.32 fixed point
-    const int q = (int)(fr >> 30);
-    const int r = (int)(fr & 0x3fffffffu) - (1 << 29);                          // angle inside the quadrant, [-1/8, 1/8) turn
-    const float th = (float)r * 1.46291807926715968e-9f /* 2 pi / 2^32 */, z = th * th;
-    const float cs = fmaf(z, fmaf(z, fmaf(z, fmaf(z, 2.43904487962774090654e-5f, -1.38867637746099294692e-3f), 4.16666233237390631894e-2f), -4.99999997251031003120e-1f), 1.f);
-    const float sn = fmaf(th * z, fmaf(z, fmaf(z, fmaf(z, 2.7183114939898219064e-6f, -1.98393348360966317347e-4f), 8.3333293858894631756e-3f), -1.66666666416265235595e-1f), th);
-    const float v = (q & 1) ? sn : cs;                     // cos(q pi/2 + th) = {cs, -sn, -cs, sn}[q]
-    return ((q + 1) & 2) ? -v : v;
-}
 
 // ---------------------------------------------------------------------------------------------
 // score_tc_kernel: one persistent launch scores all motifs.  A CTA (256 threads = 128 motifs x 2 column halves, two
@@ -313,20 +293,27 @@ __device__ __forceinline__ float cos_accurate(float x, const uint2 *tab) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 
-__global__ void __launch_bounds__(kTcThreads, 2)
+template <int CW> __device__ __forceinline__ void tmem_ldw(uint32_t taddr, float *v);
+template <> __device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, float *v) { tc::tmem_ld16(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, float *v) { tc::tmem_ld8(taddr, v); }
+
+template <int CW>            // columns of a K chunk per thread: 16 -> 256 threads, 8 -> 512 threads
+__global__ void __launch_bounds__(128 * (kKC / CW), 2)
 score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
+    constexpr int kParts = kKC / CW, kThreads = 128 * kParts;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bars[4];              // [0] MMAs done, [1] weight chunk landed, [2] staged node-feature rows landed, [3] staged edge-feature rows landed
     __shared__ uint32_t tmem_slot;
-    __shared__ float part[2][3][128];
-    const int t = threadIdx.x, warp = t >> 5, row = t & 127, half = t >> 7, kb = 16 * half;
+    __shared__ float part[kParts][3][128];
+    const int t = threadIdx.x, warp = t >> 5, row = t & 127, prt = t >> 7, kb = CW * prt;
     TcCtx x;
     x.a = smem; x.a_s = tc::smem_u32(smem); x.b_s = x.a_s + 2 * kATile; x.bars = bars; x.mma_phase = 0; x.b_phase = 0; x.blob = blob;
+    x.dbg = blockIdx.x == 0 ? a.dbg : nullptr; x.dbg_i = 0;
     float *cstE = reinterpret_cast<float *>(smem + 2 * kATile + a.b_bytes), *cstM = cstE + L.n_cstE;
     uint2 *ctab = reinterpret_cast<uint2 *>(cstM + L.n_cstM);
-    for (int i = t; i < L.n_cstE + L.n_cstM; i += kTcThreads) cstE[i] = __ldg(blob + L.cstE + i);      // cstM follows cstE in the blob
-    if (t < 64) ctab[t] = make_uint2((uint32_t)kInv2Pi[t], (uint32_t)(kInv2Pi[t] >> 32));
-    if (t == 0) { tc::mbar_init(bars, 1); tc::mbar_init(bars + 1, 1); }
+    for (int i = t; i < L.n_cstE + L.n_cstM; i += kThreads) cstE[i] = __ldg(blob + L.cstE + i);      // cstM follows cstE in the blob
+    cos_table_to_smem(ctab);
+    if (t == 0) { tc::mbar_init(bars, 1); tc::mbar_init(bars + 1, 1); tc::mbar_init(bars + 2, kThreads); tc::mbar_init(bars + 3, kThreads); }
     if (warp == 0) tc::tmem_alloc(&tmem_slot, a.tmem_cols);
     tc::fence_before_sync();
     __syncthreads();
@@ -343,11 +330,55 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     const bool ed_vec = (Ed & 3) == 0, d_vec = (D & 3) == 0;
     float *Fs = a.F + (int64_t)blockIdx.x * 12 * kSlabFloats;           // this CTA's h slabs: [position][column chunk][piece k/4][128 rows][4]
     const float *F0 = Fs, *F1 = Fs + 4 * kSlabFloats, *F2 = Fs + 8 * kSlabFloats;
-    // this thread's 16 columns [kb, kb+16) of row `row` of a [128 x 32] slab (four coalesced 16-byte pieces)
-    auto ld16 = [&](const float *slab, float *v) {
+    // this thread's CW columns [kb, kb+CW) of row `row` of a [128 x 32] slab (coalesced 16-byte pieces)
+    auto ldw = [&](const float *slab, float *v) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) { const float4 f = ldcg4(slab + ((kb >> 2) + g) * 512 + row * 4); v[4 * g] = f.x; v[4 * g + 1] = f.y; v[4 * g + 2] = f.z; v[4 * g + 3] = f.w; }
+        for (int g = 0; g < CW / 4; ++g) { const float4 f = ldcg4(slab + ((kb >> 2) + g) * 512 + row * 4); v[4 * g] = f.x; v[4 * g + 1] = f.y; v[4 * g + 2] = f.z; v[4 * g + 3] = f.w; }
     };
+
+    // Per-pass operands of this thread's row are fetched one pass ahead: the indices, dt and the edge-identity counts with
+    // plain loads; the two endpoints' feature rows (one 128-byte piece per K chunk) by 1-D bulk TMA into padded staging
+    // rows (thread part 0 requests the source row, part 1 the target row; every thread arrives on bars[2] once per request).
+    struct PassIdx { int32_t e, ns, nt; float dt, ei0, ei1, ei2; };
+    auto load_idx = [&](int64_t g, bool lv, int pos) {
+        PassIdx q; q.e = -1; q.ns = -1; q.nt = -1; q.dt = 0.f; q.ei0 = q.ei1 = q.ei2 = 0.f;
+        if (lv) {
+            q.e = a.eidx[g * 3 + pos]; q.ns = a.nodes[g * 6 + 2 * pos]; q.nt = a.nodes[g * 6 + 2 * pos + 1];
+            q.dt = __fsub_rn(a.t[g * 3 + 2], a.t[g * 3 + pos]);                          // explainer.py:326
+            if (a.eid) { const float *ei = a.eid + g * 9 + pos * 3; q.ei0 = __ldg(ei); q.ei1 = __ldg(ei + 1); q.ei2 = __ldg(ei + 2); }
+        }
+        return q;
+    };
+    const bool stage_nodes = a.stage_off != 0;
+    float *stg = reinterpret_cast<float *>(smem + a.stage_off);
+    uint32_t n_phase = 0;
+    auto request_nodes = [&](const PassIdx &q, int c) {       // chunk c of both endpoints' rows (:348-351)
+        if (!stage_nodes) return;
+        const int idx = prt == 0 ? q.ns : q.nt, bytes = min(kKC, D - c * kKC) * 4;
+        if (prt < 2 && idx >= 0 && idx < a.n_node_rows) {
+            tc::mbar_expect_tx(bars + 2, (uint32_t)bytes);
+            tc::tma_load_1d(stg + prt * kStageTable + row * kStageRow, a.node_feat + (int64_t)idx * D + c * kKC, (uint32_t)bytes, bars + 2);
+        } else mbar_arrive(bars + 2);
+    };
+    const bool stage_edges = a.stage_edge_off != 0;
+    float *stg_e = reinterpret_cast<float *>(smem + a.stage_edge_off);
+    uint32_t e_phase = 0;
+    auto request_edges = [&](const PassIdx &q, int c) {       // chunk c of the edge-feature rows (:332-338); part 0 requests
+        if (!stage_edges) return;
+        const int bytes = min(kKC, Ed - c * kKC) * 4;
+        if (prt == 0 && q.e >= 0 && q.e < a.n_edge_rows) {
+            tc::mbar_expect_tx(bars + 3, (uint32_t)bytes);
+            tc::tma_load_1d(stg_e + row * kStageRow, a.edge_feat + (int64_t)q.e * Ed + c * kKC, (uint32_t)bytes, bars + 3);
+        } else mbar_arrive(bars + 3);
+    };
+    PassIdx pcur, pnext;
+    {
+        const int64_t g0_ = (int64_t)blockIdx.x * 128 + row;
+        const bool lv = blockIdx.x < n_tiles && g0_ < n_m;
+        pcur = load_idx(lv ? g0_ : 0, lv, 0);
+        pnext = pcur;
+        if (blockIdx.x < n_tiles) { request_nodes(pcur, 0); request_edges(pcur, 0); }
+    }
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t gm_ = tile * 128 + row;
@@ -357,111 +388,142 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll 1
         for (int pos = 0; pos < 3; ++pos) {
             const int nE = pos == 2 ? L.nch_edge : L.evt.nch;          // position 2: dt = 0, the pure TimeEncode chunks are in the bias
-            int64_t e = 0, ns = 0, nt = 0; float dt = 0.f, ei0 = 0.f, ei1 = 0.f, ei2 = 0.f;
-            if (live) {
-                e = a.eidx[gm * 3 + pos]; ns = a.nodes[gm * 6 + 2 * pos]; nt = a.nodes[gm * 6 + 2 * pos + 1];
-                dt = __fsub_rn(a.t[gm * 3 + 2], a.t[gm * 3 + pos]);                       // explainer.py:326
-                if (a.eid) { const float *ei = a.eid + gm * 9 + pos * 3; ei0 = __ldg(ei); ei1 = __ldg(ei + 1); ei2 = __ldg(ei + 2); }
-            }
-            const bool e_ok = live && e >= 0 && e < a.n_edge_rows, s_ok = live && ns >= 0 && ns < a.n_node_rows, t_ok = live && nt >= 0 && nt < a.n_node_rows;
-            const float *ef = a.edge_feat + e * Ed, *sf = a.node_feat + ns * D, *tf = a.node_feat + nt * D;
+            const PassIdx pi = pcur;
+            if (pos < 2) pnext = load_idx(gm, live, pos + 1);
+            const bool e_ok = pi.e >= 0 && pi.e < a.n_edge_rows, s_ok = pi.ns >= 0 && pi.ns < a.n_node_rows, t_ok = pi.nt >= 0 && pi.nt < a.n_node_rows;
+            const float *ef = a.edge_feat + (int64_t)max(pi.e, 0) * Ed, *sf = a.node_feat + (int64_t)max(pi.ns, 0) * D, *tf = a.node_feat + (int64_t)max(pi.nt, 0) * D;
             auto xval = [&](int j) -> float {                                              // [edge features | TimeEncode] column j (:179, :55-58)
                 if (j < Ed) return e_ok ? __ldg(ef + j) : 0.f;
                 const int k = j - Ed;
-                if (k < D) return live ? cos_accurate(__fadd_rn(__fmul_rn(dt, cstE[L.e_freq + k]), cstE[L.e_phase + k]), ctab) : 0.f;
+                if (k < D) return live ? cos_accurate(__fadd_rn(__fmul_rn(pi.dt, cstE[L.e_freq + k]), cstE[L.e_phase + k]), ctab) : 0.f;
                 return 0.f;
             };
             // ---- lin_event (:93) -> E
             for (int c = 0; c < nE; ++c) {
                 const int kcols = min(kKC, L.evt.K8 - c * kKC);
-                float4 v[4];
+                const bool has_edge = c < L.nch_edge;
+                if (stage_edges && has_edge) { tc::mbar_wait(bars + 3, e_phase); e_phase ^= 1; }        // chunk c of the edge rows has landed
+                const int j0 = c * kKC + kb;                        // this thread's columns [j0, j0 + CW) of [edge | TimeEncode]
+                if (ed_vec && j0 + CW <= Ed) {                      // all edge features (warp-uniform)
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int k = kb + 4 * g, j = c * kKC + k;
-                    if (k >= kcols) { v[g] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
-                    if (ed_vec && j + 3 < Ed) v[g] = e_ok ? ldg4(ef + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    else v[g] = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
+                    for (int g = 0; g < CW / 4; ++g)
+                        store_a4(x, row, kb + 4 * g, !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stg_e + row * kStageRow + kb + 4 * g) : ldg4(ef + j0 + 4 * g));
+                } else if (j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + L.D16 && kb + CW <= kcols) {      // all TimeEncode: straight-line code, the cosines interleave
+                    float w[CW];
+#pragma unroll
+                    for (int g = 0; g < CW / 4; ++g) {
+                        const float4 fq = lds4(cstE + L.e_freq + (j0 - Ed) + 4 * g), ph = lds4(cstE + L.e_phase + (j0 - Ed) + 4 * g);      // zero-padded to D16
+                        w[4 * g] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.x), ph.x), ctab); w[4 * g + 1] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.y), ph.y), ctab);
+                        w[4 * g + 2] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.z), ph.z), ctab); w[4 * g + 3] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.w), ph.w), ctab);
+                    }
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) w[i] = (j0 - Ed + i < D && live) ? w[i] : 0.f;
+#pragma unroll
+                    for (int g = 0; g < CW / 4; ++g) store_a4(x, row, kb + 4 * g, make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]));
+                } else {                                            // mixed columns
+#pragma unroll
+                    for (int g = 0; g < CW / 4; ++g) {
+                        const int k = kb + 4 * g, j = c * kKC + k;
+                        if (k >= kcols) continue;
+                        float4 v;
+                        if (ed_vec && j + 3 < Ed) v = !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stg_e + row * kStageRow + k) : ldg4(ef + j);
+                        else v = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
+                        store_a4(x, row, k, v);
+                    }
                 }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) if (kb + 4 * g < kcols) store_a4(x, row, kb + 4 * g, v[g]);
                 const bool last = c + 1 == nE;
                 tc_mma_round(x, L.D16, kcols, colE, c != 0, last ? L.g0.w : L.evt.w + (int64_t)(c + 1) * chunk_floats(L.evt), last ? bytes_g : bytes_e);
+                if (has_edge) {                                     // the staged chunk has been consumed
+                    if (c + 1 < L.nch_edge) request_edges(pi, c + 1);
+                    else if (pos < 2) request_edges(pnext, 0);
+                }
             }
             // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
             const int eb = pos == 2 ? L.e_b2 : L.e_b;
+            for (int c = 0; c < nG; ++c) {
+                const int kcols = min(kKC, L.g0.K8 - c * kKC);
+                if (stage_nodes) { tc::mbar_wait(bars + 2, n_phase); n_phase ^= 1; }          // chunk c of the rows has landed
 #pragma unroll 1
-            for (int o = 0; o < 2; ++o)
-                for (int c = 0; c < nG; ++c) {
-                    const int kcols = min(kKC, L.g0.K8 - c * kKC);
+                for (int o = 0; o < 2; ++o) {
                     if (kb < kcols) {
-                        float sv[16], gv[16];
+                        float sv[CW], gv[CW];
 #pragma unroll
-                        for (int k = 0; k < 16; k += 4) {       // the gathers first (explainer.py:348-351)
+                        for (int k = 0; k < CW; k += 4) {
                             const int j = c * kKC + kb + k;
-                            if (d_vec && j + 3 < D) {
-                                const float4 s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f), g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
+                            float4 s4, g4;
+                            if (stage_nodes) {
+                                s4 = s_ok ? lds4(stg + row * kStageRow + kb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                g4 = t_ok ? lds4(stg + kStageTable + row * kStageRow + kb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            } else if (d_vec && j + 3 < D) {
+                                s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f); g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                             } else {
+                                float w[8];
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) { sv[k + i] = (j + i < D && s_ok) ? __ldg(sf + j + i) : 0.f; gv[k + i] = (j + i < D && t_ok) ? __ldg(tf + j + i) : 0.f; }
+                                for (int i = 0; i < 4; ++i) { w[i] = (j + i < D && s_ok) ? __ldg(sf + j + i) : 0.f; w[4 + i] = (j + i < D && t_ok) ? __ldg(tf + j + i) : 0.f; }
+                                s4 = make_float4(w[0], w[1], w[2], w[3]); g4 = make_float4(w[4], w[5], w[6], w[7]);
                             }
+                            sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
                         }
-                        float evv[16];
-                        tc::tmem_ld16(tmem + lane_base + colE + c * kKC + kb, evv);
+                        float evv[CW];
+                        tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, evv);
 #pragma unroll
-                        for (int k = 0; k < 16; k += 4) {
+                        for (int k = 0; k < CW; k += 4) {
+                            const int j0 = c * kKC + kb + k;                 // < D16: constants are zero-padded
+                            const float4 bb = lds4(cstE + eb + j0), w0 = lds4(cstE + L.e_wi + j0), w1 = lds4(cstE + L.e_wi + L.D16 + j0), w2 = lds4(cstE + L.e_wi + 2 * L.D16 + j0);
+                            const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, w0v[4] = {w0.x, w0.y, w0.z, w0.w}, w1v[4] = {w1.x, w1.y, w1.z, w1.w}, w2v[4] = {w2.x, w2.y, w2.z, w2.w};
                             float z[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int j = c * kKC + kb + k + i;          // j < D16: constants are zero-padded
-                                float e_ = evv[k + i] + cstE[eb + j];
-                                e_ = fmaf(cstE[L.e_wi + j], ei0, e_); e_ = fmaf(cstE[L.e_wi + L.D16 + j], ei1, e_); e_ = fmaf(cstE[L.e_wi + 2 * L.D16 + j], ei2, e_);
+                                float e_ = evv[k + i] + bv[i];
+                                e_ = fmaf(w0v[i], pi.ei0, e_); e_ = fmaf(w1v[i], pi.ei1, e_); e_ = fmaf(w2v[i], pi.ei2, e_);
                                 const float p_ = o ? gv[k + i] : sv[k + i], q_ = o ? sv[k + i] : gv[k + i];
-                                z[i] = (j < D && live) ? p_ + fmaxf(q_ + e_, 0.f) : 0.f;
+                                z[i] = (j0 + i < D && live) ? p_ + fmaxf(q_ + e_, 0.f) : 0.f;
                             }
                             store_a4(x, row, kb + k, make_float4(z[0], z[1], z[2], z[3]));
                         }
                     }
                     const bool last = c + 1 == nG;
                     int64_t noff; int nbytes;
-                    if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
-                    else if (o == 0) { noff = L.g0.w; nbytes = bytes_g; }
+                    if (o == 0) { noff = L.g0.w + (int64_t)c * chunk_floats(L.g0); nbytes = bytes_g; }
+                    else if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
                     else if (pos < 2) { noff = L.evt.w; nbytes = bytes_e; }
                     else { noff = L.sp.w; nbytes = bytes_sp; }
                     tc_mma_round(x, H, kcols, colZ + o * H, c != 0, noff, nbytes);
                 }
-            // ---- h_pos = relu(MLP.0 + bias): half o owns orientation o = column chunks 2o, 2o+1
-            {
-                float *fo = Fs + (pos * 4 + 2 * half) * kSlabFloats + row * 4;
-                for (int c0 = 0; c0 < H; c0 += 16) {
-                    float v[16];
-                    tc::tmem_ld16(tmem + lane_base + colZ + half * H + c0, v);
-                    float *fc = fo + (c0 >> 5) * kSlabFloats + ((c0 & 31) >> 2) * 512;
+                // the staged chunk has been consumed (both orientations' fills ended before the last round's barrier)
+                if (c + 1 < nG) request_nodes(pi, c + 1);
+                else if (pos < 2) request_nodes(pnext, 0);
+            }
+            // ---- h_pos = relu(MLP.0 + bias): thread part p owns columns [4 CW p, 4 CW (p + 1)) of [Zs | Zt]
+            for (int c0 = 4 * CW * prt; c0 < 4 * CW * (prt + 1); c0 += 16) {
+                float v[16];
+                tc::tmem_ld16(tmem + lane_base + colZ + c0, v);
+                float *fc = Fs + (pos * 4 + (c0 >> 5)) * kSlabFloats + ((c0 & 31) >> 2) * 512 + row * 4;
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const float4 bb = lds4(cstE + L.e_g0b + c0 + i);
-                        __stcg(reinterpret_cast<float4 *>(fc + (i >> 2) * 512),
-                               make_float4(fmaxf(v[i] + bb.x, 0.f), fmaxf(v[i + 1] + bb.y, 0.f), fmaxf(v[i + 2] + bb.z, 0.f), fmaxf(v[i + 3] + bb.w, 0.f)));
-                    }
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 bb = lds4(cstE + L.e_g0b + (c0 & (H - 1)) + i);
+                    __stcg(reinterpret_cast<float4 *>(fc + (i >> 2) * 512),
+                           make_float4(fmaxf(v[i] + bb.x, 0.f), fmaxf(v[i + 1] + bb.y, 0.f), fmaxf(v[i + 2] + bb.z, 0.f), fmaxf(v[i + 3] + bb.w, 0.f)));
                 }
             }
             tc::fence_before_sync();
             __syncthreads();            // TMEM reads done before the next pass overwrites E / Z; the h slabs are visible to the CTA
             tc::fence_after_sync();
+            if (pos < 2) pcur = pnext;
         }
         // =========================== motif rounds ===========================
         // ---- [U | Y] = [S; P] h_2 ; r = d . h_2
         float rp = 0.f;
         {
-            float nxt[16];
-            ld16(F2, nxt);
+            float nxt[CW];
+            ldw(F2, nxt);
             for (int c = 0; c < nchS; ++c) {
-                float cur[16];
+                float cur[CW];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
-                if (c + 1 < nchS) ld16(F2 + (c + 1) * kSlabFloats, nxt);
+                for (int i = 0; i < CW; ++i) cur[i] = nxt[i];
+                if (c + 1 < nchS) ldw(F2 + (c + 1) * kSlabFloats, nxt);
 #pragma unroll
-                for (int k = 0; k < 16; k += 4) {
+                for (int k = 0; k < CW; k += 4) {
                     const float4 dd = lds4(cstM + L.m_d + c * kKC + kb + k);
                     rp = fmaf(dd.x, cur[k], rp); rp = fmaf(dd.y, cur[k + 1], rp); rp = fmaf(dd.z, cur[k + 2], rp); rp = fmaf(dd.w, cur[k + 3], rp);
                     store_a4(x, row, kb + k, make_float4(cur[k], cur[k + 1], cur[k + 2], cur[k + 3]));
@@ -474,15 +536,15 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll 1
         for (int c = 0; c < nchS; c += 2) {
-            float p0[2][16], p1[2][16];
+            float p0[2][CW], p1[2][CW];
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) { ld16(F0 + (c + cc) * kSlabFloats, p0[cc]); ld16(F1 + (c + cc) * kSlabFloats, p1[cc]); }
+            for (int cc = 0; cc < 2; ++cc) { ldw(F0 + (c + cc) * kSlabFloats, p0[cc]); ldw(F1 + (c + cc) * kSlabFloats, p1[cc]); }
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
-                float u[16];
-                tc::tmem_ld16(tmem + lane_base + colU + (c + cc) * kKC + kb, u);
+                float u[CW];
+                tmem_ldw<CW>(tmem + lane_base + colU + (c + cc) * kKC + kb, u);
 #pragma unroll
-                for (int k = 0; k < 16; k += 4) {
+                for (int k = 0; k < CW; k += 4) {
                     const float4 cu = lds4(cstM + L.m_cu + (c + cc) * kKC + kb + k);
                     const float u0 = u[k] + cu.x, u1 = u[k + 1] + cu.y, u2 = u[k + 2] + cu.z, u3 = u[k + 3] + cu.w;
                     s0 = fmaf(p0[cc][k], u0, s0); s0 = fmaf(p0[cc][k + 1], u1, s0); s0 = fmaf(p0[cc][k + 2], u2, s0); s0 = fmaf(p0[cc][k + 3], u3, s0);
@@ -490,14 +552,16 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 }
             }
         }
-        float n0[16], n1[16];                       // mix operands of the first Q round, in flight across the reduction
-        ld16(F0, n0); ld16(F1, n1);
-        part[half][0][row] = s0; part[half][1][row] = s1; part[half][2][row] = rp;
+        float n0[CW], n1[CW];                       // mix operands of the first Q round, in flight across the reduction
+        ldw(F0, n0); ldw(F1, n1);
+        part[prt][0][row] = s0; part[prt][1][row] = s1; part[prt][2][row] = rp;
         __syncthreads();
         {
-            const float r_ = part[0][2][row] + part[1][2][row] + cstM[L.m_e];
-            s0 = part[0][0][row] + part[1][0][row] + r_;
-            s1 = part[0][1][row] + part[1][1][row] + r_;
+            float r_ = cstM[L.m_e];
+            s0 = 0.f; s1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < kParts; ++q) { s0 += part[q][0][row]; s1 += part[q][1][row]; r_ += part[q][2][row]; }
+            s0 += r_; s1 += r_;
         }
         // ---- temporal weighting + softmax (:811-839)
         if (L.use_temporal && live) {
@@ -511,23 +575,28 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         const float al0 = e0 / (e0 + e1), al1 = e1 / (e0 + e1);
         // ---- Y += Q (alpha_0 h_0 + alpha_1 h_1)   (:841-843 after folding)
         for (int c = 0; c < nchS; ++c) {
-            float c0[16], c1[16];
+            float c0[CW], c1[CW];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { c0[i] = n0[i]; c1[i] = n1[i]; }
-            if (c + 1 < nchS) { ld16(F0 + (c + 1) * kSlabFloats, n0); ld16(F1 + (c + 1) * kSlabFloats, n1); }
+            for (int i = 0; i < CW; ++i) { c0[i] = n0[i]; c1[i] = n1[i]; }
+            if (c + 1 < nchS) { ldw(F0 + (c + 1) * kSlabFloats, n0); ldw(F1 + (c + 1) * kSlabFloats, n1); }
 #pragma unroll
-            for (int k = 0; k < 16; k += 4)
+            for (int k = 0; k < CW; k += 4)
                 store_a4(x, row, kb + k, make_float4(fmaf(al0, c0[k], al1 * c1[k]), fmaf(al0, c0[k + 1], al1 * c1[k + 1]),
                                                      fmaf(al0, c0[k + 2], al1 * c1[k + 2]), fmaf(al0, c0[k + 3], al1 * c1[k + 3])));
             const bool last = c + 1 == nchS;
             tc_mma_round(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 1) * chunk_floats(L.q), last ? bytes_r : bytes_q);
         }
-        // ---- M0 = R relu(Y + cy)   (attention.MLP.3 and MLP.0 folded)
+        // ---- M0 = R relu(Y + cy)   (attention.MLP.3 and MLP.0 folded); the next tile's first-pass indices start to arrive
+        {
+            const int64_t gn = (tile + gridDim.x) * 128 + row;
+            const bool lv = more && gn < n_m;
+            pcur = load_idx(lv ? gn : 0, lv, 0);
+        }
         for (int c = 0; c < L.r.nch; ++c) {
-            float z[16];
-            tc::tmem_ld16(tmem + lane_base + colY + c * kKC + kb, z);
+            float z[CW];
+            tmem_ldw<CW>(tmem + lane_base + colY + c * kKC + kb, z);
 #pragma unroll
-            for (int k = 0; k < 16; k += 4) {
+            for (int k = 0; k < CW; k += 4) {
                 const float4 bb = lds4(cstM + L.m_cy + c * kKC + kb + k);
                 store_a4(x, row, kb + k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
             }
@@ -539,10 +608,10 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         for (int c = 0; c < L.m3.nch; ++c) {
             const int kcols = min(kKC, L.m3.K8 - c * kKC);
             if (kb < kcols) {
-                float z[16];
-                tc::tmem_ld16(tmem + lane_base + colM0 + c * kKC + kb, z);      // columns < M16 (kcols is a multiple of 8, M16 of 16)
+                float z[CW];
+                tmem_ldw<CW>(tmem + lane_base + colM0 + c * kKC + kb, z);      // columns < M16 (kcols is a multiple of 8, M16 of 16)
 #pragma unroll
-                for (int k = 0; k < 16; k += 4) {
+                for (int k = 0; k < CW; k += 4) {
                     const float4 bb = ldg4(cmr + c * kKC + kb + k);
                     const int j = c * kKC + kb + k;
                     store_a4(x, row, kb + k, make_float4(j < L.M ? fmaxf(z[k] + bb.x, 0.f) : 0.f, j + 1 < L.M ? fmaxf(z[k + 1] + bb.y, 0.f) : 0.f,
@@ -551,20 +620,26 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             }
             const bool last = c + 1 == L.m3.nch;
             tc_mma_round(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? bytes_e : 0) : bytes_m3);
+            if (c == 0 && more) { request_nodes(pcur, 0); request_edges(pcur, 0); }          // the staging overlaps the weight buffer of the larger motif-round chunks; MLP.3's are small
         }
         // ---- MLP.5 + sigmoid (:199-200)
         float z5 = 0.f;
-        for (int c0 = half * (H / 2); c0 < half * (H / 2) + H / 2; c0 += 16) {
+        for (int c0 = prt * (H / kParts); c0 < (prt + 1) * (H / kParts); c0 += 16) {
             float z[16];
             tc::tmem_ld16(tmem + lane_base + colM1 + c0, z);
 #pragma unroll
             for (int i = 0; i < 16; ++i) z5 = fmaf(fmaxf(z[i] + cstM[L.m_m3b + c0 + i], 0.f), cstM[L.m_w5 + c0 + i], z5);
         }
-        part[half][0][row] = z5;         // the score reduction's reads of part[] ended before the Q rounds' barriers
+        part[prt][0][row] = z5;         // the score reduction's reads of part[] ended before the Q rounds' barriers
         tc::fence_before_sync();
         __syncthreads();                 // also: all TMEM reads of this tile done before the next tile's MMAs overwrite it
         tc::fence_after_sync();
-        if (live && half == 0) a.scores[gm] = 1.f / (1.f + expf(-(part[0][0][row] + part[1][0][row] + cstM[L.m_b5])));
+        if (live && prt == 0) {
+            float zz = cstM[L.m_b5];
+#pragma unroll
+            for (int q = 0; q < kParts; ++q) zz += part[q][0][row];
+            a.scores[gm] = 1.f / (1.f + expf(-zz));
+        }
         // the next write to part[] comes after the barriers of the next tile's rounds
     }
     tc::fence_before_sync();
@@ -604,25 +679,51 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     if (cols > 512) { set_error("tc_encode_score: node_dim too large for the TMEM layout"); return TM_ERR_UNSUPPORTED; }
     int64_t bb = 0;
     for (const TcLin *l : {&L.evt, &L.g0, &L.sp, &L.q, &L.r, &L.m3}) bb = std::max(bb, chunk_floats(*l) * 4);
-    const size_t need = (size_t)2 * kATile + (size_t)bb + (size_t)(L.n_cstE + L.n_cstM) * 4 + 64 * 8;
+    // node-feature rows are gathered by bulk TMA into a staging area that may overlap the tail of the weight buffer: rows
+    // are in flight only while lin_event / MLP.0 / MLP.3 chunks are being loaded, so it starts behind the largest of those
+    const bool stage_nodes = L.D % 4 == 0 && ((uintptr_t)node_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING");
+    const bool stage_edges = L.Ed % 4 == 0 && ((uintptr_t)edge_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && !getenv("TEMPME_TC_NO_EDGE_STAGING");
+    const int64_t stage_rel = (std::max(std::max(chunk_floats(L.evt), chunk_floats(L.g0)), chunk_floats(L.m3)) * 4 + 127) & ~(int64_t)127;
+    const int64_t stage_edge_rel = stage_rel + (stage_nodes ? (int64_t)2 * kStageTable * 4 : 0);
+    bb = std::max(bb, stage_edge_rel + (stage_edges ? (int64_t)kStageTable * 4 : 0));
+    const size_t need = (size_t)2 * kATile + (size_t)bb + (size_t)(L.n_cstE + L.n_cstM) * 4 + 152 * 8;
     if (need > 220 * 1024) { set_error("tc_encode_score: feature dims too large for one weight chunk in shared memory"); return TM_ERR_UNSUPPORTED; }
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    // resident CTAs per SM: TMEM columns and shared memory (registers: __launch_bounds__(256, 2))
-    const int ctas = std::max(1, std::min<int>(2, std::min<int>(512 / cols, (int)((228 * 1024) / (need + 1024 + 4096)))));
-    // dynamic shared memory padded so that no more than `ctas` CTAs fit an SM (TMEM columns are not part of the occupancy
-    // calculation: a CTA beyond 512 / cols would spin in tcgen05.alloc while holding its other resources)
-    const size_t smem = std::max(need, std::min((size_t)228 * 1024 / (ctas + 1), (size_t)227 * 1024 - 4096));
+    using ScoreK = void (*)(const TcLayout, const float *, const TcArgs);
+    static const ScoreK kern[2] = {score_tc_kernel<8>, score_tc_kernel<16>};
     static bool attr_set[64] = {false};
     if (!attr_set[device]) {
-        TM_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
-        TM_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        for (ScoreK k : kern) {
+            TM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
+            TM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
         attr_set[device] = true;
     }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const char *cw_env = getenv("TEMPME_TC_CW");                 // columns per thread per K chunk: 16 (256 threads, default) or 8 (512 threads)
+    const int cw = cw_env && atoi(cw_env) == 8 ? 8 : 16;
+    static size_t static_smem[2] = {0, 0};
+    if (!static_smem[0])
+        for (int v = 0; v < 2; ++v) { cudaFuncAttributes fa; TM_CUDA(cudaFuncGetAttributes(&fa, kern[v])); static_smem[v] = fa.sharedSizeBytes; }
+    // resident CTAs per SM: TMEM columns and shared memory (registers: __launch_bounds__(threads, 2))
+    const int ctas = std::max(1, std::min<int>(2, std::min<int>(512 / cols, (int)((228 * 1024) / (need + 1024 + static_smem[cw == 16])))));
+    // dynamic shared memory padded so that no more than `ctas` CTAs fit an SM (TMEM columns are not part of the occupancy
+    // calculation: a CTA beyond 512 / cols would spin in tcgen05.alloc while holding its other resources)
+    const size_t smem = std::max(need, std::min((size_t)228 * 1024 / (ctas + 1), (size_t)227 * 1024 - 8192));
+
     TcArgs a;
     a.n_motifs = B * W; a.W = W; a.group = group; a.m_begin = 0; a.slab = 0; a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
     a.eid = eid; a.node_feat = node_feat; a.edge_feat = edge_feat; a.std_ = std_; a.n_node_rows = n_node_rows; a.n_edge_rows = n_edge_rows;
-    a.F = F; a.scores = scores; a.tmem_cols = cols; a.b_bytes = (int)bb;
+    a.F = F; a.scores = scores; a.tmem_cols = cols; a.b_bytes = (int)bb; a.dbg = nullptr;
+    a.stage_off = stage_nodes ? (int)(2 * kATile + stage_rel) : 0;
+    a.stage_edge_off = stage_edges ? (int)(2 * kATile + stage_edge_rel) : 0;
+    static long long *dbg_buf = nullptr;
+    const char *tim_env = getenv("TEMPME_TC_TIMING");          // diagnostic: per-round clock stamps of CTA 0
+    if (tim_env) {
+        if (!dbg_buf) TM_CUDA(cudaMalloc(&dbg_buf, 128 * 5 * sizeof(long long)));
+        TM_CUDA(cudaMemsetAsync(dbg_buf, 0, 128 * 5 * sizeof(long long), st));
+        a.dbg = dbg_buf;
+    }
     const int64_t tiles = (a.n_motifs + 127) / 128, cap = (int64_t)sms * ctas;
     const int64_t per_cta = (tiles + cap - 1) / cap;
     const unsigned grid = (unsigned)((tiles + per_cta - 1) / per_cta);          // every CTA gets the same number of tiles (+-1); grid <= 2 * sms
@@ -632,9 +733,18 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         pe = &g_prof_ev[g_prof_used]; g_prof_used += 2;
         cudaEventRecord(pe[0], st);
     }
-    score_tc_kernel<<<grid, kTcThreads, smem, st>>>(L, d_blob_tc, a);
+    kern[cw == 16]<<<grid, 128 * (kKC / cw), smem, st>>>(L, d_blob_tc, a);
     TM_LAUNCH_CHECK();
     if (pe) cudaEventRecord(pe[1], st);
+    if (tim_env) {
+        TM_CUDA(cudaStreamSynchronize(st));
+        std::vector<long long> h(128 * 5);
+        TM_CUDA(cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[tc timing] CTA 0: round: fill+gap | fence+sync | weights wait | MMA issue | MMA done wait || round total   (cycles)\n");
+        for (int r = 1; r < 128 && h[r * 5 + 4]; ++r)
+            fprintf(stderr, "  %3d: %6lld %6lld %6lld %6lld %6lld || %6lld\n", r, h[r * 5] - h[(r - 1) * 5 + 4], h[r * 5 + 1] - h[r * 5], h[r * 5 + 2] - h[r * 5 + 1],
+                    h[r * 5 + 3] - h[r * 5 + 2], h[r * 5 + 4] - h[r * 5 + 3], h[r * 5 + 4] - h[(r - 1) * 5 + 4]);
+    }
     return TM_OK;
 }
 

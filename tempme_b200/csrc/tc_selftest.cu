@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "tc.cuh"
+#include "timeenc.cuh"
 
 namespace tmb {
 
@@ -99,6 +100,23 @@ selftest_gemm_kernel(const float *__restrict__ A, const float *__restrict__ B, f
 }  // namespace tmb
 
 using namespace tmb;
+
+namespace tmb {
+__global__ void selftest_cos_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t n) {
+    __shared__ uint2 ctab[kInv2PiN];
+    cos_table_to_smem(ctab);
+    __syncthreads();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = cos_accurate(x[i], ctab);
+}
+}  // namespace tmb
+
+extern "C" int tm_selftest_cos(const float *d_x, float *d_out, int64_t n, tm_stream stream) {
+    if (!d_x || !d_out || n < 0) { set_error("tm_selftest_cos: bad argument"); return TM_ERR_ARG; }
+    if (n == 0) return TM_OK;
+    selftest_cos_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}
 
 extern "C" int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, int K, int N, int mode, tm_stream stream) {
     if (mode == 3 && (K % 16 || N + 2 * K > 512)) { set_error("tm_selftest_gemm: TS mode needs K %% 16 == 0 and N + 2K <= 512"); return TM_ERR_ARG; }

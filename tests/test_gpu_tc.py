@@ -37,3 +37,37 @@ def test_selftest_gemm_3xtf32(K, N):
     # 3xTF32 must be at fp32-sgemm level: compare with the fp32 product
     f32 = (A @ B.T).astype(np.float64)
     assert np.abs(out - ref).max() <= 4 * np.abs(f32 - ref).max() + 1e-6 * scale.max()
+
+
+def test_timeencode_cosine_accuracy():
+    """The scorer's cosine (exact integer argument reduction) against float64 cos of the same fp32 argument, from
+    denormals to the largest finite fp32 (TimeEncode arguments dt * basis_freq reach 1e8, reference explainer.py:55-58)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tempme_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(7)
+    mags = 10.0 ** rng.uniform(-12, 38.4, 400000)
+    x = np.concatenate([(mags * rng.choice([-1.0, 1.0], mags.size)), rng.uniform(-1e8, 1e8, 400000), rng.uniform(-40, 40, 100000),
+                        np.arange(0, 4096) * (np.pi / 2), [0.0, -0.0, 1e-45, 3.4028234e38, -3.4028234e38]]).astype(np.float32)
+    dx = torch.as_tensor(x).cuda(); out = torch.empty_like(dx)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.tm_selftest_cos(_lib.ptr(dx), _lib.ptr(out), x.size, st), "tm_selftest_cos")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.float64)
+    # exact reference: reduce the fp32 argument modulo 2 pi with exact rational arithmetic for the huge ones
+    import math
+    from fractions import Fraction
+    small = np.abs(x) < 1e15
+    ref = np.cos(x.astype(np.float64))
+    err = np.abs(got - ref)
+    assert err[small].max() < 2.5e-7, err[small].max()
+    PI = Fraction(3141592653589793238462643383279502884197169399375105820974944592307816406286208998628034825342117067982148086513282306647, 10 ** 120)
+    big = np.flatnonzero(~small)[:300]
+    for i in big:
+        f = Fraction(float(x[i]))
+        r = f - (f // (2 * PI)) * (2 * PI)
+        assert abs(got[i] - math.cos(float(r))) < 2.5e-7, (x[i], got[i], math.cos(float(r)))
+    bad = torch.tensor([float("inf"), float("-inf"), float("nan")], device="cuda"); o2 = torch.zeros(3, device="cuda")
+    _lib.check(L.tm_selftest_cos(_lib.ptr(bad), _lib.ptr(o2), 3, st), "tm_selftest_cos")
+    assert torch.isnan(o2).all()
