@@ -36,6 +36,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-Xcompiler", "-fPIC,-fopenmp", "-shared", "-o", LIB] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    if os.environ.get("TEMPME_BUILD_TIMING"):          # diagnostic build: per-round clock stamps in the scorer (TEMPME_TC_TIMING=1 at run time)
+        cmd.insert(1, "-DTM_TC_TIMING")
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

@@ -219,7 +219,11 @@ __device__ __forceinline__ void store_a4(const TcCtx &x, int row, int k, float4 
 
 // fill() has written this thread's share of the A tiles.  next_bytes != 0: weight chunk of the CTA's next round.
 __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d_col, bool accumulate, int64_t next_off, int next_bytes) {
+#ifdef TM_TC_TIMING
     const bool tim = x.dbg && threadIdx.x == 0 && x.dbg_i < 128;
+#else
+    constexpr bool tim = false;        // clock stamps compiled out (build with -DTM_TC_TIMING, TEMPME_BUILD_TIMING=1)
+#endif
     if (tim) x.dbg[x.dbg_i * 5 + 0] = clock64();
     tc::fence_smem_to_async();
     tc::fence_before_sync();
@@ -249,7 +253,9 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
     x.b_phase ^= 1;
     tc::mbar_wait(x.bars, x.mma_phase);
     if (tim) x.dbg[x.dbg_i * 5 + 4] = clock64();
+#ifdef TM_TC_TIMING
     if (x.dbg) x.dbg_i++;
+#endif
     x.mma_phase ^= 1;
     tc::fence_after_sync();
     if (threadIdx.x == 0 && next_bytes) tc_request_b(x, next_off, next_bytes);       // the weight buffer is free again
@@ -718,7 +724,11 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.stage_off = stage_nodes ? (int)(2 * kATile + stage_rel) : 0;
     a.stage_edge_off = stage_edges ? (int)(2 * kATile + stage_edge_rel) : 0;
     static long long *dbg_buf = nullptr;
+#ifdef TM_TC_TIMING
     const char *tim_env = getenv("TEMPME_TC_TIMING");          // diagnostic: per-round clock stamps of CTA 0
+#else
+    const char *tim_env = nullptr;                             // needs a -DTM_TC_TIMING build (TEMPME_BUILD_TIMING=1 python -m tempme_b200.build)
+#endif
     if (tim_env) {
         if (!dbg_buf) TM_CUDA(cudaMalloc(&dbg_buf, 128 * 5 * sizeof(long long)));
         TM_CUDA(cudaMemsetAsync(dbg_buf, 0, 128 * 5 * sizeof(long long), st));
