@@ -194,8 +194,9 @@ int tc_pack(const tm_encoder_desc &d, const tm_encoder_params &p, float *blob) {
 // round's MMAs completed; the co-resident CTAs of the SM cover each other's waits.
 // ---------------------------------------------------------------------------------------------
 struct TcCtx {
-    uint8_t *a;            // A operand: hi tile, then lo tile
+    uint8_t *a;            // A operand in shared memory (SS mode): hi tile, then lo tile
     uint32_t a_s, b_s;     // shared-space addresses of the A tiles and of the weight buffer
+    uint32_t a_col;        // A operand in TMEM (TS mode): hi at columns [a_col, a_col + 32), lo at [a_col + 32, a_col + 64)
     uint64_t *bars;        // [0] MMAs done, [1] weight chunk landed
     uint32_t mma_phase, b_phase;
     uint32_t tmem;
@@ -209,15 +210,35 @@ __device__ __forceinline__ void tc_request_b(const TcCtx &x, int64_t off, int by
     tc::tma_load_1d_s(x.b_s, x.blob + off, (uint32_t)bytes, x.bars + 1);
 }
 
-__device__ __forceinline__ void store_a4(const TcCtx &x, int row, int k, float4 v) {
-    float4 h, l;
-    tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
-    uint8_t *p = x.a + tc::tile_off(128, row, k);
-    *reinterpret_cast<float4 *>(p) = h;
-    *reinterpret_cast<float4 *>(p + kATile) = l;
-}
+// A-fill of one round.  SS mode: 16-byte pieces of the hi / lo operand tiles in shared memory.  TS mode: the thread's CW columns are
+// collected in registers and written to its TMEM lane with tcgen05.st (commit); kk = column offset inside the thread's CW columns.
+template <int CW, bool TS>
+struct AFill {
+    float hi[TS ? CW : 4], lo[TS ? CW : 4];
+    __device__ __forceinline__ void put4(const TcCtx &x, int row, int kb, int kk, float4 v) {
+        float4 h, l;
+        tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+        if (TS) {
+            hi[kk] = h.x; hi[kk + 1] = h.y; hi[kk + 2] = h.z; hi[kk + 3] = h.w;
+            lo[kk] = l.x; lo[kk + 1] = l.y; lo[kk + 2] = l.z; lo[kk + 3] = l.w;
+        } else {
+            uint8_t *p = x.a + tc::tile_off(128, row, kb + kk);
+            *reinterpret_cast<float4 *>(p) = h;
+            *reinterpret_cast<float4 *>(p + kATile) = l;
+        }
+    }
+    __device__ __forceinline__ void commit(const TcCtx &x, uint32_t lane_base, int kb) {       // all CW columns have been put
+        if (TS) {
+            const uint32_t a0 = x.tmem + lane_base + x.a_col + (uint32_t)kb;
+            if (CW == 16) { tc::tmem_st16(a0, hi); tc::tmem_st16(a0 + kKC, lo); }
+            else { tc::tmem_st8(a0, hi); tc::tmem_st8(a0 + kKC, lo); }
+            tc::tmem_st_wait();
+        }
+    }
+};
 
 // fill() has written this thread's share of the A tiles.  next_bytes != 0: weight chunk of the CTA's next round.
+template <bool TS>
 __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d_col, bool accumulate, int64_t next_off, int next_bytes) {
 #ifdef TM_TC_TIMING
     const bool tim = x.dbg && threadIdx.x == 0 && x.dbg_i < 128;
@@ -225,7 +246,7 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
     constexpr bool tim = false;        // clock stamps compiled out (build with -DTM_TC_TIMING, TEMPME_BUILD_TIMING=1)
 #endif
     if (tim) x.dbg[x.dbg_i * 5 + 0] = clock64();
-    tc::fence_smem_to_async();
+    if (!TS) tc::fence_smem_to_async();
     tc::fence_before_sync();
     __syncthreads();
     if (tim) x.dbg[x.dbg_i * 5 + 1] = clock64();
@@ -240,10 +261,17 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
         uint64_t bh = tc::smem_desc(x.b_s, lbo_b, 128), bl = tc::smem_desc(x.b_s + (uint32_t)n16 * kKC * 4, lbo_b, 128);
         const uint64_t da = (2 * lbo_a) >> 4, db = (2 * lbo_b) >> 4;      // descriptor start-address step per K = 8
         const uint32_t dcol = x.tmem + (uint32_t)d_col;
+        const uint32_t ta = x.tmem + x.a_col;
         for (int ks = 0; ks < kcols / 8; ++ks) {
-            tc::mma_tf32(dcol, ah, bh, idesc, (uint32_t)(accumulate || ks != 0), leader);
-            tc::mma_tf32(dcol, al, bh, idesc, 1, leader);
-            tc::mma_tf32(dcol, ah, bl, idesc, 1, leader);
+            if (TS) {
+                tc::mma_tf32_ts(dcol, ta + 8 * ks, bh, idesc, (uint32_t)(accumulate || ks != 0), leader);
+                tc::mma_tf32_ts(dcol, ta + kKC + 8 * ks, bh, idesc, 1, leader);
+                tc::mma_tf32_ts(dcol, ta + 8 * ks, bl, idesc, 1, leader);
+            } else {
+                tc::mma_tf32(dcol, ah, bh, idesc, (uint32_t)(accumulate || ks != 0), leader);
+                tc::mma_tf32(dcol, al, bh, idesc, 1, leader);
+                tc::mma_tf32(dcol, ah, bl, idesc, 1, leader);
+            }
             ah += da; al += da; bh += db; bl += db;
         }
         tc::mma_commit(x.bars, leader);
@@ -303,7 +331,8 @@ template <int CW> __device__ __forceinline__ void tmem_ldw(uint32_t taddr, float
 template <> __device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, float *v) { tc::tmem_ld16(taddr, v); }
 template <> __device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, float *v) { tc::tmem_ld8(taddr, v); }
 
-template <int CW>            // columns of a K chunk per thread: 16 -> 256 threads, 8 -> 512 threads
+// CW = columns of a K chunk per thread: 16 -> 256 threads, 8 -> 512 threads; TS = A operand in TMEM (else shared memory)
+template <int CW, bool TS>
 __global__ void __launch_bounds__(128 * (kKC / CW), 2)
 score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
     constexpr int kParts = kKC / CW, kThreads = 128 * kParts;
@@ -313,9 +342,9 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     __shared__ float part[kParts][3][128];
     const int t = threadIdx.x, warp = t >> 5, row = t & 127, prt = t >> 7, kb = CW * prt;
     TcCtx x;
-    x.a = smem; x.a_s = tc::smem_u32(smem); x.b_s = x.a_s + 2 * kATile; x.bars = bars; x.mma_phase = 0; x.b_phase = 0; x.blob = blob;
+    x.a = smem; x.a_s = tc::smem_u32(smem); x.b_s = x.a_s + (TS ? 0 : 2 * kATile); x.bars = bars; x.mma_phase = 0; x.b_phase = 0; x.blob = blob;
     x.dbg = blockIdx.x == 0 ? a.dbg : nullptr; x.dbg_i = 0;
-    float *cstE = reinterpret_cast<float *>(smem + 2 * kATile + a.b_bytes), *cstM = cstE + L.n_cstE;
+    float *cstE = reinterpret_cast<float *>(smem + (TS ? 0 : 2 * kATile) + a.b_bytes), *cstM = cstE + L.n_cstE;
     uint2 *ctab = reinterpret_cast<uint2 *>(cstM + L.n_cstM);
     for (int i = t; i < L.n_cstE + L.n_cstM; i += kThreads) cstE[i] = __ldg(blob + L.cstE + i);      // cstM follows cstE in the blob
     cos_table_to_smem(ctab);
@@ -325,7 +354,8 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    x.tmem = tmem;
+    x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC;
+    AFill<CW, TS> af;
     const int H = L.H, H2 = 2 * L.H, D = L.D, Ed = L.Ed, nG = L.g0.nch, nchS = L.sp.nch;
     const int colZ = 0, colE = (nG == 1 && L.D16 <= H) ? H : H2;
     const int colU = 0, colY = H2, colM0 = 0, colM1 = H2;
@@ -413,7 +443,8 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 if (ed_vec && j0 + CW <= Ed) {                      // all edge features (warp-uniform)
 #pragma unroll
                     for (int g = 0; g < CW / 4; ++g)
-                        store_a4(x, row, kb + 4 * g, !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stg_e + row * kStageRow + kb + 4 * g) : ldg4(ef + j0 + 4 * g));
+                        af.put4(x, row, kb, 4 * g, !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stg_e + row * kStageRow + kb + 4 * g) : ldg4(ef + j0 + 4 * g));
+                    af.commit(x, lane_base, kb);
                 } else if (j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + L.D16 && kb + CW <= kcols) {      // all TimeEncode: straight-line code, the cosines interleave
                     float w[CW];
 #pragma unroll
@@ -425,20 +456,23 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll
                     for (int i = 0; i < CW; ++i) w[i] = (j0 - Ed + i < D && live) ? w[i] : 0.f;
 #pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) store_a4(x, row, kb + 4 * g, make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]));
+                    for (int g = 0; g < CW / 4; ++g) af.put4(x, row, kb, 4 * g, make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]));
+                    af.commit(x, lane_base, kb);
                 } else {                                            // mixed columns
 #pragma unroll
                     for (int g = 0; g < CW / 4; ++g) {
                         const int k = kb + 4 * g, j = c * kKC + k;
-                        if (k >= kcols) continue;
-                        float4 v;
-                        if (ed_vec && j + 3 < Ed) v = !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stg_e + row * kStageRow + k) : ldg4(ef + j);
-                        else v = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
-                        store_a4(x, row, k, v);
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (k < kcols) {
+                            if (ed_vec && j + 3 < Ed) v = !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stg_e + row * kStageRow + k) : ldg4(ef + j);
+                            else v = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
+                        }
+                        if (TS || k < kcols) af.put4(x, row, kb, 4 * g, v);
                     }
+                    if (kb < kcols) af.commit(x, lane_base, kb);
                 }
                 const bool last = c + 1 == nE;
-                tc_mma_round(x, L.D16, kcols, colE, c != 0, last ? L.g0.w : L.evt.w + (int64_t)(c + 1) * chunk_floats(L.evt), last ? bytes_g : bytes_e);
+                tc_mma_round<TS>(x, L.D16, kcols, colE, c != 0, last ? L.g0.w : L.evt.w + (int64_t)(c + 1) * chunk_floats(L.evt), last ? bytes_g : bytes_e);
                 if (has_edge) {                                     // the staged chunk has been consumed
                     if (c + 1 < L.nch_edge) request_edges(pi, c + 1);
                     else if (pos < 2) request_edges(pnext, 0);
@@ -485,8 +519,9 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                                 const float p_ = o ? gv[k + i] : sv[k + i], q_ = o ? sv[k + i] : gv[k + i];
                                 z[i] = (j0 + i < D && live) ? p_ + fmaxf(q_ + e_, 0.f) : 0.f;
                             }
-                            store_a4(x, row, kb + k, make_float4(z[0], z[1], z[2], z[3]));
+                            af.put4(x, row, kb, k, make_float4(z[0], z[1], z[2], z[3]));
                         }
+                        af.commit(x, lane_base, kb);
                     }
                     const bool last = c + 1 == nG;
                     int64_t noff; int nbytes;
@@ -494,7 +529,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                     else if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
                     else if (pos < 2) { noff = L.evt.w; nbytes = bytes_e; }
                     else { noff = L.sp.w; nbytes = bytes_sp; }
-                    tc_mma_round(x, H, kcols, colZ + o * H, c != 0, noff, nbytes);
+                    tc_mma_round<TS>(x, H, kcols, colZ + o * H, c != 0, noff, nbytes);
                 }
                 // the staged chunk has been consumed (both orientations' fills ended before the last round's barrier)
                 if (c + 1 < nG) request_nodes(pi, c + 1);
@@ -532,10 +567,11 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 for (int k = 0; k < CW; k += 4) {
                     const float4 dd = lds4(cstM + L.m_d + c * kKC + kb + k);
                     rp = fmaf(dd.x, cur[k], rp); rp = fmaf(dd.y, cur[k + 1], rp); rp = fmaf(dd.z, cur[k + 2], rp); rp = fmaf(dd.w, cur[k + 3], rp);
-                    store_a4(x, row, kb + k, make_float4(cur[k], cur[k + 1], cur[k + 2], cur[k + 3]));
+                    af.put4(x, row, kb, k, make_float4(cur[k], cur[k + 1], cur[k + 2], cur[k + 3]));
                 }
+                af.commit(x, lane_base, kb);
                 const bool last = c + 1 == nchS;
-                tc_mma_round(x, 3 * H, kKC, colU, c != 0, last ? L.q.w : L.sp.w + (int64_t)(c + 1) * chunk_floats(L.sp), last ? bytes_q : bytes_sp);
+                tc_mma_round<TS>(x, 3 * H, kKC, colU, c != 0, last ? L.q.w : L.sp.w + (int64_t)(c + 1) * chunk_floats(L.sp), last ? bytes_q : bytes_sp);
             }
         }
         // ---- s_k = h_k . (U + cu) + r  (:806-808 after folding)
@@ -587,10 +623,11 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             if (c + 1 < nchS) { ldw(F0 + (c + 1) * kSlabFloats, n0); ldw(F1 + (c + 1) * kSlabFloats, n1); }
 #pragma unroll
             for (int k = 0; k < CW; k += 4)
-                store_a4(x, row, kb + k, make_float4(fmaf(al0, c0[k], al1 * c1[k]), fmaf(al0, c0[k + 1], al1 * c1[k + 1]),
-                                                     fmaf(al0, c0[k + 2], al1 * c1[k + 2]), fmaf(al0, c0[k + 3], al1 * c1[k + 3])));
+                af.put4(x, row, kb, k, make_float4(fmaf(al0, c0[k], al1 * c1[k]), fmaf(al0, c0[k + 1], al1 * c1[k + 1]),
+                                                   fmaf(al0, c0[k + 2], al1 * c1[k + 2]), fmaf(al0, c0[k + 3], al1 * c1[k + 3])));
+            af.commit(x, lane_base, kb);
             const bool last = c + 1 == nchS;
-            tc_mma_round(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 1) * chunk_floats(L.q), last ? bytes_r : bytes_q);
+            tc_mma_round<TS>(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 1) * chunk_floats(L.q), last ? bytes_r : bytes_q);
         }
         // ---- M0 = R relu(Y + cy)   (attention.MLP.3 and MLP.0 folded); the next tile's first-pass indices start to arrive
         {
@@ -604,10 +641,11 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll
             for (int k = 0; k < CW; k += 4) {
                 const float4 bb = lds4(cstM + L.m_cy + c * kKC + kb + k);
-                store_a4(x, row, kb + k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
+                af.put4(x, row, kb, k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
             }
+            af.commit(x, lane_base, kb);
             const bool last = c + 1 == L.r.nch;
-            tc_mma_round(x, L.M16, kKC, colM0, c != 0, last ? L.m3.w : L.r.w + (int64_t)(c + 1) * chunk_floats(L.r), last ? bytes_m3 : bytes_r);
+            tc_mma_round<TS>(x, L.M16, kKC, colM0, c != 0, last ? L.m3.w : L.r.w + (int64_t)(c + 1) * chunk_floats(L.r), last ? bytes_m3 : bytes_r);
         }
         // ---- M1 = MLP.3 relu(M0 + cm[category])   (:199)
         const float *cmr = blob + L.cm + (int64_t)((L.if_cat && live && a.cat) ? min((int)a.cat[gm], 11) : 0) * L.M16;
@@ -620,12 +658,13 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 for (int k = 0; k < CW; k += 4) {
                     const float4 bb = ldg4(cmr + c * kKC + kb + k);
                     const int j = c * kKC + kb + k;
-                    store_a4(x, row, kb + k, make_float4(j < L.M ? fmaxf(z[k] + bb.x, 0.f) : 0.f, j + 1 < L.M ? fmaxf(z[k + 1] + bb.y, 0.f) : 0.f,
-                                                         j + 2 < L.M ? fmaxf(z[k + 2] + bb.z, 0.f) : 0.f, j + 3 < L.M ? fmaxf(z[k + 3] + bb.w, 0.f) : 0.f));
+                    af.put4(x, row, kb, k, make_float4(j < L.M ? fmaxf(z[k] + bb.x, 0.f) : 0.f, j + 1 < L.M ? fmaxf(z[k + 1] + bb.y, 0.f) : 0.f,
+                                                       j + 2 < L.M ? fmaxf(z[k + 2] + bb.z, 0.f) : 0.f, j + 3 < L.M ? fmaxf(z[k + 3] + bb.w, 0.f) : 0.f));
                 }
+                af.commit(x, lane_base, kb);
             }
             const bool last = c + 1 == L.m3.nch;
-            tc_mma_round(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? bytes_e : 0) : bytes_m3);
+            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? bytes_e : 0) : bytes_m3);
             if (c == 0 && more) { request_nodes(pcur, 0); request_edges(pcur, 0); }          // the staging overlaps the weight buffer of the larger motif-round chunks; MLP.3's are small
         }
         // ---- MLP.5 + sigmoid (:199-200)
@@ -680,8 +719,10 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     if (device < 0 || device >= 64) { set_error("tc_encode_score: device index out of range"); return TM_ERR_UNSUPPORTED; }
     const int H = L.H;
     const bool alias_e = L.g0.nch == 1 && L.D16 <= H;
+    const char *ts_env = getenv("TEMPME_TC_A");                  // "smem": A operand in shared memory (SS); default: in TMEM (TS), the last 64 columns
+    const bool ts = !(ts_env && strcmp(ts_env, "smem") == 0);
     uint32_t cols = 32;
-    while ((int)cols < std::max(3 * H, alias_e ? 2 * H : 2 * H + L.D16)) cols <<= 1;
+    while ((int)cols < std::max(3 * H, alias_e ? 2 * H : 2 * H + L.D16) + (ts ? 2 * kKC : 0)) cols <<= 1;
     if (cols > 512) { set_error("tc_encode_score: node_dim too large for the TMEM layout"); return TM_ERR_UNSUPPORTED; }
     int64_t bb = 0;
     for (const TcLin *l : {&L.evt, &L.g0, &L.sp, &L.q, &L.r, &L.m3}) bb = std::max(bb, chunk_floats(*l) * 4);
@@ -692,10 +733,11 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     const int64_t stage_rel = (std::max(std::max(chunk_floats(L.evt), chunk_floats(L.g0)), chunk_floats(L.m3)) * 4 + 127) & ~(int64_t)127;
     const int64_t stage_edge_rel = stage_rel + (stage_nodes ? (int64_t)2 * kStageTable * 4 : 0);
     bb = std::max(bb, stage_edge_rel + (stage_edges ? (int64_t)kStageTable * 4 : 0));
-    const size_t need = (size_t)2 * kATile + (size_t)bb + (size_t)(L.n_cstE + L.n_cstM) * 4 + 152 * 8;
+    const size_t a_bytes = ts ? 0 : (size_t)2 * kATile;
+    const size_t need = a_bytes + (size_t)bb + (size_t)(L.n_cstE + L.n_cstM) * 4 + 152 * 8;
     if (need > 220 * 1024) { set_error("tc_encode_score: feature dims too large for one weight chunk in shared memory"); return TM_ERR_UNSUPPORTED; }
     using ScoreK = void (*)(const TcLayout, const float *, const TcArgs);
-    static const ScoreK kern[2] = {score_tc_kernel<8>, score_tc_kernel<16>};
+    static const ScoreK kern[4] = {score_tc_kernel<8, false>, score_tc_kernel<16, false>, score_tc_kernel<8, true>, score_tc_kernel<16, true>};
     static bool attr_set[64] = {false};
     if (!attr_set[device]) {
         for (ScoreK k : kern) {
@@ -708,11 +750,12 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const char *cw_env = getenv("TEMPME_TC_CW");                 // columns per thread per K chunk: 16 (256 threads, default) or 8 (512 threads)
     const int cw = cw_env && atoi(cw_env) == 8 ? 8 : 16;
-    static size_t static_smem[2] = {0, 0};
+    const int kv = (cw == 16) + 2 * ts;
+    static size_t static_smem[4] = {0, 0, 0, 0};
     if (!static_smem[0])
-        for (int v = 0; v < 2; ++v) { cudaFuncAttributes fa; TM_CUDA(cudaFuncGetAttributes(&fa, kern[v])); static_smem[v] = fa.sharedSizeBytes; }
+        for (int v = 0; v < 4; ++v) { cudaFuncAttributes fa; TM_CUDA(cudaFuncGetAttributes(&fa, kern[v])); static_smem[v] = fa.sharedSizeBytes; }
     // resident CTAs per SM: TMEM columns and shared memory (registers: __launch_bounds__(threads, 2))
-    const int ctas = std::max(1, std::min<int>(2, std::min<int>(512 / cols, (int)((228 * 1024) / (need + 1024 + static_smem[cw == 16])))));
+    const int ctas = std::max(1, std::min<int>(2, std::min<int>(512 / cols, (int)((228 * 1024) / (need + 1024 + static_smem[kv])))));
     // dynamic shared memory padded so that no more than `ctas` CTAs fit an SM (TMEM columns are not part of the occupancy
     // calculation: a CTA beyond 512 / cols would spin in tcgen05.alloc while holding its other resources)
     const size_t smem = std::max(need, std::min((size_t)228 * 1024 / (ctas + 1), (size_t)227 * 1024 - 8192));
@@ -721,8 +764,8 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.n_motifs = B * W; a.W = W; a.group = group; a.m_begin = 0; a.slab = 0; a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
     a.eid = eid; a.node_feat = node_feat; a.edge_feat = edge_feat; a.std_ = std_; a.n_node_rows = n_node_rows; a.n_edge_rows = n_edge_rows;
     a.F = F; a.scores = scores; a.tmem_cols = cols; a.b_bytes = (int)bb; a.dbg = nullptr;
-    a.stage_off = stage_nodes ? (int)(2 * kATile + stage_rel) : 0;
-    a.stage_edge_off = stage_edges ? (int)(2 * kATile + stage_edge_rel) : 0;
+    a.stage_off = stage_nodes ? (int)(a_bytes + stage_rel) : 0;
+    a.stage_edge_off = stage_edges ? (int)(a_bytes + stage_edge_rel) : 0;
     static long long *dbg_buf = nullptr;
 #ifdef TM_TC_TIMING
     const char *tim_env = getenv("TEMPME_TC_TIMING");          // diagnostic: per-round clock stamps of CTA 0
@@ -743,7 +786,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         pe = &g_prof_ev[g_prof_used]; g_prof_used += 2;
         cudaEventRecord(pe[0], st);
     }
-    kern[cw == 16]<<<grid, 128 * (kKC / cw), smem, st>>>(L, d_blob_tc, a);
+    kern[kv]<<<grid, 128 * (kKC / cw), smem, st>>>(L, d_blob_tc, a);
     TM_LAUNCH_CHECK();
     if (pe) cudaEventRecord(pe[1], st);
     if (tim_env) {
