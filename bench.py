@@ -283,12 +283,15 @@ def run_ours(args):
     row_off = rank * 3 * Q
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     gathered = torch.empty((world, 3 * Q, W), dtype=torch.float32, device=dev) if world > 1 else None
+    sync_token = torch.zeros(1, device=dev)
 
     def step(i, timers=None):
         scores = pipe.run_device(*dev_q[i], row_offset=row_off, timers=timers)
         if world > 1:       # the path's only exchanges: 12-bin histogram all-reduce + score gather
             dist.all_reduce(pipe.hist_null)
             dist.all_gather_into_tensor(gathered, scores)
+            if timers is not None:
+                ev = torch.cuda.Event(enable_timing=True); ev.record(); timers.append(("exchange", ev))
         return scores
 
     for i in range(args.warmup):
@@ -307,6 +310,8 @@ def run_ours(args):
     last = None
     for k in range(args.steps):
         flush.zero_()                                   # L2 flush between timed iterations (not timed)
+        if world > 1:
+            dist.all_reduce(sync_token)                 # ranks start the step together: host-side skew between steps must not leak into a peer's timed exchange
         timers = []
         last = step(args.warmup + k, timers)
         end = torch.cuda.Event(enable_timing=True); end.record()
@@ -348,6 +353,7 @@ def run_ours(args):
         "sample_walks": 3 * Q * n * (32 + 16 * N2) + M * (32 + 16 * e3_frac + 49) + 4.0 * S_total / args.steps,
         "edge_identity": M * 48.0,
         "encode": M * (4.0 * (6 * D + 3 * Ed) + 85 + 4),
+        "exchange": 96.0 + world * M * 4.0,
     }
     # algorithmic FLOPs of the reference formulation; the folded kernel executes fewer
     flops = {"encode": M * float(encoder_flops(D, Ed)), "score_tc": M * float(encoder_flops(D, Ed))}
@@ -358,7 +364,7 @@ def run_ours(args):
     dur_s = stage_ms[top] / args.steps * 1e-3
     kern = {"sample_hop": "sample_hop_kernel", "sample_walks": "sample_walks_kernel", "edge_identity": "edge_identity_kernel",
             "encode": "time_std_kernel + score_tc_kernel", "score_tc": "score_tc_kernel (tcgen05 3xTF32 scorer, one persistent launch)",
-            "encode_other": "time_std_kernel"}[top]
+            "encode_other": "time_std_kernel", "exchange": "NCCL all-reduce (histogram) + all-gather (scores)"}[top]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
