@@ -95,3 +95,45 @@ def forward(p, node_feat, edge_feat, walks, cut_time, edge_identify, dtype=np.fl
     out = 1.0 / (1.0 + np.exp(-z))                                               # :200
     out = out.astype(dt)
     return (out, h) if return_hidden else out
+
+
+def beta_mean(prob, dt=np.float32):
+    """TempME.beta_sample in eval mode, explainer.py:421-430: E[Beta(max(10 p, 1), max(10 (1 - p), 1))]."""
+    alpha = np.maximum(prob * dt(10), dt(1.0))
+    beta = np.maximum((dt(1) - prob) * dt(10), dt(1.0))
+    return alpha / (alpha + beta)
+
+
+def edge_importance(p, edge_feat, subgraph, graphlet_imp, walks, use_dependency=True, dtype=np.float32):
+    """TempME.retrieve_edge_imp_node, explainer.py:354-406, eval mode (training=False).
+
+    subgraph = (node_records [hop0 [B,n], hop1 [B,n^2]], eidx_records [same shapes], _); graphlet_imp [B,W,1] scores;
+    walks as in ``forward``.  Returns (edge_imp_0 [B,n], edge_imp_1 [B,n^2])."""
+    dt = dtype
+    node_record, eidx_record = subgraph[0], subgraph[1]
+    edge_walk = np.asarray(walks[1]).reshape(walks[1].shape[0], -1).astype(np.int64)       # [B, 3W]            :360
+    B = edge_walk.shape[0]
+    walk_imp = np.repeat(np.asarray(graphlet_imp).astype(dt).reshape(B, -1, 1), 3, axis=2).reshape(B, -1)   # :363
+    if use_dependency:
+        ef = np.asarray(edge_feat).astype(dt)[edge_walk]                                   # :369
+        tw = np.asarray(walks[2]).reshape(B, -1).astype(np.float32).astype(dt)             # :371 (.float())
+        te = time_encode(tw, p, dt)                                                         # :372 (the raw timestamps)
+        x = np.concatenate([ef, te], axis=-1)                                               # :375
+        h = np.maximum(_lin(x, p, "edge_dependency_gcn.0", dt), 0)                          # :143-151, Dropout = identity
+        h = np.maximum(_lin(h, p, "edge_dependency_gcn.3", dt), 0)
+        dep = _lin(h, p, "edge_dependency_gcn.6", dt)[..., 0]                               # :379
+        gate = dt(1) / (dt(1) + np.exp(-dep))                                               # :383
+        walk_imp = walk_imp * (dt(0.5) + dt(0.5) * gate)                                    # :386
+    outs = []
+    for l in range(2):
+        ids = np.asarray(eidx_record[l]).astype(np.int64)
+        imp = np.zeros(ids.shape, dt)
+        for b in range(B):                                                                  # scatter(max) over edge ids, then gather (:389-393)
+            m = {}
+            for e, v in zip(edge_walk[b], walk_imp[b]):
+                m[e] = max(m.get(e, dt(0)), v)
+            imp[b] = [m.get(e, dt(0)) for e in ids[b]]
+        imp = beta_mean(imp, dt)                                                            # :396-397
+        imp[np.asarray(node_record[l]) == 0] = 0                                            # :400-404
+        outs.append(imp.astype(dt))
+    return outs[0], outs[1]

@@ -14,6 +14,7 @@ Fixtures:
   uslegis.npz      the bundled processed/ml_uslegis_sampled events + reference outputs on test queries
   nullmodel.npz    utils/null_model.py pre_processing on an endpoint-shuffled copy (class histogram)
   encoder_*.npz    TempME.forward scores with the weights/features that produced them
+  edgeimp_*.npz    retrieve_edge_imp_node (eval mode) on those scores: `python tests/golden/make_golden.py edgeimp`
 """
 from __future__ import annotations
 
@@ -275,7 +276,71 @@ def gen_encoder(tag, walks5, edge_identity, cut_time, n_nodes, n_edges, D, Ed, s
     np.savez_compressed(os.path.join(HERE, f"encoder_{tag}.npz"), **out)
 
 
+def gen_edge_imp(tag, walks5, edge_identity, cut_time, subgraph, n_nodes, n_edges, D, Ed, seed):
+    """retrieve_edge_imp_node (reference models/explainer.py:354-406) in eval mode on the scores of the same module:
+    dependency gate (edge_dependency_gcn over [edge features | TimeEncode(raw t)]), per-query scatter-max over edge ids,
+    gather to the hop-1 / hop-2 slots, Beta mean, padding mask."""
+    import torch
+    import models.explainer as rexp
+    rexp.get_null_distribution = lambda data_name: {k: 1.0 / 12 for k in range(1, 13)}
+    torch.manual_seed(seed)
+    nfeat = torch.randn(n_nodes, D); efeat = torch.randn(n_edges, Ed)
+    nfeat[0] = 0; efeat[0] = 0
+
+    class Base:
+        n_feat_th = nfeat; e_feat_th = efeat
+        node_raw_features = torch.nn.Embedding.from_pretrained(nfeat, padding_idx=0, freeze=True)
+        edge_raw_features = torch.nn.Embedding.from_pretrained(efeat, padding_idx=0, freeze=True)
+
+    out = {}
+    for dep in (True, False):
+        torch.manual_seed(seed + 100)
+        m = rexp.TempME(Base(), "tgn", "uslegis_sampled", out_dim=40, hid_dim=64, device=torch.device("cpu"),
+                        use_dependency_aware_sampling=dep)
+        with torch.no_grad():
+            m.time_encoder.phase.copy_(0.1 * torch.randn(D))
+        m.eval()
+        with torch.no_grad():
+            score = m(walks5, cut_time, edge_identity)
+            imp0, imp1 = m.retrieve_edge_imp_node(subgraph, score, walks5, training=False)
+        k = "dep" if dep else "nodep"
+        out.update({f"{k}_score": score.numpy(), f"{k}_imp0": imp0.numpy(), f"{k}_imp1": imp1.numpy()})
+        if dep:
+            sd = m.state_dict()
+            out.update({"p:" + n: v.numpy() for n, v in sd.items() if n.startswith("edge_dependency_gcn.") or n.startswith("time_encoder.")})
+    out.update(edge_feat=efeat.numpy(), w_eidx=walks5[1].astype(np.int32), w_t=walks5[2].astype(np.float32),
+               h0_node=subgraph[0][0].astype(np.int32), h1_node=subgraph[0][1].astype(np.int32),
+               h0_eidx=subgraph[1][0].astype(np.int32), h1_eidx=subgraph[1][1].astype(np.int32))
+    np.savez_compressed(os.path.join(HERE, f"edgeimp_{tag}.npz"), **out)
+
+
+def gen_edge_imp_all():
+    """Fixtures of the motif -> edge aggregation; reads the committed walk fixtures (does not regenerate them)."""
+    us = dict(np.load(os.path.join(HERE, "uslegis.npz")))
+    big = dict(np.load(os.path.join(HERE, "rand_bigts.npz")))
+    B = 6
+    src, dst, eidx, ts = load_uslegis()
+    walks5 = (us["src_w_nodes"][:B].astype(np.int64), us["src_w_eidx"][:B].astype(np.int64), us["src_w_t"][:B].astype(np.float64),
+              us["src_cat"][:B, :, None].astype(np.int64), us["src_marginal"][:B, :, None])
+    sub = ([us["src_hop0_node"][:B].astype(np.int64), us["src_hop1_node"][:B].astype(np.int64)],
+           [us["src_hop0_eidx"][:B].astype(np.int64), us["src_hop1_eidx"][:B].astype(np.int64)], None)
+    gen_edge_imp("d172", walks5, us["src_edge_identity"][:B].astype(np.float64), ts[us["q"][:B]].astype(np.float64), sub,
+                 int(us["n_nodes"]), len(eidx) + 1, 172, 1, seed=3)
+    Bq = 12
+    wn, we, wt, wa = (big[f"tgt_w_{k}"][:Bq] for k in ("nodes", "eidx", "t", "anony"))
+    allw = np.concatenate([x.astype(np.float64) for x in (wn, we, wt, wa)], axis=-1)
+    new = marginal(allw, allw, allw)[0]
+    walks5 = (wn.astype(np.int64), we.astype(np.int64), wt.astype(np.float64), new[:, :, 12:13].astype(np.int64), new[:, :, 13:14])
+    ei = new_edge_info(we.astype(int))
+    sub = ([big["tgt_hop0_node"][:Bq].astype(np.int64), big["tgt_hop1_node"][:Bq].astype(np.int64)],
+           [big["tgt_hop0_eidx"][:Bq].astype(np.int64), big["tgt_hop1_eidx"][:Bq].astype(np.int64)], None)
+    gen_edge_imp("d32", walks5, ei, big["ts"][big["q"][:Bq]], sub, int(big["n_nodes"]), len(big["eidx"]) + 1, 32, 32, seed=4)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "edgeimp":
+        gen_edge_imp_all()
+        return
     gen_tie_star()
     gen_rand_small()
     gen_native_rng()

@@ -166,3 +166,17 @@ def test_encoder_oracle(golden, tag):
         out64 = orc_enc.forward(p, g["node_feat"], g["edge_feat"], walks, g["cut_time"], g["edge_identity"],
                                 dtype=np.float64, use_temporal=bool(g["use_temporal"]))
         np.testing.assert_allclose(out64, g["score"], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("tag", ["d32", "d172"])
+def test_edge_importance_oracle(golden, tag):
+    """oracle.encoder.edge_importance == the reference's retrieve_edge_imp_node (eval mode) on its own scores."""
+    from oracle import encoder as enc
+    z = golden(f"edgeimp_{tag}")
+    p = {k[2:]: z[k] for k in z if k.startswith("p:")}
+    sub = ([z["h0_node"], z["h1_node"]], [z["h0_eidx"], z["h1_eidx"]], None)
+    walks = (None, z["w_eidx"], z["w_t"], None, None)
+    for key, dep in (("dep", True), ("nodep", False)):
+        i0, i1 = enc.edge_importance(p, z["edge_feat"], sub, z[f"{key}_score"], walks, use_dependency=dep)
+        np.testing.assert_allclose(i0, z[f"{key}_imp0"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(i1, z[f"{key}_imp1"], rtol=1e-5, atol=1e-7)
