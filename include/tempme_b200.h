@@ -177,6 +177,29 @@ int tm_encode_score(const tm_encoder_desc *desc, const float *d_blob, int64_t B,
 int tm_encoder_profile(int enable);
 int tm_encoder_profile_read(float *h_event_ms, float *h_motif_ms);
 
+/* ---- motif -> edge explanation aggregation: TempME.retrieve_edge_imp_node, eval mode (models/explainer.py:354-406).
+ * walk_imp[b, 3w + p] = score[b, w] * (0.5 + 0.5 sigmoid(edge_dependency_gcn([edge_feat[e] | TimeEncode(t)])))  (:363-386; the gate is
+ * skipped when d_gate_blob is NULL = use_dependency_aware_sampling False); edge_imp = per-root scatter-max of walk_imp over the edge ids
+ * of the root's walks (0 for ids no walk carries, :389); gathered to the hop-1 / hop-2 slots (:392-393); E[Beta(max(10 p, 1),
+ * max(10 (1 - p), 1))] (:396-397, :421-430 with training = False); slots whose node id is 0 give 0 (:400-404). */
+typedef struct {
+    int32_t edge_dim, time_dim, hid_dim;     /* time_dim = node_dim (explainer.py:109); hid_dim 64 */
+} tm_gate_desc;
+typedef struct {                              /* edge_dependency_gcn (explainer.py:143-151), nn.Linear layout, host pointers */
+    const float *w0, *b0;                     /* .0  [H, Ed + D] */
+    const float *w3, *b3;                     /* .3  [H/2, H] */
+    const float *w6, *b6;                     /* .6  [1, H/2] */
+    const float *basis_freq, *phase;          /* time_encoder [D] */
+} tm_gate_params;
+int64_t tm_gate_blob_floats(const tm_gate_desc *desc);
+int tm_gate_pack(const tm_gate_desc *desc, const tm_gate_params *params, float *h_blob);
+/* d_scores [B,W] f32, d_eidx [B,W,3] i32, d_t [B,W,3] f32 (walks[1], walks[2]); hop slots d_h{0,1}_node / d_h{0,1}_eidx [B,K0] / [B,K1] i32
+ * (subgraph node_records / eidx_records); d_walk_imp [B*W*3] f32 workspace; outputs d_imp0 [B,K0], d_imp1 [B,K1] f32. */
+int tm_edge_importance(const tm_gate_desc *desc, const float *d_gate_blob, int64_t B, int64_t W, const float *d_scores,
+                       const int32_t *d_eidx, const float *d_t, const float *d_edge_feat, int64_t n_edge_rows,
+                       int64_t K0, const int32_t *d_h0_node, const int32_t *d_h0_eidx, int64_t K1, const int32_t *d_h1_node,
+                       const int32_t *d_h1_eidx, float *d_walk_imp, float *d_imp0, float *d_imp1, int device, tm_stream stream);
+
 /* Hardware self-test of the tcgen05/TMEM conventions the scorer relies on: C[128,N] = A[128,K] * B[N,K]^T on the
  * tensor cores (mode 0: one TF32 pass, mode 1: 3xTF32 split accumulation).  K % 8 == 0, N % 16 == 0, N <= 256. */
 int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, int K, int N, int mode, tm_stream stream);

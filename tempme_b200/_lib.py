@@ -32,6 +32,14 @@ class EncoderParams(C.Structure):
     _fields_ = [(f, _p) for f in PARAM_FIELDS]
 
 
+class GateDesc(C.Structure):
+    _fields_ = [("edge_dim", C.c_int32), ("time_dim", C.c_int32), ("hid_dim", C.c_int32)]
+
+
+class GateParams(C.Structure):
+    _fields_ = [(f, _p) for f in ("w0", "b0", "w3", "b3", "w6", "b6", "basis_freq", "phase")]
+
+
 SIGNATURES = {
     "tm_version": (C.c_int, []),
     "tm_last_error": (C.c_char_p, []),
@@ -56,6 +64,10 @@ SIGNATURES = {
     "tm_encoder_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tm_selftest_gemm": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p]),
     "tm_selftest_cos": (C.c_int, [_p, _p, _i64, _p]),
+    "tm_gate_blob_floats": (_i64, [C.POINTER(GateDesc)]),
+    "tm_gate_pack": (C.c_int, [C.POINTER(GateDesc), C.POINTER(GateParams), _p]),
+    "tm_edge_importance": (C.c_int, [C.POINTER(GateDesc), _p, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p, _p,
+                                     C.c_int, _p]),
     "tm_encode_score": (C.c_int, [C.POINTER(EncoderDesc), _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p,
                                   _p, _i64, _p, _i64, _p, _p, C.c_int, _p]),
 }

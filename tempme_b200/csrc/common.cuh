@@ -42,6 +42,12 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
                     int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
                     int device, cudaStream_t st);
 
+// dependency gate of the motif -> edge aggregation (encoder_tc.cu)
+int64_t tc_gate_blob_floats(const tm_gate_desc &d);
+int tc_gate_pack(const tm_gate_desc &d, const tm_gate_params &p, float *blob);
+int tc_gate_launch(const tm_gate_desc &d, const float *d_blob, int64_t n_events, const int32_t *eidx, const float *t, const float *scores,
+                   const float *edge_feat, int64_t n_edge_rows, float *out, int device, cudaStream_t st);
+
 // One CSR entry: 16 bytes so that a sampled neighbour costs one 128-bit load (one sector).
 struct __align__(16) Entry {
     int32_t nbr;

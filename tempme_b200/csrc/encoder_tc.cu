@@ -801,6 +801,197 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     return TM_OK;
 }
 
+// =================================================================================================
+// Dependency gate of retrieve_edge_imp_node (reference models/explainer.py:367-386): per walk event
+//   walk_imp = score * (0.5 + 0.5 sigmoid(edge_dependency_gcn([edge features | TimeEncode(raw t)])))
+// edge_dependency_gcn = Linear(Ed + D, H), ReLU, Linear(H, H/2), ReLU, Linear(H/2, 1) (:143-151, Dropout = identity in eval).
+// Tile = 128 events, 256 threads, same round machinery as the scorer (TS mode).  TMEM: G1 [0,H)  G2 [H, H + H/2)  A [192,256).
+// =================================================================================================
+struct GateLayout {
+    int D, Ed, H, H2, D16;                 // H2 = H / 2
+    TcLin l1, l2;
+    int b1, b2, w3, b3, freq, phase, n_cst;
+    int64_t cst, total;
+};
+
+GateLayout make_gate_layout(const tm_gate_desc &d) {
+    GateLayout G;
+    memset(&G, 0, sizeof G);
+    G.D = d.time_dim; G.Ed = d.edge_dim; G.H = d.hid_dim; G.H2 = d.hid_dim / 2; G.D16 = r16(G.D);
+    int64_t o = 0;
+    auto lin = [&](int K, int N) {
+        TcLin l; l.K8 = r8(K); l.N16 = r16(N); l.nch = (l.K8 + kKC - 1) / kKC;
+        l.w = o; o += (int64_t)l.nch * chunk_floats(l);
+        return l;
+    };
+    G.l1 = lin(G.Ed + G.D, G.H); G.l2 = lin(G.H, G.H2);
+    int c = 0;
+    G.b1 = c; c += r16(G.H); G.b2 = c; c += r16(G.H2); G.w3 = c; c += r16(G.H2); G.b3 = c; c += 16;
+    G.freq = c; c += G.D16; G.phase = c; c += G.D16; G.n_cst = c;
+    G.cst = o; o += c; G.total = o;
+    return G;
+}
+
+int64_t tc_gate_blob_floats(const tm_gate_desc &d) { return (make_gate_layout(d).total + 31) & ~(int64_t)31; }
+
+int tc_gate_pack(const tm_gate_desc &d, const tm_gate_params &p, float *blob) {
+    const GateLayout G = make_gate_layout(d);
+    memset(blob, 0, sizeof(float) * ((G.total + 31) & ~(int64_t)31));
+    const Mat W1 = dbl(p.w0, (size_t)G.H * (G.Ed + G.D)), W2 = dbl(p.w3, (size_t)G.H2 * G.H);
+    pack_tc_lin(G.l1, G.Ed + G.D, G.H, W1.data(), blob);
+    pack_tc_lin(G.l2, G.H, G.H2, W2.data(), blob);
+    float *c = blob + G.cst;
+    for (int i = 0; i < G.H; ++i) c[G.b1 + i] = p.b0[i];
+    for (int i = 0; i < G.H2; ++i) { c[G.b2 + i] = p.b3[i]; c[G.w3 + i] = p.w6[i]; }
+    c[G.b3] = p.b6[0];
+    for (int i = 0; i < G.D; ++i) { c[G.freq + i] = p.basis_freq[i]; c[G.phase + i] = p.phase[i]; }
+    return TM_OK;
+}
+
+struct GateArgs {
+    int64_t n_events;                        // B * W * 3 walk events, flat
+    const int32_t *eidx;
+    const float *t, *scores, *edge_feat;
+    int64_t n_edge_rows;
+    float *out;                              // walk_imp [n_events]
+    uint32_t tmem_cols;
+    int b_bytes;
+};
+
+__global__ void __launch_bounds__(256, 2)
+gate_tc_kernel(const GateLayout G, const float *__restrict__ blob, const GateArgs a) {
+    constexpr int CW = 16;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float part[2][128];
+    const int t = threadIdx.x, warp = t >> 5, row = t & 127, prt = t >> 7, kb = CW * prt;
+    TcCtx x;
+    x.a = smem; x.a_s = tc::smem_u32(smem); x.b_s = x.a_s; x.bars = bars; x.mma_phase = 0; x.b_phase = 0; x.blob = blob;
+    x.dbg = nullptr; x.dbg_i = 0;
+    float *cst = reinterpret_cast<float *>(smem + a.b_bytes);
+    uint2 *ctab = reinterpret_cast<uint2 *>(cst + G.n_cst);
+    for (int i = t; i < G.n_cst; i += 256) cst[i] = __ldg(blob + G.cst + i);
+    cos_table_to_smem(ctab);
+    if (t == 0) { tc::mbar_init(bars, 1); tc::mbar_init(bars + 1, 1); }
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, a.tmem_cols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC;
+    AFill<CW, true> af;
+    const int D = G.D, Ed = G.Ed, H = G.H, colG1 = 0, colG2 = H;
+    const int64_t n_tiles = (a.n_events + 127) / 128;
+    const int bytes1 = (int)chunk_floats(G.l1) * 4, bytes2 = (int)chunk_floats(G.l2) * 4;
+    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, G.l1.w, bytes1);
+    const bool ed_vec = (Ed & 3) == 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t r = tile * 128 + row;
+        const bool live = r < a.n_events, more = tile + gridDim.x < n_tiles;
+        const int32_t e = live ? a.eidx[r] : -1;
+        const float tt = live ? a.t[r] : 0.f;                                   // the raw timestamp (explainer.py:371-372)
+        const bool e_ok = e >= 0 && e < a.n_edge_rows;
+        const float *ef = a.edge_feat + (int64_t)max(e, 0) * Ed;
+        auto xval = [&](int j) -> float {                                       // [edge features | TimeEncode] column j (:375)
+            if (j < Ed) return e_ok ? __ldg(ef + j) : 0.f;
+            const int k = j - Ed;
+            return (k < D && live) ? cos_accurate(__fadd_rn(__fmul_rn(tt, cst[G.freq + k]), cst[G.phase + k]), ctab) : 0.f;
+        };
+        // ---- Linear(Ed + D, H) -> G1
+        for (int c = 0; c < G.l1.nch; ++c) {
+            const int kcols = min(kKC, G.l1.K8 - c * kKC), j0 = c * kKC + kb;
+            if (kb < kcols) {
+                if (ed_vec && j0 + CW <= Ed) {
+#pragma unroll
+                    for (int g = 0; g < CW / 4; ++g) af.put4(x, row, kb, 4 * g, e_ok ? ldg4(ef + j0 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f));
+                } else if (j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + G.D16) {
+                    float w[CW];
+#pragma unroll
+                    for (int g = 0; g < CW / 4; ++g) {
+                        const float4 fq = lds4(cst + G.freq + (j0 - Ed) + 4 * g), ph = lds4(cst + G.phase + (j0 - Ed) + 4 * g);
+                        w[4 * g] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.x), ph.x), ctab); w[4 * g + 1] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.y), ph.y), ctab);
+                        w[4 * g + 2] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.z), ph.z), ctab); w[4 * g + 3] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.w), ph.w), ctab);
+                    }
+#pragma unroll
+                    for (int g = 0; g < CW / 4; ++g) {
+                        const int k = j0 - Ed + 4 * g;
+                        af.put4(x, row, kb, 4 * g, make_float4((k < D && live) ? w[4 * g] : 0.f, (k + 1 < D && live) ? w[4 * g + 1] : 0.f,
+                                                               (k + 2 < D && live) ? w[4 * g + 2] : 0.f, (k + 3 < D && live) ? w[4 * g + 3] : 0.f));
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < CW / 4; ++g) { const int j = j0 + 4 * g; af.put4(x, row, kb, 4 * g, make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3))); }
+                }
+                af.commit(x, lane_base, kb);
+            }
+            const bool last = c + 1 == G.l1.nch;
+            tc_mma_round<true>(x, r16(H), kcols, colG1, c != 0, last ? G.l2.w : G.l1.w + (int64_t)(c + 1) * chunk_floats(G.l1), last ? bytes2 : bytes1);
+        }
+        // ---- ReLU, Linear(H, H/2) -> G2
+        for (int c = 0; c < G.l2.nch; ++c) {
+            const int kcols = min(kKC, G.l2.K8 - c * kKC);
+            if (kb < kcols) {
+                float z[CW];
+                tc::tmem_ld16(tmem + lane_base + colG1 + c * kKC + kb, z);
+#pragma unroll
+                for (int k = 0; k < CW; k += 4) {
+                    const float4 bb = lds4(cst + G.b1 + c * kKC + kb + k);
+                    af.put4(x, row, kb, k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
+                }
+                af.commit(x, lane_base, kb);
+            }
+            const bool last = c + 1 == G.l2.nch;
+            tc_mma_round<true>(x, r16(G.H2), kcols, colG2, c != 0, last ? G.l1.w : G.l2.w + (int64_t)(c + 1) * chunk_floats(G.l2), last ? (more ? bytes1 : 0) : bytes2);
+        }
+        // ---- ReLU, Linear(H/2, 1), sigmoid gate (:379-386)
+        float g_ = 0.f;
+        for (int c0 = prt * (r16(G.H2) / 2); c0 < (prt + 1) * (r16(G.H2) / 2); c0 += 16) {
+            float z[16];
+            tc::tmem_ld16(tmem + lane_base + colG2 + c0, z);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) g_ = fmaf(fmaxf(z[i] + cst[G.b2 + c0 + i], 0.f), cst[G.w3 + c0 + i], g_);
+        }
+        part[prt][row] = g_;
+        tc::fence_before_sync();
+        __syncthreads();                 // also: all TMEM reads of this tile done before the next tile's MMAs overwrite it
+        tc::fence_after_sync();
+        if (live && prt == 0) {
+            const float dep = part[0][row] + part[1][row] + cst[G.b3];
+            const float gate = 1.f / (1.f + expf(-dep));
+            a.out[r] = __fmul_rn(a.scores[r / 3], __fadd_rn(0.5f, __fmul_rn(0.5f, gate)));
+        }
+        __syncthreads();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
+}
+
+int tc_gate_launch(const tm_gate_desc &d, const float *d_blob, int64_t n_events, const int32_t *eidx, const float *t, const float *scores,
+                   const float *edge_feat, int64_t n_edge_rows, float *out, int device, cudaStream_t st) {
+    const GateLayout G = make_gate_layout(d);
+    if (G.H != 64 || G.Ed < 1 || G.D < 1 || G.D > 256) { set_error("tm_edge_importance: gate needs hid_dim 64 and time_dim in [1,256]"); return TM_ERR_UNSUPPORTED; }
+    const int64_t bb = std::max(chunk_floats(G.l1), chunk_floats(G.l2)) * 4;
+    const size_t need = (size_t)bb + (size_t)G.n_cst * 4 + 152 * 8;
+    static bool attr_set[64] = {false};
+    if (device >= 0 && device < 64 && !attr_set[device]) {
+        TM_CUDA(cudaFuncSetAttribute(gate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TM_CUDA(cudaFuncSetAttribute(gate_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_set[device] = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    GateArgs a;
+    a.n_events = n_events; a.eidx = eidx; a.t = t; a.scores = scores; a.edge_feat = edge_feat; a.n_edge_rows = n_edge_rows; a.out = out;
+    a.tmem_cols = 256; a.b_bytes = (int)bb;
+    const size_t smem = std::max(need, (size_t)228 * 1024 / 3);       // two CTAs per SM (256 TMEM columns each), never three
+    const int64_t tiles = (n_events + 127) / 128, cap = (int64_t)sms * 2, per = (tiles + cap - 1) / cap;
+    gate_tc_kernel<<<(unsigned)((tiles + per - 1) / per), 256, smem, st>>>(G, d_blob, a);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}
+
 }  // namespace tmb
 
 extern "C" int tm_encoder_profile(int enable) {

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ._lib import EncoderDesc, EncoderParams, check, lib, ptr
+from ._lib import EncoderDesc, EncoderParams, GateDesc, GateParams, check, lib, ptr
 
 
 class TimeEncode(nn.Module):
@@ -128,6 +128,9 @@ class TempME(nn.Module):
         self._blob = None
         self._blob_key = None
         self._ws = None
+        self._gate_desc = GateDesc(self.edge_dim, self.time_dim, self.hid_dim)
+        self._gate_blob = None
+        self._gate_key = None
 
     # ------------------------------------------------------------------ weights -> packed device blob
     def _forward_params(self):
@@ -197,3 +200,67 @@ class TempME(nn.Module):
         cut = self._t(cut_time_l, torch.float32)                          # .float(), explainer.py:816
         eid = self._t(edge_identify, torch.float32)                       # .float(), explainer.py:177
         return self.score_device(nodes, eidx, t, cat, cut, eid).view(B, W, 1)
+
+    # ------------------------------------------------------------------ motif -> edge aggregation (explainer.py:354-430)
+    def _packed_gate(self):
+        """edge_dependency_gcn + time_encoder packed for the tensor-core gate kernel (None without dependency-aware sampling)."""
+        if not self.use_dependency_aware_sampling:
+            return None
+        g = self.edge_dependency_gcn
+        ps = [g[0].weight, g[0].bias, g[3].weight, g[3].bias, g[6].weight, g[6].bias, self.time_encoder.basis_freq, self.time_encoder.phase]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._gate_blob is None or key != self._gate_key:
+            host = [p.detach().to("cpu", torch.float32).contiguous() for p in ps]
+            prm = GateParams(*[C.c_void_p(h.data_ptr()) for h in host])
+            blob = torch.empty(lib().tm_gate_blob_floats(C.byref(self._gate_desc)), dtype=torch.float32)
+            check(lib().tm_gate_pack(C.byref(self._gate_desc), C.byref(prm), ptr(blob)), "tm_gate_pack")
+            self._gate_blob = blob.to(self.device)
+            self._gate_key = key
+        return self._gate_blob
+
+    def beta_sample(self, prob, training):
+        """explainer.py:421-430.  Eval mode only (the mean of the Beta); sampling belongs to training."""
+        if training:
+            raise NotImplementedError("tempme_b200.TempME.beta_sample: training-mode rsample is outside the B200 hot path")
+        alpha = torch.clamp(prob * 10, min=1.0)
+        beta = torch.clamp((1 - prob) * 10, min=1.0)
+        return alpha / (alpha + beta)
+
+    def edge_importance_device(self, scores, eidx, t, h0_node, h0_eidx, h1_node, h1_eidx):
+        """All CUDA tensors: scores f32 [B,W], eidx i32 [B,W,3], t f32 [B,W,3], hop slots i32 [B,K0] / [B,K1] -> (imp0 [B,K0], imp1 [B,K1])."""
+        B, W = eidx.shape[0], eidx.shape[1]
+        K0, K1 = h0_eidx.shape[1], h1_eidx.shape[1]
+        gate = self._packed_gate()
+        _, ef = self._tables()
+        walk_imp = torch.empty(B * W * 3, dtype=torch.float32, device=self.device) if gate is not None else None
+        imp0 = torch.empty((B, K0), dtype=torch.float32, device=self.device)
+        imp1 = torch.empty((B, K1), dtype=torch.float32, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(lib().tm_edge_importance(C.byref(self._gate_desc), ptr(gate) if gate is not None else None, B, W, ptr(scores), ptr(eidx), ptr(t),
+                                       ptr(ef), ef.shape[0], K0, ptr(h0_node), ptr(h0_eidx), K1, ptr(h1_node), ptr(h1_eidx),
+                                       ptr(walk_imp) if walk_imp is not None else None, ptr(imp0), ptr(imp1), self.device.index, st),
+              "tm_edge_importance")
+        return imp0, imp1
+
+    def retrieve_edge_imp_node(self, subgraph, graphlet_imp, walks, training=True):
+        """explainer.py:354-406 with training=False (eval): dependency gate, per-root scatter-max over edge ids, gather to the
+        hop-1 / hop-2 slots, Beta mean, padding mask.  Returns CUDA tensors (edge_imp_0 [B,n], edge_imp_1 [B,n^2])."""
+        if training:
+            raise NotImplementedError("tempme_b200.TempME.retrieve_edge_imp_node is the eval-mode aggregation (training=False)")
+        node_record, eidx_record = subgraph[0], subgraph[1]
+        eidx = self._t(walks[1], torch.int32)
+        B, W = eidx.shape[0], eidx.shape[1]
+        t = self._t(walks[2], torch.float32)                               # .float(), explainer.py:371
+        scores = self._t(graphlet_imp, torch.float32).reshape(B, W)
+        return self.edge_importance_device(scores, eidx, t, self._t(node_record[0], torch.int32), self._t(eidx_record[0], torch.int32),
+                                           self._t(node_record[1], torch.int32), self._t(eidx_record[1], torch.int32))
+
+    def retrieve_explanation(self, subgraph_src, graphlet_imp_src, walks_src, subgraph_tgt, graphlet_imp_tgt, walks_tgt,
+                             subgraph_bgd, graphlet_imp_bgd, walks_bgd, training=True):
+        """explainer.py:408-419."""
+        src_0, src_1 = self.retrieve_edge_imp_node(subgraph_src, graphlet_imp_src, walks_src, training=training)
+        tgt_0, tgt_1 = self.retrieve_edge_imp_node(subgraph_tgt, graphlet_imp_tgt, walks_tgt, training=training)
+        bgd_0, bgd_1 = self.retrieve_edge_imp_node(subgraph_bgd, graphlet_imp_bgd, walks_bgd, training=training)
+        if self.base_type == "tgn":
+            return [torch.cat([src_0, tgt_0, bgd_0], dim=0), torch.cat([src_1, tgt_1, bgd_1], dim=0)]
+        return [torch.cat([src_0, tgt_0, bgd_0], dim=0)]

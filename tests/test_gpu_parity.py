@@ -401,3 +401,61 @@ def test_pipeline_matches_piecewise(tm, orc):
                 ref = m(walks, ts[q][sl], orc.edge_identity(oe))
             np.testing.assert_allclose(scores[k, sl], ref[..., 0].cpu().numpy(), rtol=1e-6, atol=0)
     assert (pipe.hist_null.cpu().numpy() == hist).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# motif -> edge aggregation: retrieve_edge_imp_node, eval mode
+# ---------------------------------------------------------------------------------------------
+def _edge_imp_model(tm, z, D, dep):
+    n_nodes = 4
+    nfeat = torch.zeros(n_nodes, D); efeat = torch.as_tensor(z["edge_feat"])
+
+    class Base:
+        n_feat_th = nfeat.cuda(); e_feat_th = efeat.cuda()
+        node_raw_features = torch.nn.Embedding.from_pretrained(n_feat_th, padding_idx=0, freeze=True)
+        edge_raw_features = torch.nn.Embedding.from_pretrained(e_feat_th, padding_idx=0, freeze=True)
+
+    m = tm.TempME(Base(), "tgn", "t", 40, 64, device="cuda:0", null_model={}, use_dependency_aware_sampling=dep).cuda().eval()
+    sd = {k[2:]: torch.as_tensor(z[k]) for k in z if k.startswith("p:")}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected or not dep          # without dependency-aware sampling the module has no edge_dependency_gcn
+    return m
+
+
+@pytest.mark.parametrize("tag,D", [("d32", 32), ("d172", 172)])
+def test_edge_importance_golden(tm, golden, tag, D):
+    """CUDA retrieve_edge_imp_node (gate on tcgen05, per-root segmented max) == the unmodified reference, rtol 1e-5."""
+    z = golden(f"edgeimp_{tag}")
+    sub = ([z["h0_node"], z["h1_node"]], [z["h0_eidx"], z["h1_eidx"]], None)
+    walks = (None, z["w_eidx"], z["w_t"], None, None)
+    for key, dep in (("dep", True), ("nodep", False)):
+        m = _edge_imp_model(tm, z, D, dep)
+        i0, i1 = m.retrieve_edge_imp_node(sub, z[f"{key}_score"], walks, training=False)
+        np.testing.assert_allclose(i0.cpu().numpy(), z[f"{key}_imp0"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(i1.cpu().numpy(), z[f"{key}_imp1"], rtol=1e-5, atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        m.retrieve_edge_imp_node(sub, z["dep_score"], walks, training=True)
+
+
+def test_edge_importance_vs_oracle_larger(tm, orc):
+    """Seeded inputs against oracle/encoder.edge_importance: ragged ids, padding slots, ids no walk carries."""
+    from oracle import encoder as enc
+    rng = np.random.default_rng(11)
+    B, W, n, D, Ed, Ne = 300, 30, 12, 32, 32, 700
+    z = {"edge_feat": rng.standard_normal((Ne, Ed)).astype(np.float32)}
+    m = _edge_imp_model(tm, z, D, True)
+    with torch.no_grad():
+        m.time_encoder.phase.copy_(0.1 * torch.randn(D))
+    p = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    w_eidx = rng.integers(0, Ne, (B, W, 3)).astype(np.int32)
+    w_eidx[rng.random((B, W, 3)) < 0.3] = 0
+    w_t = np.sort(rng.integers(1e8, 1.1e8, (B, W, 3)).astype(np.float32), axis=-1)
+    scores = rng.random((B, W, 1)).astype(np.float32)
+    h_e = [rng.integers(0, Ne, (B, n)).astype(np.int32), rng.integers(0, Ne, (B, n * n)).astype(np.int32)]
+    h_n = [rng.integers(0, 5, (B, n)).astype(np.int32), rng.integers(0, 5, (B, n * n)).astype(np.int32)]
+    h_e[0][:, :4] = w_eidx[:, :4, 2]; h_e[1][:, :W] = w_eidx[:, :, 1]
+    walks = (None, w_eidx, w_t, None, None)
+    r0, r1 = enc.edge_importance(p, z["edge_feat"], (h_n, h_e, None), scores, walks)
+    i0, i1 = m.retrieve_edge_imp_node((h_n, h_e, None), scores, walks, training=False)
+    np.testing.assert_allclose(i0.cpu().numpy(), r0, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(i1.cpu().numpy(), r1, rtol=1e-5, atol=1e-7)
