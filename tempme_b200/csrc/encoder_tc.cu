@@ -238,8 +238,10 @@ struct AFill {
 };
 
 // fill() has written this thread's share of the A tiles.  next_bytes != 0: weight chunk of the CTA's next round.
-template <bool TS>
-__device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d_col, bool accumulate, int64_t next_off, int next_bytes) {
+struct NoMid { __device__ __forceinline__ void operator()() const {} };
+// mid(): run by every warp between the issue of the round's MMAs and the wait for their completion (work that overlaps the tensor pipe)
+template <bool TS, typename Mid = NoMid>
+__device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d_col, bool accumulate, int64_t next_off, int next_bytes, Mid mid = Mid()) {
 #ifdef TM_TC_TIMING
     const bool tim = x.dbg && threadIdx.x == 0 && x.dbg_i < 128;
 #else
@@ -279,6 +281,7 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
         __syncwarp();
     }
     x.b_phase ^= 1;
+    mid();
     tc::mbar_wait(x.bars, x.mma_phase);
     if (tim) x.dbg[x.dbg_i * 5 + 4] = clock64();
 #ifdef TM_TC_TIMING
@@ -348,7 +351,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     uint2 *ctab = reinterpret_cast<uint2 *>(cstM + L.n_cstM);
     for (int i = t; i < L.n_cstE + L.n_cstM; i += kThreads) cstE[i] = __ldg(blob + L.cstE + i);      // cstM follows cstE in the blob
     cos_table_to_smem(ctab);
-    if (t == 0) { tc::mbar_init(bars, 1); tc::mbar_init(bars + 1, 1); tc::mbar_init(bars + 2, kThreads); tc::mbar_init(bars + 3, kThreads); }
+    if (t == 0) { tc::mbar_init(bars, 1); tc::mbar_init(bars + 1, 1); tc::mbar_init(bars + 2, kThreads / 32); tc::mbar_init(bars + 3, kThreads / 32); }
     if (warp == 0) tc::tmem_alloc(&tmem_slot, a.tmem_cols);
     tc::fence_before_sync();
     __syncthreads();
@@ -388,24 +391,26 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     const bool stage_nodes = a.stage_off != 0;
     float *stg = reinterpret_cast<float *>(smem + a.stage_off);
     uint32_t n_phase = 0;
+    // one mbarrier arrival per warp: lane 0 announces the bytes of the warp's valid rows, then every valid lane issues its copy
+    auto request_rows = [&](uint64_t *bar, bool valid, float *dst, const float *src, int bytes) {
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if ((t & 31) == 0) { if (m) tc::mbar_expect_tx(bar, (uint32_t)(__popc(m) * bytes)); else mbar_arrive(bar); }
+        __syncwarp();
+        if (valid) tc::tma_load_1d(dst, src, (uint32_t)bytes, bar);
+    };
     auto request_nodes = [&](const PassIdx &q, int c) {       // chunk c of both endpoints' rows (:348-351)
         if (!stage_nodes) return;
-        const int idx = prt == 0 ? q.ns : q.nt, bytes = min(kKC, D - c * kKC) * 4;
-        if (prt < 2 && idx >= 0 && idx < a.n_node_rows) {
-            tc::mbar_expect_tx(bars + 2, (uint32_t)bytes);
-            tc::tma_load_1d(stg + prt * kStageTable + row * kStageRow, a.node_feat + (int64_t)idx * D + c * kKC, (uint32_t)bytes, bars + 2);
-        } else mbar_arrive(bars + 2);
+        const int idx = prt == 0 ? q.ns : q.nt;
+        request_rows(bars + 2, prt < 2 && idx >= 0 && idx < a.n_node_rows, stg + (prt & 1) * kStageTable + row * kStageRow,
+                     a.node_feat + (int64_t)max(idx, 0) * D + c * kKC, min(kKC, D - c * kKC) * 4);
     };
     const bool stage_edges = a.stage_edge_off != 0;
     float *stg_e = reinterpret_cast<float *>(smem + a.stage_edge_off);
     uint32_t e_phase = 0;
     auto request_edges = [&](const PassIdx &q, int c) {       // chunk c of the edge-feature rows (:332-338); part 0 requests
         if (!stage_edges) return;
-        const int bytes = min(kKC, Ed - c * kKC) * 4;
-        if (prt == 0 && q.e >= 0 && q.e < a.n_edge_rows) {
-            tc::mbar_expect_tx(bars + 3, (uint32_t)bytes);
-            tc::tma_load_1d(stg_e + row * kStageRow, a.edge_feat + (int64_t)q.e * Ed + c * kKC, (uint32_t)bytes, bars + 3);
-        } else mbar_arrive(bars + 3);
+        request_rows(bars + 3, prt == 0 && q.e >= 0 && q.e < a.n_edge_rows, stg_e + row * kStageRow,
+                     a.edge_feat + (int64_t)max(q.e, 0) * Ed + c * kKC, min(kKC, Ed - c * kKC) * 4);
     };
     PassIdx pcur, pnext;
     {
@@ -472,11 +477,12 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                     if (kb < kcols) af.commit(x, lane_base, kb);
                 }
                 const bool last = c + 1 == nE;
-                tc_mma_round<TS>(x, L.D16, kcols, colE, c != 0, last ? L.g0.w : L.evt.w + (int64_t)(c + 1) * chunk_floats(L.evt), last ? bytes_g : bytes_e);
-                if (has_edge) {                                     // the staged chunk has been consumed
-                    if (c + 1 < L.nch_edge) request_edges(pi, c + 1);
-                    else if (pos < 2) request_edges(pnext, 0);
-                }
+                tc_mma_round<TS>(x, L.D16, kcols, colE, c != 0, last ? L.g0.w : L.evt.w + (int64_t)(c + 1) * chunk_floats(L.evt), last ? bytes_g : bytes_e,
+                                 [&]() {                            // the staged chunk has been consumed: the next one lands behind the MMAs
+                                     if (!has_edge) return;
+                                     if (c + 1 < L.nch_edge) request_edges(pi, c + 1);
+                                     else if (pos < 2) request_edges(pnext, 0);
+                                 });
             }
             // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
             const int eb = pos == 2 ? L.e_b2 : L.e_b;
@@ -529,11 +535,13 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                     else if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
                     else if (pos < 2) { noff = L.evt.w; nbytes = bytes_e; }
                     else { noff = L.sp.w; nbytes = bytes_sp; }
-                    tc_mma_round<TS>(x, H, kcols, colZ + o * H, c != 0, noff, nbytes);
+                    tc_mma_round<TS>(x, H, kcols, colZ + o * H, c != 0, noff, nbytes,
+                                     [&]() {                        // after the second orientation's fill the staged chunk has been consumed
+                                         if (o == 0) return;
+                                         if (c + 1 < nG) request_nodes(pi, c + 1);
+                                         else if (pos < 2) request_nodes(pnext, 0);
+                                     });
                 }
-                // the staged chunk has been consumed (both orientations' fills ended before the last round's barrier)
-                if (c + 1 < nG) request_nodes(pi, c + 1);
-                else if (pos < 2) request_nodes(pnext, 0);
             }
             // ---- h_pos = relu(MLP.0 + bias): thread part p owns columns [4 CW p, 4 CW (p + 1)) of [Zs | Zt]
             for (int c0 = 4 * CW * prt; c0 < 4 * CW * (prt + 1); c0 += 16) {
@@ -664,8 +672,9 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 af.commit(x, lane_base, kb);
             }
             const bool last = c + 1 == L.m3.nch;
-            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? bytes_e : 0) : bytes_m3);
-            if (c == 0 && more) { request_nodes(pcur, 0); request_edges(pcur, 0); }          // the staging overlaps the weight buffer of the larger motif-round chunks; MLP.3's are small
+            // the staging overlaps the weight buffer of the larger motif-round chunks; MLP.3's are small and R's MMAs have completed
+            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? bytes_e : 0) : bytes_m3,
+                             [&]() { if (c == 0 && more) { request_nodes(pcur, 0); request_edges(pcur, 0); } });
         }
         // ---- MLP.5 + sigmoid (:199-200)
         float z5 = 0.f;
