@@ -67,12 +67,14 @@ __device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
+// try_wait is potentially blocking: with a suspend-time hint the hardware parks the thread until the phase completes (or the
+// hint expires) instead of returning after its short default limit -- far fewer spin iterations competing for issue slots
 __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}\n"
-        :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
+        :: "r"(smem_u32(mbar)), "r"(parity), "r"(20000u) : "memory");
 }
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
