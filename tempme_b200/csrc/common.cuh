@@ -64,7 +64,16 @@ struct GraphView {
     const Entry *entry;   // [n_entries]  time-sorted per node
     const uint64_t *skey; // [n_entries]  per node: (nbr << 32 | position) sorted -- secondary index for the id filter of step 3
     const int4 *etab;     // [max_eidx + 1] {node_a, node_b, cut_a, cut_b}: nodeedge2idx as a table
+    const uint4 *htab;    // open-addressing directory of the runs of skey: {key lo, key hi, start, len}, key = node << 32 | nbr,
+                          //   skey[start .. start+len) = the positions of neighbour nbr in node's list; nullptr: search skey instead
+    uint64_t hmask;       // slots - 1 (power of two)
 };
+
+// 64-bit finaliser (murmur3) for the run directory
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
 
 }  // namespace tm
 

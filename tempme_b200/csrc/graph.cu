@@ -3,6 +3,7 @@
 // stable per-node sort by timestamp, literal emulation of get_ts2idx into a per-edge table),
 // followed by one upload; every query after that runs on the device.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -46,6 +47,30 @@ __global__ void find_before_kernel(GraphView g, int64_t R, const int32_t *__rest
         if (c < 0) { c = 0; if (lane == 0) report_row_error(err, row); }   // IndexError, graph.py:134-135
     } else c = 0;
     if (lane == 0) { o_start[row] = s; o_cut[row] = (int32_t)c; }
+}
+
+// Directory of the neighbour runs of skey (one warp per node, lanes stride over the node's window): a run starts where the
+// neighbour id changes; its end is the lower bound of the next id.  count != nullptr: only count the runs.
+__global__ void run_directory_kernel(GraphView g, uint4 *tab, uint64_t mask, unsigned long long *count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long local = 0;
+    for (int64_t v = warp0; v < g.n_nodes; v += n_warps) {
+        const int64_t s = g.off[v], e = g.off[v + 1];
+        for (int64_t i = s + lane; i < e; i += 32) {
+            const uint32_t nb = (uint32_t)(g.skey[i] >> 32);
+            if (i > s && (uint32_t)(g.skey[i - 1] >> 32) == nb) continue;
+            if (count) { ++local; continue; }
+            int64_t lo = i + 1, hi = e;                      // first index whose neighbour id is larger
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((uint32_t)(g.skey[mid] >> 32) <= nb) lo = mid + 1; else hi = mid; }
+            const uint64_t key = (uint64_t)v << 32 | nb;
+            uint64_t slot = mix64(key) & mask;
+            unsigned long long *words = reinterpret_cast<unsigned long long *>(tab);
+            while (atomicCAS(words + 2 * slot, ~0ull, (unsigned long long)key) != ~0ull) slot = (slot + 1) & mask;
+            words[2 * slot + 1] = (unsigned long long)(uint32_t)i | (unsigned long long)(uint32_t)(lo - i) << 32;
+        }
+    }
+    if (count && local) atomicAdd(count, local);
 }
 
 }  // namespace tm
@@ -155,7 +180,38 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
     }
     g->v.n_nodes = n_nodes; g->v.n_entries = n_entries; g->v.max_eidx = max_e;
     g->v.off = (const int64_t *)d_off; g->v.entry = (const Entry *)d_ent; g->v.skey = (const uint64_t *)d_nbr; g->v.etab = (const int4 *)d_tab;
+    g->v.htab = nullptr; g->v.hmask = 0;
     g->device_bytes = (int64_t)(b_off + b_ent + b_nbr + b_tab);
+    // run directory (node, neighbour) -> run of skey, built on the device; load factor <= 1/2
+    if (n_entries > 0 && !getenv("TEMPME_NO_RUN_DIRECTORY")) {
+        unsigned long long *d_cnt = nullptr, runs = 0;
+        uint4 *d_h = nullptr;
+        ce = cudaMalloc(&d_cnt, sizeof *d_cnt);
+        if (ce == cudaSuccess) ce = cudaMemset(d_cnt, 0, sizeof *d_cnt);
+        if (ce == cudaSuccess) {
+            run_directory_kernel<<<148 * 8, 256>>>(g->v, nullptr, 0, d_cnt);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ce = cudaMemcpy(&runs, d_cnt, sizeof runs, cudaMemcpyDeviceToHost);
+        }
+        uint64_t slots = 1024;
+        while (slots < 2 * runs) slots <<= 1;
+        if (ce == cudaSuccess) ce = cudaMalloc(&d_h, sizeof(uint4) * slots);
+        if (ce == cudaSuccess) ce = cudaMemset(d_h, 0xff, sizeof(uint4) * slots);
+        if (ce == cudaSuccess) {
+            run_directory_kernel<<<148 * 8, 256>>>(g->v, d_h, slots - 1, nullptr);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ce = cudaDeviceSynchronize();
+        }
+        cudaFree(d_cnt);
+        if (ce != cudaSuccess) {
+            set_error("run directory build failed: %s", cudaGetErrorString(ce));
+            cudaFree(d_h); cudaFree(d_off); cudaFree(d_ent); cudaFree(d_nbr); cudaFree(d_tab);
+            delete g;
+            return ce == cudaErrorMemoryAllocation ? TM_ERR_NOMEM : TM_ERR_CUDA;
+        }
+        g->v.htab = d_h; g->v.hmask = slots - 1;
+        g->device_bytes += (int64_t)(sizeof(uint4) * slots);
+    }
     *out = g;
     return TM_OK;
 }
@@ -178,7 +234,7 @@ extern "C" int tm_graph_create_from_events(int64_t n_nodes, int64_t n_events, co
 extern "C" void tm_graph_destroy(tm_graph *g) {
     if (!g) return;
     cudaSetDevice(g->device);
-    cudaFree((void *)g->v.off); cudaFree((void *)g->v.entry); cudaFree((void *)g->v.skey); cudaFree((void *)g->v.etab);
+    cudaFree((void *)g->v.off); cudaFree((void *)g->v.entry); cudaFree((void *)g->v.skey); cudaFree((void *)g->v.etab); cudaFree((void *)g->v.htab);
     delete g;
 }
 

@@ -84,9 +84,28 @@ __device__ __forceinline__ int64_t key_lower_bound(const uint64_t *__restrict__ 
     return lo;
 }
 struct IdRange { int64_t base, cnt; };   // skey[base .. base+cnt) = positions (< cut) of neighbour x, ascending
-__device__ __forceinline__ IdRange id_prefix(const uint64_t *__restrict__ k, int64_t len, int64_t cut, int32_t x) {
+// k = skey of the node's window (length len).  With the run directory the run of x costs one or two 16-byte probes instead of a
+// lower bound over the whole window; the cut inside the run is a lower bound over the run only.
+__device__ __forceinline__ IdRange id_prefix(const GraphView &g, int64_t node, const uint64_t *__restrict__ k, int64_t win, int64_t len, int64_t cut, int32_t x) {
     IdRange r;
     const uint64_t hi_key = (uint64_t)(uint32_t)x << 32;
+    if (g.htab) {
+        const uint64_t key = (uint64_t)node << 32 | (uint32_t)x;
+        uint64_t slot = mix64(key) & g.hmask;
+        r.base = 0; r.cnt = 0;
+        for (;;) {
+            const uint4 q = __ldg(g.htab + slot);
+            const uint64_t kk = (uint64_t)q.y << 32 | q.x;
+            if (kk == key) {
+                r.base = (int64_t)q.z - win;
+                r.cnt = cut > 0 ? key_lower_bound(k, r.base, r.base + (int64_t)q.w, hi_key | (uint64_t)cut) - r.base : 0;
+                break;
+            }
+            if (kk == ~0ull) break;
+            slot = (slot + 1) & g.hmask;
+        }
+        return r;
+    }
     r.base = key_lower_bound(k, 0, len, hi_key);
     r.cnt = cut > 0 ? key_lower_bound(k, r.base, len, hi_key | (uint64_t)cut) - r.base : 0;
     return r;
@@ -183,9 +202,9 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
             IdRange ra1 = {0, 0}, ra2 = {0, 0}, rb = {0, 0};
             if (code == 1) { nA = cA; nB = cB; }
             else {
-                ra1 = id_prefix(g.skey + sA, lenA, cA, fa1);
-                if (fa2 != fa1) ra2 = id_prefix(g.skey + sA, lenA, cA, fa2);
-                rb = id_prefix(g.skey + sB, lenB, cB, fb);
+                ra1 = id_prefix(g, A, g.skey + sA, sA, lenA, cA, fa1);
+                if (fa2 != fa1) ra2 = id_prefix(g, A, g.skey + sA, sA, lenA, cA, fa2);
+                rb = id_prefix(g, Bn, g.skey + sB, sB, lenB, cB, fb);
                 nA = ra1.cnt + ra2.cnt; nB = rb.cnt;
                 scan_acc += (unsigned long long)(cA + cB);
             }
