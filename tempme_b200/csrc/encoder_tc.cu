@@ -227,9 +227,10 @@ struct AFill {
             *reinterpret_cast<float4 *>(p + kATile) = l;
         }
     }
-    __device__ __forceinline__ void commit(const TcCtx &x, uint32_t lane_base, int kb) {       // all CW columns have been put
+    // all CW columns have been put; second: the event passes' second A buffer (the 64 TMEM columns below the primary one)
+    __device__ __forceinline__ void commit(const TcCtx &x, uint32_t lane_base, int kb, bool second = false) {
         if (TS) {
-            const uint32_t a0 = x.tmem + lane_base + x.a_col + (uint32_t)kb;
+            const uint32_t a0 = x.tmem + lane_base + x.a_col - (second ? 2 * kKC : 0) + (uint32_t)kb;
             if (CW == 16) { tc::tmem_st16(a0, hi); tc::tmem_st16(a0 + kKC, lo); }
             else { tc::tmem_st8(a0, hi); tc::tmem_st8(a0 + kKC, lo); }
             tc::tmem_st_wait();
@@ -240,8 +241,13 @@ struct AFill {
 // fill() has written this thread's share of the A tiles.  next_bytes != 0: weight chunk of the CTA's next round.
 struct NoMid { __device__ __forceinline__ void operator()() const {} };
 // mid(): run by every warp between the issue of the round's MMAs and the wait for their completion (work that overlaps the tensor pipe)
+// Dual rounds (TS mode, two A buffers): kDualK: D (+)= [A | A2] * [chunk | next chunk]^T (kcols + kc2 K columns);
+// kDualM: D (+)= A * chunk^T and D2 (+)= A2 * chunk^T (two row blocks share the chunk).
+enum { kSingle = 0, kDualK = 1, kDualM = 2 };
+struct Dual { int mode, kc2, d2; };
 template <bool TS, typename Mid = NoMid>
-__device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d_col, bool accumulate, int64_t next_off, int next_bytes, Mid mid = Mid()) {
+__device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d_col, bool accumulate, int64_t next_off, int next_bytes, Mid mid = Mid(),
+                                             Dual dual = Dual{kSingle, 0, 0}) {
 #ifdef TM_TC_TIMING
     const bool tim = x.dbg && threadIdx.x == 0 && x.dbg_i < 128;
 #else
@@ -269,12 +275,28 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
                 tc::mma_tf32_ts(dcol, ta + 8 * ks, bh, idesc, (uint32_t)(accumulate || ks != 0), leader);
                 tc::mma_tf32_ts(dcol, ta + kKC + 8 * ks, bh, idesc, 1, leader);
                 tc::mma_tf32_ts(dcol, ta + 8 * ks, bl, idesc, 1, leader);
+                if (dual.mode == kDualM) {
+                    const uint32_t d2 = x.tmem + (uint32_t)dual.d2, t2 = ta - 2 * kKC;
+                    tc::mma_tf32_ts(d2, t2 + 8 * ks, bh, idesc, (uint32_t)(accumulate || ks != 0), leader);
+                    tc::mma_tf32_ts(d2, t2 + kKC + 8 * ks, bh, idesc, 1, leader);
+                    tc::mma_tf32_ts(d2, t2 + 8 * ks, bl, idesc, 1, leader);
+                }
             } else {
                 tc::mma_tf32(dcol, ah, bh, idesc, (uint32_t)(accumulate || ks != 0), leader);
                 tc::mma_tf32(dcol, al, bh, idesc, 1, leader);
                 tc::mma_tf32(dcol, ah, bl, idesc, 1, leader);
             }
             ah += da; al += da; bh += db; bl += db;
+        }
+        if (TS && dual.mode == kDualK) {                    // second K chunk: A2 with the chunk that follows in the weight buffer
+            const uint32_t t2 = ta - 2 * kKC, b2 = x.b_s + 2 * (uint32_t)n16 * kKC * 4;
+            uint64_t ch = tc::smem_desc(b2, lbo_b, 128), cl = tc::smem_desc(b2 + (uint32_t)n16 * kKC * 4, lbo_b, 128);
+            for (int ks = 0; ks < dual.kc2 / 8; ++ks) {
+                tc::mma_tf32_ts(dcol, t2 + 8 * ks, ch, idesc, 1, leader);
+                tc::mma_tf32_ts(dcol, t2 + kKC + 8 * ks, ch, idesc, 1, leader);
+                tc::mma_tf32_ts(dcol, t2 + 8 * ks, cl, idesc, 1, leader);
+                ch += db; cl += db;
+            }
         }
         tc::mma_commit(x.bars, leader);
         if (tim) x.dbg[x.dbg_i * 5 + 3] = clock64();
@@ -310,6 +332,7 @@ struct TcArgs {
     int b_bytes;                             // bytes of the weight-chunk buffer
     int stage_off;                           // byte offset of the node-feature staging (src rows, then tgt rows); 0: gather with plain loads
     int stage_edge_off;                      // byte offset of the edge-feature staging; 0: gather with plain loads
+    int dual;                                // event passes with two A buffers: lin_event chunks in pairs, both orientations of MLP.0 per round
     long long *dbg;                          // TEMPME_TC_TIMING: 128 x 5 clock stamps of CTA 0
 };
 
@@ -365,7 +388,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     const int64_t n_m = a.n_motifs, n_tiles = (n_m + 127) / 128;
     const int bytes_e = (int)chunk_floats(L.evt) * 4, bytes_g = (int)chunk_floats(L.g0) * 4;
     const int bytes_sp = (int)chunk_floats(L.sp) * 4, bytes_q = (int)chunk_floats(L.q) * 4, bytes_r = (int)chunk_floats(L.r) * 4, bytes_m3 = (int)chunk_floats(L.m3) * 4;
-    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, L.evt.w, bytes_e);
+    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, L.evt.w, min(a.dual ? 2 : 1, L.evt.nch) * bytes_e);
     const bool ed_vec = (Ed & 3) == 0, d_vec = (D & 3) == 0;
     float *Fs = a.F + (int64_t)blockIdx.x * 12 * kSlabFloats;           // this CTA's h slabs: [position][column chunk][piece k/4][128 rows][4]
     const float *F0 = Fs, *F1 = Fs + 4 * kSlabFloats, *F2 = Fs + 8 * kSlabFloats;
@@ -439,17 +462,15 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 if (k < D) return live ? cos_accurate(__fadd_rn(__fmul_rn(pi.dt, cstE[L.e_freq + k]), cstE[L.e_phase + k]), ctab) : 0.f;
                 return 0.f;
             };
-            // ---- lin_event (:93) -> E
-            for (int c = 0; c < nE; ++c) {
-                const int kcols = min(kKC, L.evt.K8 - c * kKC);
-                const bool has_edge = c < L.nch_edge;
-                if (stage_edges && has_edge) { tc::mbar_wait(bars + 3, e_phase); e_phase ^= 1; }        // chunk c of the edge rows has landed
-                const int j0 = c * kKC + kb;                        // this thread's columns [j0, j0 + CW) of [edge | TimeEncode]
+            // ---- lin_event (:93) -> E.  fill_evt(cc, second): this thread's columns of chunk cc of [edge | TimeEncode] into an A buffer
+            auto fill_evt = [&](int cc, bool second) {
+                const int kcols = min(kKC, L.evt.K8 - cc * kKC);
+                const int j0 = cc * kKC + kb;                       // this thread's columns [j0, j0 + CW)
                 if (ed_vec && j0 + CW <= Ed) {                      // all edge features (warp-uniform)
 #pragma unroll
                     for (int g = 0; g < CW / 4; ++g)
                         af.put4(x, row, kb, 4 * g, !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stg_e + row * kStageRow + kb + 4 * g) : ldg4(ef + j0 + 4 * g));
-                    af.commit(x, lane_base, kb);
+                    af.commit(x, lane_base, kb, second);
                 } else if (j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + L.D16 && kb + CW <= kcols) {      // all TimeEncode: straight-line code, the cosines interleave
                     float w[CW];
 #pragma unroll
@@ -462,11 +483,11 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                     for (int i = 0; i < CW; ++i) w[i] = (j0 - Ed + i < D && live) ? w[i] : 0.f;
 #pragma unroll
                     for (int g = 0; g < CW / 4; ++g) af.put4(x, row, kb, 4 * g, make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]));
-                    af.commit(x, lane_base, kb);
+                    af.commit(x, lane_base, kb, second);
                 } else {                                            // mixed columns
 #pragma unroll
                     for (int g = 0; g < CW / 4; ++g) {
-                        const int k = kb + 4 * g, j = c * kKC + k;
+                        const int k = kb + 4 * g, j = cc * kKC + k;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (k < kcols) {
                             if (ed_vec && j + 3 < Ed) v = !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stg_e + row * kStageRow + k) : ldg4(ef + j);
@@ -474,73 +495,94 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                         }
                         if (TS || k < kcols) af.put4(x, row, kb, 4 * g, v);
                     }
-                    if (kb < kcols) af.commit(x, lane_base, kb);
+                    if (kb < kcols) af.commit(x, lane_base, kb, second);
                 }
-                const bool last = c + 1 == nE;
-                tc_mma_round<TS>(x, L.D16, kcols, colE, c != 0, last ? L.g0.w : L.evt.w + (int64_t)(c + 1) * chunk_floats(L.evt), last ? bytes_g : bytes_e,
+            };
+            const int cpr = a.dual ? 2 : 1;                         // lin_event chunks per round
+            const int nE_next = pos == 1 ? L.nch_edge : L.evt.nch;  // chunks of the next pass (position 2 skips the pure TimeEncode chunks)
+            for (int c = 0; c < nE; c += cpr) {
+                const int cnt = min(cpr, nE - c);
+                const bool has_edge = c < L.nch_edge;               // pairs are only formed when at most the first chunk holds edge columns
+                if (stage_edges && has_edge) { tc::mbar_wait(bars + 3, e_phase); e_phase ^= 1; }        // chunk c of the edge rows has landed
+                fill_evt(c, false);
+                if (cnt == 2) fill_evt(c + 1, true);
+                const int kc0 = min(kKC, L.evt.K8 - c * kKC), kc1 = cnt == 2 ? min(kKC, L.evt.K8 - (c + 1) * kKC) : 0;
+                const int left = nE - c - cnt;
+                tc_mma_round<TS>(x, L.D16, kc0, colE, c != 0, left > 0 ? L.evt.w + (int64_t)(c + cnt) * chunk_floats(L.evt) : L.g0.w,
+                                 left > 0 ? min(cpr, left) * bytes_e : bytes_g,
                                  [&]() {                            // the staged chunk has been consumed: the next one lands behind the MMAs
                                      if (!has_edge) return;
                                      if (c + 1 < L.nch_edge) request_edges(pi, c + 1);
                                      else if (pos < 2) request_edges(pnext, 0);
-                                 });
+                                 }, Dual{cnt == 2 ? kDualK : kSingle, kc1, 0});
             }
             // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
             const int eb = pos == 2 ? L.e_b2 : L.e_b;
             for (int c = 0; c < nG; ++c) {
                 const int kcols = min(kKC, L.g0.K8 - c * kKC);
                 if (stage_nodes) { tc::mbar_wait(bars + 2, n_phase); n_phase ^= 1; }          // chunk c of the rows has landed
-#pragma unroll 1
-                for (int o = 0; o < 2; ++o) {
-                    if (kb < kcols) {
-                        float sv[CW], gv[CW];
+                float sv[CW], gv[CW], ee[CW];                       // endpoints' features and lin_event output + bias + edge-identity terms
+                auto load_g = [&]() {
 #pragma unroll
-                        for (int k = 0; k < CW; k += 4) {
-                            const int j = c * kKC + kb + k;
-                            float4 s4, g4;
-                            if (stage_nodes) {
-                                s4 = s_ok ? lds4(stg + row * kStageRow + kb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                g4 = t_ok ? lds4(stg + kStageTable + row * kStageRow + kb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            } else if (d_vec && j + 3 < D) {
-                                s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f); g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            } else {
-                                float w[8];
+                    for (int k = 0; k < CW; k += 4) {
+                        const int j = c * kKC + kb + k;
+                        float4 s4, g4;
+                        if (stage_nodes) {
+                            s4 = s_ok ? lds4(stg + row * kStageRow + kb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            g4 = t_ok ? lds4(stg + kStageTable + row * kStageRow + kb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else if (d_vec && j + 3 < D) {
+                            s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f); g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else {
+                            float w[8];
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) { w[i] = (j + i < D && s_ok) ? __ldg(sf + j + i) : 0.f; w[4 + i] = (j + i < D && t_ok) ? __ldg(tf + j + i) : 0.f; }
-                                s4 = make_float4(w[0], w[1], w[2], w[3]); g4 = make_float4(w[4], w[5], w[6], w[7]);
-                            }
-                            sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
+                            for (int i = 0; i < 4; ++i) { w[i] = (j + i < D && s_ok) ? __ldg(sf + j + i) : 0.f; w[4 + i] = (j + i < D && t_ok) ? __ldg(tf + j + i) : 0.f; }
+                            s4 = make_float4(w[0], w[1], w[2], w[3]); g4 = make_float4(w[4], w[5], w[6], w[7]);
                         }
-                        float evv[CW];
-                        tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, evv);
-#pragma unroll
-                        for (int k = 0; k < CW; k += 4) {
-                            const int j0 = c * kKC + kb + k;                 // < D16: constants are zero-padded
-                            const float4 bb = lds4(cstE + eb + j0), w0 = lds4(cstE + L.e_wi + j0), w1 = lds4(cstE + L.e_wi + L.D16 + j0), w2 = lds4(cstE + L.e_wi + 2 * L.D16 + j0);
-                            const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, w0v[4] = {w0.x, w0.y, w0.z, w0.w}, w1v[4] = {w1.x, w1.y, w1.z, w1.w}, w2v[4] = {w2.x, w2.y, w2.z, w2.w};
-                            float z[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                float e_ = evv[k + i] + bv[i];
-                                e_ = fmaf(w0v[i], pi.ei0, e_); e_ = fmaf(w1v[i], pi.ei1, e_); e_ = fmaf(w2v[i], pi.ei2, e_);
-                                const float p_ = o ? gv[k + i] : sv[k + i], q_ = o ? sv[k + i] : gv[k + i];
-                                z[i] = (j0 + i < D && live) ? p_ + fmaxf(q_ + e_, 0.f) : 0.f;
-                            }
-                            af.put4(x, row, kb, k, make_float4(z[0], z[1], z[2], z[3]));
-                        }
-                        af.commit(x, lane_base, kb);
+                        sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
                     }
-                    const bool last = c + 1 == nG;
-                    int64_t noff; int nbytes;
-                    if (o == 0) { noff = L.g0.w + (int64_t)c * chunk_floats(L.g0); nbytes = bytes_g; }
-                    else if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
-                    else if (pos < 2) { noff = L.evt.w; nbytes = bytes_e; }
-                    else { noff = L.sp.w; nbytes = bytes_sp; }
-                    tc_mma_round<TS>(x, H, kcols, colZ + o * H, c != 0, noff, nbytes,
-                                     [&]() {                        // after the second orientation's fill the staged chunk has been consumed
-                                         if (o == 0) return;
-                                         if (c + 1 < nG) request_nodes(pi, c + 1);
-                                         else if (pos < 2) request_nodes(pnext, 0);
-                                     });
+                    tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, ee);
+#pragma unroll
+                    for (int k = 0; k < CW; k += 4) {
+                        const int j0 = c * kKC + kb + k;                 // < D16: constants are zero-padded
+                        const float4 bb = lds4(cstE + eb + j0), w0 = lds4(cstE + L.e_wi + j0), w1 = lds4(cstE + L.e_wi + L.D16 + j0), w2 = lds4(cstE + L.e_wi + 2 * L.D16 + j0);
+                        ee[k] = fmaf(w2.x, pi.ei2, fmaf(w1.x, pi.ei1, fmaf(w0.x, pi.ei0, ee[k] + bb.x)));
+                        ee[k + 1] = fmaf(w2.y, pi.ei2, fmaf(w1.y, pi.ei1, fmaf(w0.y, pi.ei0, ee[k + 1] + bb.y)));
+                        ee[k + 2] = fmaf(w2.z, pi.ei2, fmaf(w1.z, pi.ei1, fmaf(w0.z, pi.ei0, ee[k + 2] + bb.z)));
+                        ee[k + 3] = fmaf(w2.w, pi.ei2, fmaf(w1.w, pi.ei1, fmaf(w0.w, pi.ei0, ee[k + 3] + bb.w)));
+                    }
+                };
+                auto put_z = [&](int o, bool second) {              // orientation o: p + relu(q + event)
+#pragma unroll
+                    for (int k = 0; k < CW; k += 4) {
+                        float z[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float p_ = o ? gv[k + i] : sv[k + i], q_ = o ? sv[k + i] : gv[k + i];
+                            z[i] = (c * kKC + kb + k + i < D && live) ? p_ + fmaxf(q_ + ee[k + i], 0.f) : 0.f;
+                        }
+                        af.put4(x, row, kb, k, make_float4(z[0], z[1], z[2], z[3]));
+                    }
+                    af.commit(x, lane_base, kb, second);
+                };
+                const bool last = c + 1 == nG;
+                auto next_nodes = [&]() {                           // the staged chunk has been consumed
+                    if (c + 1 < nG) request_nodes(pi, c + 1);
+                    else if (pos < 2) request_nodes(pnext, 0);
+                };
+                int64_t noff; int nbytes;                           // weights after this chunk's last round
+                if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
+                else if (pos < 2) { noff = L.evt.w; nbytes = min(cpr, nE_next) * bytes_e; }
+                else { noff = L.sp.w; nbytes = bytes_sp; }
+                if (a.dual) {                                       // both orientations in one round: Zs from the first A buffer, Zt from the second
+                    if (kb < kcols) { load_g(); put_z(0, false); put_z(1, true); }
+                    tc_mma_round<TS>(x, H, kcols, colZ, c != 0, noff, nbytes, next_nodes, Dual{kDualM, 0, colZ + H});
+                } else {
+#pragma unroll 1
+                    for (int o = 0; o < 2; ++o) {
+                        if (kb < kcols) { load_g(); put_z(o, false); }
+                        if (o == 0) tc_mma_round<TS>(x, H, kcols, colZ, c != 0, L.g0.w + (int64_t)c * chunk_floats(L.g0), bytes_g);
+                        else tc_mma_round<TS>(x, H, kcols, colZ + H, c != 0, noff, nbytes, next_nodes);
+                    }
                 }
             }
             // ---- h_pos = relu(MLP.0 + bias): thread part p owns columns [4 CW p, 4 CW (p + 1)) of [Zs | Zt]
@@ -673,7 +715,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             }
             const bool last = c + 1 == L.m3.nch;
             // the staging overlaps the weight buffer of the larger motif-round chunks; MLP.3's are small and R's MMAs have completed
-            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? bytes_e : 0) : bytes_m3,
+            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? min(a.dual ? 2 : 1, L.evt.nch) * bytes_e : 0) : bytes_m3,
                              [&]() { if (c == 0 && more) { request_nodes(pcur, 0); request_edges(pcur, 0); } });
         }
         // ---- MLP.5 + sigmoid (:199-200)
@@ -731,15 +773,20 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     const char *ts_env = getenv("TEMPME_TC_A");                  // "smem": A operand in shared memory (SS); default: in TMEM (TS), the last 64 columns
     const bool ts = !(ts_env && strcmp(ts_env, "smem") == 0);
     uint32_t cols = 32;
-    while ((int)cols < std::max(3 * H, alias_e ? 2 * H : 2 * H + L.D16) + (ts ? 2 * kKC : 0)) cols <<= 1;
+    // event passes with two A buffers (pairs of lin_event chunks, both MLP.0 orientations per round): TS mode, at most the first
+    // lin_event chunk holds edge columns (one staged edge chunk per round)
+    const bool dual = ts && L.nch_edge <= 1 && !getenv("TEMPME_TC_NO_DUAL");
+    // motif rounds: U | Y + one A buffer; event passes: Zs | Zt (| E) + one or two A buffers (the A buffers are the top columns)
+    while ((int)cols < std::max(3 * H + (ts ? 2 * kKC : 0), (alias_e ? 2 * H : 2 * H + L.D16) + (ts ? (dual ? 4 : 2) * kKC : 0))) cols <<= 1;
     if (cols > 512) { set_error("tc_encode_score: node_dim too large for the TMEM layout"); return TM_ERR_UNSUPPORTED; }
     int64_t bb = 0;
     for (const TcLin *l : {&L.evt, &L.g0, &L.sp, &L.q, &L.r, &L.m3}) bb = std::max(bb, chunk_floats(*l) * 4);
+    if (dual) bb = std::max(bb, (int64_t)std::min(2, L.evt.nch) * chunk_floats(L.evt) * 4);          // lin_event chunks arrive in pairs
     // node-feature rows are gathered by bulk TMA into a staging area that may overlap the tail of the weight buffer: rows
     // are in flight only while lin_event / MLP.0 / MLP.3 chunks are being loaded, so it starts behind the largest of those
     const bool stage_nodes = L.D % 4 == 0 && ((uintptr_t)node_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING");
     const bool stage_edges = L.Ed % 4 == 0 && ((uintptr_t)edge_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && !getenv("TEMPME_TC_NO_EDGE_STAGING");
-    const int64_t stage_rel = (std::max(std::max(chunk_floats(L.evt), chunk_floats(L.g0)), chunk_floats(L.m3)) * 4 + 127) & ~(int64_t)127;
+    const int64_t stage_rel = (std::max(std::max((dual ? std::min(2, L.evt.nch) : 1) * chunk_floats(L.evt), chunk_floats(L.g0)), chunk_floats(L.m3)) * 4 + 127) & ~(int64_t)127;
     const int64_t stage_edge_rel = stage_rel + (stage_nodes ? (int64_t)2 * kStageTable * 4 : 0);
     bb = std::max(bb, stage_edge_rel + (stage_edges ? (int64_t)kStageTable * 4 : 0));
     const size_t a_bytes = ts ? 0 : (size_t)2 * kATile;
@@ -775,6 +822,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.F = F; a.scores = scores; a.tmem_cols = cols; a.b_bytes = (int)bb; a.dbg = nullptr;
     a.stage_off = stage_nodes ? (int)(a_bytes + stage_rel) : 0;
     a.stage_edge_off = stage_edges ? (int)(a_bytes + stage_edge_rel) : 0;
+    a.dual = dual;
     static long long *dbg_buf = nullptr;
 #ifdef TM_TC_TIMING
     const char *tim_env = getenv("TEMPME_TC_TIMING");          // diagnostic: per-round clock stamps of CTA 0
