@@ -208,6 +208,11 @@ int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, int K, int 
  * scorer's device routine (exact integer argument reduction; arguments reach 1e8 and beyond). */
 int tm_selftest_cos(const float *d_x, float *d_out, int64_t n, tm_stream stream);
 
+/* Self-test of the tensor-map row gather (cp.async.bulk.tensor tile::gather4) the scorer stages feature rows with: 128 row indices,
+ * columns [col, col + 32) of a row-major fp32 table [rows, dim] -> d_out = the raw 128 x 32 floats left in shared memory (row r of the
+ * staging at floats [32 r, 32 r + 32); with swizzle128 the 16-byte chunk c of row r sits at chunk c ^ (r & 7)). */
+int tm_selftest_gather4(const float *d_table, int64_t rows, int dim, const int32_t *d_idx128, int col, int swizzle128, float *d_out, tm_stream stream);
+
 /* Launch counter: number of kernels this library has launched in this process (bench gpu_launches). */
 uint64_t tm_launch_count(void);
 

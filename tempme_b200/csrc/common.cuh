@@ -1,5 +1,6 @@
 // Shared device/host helpers of libtempme_b200 (sm_100a).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -41,6 +42,9 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
                     const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
                     int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
                     int device, cudaStream_t st);
+
+// tensor map for tile::gather4 row gathers (encoder_tc.cu)
+bool make_gather_map(CUtensorMap *map, const float *table, int64_t rows, int dim, int swizzle128);
 
 // dependency gate of the motif -> edge aggregation (encoder_tc.cu)
 int64_t tc_gate_blob_floats(const tm_gate_desc &d);

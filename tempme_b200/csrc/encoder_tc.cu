@@ -19,6 +19,7 @@
 // Thread (row, part) owns TMEM lane `row` and CW of the 32 columns of every K chunk (CW = 8: 512 threads): it reads the previous
 // accumulator row with tcgen05.ld, applies bias / ReLU / mixing in fp32 registers, splits into tf32 hi + lo and stores
 // the K-major operand tile in shared memory; weights arrive pre-split and pre-tiled by 1-D bulk TMA.
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -315,8 +316,19 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(tc::smem_u32(mbar)) : "memory"); }
-constexpr int kStageRow = 36;     // floats per staged feature row piece: 128 bytes + 16 bytes of padding (conflict-free 16-byte reads down a column of rows)
+// Feature rows are gathered by tensor-map TMA, four rows per instruction (tile::gather4), into 128-byte staging rows with the
+// 128-byte swizzle: chunk c (16 bytes) of a staging row sits at chunk c ^ (bits 7-9 of the row's shared-memory address), so 16-byte
+// reads down a column of rows are conflict-free.  One table's staging = 128 rows x 128 bytes (tm_selftest_gather4 pins the layout).
+constexpr int kStageRow = 32;     // floats per staged row piece
 constexpr int kStageTable = 128 * kStageRow;
+__device__ __forceinline__ const float *stage_piece(const float *tab, int row, int k) {      // columns [k, k+4) of the chunk, k % 4 == 0
+    const float *p = tab + row * kStageRow;
+    return p + (((k >> 2) ^ (int)((tc::smem_u32(p) >> 7) & 7u)) << 2);
+}
+__device__ __forceinline__ void tma_gather4(void *dst_smem, const CUtensorMap *map, int col, int r0, int r1, int r2, int r3, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n"
+                 :: "r"(tc::smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(tc::smem_u32(mbar)) : "memory");
+}
 
 struct TcArgs {
     int64_t n_motifs, W, group, m_begin;     // this launch scores motifs [m_begin, m_begin + slab)
@@ -360,9 +372,10 @@ template <> __device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, float *v
 // CW = columns of a K chunk per thread: 16 -> 256 threads, 8 -> 512 threads; TS = A operand in TMEM (else shared memory)
 template <int CW, bool TS>
 __global__ void __launch_bounds__(128 * (kKC / CW), 2)
-score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a) {
+score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a, const __grid_constant__ CUtensorMap tm_node,
+                const __grid_constant__ CUtensorMap tm_edge) {
     constexpr int kParts = kKC / CW, kThreads = 128 * kParts;
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[4];              // [0] MMAs done, [1] weight chunk landed, [2] staged node-feature rows landed, [3] staged edge-feature rows landed
     __shared__ uint32_t tmem_slot;
     __shared__ float part[kParts][3][128];
@@ -414,26 +427,27 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     const bool stage_nodes = a.stage_off != 0;
     float *stg = reinterpret_cast<float *>(smem + a.stage_off);
     uint32_t n_phase = 0;
-    // one mbarrier arrival per warp: lane 0 announces the bytes of the warp's valid rows, then every valid lane issues its copy
-    auto request_rows = [&](uint64_t *bar, bool valid, float *dst, const float *src, int bytes) {
-        const unsigned m = __ballot_sync(0xffffffffu, valid);
-        if ((t & 31) == 0) { if (m) tc::mbar_expect_tx(bar, (uint32_t)(__popc(m) * bytes)); else mbar_arrive(bar); }
+    // One mbarrier arrival per warp.  A requesting warp gathers its 32 rows with eight gather4 instructions (lanes 0-7, the row
+    // indices come from the owning lanes by shuffle; rows that are out of range fetch row 0 and are ignored by the reader).
+    auto request_rows = [&](uint64_t *bar, bool warp_requests, const CUtensorMap *map, int idx, float *tab, int col) {
+        const int lane = t & 31, l4 = (lane & 7) * 4;
+        const int r0 = __shfl_sync(0xffffffffu, idx, l4), r1 = __shfl_sync(0xffffffffu, idx, l4 + 1), r2 = __shfl_sync(0xffffffffu, idx, l4 + 2),
+                  r3 = __shfl_sync(0xffffffffu, idx, l4 + 3);
+        if (lane == 0) { if (warp_requests) tc::mbar_expect_tx(bar, 8u * 4u * kStageRow * 4u); else mbar_arrive(bar); }
         __syncwarp();
-        if (valid) tc::tma_load_1d(dst, src, (uint32_t)bytes, bar);
+        if (warp_requests && lane < 8) tma_gather4(tab + ((warp & 3) * 32 + l4) * kStageRow, map, col, r0, r1, r2, r3, bar);
     };
-    auto request_nodes = [&](const PassIdx &q, int c) {       // chunk c of both endpoints' rows (:348-351)
+    auto request_nodes = [&](const PassIdx &q, int c) {       // chunk c of both endpoints' rows (:348-351): part 0 source rows, part 1 target rows
         if (!stage_nodes) return;
         const int idx = prt == 0 ? q.ns : q.nt;
-        request_rows(bars + 2, prt < 2 && idx >= 0 && idx < a.n_node_rows, stg + (prt & 1) * kStageTable + row * kStageRow,
-                     a.node_feat + (int64_t)max(idx, 0) * D + c * kKC, min(kKC, D - c * kKC) * 4);
+        request_rows(bars + 2, prt < 2, &tm_node, (idx >= 0 && idx < a.n_node_rows) ? idx : 0, stg + (prt & 1) * kStageTable, c * kKC);
     };
     const bool stage_edges = a.stage_edge_off != 0;
     float *stg_e = reinterpret_cast<float *>(smem + a.stage_edge_off);
     uint32_t e_phase = 0;
     auto request_edges = [&](const PassIdx &q, int c) {       // chunk c of the edge-feature rows (:332-338); part 0 requests
         if (!stage_edges) return;
-        request_rows(bars + 3, prt == 0 && q.e >= 0 && q.e < a.n_edge_rows, stg_e + row * kStageRow,
-                     a.edge_feat + (int64_t)max(q.e, 0) * Ed + c * kKC, min(kKC, Ed - c * kKC) * 4);
+        request_rows(bars + 3, prt == 0, &tm_edge, (q.e >= 0 && q.e < a.n_edge_rows) ? q.e : 0, stg_e, c * kKC);
     };
     PassIdx pcur, pnext;
     {
@@ -469,7 +483,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 if (ed_vec && j0 + CW <= Ed) {                      // all edge features (warp-uniform)
 #pragma unroll
                     for (int g = 0; g < CW / 4; ++g)
-                        af.put4(x, row, kb, 4 * g, !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stg_e + row * kStageRow + kb + 4 * g) : ldg4(ef + j0 + 4 * g));
+                        af.put4(x, row, kb, 4 * g, !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stage_piece(stg_e, row, kb + 4 * g)) : ldg4(ef + j0 + 4 * g));
                     af.commit(x, lane_base, kb, second);
                 } else if (j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + L.D16 && kb + CW <= kcols) {      // all TimeEncode: straight-line code, the cosines interleave
                     float w[CW];
@@ -490,7 +504,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                         const int k = kb + 4 * g, j = cc * kKC + k;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (k < kcols) {
-                            if (ed_vec && j + 3 < Ed) v = !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stg_e + row * kStageRow + k) : ldg4(ef + j);
+                            if (ed_vec && j + 3 < Ed) v = !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stage_piece(stg_e, row, k)) : ldg4(ef + j);
                             else v = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
                         }
                         if (TS || k < kcols) af.put4(x, row, kb, 4 * g, v);
@@ -528,8 +542,8 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                         const int j = c * kKC + kb + k;
                         float4 s4, g4;
                         if (stage_nodes) {
-                            s4 = s_ok ? lds4(stg + row * kStageRow + kb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            g4 = t_ok ? lds4(stg + kStageTable + row * kStageRow + kb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            s4 = s_ok ? lds4(stage_piece(stg, row, kb + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            g4 = t_ok ? lds4(stage_piece(stg + kStageTable, row, kb + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         } else if (d_vec && j + 3 < D) {
                             s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f); g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                         } else {
@@ -760,6 +774,24 @@ static bool g_prof = false;
 static std::vector<cudaEvent_t> g_prof_ev;      // pairs: before, after
 static size_t g_prof_used = 0;
 
+// 2-D tensor map over a row-major fp32 feature table [rows x dim] with a box of 32 columns x 1 row (tile::gather4 fetches four such
+// rows), 128-byte swizzle, zero fill outside the table
+bool make_gather_map(CUtensorMap *map, const float *table, int64_t rows, int dim, int swizzle128) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return false;
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows}, gstride[1] = {(cuuint64_t)dim * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kKC, 1}, estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)table, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // std_ = per-batch std (already computed); F = scratch for the h slabs of the resident CTAs
 int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
                     const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
@@ -784,15 +816,18 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     if (dual) bb = std::max(bb, (int64_t)std::min(2, L.evt.nch) * chunk_floats(L.evt) * 4);          // lin_event chunks arrive in pairs
     // node-feature rows are gathered by bulk TMA into a staging area that may overlap the tail of the weight buffer: rows
     // are in flight only while lin_event / MLP.0 / MLP.3 chunks are being loaded, so it starts behind the largest of those
-    const bool stage_nodes = L.D % 4 == 0 && ((uintptr_t)node_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING");
-    const bool stage_edges = L.Ed % 4 == 0 && ((uintptr_t)edge_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && !getenv("TEMPME_TC_NO_EDGE_STAGING");
-    const int64_t stage_rel = (std::max(std::max((dual ? std::min(2, L.evt.nch) : 1) * chunk_floats(L.evt), chunk_floats(L.g0)), chunk_floats(L.m3)) * 4 + 127) & ~(int64_t)127;
+    CUtensorMap tm_node, tm_edge;
+    memset(&tm_node, 0, sizeof tm_node); memset(&tm_edge, 0, sizeof tm_edge);
+    const bool stage_nodes = L.D % 4 == 0 && ((uintptr_t)node_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && make_gather_map(&tm_node, node_feat, n_node_rows, L.D, 1);
+    const bool stage_edges = L.Ed % 4 == 0 && ((uintptr_t)edge_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && !getenv("TEMPME_TC_NO_EDGE_STAGING") &&
+                             make_gather_map(&tm_edge, edge_feat, n_edge_rows, L.Ed, 1);
+    const int64_t stage_rel = (std::max(std::max((dual ? std::min(2, L.evt.nch) : 1) * chunk_floats(L.evt), chunk_floats(L.g0)), chunk_floats(L.m3)) * 4 + 1023) & ~(int64_t)1023;
     const int64_t stage_edge_rel = stage_rel + (stage_nodes ? (int64_t)2 * kStageTable * 4 : 0);
     bb = std::max(bb, stage_edge_rel + (stage_edges ? (int64_t)kStageTable * 4 : 0));
     const size_t a_bytes = ts ? 0 : (size_t)2 * kATile;
     const size_t need = a_bytes + (size_t)bb + (size_t)(L.n_cstE + L.n_cstM) * 4 + 152 * 8;
     if (need > 220 * 1024) { set_error("tc_encode_score: feature dims too large for one weight chunk in shared memory"); return TM_ERR_UNSUPPORTED; }
-    using ScoreK = void (*)(const TcLayout, const float *, const TcArgs);
+    using ScoreK = void (*)(const TcLayout, const float *, const TcArgs, const CUtensorMap, const CUtensorMap);
     static const ScoreK kern[4] = {score_tc_kernel<8, false>, score_tc_kernel<16, false>, score_tc_kernel<8, true>, score_tc_kernel<16, true>};
     static bool attr_set[64] = {false};
     if (!attr_set[device]) {
@@ -843,7 +878,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         pe = &g_prof_ev[g_prof_used]; g_prof_used += 2;
         cudaEventRecord(pe[0], st);
     }
-    kern[kv]<<<grid, 128 * (kKC / cw), smem, st>>>(L, d_blob_tc, a);
+    kern[kv]<<<grid, 128 * (kKC / cw), smem, st>>>(L, d_blob_tc, a, tm_node, tm_edge);
     TM_LAUNCH_CHECK();
     if (pe) cudaEventRecord(pe[1], st);
     if (tim_env) {

@@ -110,6 +110,38 @@ __global__ void selftest_cos_kernel(const float *__restrict__ x, float *__restri
 }
 }  // namespace tmb
 
+namespace tmb {
+// raw dump of what eight gather4 instructions per warp leave in shared memory: 128 staging rows x 32 floats
+__global__ void selftest_gather4_kernel(const __grid_constant__ CUtensorMap map, const int32_t *__restrict__ idx, int col, float *__restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    float *stg = reinterpret_cast<float *>(smem);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < 128 * 32; i += blockDim.x) stg[i] = -12345.f;
+    if (t == 0) tc::mbar_init(&bar, 4);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    const int id = idx[t], l4 = (lane & 7) * 4;
+    const int r0 = __shfl_sync(0xffffffffu, id, l4), r1 = __shfl_sync(0xffffffffu, id, l4 + 1), r2 = __shfl_sync(0xffffffffu, id, l4 + 2), r3 = __shfl_sync(0xffffffffu, id, l4 + 3);
+    if (lane == 0) tc::mbar_expect_tx(&bar, 8u * 512u);
+    __syncwarp();
+    if (lane < 8)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n"
+                     :: "r"(tc::smem_u32(stg + (warp * 32 + l4) * 32)), "l"(reinterpret_cast<uint64_t>(&map)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3),
+                        "r"(tc::smem_u32(&bar)) : "memory");
+    tc::mbar_wait(&bar, 0);
+    for (int i = t; i < 128 * 32; i += blockDim.x) out[i] = stg[i];
+}
+}  // namespace tmb
+
+extern "C" int tm_selftest_gather4(const float *d_table, int64_t rows, int dim, const int32_t *d_idx128, int col, int swizzle128, float *d_out, tm_stream stream) {
+    CUtensorMap map;
+    if (!make_gather_map(&map, d_table, rows, dim, swizzle128)) { set_error("tm_selftest_gather4: cuTensorMapEncodeTiled failed"); return TM_ERR_CUDA; }
+    selftest_gather4_kernel<<<1, 128, 128 * 32 * 4, (cudaStream_t)stream>>>(map, d_idx128, col, d_out);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}
+
 extern "C" int tm_selftest_cos(const float *d_x, float *d_out, int64_t n, tm_stream stream) {
     if (!d_x || !d_out || n < 0) { set_error("tm_selftest_cos: bad argument"); return TM_ERR_ARG; }
     if (n == 0) return TM_OK;

@@ -71,3 +71,29 @@ def test_timeencode_cosine_accuracy():
     bad = torch.tensor([float("inf"), float("-inf"), float("nan")], device="cuda"); o2 = torch.zeros(3, device="cuda")
     _lib.check(L.tm_selftest_cos(_lib.ptr(bad), _lib.ptr(o2), 3, st), "tm_selftest_cos")
     assert torch.isnan(o2).all()
+
+
+@pytest.mark.parametrize("swizzle", [0, 1])
+def test_tma_gather4_layout(swizzle):
+    """tile::gather4 row gathers (the scorer's feature staging): four table rows per instruction land as consecutive 128-byte
+    staging rows; with the 128-byte swizzle the 16-byte chunk c of a row sits at c ^ (bits 7-9 of its shared-memory address);
+    columns beyond the table are zero-filled."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tempme_b200 import _lib
+    L = _lib.lib()
+    rows, dim = 500, 44
+    tab = (np.arange(rows)[:, None] * 1000 + np.arange(dim)[None, :]).astype(np.float32)
+    idx = np.random.default_rng(0).integers(0, rows, 128).astype(np.int32)
+    dt, di = torch.as_tensor(tab).cuda(), torch.as_tensor(idx).cuda()
+    for col in (0, 32):
+        out = torch.zeros(128 * 32, device="cuda")
+        _lib.check(L.tm_selftest_gather4(_lib.ptr(dt), rows, dim, _lib.ptr(di), col, swizzle, _lib.ptr(out), None), "tm_selftest_gather4")
+        torch.cuda.synchronize()
+        o = out.cpu().numpy().reshape(128, 32)
+        shift = int(np.flatnonzero(o[0, ::4] == tab[idx[0], col])[0]) if swizzle else 0     # (address bits 7-9) of staging row 0
+        for r in range(128):
+            v = np.zeros(32, np.float32); n = max(0, min(32, dim - col)); v[:n] = tab[idx[r], col:col + n]
+            x = (r + shift) & 7 if swizzle else 0
+            exp = np.concatenate([v[4 * (c ^ x):4 * (c ^ x) + 4] for c in range(8)])
+            assert (o[r] == exp).all(), (swizzle, col, r)
