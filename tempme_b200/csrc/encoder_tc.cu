@@ -198,6 +198,7 @@ struct TcCtx {
     uint8_t *a;            // A operand in shared memory (SS mode): hi tile, then lo tile
     uint32_t a_s, b_s;     // shared-space addresses of the A tiles and of the weight buffer
     uint32_t a_col;        // A operand in TMEM (TS mode): hi at columns [a_col, a_col + 32), lo at [a_col + 32, a_col + 64)
+    uint32_t a_col2;       // second A buffer of the dual rounds (event passes: the 64 columns below a_col; Q / R rounds: columns [0, 64))
     uint64_t *bars;        // [0] MMAs done, [1] weight chunk landed
     uint32_t mma_phase, b_phase;
     uint32_t tmem;
@@ -231,7 +232,7 @@ struct AFill {
     // all CW columns have been put; second: the event passes' second A buffer (the 64 TMEM columns below the primary one)
     __device__ __forceinline__ void commit(const TcCtx &x, uint32_t lane_base, int kb, bool second = false) {
         if (TS) {
-            const uint32_t a0 = x.tmem + lane_base + x.a_col - (second ? 2 * kKC : 0) + (uint32_t)kb;
+            const uint32_t a0 = x.tmem + lane_base + (second ? x.a_col2 : x.a_col) + (uint32_t)kb;
             if (CW == 16) { tc::tmem_st16(a0, hi); tc::tmem_st16(a0 + kKC, lo); }
             else { tc::tmem_st8(a0, hi); tc::tmem_st8(a0 + kKC, lo); }
             tc::tmem_st_wait();
@@ -277,7 +278,7 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
                 tc::mma_tf32_ts(dcol, ta + kKC + 8 * ks, bh, idesc, 1, leader);
                 tc::mma_tf32_ts(dcol, ta + 8 * ks, bl, idesc, 1, leader);
                 if (dual.mode == kDualM) {
-                    const uint32_t d2 = x.tmem + (uint32_t)dual.d2, t2 = ta - 2 * kKC;
+                    const uint32_t d2 = x.tmem + (uint32_t)dual.d2, t2 = x.tmem + x.a_col2;
                     tc::mma_tf32_ts(d2, t2 + 8 * ks, bh, idesc, (uint32_t)(accumulate || ks != 0), leader);
                     tc::mma_tf32_ts(d2, t2 + kKC + 8 * ks, bh, idesc, 1, leader);
                     tc::mma_tf32_ts(d2, t2 + 8 * ks, bl, idesc, 1, leader);
@@ -290,7 +291,7 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
             ah += da; al += da; bh += db; bl += db;
         }
         if (TS && dual.mode == kDualK) {                    // second K chunk: A2 with the chunk that follows in the weight buffer
-            const uint32_t t2 = ta - 2 * kKC, b2 = x.b_s + 2 * (uint32_t)n16 * kKC * 4;
+            const uint32_t t2 = x.tmem + x.a_col2, b2 = x.b_s + 2 * (uint32_t)n16 * kKC * 4;
             uint64_t ch = tc::smem_desc(b2, lbo_b, 128), cl = tc::smem_desc(b2 + (uint32_t)n16 * kKC * 4, lbo_b, 128);
             for (int ks = 0; ks < dual.kc2 / 8; ++ks) {
                 tc::mma_tf32_ts(dcol, t2 + 8 * ks, ch, idesc, 1, leader);
@@ -393,11 +394,12 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC;
+    x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC; x.a_col2 = x.a_col - 2 * kKC;
     AFill<CW, TS> af;
     const int H = L.H, H2 = 2 * L.H, D = L.D, Ed = L.Ed, nG = L.g0.nch, nchS = L.sp.nch;
     const int colZ = 0, colE = (nG == 1 && L.D16 <= H) ? H : H2;
-    const int colU = 0, colY = H2, colM0 = 0, colM1 = H2;
+    const bool dq = a.dual != 0;                           // Q and R rounds in pairs: second A buffer = columns [0, 64) (U is dead by then)
+    const int colU = 0, colY = H2, colM0 = dq ? H : 0, colM1 = dq ? 0 : H2;
     const int64_t n_m = a.n_motifs, n_tiles = (n_m + 127) / 128;
     const int bytes_e = (int)chunk_floats(L.evt) * 4, bytes_g = (int)chunk_floats(L.g0) * 4;
     const int bytes_sp = (int)chunk_floats(L.sp) * 4, bytes_q = (int)chunk_floats(L.q) * 4, bytes_r = (int)chunk_floats(L.r) * 4, bytes_m3 = (int)chunk_floats(L.m3) * 4;
@@ -463,6 +465,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         const bool live = gm_ < n_m, more = tile + gridDim.x < n_tiles;
         const int64_t gm = live ? gm_ : 0;
         // =========================== event passes ===========================
+        x.a_col2 = x.a_col - 2 * kKC;
 #pragma unroll 1
         for (int pos = 0; pos < 3; ++pos) {
             const int nE = pos == 2 ? L.nch_edge : L.evt.nch;          // position 2: dt = 0, the pure TimeEncode chunks are in the bias
@@ -635,7 +638,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 }
                 af.commit(x, lane_base, kb);
                 const bool last = c + 1 == nchS;
-                tc_mma_round<TS>(x, 3 * H, kKC, colU, c != 0, last ? L.q.w : L.sp.w + (int64_t)(c + 1) * chunk_floats(L.sp), last ? bytes_q : bytes_sp);
+                tc_mma_round<TS>(x, 3 * H, kKC, colU, c != 0, last ? L.q.w : L.sp.w + (int64_t)(c + 1) * chunk_floats(L.sp), last ? (dq ? 2 : 1) * bytes_q : bytes_sp);
             }
         }
         // ---- s_k = h_k . (U + cu) + r  (:806-808 after folding)
@@ -680,18 +683,35 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         const float mx = fmaxf(s0, s1), e0 = expf(s0 - mx), e1 = expf(s1 - mx);
         const float al0 = e0 / (e0 + e1), al1 = e1 / (e0 + e1);
         // ---- Y += Q (alpha_0 h_0 + alpha_1 h_1)   (:841-843 after folding)
-        for (int c = 0; c < nchS; ++c) {
-            float c0[CW], c1[CW];
-#pragma unroll
-            for (int i = 0; i < CW; ++i) { c0[i] = n0[i]; c1[i] = n1[i]; }
-            if (c + 1 < nchS) { ldw(F0 + (c + 1) * kSlabFloats, n0); ldw(F1 + (c + 1) * kSlabFloats, n1); }
+        auto put_mix = [&](const float *c0, const float *c1, bool second) {
 #pragma unroll
             for (int k = 0; k < CW; k += 4)
                 af.put4(x, row, kb, k, make_float4(fmaf(al0, c0[k], al1 * c1[k]), fmaf(al0, c0[k + 1], al1 * c1[k + 1]),
                                                    fmaf(al0, c0[k + 2], al1 * c1[k + 2]), fmaf(al0, c0[k + 3], al1 * c1[k + 3])));
-            af.commit(x, lane_base, kb);
-            const bool last = c + 1 == nchS;
-            tc_mma_round<TS>(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 1) * chunk_floats(L.q), last ? bytes_r : bytes_q);
+            af.commit(x, lane_base, kb, second);
+        };
+        if (dq) {                                               // two K chunks per round
+            x.a_col2 = colU;
+            for (int c = 0; c < nchS; c += 2) {
+                float m0[CW], m1[CW];
+                ldw(F0 + (c + 1) * kSlabFloats, m0); ldw(F1 + (c + 1) * kSlabFloats, m1);
+                put_mix(n0, n1, false);
+                if (c + 2 < nchS) { ldw(F0 + (c + 2) * kSlabFloats, n0); ldw(F1 + (c + 2) * kSlabFloats, n1); }
+                put_mix(m0, m1, true);
+                const bool last = c + 2 >= nchS;
+                tc_mma_round<TS>(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 2) * chunk_floats(L.q), last ? 2 * bytes_r : 2 * bytes_q, NoMid(),
+                                 Dual{kDualK, kKC, 0});
+            }
+        } else {
+            for (int c = 0; c < nchS; ++c) {
+                float c0[CW], c1[CW];
+#pragma unroll
+                for (int i = 0; i < CW; ++i) { c0[i] = n0[i]; c1[i] = n1[i]; }
+                if (c + 1 < nchS) { ldw(F0 + (c + 1) * kSlabFloats, n0); ldw(F1 + (c + 1) * kSlabFloats, n1); }
+                put_mix(c0, c1, false);
+                const bool last = c + 1 == nchS;
+                tc_mma_round<TS>(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 1) * chunk_floats(L.q), last ? bytes_r : bytes_q);
+            }
         }
         // ---- M0 = R relu(Y + cy)   (attention.MLP.3 and MLP.0 folded); the next tile's first-pass indices start to arrive
         {
@@ -699,7 +719,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             const bool lv = more && gn < n_m;
             pcur = load_idx(lv ? gn : 0, lv, 0);
         }
-        for (int c = 0; c < L.r.nch; ++c) {
+        auto put_y = [&](int c, bool second) {
             float z[CW];
             tmem_ldw<CW>(tmem + lane_base + colY + c * kKC + kb, z);
 #pragma unroll
@@ -707,9 +727,17 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 const float4 bb = lds4(cstM + L.m_cy + c * kKC + kb + k);
                 af.put4(x, row, kb, k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
             }
-            af.commit(x, lane_base, kb);
-            const bool last = c + 1 == L.r.nch;
-            tc_mma_round<TS>(x, L.M16, kKC, colM0, c != 0, last ? L.m3.w : L.r.w + (int64_t)(c + 1) * chunk_floats(L.r), last ? bytes_m3 : bytes_r);
+            af.commit(x, lane_base, kb, second);
+        };
+        if (dq) {                                               // both K chunks in one round; M0 lands at [H, H + M16) (Y has been read completely)
+            put_y(0, false); put_y(1, true);
+            tc_mma_round<TS>(x, L.M16, kKC, colM0, false, L.m3.w, bytes_m3, NoMid(), Dual{kDualK, kKC, 0});
+        } else {
+            for (int c = 0; c < L.r.nch; ++c) {
+                put_y(c, false);
+                const bool last = c + 1 == L.r.nch;
+                tc_mma_round<TS>(x, L.M16, kKC, colM0, c != 0, last ? L.m3.w : L.r.w + (int64_t)(c + 1) * chunk_floats(L.r), last ? bytes_m3 : bytes_r);
+            }
         }
         // ---- M1 = MLP.3 relu(M0 + cm[category])   (:199)
         const float *cmr = blob + L.cm + (int64_t)((L.if_cat && live && a.cat) ? min((int)a.cat[gm], 11) : 0) * L.M16;
@@ -971,7 +999,7 @@ gate_tc_kernel(const GateLayout G, const float *__restrict__ blob, const GateArg
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC;
+    x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC; x.a_col2 = x.a_col;
     AFill<CW, true> af;
     const int D = G.D, Ed = G.Ed, H = G.H, colG1 = 0, colG2 = H;
     const int64_t n_tiles = (a.n_events + 127) / 128;
