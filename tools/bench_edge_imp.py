@@ -38,17 +38,20 @@ roots, e, cut64 = pipe.stage_queries(*synth.make_queries(graph, rng, Q))
 R = roots.numel()
 scores, (nodes, eidx, t, cat, eid) = pipe.run_device(roots, e, cut64, want_walks=True)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-ms = {"hop2": 0.0, "edge_imp": 0.0}
+ms = {"hop2": 0.0, "edge_imp": 0.0, "aggregate_only": 0.0}
+nodep = tm.TempME(Base(), "tgn", args.workload, 40, 64, device=dev, null_model={}, use_dependency_aware_sampling=False).to(dev).eval()
 for it in range(args.warmup + args.steps):
     flush.zero_()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     ev[0].record()
     sub = finder.find_k_hop_device(2, roots, None, n, e, seed=9)          # hop-1 + hop-2 slots (graph.py:233-262)
     ev[1].record()
     imp0, imp1 = model.edge_importance_device(scores, eidx, t, sub[0][0].view(R, n), sub[1][0].view(R, n), sub[0][1].view(R, n * n), sub[1][1].view(R, n * n))
-    ev[2].record(); ev[2].synchronize()
+    ev[2].record()
+    nodep.edge_importance_device(scores, eidx, t, sub[0][0].view(R, n), sub[1][0].view(R, n), sub[0][1].view(R, n * n), sub[1][1].view(R, n * n))   # no gate: segmented max only
+    ev[3].record(); ev[3].synchronize()
     if it >= args.warmup:
-        ms["hop2"] += ev[0].elapsed_time(ev[1]); ms["edge_imp"] += ev[1].elapsed_time(ev[2])
+        ms["hop2"] += ev[0].elapsed_time(ev[1]); ms["edge_imp"] += ev[1].elapsed_time(ev[2]); ms["aggregate_only"] += ev[2].elapsed_time(ev[3])
 ms = {k: v / args.steps for k, v in ms.items()}
 M = R * W
 gate_flops = M * 3 * 2.0 * ((Ed + D) * 64 + 64 * 32 + 32)
