@@ -999,12 +999,12 @@ gate_tc_kernel(const GateLayout G, const float *__restrict__ blob, const GateArg
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC; x.a_col2 = x.a_col;
+    x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC; x.a_col2 = x.a_col - 2 * kKC;          // TMEM: G1 [0,H)  G2 [H, H + H/2)  A2 [128,192)  A [192,256)
     AFill<CW, true> af;
     const int D = G.D, Ed = G.Ed, H = G.H, colG1 = 0, colG2 = H;
     const int64_t n_tiles = (a.n_events + 127) / 128;
     const int bytes1 = (int)chunk_floats(G.l1) * 4, bytes2 = (int)chunk_floats(G.l2) * 4;
-    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, G.l1.w, bytes1);
+    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, G.l1.w, min(2, G.l1.nch) * bytes1);
     const bool ed_vec = (Ed & 3) == 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t r = tile * 128 + row;
@@ -1018,51 +1018,61 @@ gate_tc_kernel(const GateLayout G, const float *__restrict__ blob, const GateArg
             const int k = j - Ed;
             return (k < D && live) ? cos_accurate(__fadd_rn(__fmul_rn(tt, cst[G.freq + k]), cst[G.phase + k]), ctab) : 0.f;
         };
-        // ---- Linear(Ed + D, H) -> G1
-        for (int c = 0; c < G.l1.nch; ++c) {
+        // ---- Linear(Ed + D, H) -> G1, two K chunks per round
+        auto fill1 = [&](int c, bool second) {
             const int kcols = min(kKC, G.l1.K8 - c * kKC), j0 = c * kKC + kb;
-            if (kb < kcols) {
-                if (ed_vec && j0 + CW <= Ed) {
+            if (kb >= kcols) return;
+            if (ed_vec && j0 + CW <= Ed) {
 #pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) af.put4(x, row, kb, 4 * g, e_ok ? ldg4(ef + j0 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f));
-                } else if (j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + G.D16) {
-                    float w[CW];
+                for (int g = 0; g < CW / 4; ++g) af.put4(x, row, kb, 4 * g, e_ok ? ldg4(ef + j0 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f));
+            } else if (j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + G.D16) {
+                float w[CW];
 #pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) {
-                        const float4 fq = lds4(cst + G.freq + (j0 - Ed) + 4 * g), ph = lds4(cst + G.phase + (j0 - Ed) + 4 * g);
-                        w[4 * g] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.x), ph.x), ctab); w[4 * g + 1] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.y), ph.y), ctab);
-                        w[4 * g + 2] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.z), ph.z), ctab); w[4 * g + 3] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.w), ph.w), ctab);
-                    }
-#pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) {
-                        const int k = j0 - Ed + 4 * g;
-                        af.put4(x, row, kb, 4 * g, make_float4((k < D && live) ? w[4 * g] : 0.f, (k + 1 < D && live) ? w[4 * g + 1] : 0.f,
-                                                               (k + 2 < D && live) ? w[4 * g + 2] : 0.f, (k + 3 < D && live) ? w[4 * g + 3] : 0.f));
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) { const int j = j0 + 4 * g; af.put4(x, row, kb, 4 * g, make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3))); }
+                for (int g = 0; g < CW / 4; ++g) {
+                    const float4 fq = lds4(cst + G.freq + (j0 - Ed) + 4 * g), ph = lds4(cst + G.phase + (j0 - Ed) + 4 * g);
+                    w[4 * g] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.x), ph.x), ctab); w[4 * g + 1] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.y), ph.y), ctab);
+                    w[4 * g + 2] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.z), ph.z), ctab); w[4 * g + 3] = cos_accurate(__fadd_rn(__fmul_rn(tt, fq.w), ph.w), ctab);
                 }
-                af.commit(x, lane_base, kb);
+#pragma unroll
+                for (int g = 0; g < CW / 4; ++g) {
+                    const int k = j0 - Ed + 4 * g;
+                    af.put4(x, row, kb, 4 * g, make_float4((k < D && live) ? w[4 * g] : 0.f, (k + 1 < D && live) ? w[4 * g + 1] : 0.f,
+                                                           (k + 2 < D && live) ? w[4 * g + 2] : 0.f, (k + 3 < D && live) ? w[4 * g + 3] : 0.f));
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < CW / 4; ++g) { const int j = j0 + 4 * g; af.put4(x, row, kb, 4 * g, make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3))); }
             }
-            const bool last = c + 1 == G.l1.nch;
-            tc_mma_round<true>(x, r16(H), kcols, colG1, c != 0, last ? G.l2.w : G.l1.w + (int64_t)(c + 1) * chunk_floats(G.l1), last ? bytes2 : bytes1);
+            af.commit(x, lane_base, kb, second);
+        };
+        for (int c = 0; c < G.l1.nch; c += 2) {
+            const int cnt = min(2, G.l1.nch - c), left = G.l1.nch - c - cnt;
+            fill1(c, false);
+            if (cnt == 2) fill1(c + 1, true);
+            const int kc0 = min(kKC, G.l1.K8 - c * kKC), kc1 = cnt == 2 ? min(kKC, G.l1.K8 - (c + 1) * kKC) : 0;
+            tc_mma_round<true>(x, r16(H), kc0, colG1, c != 0, left > 0 ? G.l1.w + (int64_t)(c + 2) * chunk_floats(G.l1) : G.l2.w,
+                               left > 0 ? min(2, left) * bytes1 : min(2, G.l2.nch) * bytes2, NoMid(), Dual{cnt == 2 ? kDualK : kSingle, kc1, 0});
         }
-        // ---- ReLU, Linear(H, H/2) -> G2
-        for (int c = 0; c < G.l2.nch; ++c) {
+        // ---- ReLU, Linear(H, H/2) -> G2, two K chunks per round
+        auto fill2 = [&](int c, bool second) {
             const int kcols = min(kKC, G.l2.K8 - c * kKC);
-            if (kb < kcols) {
-                float z[CW];
-                tc::tmem_ld16(tmem + lane_base + colG1 + c * kKC + kb, z);
+            if (kb >= kcols) return;
+            float z[CW];
+            tc::tmem_ld16(tmem + lane_base + colG1 + c * kKC + kb, z);
 #pragma unroll
-                for (int k = 0; k < CW; k += 4) {
-                    const float4 bb = lds4(cst + G.b1 + c * kKC + kb + k);
-                    af.put4(x, row, kb, k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
-                }
-                af.commit(x, lane_base, kb);
+            for (int k = 0; k < CW; k += 4) {
+                const float4 bb = lds4(cst + G.b1 + c * kKC + kb + k);
+                af.put4(x, row, kb, k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
             }
-            const bool last = c + 1 == G.l2.nch;
-            tc_mma_round<true>(x, r16(G.H2), kcols, colG2, c != 0, last ? G.l1.w : G.l2.w + (int64_t)(c + 1) * chunk_floats(G.l2), last ? (more ? bytes1 : 0) : bytes2);
+            af.commit(x, lane_base, kb, second);
+        };
+        for (int c = 0; c < G.l2.nch; c += 2) {
+            const int cnt = min(2, G.l2.nch - c), left = G.l2.nch - c - cnt;
+            fill2(c, false);
+            if (cnt == 2) fill2(c + 1, true);
+            const int kc0 = min(kKC, G.l2.K8 - c * kKC), kc1 = cnt == 2 ? min(kKC, G.l2.K8 - (c + 1) * kKC) : 0;
+            tc_mma_round<true>(x, r16(G.H2), kc0, colG2, c != 0, left > 0 ? G.l2.w + (int64_t)(c + 2) * chunk_floats(G.l2) : G.l1.w,
+                               left > 0 ? min(2, left) * bytes2 : (more ? min(2, G.l1.nch) * bytes1 : 0), NoMid(), Dual{cnt == 2 ? kDualK : kSingle, kc1, 0});
         }
         // ---- ReLU, Linear(H/2, 1), sigmoid gate (:379-386)
         float g_ = 0.f;
@@ -1092,7 +1102,7 @@ int tc_gate_launch(const tm_gate_desc &d, const float *d_blob, int64_t n_events,
                    const float *edge_feat, int64_t n_edge_rows, float *out, int device, cudaStream_t st) {
     const GateLayout G = make_gate_layout(d);
     if (G.H != 64 || G.Ed < 1 || G.D < 1 || G.D > 256) { set_error("tm_edge_importance: gate needs hid_dim 64 and time_dim in [1,256]"); return TM_ERR_UNSUPPORTED; }
-    const int64_t bb = std::max(chunk_floats(G.l1), chunk_floats(G.l2)) * 4;
+    const int64_t bb = std::max(std::min(2, G.l1.nch) * chunk_floats(G.l1), std::min(2, G.l2.nch) * chunk_floats(G.l2)) * 4;       // chunks arrive in pairs
     const size_t need = (size_t)bb + (size_t)G.n_cst * 4 + 152 * 8;
     static bool attr_set[64] = {false};
     if (device >= 0 && device < 64 && !attr_set[device]) {
