@@ -345,7 +345,7 @@ struct TcArgs {
     int b_bytes;                             // bytes of the weight-chunk buffer
     int stage_off;                           // byte offset of the node-feature staging (src rows, then tgt rows); 0: gather with plain loads
     int stage_edge_off;                      // byte offset of the edge-feature staging; 0: gather with plain loads
-    int dual;                                // event passes with two A buffers: lin_event chunks in pairs, both orientations of MLP.0 per round
+    int dual;                                // two A buffers: bit 0 both orientations of MLP.0 per round + Q / R chunk pairs, bit 1 lin_event chunk pairs
     long long *dbg;                          // TEMPME_TC_TIMING: 128 x 5 clock stamps of CTA 0
 };
 
@@ -398,12 +398,12 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     AFill<CW, TS> af;
     const int H = L.H, H2 = 2 * L.H, D = L.D, Ed = L.Ed, nG = L.g0.nch, nchS = L.sp.nch;
     const int colZ = 0, colE = (nG == 1 && L.D16 <= H) ? H : H2;
-    const bool dq = a.dual != 0;                           // Q and R rounds in pairs: second A buffer = columns [0, 64) (U is dead by then)
+    const bool dq = a.dual != 0, de = (a.dual & 2) != 0;   // dual rounds (bit 0: MLP.0 orientations, Q, R; bit 1: lin_event chunk pairs).  Q and R rounds in pairs: second A buffer = columns [0, 64) (U is dead by then)
     const int colU = 0, colY = H2, colM0 = dq ? H : 0, colM1 = dq ? 0 : H2;
     const int64_t n_m = a.n_motifs, n_tiles = (n_m + 127) / 128;
     const int bytes_e = (int)chunk_floats(L.evt) * 4, bytes_g = (int)chunk_floats(L.g0) * 4;
     const int bytes_sp = (int)chunk_floats(L.sp) * 4, bytes_q = (int)chunk_floats(L.q) * 4, bytes_r = (int)chunk_floats(L.r) * 4, bytes_m3 = (int)chunk_floats(L.m3) * 4;
-    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, L.evt.w, min(a.dual ? 2 : 1, L.evt.nch) * bytes_e);
+    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, L.evt.w, min(de ? 2 : 1, L.evt.nch) * bytes_e);
     const bool ed_vec = (Ed & 3) == 0, d_vec = (D & 3) == 0;
     float *Fs = a.F + (int64_t)blockIdx.x * 12 * kSlabFloats;           // this CTA's h slabs: [position][column chunk][piece k/4][128 rows][4]
     const float *F0 = Fs, *F1 = Fs + 4 * kSlabFloats, *F2 = Fs + 8 * kSlabFloats;
@@ -515,7 +515,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                     if (kb < kcols) af.commit(x, lane_base, kb, second);
                 }
             };
-            const int cpr = a.dual ? 2 : 1;                         // lin_event chunks per round
+            const int cpr = de ? 2 : 1;                             // lin_event chunks per round
             const int nE_next = pos == 1 ? L.nch_edge : L.evt.nch;  // chunks of the next pass (position 2 skips the pure TimeEncode chunks)
             for (int c = 0; c < nE; c += cpr) {
                 const int cnt = min(cpr, nE - c);
@@ -757,7 +757,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             }
             const bool last = c + 1 == L.m3.nch;
             // the staging overlaps the weight buffer of the larger motif-round chunks; MLP.3's are small and R's MMAs have completed
-            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? min(a.dual ? 2 : 1, L.evt.nch) * bytes_e : 0) : bytes_m3,
+            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? min(de ? 2 : 1, L.evt.nch) * bytes_e : 0) : bytes_m3,
                              [&]() { if (c == 0 && more) { request_nodes(pcur, 0); request_edges(pcur, 0); } });
         }
         // ---- MLP.5 + sigmoid (:199-200)
@@ -835,13 +835,15 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     uint32_t cols = 32;
     // event passes with two A buffers (pairs of lin_event chunks, both MLP.0 orientations per round): TS mode, at most the first
     // lin_event chunk holds edge columns (one staged edge chunk per round)
-    const bool dual = ts && L.nch_edge <= 1 && !getenv("TEMPME_TC_NO_DUAL");
+    const bool dual = ts && !getenv("TEMPME_TC_NO_DUAL");
+    const bool dual_e = dual && L.nch_edge <= 1;             // pairs of lin_event chunks: one staged edge chunk per round at most
     // motif rounds: U | Y + one A buffer; event passes: Zs | Zt (| E) + one or two A buffers (the A buffers are the top columns)
     while ((int)cols < std::max(3 * H + (ts ? 2 * kKC : 0), (alias_e ? 2 * H : 2 * H + L.D16) + (ts ? (dual ? 4 : 2) * kKC : 0))) cols <<= 1;
     if (cols > 512) { set_error("tc_encode_score: node_dim too large for the TMEM layout"); return TM_ERR_UNSUPPORTED; }
     int64_t bb = 0;
     for (const TcLin *l : {&L.evt, &L.g0, &L.sp, &L.q, &L.r, &L.m3}) bb = std::max(bb, chunk_floats(*l) * 4);
-    if (dual) bb = std::max(bb, (int64_t)std::min(2, L.evt.nch) * chunk_floats(L.evt) * 4);          // lin_event chunks arrive in pairs
+    if (dual_e) bb = std::max(bb, (int64_t)std::min(2, L.evt.nch) * chunk_floats(L.evt) * 4);        // lin_event chunks arrive in pairs
+    if (dual) bb = std::max(bb, 2 * std::max(chunk_floats(L.q), chunk_floats(L.r)) * 4);             // so do Q's and R's
     // node-feature rows are gathered by bulk TMA into a staging area that may overlap the tail of the weight buffer: rows
     // are in flight only while lin_event / MLP.0 / MLP.3 chunks are being loaded, so it starts behind the largest of those
     CUtensorMap tm_node, tm_edge;
@@ -849,7 +851,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     const bool stage_nodes = L.D % 4 == 0 && ((uintptr_t)node_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && make_gather_map(&tm_node, node_feat, n_node_rows, L.D, 1);
     const bool stage_edges = L.Ed % 4 == 0 && ((uintptr_t)edge_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && !getenv("TEMPME_TC_NO_EDGE_STAGING") &&
                              make_gather_map(&tm_edge, edge_feat, n_edge_rows, L.Ed, 1);
-    const int64_t stage_rel = (std::max(std::max((dual ? std::min(2, L.evt.nch) : 1) * chunk_floats(L.evt), chunk_floats(L.g0)), chunk_floats(L.m3)) * 4 + 1023) & ~(int64_t)1023;
+    const int64_t stage_rel = (std::max(std::max((dual_e ? std::min(2, L.evt.nch) : 1) * chunk_floats(L.evt), chunk_floats(L.g0)), chunk_floats(L.m3)) * 4 + 1023) & ~(int64_t)1023;
     const int64_t stage_edge_rel = stage_rel + (stage_nodes ? (int64_t)2 * kStageTable * 4 : 0);
     bb = std::max(bb, stage_edge_rel + (stage_edges ? (int64_t)kStageTable * 4 : 0));
     const size_t a_bytes = ts ? 0 : (size_t)2 * kATile;
@@ -885,7 +887,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.F = F; a.scores = scores; a.tmem_cols = cols; a.b_bytes = (int)bb; a.dbg = nullptr;
     a.stage_off = stage_nodes ? (int)(a_bytes + stage_rel) : 0;
     a.stage_edge_off = stage_edges ? (int)(a_bytes + stage_edge_rel) : 0;
-    a.dual = dual;
+    a.dual = (dual ? 1 : 0) | (dual_e ? 2 : 0);
     static long long *dbg_buf = nullptr;
 #ifdef TM_TC_TIMING
     const char *tim_env = getenv("TEMPME_TC_TIMING");          // diagnostic: per-round clock stamps of CTA 0
