@@ -86,6 +86,49 @@ class MotifPipeline:
             self._hb_q = Q
         return self._pin_i32, self._pin_f64, self._pin_out
 
+    # ------------------------------------------------------------------ asynchronous host API (two batches in flight)
+    def _slots(self, Q):
+        if getattr(self, "_sl_q", None) != Q:
+            dev = self.device
+            self._sl = [dict(pin_i=torch.empty((2, 3 * Q), dtype=torch.int32).pin_memory(), pin_t=torch.empty(3 * Q, dtype=torch.float64).pin_memory(),
+                             pin_out=torch.empty((3, Q, self.W), dtype=torch.float32).pin_memory(),
+                             dev_i=torch.empty((2, 3 * Q), dtype=torch.int32, device=dev), dev_t=torch.empty(3 * Q, dtype=torch.float64, device=dev),
+                             dev_out=torch.empty((3, Q, self.W), dtype=torch.float32, device=dev),
+                             ready=torch.cuda.Event(), copied=torch.cuda.Event()) for _ in range(2)]
+            self._sl_next = 0
+            self._sl_q = Q
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        return self._sl
+
+    def submit_host(self, src, dst, fake, ts, eidx, row_offset=0):
+        """Asynchronous ``run_host``: stages the queries into one of two pinned slots, enqueues H2D + the device pipeline on the
+        current stream and the D2H of the scores on a copy stream, and returns a ticket for ``collect``.  At most two batches are in
+        flight; collect batch k-1 before submitting batch k+1."""
+        Q = len(src)
+        nb, g = self._layout(Q)
+        sl = self._slots(Q)[self._sl_next]
+        ticket = self._sl_next
+        self._sl_next ^= 1
+        r = sl["pin_i"][0].numpy().reshape(nb, 3, g); e = sl["pin_i"][1].numpy().reshape(nb, 3, g); c = sl["pin_t"].numpy().reshape(nb, 3, g)
+        r[:, 0] = np.asarray(src).reshape(nb, g); r[:, 1] = np.asarray(dst).reshape(nb, g); r[:, 2] = np.asarray(fake).reshape(nb, g)
+        e[:, 0] = e[:, 1] = np.asarray(eidx).reshape(nb, g); e[:, 2] = TM_EIDX_NONE                  # bgd roots are cut by time
+        c[:] = np.asarray(ts, np.float64).reshape(nb, 1, g)
+        sl["dev_i"].copy_(sl["pin_i"], non_blocking=True)
+        sl["dev_t"].copy_(sl["pin_t"], non_blocking=True)
+        sl["dev_out"].copy_(self.unstage_scores(self.run_device(sl["dev_i"][0], sl["dev_i"][1], sl["dev_t"], row_offset), Q))   # slot-owned: no allocator traffic
+        sl["ready"].record()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(sl["ready"])
+            sl["pin_out"].copy_(sl["dev_out"], non_blocking=True)
+            sl["copied"].record()
+        return ticket
+
+    def collect(self, ticket):
+        """Scores [3, Q, W] of a submitted batch (a view of the slot's pinned buffer, valid until the slot is submitted again)."""
+        sl = self._sl[ticket]
+        sl["copied"].synchronize()
+        return sl["pin_out"].numpy()
+
     def run_host(self, src, dst, fake, ts, eidx, row_offset=0):
         """End-to-end call with host buffers: H2D of the queries, the device pipeline, D2H of the scores.
         Returns a [3, Q, W] float32 array backed by an internal pinned buffer (valid until the next run_host call)."""

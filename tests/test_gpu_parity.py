@@ -401,6 +401,15 @@ def test_pipeline_matches_piecewise(tm, orc):
                 ref = m(walks, ts[q][sl], orc.edge_identity(oe))
             np.testing.assert_allclose(scores[k, sl], ref[..., 0].cpu().numpy(), rtol=1e-6, atol=0)
     assert (pipe.hist_null.cpu().numpy() == hist).all()
+    # asynchronous host API: two batches in flight give the scores of run_host
+    q2 = np.arange(31000, 31200)
+    ref1, ref2 = pipe.run_host(src[q], dst[q], fake, ts[q], eidx[q]).copy(), pipe.run_host(src[q2], dst[q2], fake, ts[q2], eidx[q2]).copy()
+    t1 = pipe.submit_host(src[q], dst[q], fake, ts[q], eidx[q])
+    t2 = pipe.submit_host(src[q2], dst[q2], fake, ts[q2], eidx[q2])
+    a1 = pipe.collect(t1).copy()
+    t3 = pipe.submit_host(src[q], dst[q], fake, ts[q], eidx[q])
+    a2, a3 = pipe.collect(t2).copy(), pipe.collect(t3).copy()
+    assert (a1 == ref1).all() and (a2 == ref2).all() and (a3 == ref1).all()
 
 
 # ---------------------------------------------------------------------------------------------
