@@ -345,6 +345,7 @@ struct TcArgs {
     int b_bytes;                             // bytes of the weight-chunk buffer
     int stage_off;                           // byte offset of the node-feature staging (src rows, then tgt rows); 0: gather with plain loads
     int stage_edge_off;                      // byte offset of the edge-feature staging; 0: gather with plain loads
+    unsigned long long *tile_counter;        // dynamic tile scheduler: CTA b takes tile b first, then gridDim.x + atomicAdd(counter, 1)
     int dual;                                // two A buffers: bit 0 both orientations of MLP.0 per round + Q / R chunk pairs, bit 1 lin_event chunk pairs
     long long *dbg;                          // TEMPME_TC_TIMING: 128 x 5 clock stamps of CTA 0
 };
@@ -380,6 +381,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     __shared__ __align__(8) uint64_t bars[4];              // [0] MMAs done, [1] weight chunk landed, [2] staged node-feature rows landed, [3] staged edge-feature rows landed
     __shared__ uint32_t tmem_slot;
     __shared__ float part[kParts][3][128];
+    __shared__ long long s_next_tile;
     const int t = threadIdx.x, warp = t >> 5, row = t & 127, prt = t >> 7, kb = CW * prt;
     TcCtx x;
     x.a = smem; x.a_s = tc::smem_u32(smem); x.b_s = x.a_s + (TS ? 0 : 2 * kATile); x.bars = bars; x.mma_phase = 0; x.b_phase = 0; x.blob = blob;
@@ -460,10 +462,12 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         if (blockIdx.x < n_tiles) { request_nodes(pcur, 0); request_edges(pcur, 0); }
     }
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < n_tiles;) {
         const int64_t gm_ = tile * 128 + row;
-        const bool live = gm_ < n_m, more = tile + gridDim.x < n_tiles;
+        const bool live = gm_ < n_m;
         const int64_t gm = live ? gm_ : 0;
+        // the CTA's next tile (dynamic: SMs that run a single CTA, or faster ones, take more tiles); read after the event passes' barriers
+        if (t == 0) s_next_tile = (long long)gridDim.x + (long long)atomicAdd(a.tile_counter, 1ull);
         // =========================== event passes ===========================
         x.a_col2 = x.a_col - 2 * kKC;
 #pragma unroll 1
@@ -714,8 +718,10 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             }
         }
         // ---- M0 = R relu(Y + cy)   (attention.MLP.3 and MLP.0 folded); the next tile's first-pass indices start to arrive
+        const int64_t next_tile = s_next_tile;
+        const bool more = next_tile < n_tiles;
         {
-            const int64_t gn = (tile + gridDim.x) * 128 + row;
+            const int64_t gn = next_tile * 128 + row;
             const bool lv = more && gn < n_m;
             pcur = load_idx(lv ? gn : 0, lv, 0);
         }
@@ -778,6 +784,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             for (int q = 0; q < kParts; ++q) zz += part[q][0][row];
             a.scores[gm] = 1.f / (1.f + expf(-zz));
         }
+        tile = next_tile;
         // the next write to part[] comes after the barriers of the next tile's rounds
     }
     tc::fence_before_sync();
@@ -900,8 +907,9 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         a.dbg = dbg_buf;
     }
     const int64_t tiles = (a.n_motifs + 127) / 128, cap = (int64_t)sms * ctas;
-    const int64_t per_cta = (tiles + cap - 1) / cap;
-    const unsigned grid = (unsigned)((tiles + per_cta - 1) / per_cta);          // every CTA gets the same number of tiles (+-1); grid <= 2 * sms
+    const unsigned grid = (unsigned)std::min(tiles, cap);
+    a.tile_counter = reinterpret_cast<unsigned long long *>(F + (int64_t)grid * 12 * kSlabFloats);          // behind the h scratch (the workspace holds twice as much)
+    TM_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), st));
     if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] score kernel: %u CTAs (%d per SM), smem %zu B (needs %zu), %u TMEM columns, %lld tiles\n", grid, ctas, smem, need, cols, (long long)tiles);
     cudaEvent_t *pe = nullptr;
     if (g_prof && g_prof_used + 2 <= g_prof_ev.size()) {        // pool is created by tm_encoder_profile(1); when exhausted, stop recording
