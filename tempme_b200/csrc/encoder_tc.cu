@@ -1,5 +1,5 @@
-// tcgen05 (5th-gen tensor core) scorer: TempME.forward (reference models/explainer.py:174-201) as two kernels of
-// 3xTF32 GEMM rounds with TMEM accumulators.
+// tcgen05 (5th-gen tensor core) scorer: TempME.forward (reference models/explainer.py:174-201) as one persistent kernel of
+// 3xTF32 GEMM rounds with TMEM accumulators (and the dependency gate of retrieve_edge_imp_node at the end of the file).
 //
 // Algebra.  Between event_conv.MLP.0's ReLU and attention.MLP.0's ReLU the reference applies only linear maps and the
 // two softmax weights, and between attention.MLP.0's ReLU and MLP.0's ReLU only linear maps and a one-hot, so those
@@ -9,16 +9,18 @@
 //     s_k  = Wp . Wq_k = h_k . (S h_2 + cu) + (d . h_2 + e)      S = A2^T A1, cu = A2^T c1, d = A1^T c2, e = c1 . c2
 //     y    = relu(attention.MLP.0(f_2 + sum_k alpha_k Wq_k)) = relu(P h_2 + Q (alpha_0 h_0 + alpha_1 h_1) + cy)   (:841-843)
 //     m0   = relu(MLP.0([attention.MLP.3(y) | onehot(cat)])) = relu(R y + cm[cat])                                (:196-200)
-// which halves the multiply-adds per motif and takes the per-tile GEMM rounds from 34 to 17 (D = Ed = 32).  The
-// folded weights are rounded to fp32 once; scores agree with the unfolded fp32 evaluation to ~2e-7 relative.
+// which halves the multiply-adds per motif and, with the chunk pairs below, takes the per-tile GEMM rounds from 34 to 16
+// (D = Ed = 32).  The folded weights are rounded to fp32 once; scores agree with the unfolded fp32 evaluation to ~2e-7 relative.
 //
 // One persistent kernel (score_tc_kernel) takes tiles of 128 motifs through three event passes (lin_event over
 // [edge features | TimeEncode]; the three edge-identity columns are added on the CUDA cores; position-2 rows have
 // dt = 0, so their TimeEncode chunks collapse into a bias; event_conv.MLP.0 + ReLU for the two orientations) and the
 // motif rounds ([S; P] h_2 -> scores -> temporal weights, softmax -> + Q mix -> R -> MLP.3 -> MLP.5 + sigmoid).
-// Thread (row, part) owns TMEM lane `row` and CW of the 32 columns of every K chunk (CW = 8: 512 threads): it reads the previous
-// accumulator row with tcgen05.ld, applies bias / ReLU / mixing in fp32 registers, splits into tf32 hi + lo and stores
-// the K-major operand tile in shared memory; weights arrive pre-split and pre-tiled by 1-D bulk TMA.
+// Thread (row, part) owns TMEM lane `row` and CW of the 32 columns of every K chunk (CW = 16: 256 threads): it reads the previous
+// accumulator row with tcgen05.ld, applies bias / ReLU / mixing in fp32 registers, splits into tf32 hi + lo and writes its columns of
+// the A operand into TMEM (tcgen05.st; TS-mode MMA) -- or, with TEMPME_TC_A=smem, the K-major operand tile in shared memory.  Weights
+// arrive pre-split and pre-tiled by 1-D bulk TMA; feature rows by tensor-map TMA (tile::gather4) one pass ahead.  Dual rounds use a
+// second A buffer: two K chunks, or two row blocks sharing a chunk, per barrier.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -361,9 +363,11 @@ __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cas
 //   motif rounds: [S; P] h_2 -> scores -> temporal weights, softmax -> + Q mix -> R -> MLP.3 -> MLP.5 + sigmoid.
 // While one CTA of the SM is in its (CUDA-core heavy) event passes the other is usually in its (tensor heavy)
 // motif rounds.
-// TMEM (256 columns): event passes Zs [0,H)  Zt [H,2H)  E [2H, 2H + D16), or E aliasing Zt when MLP.0 has a single
-// K chunk (D <= 32): E has then been read completely before the MMA that writes Zt is issued.  Motif rounds:
-// U [0,2H) | Y [2H,3H) (one N = 3H accumulator of the [S; P] rounds), later M0 [0,M16) and M1 [2H,3H).
+// TMEM (256 columns at D <= 32): event passes Zs [0,H)  Zt [H,2H)  E [2H, 2H + D16), or E aliasing Zt when MLP.0 has a single
+// K chunk (D <= 32): E has then been read completely before the MMAs that write Zt are issued; A2 | A = the top 128 columns.
+// Motif rounds: U [0,2H) | Y [2H,3H) (one N = 3H accumulator of the [S; P] rounds) | A; then A2 = [0,64) over the dead U,
+// M0 [H, H + M16) and M1 [0,H) (single-buffer mode: M0 [0,M16), M1 [2H,3H)).
+// Tiles are handed out dynamically (CTA b starts with tile b, then takes gridDim.x + atomicAdd(counter)).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 
