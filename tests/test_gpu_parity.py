@@ -468,3 +468,39 @@ def test_edge_importance_vs_oracle_larger(tm, orc):
     i0, i1 = m.retrieve_edge_imp_node((h_n, h_e, None), scores, walks, training=False)
     np.testing.assert_allclose(i0.cpu().numpy(), r0, rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(i1.cpu().numpy(), r1, rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+# full BASELINE size (cfg2: 16,000 query events = 1.44 M motifs per step): size-independent properties
+# ---------------------------------------------------------------------------------------------
+def test_full_size_cfg2_properties(tm, monkeypatch):
+    """At the bench size the oracle is too slow, so check properties: (1) the tensor-core scorer (host-folded chain, TMEM
+    operands, dual rounds, gather4 staging, dynamic tiles) agrees with the layer-by-layer fp32 CUDA-core scorer of the same library
+    within 1e-5 on every motif; (2) scores do not depend on how the query batches are split into calls (draws are keyed by the
+    global row); (3) the class histogram counts every motif once; (4) repeated calls are bit-identical."""
+    from tempme_b200 import synth
+    from bench import random_params
+    g = synth.make_graph("cfg2", 1.0)
+    sh = synth.SHAPES["cfg2"]
+    f = tm.NeighborFinder.from_events(g["n_nodes"], g["src"], g["dst"], g["eidx"], g["ts"], device="cuda:0", seed=3)
+    nfeat, efeat = synth.make_features("cfg2", g["n_nodes"], len(g["src"]))
+    m = tm.TempME(_Base(nfeat.numpy(), efeat.numpy()), "tgn", "cfg2", 40, 64, device="cuda", null_model={}).cuda().eval()
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in random_params(sh["D"], sh["Ed"]).items()}, strict=False)
+    pipe = tm.MotifPipeline(f, m, sh["n"], sh["N2"], group=100, seed=7)
+    Q = 16000
+    q = synth.make_queries(g, np.random.default_rng(5), Q)
+    dq = pipe.stage_queries(*q)
+    s_tc = pipe.run_device(*dq).clone()
+    assert int(pipe.hist_null.sum().item()) == 3 * Q * pipe.W == int(pipe.hist_prep.sum().item())
+    assert torch.isfinite(s_tc).all() and float(s_tc.min()) > 0 and float(s_tc.max()) < 1
+    assert torch.equal(pipe.run_device(*dq), s_tc)                       # (4)
+    monkeypatch.setenv("TEMPME_ENCODER", "ffma")                          # (1) unfolded fp32 FFMA kernel, same inputs
+    s_ff = pipe.run_device(*dq).clone()
+    monkeypatch.delenv("TEMPME_ENCODER")
+    rel = ((s_tc - s_ff).abs() / s_ff.abs()).max().item()
+    assert rel < 1e-5, rel
+    # (2) the same 16,000 events as two calls of 8,000 (whole reference batches), global row offsets
+    half = 3 * (Q // 2)
+    a = pipe.run_device(dq[0][:half], dq[1][:half], dq[2][:half], row_offset=0)
+    b = pipe.run_device(dq[0][half:], dq[1][half:], dq[2][half:], row_offset=half)
+    assert torch.equal(torch.cat([a, b]), s_tc)
