@@ -170,7 +170,7 @@ int tm_encode_score(const tm_encoder_desc *desc, const float *d_blob, int64_t B,
                     const float *d_node_feat, int64_t n_node_rows, const float *d_edge_feat, int64_t n_edge_rows,
                     float *d_workspace, float *d_scores, int device, tm_stream stream);
 
-/* Per-kernel timing of the tensor-core scorer (CUDA events around every launch of its two kernels on the caller's
+/* Kernel timing of the tensor-core scorer (CUDA events around its launch on the caller's
  * stream).  tm_encoder_profile(1) starts collecting; tm_encoder_profile_read returns in h_event_ms the accumulated
  * milliseconds of the scorer kernel since the last read (synchronises on the recorded events); h_motif_ms is 0 since the
  * event-level and the motif-level phases run as one kernel. */

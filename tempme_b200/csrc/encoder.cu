@@ -272,9 +272,9 @@ extern "C" int64_t tm_encoder_blob_floats(const tm_encoder_desc *desc) { return 
 
 extern "C" int64_t tm_encoder_workspace_floats(const tm_encoder_desc *desc, int64_t B, int64_t W, int64_t group) {
     if (!desc || B < 0 || group <= 0) return -1;
-    const int64_t n_std = (std::max<int64_t>(32, (B + group - 1) / group) + 31) & ~(int64_t)31;   // per-batch std, then the F slab (16-byte aligned)
+    const int64_t n_std = (std::max<int64_t>(32, (B + group - 1) / group) + 31) & ~(int64_t)31;   // per-batch std, then the scorer's scratch (16-byte aligned)
     const int64_t slab = std::min<int64_t>(tc_slab_motifs(), (std::max<int64_t>(B * W, 1) + 127) / 128 * 128);   // whole tiles of 128 motifs
-    return n_std + 2 * slab * 3 * 2 * desc->hid_dim;                         // two slabs in flight (alternating internal streams)
+    return n_std + 2 * slab * 3 * 2 * desc->hid_dim;                         // h scratch of the resident CTAs (192 KB each) + the tile counter behind it
 }
 
 extern "C" int tm_encoder_pack(const tm_encoder_desc *desc, const tm_encoder_params *p, float *h_blob) {
