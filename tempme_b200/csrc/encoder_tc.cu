@@ -334,8 +334,7 @@ __device__ __forceinline__ void tma_gather4(void *dst_smem, const CUtensorMap *m
 }
 
 struct TcArgs {
-    int64_t n_motifs, W, group, m_begin;     // this launch scores motifs [m_begin, m_begin + slab)
-    int64_t slab;
+    int64_t n_motifs, W, group;              // B * W motifs; W walks per root; roots per reference batch (index of std_)
     const int32_t *nodes, *eidx;
     const float *t;
     const uint8_t *cat;
@@ -893,7 +892,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     const size_t smem = std::max(need, std::min((size_t)228 * 1024 / (ctas + 1), (size_t)227 * 1024 - 8192));
 
     TcArgs a;
-    a.n_motifs = B * W; a.W = W; a.group = group; a.m_begin = 0; a.slab = 0; a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
+    a.n_motifs = B * W; a.W = W; a.group = group; a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
     a.eid = eid; a.node_feat = node_feat; a.edge_feat = edge_feat; a.std_ = std_; a.n_node_rows = n_node_rows; a.n_edge_rows = n_edge_rows;
     a.F = F; a.scores = scores; a.tmem_cols = cols; a.b_bytes = (int)bb; a.dbg = nullptr;
     a.stage_off = stage_nodes ? (int)(a_bytes + stage_rel) : 0;
