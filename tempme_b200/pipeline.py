@@ -68,6 +68,26 @@ class MotifPipeline:
         mark("encode")
         return (scores, (nodes, eidx, t, cat, eid)) if want_walks else scores
 
+    def explain_device(self, roots, e, cut64, row_offset=0):
+        """The explanation pass of temp_exp_main.py's evaluation for a staged batch, without leaving the GPU: 2-hop subgraph
+        (find_k_hop, graph.py:233-262), walks on its first hop, scores, and TempME.retrieve_edge_imp_node (eval) on them.
+        Returns (scores [3Q, W], edge_imp_0 [3Q, n], edge_imp_1 [3Q, n^2], subgraph records) in the staged row order."""
+        f, n, N2 = self.finder, self.n, self.N2
+        R = roots.numel()
+        g = self.group if R >= 3 * self.group else R // 3
+        # find_k_hop(2): hop 0 as in run_device (e_idx window for src / tgt roots, time cut for the bgd roots), hop 1 by e_idx (graph.py:247-250)
+        h0 = f.sample_hop_device(roots, cut64, n, e, seed=self.seed, stage=0, row_offset=row_offset)
+        h1 = f.sample_hop_device(h0[0].reshape(-1), None, n, h0[1].reshape(-1), seed=self.seed, stage=1, row_offset=row_offset * n)
+        sub = ([h0[0], h1[0].view(R, n * n)], [h0[1], h1[1].view(R, n * n)], [h0[2], h1[2].view(R, n * n)])
+        nodes, eidx, t, _, cat = f.find_k_walks_device(n, roots, N2, ([sub[0][0]], [sub[1][0]], [sub[2][0]]), seed=self.seed + 1,
+                                                       row_offset=row_offset, want_anony=False, want_cat=True,
+                                                       hist_null=self.hist_null, hist_prep=self.hist_prep, scanned=self.scanned)
+        eid = edge_identity_device(eidx)
+        scores = self.explainer.score_device(nodes, eidx, t, cat, cut64.to(torch.float32), eid, group=max(g, 1))
+        imp0, imp1 = self.explainer.edge_importance_device(scores, eidx, t, sub[0][0].view(R, n), sub[1][0].view(R, n),
+                                                           sub[0][1].view(R, n * n), sub[1][1].view(R, n * n))
+        return scores, imp0, imp1, sub
+
     def unstage_scores(self, scores, Q):
         """[3Q, W] in batch-major row order -> [3, Q, W] (src | tgt | bgd)."""
         nb, g = self._layout(Q)

@@ -504,3 +504,31 @@ def test_full_size_cfg2_properties(tm, monkeypatch):
     a = pipe.run_device(dq[0][:half], dq[1][:half], dq[2][:half], row_offset=0)
     b = pipe.run_device(dq[0][half:], dq[1][half:], dq[2][half:], row_offset=half)
     assert torch.equal(torch.cat([a, b]), s_tc)
+
+
+def test_pipeline_explain_matches_oracle(tm, orc):
+    """MotifPipeline.explain_device (2-hop subgraph + walks + scores + edge importance on the GPU) == the oracle's pieces."""
+    from oracle import encoder as enc
+    src, dst, eidx, ts = synth_graph(11, 120, 20000, 10 ** 7)
+    f = tm.NeighborFinder.from_events(120, src, dst, eidx, ts)
+    rng = np.random.default_rng(2)
+    nfeat = rng.standard_normal((120, 32)).astype(np.float32); efeat = rng.standard_normal((20001, 32)).astype(np.float32)
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, 64, device="cuda", null_model={}).cuda().eval()
+    p = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    q = np.arange(15000, 15100)
+    fake = rng.integers(1, 120, len(q))
+    n = 8
+    pipe = tm.MotifPipeline(f, m, n, 1, group=100, seed=17)
+    roots, e, cut64 = pipe.stage_queries(src[q], dst[q], fake, ts[q], eidx[q])
+    scores, imp0, imp1, sub = pipe.explain_device(roots, e, cut64)
+    scores, imp0, imp1 = scores.cpu().numpy(), imp0.cpu().numpy(), imp1.cpu().numpy()
+    og = orc.OracleGraph.from_events(120, src, dst, eidx, ts)
+    for k, (rr, ee) in enumerate(((src[q], eidx[q]), (dst[q], eidx[q]), (fake, None))):
+        off = k * 100
+        osub = og.find_k_hop(2, rr, ts[q], n, ee, seed=17, row_offset=off)
+        on, oe, ot, oa = og.sample_walks(rr, osub[0][0], osub[1][0], osub[2][0], 1, seed=18, row_offset=off)
+        sl = slice(off, off + 100)
+        assert (sub[0][1][sl].cpu().numpy() == osub[0][1]).all() and (sub[1][1][sl].cpu().numpy() == osub[1][1]).all()
+        r0, r1 = enc.edge_importance(p, efeat, ([osub[0][0], osub[0][1]], [osub[1][0], osub[1][1]], None), scores[sl][..., None], (None, oe, ot, None, None))
+        np.testing.assert_allclose(imp0[sl], r0, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(imp1[sl], r1, rtol=1e-5, atol=1e-7)
