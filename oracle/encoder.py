@@ -61,7 +61,7 @@ def temporal_attention(feat, time_idx, cut_time, p, dt, use_temporal=True):
 
 
 def forward(p, node_feat, edge_feat, walks, cut_time, edge_identify, dtype=np.float32,
-            use_temporal=True, if_cat=True, return_hidden=False):
+            use_temporal=True, if_cat=True, return_hidden=False, attention_only=False):
     """TempME.forward, explainer.py:174-201.
 
     walks = (node_idx [B,W,6], edge_idx [B,W,3], time_idx [B,W,3], cat_feat [B,W,1] or [B,W], _)
@@ -85,6 +85,8 @@ def forward(p, node_feat, edge_feat, walks, cut_time, edge_identify, dtype=np.fl
     up_tgt = event_gcn(ev, tgtf, srcf, p, dt)                                    # :184
     feat = np.concatenate([up_src, up_tgt], axis=-1)                             # :185
     h = temporal_attention(feat, t32.astype(dt), cut32.astype(dt), p, dt, use_temporal)   # :190-193
+    if attention_only:
+        return h                                                                 # [B, W, H] (enhance_predict_walks :240-243)
     if if_cat:
         cat = np.asarray(cat_feat).astype(np.int64).reshape(B, W)
         onehot = np.eye(12, dtype=dt)[cat]                                       # :308-315
@@ -137,3 +139,42 @@ def edge_importance(p, edge_feat, subgraph, graphlet_imp, walks, use_dependency=
         imp[np.asarray(node_record[l]) == 0] = 0                                            # :400-404
         outs.append(imp.astype(dt))
     return outs[0], outs[1]
+
+
+def walk_importance(time_idx, node_idx, cut_time, node_degree, dtype=np.float32):
+    """TempME.compute_walk_importance, explainer.py:257-306: soft weights [B, W] from recency (batch-global std) and the mean degree
+    of the walk's non-padding nodes (batch-global mean / std), normalised to sum to W per root."""
+    dt = dtype
+    t = np.asarray(time_idx).astype(np.float32).astype(dt)
+    nid = np.asarray(node_idx).astype(np.int64)
+    cut = np.asarray(cut_time).astype(np.float32).astype(dt)
+    W = t.shape[1]
+    diff = np.abs(cut[:, None] - t.max(-1))                                              # :274-277
+    rec = np.exp(-diff / (dt(diff.astype(np.float64).std(ddof=1)) + dt(1e-6)) / dt(1.0))  # :281
+    valid = nid > 0
+    deg = np.where(valid, np.asarray(node_degree).astype(dt)[nid], dt(0))               # :286-291
+    avg = deg.sum(-1) / (valid.sum(-1).astype(dt) + dt(1e-6))                            # :292
+    z = (avg - dt(avg.astype(np.float64).mean())) / (dt(avg.astype(np.float64).std(ddof=1)) + dt(1e-6))
+    dw = dt(1) / (dt(1) + np.exp(-z))                                                     # :295
+    imp = dt(0.5) * rec + dt(0.5) * dw                                                    # :298
+    return (imp / (imp.sum(-1, keepdims=True) / dt(W) + dt(1e-6))).astype(dt)             # :301
+
+
+def enhance_predict_walks(p, node_feat, edge_feat, walks, cut_time, edge_identify, node_degree, dtype=np.float32, use_temporal=True, if_cat=True):
+    """TempME.enhance_predict_walks, explainer.py:222-255: attention output per walk, weighted by walk_importance, summed over the
+    walks; with if_cat the per-root class counts are appended (:307-313)."""
+    dt = dtype
+    h = forward(p, node_feat, edge_feat, walks, cut_time, edge_identify, dtype=dt, use_temporal=use_temporal, if_cat=if_cat, attention_only=True)
+    w = walk_importance(walks[2], walks[0], cut_time, node_degree, dt)
+    out = (h * w[..., None]).sum(1)                                                       # :245-249
+    if if_cat:
+        cat = np.asarray(walks[3]).astype(np.int64).reshape(h.shape[0], h.shape[1])
+        out = np.concatenate([out, np.eye(12, dtype=dt)[cat].sum(1)], axis=-1)            # :251-253
+    return out.astype(dt)
+
+
+def affinity_score(p, x1, x2, dtype=np.float32):
+    """_MergeLayer.forward, explainer.py:71-76."""
+    dt = dtype
+    x = np.concatenate([x1, x2], axis=-1).astype(dt)
+    return _lin(np.maximum(_lin(x, p, "affinity_score.fc1", dt), 0), p, "affinity_score.fc2", dt)

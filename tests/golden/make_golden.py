@@ -15,6 +15,7 @@ Fixtures:
   nullmodel.npz    utils/null_model.py pre_processing on an endpoint-shuffled copy (class histogram)
   encoder_*.npz    TempME.forward scores with the weights/features that produced them
   edgeimp_*.npz    retrieve_edge_imp_node (eval mode) on those scores: `python tests/golden/make_golden.py edgeimp`
+  enhance_*.npz    enhance_predict_walks / compute_walk_importance / enhance_predict_agg (eval): `python tests/golden/make_golden.py enhance`
 """
 from __future__ import annotations
 
@@ -314,6 +315,59 @@ def gen_edge_imp(tag, walks5, edge_identity, cut_time, subgraph, n_nodes, n_edge
     np.savez_compressed(os.path.join(HERE, f"edgeimp_{tag}.npz"), **out)
 
 
+def gen_enhance(tag, walks_src, walks_tgt, ei_src, ei_tgt, cut_time, n_nodes, n_edges, D, Ed, seed):
+    """enhance_predict_walks / enhance_predict_agg (reference models/explainer.py:203-306) in eval mode: attention output per walk,
+    soft walk-importance weights (batch-global statistics, node_degree gather), weighted sum over the walks, category counts,
+    affinity score of the (src, tgt) and (src, bgd) pairs."""
+    import torch
+    import models.explainer as rexp
+    rexp.get_null_distribution = lambda data_name: {k: 1.0 / 12 for k in range(1, 13)}
+    torch.manual_seed(seed)
+    nfeat = torch.randn(n_nodes, D); efeat = torch.randn(n_edges, Ed)
+    nfeat[0] = 0; efeat[0] = 0
+
+    class Base:
+        n_feat_th = nfeat; e_feat_th = efeat
+        node_raw_features = torch.nn.Embedding.from_pretrained(nfeat, padding_idx=0, freeze=True)
+        edge_raw_features = torch.nn.Embedding.from_pretrained(efeat, padding_idx=0, freeze=True)
+
+    m = rexp.TempME(Base(), "tgn", "uslegis_sampled", out_dim=40, hid_dim=64, device=torch.device("cpu"))
+    with torch.no_grad():
+        m.time_encoder.phase.copy_(0.1 * torch.randn(D))
+        m.node_degree = torch.randint(1, 60, (n_nodes,)).float()
+    m.eval()
+    B = walks_src[0].shape[0]
+    src_gat, tgt_gat, bgd_gat = torch.randn(B, D), torch.randn(B, D), torch.randn(B, D)
+    with torch.no_grad():
+        emb_src = m.enhance_predict_walks(walks_src, cut_time, ei_src)
+        emb_tgt = m.enhance_predict_walks(walks_tgt, cut_time, ei_tgt)
+        w_src = m.compute_walk_importance(walks_src[2], walks_src[0], cut_time)
+        pos, neg = m.enhance_predict_agg(cut_time, walks_src, walks_tgt, walks_src, (ei_src, ei_tgt, ei_src), src_gat, tgt_gat, bgd_gat)
+    sd = m.state_dict()
+    out = {"p:" + k: v.numpy() for k, v in sd.items()
+           if any(k.startswith(q + ".") for q in FWD_PARAMS) or k.startswith("time_encoder.") or k.startswith("affinity_score.")}
+    for pre, w, ei in (("src", walks_src, ei_src), ("tgt", walks_tgt, ei_tgt)):
+        out.update({f"{pre}_nodes": w[0].astype(np.int32), f"{pre}_eidx": w[1].astype(np.int32), f"{pre}_t": w[2].astype(np.float32),
+                    f"{pre}_cat": w[3].astype(np.int8), f"{pre}_ei": ei.astype(np.float32)})
+    out.update(node_feat=nfeat.numpy(), edge_feat=efeat.numpy(), node_degree=m.node_degree.numpy(), cut_time=cut_time,
+               src_gat=src_gat.numpy(), tgt_gat=tgt_gat.numpy(), bgd_gat=bgd_gat.numpy(),
+               emb_src=emb_src.numpy(), emb_tgt=emb_tgt.numpy(), w_src=w_src.numpy(), pos=pos.numpy(), neg=neg.numpy())
+    np.savez_compressed(os.path.join(HERE, f"enhance_{tag}.npz"), **out)
+
+
+def gen_enhance_all():
+    big = dict(np.load(os.path.join(HERE, "rand_bigts.npz")))
+    Bq = 12
+    ws = []
+    for pre in ("src", "tgt"):
+        wn, we, wt, wa = (big[f"{pre}_w_{k}"][:Bq] for k in ("nodes", "eidx", "t", "anony"))
+        allw = np.concatenate([x.astype(np.float64) for x in (wn, we, wt, wa)], axis=-1)
+        new = marginal(allw, allw, allw)[0]
+        ws.append(((wn.astype(np.int64), we.astype(np.int64), wt.astype(np.float64), new[:, :, 12:13].astype(np.int64), new[:, :, 13:14]),
+                   new_edge_info(we.astype(int))))
+    gen_enhance("d32", ws[0][0], ws[1][0], ws[0][1], ws[1][1], big["ts"][big["q"][:Bq]], int(big["n_nodes"]), len(big["eidx"]) + 1, 32, 32, seed=5)
+
+
 def gen_edge_imp_all():
     """Fixtures of the motif -> edge aggregation; reads the committed walk fixtures (does not regenerate them)."""
     us = dict(np.load(os.path.join(HERE, "uslegis.npz")))
@@ -340,6 +394,9 @@ def gen_edge_imp_all():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "edgeimp":
         gen_edge_imp_all()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "enhance":
+        gen_enhance_all()
         return
     gen_tie_star()
     gen_rand_small()

@@ -180,3 +180,20 @@ def test_edge_importance_oracle(golden, tag):
         i0, i1 = enc.edge_importance(p, z["edge_feat"], sub, z[f"{key}_score"], walks, use_dependency=dep)
         np.testing.assert_allclose(i0, z[f"{key}_imp0"], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(i1, z[f"{key}_imp1"], rtol=1e-5, atol=1e-7)
+
+
+def test_enhance_path_oracle(golden):
+    """oracle.encoder enhance path == the reference's compute_walk_importance / enhance_predict_walks / enhance_predict_agg (eval)."""
+    from oracle import encoder as enc
+    z = golden("enhance_d32")
+    p = {k[2:]: z[k] for k in z if k.startswith("p:")}
+    ws = {pre: (z[f"{pre}_nodes"], z[f"{pre}_eidx"], z[f"{pre}_t"], z[f"{pre}_cat"], None) for pre in ("src", "tgt")}
+    w = enc.walk_importance(ws["src"][2], ws["src"][0], z["cut_time"], z["node_degree"])
+    np.testing.assert_allclose(w, z["w_src"], rtol=1e-5, atol=1e-7)
+    emb = {pre: enc.enhance_predict_walks(p, z["node_feat"], z["edge_feat"], ws[pre], z["cut_time"], z[f"{pre}_ei"], z["node_degree"]) for pre in ws}
+    np.testing.assert_allclose(emb["src"], z["emb_src"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(emb["tgt"], z["emb_tgt"], rtol=2e-5, atol=2e-5)
+    pos = enc.affinity_score(p, np.concatenate([emb["src"], z["src_gat"]], -1), np.concatenate([emb["tgt"], z["tgt_gat"]], -1))
+    neg = enc.affinity_score(p, np.concatenate([emb["src"], z["src_gat"]], -1), np.concatenate([emb["src"], z["bgd_gat"]], -1))
+    np.testing.assert_allclose(pos, z["pos"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(neg, z["neg"], rtol=1e-4, atol=1e-4)
