@@ -170,6 +170,24 @@ int tm_encode_score(const tm_encoder_desc *desc, const float *d_blob, int64_t B,
                     const float *d_node_feat, int64_t n_node_rows, const float *d_edge_feat, int64_t n_edge_rows,
                     float *d_workspace, float *d_scores, int device, tm_stream stream);
 
+/* As tm_encode_score, and additionally d_y [B*W, hid_dim] = relu(attention.MLP.0(.)) of every walk: the input of attention.MLP.3, i.e. the
+ * attention output of TempME.enhance_predict_walks (models/explainer.py:240-243) before its last Linear. */
+int tm_encode_attention(const tm_encoder_desc *desc, const float *d_blob, int64_t B, int64_t W, int64_t group,
+                        const int32_t *d_nodes, const int32_t *d_eidx, const float *d_t, const uint8_t *d_cat,
+                        const float *d_cut_time, const float *d_edge_identity,
+                        const float *d_node_feat, int64_t n_node_rows, const float *d_edge_feat, int64_t n_edge_rows,
+                        float *d_workspace, float *d_scores, float *d_y, int device, tm_stream stream);
+
+/* ---- enhance path (models/explainer.py:222-306, eval mode).
+ * tm_walk_importance: TempME.compute_walk_importance (:257-306) -> d_weights [B,W]; the recency std and the degree mean / std run over
+ * each reference batch of `group` roots; d_node_degree [n_nodes] f32 (TempME.node_degree).
+ * tm_enhance_reduce: sum over the walks of weight * attention output (:245-249) = attention.MLP.3 applied once per root to the weighted
+ * sum of d_y, plus (d_cat != NULL) the 12 per-root class counts (:251-253, :307-313) -> d_out [B, hid_dim (+ 12)]. */
+int tm_walk_importance(int64_t B, int64_t W, int64_t group, const float *d_t, const int32_t *d_nodes, const float *d_cut_time,
+                       const float *d_node_degree, int64_t n_nodes, float *d_weights, tm_stream stream);
+int tm_enhance_reduce(int64_t B, int64_t W, int hid_dim, const float *d_y, const float *d_weights, const float *d_att_mlp3_w,
+                      const float *d_att_mlp3_b, const uint8_t *d_cat_or_null, float *d_out, tm_stream stream);
+
 /* Kernel timing of the tensor-core scorer (CUDA events around its launch on the caller's
  * stream).  tm_encoder_profile(1) starts collecting; tm_encoder_profile_read returns in h_event_ms the accumulated
  * milliseconds of the scorer kernel since the last read (synchronises on the recorded events); h_motif_ms is 0 since the

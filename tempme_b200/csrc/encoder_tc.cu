@@ -342,6 +342,7 @@ struct TcArgs {
     int64_t n_node_rows, n_edge_rows;
     float *F;                                // scratch: per CTA 12 h slabs [position][column chunk][piece k/4][128 rows][4]
     float *scores;
+    float *y_out;                            // optional [n_motifs, H]: relu(attention.MLP.0(.)), the input of attention.MLP.3 (enhance path)
     uint32_t tmem_cols;
     int b_bytes;                             // bytes of the weight-chunk buffer
     int stage_off;                           // byte offset of the node-feature staging (src rows, then tgt rows); 0: gather with plain loads
@@ -734,7 +735,9 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll
             for (int k = 0; k < CW; k += 4) {
                 const float4 bb = lds4(cstM + L.m_cy + c * kKC + kb + k);
-                af.put4(x, row, kb, k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
+                const float4 yv = make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f));
+                af.put4(x, row, kb, k, yv);
+                if (a.y_out && live) *reinterpret_cast<float4 *>(a.y_out + gm * H + c * kKC + kb + k) = yv;
             }
             af.commit(x, lane_base, kb, second);
         };
@@ -834,7 +837,7 @@ bool make_gather_map(CUtensorMap *map, const float *table, int64_t rows, int dim
 int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
                     const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
                     int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
-                    int device, cudaStream_t st) {
+                    float *y_out, int device, cudaStream_t st) {
     const TcLayout L = make_tc_layout(d);
     if (L.H != 64) { set_error("tc_encode_score: hid_dim must be 64"); return TM_ERR_UNSUPPORTED; }
     if (device < 0 || device >= 64) { set_error("tc_encode_score: device index out of range"); return TM_ERR_UNSUPPORTED; }
@@ -894,7 +897,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     TcArgs a;
     a.n_motifs = B * W; a.W = W; a.group = group; a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
     a.eid = eid; a.node_feat = node_feat; a.edge_feat = edge_feat; a.std_ = std_; a.n_node_rows = n_node_rows; a.n_edge_rows = n_edge_rows;
-    a.F = F; a.scores = scores; a.tmem_cols = cols; a.b_bytes = (int)bb; a.dbg = nullptr;
+    a.F = F; a.scores = scores; a.y_out = y_out; a.tmem_cols = cols; a.b_bytes = (int)bb; a.dbg = nullptr;
     a.stage_off = stage_nodes ? (int)(a_bytes + stage_rel) : 0;
     a.stage_edge_off = stage_edges ? (int)(a_bytes + stage_edge_rel) : 0;
     a.dual = (dual ? 1 : 0) | (dual_e ? 2 : 0);

@@ -70,6 +70,9 @@ class _MergeLayer(nn.Module):  # _MergeLayer (explainer.py:62-69)
         nn.init.xavier_normal_(self.fc2.weight)
         self.act = nn.ReLU()
 
+    def forward(self, x1, x2):  # explainer.py:71-76; one row per query event
+        return self.fc2(self.act(self.fc1(torch.cat([x1, x2], dim=-1))))
+
 
 class TempME(nn.Module):
     def __init__(self, base, base_model_type, data, out_dim, hid_dim, prior="empirical", temp=0.07,
@@ -200,6 +203,66 @@ class TempME(nn.Module):
         cut = self._t(cut_time_l, torch.float32)                          # .float(), explainer.py:816
         eid = self._t(edge_identify, torch.float32)                       # .float(), explainer.py:177
         return self.score_device(nodes, eidx, t, cat, cut, eid).view(B, W, 1)
+
+    # ------------------------------------------------------------------ enhance path (explainer.py:203-306), eval mode
+    def _walk_tensors(self, walks, cut_time_l, edge_identify):
+        node_idx, edge_idx, time_idx, cat_feat, _ = walks
+        nodes = self._t(node_idx, torch.int32); eidx = self._t(edge_idx, torch.int32); t = self._t(time_idx, torch.float32)
+        B, W = nodes.shape[0], nodes.shape[1]
+        cat = self._t(cat_feat, torch.uint8).view(B, W) if self.if_cat else None
+        return nodes, eidx, t, cat, self._t(cut_time_l, torch.float32), self._t(edge_identify, torch.float32)
+
+    def compute_walk_importance(self, time_idx, node_idx, cut_time_l, group=None):
+        """explainer.py:257-306 -> soft walk weights [B, W] (CUDA tensor); the statistics run over the call's batch (or `group` roots)."""
+        t = self._t(time_idx, torch.float32); nodes = self._t(node_idx, torch.int32); cut = self._t(cut_time_l, torch.float32)
+        B, W = t.shape[0], t.shape[1]
+        deg = self.node_degree.detach().to(self.device, torch.float32).contiguous()
+        w = torch.empty((B, W), dtype=torch.float32, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(lib().tm_walk_importance(B, W, int(group or self.batch_group or max(B, 1)), ptr(t), ptr(nodes), ptr(cut), ptr(deg), deg.shape[0], ptr(w), st),
+              "tm_walk_importance")
+        return w
+
+    def enhance_predict_walks(self, walks, cut_time_l, edge_identify):
+        """explainer.py:222-255 -> [B, hid_dim (+ 12)] CUDA tensor: the attention output of every walk (the scorer kernel with its
+        hidden-vector output), weighted by compute_walk_importance, summed over the walks; class counts appended with if_cat."""
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("tempme_b200.TempME.enhance_predict_walks is the eval-mode path")
+        nodes, eidx, t, cat, cut, eid = self._walk_tensors(walks, cut_time_l, edge_identify)
+        B, W = nodes.shape[0], nodes.shape[1]
+        group = int(self.batch_group or max(B, 1))
+        blob = self.packed_weights()
+        nf, ef = self._tables()
+        nws = lib().tm_encoder_workspace_floats(C.byref(self._desc), B, W, group)
+        if self._ws is None or self._ws.numel() < nws:
+            self._ws = torch.empty(max(nws, 1024), dtype=torch.float32, device=self.device)
+        scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
+        y = torch.empty((B, W, self.hid_dim), dtype=torch.float32, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(lib().tm_encode_attention(C.byref(self._desc), ptr(blob), B, W, group, ptr(nodes), ptr(eidx), ptr(t), ptr(cat), ptr(cut), ptr(eid),
+                                        ptr(nf), nf.shape[0], ptr(ef), ef.shape[0], ptr(self._ws), ptr(scores), ptr(y), self.device.index, st),
+              "tm_encode_attention")
+        w = self.compute_walk_importance(t, nodes, cut, group=group)
+        a3 = self.attention.MLP[3] if self.use_temporal_guidance else self.attention.MLP[2]
+        a3w = a3.weight.detach().to(self.device, torch.float32).contiguous(); a3b = a3.bias.detach().to(self.device, torch.float32).contiguous()
+        out = torch.empty((B, self.hid_dim + (12 if self.if_cat else 0)), dtype=torch.float32, device=self.device)
+        check(lib().tm_enhance_reduce(B, W, self.hid_dim, ptr(y), ptr(w), ptr(a3w), ptr(a3b), ptr(cat), ptr(out), st), "tm_enhance_reduce")
+        return out
+
+    def enhance_predict_pairs(self, walks_src, walks_tgt, cut_time_l, src_edge, tgt_edge):
+        return self.enhance_predict_walks(walks_src, cut_time_l, src_edge), self.enhance_predict_walks(walks_tgt, cut_time_l, tgt_edge)
+
+    def enhance_predict_agg(self, ts_l_cut, walks_src, walks_tgt, walks_bgd, edge_id_info, src_gat, tgt_gat, bgd_gat):
+        """explainer.py:203-213 -> (pos_score, neg_score), each [B, 1]."""
+        src_edge, tgt_edge, bgd_edge = edge_id_info
+        gat = [g.to(self.device, torch.float32) if isinstance(g, torch.Tensor) else torch.as_tensor(np.asarray(g), dtype=torch.float32, device=self.device)
+               for g in (src_gat, tgt_gat, bgd_gat)]
+        with torch.no_grad():
+            src_emb, tgt_emb = self.enhance_predict_pairs(walks_src, walks_tgt, ts_l_cut, src_edge, tgt_edge)
+            pos = self.affinity_score(torch.cat([src_emb, gat[0]], dim=-1), torch.cat([tgt_emb, gat[1]], dim=-1))
+            src_emb, bgd_emb = self.enhance_predict_pairs(walks_src, walks_bgd, ts_l_cut, src_edge, bgd_edge)
+            neg = self.affinity_score(torch.cat([src_emb, gat[0]], dim=-1), torch.cat([bgd_emb, gat[2]], dim=-1))
+        return pos, neg
 
     # ------------------------------------------------------------------ motif -> edge aggregation (explainer.py:354-430)
     def _packed_gate(self):

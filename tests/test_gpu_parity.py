@@ -532,3 +532,44 @@ def test_pipeline_explain_matches_oracle(tm, orc):
         r0, r1 = enc.edge_importance(p, efeat, ([osub[0][0], osub[0][1]], [osub[1][0], osub[1][1]], None), scores[sl][..., None], (None, oe, ot, None, None))
         np.testing.assert_allclose(imp0[sl], r0, rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(imp1[sl], r1, rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+# enhance path: compute_walk_importance, enhance_predict_walks, enhance_predict_agg, eval mode
+# ---------------------------------------------------------------------------------------------
+def test_enhance_path_golden(tm, golden):
+    z = golden("enhance_d32")
+    m = tm.TempME(_Base(z["node_feat"], z["edge_feat"]), "tgn", "t", 40, 64, device="cuda:0", null_model={}).cuda().eval()
+    missing, unexpected = m.load_state_dict({k[2:]: torch.as_tensor(z[k]) for k in z if k.startswith("p:")}, strict=False)
+    assert not unexpected
+    m.node_degree = torch.as_tensor(z["node_degree"]).cuda()
+    ws = {pre: (z[f"{pre}_nodes"], z[f"{pre}_eidx"], z[f"{pre}_t"], z[f"{pre}_cat"], None) for pre in ("src", "tgt")}
+    w = m.compute_walk_importance(ws["src"][2], ws["src"][0], z["cut_time"])
+    np.testing.assert_allclose(w.cpu().numpy(), z["w_src"], rtol=1e-5, atol=1e-7)
+    for pre in ws:
+        emb = m.enhance_predict_walks(ws[pre], z["cut_time"], z[f"{pre}_ei"])
+        np.testing.assert_allclose(emb.cpu().numpy(), z[f"emb_{pre}"], rtol=2e-5, atol=2e-5)
+    pos, neg = m.enhance_predict_agg(z["cut_time"], ws["src"], ws["tgt"], ws["src"], (z["src_ei"], z["tgt_ei"], z["src_ei"]), z["src_gat"], z["tgt_gat"], z["bgd_gat"])
+    np.testing.assert_allclose(pos.cpu().numpy(), z["pos"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(neg.cpu().numpy(), z["neg"], rtol=1e-4, atol=1e-4)
+
+
+def test_enhance_walks_vs_oracle_larger(tm, orc):
+    """Seeded inputs at several hundred roots against oracle/encoder.enhance_predict_walks (padding nodes, ragged degrees)."""
+    from oracle import encoder as enc
+    rng = np.random.default_rng(21)
+    B, W, D, Ed, Nn, Ne = 300, 30, 32, 32, 150, 900
+    nfeat = rng.standard_normal((Nn, D)).astype(np.float32); efeat = rng.standard_normal((Ne, Ed)).astype(np.float32)
+    nfeat[0] = 0; efeat[0] = 0
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "t", 40, 64, device="cuda:0", null_model={}).cuda().eval()
+    m.node_degree = torch.as_tensor(rng.integers(1, 80, Nn).astype(np.float32)).cuda()
+    p = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    nodes = rng.integers(0, Nn, (B, W, 6)); nodes[rng.random((B, W, 6)) < 0.15] = 0
+    eidx = rng.integers(0, Ne, (B, W, 3))
+    t = np.sort(rng.integers(1e8, 1.1e8, (B, W, 3)).astype(np.float64), -1)
+    cat = rng.integers(0, 12, (B, W, 1)); cut = t[:, :, 2].max(1) + rng.integers(1, 1000, B)
+    eid = rng.integers(0, W, (B, W, 3, 3)).astype(np.float64)
+    walks = (nodes, eidx, t, cat, None)
+    ref = enc.enhance_predict_walks(p, nfeat, efeat, walks, cut, eid, m.node_degree.cpu().numpy())
+    got = m.enhance_predict_walks(walks, cut, eid).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=5e-5)
