@@ -573,3 +573,40 @@ def test_enhance_walks_vs_oracle_larger(tm, orc):
     ref = enc.enhance_predict_walks(p, nfeat, efeat, walks, cut, eid, m.node_degree.cpu().numpy())
     got = m.enhance_predict_walks(walks, cut, eid).cpu().numpy()
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=5e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# offline explanation pack: pre_processing + marginal + calculate_edge of processed/data_preprocess.py
+# ---------------------------------------------------------------------------------------------
+def test_build_pack_matches_oracle(tm, orc, tmp_path):
+    src, dst, eidx, ts = synth_graph(13, 150, 25000, 10 ** 6)
+    f = tm.NeighborFinder.from_events(150, src, dst, eidx, ts)
+    og = orc.OracleGraph.from_events(150, src, dst, eidx, ts)
+    rng = np.random.default_rng(4)
+    q = np.arange(20000, 20060)
+    fake = rng.integers(1, 150, len(q))
+    n, N2 = 6, 3
+    pack, edge = tm.build_pack(f, src[q], dst[q], ts[q], eidx[q], fake, n, N2, seed=100)
+    assert sorted(pack) == sorted(tm.pack.PACK_KEYS) and edge.shape == (3, len(q), n * N2, 3, 3)
+    anonys, walks = [], {}
+    for k, (name, roots, ee) in enumerate((("src", src[q], eidx[q]), ("tgt", dst[q], eidx[q]), ("bgd", fake, None))):
+        osub = og.find_k_hop(2, roots, ts[q], n, ee, seed=100 + 2 * k)
+        on, oe, ot, oa = og.sample_walks(roots, osub[0][0], osub[1][0], osub[2][0], N2, seed=100 + 2 * k + 1)
+        for l in range(2):                                    # [node | eidx | t] (data_preprocess.py:115-116)
+            ref = np.concatenate([osub[0][l], osub[1][l], osub[2][l]], axis=-1).astype(np.float64)
+            assert (pack[f"subgraph_{name}_{l}"] == ref).all()
+        anonys.append(oa); walks[name] = (on, oe, ot, oa)
+        assert (edge[k] == orc.edge_identity(oe)).all()       # calculate_edge (:345-357)
+    hist = sum(np.bincount(orc.class_ids_prep(a)[0].ravel(), minlength=12) for a in anonys)
+    freq = hist / (len(q) * n * N2 * 3)                        # marginal (:190-192)
+    for name, (on, oe, ot, oa) in walks.items():
+        cat = orc.class_ids_prep(oa)[0]
+        ref = np.concatenate([on.astype(np.float64), oe.astype(np.float64), ot.astype(np.float64), cat[..., None].astype(np.float64), freq[cat][..., None]], axis=-1)
+        assert (pack[f"walks_{name}_new"] == ref).all()
+    # the reference loader's slicing (utils/batch_loader.py:120-201) applies to the dict / npz as is
+    path, edge_path = tm.save_pack(pack, edge, str(tmp_path), "unit", "test")
+    z = np.load(path) if path.endswith(".npz") else None
+    if z is not None:
+        x0 = z["subgraph_src_0"][:]
+        assert x0[:, 0:n].shape == (len(q), n) and (z["walks_src_new"][:][:, :, 12:13].astype(int) == orc.class_ids_prep(walks["src"][3])[0][..., None]).all()
+    assert np.load(edge_path).shape == edge.shape
