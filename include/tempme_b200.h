@@ -188,6 +188,12 @@ int tm_walk_importance(int64_t B, int64_t W, int64_t group, const float *d_t, co
 int tm_enhance_reduce(int64_t B, int64_t W, int hid_dim, const float *d_y, const float *d_weights, const float *d_att_mlp3_w,
                       const float *d_att_mlp3_b, const uint8_t *d_cat_or_null, float *d_out, tm_stream stream);
 
+/* ---- TempME.kl_loss, forward value (models/explainer.py:432-453; logged by the reference's eval loops, temp_exp_main.py:326-328 / :459-461).
+ * d_prob [B,W] motif scores, d_cat [B,W] walk classes, d_null_values [n_cat] = list(null_model.values()) (paired with the class index by
+ * position, as the reference does), empirical != 0 for prior == "empirical".  d_workspace: B doubles.  d_loss: 1 float. */
+int tm_kl_loss(int64_t B, int64_t W, const float *d_prob, const uint8_t *d_cat, const float *d_null_values, int n_cat, float target,
+               int empirical, double *d_workspace, float *d_loss, tm_stream stream);
+
 /* Kernel timing of the tensor-core scorer (CUDA events around its launch on the caller's
  * stream).  tm_encoder_profile(1) starts collecting; tm_encoder_profile_read returns in h_event_ms the accumulated
  * milliseconds of the scorer kernel since the last read (synchronises on the recorded events); h_motif_ms is 0 since the

@@ -178,3 +178,24 @@ def affinity_score(p, x1, x2, dtype=np.float32):
     dt = dtype
     x = np.concatenate([x1, x2], axis=-1).astype(dt)
     return _lin(np.maximum(_lin(x, p, "affinity_score.fc1", dt), 0), p, "affinity_score.fc2", dt)
+
+
+def kl_loss(prob, cat_feat, null_values, target=0.3, prior="empirical", dtype=np.float32):
+    """TempME.kl_loss, explainer.py:432-453.  prob [B,W] scores, cat_feat [B,W] classes, null_values = list(null_model.values())."""
+    dt = dtype
+    cat = np.asarray(cat_feat).astype(np.int64).reshape(np.asarray(cat_feat).shape[0], -1)
+    B, W = cat.shape
+    p = np.clip(np.asarray(prob).astype(dt).reshape(B, W), dt(1e-6), dt(1 - 1e-6))          # :435
+    t = dt(target)
+    if prior != "empirical":
+        v = p * np.log(p / t + dt(1e-6)) + (dt(1) - p) * np.log((dt(1) - p) / (dt(1) - t + dt(1e-6)) + dt(1e-6))   # :450-451
+        return dt(v.astype(np.float64).mean())
+    null = np.asarray(null_values).astype(dt)
+    C = null.shape[0]
+    s = p.mean(1, keepdims=True)                                                              # :438
+    onehot = (cat[:, :, None] == np.arange(C)[None, None, :])
+    cnt = np.maximum(onehot.sum(1), 1).astype(dt)
+    emp = s * ((p[:, :, None] * onehot).sum(1) / cnt)                                         # :443-444 (scatter mean: absent class -> 0)
+    nd = t * null[None, :]                                                                    # :445
+    v = (dt(1) - s) * np.log((dt(1) - s) / (dt(1) - t + dt(1e-6)) + dt(1e-6)) + emp * np.log(emp / (nd + dt(1e-6)) + dt(1e-6))
+    return dt(v.astype(np.float64).mean())                                                    # :447-448

@@ -318,6 +318,21 @@ class TempME(nn.Module):
         return self.edge_importance_device(scores, eidx, t, self._t(node_record[0], torch.int32), self._t(eidx_record[0], torch.int32),
                                            self._t(node_record[1], torch.int32), self._t(eidx_record[1], torch.int32))
 
+    def kl_loss(self, prob, walks, target=0.3):
+        """explainer.py:432-453, forward value (a 0-dim CUDA tensor without a graph: what the reference's eval loops log,
+        temp_exp_main.py:326-328).  The classes are paired with ``list(self.null_model.values())`` by position, as the reference does."""
+        cat = self._t(walks[3], torch.uint8)
+        B, W = cat.shape[0], cat.shape[1]
+        p = self._t(prob.detach() if isinstance(prob, torch.Tensor) else prob, torch.float32).reshape(B, W)
+        empirical = self.prior == "empirical"
+        null = torch.tensor([float(v) for v in self.null_model.values()], dtype=torch.float32, device=self.device)
+        work = torch.empty(B, dtype=torch.float64, device=self.device)
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(lib().tm_kl_loss(B, W, ptr(p), ptr(cat.reshape(B, W)), ptr(null), int(null.numel()), float(target), int(empirical),
+                               ptr(work), ptr(loss), st), "tm_kl_loss")
+        return loss
+
     def retrieve_explanation(self, subgraph_src, graphlet_imp_src, walks_src, subgraph_tgt, graphlet_imp_tgt, walks_tgt,
                              subgraph_bgd, graphlet_imp_bgd, walks_bgd, training=True):
         """explainer.py:408-419."""

@@ -16,6 +16,7 @@ Fixtures:
   encoder_*.npz    TempME.forward scores with the weights/features that produced them
   edgeimp_*.npz    retrieve_edge_imp_node (eval mode) on those scores: `python tests/golden/make_golden.py edgeimp`
   enhance_*.npz    enhance_predict_walks / compute_walk_importance / enhance_predict_agg (eval): `python tests/golden/make_golden.py enhance`
+  kl_loss.npz      TempME.kl_loss on fixed scores / classes, both priors: `python tests/golden/make_golden.py kl`
 """
 from __future__ import annotations
 
@@ -368,6 +369,38 @@ def gen_enhance_all():
     gen_enhance("d32", ws[0][0], ws[1][0], ws[0][1], ws[1][1], big["ts"][big["q"][:Bq]], int(big["n_nodes"]), len(big["eidx"]) + 1, 32, 32, seed=5)
 
 
+def gen_kl_all():
+    """TempME.kl_loss (reference models/explainer.py:432-453) on the classes of the committed walk fixtures and seeded scores (with
+    exact 0 / 1 entries for the clamp), for both priors and two targets.  The null model is non-uniform, in the reference's dict order."""
+    import torch
+    import models.explainer as rexp
+    rs = np.random.RandomState(11)
+    null = {k: float(v) for k, v in zip(range(1, 13), rs.dirichlet(np.ones(12) * 0.7))}
+    rexp.get_null_distribution = lambda data_name: null
+    nfeat = torch.zeros(4, 8); efeat = torch.zeros(4, 8)
+
+    class Base:
+        n_feat_th = nfeat; e_feat_th = efeat
+        node_raw_features = torch.nn.Embedding.from_pretrained(nfeat, padding_idx=0, freeze=True)
+        edge_raw_features = torch.nn.Embedding.from_pretrained(efeat, padding_idx=0, freeze=True)
+
+    us = dict(np.load(os.path.join(HERE, "uslegis.npz")))
+    out = {"null_values": np.array(list(null.values()), np.float64)}
+    cases = {"us": us["src_cat"][:16].astype(np.int64), "few": (rs.randint(0, 3, (5, 20)) * 4).astype(np.int64), "one": np.full((1, 7), 11, np.int64)}
+    for name, cat in cases.items():
+        B, W = cat.shape
+        prob = rs.rand(B, W, 1).astype(np.float32) ** 2
+        prob[0, 0] = 0.0; prob[-1, -1] = 1.0
+        out[f"{name}_cat"] = cat.astype(np.int8); out[f"{name}_prob"] = prob
+        for prior in ("empirical", "uniform"):
+            m = rexp.TempME(Base(), "tgn", "x", out_dim=8, hid_dim=16, prior=prior, device=torch.device("cpu"))
+            for target in (0.3, 0.05):
+                with torch.no_grad():
+                    v = m.kl_loss(torch.from_numpy(prob), (None, None, None, cat[:, :, None], None), target=target)
+                out[f"{name}_{prior}_{target}"] = np.float64(v.item())
+    np.savez_compressed(os.path.join(HERE, "kl_loss.npz"), **out)
+
+
 def gen_edge_imp_all():
     """Fixtures of the motif -> edge aggregation; reads the committed walk fixtures (does not regenerate them)."""
     us = dict(np.load(os.path.join(HERE, "uslegis.npz")))
@@ -394,6 +427,9 @@ def gen_edge_imp_all():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "edgeimp":
         gen_edge_imp_all()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "kl":
+        gen_kl_all()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "enhance":
         gen_enhance_all()

@@ -610,3 +610,25 @@ def test_build_pack_matches_oracle(tm, orc, tmp_path):
         x0 = z["subgraph_src_0"][:]
         assert x0[:, 0:n].shape == (len(q), n) and (z["walks_src_new"][:][:, :, 12:13].astype(int) == orc.class_ids_prep(walks["src"][3])[0][..., None]).all()
     assert np.load(edge_path).shape == edge.shape
+
+
+# ---------------------------------------------------------------------------------------------
+# kl_loss forward value (the part the reference's eval loops use)
+# ---------------------------------------------------------------------------------------------
+def test_kl_loss_golden_and_oracle(tm, golden):
+    from oracle import encoder as enc
+    z = golden("kl_loss")
+    null = {k + 1: float(v) for k, v in enumerate(z["null_values"])}
+    nfeat = np.zeros((4, 8), np.float32)
+    for prior in ("empirical", "uniform"):
+        m = tm.TempME(_Base(nfeat, nfeat), "tgn", "t", 8, 16, prior=prior, device="cuda:0", null_model=null).cuda().eval()
+        for name in ("us", "few", "one"):
+            for target in (0.3, 0.05):
+                v = m.kl_loss(torch.as_tensor(z[f"{name}_prob"]).cuda(), (None, None, None, z[f"{name}_cat"][:, :, None], None), target=target)
+                assert v.shape == () and v.is_cuda
+                np.testing.assert_allclose(v.item(), float(z[f"{name}_{prior}_{target}"]), rtol=1e-5, atol=1e-7)
+        rng = np.random.default_rng(5)                       # a full batch of cfg2's shape against the oracle
+        B, W = 3000, 30
+        prob = rng.random((B, W, 1)).astype(np.float32); cat = rng.integers(0, 12, (B, W, 1))
+        v = m.kl_loss(prob, (None, None, None, cat, None), target=0.3)
+        np.testing.assert_allclose(v.item(), enc.kl_loss(prob, cat, z["null_values"], 0.3, prior), rtol=1e-5, atol=1e-7)

@@ -197,3 +197,14 @@ def test_enhance_path_oracle(golden):
     neg = enc.affinity_score(p, np.concatenate([emb["src"], z["src_gat"]], -1), np.concatenate([emb["src"], z["bgd_gat"]], -1))
     np.testing.assert_allclose(pos, z["pos"], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(neg, z["neg"], rtol=1e-4, atol=1e-4)
+
+
+def test_kl_loss_oracle(golden):
+    """oracle.encoder.kl_loss == the reference's TempME.kl_loss for both priors (absent classes, clamped 0 / 1 scores, one root)."""
+    from oracle import encoder as enc
+    z = golden("kl_loss")
+    for name in ("us", "few", "one"):
+        for prior in ("empirical", "uniform"):
+            for target in (0.3, 0.05):
+                v = enc.kl_loss(z[f"{name}_prob"], z[f"{name}_cat"], z["null_values"], target, prior)
+                np.testing.assert_allclose(v, float(z[f"{name}_{prior}_{target}"]), rtol=1e-5, atol=1e-7)
