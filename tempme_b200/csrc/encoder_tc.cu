@@ -504,8 +504,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                         w[4 * g] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.x), ph.x), ctab); w[4 * g + 1] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.y), ph.y), ctab);
                         w[4 * g + 2] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.z), ph.z), ctab); w[4 * g + 3] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.w), ph.w), ctab);
                     }
-#pragma unroll
-                    for (int i = 0; i < CW; ++i) w[i] = (j0 - Ed + i < D && live) ? w[i] : 0.f;
+                    // no masks: columns >= D have zero frequency / phase (cos = 1) and zero weights; rows past the last motif are never stored
 #pragma unroll
                     for (int g = 0; g < CW / 4; ++g) af.put4(x, row, kb, 4 * g, make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]));
                     af.commit(x, lane_base, kb, second);
@@ -583,7 +582,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float p_ = o ? gv[k + i] : sv[k + i], q_ = o ? sv[k + i] : gv[k + i];
-                            z[i] = (c * kKC + kb + k + i < D && live) ? p_ + fmaxf(q_ + ee[k + i], 0.f) : 0.f;
+                            z[i] = p_ + fmaxf(q_ + ee[k + i], 0.f);     // columns >= D: features, lin_event output and constants are all zero (padding)
                         }
                         af.put4(x, row, kb, k, make_float4(z[0], z[1], z[2], z[3]));
                     }
@@ -761,9 +760,8 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll
                 for (int k = 0; k < CW; k += 4) {
                     const float4 bb = ldg4(cmr + c * kKC + kb + k);
-                    const int j = c * kKC + kb + k;
-                    af.put4(x, row, kb, k, make_float4(j < L.M ? fmaxf(z[k] + bb.x, 0.f) : 0.f, j + 1 < L.M ? fmaxf(z[k + 1] + bb.y, 0.f) : 0.f,
-                                                       j + 2 < L.M ? fmaxf(z[k + 2] + bb.z, 0.f) : 0.f, j + 3 < L.M ? fmaxf(z[k + 3] + bb.w, 0.f) : 0.f));
+                    // columns in [M, M16): R's rows and cm are zero-padded, relu(0) = 0
+                    af.put4(x, row, kb, k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
                 }
                 af.commit(x, lane_base, kb);
             }
