@@ -232,9 +232,10 @@ struct AFill {
         }
     }
     // all CW columns have been put; second: the event passes' second A buffer (the 64 TMEM columns below the primary one)
-    __device__ __forceinline__ void commit(const TcCtx &x, uint32_t lane_base, int kb, bool second = false) {
+    __device__ __forceinline__ void commit(const TcCtx &x, uint32_t lane_base, int kb, bool second = false) { commit_at(x, lane_base, kb, second ? x.a_col2 : x.a_col); }
+    __device__ __forceinline__ void commit_at(const TcCtx &x, uint32_t lane_base, int kb, uint32_t col) {
         if (TS) {
-            const uint32_t a0 = x.tmem + lane_base + (second ? x.a_col2 : x.a_col) + (uint32_t)kb;
+            const uint32_t a0 = x.tmem + lane_base + col + (uint32_t)kb;
             if (CW == 16) { tc::tmem_st16(a0, hi); tc::tmem_st16(a0 + kKC, lo); }
             else { tc::tmem_st8(a0, hi); tc::tmem_st8(a0 + kKC, lo); }
             tc::tmem_st_wait();
@@ -248,10 +249,10 @@ struct NoMid { __device__ __forceinline__ void operator()() const {} };
 // Dual rounds (TS mode, two A buffers): kDualK: D (+)= [A | A2] * [chunk | next chunk]^T (kcols + kc2 K columns);
 // kDualM: D (+)= A * chunk^T and D2 (+)= A2 * chunk^T (two row blocks share the chunk).
 enum { kSingle = 0, kDualK = 1, kDualM = 2 };
-struct Dual { int mode, kc2, d2; };
+struct Dual { int mode, kc2, d2, kc3, a3; };      // kc3 != 0 (with kDualK): a third K chunk from the A buffer at TMEM column a3
 template <bool TS, typename Mid = NoMid>
 __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d_col, bool accumulate, int64_t next_off, int next_bytes, Mid mid = Mid(),
-                                             Dual dual = Dual{kSingle, 0, 0}) {
+                                             Dual dual = Dual{kSingle, 0, 0, 0, 0}) {
 #ifdef TM_TC_TIMING
     const bool tim = x.dbg && threadIdx.x == 0 && x.dbg_i < 128;
 #else
@@ -301,6 +302,16 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
                 tc::mma_tf32_ts(dcol, t2 + 8 * ks, cl, idesc, 1, leader);
                 ch += db; cl += db;
             }
+            if (dual.kc3) {                                 // third K chunk
+                const uint32_t t3 = x.tmem + (uint32_t)dual.a3, b3 = x.b_s + 4 * (uint32_t)n16 * kKC * 4;
+                uint64_t eh = tc::smem_desc(b3, lbo_b, 128), el = tc::smem_desc(b3 + (uint32_t)n16 * kKC * 4, lbo_b, 128);
+                for (int ks = 0; ks < dual.kc3 / 8; ++ks) {
+                    tc::mma_tf32_ts(dcol, t3 + 8 * ks, eh, idesc, 1, leader);
+                    tc::mma_tf32_ts(dcol, t3 + kKC + 8 * ks, eh, idesc, 1, leader);
+                    tc::mma_tf32_ts(dcol, t3 + 8 * ks, el, idesc, 1, leader);
+                    eh += db; el += db;
+                }
+            }
         }
         tc::mma_commit(x.bars, leader);
         if (tim) x.dbg[x.dbg_i * 5 + 3] = clock64();
@@ -348,7 +359,7 @@ struct TcArgs {
     int stage_off;                           // byte offset of the node-feature staging (src rows, then tgt rows); 0: gather with plain loads
     int stage_edge_off;                      // byte offset of the edge-feature staging; 0: gather with plain loads
     unsigned long long *tile_counter;        // dynamic tile scheduler: CTA b takes tile b first, then gridDim.x + atomicAdd(counter, 1)
-    int dual;                                // two A buffers: bit 0 both orientations of MLP.0 per round + Q / R chunk pairs, bit 1 lin_event chunk pairs
+    int dual;                                // two A buffers: bit 0 both orientations of MLP.0 per round + Q / R chunk pairs, bit 1 lin_event chunk pairs, bit 2 MLP.3 in one round
     long long *dbg;                          // TEMPME_TC_TIMING: 128 x 5 clock stamps of CTA 0
 };
 
@@ -405,7 +416,10 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     const int H = L.H, H2 = 2 * L.H, D = L.D, Ed = L.Ed, nG = L.g0.nch, nchS = L.sp.nch;
     const int colZ = 0, colE = (nG == 1 && L.D16 <= H) ? H : H2;
     const bool dq = a.dual != 0, de = (a.dual & 2) != 0;   // dual rounds (bit 0: MLP.0 orientations, Q, R; bit 1: lin_event chunk pairs).  Q and R rounds in pairs: second A buffer = columns [0, 64) (U is dead by then)
-    const int colU = 0, colY = H2, colM0 = dq ? H : 0, colM1 = dq ? 0 : H2;
+    // m3one: MLP.3 in one round -- its two or three K chunks from A, A2 and a third buffer behind M0; M1 then lands over M0's first
+    // chunks (they have been read into the A buffers before the MMAs are issued)
+    const bool m3one = (a.dual & 4) != 0;
+    const int colU = 0, colY = H2, colM0 = dq ? H : 0, colM1 = m3one ? H : dq ? 0 : H2, colA3 = H + L.M16;
     const int64_t n_m = a.n_motifs, n_tiles = (n_m + 127) / 128;
     const int bytes_e = (int)chunk_floats(L.evt) * 4, bytes_g = (int)chunk_floats(L.g0) * 4;
     const int bytes_sp = (int)chunk_floats(L.sp) * 4, bytes_q = (int)chunk_floats(L.q) * 4, bytes_r = (int)chunk_floats(L.r) * 4, bytes_m3 = (int)chunk_floats(L.m3) * 4;
@@ -538,7 +552,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                                      if (!has_edge) return;
                                      if (c + 1 < L.nch_edge) request_edges(pi, c + 1);
                                      else if (pos < 2) request_edges(pnext, 0);
-                                 }, Dual{cnt == 2 ? kDualK : kSingle, kc1, 0});
+                                 }, Dual{cnt == 2 ? kDualK : kSingle, kc1, 0, 0, 0});
             }
             // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
             const int eb = pos == 2 ? L.e_b2 : L.e_b;
@@ -599,7 +613,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 else { noff = L.sp.w; nbytes = bytes_sp; }
                 if (a.dual) {                                       // both orientations in one round: Zs from the first A buffer, Zt from the second
                     if (kb < kcols) { load_g(); put_z(0, false); put_z(1, true); }
-                    tc_mma_round<TS>(x, H, kcols, colZ, c != 0, noff, nbytes, next_nodes, Dual{kDualM, 0, colZ + H});
+                    tc_mma_round<TS>(x, H, kcols, colZ, c != 0, noff, nbytes, next_nodes, Dual{kDualM, 0, colZ + H, 0, 0});
                 } else {
 #pragma unroll 1
                     for (int o = 0; o < 2; ++o) {
@@ -707,7 +721,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 put_mix(m0, m1, true);
                 const bool last = c + 2 >= nchS;
                 tc_mma_round<TS>(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 2) * chunk_floats(L.q), last ? 2 * bytes_r : 2 * bytes_q, NoMid(),
-                                 Dual{kDualK, kKC, 0});
+                                 Dual{kDualK, kKC, 0, 0, 0});
             }
         } else {
             for (int c = 0; c < nchS; ++c) {
@@ -742,7 +756,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         };
         if (dq) {                                               // both K chunks in one round; M0 lands at [H, H + M16) (Y has been read completely)
             put_y(0, false); put_y(1, true);
-            tc_mma_round<TS>(x, L.M16, kKC, colM0, false, L.m3.w, bytes_m3, NoMid(), Dual{kDualK, kKC, 0});
+            tc_mma_round<TS>(x, L.M16, kKC, colM0, false, L.m3.w, (m3one ? L.m3.nch : 1) * bytes_m3, NoMid(), Dual{kDualK, kKC, 0, 0, 0});
         } else {
             for (int c = 0; c < L.r.nch; ++c) {
                 put_y(c, false);
@@ -752,7 +766,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         }
         // ---- M1 = MLP.3 relu(M0 + cm[category])   (:199)
         const float *cmr = blob + L.cm + (int64_t)((L.if_cat && live && a.cat) ? min((int)a.cat[gm], 11) : 0) * L.M16;
-        for (int c = 0; c < L.m3.nch; ++c) {
+        auto fill_m3 = [&](int c, uint32_t col) {
             const int kcols = min(kKC, L.m3.K8 - c * kKC);
             if (kb < kcols) {
                 float z[CW];
@@ -763,8 +777,21 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                     // columns in [M, M16): R's rows and cm are zero-padded, relu(0) = 0
                     af.put4(x, row, kb, k, make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f)));
                 }
-                af.commit(x, lane_base, kb);
+                af.commit_at(x, lane_base, kb, col);
             }
+        };
+        if (m3one) {
+            const int nc = L.m3.nch;
+            fill_m3(0, x.a_col);
+            if (nc > 1) fill_m3(1, x.a_col2);
+            if (nc > 2) fill_m3(2, (uint32_t)colA3);
+            tc_mma_round<TS>(x, H, min(kKC, L.m3.K8), colM1, false, L.evt.w, more ? min(de ? 2 : 1, L.evt.nch) * bytes_e : 0,
+                             [&]() { if (more) { request_nodes(pcur, 0); request_edges(pcur, 0); } },
+                             Dual{nc > 1 ? kDualK : kSingle, nc > 1 ? min(kKC, L.m3.K8 - kKC) : 0, 0, nc > 2 ? L.m3.K8 - 2 * kKC : 0, colA3});
+        } else
+        for (int c = 0; c < L.m3.nch; ++c) {
+            const int kcols = min(kKC, L.m3.K8 - c * kKC);
+            fill_m3(c, x.a_col);
             const bool last = c + 1 == L.m3.nch;
             // the staging overlaps the weight buffer of the larger motif-round chunks; MLP.3's are small and R's MMAs have completed
             tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? min(de ? 2 : 1, L.evt.nch) * bytes_e : 0) : bytes_m3,
@@ -855,6 +882,9 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     for (const TcLin *l : {&L.evt, &L.g0, &L.sp, &L.q, &L.r, &L.m3}) bb = std::max(bb, chunk_floats(*l) * 4);
     if (dual_e) bb = std::max(bb, (int64_t)std::min(2, L.evt.nch) * chunk_floats(L.evt) * 4);        // lin_event chunks arrive in pairs
     if (dual) bb = std::max(bb, 2 * std::max(chunk_floats(L.q), chunk_floats(L.r)) * 4);             // so do Q's and R's
+    // MLP.3 in one round: all of its (two or three) K chunks in the weight buffer; the third A buffer sits between M0 and the A buffers
+    const bool m3one = dual && !getenv("TEMPME_TC_NO_M3ONE") && L.m3.nch <= 3 && (L.m3.nch < 3 || (L.m3.K8 - 2 * kKC <= 16 && H + L.M16 + 3 * kKC / 2 <= 3 * H));
+    if (m3one) bb = std::max(bb, (int64_t)L.m3.nch * chunk_floats(L.m3) * 4);
     // node-feature rows are gathered by bulk TMA into a staging area that may overlap the tail of the weight buffer: rows
     // are in flight only while lin_event / MLP.0 / MLP.3 chunks are being loaded, so it starts behind the largest of those
     CUtensorMap tm_node, tm_edge;
@@ -862,7 +892,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     const bool stage_nodes = L.D % 4 == 0 && ((uintptr_t)node_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && make_gather_map(&tm_node, node_feat, n_node_rows, L.D, 1);
     const bool stage_edges = L.Ed % 4 == 0 && ((uintptr_t)edge_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && !getenv("TEMPME_TC_NO_EDGE_STAGING") &&
                              make_gather_map(&tm_edge, edge_feat, n_edge_rows, L.Ed, 1);
-    const int64_t stage_rel = (std::max(std::max((dual_e ? std::min(2, L.evt.nch) : 1) * chunk_floats(L.evt), chunk_floats(L.g0)), chunk_floats(L.m3)) * 4 + 1023) & ~(int64_t)1023;
+    const int64_t stage_rel = (std::max(std::max((dual_e ? std::min(2, L.evt.nch) : 1) * chunk_floats(L.evt), chunk_floats(L.g0)), (m3one ? L.m3.nch : 1) * chunk_floats(L.m3)) * 4 + 1023) & ~(int64_t)1023;
     const int64_t stage_edge_rel = stage_rel + (stage_nodes ? (int64_t)2 * kStageTable * 4 : 0);
     bb = std::max(bb, stage_edge_rel + (stage_edges ? (int64_t)kStageTable * 4 : 0));
     const size_t a_bytes = ts ? 0 : (size_t)2 * kATile;
@@ -898,7 +928,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.F = F; a.scores = scores; a.y_out = y_out; a.tmem_cols = cols; a.b_bytes = (int)bb; a.dbg = nullptr;
     a.stage_off = stage_nodes ? (int)(a_bytes + stage_rel) : 0;
     a.stage_edge_off = stage_edges ? (int)(a_bytes + stage_edge_rel) : 0;
-    a.dual = (dual ? 1 : 0) | (dual_e ? 2 : 0);
+    a.dual = (dual ? 1 : 0) | (dual_e ? 2 : 0) | (m3one ? 4 : 0);
     static long long *dbg_buf = nullptr;
 #ifdef TM_TC_TIMING
     const char *tim_env = getenv("TEMPME_TC_TIMING");          // diagnostic: per-round clock stamps of CTA 0
@@ -1065,7 +1095,7 @@ gate_tc_kernel(const GateLayout G, const float *__restrict__ blob, const GateArg
             if (cnt == 2) fill1(c + 1, true);
             const int kc0 = min(kKC, G.l1.K8 - c * kKC), kc1 = cnt == 2 ? min(kKC, G.l1.K8 - (c + 1) * kKC) : 0;
             tc_mma_round<true>(x, r16(H), kc0, colG1, c != 0, left > 0 ? G.l1.w + (int64_t)(c + 2) * chunk_floats(G.l1) : G.l2.w,
-                               left > 0 ? min(2, left) * bytes1 : min(2, G.l2.nch) * bytes2, NoMid(), Dual{cnt == 2 ? kDualK : kSingle, kc1, 0});
+                               left > 0 ? min(2, left) * bytes1 : min(2, G.l2.nch) * bytes2, NoMid(), Dual{cnt == 2 ? kDualK : kSingle, kc1, 0, 0, 0});
         }
         // ---- ReLU, Linear(H, H/2) -> G2, two K chunks per round
         auto fill2 = [&](int c, bool second) {
@@ -1086,7 +1116,7 @@ gate_tc_kernel(const GateLayout G, const float *__restrict__ blob, const GateArg
             if (cnt == 2) fill2(c + 1, true);
             const int kc0 = min(kKC, G.l2.K8 - c * kKC), kc1 = cnt == 2 ? min(kKC, G.l2.K8 - (c + 1) * kKC) : 0;
             tc_mma_round<true>(x, r16(G.H2), kc0, colG2, c != 0, left > 0 ? G.l2.w + (int64_t)(c + 2) * chunk_floats(G.l2) : G.l1.w,
-                               left > 0 ? min(2, left) * bytes2 : (more ? min(2, G.l1.nch) * bytes1 : 0), NoMid(), Dual{cnt == 2 ? kDualK : kSingle, kc1, 0});
+                               left > 0 ? min(2, left) * bytes2 : (more ? min(2, G.l1.nch) * bytes1 : 0), NoMid(), Dual{cnt == 2 ? kDualK : kSingle, kc1, 0, 0, 0});
         }
         // ---- ReLU, Linear(H/2, 1), sigmoid gate (:379-386)
         float g_ = 0.f;
