@@ -228,6 +228,10 @@ int tm_edge_importance(const tm_gate_desc *desc, const float *d_gate_blob, int64
  * tensor cores (mode 0: one TF32 pass, mode 1: 3xTF32 split accumulation).  K % 8 == 0, N % 16 == 0, N <= 256. */
 int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, int K, int N, int mode, tm_stream stream);
 
+/* Issue-rate probe of the tensor pipe: groups x 8 back-to-back tcgen05.mma (M = 128, N, K = 8, tf32, A operand in TMEM) with loop-invariant
+ * operands on one otherwise idle SM.  d_out[0] = cycles to issue them, d_out[1] = cycles until they have completed (tools/mma_rate.py). */
+int tm_selftest_mma_rate(int N, int groups, long long *d_out, tm_stream stream);
+
 /* Self-test of the TimeEncode cosine (reference models/explainer.py:55-58): d_out[i] = cos(d_x[i]) evaluated by the
  * scorer's device routine (exact integer argument reduction; arguments reach 1e8 and beyond). */
 int tm_selftest_cos(const float *d_x, float *d_out, int64_t n, tm_stream stream);

@@ -69,6 +69,7 @@ SIGNATURES = {
                                       _p, _i64, _p, _i64, _p, _p, _p, C.c_int, _p]),
     "tm_walk_importance": (C.c_int, [_i64, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p]),
     "tm_enhance_reduce": (C.c_int, [_i64, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p]),
+    "tm_selftest_mma_rate": (C.c_int, [C.c_int, C.c_int, _p, _p]),
     "tm_kl_loss": (C.c_int, [_i64, _i64, _p, _p, _p, C.c_int, C.c_float, C.c_int, _p, _p, _p]),
     "tm_gate_blob_floats": (_i64, [C.POINTER(GateDesc)]),
     "tm_gate_pack": (C.c_int, [C.POINTER(GateDesc), C.POINTER(GateParams), _p]),

@@ -273,44 +273,46 @@ __device__ __forceinline__ void tc_mma_round(TcCtx &x, int n16, int kcols, int d
         uint64_t ah = tc::smem_desc(x.a_s, lbo_a, 128), al = tc::smem_desc(x.a_s + kATile, lbo_a, 128);
         uint64_t bh = tc::smem_desc(x.b_s, lbo_b, 128), bl = tc::smem_desc(x.b_s + (uint32_t)n16 * kKC * 4, lbo_b, 128);
         const uint64_t da = (2 * lbo_a) >> 4, db = (2 * lbo_b) >> 4;      // descriptor start-address step per K = 8
-        const uint32_t dcol = x.tmem + (uint32_t)d_col;
-        const uint32_t ta = x.tmem + x.a_col;
-        for (int ks = 0; ks < kcols / 8; ++ks) {
-            if (TS) {
-                tc::mma_tf32_ts(dcol, ta + 8 * ks, bh, idesc, (uint32_t)(accumulate || ks != 0), leader);
-                tc::mma_tf32_ts(dcol, ta + kKC + 8 * ks, bh, idesc, 1, leader);
-                tc::mma_tf32_ts(dcol, ta + 8 * ks, bl, idesc, 1, leader);
-                if (dual.mode == kDualM) {
-                    const uint32_t d2 = x.tmem + (uint32_t)dual.d2, t2 = x.tmem + x.a_col2;
-                    tc::mma_tf32_ts(d2, t2 + 8 * ks, bh, idesc, (uint32_t)(accumulate || ks != 0), leader);
-                    tc::mma_tf32_ts(d2, t2 + kKC + 8 * ks, bh, idesc, 1, leader);
-                    tc::mma_tf32_ts(d2, t2 + 8 * ks, bl, idesc, 1, leader);
+        if (TS) {
+            // The operands of every MMA are derived from warp-uniform bases taken through a warp reduction (REDUX writes a uniform register):
+            // ptxas then steps addresses and descriptors on the uniform datapath instead of moving each operand of each MMA from the
+            // elected lane's vector registers (tools/mma_rate.py: with lean issue code an MMA costs 128 N / 256 cycles, i.e. 16 at N = 32).
+            const uint32_t tm_u = __reduce_or_sync(0xffffffffu, x.tmem), bs_u = __reduce_or_sync(0xffffffffu, x.b_s);
+            const uint32_t dcol = tm_u + (uint32_t)d_col, ta = tm_u + x.a_col, ta2 = tm_u + x.a_col2;
+            // low words of the weight descriptors: [hi tile | lo tile] per chunk, chunks back to back; a K = 8 step advances the start address
+            const uint32_t hiw = tc::smem_desc_hi(128), tile = ((uint32_t)n16 * kKC * 4) >> 4, dbw = (2 * lbo_b) >> 4;
+            const uint32_t b0 = tc::smem_desc_lo(bs_u, lbo_b);
+            const int nks = kcols >> 3;                     // K chunks have at most kKC / 8 = 4 steps: unrolled, so the offsets are immediates
+#pragma unroll
+            for (int ks = 0; ks < kKC / 8; ++ks) {
+                if (ks < nks) {
+                    tc::mma3_tf32_ts(dcol, ta + 8 * ks, ta + kKC + 8 * ks, b0 + ks * dbw, b0 + tile + ks * dbw, hiw, idesc, (uint32_t)(accumulate || ks != 0), leader);
+                    if (dual.mode == kDualM)
+                        tc::mma3_tf32_ts(tm_u + (uint32_t)dual.d2, ta2 + 8 * ks, ta2 + kKC + 8 * ks, b0 + ks * dbw, b0 + tile + ks * dbw, hiw, idesc,
+                                         (uint32_t)(accumulate || ks != 0), leader);
                 }
-            } else {
+            }
+            if (dual.mode == kDualK) {                      // second K chunk: A2 with the chunk that follows in the weight buffer
+                const uint32_t b2 = b0 + 2 * tile;
+                const int nk2 = dual.kc2 >> 3;
+#pragma unroll
+                for (int ks = 0; ks < kKC / 8; ++ks)
+                    if (ks < nk2) tc::mma3_tf32_ts(dcol, ta2 + 8 * ks, ta2 + kKC + 8 * ks, b2 + ks * dbw, b2 + tile + ks * dbw, hiw, idesc, 1, leader);
+                if (dual.kc3) {                             // third K chunk
+                    const uint32_t t3 = tm_u + (uint32_t)dual.a3, b3 = b0 + 4 * tile;
+                    const int nk3 = dual.kc3 >> 3;
+#pragma unroll
+                    for (int ks = 0; ks < kKC / 8; ++ks)
+                        if (ks < nk3) tc::mma3_tf32_ts(dcol, t3 + 8 * ks, t3 + kKC + 8 * ks, b3 + ks * dbw, b3 + tile + ks * dbw, hiw, idesc, 1, leader);
+                }
+            }
+        } else {
+            const uint32_t dcol = x.tmem + (uint32_t)d_col;
+            for (int ks = 0; ks < kcols / 8; ++ks) {
                 tc::mma_tf32(dcol, ah, bh, idesc, (uint32_t)(accumulate || ks != 0), leader);
                 tc::mma_tf32(dcol, al, bh, idesc, 1, leader);
                 tc::mma_tf32(dcol, ah, bl, idesc, 1, leader);
-            }
-            ah += da; al += da; bh += db; bl += db;
-        }
-        if (TS && dual.mode == kDualK) {                    // second K chunk: A2 with the chunk that follows in the weight buffer
-            const uint32_t t2 = x.tmem + x.a_col2, b2 = x.b_s + 2 * (uint32_t)n16 * kKC * 4;
-            uint64_t ch = tc::smem_desc(b2, lbo_b, 128), cl = tc::smem_desc(b2 + (uint32_t)n16 * kKC * 4, lbo_b, 128);
-            for (int ks = 0; ks < dual.kc2 / 8; ++ks) {
-                tc::mma_tf32_ts(dcol, t2 + 8 * ks, ch, idesc, 1, leader);
-                tc::mma_tf32_ts(dcol, t2 + kKC + 8 * ks, ch, idesc, 1, leader);
-                tc::mma_tf32_ts(dcol, t2 + 8 * ks, cl, idesc, 1, leader);
-                ch += db; cl += db;
-            }
-            if (dual.kc3) {                                 // third K chunk
-                const uint32_t t3 = x.tmem + (uint32_t)dual.a3, b3 = x.b_s + 4 * (uint32_t)n16 * kKC * 4;
-                uint64_t eh = tc::smem_desc(b3, lbo_b, 128), el = tc::smem_desc(b3 + (uint32_t)n16 * kKC * 4, lbo_b, 128);
-                for (int ks = 0; ks < dual.kc3 / 8; ++ks) {
-                    tc::mma_tf32_ts(dcol, t3 + 8 * ks, eh, idesc, 1, leader);
-                    tc::mma_tf32_ts(dcol, t3 + kKC + 8 * ks, eh, idesc, 1, leader);
-                    tc::mma_tf32_ts(dcol, t3 + 8 * ks, el, idesc, 1, leader);
-                    eh += db; el += db;
-                }
+                ah += da; al += da; bh += db; bl += db;
             }
         }
         tc::mma_commit(x.bars, leader);

@@ -53,6 +53,22 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
         :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
 }
+// One K = 8 step of a 3xTF32 product with the A operand in TMEM: D (+)= Ah Bh + Al Bh + Ah Bl.  The B descriptors are passed as their low
+// words (start address | LBO, smem_desc_lo) with the shared high word (smem_desc_hi): stepping along K is a 32-bit add, and ptxas keeps
+// the operands in uniform registers.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ void mma3_tf32_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t bh_lo, uint32_t bl_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accumulate, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, one;\n\t.reg .b64 dh, dl;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\tsetp.ne.b32 q, %8, 0;\n\tsetp.eq.b32 one, 0, 0;\n\t"
+        "mov.b64 dh, {%3, %5};\n\tmov.b64 dl, {%4, %5};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dh, %6, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], dh, %6, one;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dl, %6, one;\n\t}\n"
+        :: "r"(tmem_d), "r"(a_hi), "r"(a_lo), "r"(bh_lo), "r"(bl_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
 // all MMAs issued so far by the leader arrive on the mbarrier when they complete
 __device__ __forceinline__ void mma_commit(uint64_t *mbar, uint32_t leader = 1) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"

@@ -97,6 +97,62 @@ selftest_gemm_kernel(const float *__restrict__ A, const float *__restrict__ B, f
     if (warp == 0) tc::tmem_dealloc(tmem, ncols);
 }
 
+// Issue-rate probe: `groups` x 8 back-to-back tcgen05.mma (M = 128, K = 8, tf32, A operand in TMEM) with identical, loop-invariant
+// operands, so the loop holds nothing but the MMAs.  out[0] = cycles to issue them, out[1] = cycles until they have completed.
+__global__ void __launch_bounds__(128) mma_rate_kernel(int N, int groups, long long *__restrict__ out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < N * 32; i += 128) reinterpret_cast<float *>(smem)[i] = 0.f;
+    if (t == 0) tc::mbar_init(&mbar, 1);
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    tc::fence_smem_to_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    {
+        float z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0.f;
+        for (int c = 0; c < 512; c += 16) tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + c, z);
+        tc::tmem_st_wait();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    long long t0 = 0, t1 = 0;
+    if (warp == 0) {
+        const uint32_t leader = tc::elect_one();
+        const uint32_t idesc = tc::idesc_tf32(128, N);
+        const uint64_t bdesc = tc::smem_desc(tc::smem_u32(smem), (uint32_t)N * 16, 128);
+        const uint32_t ta = tmem + 256;
+        t0 = clock64();
+        for (int g = 0; g < groups; ++g)
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, 1, 0;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                :: "r"(tmem), "r"(ta), "l"(bdesc), "r"(idesc), "r"(leader) : "memory");
+        tc::mma_commit(&mbar, leader);
+        t1 = clock64();
+        __syncwarp();
+    }
+    tc::mbar_wait(&mbar, 0);
+    const long long t2 = clock64();
+    if (t == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace tmb
 
 using namespace tmb;
@@ -157,6 +213,13 @@ extern "C" int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, 
     if (smem > 200 * 1024) { set_error("tm_selftest_gemm: tile too large"); return TM_ERR_UNSUPPORTED; }
     TM_CUDA(cudaFuncSetAttribute(selftest_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     selftest_gemm_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(d_A, d_B, d_C, K, N, mode);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}
+
+extern "C" int tm_selftest_mma_rate(int N, int groups, long long *d_out, tm_stream stream) {
+    if (!d_out || N < 16 || N > 256 || N % 16 || groups < 1) { set_error("tm_selftest_mma_rate: need 16 <= N <= 256, N %% 16 == 0, groups >= 1"); return TM_ERR_ARG; }
+    mma_rate_kernel<<<1, 128, (size_t)N * 32 * 4, (cudaStream_t)stream>>>(N, groups, d_out);
     TM_LAUNCH_CHECK();
     return TM_OK;
 }
