@@ -9,9 +9,8 @@ namespace tmb {
 // Branch-free exact argument reduction in integer arithmetic: |x| = m * 2^e with a 24-bit integer m, so
 // frac(|x| / 2pi) = frac(m * frac(2^e / 2pi)); kInv2Pi[e + 44] holds frac(2^e / 2pi) in 0.64 fixed point for every
 // finite fp32 exponent (e = -44 .. 104; below that the angle is 0), of which the top 32 bits of the product are kept
-// (error < 2^-32 turn = 1.5e-9 rad).  The turn fraction is split into a quadrant and an angle in [-pi/4, pi/4) for the
-// fdlibm single-precision sin/cos kernels.  Max error ~1.5 ulp of 1.0 against the exact cosine of the fp32 argument
-// (cosf: 1-2 ulp); inf and nan give nan.  The table is read from shared memory (a copy of kInv2Pi): lanes index it with
+// (error < 2^-32 turn = 1.5e-9 rad).  The turn fraction is shifted by a quarter turn (cos -> sin) and folded into [-pi/2, pi/2] for one
+// odd polynomial.  Max error ~2 ulp of 1.0 (< 2e-7) against the exact cosine of the fp32 argument (cosf: 1-2 ulp); inf and nan give nan.  The table is read from shared memory (a copy of kInv2Pi): lanes index it with
 // different exponents.
 constexpr int kInv2PiN = 149;
 __constant__ unsigned long long kInv2Pi[kInv2PiN] = {
@@ -46,14 +45,14 @@ __device__ __forceinline__ float cos_accurate(float x, const uint2 *tab) {
     const uint32_t bits = __float_as_uint(x) & 0x7fffffffu, ex = bits >> 23;              // |x| = m * 2^(ex - 150)
     const uint32_t m = ex < 106u ? 0u : ((bits & 0x7fffffu) | 0x800000u);                  // tiny |x|: angle 0
     const uint2 T = tab[min(max((int)ex - 106, 0), kInv2PiN - 1)];                          // {low, high} words of frac(2^e / 2pi)
-    const uint32_t fr = m * T.y + __umulhi(m, T.x) + (1u << 29);                           // turn fraction + 1/8 turn, 0.32 fixed point
-    const int q = (int)(fr >> 30);
-    const int r = (int)(fr & 0x3fffffffu) - (1 << 29);                                      // angle inside the quadrant, [-1/8, 1/8) turn
-    const float th = (float)r * 1.46291807926715968e-9f /* 2 pi / 2^32 */, z = th * th;
-    const float cs = fmaf(z, fmaf(z, fmaf(z, fmaf(z, 2.43904487962774090654e-5f, -1.38867637746099294692e-3f), 4.16666233237390631894e-2f), -4.99999997251031003120e-1f), 1.f);
-    const float sn = fmaf(th * z, fmaf(z, fmaf(z, fmaf(z, 2.7183114939898219064e-6f, -1.98393348360966317347e-4f), 8.3333293858894631756e-3f), -1.66666666416265235595e-1f), th);
-    float v = (q & 1) ? sn : cs;                                                            // cos(q pi/2 + th) = {cs, -sn, -cs, sn}[q]
-    v = ((q + 1) & 2) ? -v : v;
+    // cos(2 pi t) = sin(2 pi (t + 1/4)): turn fraction + a quarter turn, 0.32 fixed point, read as a signed angle in [-1/2, 1/2) turn
+    const uint32_t s = m * T.y + __umulhi(m, T.x) + (1u << 30);
+    // fold into [-1/4, 1/4] turn (sin(pi - a) = sin(a)): the two top bits differ exactly when |angle| >= 1/4 turn
+    const int y = (int)(s ^ (s << 1)) < 0 ? (int)(0x80000000u - s) : (int)s;
+    const float th = (float)y * 1.46291807926715968e-9f /* 2 pi / 2^32 */, z = th * th;
+    // odd minimax polynomial of sin on [-pi/2, pi/2] (degree 11, fit error 2e-11; fp32 evaluation error < 1.2e-7)
+    const float p = fmaf(z, fmaf(z, fmaf(z, fmaf(z, -2.3846693508744465e-8f, 2.752261934801936e-6f), -1.9840804452542216e-4f), 8.333330042660236e-3f), -1.666666716337204e-1f);
+    const float v = fmaf(th * z, p, th);
     return ex == 255u ? __int_as_float(0x7fffffff) : v;
 }
 
