@@ -282,16 +282,37 @@ def run_ours(args):
     dev_q = [pipe.stage_queries(*q) for q in host_q]
     row_off = rank * 3 * Q
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    gathered = torch.empty((world, 3 * Q, W), dtype=torch.float32, device=dev) if world > 1 else None
+    gathered, xchg, exchange_kind = None, None, "none"
+    if world > 1:
+        # score gather: fused into the scorer kernel (peer stores into symmetric memory over NVLink) when every rank can map its peers,
+        # else NCCL all-gather.  TEMPME_EXCHANGE=nccl forces the collective.
+        ok = torch.zeros(1, device=dev)
+        if os.environ.get("TEMPME_EXCHANGE", "fused") != "nccl":
+            try:
+                from tempme_b200.dist import ScoreExchange
+                xchg = ScoreExchange(3 * Q, W, dev)
+                ok += 1
+            except Exception as e:      # noqa: BLE001 -- any failure of the symmetric-memory setup selects the NCCL path on ALL ranks
+                if rank == 0:
+                    print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); score gather through NCCL", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1:
+            xchg = None
+        exchange_kind = "peer stores fused in the scorer + NCCL histogram all-reduce" if xchg is not None else "NCCL all-reduce (histogram) + all-gather (scores)"
+        gathered = xchg.gathered if xchg is not None else torch.empty((world, 3 * Q, W), dtype=torch.float32, device=dev)
     sync_token = torch.zeros(1, device=dev)
 
     def step(i, timers=None):
-        scores = pipe.run_device(*dev_q[i], row_offset=row_off, timers=timers)
-        if world > 1:       # the path's only exchanges: 12-bin histogram all-reduce + score gather
+        if xchg is not None:        # scores land in this rank's segment of every rank's gathered buffer; the all-reduce orders the reads after them
+            scores = pipe.run_device(*dev_q[i], row_offset=row_off, timers=timers, out=xchg.local, peer_ptrs=xchg.peer_ptrs)
             dist.all_reduce(pipe.hist_null)
-            dist.all_gather_into_tensor(gathered, scores)
-            if timers is not None:
-                ev = torch.cuda.Event(enable_timing=True); ev.record(); timers.append(("exchange", ev))
+        else:
+            scores = pipe.run_device(*dev_q[i], row_offset=row_off, timers=timers)
+            if world > 1:       # the path's only exchanges: 12-bin histogram all-reduce + score gather
+                dist.all_reduce(pipe.hist_null)
+                dist.all_gather_into_tensor(gathered, scores)
+        if world > 1 and timers is not None:
+            ev = torch.cuda.Event(enable_timing=True); ev.record(); timers.append(("exchange", ev))
         return scores
 
     for i in range(args.warmup):
@@ -433,7 +454,7 @@ def run_ours(args):
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {sh['desc']}", "events_per_gpu_per_step": Q, "roots_per_event": 3, "walks_per_root": W,
                        "motifs_per_step_per_gpu": motifs_step, "reference_batch": args.group, "node_dim": D, "edge_dim": Ed, "hid_dim": 64,
-                       "parallelism": f"query-sharded x{world}, graph replicated", "l2": "flushed between timed steps (256 MiB memset)",
+                       "parallelism": f"query-sharded x{world}, graph replicated", "exchange": exchange_kind, "l2": "flushed between timed steps (256 MiB memset)",
                        "graph_build_s": build_s, "graph_device_bytes": finder.device_bytes()},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(ln.item()), "clocks": clk,
             "wall_s_timed_region": wall}))

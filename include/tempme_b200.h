@@ -170,6 +170,17 @@ int tm_encode_score(const tm_encoder_desc *desc, const float *d_blob, int64_t B,
                     const float *d_node_feat, int64_t n_node_rows, const float *d_edge_feat, int64_t n_edge_rows,
                     float *d_workspace, float *d_scores, int device, tm_stream stream);
 
+/* As tm_encode_score, with the score gather of the sharded path (tempme_b200/dist.py; the reference has no multi-GPU path) fused into
+ * the kernel: every score is also stored to h_peer_scores[p] + (its index), p < n_peers <= 7 -- device addresses, mapped on this GPU, of this
+ * rank's [B*W] segment inside each peer GPU's gathered buffer (NVLink peer stores, 128 bytes per warp).  The stores are visible to the peers
+ * when the kernel has completed; order them with the collective that follows on the stream (the histogram all-reduce).  h_peer_scores is a
+ * HOST array read during the call. */
+int tm_encode_score_gather(const tm_encoder_desc *desc, const float *d_blob, int64_t B, int64_t W, int64_t group,
+                           const int32_t *d_nodes, const int32_t *d_eidx, const float *d_t, const uint8_t *d_cat,
+                           const float *d_cut_time, const float *d_edge_identity,
+                           const float *d_node_feat, int64_t n_node_rows, const float *d_edge_feat, int64_t n_edge_rows,
+                           float *d_workspace, float *d_scores, const uint64_t *h_peer_scores, int n_peers, int device, tm_stream stream);
+
 /* As tm_encode_score, and additionally d_y [B*W, hid_dim] = relu(attention.MLP.0(.)) of every walk: the input of attention.MLP.3, i.e. the
  * attention output of TempME.enhance_predict_walks (models/explainer.py:240-243) before its last Linear. */
 int tm_encode_attention(const tm_encoder_desc *desc, const float *d_blob, int64_t B, int64_t W, int64_t group,

@@ -41,7 +41,7 @@ int64_t tc_slab_motifs();
 int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
                     const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
                     int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
-                    float *y_out, int device, cudaStream_t st);
+                    float *y_out, float *const *peer_scores, int n_peers, int device, cudaStream_t st);
 
 // tensor map for tile::gather4 row gathers (encoder_tc.cu)
 bool make_gather_map(CUtensorMap *map, const float *table, int64_t rows, int dim, int swizzle128);

@@ -325,7 +325,7 @@ static int encode_score_impl(const tm_encoder_desc *desc, const float *d_blob, i
                              const int32_t *d_nodes, const int32_t *d_eidx, const float *d_t, const uint8_t *d_cat,
                              const float *d_cut_time, const float *d_edge_identity,
                              const float *d_node_feat, int64_t n_node_rows, const float *d_edge_feat, int64_t n_edge_rows,
-                             float *d_workspace, float *d_scores, float *d_y, int device, tm_stream stream) {
+                             float *d_workspace, float *d_scores, float *d_y, float *const *peer_scores, int n_peers, int device, tm_stream stream) {
     if (!desc || !d_blob || B < 0 || W <= 0 || group <= 0 ||
         (B > 0 && (!d_nodes || !d_eidx || !d_t || !d_cut_time || !d_node_feat || !d_edge_feat || !d_workspace || !d_scores))) {
         set_error("tm_encode_score: bad argument");
@@ -344,10 +344,10 @@ static int encode_score_impl(const tm_encoder_desc *desc, const float *d_blob, i
         TM_LAUNCH_CHECK();
     }
     const char *which = getenv("TEMPME_ENCODER");     // "ffma" selects the fp32 CUDA-core kernel (A/B validation); default: tcgen05
-    if (d_y || !which || strcmp(which, "ffma") != 0) {
+    if (d_y || n_peers > 0 || !which || strcmp(which, "ffma") != 0) {
         const int64_t n_std = (std::max<int64_t>(32, n_groups) + 31) & ~(int64_t)31;
         return tc_encode_score(*desc, d_blob + L.total, B, W, group, d_nodes, d_eidx, d_t, d_cat, d_cut_time, d_edge_identity, d_node_feat,
-                               n_node_rows, d_edge_feat, n_edge_rows, d_workspace, d_workspace + n_std, d_scores, d_y, device, st);
+                               n_node_rows, d_edge_feat, n_edge_rows, d_workspace, d_workspace + n_std, d_scores, d_y, peer_scores, n_peers, device, st);
     }
     const int64_t cap = (227 * 1024 - 1024) / 4;
     int T = 64;
@@ -380,7 +380,22 @@ extern "C" int tm_encode_score(const tm_encoder_desc *desc, const float *d_blob,
                                const float *d_node_feat, int64_t n_node_rows, const float *d_edge_feat, int64_t n_edge_rows,
                                float *d_workspace, float *d_scores, int device, tm_stream stream) {
     return encode_score_impl(desc, d_blob, B, W, group, d_nodes, d_eidx, d_t, d_cat, d_cut_time, d_edge_identity, d_node_feat, n_node_rows,
-                             d_edge_feat, n_edge_rows, d_workspace, d_scores, nullptr, device, stream);
+                             d_edge_feat, n_edge_rows, d_workspace, d_scores, nullptr, nullptr, 0, device, stream);
+}
+
+extern "C" int tm_encode_score_gather(const tm_encoder_desc *desc, const float *d_blob, int64_t B, int64_t W, int64_t group,
+                                      const int32_t *d_nodes, const int32_t *d_eidx, const float *d_t, const uint8_t *d_cat,
+                                      const float *d_cut_time, const float *d_edge_identity,
+                                      const float *d_node_feat, int64_t n_node_rows, const float *d_edge_feat, int64_t n_edge_rows,
+                                      float *d_workspace, float *d_scores, const uint64_t *h_peer_scores, int n_peers, int device, tm_stream stream) {
+    float *peers[8] = {nullptr};
+    if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && !h_peer_scores)) { set_error("tm_encode_score_gather: 0 <= n_peers <= 7"); return TM_ERR_ARG; }
+    for (int p = 0; p < n_peers; ++p) {
+        peers[p] = reinterpret_cast<float *>((uintptr_t)h_peer_scores[p]);
+        if (!peers[p]) { set_error("tm_encode_score_gather: null peer pointer"); return TM_ERR_ARG; }
+    }
+    return encode_score_impl(desc, d_blob, B, W, group, d_nodes, d_eidx, d_t, d_cat, d_cut_time, d_edge_identity, d_node_feat, n_node_rows,
+                             d_edge_feat, n_edge_rows, d_workspace, d_scores, nullptr, peers, n_peers, device, stream);
 }
 
 extern "C" int tm_encode_attention(const tm_encoder_desc *desc, const float *d_blob, int64_t B, int64_t W, int64_t group,
@@ -390,5 +405,5 @@ extern "C" int tm_encode_attention(const tm_encoder_desc *desc, const float *d_b
                                    float *d_workspace, float *d_scores, float *d_y, int device, tm_stream stream) {
     if (!d_y && B > 0) { set_error("tm_encode_attention: d_y is required"); return TM_ERR_ARG; }
     return encode_score_impl(desc, d_blob, B, W, group, d_nodes, d_eidx, d_t, d_cat, d_cut_time, d_edge_identity, d_node_feat, n_node_rows,
-                             d_edge_feat, n_edge_rows, d_workspace, d_scores, d_y, device, stream);
+                             d_edge_feat, n_edge_rows, d_workspace, d_scores, d_y, nullptr, 0, device, stream);
 }

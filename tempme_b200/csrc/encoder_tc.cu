@@ -346,6 +346,7 @@ __device__ __forceinline__ void tma_gather4(void *dst_smem, const CUtensorMap *m
                  :: "r"(tc::smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(tc::smem_u32(mbar)) : "memory");
 }
 
+constexpr int kMaxPeers = 7;
 struct TcArgs {
     int64_t n_motifs, W, group;              // B * W motifs; W walks per root; roots per reference batch (index of std_)
     const int32_t *nodes, *eidx;
@@ -356,6 +357,8 @@ struct TcArgs {
     float *F;                                // scratch: per CTA 12 h slabs [position][column chunk][piece k/4][128 rows][4]
     float *scores;
     float *y_out;                            // optional [n_motifs, H]: relu(attention.MLP.0(.)), the input of attention.MLP.3 (enhance path)
+    float *peer[kMaxPeers];                  // score gather fused into the kernel: the same [n_motifs] segment in each peer GPU's gathered buffer (NVLink peer stores)
+    int n_peer;
     uint32_t tmem_cols;
     int b_bytes;                             // bytes of the weight-chunk buffer
     int stage_off;                           // byte offset of the node-feature staging (src rows, then tgt rows); 0: gather with plain loads
@@ -815,7 +818,9 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             float zz = cstM[L.m_b5];
 #pragma unroll
             for (int q = 0; q < kParts; ++q) zz += part[q][0][row];
-            a.scores[gm] = 1.f / (1.f + expf(-zz));
+            const float sc = 1.f / (1.f + expf(-zz));
+            a.scores[gm] = sc;
+            for (int p = 0; p < a.n_peer; ++p) a.peer[p][gm] = sc;       // 128-byte warp stores over NVLink; visible to the peers at kernel end
         }
         tile = next_tile;
         // the next write to part[] comes after the barriers of the next tile's rounds
@@ -864,8 +869,9 @@ bool make_gather_map(CUtensorMap *map, const float *table, int64_t rows, int dim
 int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
                     const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
                     int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
-                    float *y_out, int device, cudaStream_t st) {
+                    float *y_out, float *const *peer_scores, int n_peers, int device, cudaStream_t st) {
     const TcLayout L = make_tc_layout(d);
+    if (n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !peer_scores)) { set_error("tc_encode_score: at most %d peer outputs", kMaxPeers); return TM_ERR_ARG; }
     if (L.H != 64) { set_error("tc_encode_score: hid_dim must be 64"); return TM_ERR_UNSUPPORTED; }
     if (device < 0 || device >= 64) { set_error("tc_encode_score: device index out of range"); return TM_ERR_UNSUPPORTED; }
     const int H = L.H;
@@ -927,6 +933,8 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     TcArgs a;
     a.n_motifs = B * W; a.W = W; a.group = group; a.nodes = nodes; a.eidx = eidx; a.t = t; a.cat = cat; a.cut = cut;
     a.eid = eid; a.node_feat = node_feat; a.edge_feat = edge_feat; a.std_ = std_; a.n_node_rows = n_node_rows; a.n_edge_rows = n_edge_rows;
+    a.n_peer = n_peers;
+    for (int p = 0; p < kMaxPeers; ++p) a.peer[p] = p < n_peers ? peer_scores[p] : nullptr;
     a.F = F; a.scores = scores; a.y_out = y_out; a.tmem_cols = cols; a.b_bytes = (int)bb; a.dbg = nullptr;
     a.stage_off = stage_nodes ? (int)(a_bytes + stage_rel) : 0;
     a.stage_edge_off = stage_edges ? (int)(a_bytes + stage_edge_rel) : 0;

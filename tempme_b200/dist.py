@@ -4,6 +4,10 @@ The path shards by *whole reference batches* (the temporal attention normalises 
 explainer.py:826-828); graph, feature tables and weights are replicated.  Draws are keyed by the global root
 row, so every split produces the same walks and scores as one GPU.  The only exchanges are the 12-bin class
 histogram all-reduce and the score gather (NCCL over NVLink on GPUs; gloo in the CPU tests of this logic).
+
+ScoreExchange fuses the score gather into the scorer kernel: the gathered buffer lives in symmetric memory (every rank maps every
+peer's copy over NVLink), the kernel stores each score into its rank's segment of every copy, and the histogram all-reduce that
+follows on the stream orders the peers' reads after those stores.
 """
 from __future__ import annotations
 
@@ -17,6 +21,41 @@ def shard_batches(n_batches: int, world: int, rank: int):
     base, extra = divmod(n_batches, world)
     b0 = rank * base + min(rank, extra)
     return b0, b0 + base + (1 if rank < extra else 0)
+
+
+def segment_offsets(rows_per_rank: int, W: int, world: int, rank: int, base_ptrs):
+    """Device addresses of `rank`'s [rows_per_rank, W] float32 segment inside every OTHER rank's gathered buffer [world, rows_per_rank, W]
+    (base_ptrs[p] = address of rank p's buffer as mapped on this GPU)."""
+    seg = rank * rows_per_rank * W * 4
+    return [int(base_ptrs[p]) + seg for p in range(world) if p != rank]
+
+
+class ScoreExchange:
+    """Gathered scores [world, rows_per_rank, W] in symmetric memory; `local` is this rank's segment (pass it as `out` of
+    MotifPipeline.run_device / TempME.score_device) and `peer_ptrs` the same segment on the peers (pass as `peer_ptrs`).
+    After the step's histogram all-reduce has completed on the stream, `gathered` holds every rank's scores.
+    Before a rank overwrites its segment again, all ranks must have consumed the previous contents (any collective between the
+    consumer and the next step orders that; bench.py's per-step token all-reduce does).
+    Raises RuntimeError when symmetric memory is unavailable (callers fall back to dist.all_gather_into_tensor)."""
+
+    def __init__(self, rows_per_rank: int, W: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("ScoreExchange: at most 8 ranks (one NVSwitch domain)")
+        grp = group if group is not None else dist.group.WORLD
+        try:
+            if hasattr(symm, "is_symm_mem_enabled_for_group") and not symm.is_symm_mem_enabled_for_group(grp.group_name):
+                symm.enable_symm_mem_for_group(grp.group_name)
+        except Exception:       # newer torch enables it lazily in rendezvous
+            pass
+        self.gathered = symm.empty((self.world, rows_per_rank, W), dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.gathered, grp)
+        ptrs = list(self.handle.buffer_ptrs)
+        if len(ptrs) != self.world or int(ptrs[self.rank]) != self.gathered.data_ptr():
+            raise RuntimeError("ScoreExchange: unexpected symmetric-memory mapping")
+        self.local = self.gathered[self.rank]
+        self.peer_ptrs = segment_offsets(rows_per_rank, W, self.world, self.rank, ptrs)
 
 
 class ShardedPipeline:

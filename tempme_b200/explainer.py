@@ -173,9 +173,11 @@ class TempME(nn.Module):
         return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(self.device, non_blocking=True)
 
     # ------------------------------------------------------------------ forward (explainer.py:174-201)
-    def score_device(self, nodes, eidx, t, cat, cut_time, edge_identity, group=None):
+    def score_device(self, nodes, eidx, t, cat, cut_time, edge_identity, group=None, out=None, peer_ptrs=None):
         """All arguments CUDA tensors: nodes i32 [B,W,6], eidx i32 [B,W,3], t f32 [B,W,3], cat u8 [B,W],
-        cut_time f32 [B], edge_identity f32 [B,W,3,3] -> scores f32 [B,W]."""
+        cut_time f32 [B], edge_identity f32 [B,W,3,3] -> scores f32 [B,W].  out: preallocated [B,W] result (e.g. this rank's segment of a
+        gathered buffer); peer_ptrs: device addresses of the same segment on up to 7 peer GPUs -- the kernel stores every score there too
+        (tm_encode_score_gather; tempme_b200.dist.ScoreExchange)."""
         B, W = nodes.shape[0], nodes.shape[1]
         group = int(group or self.batch_group or max(B, 1))
         blob = self.packed_weights()
@@ -183,8 +185,19 @@ class TempME(nn.Module):
         nws = lib().tm_encoder_workspace_floats(C.byref(self._desc), B, W, group)
         if self._ws is None or self._ws.numel() < nws:
             self._ws = torch.empty(max(nws, 1024), dtype=torch.float32, device=self.device)
-        scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
+        if out is None:
+            scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
+        else:
+            scores = out
+            if scores.dtype != torch.float32 or scores.numel() != B * W or not scores.is_contiguous() or scores.device != self.device:
+                raise ValueError("score_device: out must be a contiguous float32 [B, W] tensor on the explainer's device")
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if peer_ptrs:
+            arr = (C.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+            check(lib().tm_encode_score_gather(C.byref(self._desc), ptr(blob), B, W, group, ptr(nodes), ptr(eidx), ptr(t), ptr(cat),
+                                               ptr(cut_time), ptr(edge_identity), ptr(nf), nf.shape[0], ptr(ef), ef.shape[0],
+                                               ptr(self._ws), ptr(scores), arr, len(peer_ptrs), self.device.index, st), "tm_encode_score_gather")
+            return scores
         check(lib().tm_encode_score(C.byref(self._desc), ptr(blob), B, W, group, ptr(nodes), ptr(eidx), ptr(t), ptr(cat),
                                     ptr(cut_time), ptr(edge_identity), ptr(nf), nf.shape[0], ptr(ef), ef.shape[0],
                                     ptr(self._ws), ptr(scores), self.device.index, st), "tm_encode_score")

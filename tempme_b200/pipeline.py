@@ -46,7 +46,7 @@ class MotifPipeline:
         cut64 = lay(ts, ts, ts, np.float64)
         return roots, e, cut64
 
-    def run_device(self, roots, e, cut64, row_offset=0, want_walks=False, timers=None):
+    def run_device(self, roots, e, cut64, row_offset=0, want_walks=False, timers=None, out=None, peer_ptrs=None):
         """roots/e/cut64: [3Q] device tensors in the stage_queries layout; row_offset = global index of the first
         root row (3 * events before this shard).  Returns scores [3Q, W] in the same row order."""
         f, n, N2, W = self.finder, self.n, self.N2, self.W
@@ -64,7 +64,7 @@ class MotifPipeline:
         mark("sample_walks")
         eid = edge_identity_device(eidx)
         mark("edge_identity")
-        scores = self.explainer.score_device(nodes, eidx, t, cat, cut64.to(torch.float32), eid, group=max(g, 1))
+        scores = self.explainer.score_device(nodes, eidx, t, cat, cut64.to(torch.float32), eid, group=max(g, 1), out=out, peer_ptrs=peer_ptrs)
         mark("encode")
         return (scores, (nodes, eidx, t, cat, eid)) if want_walks else scores
 

@@ -38,7 +38,33 @@ def _worker(rank, world, port, ret):
         single = tm.MotifPipeline(f, m, 30, 1, group=100, seed=11)
         ref = single.run_host(*q)
         ok = int(np.array_equal(scores, ref) and torch.equal(hist, single.hist_null))
-        ret.put(ok)
+    # score gather fused into the scorer kernel (peer stores into symmetric memory) == NCCL all-gather of the same shards
+    from tempme_b200.dist import ScoreExchange
+    Q = 200                                                        # 2 batches per rank
+    mine = [np.asarray(a)[rank * Q:(rank + 1) * Q] for a in synth.make_queries(g, np.random.default_rng(4), 2 * Q)]
+    dq = pipe.stage_queries(*mine)
+    try:
+        x = ScoreExchange(3 * Q, pipe.W, dev)
+    except Exception as e:      # noqa: BLE001
+        x = None
+        print(f"[rank {rank}] symmetric memory unavailable: {type(e).__name__}: {e}", flush=True)
+    flag = torch.tensor([1.0 if x is not None else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if flag.item() > 0:
+        plain = pipe.run_device(*dq, row_offset=rank * 3 * Q)
+        want = torch.empty((world, 3 * Q, pipe.W), device=dev)
+        dist.all_gather_into_tensor(want, plain)
+        for rep in range(3):                                       # reuse of the buffer across steps, ordered by the all-reduce
+            x.gathered.fill_(float("nan"))
+            dist.all_reduce(flag)
+            got_local = pipe.run_device(*dq, row_offset=rank * 3 * Q, out=x.local, peer_ptrs=x.peer_ptrs)
+            dist.all_reduce(pipe.hist_null)
+            torch.cuda.synchronize()
+            ok &= int(got_local.data_ptr() == x.local.data_ptr() and torch.equal(x.gathered, want))
+    res = torch.tensor([ok, int(flag.item() > 0)], device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put((int(res[0].item()), int(res[1].item())))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,4 +84,7 @@ def test_two_gpu_sharding_matches_single_gpu():
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    assert ret.get(timeout=5) == 1
+    ok, fused = ret.get(timeout=5)
+    assert ok == 1
+    if not fused:
+        pytest.skip("sharding verified; symmetric memory unavailable on this box, fused score gather not exercised")

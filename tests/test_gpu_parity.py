@@ -632,3 +632,33 @@ def test_kl_loss_golden_and_oracle(tm, golden):
         prob = rng.random((B, W, 1)).astype(np.float32); cat = rng.integers(0, 12, (B, W, 1))
         v = m.kl_loss(prob, (None, None, None, cat, None), target=0.3)
         np.testing.assert_allclose(v.item(), enc.kl_loss(prob, cat, z["null_values"], 0.3, prior), rtol=1e-5, atol=1e-7)
+
+
+def test_score_gather_peer_stores_single_gpu(tm):
+    """tm_encode_score_gather: the scorer writes every score to `out` and to each peer segment (here: other buffers of the same GPU);
+    results identical to the plain call.  The two-GPU version over symmetric memory is tests/test_gpu_multi.py."""
+    rng = np.random.default_rng(31)
+    B, W, D, Ed, Nn, Ne = 77, 30, 32, 32, 120, 600
+    nfeat = rng.standard_normal((Nn, D)).astype(np.float32); efeat = rng.standard_normal((Ne, Ed)).astype(np.float32)
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "t", 40, 64, device="cuda:0", null_model={}).cuda().eval()
+    dev = torch.device("cuda:0")
+    nodes = torch.as_tensor(rng.integers(0, Nn, (B, W, 6)).astype(np.int32)).to(dev)
+    eidx = torch.as_tensor(rng.integers(0, Ne, (B, W, 3)).astype(np.int32)).to(dev)
+    t = torch.as_tensor(np.sort(rng.integers(1e8, 1.1e8, (B, W, 3)), -1).astype(np.float32)).to(dev)
+    cat = torch.as_tensor(rng.integers(0, 12, (B, W)).astype(np.uint8)).to(dev)
+    cut = (t[:, :, 2].max(1).values + 5).contiguous()
+    eid = torch.as_tensor(rng.integers(0, 4, (B, W, 3, 3)).astype(np.float32)).to(dev)
+    ref = m.score_device(nodes, eidx, t, cat, cut, eid, group=B)
+    world, rank = 4, 2
+    bufs = [torch.full((world, B, W), float("nan"), device=dev) for _ in range(world)]
+    from tempme_b200.dist import segment_offsets
+    peers = segment_offsets(B, W, world, rank, [b.data_ptr() for b in bufs])
+    assert len(peers) == world - 1
+    out = m.score_device(nodes, eidx, t, cat, cut, eid, group=B, out=bufs[rank][rank], peer_ptrs=peers)
+    torch.cuda.synchronize()
+    assert out.data_ptr() == bufs[rank][rank].data_ptr()
+    for b in bufs:
+        assert torch.equal(b[rank], ref)
+        assert torch.isnan(b[[r for r in range(world) if r != rank]]).all()
+    with pytest.raises(Exception):
+        m.score_device(nodes, eidx, t, cat, cut, eid, group=B, peer_ptrs=[bufs[0].data_ptr()] * 8)
