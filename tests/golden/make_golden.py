@@ -247,7 +247,7 @@ FWD_PARAMS = ["event_conv.lin_event", "event_conv.MLP.0", "event_conv.MLP.2", "a
               "attention.MLP.0", "attention.MLP.2", "attention.MLP.3", "MLP.0", "MLP.3", "MLP.5"]
 
 
-def gen_encoder(tag, walks5, edge_identity, cut_time, n_nodes, n_edges, D, Ed, seed, use_temporal=True, zero_node=False):
+def gen_encoder(tag, walks5, edge_identity, cut_time, n_nodes, n_edges, D, Ed, seed, use_temporal=True, zero_node=False, if_cat=True):
     import torch
     import models.explainer as rexp  # the reference's module
     rexp.get_null_distribution = lambda data_name: {k: 1.0 / 12 for k in range(1, 13)}  # skip the 8 s CSV pass
@@ -262,7 +262,7 @@ def gen_encoder(tag, walks5, edge_identity, cut_time, n_nodes, n_edges, D, Ed, s
         edge_raw_features = torch.nn.Embedding.from_pretrained(efeat, padding_idx=0, freeze=True)
 
     m = rexp.TempME(Base(), "tgn", "uslegis_sampled", out_dim=40, hid_dim=64, device=torch.device("cpu"),
-                    use_temporal_guidance=use_temporal)
+                    use_temporal_guidance=use_temporal, if_cat_feature=if_cat)
     with torch.no_grad():  # move the trainable phase off zero so the +phase step is exercised
         m.time_encoder.phase.copy_(0.1 * torch.randn(D))
     m.eval()
@@ -274,7 +274,7 @@ def gen_encoder(tag, walks5, edge_identity, cut_time, n_nodes, n_edges, D, Ed, s
     out.update(node_feat=nfeat.numpy(), edge_feat=efeat.numpy(), w_nodes=walks5[0].astype(np.int32),
                w_eidx=walks5[1].astype(np.int32), w_t=walks5[2].astype(np.float32), w_cat=walks5[3].astype(np.int8),
                cut_time=cut_time, edge_identity=edge_identity.astype(np.float32), score=score,
-               use_temporal=int(use_temporal))
+               use_temporal=int(use_temporal), if_cat=int(if_cat))
     np.savez_compressed(os.path.join(HERE, f"encoder_{tag}.npz"), **out)
 
 
@@ -369,6 +369,18 @@ def gen_enhance_all():
     gen_enhance("d32", ws[0][0], ws[1][0], ws[0][1], ws[1][1], big["ts"][big["q"][:Bq]], int(big["n_nodes"]), len(big["eidx"]) + 1, 32, 32, seed=5)
 
 
+def gen_encoder_nocat():
+    """TempME(if_cat_feature=False): MLP over the attention output alone (mlp_dim = hid_dim); `python tests/golden/make_golden.py nocat`."""
+    big = dict(np.load(os.path.join(HERE, "rand_bigts.npz")))
+    Bq = 12
+    wn, we, wt, wa = (big[f"src_w_{k}"][:Bq] for k in ("nodes", "eidx", "t", "anony"))
+    allw = np.concatenate([x.astype(np.float64) for x in (wn, we, wt, wa)], axis=-1)
+    new = marginal(allw, allw, allw)[0]
+    walks5 = (wn.astype(np.int64), we.astype(np.int64), wt.astype(np.float64), new[:, :, 12:13].astype(np.int64), new[:, :, 13:14])
+    gen_encoder("d32_nocat", walks5, new_edge_info(we.astype(int)), big["ts"][big["q"][:Bq]], big["n_nodes"], len(big["eidx"]) + 1, 32, 32, seed=6,
+                if_cat=False)
+
+
 def gen_kl_all():
     """TempME.kl_loss (reference models/explainer.py:432-453) on the classes of the committed walk fixtures and seeded scores (with
     exact 0 / 1 entries for the clamp), for both priors and two targets.  The null model is non-uniform, in the reference's dict order."""
@@ -427,6 +439,9 @@ def gen_edge_imp_all():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "edgeimp":
         gen_edge_imp_all()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "nocat":
+        gen_encoder_nocat()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "kl":
         gen_kl_all()

@@ -326,14 +326,14 @@ class _Base:
 def explainer_from_golden(tm, g):
     base = _Base(g["node_feat"], g["edge_feat"])
     m = tm.TempME(base, "tgn", "unit", out_dim=40, hid_dim=64, device="cuda", use_temporal_guidance=bool(g["use_temporal"]),
-                  null_model={k: 1 / 12 for k in range(1, 13)})
+                  if_cat_feature=bool(g["if_cat"]) if "if_cat" in g else True, null_model={k: 1 / 12 for k in range(1, 13)})
     sd = {k[2:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("p:")}
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected                       # every reference parameter name exists in our module
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("tag", ["d172", "d32", "d32_plainattn"])
+@pytest.mark.parametrize("tag", ["d172", "d32", "d32_plainattn", "d32_nocat"])
 def test_encoder_golden(tm, golden, tag):
     g = golden("encoder_" + tag)
     m = explainer_from_golden(tm, g)
@@ -345,9 +345,11 @@ def test_encoder_golden(tm, golden, tag):
     np.testing.assert_allclose(out.cpu().numpy(), g["score"], rtol=1e-5, atol=0)
 
 
-@pytest.mark.parametrize("D,Ed", [(32, 32), (172, 172), (100, 7)])
-def test_encoder_vs_oracle_larger(tm, orc, D, Ed):
-    """Scores for many roots in reference batches of 100 (ragged last batch) vs the numpy oracle."""
+@pytest.mark.parametrize("D,Ed,if_cat,use_temporal", [(32, 32, True, True), (172, 172, True, True), (100, 7, True, True),
+                                                      (32, 32, False, False), (172, 1, False, True), (64, 32, False, True)])
+def test_encoder_vs_oracle_larger(tm, orc, D, Ed, if_cat, use_temporal):
+    """Scores for many roots in reference batches of 100 (ragged last batch) vs the numpy oracle; with and without the category one-hot
+    (if_cat_feature, explainer.py:122-126) and the temporal weighting (use_temporal_guidance)."""
     from oracle import encoder as orc_enc
     rng = np.random.default_rng(D)
     src, dst, eidx, ts = synth_graph(7, 400, 30000, 10 ** 6)
@@ -360,16 +362,17 @@ def test_encoder_vs_oracle_larger(tm, orc, D, Ed):
     nfeat = rng.standard_normal((400, D)).astype(np.float32); efeat = rng.standard_normal((30001, Ed)).astype(np.float32)
     nfeat[0] = 0; efeat[0] = 0
     torch.manual_seed(D)
-    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, 64, device="cuda", null_model={}).cuda().eval()
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, 64, device="cuda", null_model={}, if_cat_feature=if_cat,
+                  use_temporal_guidance=use_temporal).cuda().eval()
     with torch.no_grad():
         m.time_encoder.phase.normal_(0, 0.1)
     cut = torch.as_tensor(ts[q].astype(np.float32)).cuda()
-    scores = m.score_device(nodes, we, wt, cat, cut, eid, group=100).cpu().numpy()
+    scores = m.score_device(nodes, we, wt, cat if if_cat else None, cut, eid, group=100).cpu().numpy()
     p = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
     for s in range(0, len(q), 100):
         sl = slice(s, s + 100)
         walks = (nodes[sl].cpu().numpy(), we[sl].cpu().numpy(), wt[sl].cpu().numpy(), cat[sl].cpu().numpy(), None)
-        ref = orc_enc.forward(p, nfeat, efeat, walks, ts[q][sl], eid[sl].cpu().numpy())
+        ref = orc_enc.forward(p, nfeat, efeat, walks, ts[q][sl], eid[sl].cpu().numpy(), if_cat=if_cat, use_temporal=use_temporal)
         np.testing.assert_allclose(scores[sl], ref[..., 0], rtol=1e-5, atol=0)
 
 

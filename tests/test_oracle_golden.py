@@ -150,13 +150,13 @@ def test_null_model_distribution(golden):
     assert np.array_equal(hist / (500 * 3 * n), g["dist"])
 
 
-@pytest.mark.parametrize("tag", ["d172", "d32", "d32_plainattn"])
+@pytest.mark.parametrize("tag", ["d172", "d32", "d32_plainattn", "d32_nocat"])
 def test_encoder_oracle(golden, tag):
     g = golden("encoder_" + tag)
     p = {k[2:]: v for k, v in g.items() if k.startswith("p:")}
     walks = (g["w_nodes"], g["w_eidx"], g["w_t"], g["w_cat"], None)
     out = orc_enc.forward(p, g["node_feat"], g["edge_feat"], walks, g["cut_time"], g["edge_identity"],
-                          use_temporal=bool(g["use_temporal"]))
+                          use_temporal=bool(g["use_temporal"]), if_cat=bool(g["if_cat"]) if "if_cat" in g else True)
     assert out.shape == g["score"].shape and out.dtype == np.float32
     np.testing.assert_allclose(out, g["score"], rtol=1e-5, atol=0)   # the north_star tolerance
     if tag == "d172":
