@@ -132,7 +132,7 @@ int tm_edge_identity(int64_t B, int64_t W, const int32_t *d_eidx, float *d_out, 
 typedef struct {
     int32_t node_dim;     /* D  = base.n_feat_th.shape[1] = time_dim   explainer.py:107-109 */
     int32_t edge_dim;     /* Ed = base.e_feat_th.shape[1]              explainer.py:108 */
-    int32_t hid_dim;      /* H                                          explainer.py:111 */
+    int32_t hid_dim;      /* H: 64 or 32 (temp_exp_main.py:40, enhance_main.py:66)   explainer.py:111 */
     int32_t use_temporal; /* TemporalAwareAttention (1) or Attention (0) explainer.py:121 */
     int32_t if_cat;       /* one-hot category features                 explainer.py:116,195-197 */
 } tm_encoder_desc;

@@ -332,7 +332,7 @@ static int encode_score_impl(const tm_encoder_desc *desc, const float *d_blob, i
         return TM_ERR_ARG;
     }
     if (desc->if_cat && !d_cat && B > 0) { set_error("tm_encode_score: if_cat needs d_cat"); return TM_ERR_ARG; }
-    if (desc->hid_dim != 64) { set_error("tm_encode_score: hid_dim %d unsupported (only 64, the reference default)", desc->hid_dim); return TM_ERR_UNSUPPORTED; }
+    if (desc->hid_dim != 64 && desc->hid_dim != 32) { set_error("tm_encode_score: hid_dim %d unsupported (64 and 32, the reference's defaults)", desc->hid_dim); return TM_ERR_UNSUPPORTED; }
     if (desc->node_dim < 1 || desc->node_dim > 256 || desc->edge_dim < 1 || desc->edge_dim > 1024) { set_error("tm_encode_score: node_dim must be in [1,256], edge_dim in [1,1024]"); return TM_ERR_UNSUPPORTED; }
     if (B == 0) return TM_OK;
     TM_CUDA(cudaSetDevice(device));
@@ -344,7 +344,7 @@ static int encode_score_impl(const tm_encoder_desc *desc, const float *d_blob, i
         TM_LAUNCH_CHECK();
     }
     const char *which = getenv("TEMPME_ENCODER");     // "ffma" selects the fp32 CUDA-core kernel (A/B validation); default: tcgen05
-    if (d_y || n_peers > 0 || !which || strcmp(which, "ffma") != 0) {
+    if (d_y || n_peers > 0 || desc->hid_dim != 64 || !which || strcmp(which, "ffma") != 0) {
         const int64_t n_std = (std::max<int64_t>(32, n_groups) + 31) & ~(int64_t)31;
         return tc_encode_score(*desc, d_blob + L.total, B, W, group, d_nodes, d_eidx, d_t, d_cat, d_cut_time, d_edge_identity, d_node_feat,
                                n_node_rows, d_edge_feat, n_edge_rows, d_workspace, d_workspace + n_std, d_scores, d_y, peer_scores, n_peers, device, st);

@@ -424,14 +424,16 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     // m3one: MLP.3 in one round -- its two or three K chunks from A, A2 and a third buffer behind M0; M1 then lands over M0's first
     // chunks (they have been read into the A buffers before the MMAs are issued)
     const bool m3one = (a.dual & 4) != 0;
-    const int colU = 0, colY = H2, colM0 = dq ? H : 0, colM1 = m3one ? H : dq ? 0 : H2, colA3 = H + L.M16;
+    // (hid_dim 32: U [0,64) | Y [64,96); M0 then starts at column 64, clear of the second A buffer [0,64))
+    const int colU = 0, colY = H2, colM0 = dq ? max(H, 2 * kKC) : 0, colM1 = m3one ? colM0 : dq ? 0 : H2, colA3 = colM0 + L.M16;
+    const int nsl = H2 / kKC;                              // h slabs per walk position
     const int64_t n_m = a.n_motifs, n_tiles = (n_m + 127) / 128;
     const int bytes_e = (int)chunk_floats(L.evt) * 4, bytes_g = (int)chunk_floats(L.g0) * 4;
     const int bytes_sp = (int)chunk_floats(L.sp) * 4, bytes_q = (int)chunk_floats(L.q) * 4, bytes_r = (int)chunk_floats(L.r) * 4, bytes_m3 = (int)chunk_floats(L.m3) * 4;
     if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, L.evt.w, min(de ? 2 : 1, L.evt.nch) * bytes_e);
     const bool ed_vec = (Ed & 3) == 0, d_vec = (D & 3) == 0;
-    float *Fs = a.F + (int64_t)blockIdx.x * 12 * kSlabFloats;           // this CTA's h slabs: [position][column chunk][piece k/4][128 rows][4]
-    const float *F0 = Fs, *F1 = Fs + 4 * kSlabFloats, *F2 = Fs + 8 * kSlabFloats;
+    float *Fs = a.F + (int64_t)blockIdx.x * 3 * nsl * kSlabFloats;      // this CTA's h slabs: [position][column chunk][piece k/4][128 rows][4]
+    const float *F0 = Fs, *F1 = Fs + nsl * kSlabFloats, *F2 = Fs + 2 * nsl * kSlabFloats;
     // this thread's CW columns [kb, kb+CW) of row `row` of a [128 x 32] slab (coalesced 16-byte pieces)
     auto ldw = [&](const float *slab, float *v) {
 #pragma unroll
@@ -629,10 +631,10 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 }
             }
             // ---- h_pos = relu(MLP.0 + bias): thread part p owns columns [4 CW p, 4 CW (p + 1)) of [Zs | Zt]
-            for (int c0 = 4 * CW * prt; c0 < 4 * CW * (prt + 1); c0 += 16) {
+            for (int c0 = (H2 / kParts) * prt; c0 < (H2 / kParts) * (prt + 1); c0 += 16) {
                 float v[16];
                 tc::tmem_ld16(tmem + lane_base + colZ + c0, v);
-                float *fc = Fs + (pos * 4 + (c0 >> 5)) * kSlabFloats + ((c0 & 31) >> 2) * 512 + row * 4;
+                float *fc = Fs + (pos * nsl + (c0 >> 5)) * kSlabFloats + ((c0 & 31) >> 2) * 512 + row * 4;
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
                     const float4 bb = lds4(cstE + L.e_g0b + (c0 & (H - 1)) + i);
@@ -725,7 +727,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 if (c + 2 < nchS) { ldw(F0 + (c + 2) * kSlabFloats, n0); ldw(F1 + (c + 2) * kSlabFloats, n1); }
                 put_mix(m0, m1, true);
                 const bool last = c + 2 >= nchS;
-                tc_mma_round<TS>(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 2) * chunk_floats(L.q), last ? 2 * bytes_r : 2 * bytes_q, NoMid(),
+                tc_mma_round<TS>(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 2) * chunk_floats(L.q), last ? min(2, L.r.nch) * bytes_r : 2 * bytes_q, NoMid(),
                                  Dual{kDualK, kKC, 0, 0, 0});
             }
         } else {
@@ -759,9 +761,11 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             }
             af.commit(x, lane_base, kb, second);
         };
-        if (dq) {                                               // both K chunks in one round; M0 lands at [H, H + M16) (Y has been read completely)
-            put_y(0, false); put_y(1, true);
-            tc_mma_round<TS>(x, L.M16, kKC, colM0, false, L.m3.w, (m3one ? L.m3.nch : 1) * bytes_m3, NoMid(), Dual{kDualK, kKC, 0, 0, 0});
+        if (dq) {                                               // both K chunks in one round; M0 lands at colM0 (Y has been read completely)
+            put_y(0, false);
+            if (L.r.nch > 1) put_y(1, true);
+            tc_mma_round<TS>(x, L.M16, kKC, colM0, false, L.m3.w, (m3one ? L.m3.nch : 1) * bytes_m3, NoMid(),
+                             Dual{L.r.nch > 1 ? kDualK : kSingle, L.r.nch > 1 ? kKC : 0, 0, 0, 0});
         } else {
             for (int c = 0; c < L.r.nch; ++c) {
                 put_y(c, false);
@@ -872,7 +876,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
                     float *y_out, float *const *peer_scores, int n_peers, int device, cudaStream_t st) {
     const TcLayout L = make_tc_layout(d);
     if (n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !peer_scores)) { set_error("tc_encode_score: at most %d peer outputs", kMaxPeers); return TM_ERR_ARG; }
-    if (L.H != 64) { set_error("tc_encode_score: hid_dim must be 64"); return TM_ERR_UNSUPPORTED; }
+    if (L.H != 64 && L.H != 32) { set_error("tc_encode_score: hid_dim must be 64 or 32 (the defaults of temp_exp_main.py / enhance_main.py)"); return TM_ERR_UNSUPPORTED; }
     if (device < 0 || device >= 64) { set_error("tc_encode_score: device index out of range"); return TM_ERR_UNSUPPORTED; }
     const int H = L.H;
     const bool alias_e = L.g0.nch == 1 && L.D16 <= H;
@@ -891,7 +895,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     if (dual_e) bb = std::max(bb, (int64_t)std::min(2, L.evt.nch) * chunk_floats(L.evt) * 4);        // lin_event chunks arrive in pairs
     if (dual) bb = std::max(bb, 2 * std::max(chunk_floats(L.q), chunk_floats(L.r)) * 4);             // so do Q's and R's
     // MLP.3 in one round: all of its (two or three) K chunks in the weight buffer; the third A buffer sits between M0 and the A buffers
-    const bool m3one = dual && !getenv("TEMPME_TC_NO_M3ONE") && L.m3.nch <= 3 && (L.m3.nch < 3 || (L.m3.K8 - 2 * kKC <= 16 && H + L.M16 + 3 * kKC / 2 <= 3 * H));
+    const bool m3one = dual && !getenv("TEMPME_TC_NO_M3ONE") && L.m3.nch <= 3 && (L.m3.nch < 3 || (L.m3.K8 - 2 * kKC <= 16 && H == 64 && H + L.M16 + 3 * kKC / 2 <= 3 * H));
     if (m3one) bb = std::max(bb, (int64_t)L.m3.nch * chunk_floats(L.m3) * 4);
     // node-feature rows are gathered by bulk TMA into a staging area that may overlap the tail of the weight buffer: rows
     // are in flight only while lin_event / MLP.0 / MLP.3 chunks are being loaded, so it starts behind the largest of those
@@ -919,7 +923,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const char *cw_env = getenv("TEMPME_TC_CW");                 // columns per thread per K chunk: 16 (256 threads, default) or 8 (512 threads)
-    const int cw = cw_env && atoi(cw_env) == 8 ? 8 : 16;
+    const int cw = cw_env && atoi(cw_env) == 8 && H == 64 ? 8 : 16;
     const int kv = (cw == 16) + 2 * ts;
     static size_t static_smem[4] = {0, 0, 0, 0};
     if (!static_smem[0])
@@ -952,7 +956,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     }
     const int64_t tiles = (a.n_motifs + 127) / 128, cap = (int64_t)sms * ctas;
     const unsigned grid = (unsigned)std::min(tiles, cap);
-    a.tile_counter = reinterpret_cast<unsigned long long *>(F + (int64_t)grid * 12 * kSlabFloats);          // behind the h scratch (the workspace holds twice as much)
+    a.tile_counter = reinterpret_cast<unsigned long long *>(F + (int64_t)grid * 3 * (2 * H / kKC) * kSlabFloats);          // behind the h scratch (the workspace holds twice as much)
     TM_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), st));
     if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] score kernel: %u CTAs (%d per SM), smem %zu B (needs %zu), %u TMEM columns, %lld tiles\n", grid, ctas, smem, need, cols, (long long)tiles);
     cudaEvent_t *pe = nullptr;

@@ -247,7 +247,7 @@ FWD_PARAMS = ["event_conv.lin_event", "event_conv.MLP.0", "event_conv.MLP.2", "a
               "attention.MLP.0", "attention.MLP.2", "attention.MLP.3", "MLP.0", "MLP.3", "MLP.5"]
 
 
-def gen_encoder(tag, walks5, edge_identity, cut_time, n_nodes, n_edges, D, Ed, seed, use_temporal=True, zero_node=False, if_cat=True):
+def gen_encoder(tag, walks5, edge_identity, cut_time, n_nodes, n_edges, D, Ed, seed, use_temporal=True, zero_node=False, if_cat=True, hid=64):
     import torch
     import models.explainer as rexp  # the reference's module
     rexp.get_null_distribution = lambda data_name: {k: 1.0 / 12 for k in range(1, 13)}  # skip the 8 s CSV pass
@@ -261,7 +261,7 @@ def gen_encoder(tag, walks5, edge_identity, cut_time, n_nodes, n_edges, D, Ed, s
         node_raw_features = torch.nn.Embedding.from_pretrained(nfeat, padding_idx=0, freeze=True)
         edge_raw_features = torch.nn.Embedding.from_pretrained(efeat, padding_idx=0, freeze=True)
 
-    m = rexp.TempME(Base(), "tgn", "uslegis_sampled", out_dim=40, hid_dim=64, device=torch.device("cpu"),
+    m = rexp.TempME(Base(), "tgn", "uslegis_sampled", out_dim=40, hid_dim=hid, device=torch.device("cpu"),
                     use_temporal_guidance=use_temporal, if_cat_feature=if_cat)
     with torch.no_grad():  # move the trainable phase off zero so the +phase step is exercised
         m.time_encoder.phase.copy_(0.1 * torch.randn(D))
@@ -274,7 +274,7 @@ def gen_encoder(tag, walks5, edge_identity, cut_time, n_nodes, n_edges, D, Ed, s
     out.update(node_feat=nfeat.numpy(), edge_feat=efeat.numpy(), w_nodes=walks5[0].astype(np.int32),
                w_eidx=walks5[1].astype(np.int32), w_t=walks5[2].astype(np.float32), w_cat=walks5[3].astype(np.int8),
                cut_time=cut_time, edge_identity=edge_identity.astype(np.float32), score=score,
-               use_temporal=int(use_temporal), if_cat=int(if_cat))
+               use_temporal=int(use_temporal), if_cat=int(if_cat), hid_dim=int(hid))
     np.savez_compressed(os.path.join(HERE, f"encoder_{tag}.npz"), **out)
 
 
@@ -379,6 +379,8 @@ def gen_encoder_nocat():
     walks5 = (wn.astype(np.int64), we.astype(np.int64), wt.astype(np.float64), new[:, :, 12:13].astype(np.int64), new[:, :, 13:14])
     gen_encoder("d32_nocat", walks5, new_edge_info(we.astype(int)), big["ts"][big["q"][:Bq]], big["n_nodes"], len(big["eidx"]) + 1, 32, 32, seed=6,
                 if_cat=False)
+    # enhance_main.py's defaults: hid_dim = 32 (enhance_main.py:65-66)
+    gen_encoder("d32_hid32", walks5, new_edge_info(we.astype(int)), big["ts"][big["q"][:Bq]], big["n_nodes"], len(big["eidx"]) + 1, 32, 32, seed=7, hid=32)
 
 
 def gen_kl_all():

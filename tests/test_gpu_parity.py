@@ -325,7 +325,7 @@ class _Base:
 
 def explainer_from_golden(tm, g):
     base = _Base(g["node_feat"], g["edge_feat"])
-    m = tm.TempME(base, "tgn", "unit", out_dim=40, hid_dim=64, device="cuda", use_temporal_guidance=bool(g["use_temporal"]),
+    m = tm.TempME(base, "tgn", "unit", out_dim=40, hid_dim=int(g["hid_dim"]) if "hid_dim" in g else 64, device="cuda", use_temporal_guidance=bool(g["use_temporal"]),
                   if_cat_feature=bool(g["if_cat"]) if "if_cat" in g else True, null_model={k: 1 / 12 for k in range(1, 13)})
     sd = {k[2:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("p:")}
     missing, unexpected = m.load_state_dict(sd, strict=False)
@@ -333,7 +333,7 @@ def explainer_from_golden(tm, g):
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("tag", ["d172", "d32", "d32_plainattn", "d32_nocat"])
+@pytest.mark.parametrize("tag", ["d172", "d32", "d32_plainattn", "d32_nocat", "d32_hid32"])
 def test_encoder_golden(tm, golden, tag):
     g = golden("encoder_" + tag)
     m = explainer_from_golden(tm, g)
@@ -345,9 +345,11 @@ def test_encoder_golden(tm, golden, tag):
     np.testing.assert_allclose(out.cpu().numpy(), g["score"], rtol=1e-5, atol=0)
 
 
-@pytest.mark.parametrize("D,Ed,if_cat,use_temporal", [(32, 32, True, True), (172, 172, True, True), (100, 7, True, True),
-                                                      (32, 32, False, False), (172, 1, False, True), (64, 32, False, True)])
-def test_encoder_vs_oracle_larger(tm, orc, D, Ed, if_cat, use_temporal):
+@pytest.mark.parametrize("D,Ed,if_cat,use_temporal,hid", [(32, 32, True, True, 64), (172, 172, True, True, 64), (100, 7, True, True, 64),
+                                                          (32, 32, False, False, 64), (172, 1, False, True, 64), (64, 32, False, True, 64),
+                                                          (32, 32, True, True, 32), (172, 172, True, True, 32), (100, 7, False, True, 32),
+                                                          (64, 4, True, False, 32)])
+def test_encoder_vs_oracle_larger(tm, orc, D, Ed, if_cat, use_temporal, hid):
     """Scores for many roots in reference batches of 100 (ragged last batch) vs the numpy oracle; with and without the category one-hot
     (if_cat_feature, explainer.py:122-126) and the temporal weighting (use_temporal_guidance)."""
     from oracle import encoder as orc_enc
@@ -362,7 +364,7 @@ def test_encoder_vs_oracle_larger(tm, orc, D, Ed, if_cat, use_temporal):
     nfeat = rng.standard_normal((400, D)).astype(np.float32); efeat = rng.standard_normal((30001, Ed)).astype(np.float32)
     nfeat[0] = 0; efeat[0] = 0
     torch.manual_seed(D)
-    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, 64, device="cuda", null_model={}, if_cat_feature=if_cat,
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, hid, device="cuda", null_model={}, if_cat_feature=if_cat,
                   use_temporal_guidance=use_temporal).cuda().eval()
     with torch.no_grad():
         m.time_encoder.phase.normal_(0, 0.1)
@@ -557,14 +559,15 @@ def test_enhance_path_golden(tm, golden):
     np.testing.assert_allclose(neg.cpu().numpy(), z["neg"], rtol=1e-4, atol=1e-4)
 
 
-def test_enhance_walks_vs_oracle_larger(tm, orc):
+@pytest.mark.parametrize("hid", [64, 32])      # 32: enhance_main.py's default (--hid_dim, enhance_main.py:66)
+def test_enhance_walks_vs_oracle_larger(tm, orc, hid):
     """Seeded inputs at several hundred roots against oracle/encoder.enhance_predict_walks (padding nodes, ragged degrees)."""
     from oracle import encoder as enc
     rng = np.random.default_rng(21)
     B, W, D, Ed, Nn, Ne = 300, 30, 32, 32, 150, 900
     nfeat = rng.standard_normal((Nn, D)).astype(np.float32); efeat = rng.standard_normal((Ne, Ed)).astype(np.float32)
     nfeat[0] = 0; efeat[0] = 0
-    m = tm.TempME(_Base(nfeat, efeat), "tgn", "t", 40, 64, device="cuda:0", null_model={}).cuda().eval()
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "t", 40, hid, device="cuda:0", null_model={}).cuda().eval()
     m.node_degree = torch.as_tensor(rng.integers(1, 80, Nn).astype(np.float32)).cuda()
     p = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
     nodes = rng.integers(0, Nn, (B, W, 6)); nodes[rng.random((B, W, 6)) < 0.15] = 0

@@ -150,7 +150,7 @@ def test_null_model_distribution(golden):
     assert np.array_equal(hist / (500 * 3 * n), g["dist"])
 
 
-@pytest.mark.parametrize("tag", ["d172", "d32", "d32_plainattn", "d32_nocat"])
+@pytest.mark.parametrize("tag", ["d172", "d32", "d32_plainattn", "d32_nocat", "d32_hid32"])
 def test_encoder_oracle(golden, tag):
     g = golden("encoder_" + tag)
     p = {k[2:]: v for k, v in g.items() if k.startswith("p:")}

@@ -13,6 +13,7 @@ from bench import random_params
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg2"); ap.add_argument("--events", type=int, default=16000)
 ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--hid", type=int, default=64, help="hid_dim: 64 (temp_exp_main.py) or 32 (enhance_main.py's default)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0); torch.cuda.set_device(0)
 sh = synth.SHAPES[args.workload]; n, N2, D, Ed = sh["n"], sh["N2"], sh["D"], sh["Ed"]; W = n * N2
@@ -25,8 +26,9 @@ class Base:
     node_raw_features = torch.nn.Embedding.from_pretrained(n_feat_th, padding_idx=0, freeze=True)
     edge_raw_features = torch.nn.Embedding.from_pretrained(e_feat_th, padding_idx=0, freeze=True)
 
-model = tm.TempME(Base(), "tgn", args.workload, 40, 64, device=dev, null_model={}, batch_group=100).to(dev).eval()
-model.load_state_dict({k: torch.as_tensor(v) for k, v in random_params(D, Ed).items()}, strict=False)
+model = tm.TempME(Base(), "tgn", args.workload, 40, args.hid, device=dev, null_model={}, batch_group=100).to(dev).eval()
+if args.hid == 64:
+    model.load_state_dict({k: torch.as_tensor(v) for k, v in random_params(D, Ed).items()}, strict=False)
 model.node_degree = torch.as_tensor(np.bincount(np.concatenate([graph["src"], graph["dst"]]), minlength=graph["n_nodes"]).astype(np.float32)).to(dev)
 pipe = tm.MotifPipeline(finder, model, n, N2, group=100, seed=5)
 Q = args.events // 100 * 100
@@ -46,5 +48,5 @@ for it in range(args.warmup + args.steps):
         ms += a.elapsed_time(b)
 ms /= args.steps
 print(json.dumps({"metric": "enhance_predict_walks_motifs_per_sec", "value": R * W / (ms * 1e-3), "unit": "motifs/s", "roots_per_sec": R / (ms * 1e-3),
-                  "config": {"workload": args.workload, "roots": R, "walks_per_root": W}, "ms": ms, "launches": tm.launch_count(),
+                  "config": {"workload": args.workload, "roots": R, "walks_per_root": W, "hid_dim": args.hid}, "ms": ms, "launches": tm.launch_count(),
                   "emb_mean_abs": float(emb.abs().mean())}))
