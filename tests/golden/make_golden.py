@@ -316,7 +316,7 @@ def gen_edge_imp(tag, walks5, edge_identity, cut_time, subgraph, n_nodes, n_edge
     np.savez_compressed(os.path.join(HERE, f"edgeimp_{tag}.npz"), **out)
 
 
-def gen_enhance(tag, walks_src, walks_tgt, ei_src, ei_tgt, cut_time, n_nodes, n_edges, D, Ed, seed):
+def gen_enhance(tag, walks_src, walks_tgt, ei_src, ei_tgt, cut_time, n_nodes, n_edges, D, Ed, seed, hid=64, out_dim=40):
     """enhance_predict_walks / enhance_predict_agg (reference models/explainer.py:203-306) in eval mode: attention output per walk,
     soft walk-importance weights (batch-global statistics, node_degree gather), weighted sum over the walks, category counts,
     affinity score of the (src, tgt) and (src, bgd) pairs."""
@@ -332,7 +332,7 @@ def gen_enhance(tag, walks_src, walks_tgt, ei_src, ei_tgt, cut_time, n_nodes, n_
         node_raw_features = torch.nn.Embedding.from_pretrained(nfeat, padding_idx=0, freeze=True)
         edge_raw_features = torch.nn.Embedding.from_pretrained(efeat, padding_idx=0, freeze=True)
 
-    m = rexp.TempME(Base(), "tgn", "uslegis_sampled", out_dim=40, hid_dim=64, device=torch.device("cpu"))
+    m = rexp.TempME(Base(), "tgn", "uslegis_sampled", out_dim=out_dim, hid_dim=hid, device=torch.device("cpu"))
     with torch.no_grad():
         m.time_encoder.phase.copy_(0.1 * torch.randn(D))
         m.node_degree = torch.randint(1, 60, (n_nodes,)).float()
@@ -352,7 +352,7 @@ def gen_enhance(tag, walks_src, walks_tgt, ei_src, ei_tgt, cut_time, n_nodes, n_
                     f"{pre}_cat": w[3].astype(np.int8), f"{pre}_ei": ei.astype(np.float32)})
     out.update(node_feat=nfeat.numpy(), edge_feat=efeat.numpy(), node_degree=m.node_degree.numpy(), cut_time=cut_time,
                src_gat=src_gat.numpy(), tgt_gat=tgt_gat.numpy(), bgd_gat=bgd_gat.numpy(),
-               emb_src=emb_src.numpy(), emb_tgt=emb_tgt.numpy(), w_src=w_src.numpy(), pos=pos.numpy(), neg=neg.numpy())
+               emb_src=emb_src.numpy(), emb_tgt=emb_tgt.numpy(), w_src=w_src.numpy(), pos=pos.numpy(), neg=neg.numpy(), hid_dim=hid, out_dim=out_dim)
     np.savez_compressed(os.path.join(HERE, f"enhance_{tag}.npz"), **out)
 
 
@@ -367,6 +367,9 @@ def gen_enhance_all():
         ws.append(((wn.astype(np.int64), we.astype(np.int64), wt.astype(np.float64), new[:, :, 12:13].astype(np.int64), new[:, :, 13:14]),
                    new_edge_info(we.astype(int))))
     gen_enhance("d32", ws[0][0], ws[1][0], ws[0][1], ws[1][1], big["ts"][big["q"][:Bq]], int(big["n_nodes"]), len(big["eidx"]) + 1, 32, 32, seed=5)
+    # enhance_main.py's own defaults: --hid_dim 32 --out_dim 32 (enhance_main.py:65-66)
+    gen_enhance("d32_hid32", ws[0][0], ws[1][0], ws[0][1], ws[1][1], big["ts"][big["q"][:Bq]], int(big["n_nodes"]), len(big["eidx"]) + 1, 32, 32, seed=8,
+                hid=32, out_dim=32)
 
 
 def gen_encoder_nocat():

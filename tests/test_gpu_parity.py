@@ -542,9 +542,11 @@ def test_pipeline_explain_matches_oracle(tm, orc):
 # ---------------------------------------------------------------------------------------------
 # enhance path: compute_walk_importance, enhance_predict_walks, enhance_predict_agg, eval mode
 # ---------------------------------------------------------------------------------------------
-def test_enhance_path_golden(tm, golden):
-    z = golden("enhance_d32")
-    m = tm.TempME(_Base(z["node_feat"], z["edge_feat"]), "tgn", "t", 40, 64, device="cuda:0", null_model={}).cuda().eval()
+@pytest.mark.parametrize("tag", ["d32", "d32_hid32"])      # hid32: enhance_main.py's own defaults (--hid_dim 32 --out_dim 32)
+def test_enhance_path_golden(tm, golden, tag):
+    z = golden("enhance_" + tag)
+    hid, od = (int(z["hid_dim"]), int(z["out_dim"])) if "hid_dim" in z else (64, 40)
+    m = tm.TempME(_Base(z["node_feat"], z["edge_feat"]), "tgn", "t", od, hid, device="cuda:0", null_model={}).cuda().eval()
     missing, unexpected = m.load_state_dict({k[2:]: torch.as_tensor(z[k]) for k in z if k.startswith("p:")}, strict=False)
     assert not unexpected
     m.node_degree = torch.as_tensor(z["node_degree"]).cuda()

@@ -182,10 +182,11 @@ def test_edge_importance_oracle(golden, tag):
         np.testing.assert_allclose(i1, z[f"{key}_imp1"], rtol=1e-5, atol=1e-7)
 
 
-def test_enhance_path_oracle(golden):
+@pytest.mark.parametrize("tag", ["d32", "d32_hid32"])      # hid32: enhance_main.py's own defaults (--hid_dim 32 --out_dim 32)
+def test_enhance_path_oracle(golden, tag):
     """oracle.encoder enhance path == the reference's compute_walk_importance / enhance_predict_walks / enhance_predict_agg (eval)."""
     from oracle import encoder as enc
-    z = golden("enhance_d32")
+    z = golden("enhance_" + tag)
     p = {k[2:]: z[k] for k in z if k.startswith("p:")}
     ws = {pre: (z[f"{pre}_nodes"], z[f"{pre}_eidx"], z[f"{pre}_t"], z[f"{pre}_cat"], None) for pre in ("src", "tgt")}
     w = enc.walk_importance(ws["src"][2], ws["src"][0], z["cut_time"], z["node_degree"])
