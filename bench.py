@@ -179,10 +179,25 @@ class ClockSampler:
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.nv = pynvml
             self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
-            self.t = threading.Thread(target=self._loop, daemon=True)
-            self.t.start()
+            names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0)),
+                     "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                     "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                     "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+            self.names = names
+            self.get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+            # An NVML query takes a driver lock that kernel launches also need.  It normally returns in microseconds, but with tens of GB
+            # mapped (cfg5) one query takes ~20 ms and a 2 ms background sampler stalls a launch of every step.  Probe once while the GPU is
+            # idle: if the query is slow, sample on the main thread right after each timed step instead (`slow`, sample_now()).
+            self._sample(record=False)                  # the first query pays NVML's lazy initialisation
+            t0 = time.perf_counter()
+            self._sample(record=False)
+            self.slow = time.perf_counter() - t0 > 1.5e-3
+            if not self.slow:
+                self.t = threading.Thread(target=self._loop, daemon=True)
+                self.t.start()
         except Exception:
             self.nv = None
+            self.slow = False
             self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             try:
                 self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -190,31 +205,45 @@ class ClockSampler:
             except OSError:
                 self.p = None
 
-    def _loop(self):
+    def _sample(self, record=True):
         nv = self.nv
-        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else nv.nvmlClocksThrottleReasonHwSlowdown,
-                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
-                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
-                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0))}
-        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
-        while not self.stop_flag.is_set():
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = self.get_reasons(self.h) if self.get_reasons else 0
+        if record:
+            self.sm.append(sm)
+            for k, bit in self.names.items():
+                if bit and r & bit:
+                    self.reasons.add(k)
+
+    def sample_now(self):
+        """One sample on the calling thread (used between timed steps when the NVML query is slow)."""
+        if self.nv is not None:
             try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                if get_reasons:
-                    r = get_reasons(self.h)
-                    for k, bit in names.items():
-                        if bit and r & bit:
-                            self.reasons.add(k)
+                self._sample()
             except Exception:
                 pass
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            t0 = time.perf_counter()
+            try:
+                self._sample()
+            except Exception:
+                pass
+            if time.perf_counter() - t0 > 1.5e-3:       # became slow under load: hand over to the per-step samples
+                self.slow = True
+                return
             time.sleep(0.002)
 
     def stop(self):
         if self.nv is not None:
             self.stop_flag.set()
-            self.t.join(timeout=2)
+            if self.t is not None:
+                self.t.join(timeout=2)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
-                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 2 ms period, inside the timed region"}
+                    "reasons": sorted(self.reasons), "samples": len(self.sm),
+                    "source": "nvml, one sample after every timed step (query too slow for a background sampler)" if self.slow
+                              else "nvml, 2 ms period, inside the timed region"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -321,7 +350,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     pipe.hist_null.zero_(); pipe.hist_prep.zero_(); pipe.scanned.zero_()
-    clocks = ClockSampler(local) if rank == 0 else None
+    clocks = ClockSampler(local) if rank == 0 and not os.environ.get("TEMPME_BENCH_NO_CLOCKS") else None     # (diagnostic switch)
     tm.lib().tm_encoder_profile(1)                     # CUDA events around the two scorer kernels (same stream)
     launches0 = tm.launch_count()
     stage_ms = {}
@@ -337,6 +366,8 @@ def run_ours(args):
         last = step(args.warmup + k, timers)
         end = torch.cuda.Event(enable_timing=True); end.record()
         end.synchronize()
+        if clocks is not None and clocks.slow:
+            clocks.sample_now()
         t_dev += timers[0][1].elapsed_time(end)
         for (_, a), (name, b) in zip(timers[:-1], timers[1:]):
             stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
