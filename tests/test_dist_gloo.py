@@ -79,3 +79,24 @@ def test_shard_batches_partition():
                 assert 0 <= a <= b <= n and (b - a) in (n // w, n // w + 1)
                 cover += list(range(a, b))
             assert cover == list(range(n))
+
+
+def test_score_exchange_segment_offsets():
+    """ScoreExchange's address arithmetic: rank r writes its [rows, W] float32 segment at the same offset of every OTHER rank's
+    gathered buffer [world, rows, W]; the segments of all ranks tile a buffer without overlap."""
+    from tempme_b200.dist import segment_offsets
+    rows, W, world = 300, 30, 8
+    bases = [0x7F00_0000_0000 + p * 0x4000_0000 for p in range(world)]
+    seen = {}
+    for r in range(world):
+        ptrs = segment_offsets(rows, W, world, r, bases)
+        assert len(ptrs) == world - 1
+        peers = [p for p in range(world) if p != r]
+        for p, a in zip(peers, ptrs):
+            off = a - bases[p]
+            assert off == r * rows * W * 4 and off % 4 == 0
+            seen.setdefault(p, []).append((off, off + rows * W * 4))
+    for p, segs in seen.items():
+        segs.sort()
+        assert all(a[1] <= b[0] for a, b in zip(segs, segs[1:]))     # no overlap between the writers of one buffer
+        assert segs[-1][1] <= world * rows * W * 4
