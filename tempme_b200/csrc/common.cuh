@@ -34,10 +34,34 @@ extern std::atomic<uint64_t> g_launches;
         }                                                                                      \
     } while (0)
 
+// RAII current-device guard of the C entry points: switch to `dev` for the call, restore the caller's device on return
+// (a process that drives several GPUs -- or torch's own current device -- is left as it was found).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) { ok = false; return; }
+        if (dev >= 0 && dev != cur) { ok = cudaSetDevice(dev) == cudaSuccess; if (ok) prev = cur; }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+// device that owns a device pointer (-1: unknown / host memory): entry points without a device argument run where their data lives
+inline int device_of(const void *p) {
+    cudaPointerAttributes at;
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? at.device : -1;
+}
+#define TM_DEVICE(dev)                                                                         \
+    tmb::DeviceGuard guard__(dev);                                                             \
+    if (!guard__.ok) { tmb::set_error("cannot select CUDA device %d (%s:%d)", (int)(dev), __FILE__, __LINE__); return TM_ERR_CUDA; }
+
 // tensor-core scorer (encoder_tc.cu)
 int64_t tc_blob_floats(const tm_encoder_desc &d);
 int tc_pack(const tm_encoder_desc &d, const tm_encoder_params &p, float *blob);
-int64_t tc_slab_motifs();
+int64_t tc_slab_motifs(int device = -1);
 int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
                     const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
                     int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,

@@ -79,7 +79,7 @@ extern "C" int tm_edge_importance(const tm_gate_desc *desc, const float *d_gate_
     while (slots < 6 * W) slots <<= 1;                       // load factor <= 1/2
     const size_t smem = sizeof(int32_t) * 2 * (size_t)slots;
     if (smem > 48 * 1024) { set_error("tm_edge_importance: %lld walks per root exceed the shared-memory window", (long long)W); return TM_ERR_UNSUPPORTED; }
-    TM_CUDA(cudaSetDevice(device));
+    TM_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
     if (d_gate_blob) {
         const int rc = tc_gate_launch(*desc, d_gate_blob, B * W * 3, d_eidx, d_t, d_scores, d_edge_feat, n_edge_rows, d_walk_imp, device, st);

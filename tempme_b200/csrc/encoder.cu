@@ -335,7 +335,7 @@ static int encode_score_impl(const tm_encoder_desc *desc, const float *d_blob, i
     if (desc->hid_dim != 64 && desc->hid_dim != 32) { set_error("tm_encode_score: hid_dim %d unsupported (64 and 32, the reference's defaults)", desc->hid_dim); return TM_ERR_UNSUPPORTED; }
     if (desc->node_dim < 1 || desc->node_dim > 256 || desc->edge_dim < 1 || desc->edge_dim > 1024) { set_error("tm_encode_score: node_dim must be in [1,256], edge_dim in [1,1024]"); return TM_ERR_UNSUPPORTED; }
     if (B == 0) return TM_OK;
-    TM_CUDA(cudaSetDevice(device));
+    TM_DEVICE(device);
     const EncLayout L = make_layout(*desc);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_groups = (B + group - 1) / group;

@@ -835,15 +835,16 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 }
 
 // Motifs whose h rows the workspace holds: two resident CTAs per SM x 128 motifs (tm_encoder_workspace_floats)
-int64_t tc_slab_motifs() {
-    static int64_t v = 0;
-    if (!v) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        v = (int64_t)sms * 2 * 128;
+int64_t tc_slab_motifs(int device) {
+    static int64_t v[64] = {0};
+    if (device < 0) cudaGetDevice(&device);
+    const int slot = device >= 0 && device < 64 ? device : 0;
+    if (!v[slot]) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        v[slot] = (int64_t)sms * 2 * 128;
     }
-    return v;
+    return v[slot];
 }
 
 // optional kernel timing (bench.py roofline): CUDA events around the launch

@@ -101,6 +101,7 @@ extern "C" int tm_walk_importance(int64_t B, int64_t W, int64_t group, const flo
         return TM_ERR_ARG;
     }
     if (B == 0) return TM_OK;
+    TM_DEVICE(device_of(d_weights));
     walk_importance_kernel<<<(unsigned)((B + group - 1) / group), 256, 0, (cudaStream_t)stream>>>(B, (int)W, group, d_t, d_nodes, d_cut_time,
                                                                                                    d_node_degree, n_nodes, d_weights);
     TM_LAUNCH_CHECK();
@@ -114,6 +115,7 @@ extern "C" int tm_enhance_reduce(int64_t B, int64_t W, int hid_dim, const float 
         return TM_ERR_ARG;
     }
     if (B == 0) return TM_OK;
+    TM_DEVICE(device_of(d_out));
     const int out_dim = hid_dim + (d_cat_or_null ? 12 : 0);
     enhance_reduce_kernel<<<(unsigned)B, hid_dim, sizeof(float) * hid_dim, (cudaStream_t)stream>>>(B, (int)W, hid_dim, d_y, d_weights, d_att_mlp3_w,
                                                                                                    d_att_mlp3_b, d_cat_or_null, out_dim, d_out);

@@ -158,7 +158,7 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
         std::sort(skey.begin() + s, skey.begin() + s + len);
     }
 
-    TM_CUDA(cudaSetDevice(device));
+    TM_DEVICE(device);
     tm_graph *g = new tm_graph();
     g->device = device;
     void *d_off = nullptr, *d_ent = nullptr, *d_nbr = nullptr, *d_tab = nullptr;
@@ -233,7 +233,7 @@ extern "C" int tm_graph_create_from_events(int64_t n_nodes, int64_t n_events, co
 
 extern "C" void tm_graph_destroy(tm_graph *g) {
     if (!g) return;
-    cudaSetDevice(g->device);
+    DeviceGuard guard(g->device);       // also runs from NeighborFinder.__del__ at GC time: the caller's device is restored
     cudaFree((void *)g->v.off); cudaFree((void *)g->v.entry); cudaFree((void *)g->v.skey); cudaFree((void *)g->v.etab); cudaFree((void *)g->v.htab);
     delete g;
 }
@@ -249,7 +249,7 @@ extern "C" int tm_graph_sizes(const tm_graph *g, int64_t *n_nodes, int64_t *n_en
 
 extern "C" int tm_graph_export(const tm_graph *g, int64_t *h_off, int32_t *h_nbr, int32_t *h_eidx, double *h_ts) {
     if (!g) { set_error("tm_graph_export: null graph"); return TM_ERR_ARG; }
-    TM_CUDA(cudaSetDevice(g->device));
+    TM_DEVICE(g->device);
     if (h_off) TM_CUDA(cudaMemcpy(h_off, g->v.off, sizeof(int64_t) * (g->v.n_nodes + 1), cudaMemcpyDeviceToHost));
     if ((h_nbr || h_eidx || h_ts) && g->v.n_entries) {
         std::vector<Entry> ent(g->v.n_entries);
@@ -265,7 +265,7 @@ extern "C" int tm_graph_export(const tm_graph *g, int64_t *h_off, int32_t *h_nbr
 
 extern "C" int tm_graph_export_edge_table(const tm_graph *g, int32_t *h_tab) {
     if (!g || !h_tab) { set_error("tm_graph_export_edge_table: bad argument"); return TM_ERR_ARG; }
-    TM_CUDA(cudaSetDevice(g->device));
+    TM_DEVICE(g->device);
     if (g->v.max_eidx >= 0) TM_CUDA(cudaMemcpy(h_tab, g->v.etab, sizeof(int4) * (g->v.max_eidx + 1), cudaMemcpyDeviceToHost));
     return TM_OK;
 }
@@ -274,7 +274,7 @@ extern "C" int tm_find_before_batch(const tm_graph *g, int64_t R, const int32_t 
                                     const int32_t *d_eidx, int64_t *d_start, int32_t *d_cut, int32_t *d_err, tm_stream stream) {
     if (!g || R < 0 || (R > 0 && (!d_node || !d_start || !d_cut || (!d_cut_time && !d_eidx)))) { set_error("tm_find_before_batch: bad argument"); return TM_ERR_ARG; }
     if (R == 0) return TM_OK;
-    TM_CUDA(cudaSetDevice(g->device));
+    TM_DEVICE(g->device);
     const int threads = 256;
     const int64_t blocks = (R * 32 + threads - 1) / threads;
     find_before_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(g->v, R, d_node, d_cut_time, d_eidx, d_start, d_cut, d_err);

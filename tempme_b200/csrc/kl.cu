@@ -79,6 +79,7 @@ extern "C" int tm_kl_loss(int64_t B, int64_t W, const float *d_prob, const uint8
         set_error("tm_kl_loss: bad argument");
         return TM_ERR_ARG;
     }
+    TM_DEVICE(device_of(d_loss));
     kl_root_kernel<<<(unsigned)((B + kKlWarps - 1) / kKlWarps), kKlWarps * 32, 0, (cudaStream_t)stream>>>(
         B, (int)W, d_prob, d_cat, d_null_values, n_cat, target, empirical, d_workspace);
     TM_LAUNCH_CHECK();

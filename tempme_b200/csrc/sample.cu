@@ -305,7 +305,7 @@ extern "C" int tm_sample_hop(const tm_graph *g, int64_t R, const int32_t *d_node
     const size_t smem = sizeof(uint32_t) * kWarpsPerBlock * (size_t)n;
     if (smem > 48 * 1024) { set_error("tm_sample_hop: fan-out %d too large (max %d)", n, 48 * 1024 / 4 / kWarpsPerBlock); return TM_ERR_UNSUPPORTED; }
     if (R == 0) return TM_OK;
-    TM_CUDA(cudaSetDevice(g->device));
+    TM_DEVICE(g->device);
     const int64_t blocks = (R + kWarpsPerBlock - 1) / kWarpsPerBlock;
     sample_hop_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
         g->v, R, d_node, d_cut_time, d_eidx, n, seed, stage, row_offset, d_inject, d_o_node, d_o_eidx, d_o_ts, d_err);
@@ -326,7 +326,7 @@ static int walks_impl(const tm_graph *g, int64_t B, int n, int N2, const int32_t
     }
     if (N2 > TM_MAX_STEP2_FANOUT) { set_error("tm_sample_walks: step-2 fan-out %d > %d", N2, TM_MAX_STEP2_FANOUT); return TM_ERR_UNSUPPORTED; }
     if (B == 0) return TM_OK;
-    TM_CUDA(cudaSetDevice(g->device));
+    TM_DEVICE(g->device);
     const int64_t rows = B * n, blocks = (rows + 255) / 256;
 #define TM_WALKS(CAP) sample_walks_kernel<CAP><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                           \
         g->v, B, n, N2, d_root, d_h1_node, d_h1_eidx, d_h1_ts, seed, row_offset, d_inject2, d_inject3, d_pre2, d_pre2_t,     \
@@ -361,6 +361,7 @@ extern "C" int tm_class_hist(int64_t count, const int32_t *d_anony, unsigned lon
                              unsigned long long *d_hist_prep, uint8_t *d_o_cat, int32_t *d_err, tm_stream stream) {
     if (count < 0 || (count > 0 && !d_anony)) { set_error("tm_class_hist: bad argument"); return TM_ERR_ARG; }
     if (count == 0) return TM_OK;
+    TM_DEVICE(device_of(d_anony));
     const int64_t blocks = std::min<int64_t>((count + 255) / 256, 148 * 8);
     class_hist_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(count, d_anony, d_hist_null, d_hist_prep, d_o_cat, d_err);
     TM_LAUNCH_CHECK();
@@ -372,6 +373,7 @@ extern "C" int tm_edge_identity(int64_t B, int64_t W, const int32_t *d_eidx, flo
     const size_t smem = sizeof(int32_t) * 3 * (size_t)W;
     if (smem > 48 * 1024) { set_error("tm_edge_identity: %lld walks per root exceed the shared-memory window", (long long)W); return TM_ERR_UNSUPPORTED; }
     if (B == 0) return TM_OK;
+    TM_DEVICE(device_of(d_eidx));
     const int threads = (int)std::min<int64_t>(1024, ((3 * W + 31) / 32) * 32);
     edge_identity_kernel<<<(unsigned)B, threads, smem, (cudaStream_t)stream>>>(B, (int)W, d_eidx, d_out);
     TM_LAUNCH_CHECK();

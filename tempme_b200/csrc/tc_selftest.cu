@@ -191,6 +191,7 @@ __global__ void selftest_gather4_kernel(const __grid_constant__ CUtensorMap map,
 }  // namespace tmb
 
 extern "C" int tm_selftest_gather4(const float *d_table, int64_t rows, int dim, const int32_t *d_idx128, int col, int swizzle128, float *d_out, tm_stream stream) {
+    TM_DEVICE(device_of(d_out));
     CUtensorMap map;
     if (!make_gather_map(&map, d_table, rows, dim, swizzle128)) { set_error("tm_selftest_gather4: cuTensorMapEncodeTiled failed"); return TM_ERR_CUDA; }
     selftest_gather4_kernel<<<1, 128, 128 * 32 * 4, (cudaStream_t)stream>>>(map, d_idx128, col, d_out);
@@ -201,6 +202,7 @@ extern "C" int tm_selftest_gather4(const float *d_table, int64_t rows, int dim, 
 extern "C" int tm_selftest_cos(const float *d_x, float *d_out, int64_t n, tm_stream stream) {
     if (!d_x || !d_out || n < 0) { set_error("tm_selftest_cos: bad argument"); return TM_ERR_ARG; }
     if (n == 0) return TM_OK;
+    TM_DEVICE(device_of(d_out));
     selftest_cos_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n);
     TM_LAUNCH_CHECK();
     return TM_OK;
@@ -211,6 +213,7 @@ extern "C" int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, 
     if (!d_A || !d_B || !d_C || K <= 0 || K % 8 || N < 16 || N > 256 || N % 16) { set_error("tm_selftest_gemm: need K %% 8 == 0, 16 <= N <= 256, N %% 16 == 0"); return TM_ERR_ARG; }
     const size_t smem = (size_t)(2 * 128 + 2 * N) * K * 4;
     if (smem > 200 * 1024) { set_error("tm_selftest_gemm: tile too large"); return TM_ERR_UNSUPPORTED; }
+    TM_DEVICE(device_of(d_C));
     TM_CUDA(cudaFuncSetAttribute(selftest_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     selftest_gemm_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(d_A, d_B, d_C, K, N, mode);
     TM_LAUNCH_CHECK();
@@ -219,6 +222,7 @@ extern "C" int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, 
 
 extern "C" int tm_selftest_mma_rate(int N, int groups, long long *d_out, tm_stream stream) {
     if (!d_out || N < 16 || N > 256 || N % 16 || groups < 1) { set_error("tm_selftest_mma_rate: need 16 <= N <= 256, N %% 16 == 0, groups >= 1"); return TM_ERR_ARG; }
+    TM_DEVICE(device_of(d_out));
     mma_rate_kernel<<<1, 128, (size_t)N * 32 * 4, (cudaStream_t)stream>>>(N, groups, d_out);
     TM_LAUNCH_CHECK();
     return TM_OK;

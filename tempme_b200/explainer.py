@@ -131,6 +131,7 @@ class TempME(nn.Module):
         self._blob = None
         self._blob_key = None
         self._ws = None
+        self._ws_retired = []
         self._gate_desc = GateDesc(self.edge_dim, self.time_dim, self.hid_dim)
         self._gate_blob = None
         self._gate_key = None
@@ -167,6 +168,17 @@ class TempME(nn.Module):
             ef = ef.detach().to(self.device, torch.float32).contiguous()
         return nf, ef
 
+    def _workspace(self, B, W, group):
+        """Scratch of the scorer (per-batch std + the resident CTAs' h slabs).  It only grows, and a replaced buffer stays alive:
+        a captured CUDA graph (MotifPipeline) may still hold its address."""
+        with torch.cuda.device(self.device):
+            nws = lib().tm_encoder_workspace_floats(C.byref(self._desc), B, W, group)
+        if self._ws is None or self._ws.numel() < nws:
+            if self._ws is not None:
+                self._ws_retired.append(self._ws)
+            self._ws = torch.empty(max(nws, 1024), dtype=torch.float32, device=self.device)
+        return self._ws
+
     def _t(self, a, dtype):
         if isinstance(a, torch.Tensor):
             return a.to(device=self.device, dtype=dtype).contiguous()
@@ -182,9 +194,7 @@ class TempME(nn.Module):
         group = int(group or self.batch_group or max(B, 1))
         blob = self.packed_weights()
         nf, ef = self._tables()
-        nws = lib().tm_encoder_workspace_floats(C.byref(self._desc), B, W, group)
-        if self._ws is None or self._ws.numel() < nws:
-            self._ws = torch.empty(max(nws, 1024), dtype=torch.float32, device=self.device)
+        self._workspace(B, W, group)
         if out is None:
             scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
         else:
@@ -246,9 +256,7 @@ class TempME(nn.Module):
         group = int(self.batch_group or max(B, 1))
         blob = self.packed_weights()
         nf, ef = self._tables()
-        nws = lib().tm_encoder_workspace_floats(C.byref(self._desc), B, W, group)
-        if self._ws is None or self._ws.numel() < nws:
-            self._ws = torch.empty(max(nws, 1024), dtype=torch.float32, device=self.device)
+        self._workspace(B, W, group)
         scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
         y = torch.empty((B, W, self.hid_dim), dtype=torch.float32, device=self.device)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -175,6 +175,16 @@ class NeighborFinder:
             self._err.zero_()
             raise IndexError(f"{what}: e_idx not found in edge list (or node id out of range) at row {row - 1}")
 
+    def check_errors(self, what="device call"):
+        """Raises the IndexError the reference raises (graph.py:134-135) if any device-API call since the last check saw an
+        e_idx that is not in its node's list or a node id out of range; clears the flag.  Synchronises the current stream.
+        The host wrappers call this themselves; callers of the ``*_device`` methods call it where they synchronise anyway."""
+        self._raise_if_err(what)
+
+    def _clear_err(self):
+        """Start of a host wrapper: a flag left by an earlier, unchecked device call must not be blamed on this one."""
+        self._err.zero_()
+
     # ------------------------------------------------------------------ find_before (graph.py:103-146)
     def find_before_batch_device(self, node, cut_time=None, e_idx=None):
         node = self._dev(node, torch.int32)
@@ -188,28 +198,46 @@ class NeighborFinder:
         return start, cut
 
     def find_before(self, src_idx, cut_time, e_idx=None, return_binary_prob=False):
-        """Returns views into the exported CSR arrays, like the reference."""
-        start, cut = self.find_before_batch_device([int(src_idx)], [float(cut_time)] if e_idx is None else None,
-                                                   None if e_idx is None else [int(e_idx)])
-        s, c = int(start.item()), int(cut.item())
-        row = int(self._err.item())
+        """Returns views into the exported CSR arrays, like the reference.  One packed 32-byte H2D, the lookup kernel, one packed
+        D2H and a single stream synchronisation per call (scalar callers: TGN / GraphMixer style per-event lookups)."""
+        if getattr(self, "_fb_pin", None) is None:
+            self._fb_pin = torch.zeros(4, dtype=torch.int64).pin_memory()      # f64 cut_time | i32 node, i32 e_idx | i64 start | i32 cut, i32 err
+            self._fb_dev = torch.zeros(4, dtype=torch.int64, device=self.device)
+        h = self._fb_pin.numpy()
+        h.view(np.float64)[0] = float(cut_time)
+        h32 = h.view(np.int32)
+        h32[2] = int(src_idx)
+        h32[3] = TM_EIDX_NONE if e_idx is None else int(e_idx)
+        h[2] = 0; h[3] = 0
+        with torch.cuda.device(self.device):
+            self._fb_dev.copy_(self._fb_pin, non_blocking=True)
+            base = self._fb_dev.data_ptr()
+            check(lib().tm_find_before_batch(self._h, 1, C.c_void_p(base + 8), C.c_void_p(base), C.c_void_p(base + 12), C.c_void_p(base + 16),
+                                             C.c_void_p(base + 24), C.c_void_p(base + 28), self._stream()), "tm_find_before_batch")
+            self._fb_pin.copy_(self._fb_dev, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        s, c, row = int(h[2]), int(h32[6]), int(h32[7])
         if row:
-            self._err.zero_()
             raise IndexError('e_idx {} not found in edge list of {}'.format(e_idx, src_idx))
         off, nbr, e, ts = self._export()
         prob = self.binary_prob_l[s:s + c] if return_binary_prob else None
         return nbr[s:s + c], e[s:s + c], ts[s:s + c], prob
 
     # ------------------------------------------------------------------ get_temporal_neighbor (graph.py:197-231)
-    def sample_hop_device(self, node, cut_time, num_neighbor, e_idx=None, seed=0, stage=0, row_offset=0, inject=None):
+    def sample_hop_device(self, node, cut_time, num_neighbor, e_idx=None, seed=0, stage=0, row_offset=0, inject=None, out=None):
+        """out: optional preallocated (node i32 [R,n], eidx i32 [R,n], ts f32 [R,n]) to write into (no allocation on the call)."""
         node = self._dev(node, torch.int32)
         R = node.numel()
         ct = self._dev(cut_time, torch.float64) if cut_time is not None else None
         e = self._dev(e_idx, torch.int32)
         inj = self._dev(inject, torch.int64).to(torch.int32) if inject is not None else None
-        o_node = torch.empty((R, num_neighbor), dtype=torch.int32, device=self.device)
-        o_eidx = torch.empty_like(o_node)
-        o_ts = torch.empty((R, num_neighbor), dtype=torch.float32, device=self.device)
+        if out is not None:
+            o_node, o_eidx, o_ts = out
+            assert o_node.shape == (R, num_neighbor) and o_node.dtype == torch.int32 and o_ts.dtype == torch.float32 and o_node.is_contiguous()
+        else:
+            o_node = torch.empty((R, num_neighbor), dtype=torch.int32, device=self.device)
+            o_eidx = torch.empty_like(o_node)
+            o_ts = torch.empty((R, num_neighbor), dtype=torch.float32, device=self.device)
         check(lib().tm_sample_hop(self._h, R, ptr(node), ptr(ct), ptr(e), int(num_neighbor), seed, stage, row_offset,
                                   ptr(inj), ptr(o_node), ptr(o_eidx), ptr(o_ts), ptr(self._err), self._stream()),
               "tm_sample_hop")
@@ -217,6 +245,7 @@ class NeighborFinder:
 
     def get_temporal_neighbor(self, src_idx_l, cut_time_l, num_neighbor, e_idx_l=None, seed=None, row_offset=0, inject=None):
         assert (len(src_idx_l) == len(cut_time_l))
+        self._clear_err()
         s = self._next_seed(seed)
         ct = None if e_idx_l is not None else cut_time_l
         o = self.sample_hop_device(src_idx_l, ct, num_neighbor, e_idx_l, s, 0, row_offset, inject)
@@ -245,6 +274,7 @@ class NeighborFinder:
         return recs
 
     def find_k_hop(self, k, src_idx_l, cut_time_l, num_neighbors, e_idx_l=None, seed=None, row_offset=0, inject=None):
+        self._clear_err()
         recs = self.find_k_hop_device(k, src_idx_l, cut_time_l, num_neighbors, e_idx_l, seed, row_offset, inject)
         out = tuple([t.cpu().numpy() for t in r] for r in recs)
         self._raise_if_err("find_k_hop")
@@ -253,7 +283,8 @@ class NeighborFinder:
     # ------------------------------------------------------------------ find_k_walks (graph.py:265-476)
     def find_k_walks_device(self, degree, src_idx_l, num_neighbors, subgraph_src, seed=None, row_offset=0,
                             inject2=None, inject3=None, want_anony=True, want_cat=True, hist_null=None, hist_prep=None,
-                            scanned=None):
+                            scanned=None, out=None):
+        """out: optional preallocated (nodes i32 [B,W,6], eidx i32 [B,W,3], t f32 [B,W,3], cat u8 [B,W]) to write into."""
         s = self._next_seed(seed)
         root = self._dev(src_idx_l, torch.int32)
         B = root.numel()
@@ -263,11 +294,15 @@ class NeighborFinder:
         assert h1n.shape == (B, n)
         W = n * N2
         dev = self.device
-        nodes = torch.empty((B, W, 6), dtype=torch.int32, device=dev)
-        eidx = torch.empty((B, W, 3), dtype=torch.int32, device=dev)
-        t = torch.empty((B, W, 3), dtype=torch.float32, device=dev)
+        if out is not None:
+            nodes, eidx, t, cat = out
+            assert nodes.shape == (B, W, 6) and eidx.shape == (B, W, 3) and t.shape == (B, W, 3) and nodes.is_contiguous()
+        else:
+            nodes = torch.empty((B, W, 6), dtype=torch.int32, device=dev)
+            eidx = torch.empty((B, W, 3), dtype=torch.int32, device=dev)
+            t = torch.empty((B, W, 3), dtype=torch.float32, device=dev)
+            cat = torch.empty((B, W), dtype=torch.uint8, device=dev) if want_cat else None
         anony = torch.empty((B, W, 3), dtype=torch.int32, device=dev) if want_anony else None
-        cat = torch.empty((B, W), dtype=torch.uint8, device=dev) if want_cat else None
         i2 = self._dev(inject2, torch.int64).to(torch.int32) if inject2 is not None else None
         i3 = self._dev(inject3, torch.int64).to(torch.int32) if inject3 is not None else None
         check(lib().tm_sample_walks(self._h, B, n, N2, ptr(root), ptr(h1n), ptr(h1e), ptr(h1t), s, row_offset,
@@ -339,11 +374,12 @@ def class_hist_device(anony, want_cat=True):
     return hn, hp, (cat.view(anony.shape[:-1]) if want_cat else None), err
 
 
-def edge_identity_device(eidx):
+def edge_identity_device(eidx, out=None):
     """new_edge_info (processed/data_preprocess.py:327-343): [B, W, 3] int32 -> [B, W, 3, 3] float32."""
     e = eidx.contiguous()
     B, W, _ = e.shape
-    out = torch.empty((B, W, 3, 3), dtype=torch.float32, device=e.device)
+    if out is None:
+        out = torch.empty((B, W, 3, 3), dtype=torch.float32, device=e.device)
     st = C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream)
     with torch.cuda.device(e.device):
         check(lib().tm_edge_identity(B, W, ptr(e), ptr(out), st), "tm_edge_identity")

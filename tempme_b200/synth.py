@@ -92,10 +92,53 @@ def make_features(cfg: str, n_nodes: int, n_events: int, device=None):
 
 def make_queries(graph, rng, count):
     """Query events drawn from the test split (ts > 85th percentile), in chronological order, with a random
-    fake destination per event (RandEdgeSampler semantics, utils/batch_loader.py:39-42)."""
+    fake destination per event (RandEdgeSampler semantics, utils/batch_loader.py:39-42).  The split and the destination
+    pool are computed once per graph (cached in the dict)."""
     ts = graph["ts"]
-    pool = np.nonzero(ts > np.quantile(ts, 0.85))[0]
+    if "_pool" not in graph:
+        graph["_pool"] = np.nonzero(ts > np.quantile(ts, 0.85))[0]
+        graph["_dst_pool"] = np.flatnonzero(np.bincount(graph["dst"], minlength=int(graph["n_nodes"])))      # == np.unique(dst)
+    pool, dst_pool = graph["_pool"], graph["_dst_pool"]
     q = np.sort(rng.choice(pool, size=count, replace=count > len(pool)))
-    dst_pool = np.unique(graph["dst"])
     fake = dst_pool[rng.integers(0, len(dst_pool), count)]
     return graph["src"][q], graph["dst"][q], fake, ts[q], graph["eidx"][q]
+
+
+def share_graph(cfg: str, scale: float, local_rank: int, world: int, barrier, tag: str = ""):
+    """One graph per NODE instead of one per rank: local rank 0 generates it and writes the event arrays to /dev/shm, the other
+    ranks map them read-only after `barrier()`.  Returns (graph, cleanup) -- call cleanup() on every rank after a later barrier."""
+    if world <= 1:
+        return make_graph(cfg, scale), (lambda: None)
+    base = os.path.join("/dev/shm", f"tempme_b200_{cfg}_{scale}_{tag}")
+    names = ("src", "dst", "ts")
+    if local_rank == 0:
+        g = make_graph(cfg, scale)
+        try:
+            for k in names:
+                np.save(f"{base}_{k}.npy", g[k].astype(np.int32) if k != "ts" else g[k])
+            with open(base + "_meta", "w") as fh:
+                fh.write(str(int(g["n_nodes"])))
+        except OSError:
+            pass
+    barrier()
+    if local_rank != 0:
+        try:
+            g = dict(n_nodes=int(open(base + "_meta").read()))
+            for k in names:
+                g[k] = np.load(f"{base}_{k}.npy", mmap_mode="r")
+            g["eidx"] = np.arange(1, len(g["src"]) + 1, dtype=np.int64)
+        except OSError:
+            g = make_graph(cfg, scale)          # no shared memory file system: every rank generates (same seed, same graph)
+
+    def cleanup():
+        if local_rank == 0:
+            for k in names:
+                try:
+                    os.unlink(f"{base}_{k}.npy")
+                except OSError:
+                    pass
+            try:
+                os.unlink(base + "_meta")
+            except OSError:
+                pass
+    return g, cleanup

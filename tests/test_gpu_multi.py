@@ -51,6 +51,8 @@ def _worker(rank, world, port, ret):
     flag = torch.tensor([1.0 if x is not None else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if flag.item() > 0:
+        pipe.reset_counters()
+        token = torch.zeros(1, device=dev)
         plain = pipe.run_device(*dq, row_offset=rank * 3 * Q)
         want = torch.empty((world, 3 * Q, pipe.W), device=dev)
         dist.all_gather_into_tensor(want, plain)
@@ -58,9 +60,17 @@ def _worker(rank, world, port, ret):
             x.gathered.fill_(float("nan"))
             dist.all_reduce(flag)
             got_local = pipe.run_device(*dq, row_offset=rank * 3 * Q, out=x.local, peer_ptrs=x.peer_ptrs)
-            dist.all_reduce(pipe.hist_null)
+            dist.all_reduce(token)                                 # any collective after the step orders the peers' reads behind the stores
             torch.cuda.synchronize()
             ok &= int(got_local.data_ptr() == x.local.data_ptr() and torch.equal(x.gathered, want))
+        # the job-wide histogram after 1 + 3 steps: all-reduce of a COPY of the running totals == 4 x one single-GPU pass over both shards
+        gh = pipe.global_hist()
+        if rank == 0:
+            both = synth.make_queries(g, np.random.default_rng(4), 2 * Q)
+            one = tm.MotifPipeline(f, m, 30, 1, group=100, seed=11)
+            one.run_device(*one.stage_queries(*both))
+            ok &= int(torch.equal(gh, 4 * one.hist_null))
+            ok &= int(torch.equal(pipe.hist_null * 2 > 0, pipe.hist_null > 0) and int(pipe.hist_null.sum()) == 4 * 3 * Q * pipe.W)   # local totals untouched by the reduction
     res = torch.tensor([ok, int(flag.item() > 0)], device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -524,7 +524,7 @@ def test_pipeline_explain_matches_oracle(tm, orc):
     fake = rng.integers(1, 120, len(q))
     n = 8
     pipe = tm.MotifPipeline(f, m, n, 1, group=100, seed=17)
-    roots, e, cut64 = pipe.stage_queries(src[q], dst[q], fake, ts[q], eidx[q])
+    roots, e, cut64, _ = pipe.stage_queries(src[q], dst[q], fake, ts[q], eidx[q])
     scores, imp0, imp1, sub = pipe.explain_device(roots, e, cut64)
     scores, imp0, imp1 = scores.cpu().numpy(), imp0.cpu().numpy(), imp1.cpu().numpy()
     og = orc.OracleGraph.from_events(120, src, dst, eidx, ts)

@@ -34,7 +34,7 @@ model.load_state_dict({k: torch.as_tensor(v) for k, v in random_params(D, Ed).it
 pipe = tm.MotifPipeline(finder, model, n, N2, group=100, seed=5)
 rng = np.random.default_rng(3)
 Q = args.events // 100 * 100
-roots, e, cut64 = pipe.stage_queries(*synth.make_queries(graph, rng, Q))
+roots, e, cut64, _ = pipe.stage_queries(*synth.make_queries(graph, rng, Q))
 R = roots.numel()
 scores, (nodes, eidx, t, cat, eid) = pipe.run_device(roots, e, cut64, want_walks=True)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)

@@ -32,7 +32,7 @@ if args.hid == 64:
 model.node_degree = torch.as_tensor(np.bincount(np.concatenate([graph["src"], graph["dst"]]), minlength=graph["n_nodes"]).astype(np.float32)).to(dev)
 pipe = tm.MotifPipeline(finder, model, n, N2, group=100, seed=5)
 Q = args.events // 100 * 100
-roots, e, cut64 = pipe.stage_queries(*synth.make_queries(graph, np.random.default_rng(3), Q))
+roots, e, cut64, _ = pipe.stage_queries(*synth.make_queries(graph, np.random.default_rng(3), Q))
 R = roots.numel()
 _, (nodes, eidx, t, cat, eid) = pipe.run_device(roots, e, cut64, want_walks=True)
 cut = cut64.to(torch.float32)
