@@ -72,7 +72,7 @@ def executed_flops(D, Ed, H=HID):
 
 # events per GPU per step: sized so that the default --steps 20 run keeps the GPU busy for >= 1 s (sustained clocks)
 DEFAULT_EVENTS = {"cfg1": 16000, "cfg2": 256000, "cfg3": 32000, "cfg4": 24000, "cfg5": 256000}
-DEFAULT_CHUNK = {"cfg1": 2000, "cfg2": 16000, "cfg3": 4000, "cfg4": 4000, "cfg5": 16000}
+DEFAULT_CHUNK = {"cfg1": 2000, "cfg2": 32000, "cfg3": 4000, "cfg4": 4000, "cfg5": 32000}
 
 
 def workload_config(args, world=1):
@@ -569,7 +569,7 @@ def run_ours(args):
     m_launch = M / n_chunks
     traffic = dram_per_motif(top) * m_launch if dram_per_motif(top) is not None else None   # ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch
     if top in flops:
-        ach = flops[top] / launches_top / dur_s / 1e12
+        ach = flops[top] / n_chunks / dur_s / 1e12                  # FLOPs of one launch / its average duration
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": traffic}
         roof.update(frac_of_burst_peak=ach / pk["tensor_burst"], executed_tflops=ach * executed_flops(D, Ed) / encoder_flops(D, Ed),
                     frac_executed_of_3xtf32_ceiling=ach * executed_flops(D, Ed) / encoder_flops(D, Ed) / (pk["tensor"] / 6.0),
@@ -578,7 +578,7 @@ def run_ours(args):
                          "bf16 dense.  The scorer needs fp32 accuracy (rtol 1e-5): every product is 3 TF32 MMAs at half the bf16 rate, so the ceiling per "
                          "executed FLOP is peak/6; the kernel executes the host-folded chain (executed_flops_per_motif)")
     else:
-        ach = alg_bytes[top] / launches_top / dur_s / 1e9
+        ach = alg_bytes[top] / n_chunks / dur_s / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic}
     step_s = t_ms / args.steps * 1e-3
     stage_keys = [k for k in stage_ms if k != "exchange"]

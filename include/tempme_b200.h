@@ -218,7 +218,7 @@ int tm_encoder_profile_read(float *h_event_ms, float *h_motif_ms);
  * of the root's walks (0 for ids no walk carries, :389); gathered to the hop-1 / hop-2 slots (:392-393); E[Beta(max(10 p, 1),
  * max(10 (1 - p), 1))] (:396-397, :421-430 with training = False); slots whose node id is 0 give 0 (:400-404). */
 typedef struct {
-    int32_t edge_dim, time_dim, hid_dim;     /* time_dim = node_dim (explainer.py:109); hid_dim 64 */
+    int32_t edge_dim, time_dim, hid_dim;     /* time_dim = node_dim (explainer.py:109); hid_dim 64 or 32 */
 } tm_gate_desc;
 typedef struct {                              /* edge_dependency_gcn (explainer.py:143-151), nn.Linear layout, host pointers */
     const float *w0, *b0;                     /* .0  [H, Ed + D] */
@@ -233,7 +233,20 @@ int tm_gate_pack(const tm_gate_desc *desc, const tm_gate_params *params, float *
 int tm_edge_importance(const tm_gate_desc *desc, const float *d_gate_blob, int64_t B, int64_t W, const float *d_scores,
                        const int32_t *d_eidx, const float *d_t, const float *d_edge_feat, int64_t n_edge_rows,
                        int64_t K0, const int32_t *d_h0_node, const int32_t *d_h0_eidx, int64_t K1, const int32_t *d_h1_node,
-                       const int32_t *d_h1_eidx, float *d_walk_imp, float *d_imp0, float *d_imp1, int device, tm_stream stream);
+                       const int32_t *d_h1_eidx, float *d_walk_imp, float *d_imp0, float *d_imp1, int beta_sample, uint64_t seed, int device,
+                       tm_stream stream);
+
+/* ---- Training side of the explainer.
+ * tm_beta_sample: TempME.beta_sample(prob, training=True) (models/explainer.py:421-427): d_out[i] ~ Beta(max(10 p_i, 1), max(10 (1 - p_i), 1)),
+ * drawn as g1 / (g1 + g2) from two Marsaglia-Tsang gammas on counter-based Philox draws (key = seed, counter = offset + i); slots whose
+ * d_node_or_null id is 0 give 0 (:400-404).  d_g1 / d_g2 (optional) receive the gammas for the reparameterised gradient.
+ * tm_edge_importance with beta_sample != 0 draws the same way inside the aggregation kernel (the reference's eval loops pass
+ * training=args.if_bern, temp_exp_main.py:312-318,446-453).
+ * tm_kl_loss_backward: d loss / d prob of tm_kl_loss scaled by *d_grad_out (NULL: 1) -> d_grad_prob [B,W]. */
+int tm_beta_sample(int64_t n, const float *d_prob, const int32_t *d_node_or_null, uint64_t seed, uint64_t offset, float *d_out,
+                   float *d_g1_or_null, float *d_g2_or_null, tm_stream stream);
+int tm_kl_loss_backward(int64_t B, int64_t W, const float *d_prob, const uint8_t *d_cat, const float *d_null_values, int n_cat, float target,
+                        int empirical, const float *d_grad_out_or_null, float *d_grad_prob, tm_stream stream);
 
 /* Hardware self-test of the tcgen05/TMEM conventions the scorer relies on: C[128,N] = A[128,K] * B[N,K]^T on the
  * tensor cores (mode 0: one TF32 pass, mode 1: 3xTF32 split accumulation).  K % 8 == 0, N % 16 == 0, N <= 256. */

@@ -74,7 +74,9 @@ SIGNATURES = {
     "tm_gate_blob_floats": (_i64, [C.POINTER(GateDesc)]),
     "tm_gate_pack": (C.c_int, [C.POINTER(GateDesc), C.POINTER(GateParams), _p]),
     "tm_edge_importance": (C.c_int, [C.POINTER(GateDesc), _p, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p, _p,
-                                     C.c_int, _p]),
+                                     C.c_int, _u64, C.c_int, _p]),
+    "tm_beta_sample": (C.c_int, [_i64, _p, _p, _u64, _u64, _p, _p, _p, _p]),
+    "tm_kl_loss_backward": (C.c_int, [_i64, _i64, _p, _p, _p, C.c_int, C.c_float, C.c_int, _p, _p, _p]),
     "tm_encode_score_gather": (C.c_int, [C.POINTER(EncoderDesc), _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p,
                                          _p, _i64, _p, _i64, _p, _p, C.POINTER(C.c_uint64), C.c_int, C.c_int, _p]),
     "tm_encode_score": (C.c_int, [C.POINTER(EncoderDesc), _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p,

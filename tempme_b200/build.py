@@ -16,8 +16,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["graph.cu", "sample.cu", "encoder.cu", "encoder_tc.cu", "tc_selftest.cu", "edge_imp.cu", "enhance.cu", "kl.cu"]
-HEADERS = ["common.cuh", "tc.cuh", "timeenc.cuh", os.path.join("..", "..", "include", "tempme_b200.h")]
+SOURCES = ["graph.cu", "sample.cu", "encoder.cu", "encoder_tc.cu", "tc_selftest.cu", "edge_imp.cu", "enhance.cu", "kl.cu", "train.cu"]
+HEADERS = ["common.cuh", "tc.cuh", "timeenc.cuh", "beta.cuh", os.path.join("..", "..", "include", "tempme_b200.h")]
 LIB = os.path.join(CSRC, "libtempme_b200.so")
 STAMP = LIB + ".stamp"
 LOCK = os.path.join(CSRC, ".build.lock")

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 
+#include "beta.cuh"
 #include "common.cuh"
 
 namespace tmb {
@@ -15,7 +16,8 @@ namespace tmb {
 __global__ void edge_imp_kernel(int64_t B, int W3, int slots_mask, const int32_t *__restrict__ w_eidx, const float *__restrict__ walk_imp,
                                 const float *__restrict__ scores, int K0, const int32_t *__restrict__ h0_node,
                                 const int32_t *__restrict__ h0_eidx, int K1, const int32_t *__restrict__ h1_node,
-                                const int32_t *__restrict__ h1_eidx, float *__restrict__ imp0, float *__restrict__ imp1) {
+                                const int32_t *__restrict__ h1_eidx, float *__restrict__ imp0, float *__restrict__ imp1, int sample,
+                                uint64_t seed) {
     extern __shared__ int32_t sh[];             // keys [slots], then importance bit patterns [slots]
     int32_t *keys = sh, *vals = sh + slots_mask + 1;
     const int64_t b = blockIdx.x;
@@ -44,7 +46,9 @@ __global__ void edge_imp_kernel(int64_t B, int W3, int slots_mask, const int32_t
             if (k == INT32_MIN) break;
         }
         const float alpha = fmaxf(__fmul_rn(m, 10.f), 1.f), beta = fmaxf(__fmul_rn(__fsub_rn(1.f, m), 10.f), 1.f);   // :423-424
-        const float out = node == 0 ? 0.f : __fdiv_rn(alpha, __fadd_rn(alpha, beta));                                   // :429, :400-404
+        // training: one Beta draw per slot (:426-427; hop-1 slots use draw index o, hop-2 slots o + 2^40); else the mean (:429); padding :400-404
+        const float val = sample ? beta_draw(m, seed, (uint64_t)o + (l0 ? 0ull : (1ull << 40)), nullptr, nullptr) : __fdiv_rn(alpha, __fadd_rn(alpha, beta));
+        const float out = node == 0 ? 0.f : val;
         (l0 ? imp0 : imp1)[o] = out;
     }
 }
@@ -60,14 +64,15 @@ extern "C" int tm_gate_pack(const tm_gate_desc *desc, const tm_gate_params *p, f
         set_error("tm_gate_pack: bad argument");
         return TM_ERR_ARG;
     }
-    if (desc->hid_dim != 64) { set_error("tm_gate_pack: hid_dim %d unsupported (only 64, the reference default)", desc->hid_dim); return TM_ERR_UNSUPPORTED; }
+    if (desc->hid_dim != 64 && desc->hid_dim != 32) { set_error("tm_gate_pack: hid_dim %d unsupported (64 and 32, the defaults of temp_exp_main.py / enhance_main.py)", desc->hid_dim); return TM_ERR_UNSUPPORTED; }
     return tc_gate_pack(*desc, *p, h_blob);
 }
 
 extern "C" int tm_edge_importance(const tm_gate_desc *desc, const float *d_gate_blob, int64_t B, int64_t W, const float *d_scores,
                                   const int32_t *d_eidx, const float *d_t, const float *d_edge_feat, int64_t n_edge_rows,
                                   int64_t K0, const int32_t *d_h0_node, const int32_t *d_h0_eidx, int64_t K1, const int32_t *d_h1_node,
-                                  const int32_t *d_h1_eidx, float *d_walk_imp, float *d_imp0, float *d_imp1, int device, tm_stream stream) {
+                                  const int32_t *d_h1_eidx, float *d_walk_imp, float *d_imp0, float *d_imp1, int beta_sample, uint64_t seed, int device,
+                                  tm_stream stream) {
     if (B < 0 || W <= 0 || K0 < 0 || K1 < 0 ||
         (B > 0 && (!d_scores || !d_eidx || (K0 > 0 && (!d_h0_node || !d_h0_eidx || !d_imp0)) || (K1 > 0 && (!d_h1_node || !d_h1_eidx || !d_imp1))))) {
         set_error("tm_edge_importance: bad argument");
@@ -87,7 +92,7 @@ extern "C" int tm_edge_importance(const tm_gate_desc *desc, const float *d_gate_
     }
     const int threads = (int)std::min<int64_t>(256, std::max<int64_t>(64, ((K0 + K1 + 31) / 32) * 32));
     edge_imp_kernel<<<(unsigned)B, threads, smem, st>>>(B, (int)(3 * W), slots - 1, d_eidx, d_gate_blob ? d_walk_imp : nullptr, d_scores, (int)K0, d_h0_node,
-                                                       d_h0_eidx, (int)K1, d_h1_node, d_h1_eidx, d_imp0, d_imp1);
+                                                       d_h0_eidx, (int)K1, d_h1_node, d_h1_eidx, d_imp0, d_imp1, beta_sample, seed);
     TM_LAUNCH_CHECK();
     return TM_OK;
 }

@@ -364,6 +364,7 @@ struct TcArgs {
     int stage_off;                           // byte offset of the node-feature staging (src rows, then tgt rows); 0: gather with plain loads
     int stage_edge_off;                      // byte offset of the edge-feature staging; 0: gather with plain loads
     unsigned long long *tile_counter;        // dynamic tile scheduler: CTA b takes tile b first, then gridDim.x + atomicAdd(counter, 1)
+    int discard;                             // discard.global.L2 on the h slabs once a tile has consumed them (no write-back of the scratch)
     int dual;                                // two A buffers: bit 0 both orientations of MLP.0 per round + Q / R chunk pairs, bit 1 lin_event chunk pairs, bit 2 MLP.3 in one round
     long long *dbg;                          // TEMPME_TC_TIMING: 128 x 5 clock stamps of CTA 0
 };
@@ -741,6 +742,16 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 tc_mma_round<TS>(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 1) * chunk_floats(L.q), last ? bytes_r : bytes_q);
             }
         }
+        // The tile's h slabs have been consumed (their last readers were the Q rounds' fills, completed before the rounds' barriers):
+        // drop the dirty L2 lines instead of letting them be written back to HBM.  A 128-byte line = 8 rows x one 16-byte piece, read
+        // only by this warp; the lane of row 8j discards it.
+        if (a.discard && (t & 7) == 0) {
+#pragma unroll 1
+            for (int sI = 0; sI < 3 * nsl; ++sI)
+#pragma unroll
+                for (int g = 0; g < CW / 4; ++g)
+                    asm volatile("discard.global.L2 [%0], 128;\n" :: "l"(Fs + sI * kSlabFloats + ((kb >> 2) + g) * 512 + row * 4) : "memory");
+        }
         // ---- M0 = R relu(Y + cy)   (attention.MLP.3 and MLP.0 folded); the next tile's first-pass indices start to arrive
         const int64_t next_tile = s_next_tile;
         const bool more = next_tile < n_tiles;
@@ -944,6 +955,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.stage_off = stage_nodes ? (int)(a_bytes + stage_rel) : 0;
     a.stage_edge_off = stage_edges ? (int)(a_bytes + stage_edge_rel) : 0;
     a.dual = (dual ? 1 : 0) | (dual_e ? 2 : 0) | (m3one ? 4 : 0);
+    a.discard = getenv("TEMPME_TC_DISCARD") ? 1 : 0;          // A/B knob, off: the discards removed the scratch write-back but cost 2.6 % of kernel time (profiles/README.md r02b)
     static long long *dbg_buf = nullptr;
 #ifdef TM_TC_TIMING
     const char *tim_env = getenv("TEMPME_TC_TIMING");          // diagnostic: per-round clock stamps of CTA 0
@@ -1135,7 +1147,7 @@ gate_tc_kernel(const GateLayout G, const float *__restrict__ blob, const GateArg
         }
         // ---- ReLU, Linear(H/2, 1), sigmoid gate (:379-386)
         float g_ = 0.f;
-        for (int c0 = prt * (r16(G.H2) / 2); c0 < (prt + 1) * (r16(G.H2) / 2); c0 += 16) {
+        for (int c0 = prt * 16; c0 < r16(G.H2); c0 += 32) {          // part p takes the 16-column groups p, p + 2, ... (hid_dim 32: one group)
             float z[16];
             tc::tmem_ld16(tmem + lane_base + colG2 + c0, z);
 #pragma unroll
@@ -1160,7 +1172,7 @@ gate_tc_kernel(const GateLayout G, const float *__restrict__ blob, const GateArg
 int tc_gate_launch(const tm_gate_desc &d, const float *d_blob, int64_t n_events, const int32_t *eidx, const float *t, const float *scores,
                    const float *edge_feat, int64_t n_edge_rows, float *out, int device, cudaStream_t st) {
     const GateLayout G = make_gate_layout(d);
-    if (G.H != 64 || G.Ed < 1 || G.D < 1 || G.D > 256) { set_error("tm_edge_importance: gate needs hid_dim 64 and time_dim in [1,256]"); return TM_ERR_UNSUPPORTED; }
+    if ((G.H != 64 && G.H != 32) || G.Ed < 1 || G.D < 1 || G.D > 256) { set_error("tm_edge_importance: gate needs hid_dim 64 or 32 and time_dim in [1,256]"); return TM_ERR_UNSUPPORTED; }
     const int64_t bb = std::max(std::min(2, G.l1.nch) * chunk_floats(G.l1), std::min(2, G.l2.nch) * chunk_floats(G.l2)) * 4;       // chunks arrive in pairs
     const size_t need = (size_t)bb + (size_t)G.n_cst * 4 + 152 * 8;
     static bool attr_set[64] = {false};

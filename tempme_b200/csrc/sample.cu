@@ -270,23 +270,41 @@ class_hist_kernel(int64_t count, const int32_t *__restrict__ anony, unsigned lon
 }
 
 // ---------------------------------------------------------------------------------------------
-// new_edge_info (processed/data_preprocess.py:327-343): one block per root, ids staged in smem
+// new_edge_info (processed/data_preprocess.py:327-343): for every walk event, how many walks of the same root carry its edge id
+// at position 0, 1, 2 (edge id 0 = padding, counted like any id).  One WARP per root: the root's 3W ids are counted in a small
+// open-addressing table in shared memory (key, three 10-bit position counters packed in one word), then every id looks its slot up
+// again: O(3W) table operations per root instead of the (3W)^2 comparisons of the all-pairs form.
 // ---------------------------------------------------------------------------------------------
-__global__ void edge_identity_kernel(int64_t B, int W, const int32_t *__restrict__ eidx, float *__restrict__ out) {
-    extern __shared__ int32_t sh_ids[];  // [W * 3]
-    const int64_t b = blockIdx.x;
+constexpr int kEidWarps = 8;
+__global__ void __launch_bounds__(kEidWarps * 32)
+edge_identity_kernel(int64_t B, int W, int slots_mask, const int32_t *__restrict__ eidx, float *__restrict__ out) {
+    extern __shared__ int32_t sh_tab[];         // per warp: keys [slots], counters [slots]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slots = slots_mask + 1;
+    int32_t *keys = sh_tab + (size_t)warp * 2 * slots;
+    unsigned *cnt = reinterpret_cast<unsigned *>(keys + slots);
+    const int64_t b = (int64_t)blockIdx.x * kEidWarps + warp;
+    if (b >= B) return;
     const int n3 = W * 3;
     const int32_t *src = eidx + b * n3;
-    for (int i = threadIdx.x; i < n3; i += blockDim.x) sh_ids[i] = src[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < n3; i += blockDim.x) {
-        const int32_t id = sh_ids[i];
-        int c0 = 0, c1 = 0, c2 = 0;
-        for (int m = 0; m < W; ++m) {  // every thread reads the same word: shared-memory broadcast
-            c0 += sh_ids[3 * m] == id; c1 += sh_ids[3 * m + 1] == id; c2 += sh_ids[3 * m + 2] == id;
+    for (int i = lane; i < slots; i += 32) { keys[i] = INT32_MIN; cnt[i] = 0u; }
+    __syncwarp();
+    auto hash = [&](int32_t id) { return (int)(((uint32_t)id * 2654435761u) >> 10) & slots_mask; };
+    for (int i = lane; i < n3; i += 32) {
+        const int32_t id = src[i];
+        const unsigned inc = 1u << (10 * (i % 3));              // position of the event inside its walk
+        for (int slot = hash(id);; slot = (slot + 1) & slots_mask) {
+            const int32_t prev = atomicCAS(&keys[slot], INT32_MIN, id);
+            if (prev == INT32_MIN || prev == id) { atomicAdd(&cnt[slot], inc); break; }
         }
+    }
+    __syncwarp();
+    for (int i = lane; i < n3; i += 32) {
+        const int32_t id = src[i];
+        int slot = hash(id);
+        while (keys[slot] != id) slot = (slot + 1) & slots_mask;
+        const unsigned c = cnt[slot];
         float *o = out + (b * n3 + i) * 3;
-        o[0] = (float)c0; o[1] = (float)c1; o[2] = (float)c2;
+        o[0] = (float)(c & 1023u); o[1] = (float)((c >> 10) & 1023u); o[2] = (float)((c >> 20) & 1023u);
     }
 }
 
@@ -370,12 +388,21 @@ extern "C" int tm_class_hist(int64_t count, const int32_t *d_anony, unsigned lon
 
 extern "C" int tm_edge_identity(int64_t B, int64_t W, const int32_t *d_eidx, float *d_out, tm_stream stream) {
     if (B < 0 || W <= 0 || (B > 0 && (!d_eidx || !d_out))) { set_error("tm_edge_identity: bad argument"); return TM_ERR_ARG; }
-    const size_t smem = sizeof(int32_t) * 3 * (size_t)W;
-    if (smem > 48 * 1024) { set_error("tm_edge_identity: %lld walks per root exceed the shared-memory window", (long long)W); return TM_ERR_UNSUPPORTED; }
+    if (W > 1023) { set_error("tm_edge_identity: %lld walks per root exceed the 10-bit position counters", (long long)W); return TM_ERR_UNSUPPORTED; }
+    int slots = 64;
+    while (slots < 6 * W) slots <<= 1;                       // load factor <= 1/2
+    const size_t smem = sizeof(int32_t) * 2 * (size_t)slots * kEidWarps;
     if (B == 0) return TM_OK;
     TM_DEVICE(device_of(d_eidx));
-    const int threads = (int)std::min<int64_t>(1024, ((3 * W + 31) / 32) * 32);
-    edge_identity_kernel<<<(unsigned)B, threads, smem, (cudaStream_t)stream>>>(B, (int)W, d_eidx, d_out);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    TM_CUDA(cudaGetDevice(&dev));
+    if (smem > 48 * 1024 && dev < 64 && !attr_set[dev]) {
+        TM_CUDA(cudaFuncSetAttribute(edge_identity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[dev] = true;
+    }
+    if (smem > 200 * 1024) { set_error("tm_edge_identity: %lld walks per root exceed the shared-memory window", (long long)W); return TM_ERR_UNSUPPORTED; }
+    edge_identity_kernel<<<(unsigned)((B + kEidWarps - 1) / kEidWarps), kEidWarps * 32, smem, (cudaStream_t)stream>>>(B, (int)W, slots - 1, d_eidx, d_out);
     TM_LAUNCH_CHECK();
     return TM_OK;
 }

@@ -3,9 +3,10 @@
 libtempme_b200 (``tm_encode_score``).
 
 The sub-module / parameter names equal the reference's so a reference
-``state_dict`` loads with ``load_state_dict`` and ours loads into the reference class.  The fused
-kernel implements eval-mode ``forward``; training (autograd, dropout) is outside the hot path and
-is not built (DESIGN.md "out of scope").
+``state_dict`` loads with ``load_state_dict`` and ours loads into the reference class.  Forward values
+come from the fused kernel whenever no dropout is active; when gradients are requested the methods return
+tensors with an autograd graph (``tempme_b200.training``: recompute backward of the scorer, Beta ``rsample``
+and ``kl_loss`` kernels with their own backward), so ``temp_exp_main.py``'s training loop runs on this class.
 """
 from __future__ import annotations
 
@@ -15,6 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import training as _tr
 from ._lib import EncoderDesc, EncoderParams, GateDesc, GateParams, check, lib, ptr
 
 
@@ -130,6 +132,7 @@ class TempME(nn.Module):
         self._desc = EncoderDesc(self.node_dim, self.edge_dim, self.hid_dim, int(bool(use_temporal_guidance)), int(bool(self.if_cat)))
         self._blob = None
         self._blob_key = None
+        self.autograd_in_eval = False           # see _wants_grad
         self._ws = None
         self._ws_retired = []
         self._gate_desc = GateDesc(self.edge_dim, self.time_dim, self.hid_dim)
@@ -213,10 +216,19 @@ class TempME(nn.Module):
                                     ptr(self._ws), ptr(scores), self.device.index, st), "tm_encode_score")
         return scores
 
+    def scorer_parameters(self):
+        """The parameters ``forward`` depends on, in a fixed order (the autograd inputs of training.FusedScore)."""
+        att = self.attention
+        mods = [self.event_conv, att.W1, att.W2, att.MLP, self.MLP, self.time_encoder]
+        return [p for mod in mods for p in mod.parameters()]
+
+    def _wants_grad(self):
+        """Build an autograd graph?  In train() mode whenever gradients are enabled and a scorer parameter requires them.  In eval()
+        mode the reference's own evaluation loops run with gradients enabled and never call backward (temp_exp_main.py:300-330), so
+        eval() returns plain values from the fused kernels unless ``autograd_in_eval`` is set."""
+        return (self.training or self.autograd_in_eval) and torch.is_grad_enabled() and any(p.requires_grad for p in self.scorer_parameters())
+
     def forward(self, walks, cut_time_l, edge_identify):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("tempme_b200.TempME.forward is the eval-mode scorer; call .eval() / torch.no_grad() "
-                                      "(training the explainer is outside the B200 hot path)")
         node_idx, edge_idx, time_idx, cat_feat, _ = walks
         nodes = self._t(node_idx, torch.int32)
         eidx = self._t(edge_idx, torch.int32)
@@ -225,6 +237,10 @@ class TempME(nn.Module):
         cat = self._t(cat_feat, torch.uint8).view(B, W) if self.if_cat else None
         cut = self._t(cut_time_l, torch.float32)                          # .float(), explainer.py:816
         eid = self._t(edge_identify, torch.float32)                       # .float(), explainer.py:177
+        if self._wants_grad():                                            # training loop (temp_exp_main.py:605-632): scores with an autograd graph
+            return _tr.score_autograd(self, nodes, eidx, t, cat, cut, eid)
+        if self.training and self.dropout_p > 0:                          # train() under no_grad: dropout is part of the value
+            return _tr.scores_layerwise(self, nodes.long(), eidx.long(), t, cat, cut, eid)
         return self.score_device(nodes, eidx, t, cat, cut, eid).view(B, W, 1)
 
     # ------------------------------------------------------------------ enhance path (explainer.py:203-306), eval mode
@@ -249,11 +265,16 @@ class TempME(nn.Module):
     def enhance_predict_walks(self, walks, cut_time_l, edge_identify):
         """explainer.py:222-255 -> [B, hid_dim (+ 12)] CUDA tensor: the attention output of every walk (the scorer kernel with its
         hidden-vector output), weighted by compute_walk_importance, summed over the walks; class counts appended with if_cat."""
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("tempme_b200.TempME.enhance_predict_walks is the eval-mode path")
         nodes, eidx, t, cat, cut, eid = self._walk_tensors(walks, cut_time_l, edge_identify)
         B, W = nodes.shape[0], nodes.shape[1]
         group = int(self.batch_group or max(B, 1))
+        if self._wants_grad() or (self.training and self.dropout_p > 0):      # enhance_main.py:321-357 trains through the walk embeddings
+            y = _tr.attention_layerwise(self, nodes.long(), eidx.long(), t, cut, eid)
+            w = self.compute_walk_importance(t, nodes, cut, group=group)     # a function of timestamps and degrees only: no parameters
+            emb = (y * w.unsqueeze(-1)).sum(1)
+            if self.if_cat:
+                emb = torch.cat([emb, torch.nn.functional.one_hot(cat.long(), 12).sum(1).to(emb.dtype)], dim=-1)
+            return emb
         blob = self.packed_weights()
         nf, ef = self._tables()
         self._workspace(B, W, group)
@@ -278,11 +299,10 @@ class TempME(nn.Module):
         src_edge, tgt_edge, bgd_edge = edge_id_info
         gat = [g.to(self.device, torch.float32) if isinstance(g, torch.Tensor) else torch.as_tensor(np.asarray(g), dtype=torch.float32, device=self.device)
                for g in (src_gat, tgt_gat, bgd_gat)]
-        with torch.no_grad():
-            src_emb, tgt_emb = self.enhance_predict_pairs(walks_src, walks_tgt, ts_l_cut, src_edge, tgt_edge)
-            pos = self.affinity_score(torch.cat([src_emb, gat[0]], dim=-1), torch.cat([tgt_emb, gat[1]], dim=-1))
-            src_emb, bgd_emb = self.enhance_predict_pairs(walks_src, walks_bgd, ts_l_cut, src_edge, bgd_edge)
-            neg = self.affinity_score(torch.cat([src_emb, gat[0]], dim=-1), torch.cat([bgd_emb, gat[2]], dim=-1))
+        src_emb, tgt_emb = self.enhance_predict_pairs(walks_src, walks_tgt, ts_l_cut, src_edge, tgt_edge)
+        pos = self.affinity_score(torch.cat([src_emb, gat[0]], dim=-1), torch.cat([tgt_emb, gat[1]], dim=-1))
+        src_emb, bgd_emb = self.enhance_predict_pairs(walks_src, walks_bgd, ts_l_cut, src_edge, bgd_edge)
+        neg = self.affinity_score(torch.cat([src_emb, gat[0]], dim=-1), torch.cat([bgd_emb, gat[2]], dim=-1))
         return pos, neg
 
     # ------------------------------------------------------------------ motif -> edge aggregation (explainer.py:354-430)
@@ -303,15 +323,17 @@ class TempME(nn.Module):
         return self._gate_blob
 
     def beta_sample(self, prob, training):
-        """explainer.py:421-430.  Eval mode only (the mean of the Beta); sampling belongs to training."""
+        """explainer.py:421-430: Beta(max(10 p, 1), max(10 (1 - p), 1)) -- its mean in eval, a reparameterised sample when training
+        (device Philox sampler; the draws follow torch.manual_seed through the key of each call)."""
         if training:
-            raise NotImplementedError("tempme_b200.TempME.beta_sample: training-mode rsample is outside the B200 hot path")
+            return _tr.BetaRSample.apply(prob if isinstance(prob, torch.Tensor) else self._t(prob, torch.float32), None, _tr.next_seed(), 0)
         alpha = torch.clamp(prob * 10, min=1.0)
         beta = torch.clamp((1 - prob) * 10, min=1.0)
         return alpha / (alpha + beta)
 
-    def edge_importance_device(self, scores, eidx, t, h0_node, h0_eidx, h1_node, h1_eidx):
-        """All CUDA tensors: scores f32 [B,W], eidx i32 [B,W,3], t f32 [B,W,3], hop slots i32 [B,K0] / [B,K1] -> (imp0 [B,K0], imp1 [B,K1])."""
+    def edge_importance_device(self, scores, eidx, t, h0_node, h0_eidx, h1_node, h1_eidx, training=False, seed=0):
+        """All CUDA tensors: scores f32 [B,W], eidx i32 [B,W,3], t f32 [B,W,3], hop slots i32 [B,K0] / [B,K1] -> (imp0 [B,K0], imp1 [B,K1]).
+        training: one Beta draw per slot inside the aggregation kernel (key = seed) instead of the Beta mean; values only, no graph."""
         B, W = eidx.shape[0], eidx.shape[1]
         K0, K1 = h0_eidx.shape[1], h1_eidx.shape[1]
         gate = self._packed_gate()
@@ -322,37 +344,45 @@ class TempME(nn.Module):
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         check(lib().tm_edge_importance(C.byref(self._gate_desc), ptr(gate) if gate is not None else None, B, W, ptr(scores), ptr(eidx), ptr(t),
                                        ptr(ef), ef.shape[0], K0, ptr(h0_node), ptr(h0_eidx), K1, ptr(h1_node), ptr(h1_eidx),
-                                       ptr(walk_imp) if walk_imp is not None else None, ptr(imp0), ptr(imp1), self.device.index, st),
+                                       ptr(walk_imp) if walk_imp is not None else None, ptr(imp0), ptr(imp1), int(bool(training)), int(seed),
+                                       self.device.index, st),
               "tm_edge_importance")
         return imp0, imp1
 
     def retrieve_edge_imp_node(self, subgraph, graphlet_imp, walks, training=True):
-        """explainer.py:354-406 with training=False (eval): dependency gate, per-root scatter-max over edge ids, gather to the
-        hop-1 / hop-2 slots, Beta mean, padding mask.  Returns CUDA tensors (edge_imp_0 [B,n], edge_imp_1 [B,n^2])."""
-        if training:
-            raise NotImplementedError("tempme_b200.TempME.retrieve_edge_imp_node is the eval-mode aggregation (training=False)")
+        """explainer.py:354-406: dependency gate, per-root scatter-max over edge ids, gather to the hop-1 / hop-2 slots, Beta sample
+        (training=True, the reference's default and what its eval loops pass, temp_exp_main.py:312-318) or Beta mean, padding mask.
+        Returns CUDA tensors (edge_imp_0 [B,n], edge_imp_1 [B,n^2]).  When graphlet_imp carries an autograd graph (training loop) the
+        result does too; otherwise the fused aggregation kernels run.  In train() mode the gate's dropout is part of the value, so
+        that case also takes the layer-by-layer route."""
         node_record, eidx_record = subgraph[0], subgraph[1]
         eidx = self._t(walks[1], torch.int32)
         B, W = eidx.shape[0], eidx.shape[1]
         t = self._t(walks[2], torch.float32)                               # .float(), explainer.py:371
-        scores = self._t(graphlet_imp, torch.float32).reshape(B, W)
-        return self.edge_importance_device(scores, eidx, t, self._t(node_record[0], torch.int32), self._t(eidx_record[0], torch.int32),
-                                           self._t(node_record[1], torch.int32), self._t(eidx_record[1], torch.int32))
+        h_nodes = [self._t(node_record[0], torch.int32), self._t(node_record[1], torch.int32)]
+        h_eidx = [self._t(eidx_record[0], torch.int32), self._t(eidx_record[1], torch.int32)]
+        g_imp = graphlet_imp if isinstance(graphlet_imp, torch.Tensor) else self._t(graphlet_imp, torch.float32)
+        gate_dropout = self.training and self.use_dependency_aware_sampling and self.dropout_p > 0
+        want = (self.training or self.autograd_in_eval) and torch.is_grad_enabled() and (
+            g_imp.requires_grad or (self.use_dependency_aware_sampling and any(p.requires_grad for p in self.edge_dependency_gcn.parameters())))
+        if want or gate_dropout:
+            imp0, imp1 = _tr.edge_importance_autograd(self, g_imp.to(self.device, torch.float32), eidx.long(), t, [x.long() for x in h_nodes],
+                                                      [x.long() for x in h_eidx], bool(training))
+            return imp0, imp1
+        scores = g_imp.detach().to(self.device, torch.float32).reshape(B, W).contiguous()
+        return self.edge_importance_device(scores, eidx, t, h_nodes[0], h_eidx[0], h_nodes[1], h_eidx[1], training=bool(training),
+                                           seed=_tr.next_seed() if training else 0)
 
     def kl_loss(self, prob, walks, target=0.3):
-        """explainer.py:432-453, forward value (a 0-dim CUDA tensor without a graph: what the reference's eval loops log,
-        temp_exp_main.py:326-328).  The classes are paired with ``list(self.null_model.values())`` by position, as the reference does."""
+        """explainer.py:432-453 as a 0-dim CUDA tensor; carries an autograd graph (tm_kl_loss_backward) when ``prob`` does.
+        The classes are paired with ``list(self.null_model.values())`` by position, as the reference does."""
         cat = self._t(walks[3], torch.uint8)
         B, W = cat.shape[0], cat.shape[1]
-        p = self._t(prob.detach() if isinstance(prob, torch.Tensor) else prob, torch.float32).reshape(B, W)
+        cat = cat.reshape(B, W).contiguous()
         empirical = self.prior == "empirical"
         null = torch.tensor([float(v) for v in self.null_model.values()], dtype=torch.float32, device=self.device)
-        work = torch.empty(B, dtype=torch.float64, device=self.device)
-        loss = torch.empty((), dtype=torch.float32, device=self.device)
-        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        check(lib().tm_kl_loss(B, W, ptr(p), ptr(cat.reshape(B, W)), ptr(null), int(null.numel()), float(target), int(empirical),
-                               ptr(work), ptr(loss), st), "tm_kl_loss")
-        return loss
+        p = prob if isinstance(prob, torch.Tensor) else self._t(prob, torch.float32)
+        return _tr.KLLoss.apply(p.to(self.device), cat, null, float(target), int(empirical))
 
     def retrieve_explanation(self, subgraph_src, graphlet_imp_src, walks_src, subgraph_tgt, graphlet_imp_tgt, walks_tgt,
                              subgraph_bgd, graphlet_imp_bgd, walks_bgd, training=True):

@@ -17,6 +17,8 @@ Fixtures:
   edgeimp_*.npz    retrieve_edge_imp_node (eval mode) on those scores: `python tests/golden/make_golden.py edgeimp`
   enhance_*.npz    enhance_predict_walks / compute_walk_importance / enhance_predict_agg (eval): `python tests/golden/make_golden.py enhance`
   kl_loss.npz      TempME.kl_loss on fixed scores / classes, both priors: `python tests/golden/make_golden.py kl`
+  trainstep_*.npz  one temp_exp_main.py:605-632-shaped step in train() mode with dropout_p = 0 (deterministic): scores, edge importances,
+                   kl_loss, the loss and d loss / d parameter for every explainer parameter: `python tests/golden/make_golden.py train`
 """
 from __future__ import annotations
 
@@ -418,6 +420,70 @@ def gen_kl_all():
     np.savez_compressed(os.path.join(HERE, "kl_loss.npz"), **out)
 
 
+def gen_train_step(tag, walks5, edge_identity, cut_time, subgraph, n_nodes, n_edges, D, Ed, seed, hid=64, prior="empirical", use_temporal=True):
+    """forward -> retrieve_edge_imp_node(training=False: Beta mean, deterministic) -> kl_loss -> backward on the unmodified reference
+    module in train() mode with dropout_p = 0, as temp_exp_main.py:605-632 does per root type.  loss = sum(w0 imp0) + sum(w1 imp1) + 0.5 kl."""
+    import torch
+    import models.explainer as rexp
+    rs = np.random.RandomState(seed)
+    null = {k: float(v) for k, v in zip(range(1, 13), rs.dirichlet(np.ones(12) * 0.7))}
+    rexp.get_null_distribution = lambda data_name: null
+    torch.manual_seed(seed)
+    nfeat = torch.randn(n_nodes, D); efeat = torch.randn(n_edges, Ed)
+    nfeat[0] = 0; efeat[0] = 0
+
+    class Base:
+        n_feat_th = nfeat; e_feat_th = efeat
+        node_raw_features = torch.nn.Embedding.from_pretrained(nfeat, padding_idx=0, freeze=True)
+        edge_raw_features = torch.nn.Embedding.from_pretrained(efeat, padding_idx=0, freeze=True)
+
+    m = rexp.TempME(Base(), "tgn", "uslegis_sampled", out_dim=40, hid_dim=hid, prior=prior, dropout_p=0.0, device=torch.device("cpu"),
+                    use_temporal_guidance=use_temporal)
+    with torch.no_grad():
+        m.time_encoder.phase.copy_(0.1 * torch.randn(D))
+    m.train()
+    score = m(walks5, cut_time, edge_identity)
+    imp0, imp1 = m.retrieve_edge_imp_node(subgraph, score, walks5, training=False)
+    kl = m.kl_loss(score, walks5, target=0.3)
+    w0 = torch.from_numpy(rs.rand(*imp0.shape).astype(np.float32)); w1 = torch.from_numpy(rs.rand(*imp1.shape).astype(np.float32))
+    loss = (imp0 * w0).sum() + (imp1 * w1).sum() + 0.5 * kl
+    loss.backward()
+    out = {"p:" + k: v.detach().numpy() for k, v in m.state_dict().items()
+           if not (k.startswith("node_raw_embed") or k.startswith("edge_raw_embed") or k.startswith("node_degree"))}
+    out.update({"g:" + k: v.grad.numpy() for k, v in m.named_parameters() if v.grad is not None})
+    out.update(node_feat=nfeat.numpy(), edge_feat=efeat.numpy(), w_nodes=walks5[0].astype(np.int32), w_eidx=walks5[1].astype(np.int32),
+               w_t=walks5[2].astype(np.float32), w_cat=walks5[3].astype(np.int8), cut_time=cut_time, edge_identity=edge_identity.astype(np.float32),
+               h0_node=subgraph[0][0].astype(np.int32), h1_node=subgraph[0][1].astype(np.int32), h0_eidx=subgraph[1][0].astype(np.int32),
+               h1_eidx=subgraph[1][1].astype(np.int32), w0=w0.numpy(), w1=w1.numpy(), score=score.detach().numpy(), imp0=imp0.detach().numpy(),
+               imp1=imp1.detach().numpy(), kl=np.float64(kl.item()), loss=np.float64(loss.item()), null_values=np.array(list(null.values()), np.float64),
+               hid_dim=int(hid), use_temporal=int(use_temporal), prior=np.array(prior))
+    np.savez_compressed(os.path.join(HERE, f"trainstep_{tag}.npz"), **out)
+
+
+def gen_train_all():
+    big = dict(np.load(os.path.join(HERE, "rand_bigts.npz")))
+    Bq = 12
+    wn, we, wt, wa = (big[f"tgt_w_{k}"][:Bq] for k in ("nodes", "eidx", "t", "anony"))
+    allw = np.concatenate([x.astype(np.float64) for x in (wn, we, wt, wa)], axis=-1)
+    new = marginal(allw, allw, allw)[0]
+    walks5 = (wn.astype(np.int64), we.astype(np.int64), wt.astype(np.float64), new[:, :, 12:13].astype(np.int64), new[:, :, 13:14])
+    ei = new_edge_info(we.astype(int))
+    sub = ([big["tgt_hop0_node"][:Bq].astype(np.int64), big["tgt_hop1_node"][:Bq].astype(np.int64)],
+           [big["tgt_hop0_eidx"][:Bq].astype(np.int64), big["tgt_hop1_eidx"][:Bq].astype(np.int64)], None)
+    args = (walks5, ei, big["ts"][big["q"][:Bq]], sub, int(big["n_nodes"]), len(big["eidx"]) + 1)
+    gen_train_step("d32", *args, 32, 32, seed=21)
+    gen_train_step("d32_hid32_uniform", *args, 32, 32, seed=22, hid=32, prior="uniform")
+    us = dict(np.load(os.path.join(HERE, "uslegis.npz")))
+    B = 4
+    src, dst, eidx, ts = load_uslegis()
+    walks5 = (us["src_w_nodes"][:B].astype(np.int64), us["src_w_eidx"][:B].astype(np.int64), us["src_w_t"][:B].astype(np.float64),
+              us["src_cat"][:B, :, None].astype(np.int64), us["src_marginal"][:B, :, None])
+    sub = ([us["src_hop0_node"][:B].astype(np.int64), us["src_hop1_node"][:B].astype(np.int64)],
+           [us["src_hop0_eidx"][:B].astype(np.int64), us["src_hop1_eidx"][:B].astype(np.int64)], None)
+    gen_train_step("d172", walks5, us["src_edge_identity"][:B].astype(np.float64), ts[us["q"][:B]].astype(np.float64), sub,
+                   int(us["n_nodes"]), len(eidx) + 1, 172, 1, seed=23)
+
+
 def gen_edge_imp_all():
     """Fixtures of the motif -> edge aggregation; reads the committed walk fixtures (does not regenerate them)."""
     us = dict(np.load(os.path.join(HERE, "uslegis.npz")))
@@ -450,6 +516,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "kl":
         gen_kl_all()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        gen_train_all()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "enhance":
         gen_enhance_all()
