@@ -274,7 +274,11 @@ extern "C" int64_t tm_encoder_workspace_floats(const tm_encoder_desc *desc, int6
     if (!desc || B < 0 || group <= 0) return -1;
     const int64_t n_std = (std::max<int64_t>(32, (B + group - 1) / group) + 31) & ~(int64_t)31;   // per-batch std, then the scorer's scratch (16-byte aligned)
     const int64_t slab = std::min<int64_t>(tc_slab_motifs(), (std::max<int64_t>(B * W, 1) + 127) / 128 * 128);   // whole tiles of 128 motifs
-    return n_std + 2 * slab * 3 * 2 * desc->hid_dim;                         // h scratch of the resident CTAs (192 KB each) + the tile counter behind it
+    const int64_t full = tc_slab_motifs();
+    const int64_t n_g = ((desc->node_dim + 7) / 8 * 8 + 31) / 32;           // MLP.0 K chunks: the E scratch of the drain mode (node_dim > 32) holds n_g slabs per CTA
+    // h scratch of the resident CTAs (192 KB each) + the tile counter behind it; for small calls the scratch is still sized for a full grid
+    // when the E scratch follows it (its offset does not depend on the call)
+    return n_std + 2 * (n_g > 1 ? full : slab) * 3 * 2 * desc->hid_dim + (n_g > 1 ? 64 + full / 128 * n_g * 4096 : 0);
 }
 
 extern "C" int tm_encoder_pack(const tm_encoder_desc *desc, const tm_encoder_params *p, float *h_blob) {

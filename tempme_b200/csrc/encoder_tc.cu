@@ -355,6 +355,9 @@ struct TcArgs {
     const float *cut, *eid, *node_feat, *edge_feat, *std_;
     int64_t n_node_rows, n_edge_rows;
     float *F;                                // scratch: per CTA 12 h slabs [position][column chunk][piece k/4][128 rows][4]
+    float *Es;                               // drain mode (node_dim > 32): per CTA nG slabs [MLP.0 chunk][piece][128 rows][4] that hold lin_event's output
+                                             //   (+ bias + edge-identity terms) between the lin_event rounds and the MLP.0 rounds, so that E and Zs | Zt
+                                             //   can share TMEM columns and two tiles fit an SM; nullptr: E stays in TMEM
     float *scores;
     float *y_out;                            // optional [n_motifs, H]: relu(attention.MLP.0(.)), the input of attention.MLP.3 (enhance path)
     float *peer[kMaxPeers];                  // score gather fused into the kernel: the same [n_motifs] segment in each peer GPU's gathered buffer (NVLink peer stores)
@@ -420,7 +423,8 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC; x.a_col2 = x.a_col - 2 * kKC;
     AFill<CW, TS> af;
     const int H = L.H, H2 = 2 * L.H, D = L.D, Ed = L.Ed, nG = L.g0.nch, nchS = L.sp.nch;
-    const int colZ = 0, colE = (nG == 1 && L.D16 <= H) ? H : H2;
+    const bool drain = a.Es != nullptr;
+    const int colZ = 0, colE = drain ? 0 : (nG == 1 && L.D16 <= H) ? H : H2;
     const bool dq = a.dual != 0, de = (a.dual & 2) != 0;   // dual rounds (bit 0: MLP.0 orientations, Q, R; bit 1: lin_event chunk pairs).  Q and R rounds in pairs: second A buffer = columns [0, 64) (U is dead by then)
     // m3one: MLP.3 in one round -- its two or three K chunks from A, A2 and a third buffer behind M0; M1 then lands over M0's first
     // chunks (they have been read into the A buffers before the MMAs are issued)
@@ -435,6 +439,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     const bool ed_vec = (Ed & 3) == 0, d_vec = (D & 3) == 0;
     float *Fs = a.F + (int64_t)blockIdx.x * 3 * nsl * kSlabFloats;      // this CTA's h slabs: [position][column chunk][piece k/4][128 rows][4]
     const float *F0 = Fs, *F1 = Fs + nsl * kSlabFloats, *F2 = Fs + 2 * nsl * kSlabFloats;
+    float *Es = drain ? a.Es + (int64_t)blockIdx.x * nG * kSlabFloats : nullptr;
     // this thread's CW columns [kb, kb+CW) of row `row` of a [128 x 32] slab (coalesced 16-byte pieces)
     auto ldw = [&](const float *slab, float *v) {
 #pragma unroll
@@ -564,6 +569,36 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             }
             // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
             const int eb = pos == 2 ? L.e_b2 : L.e_b;
+            // lin_event's bias and the three edge-identity columns (applied on the CUDA cores) for this thread's columns of MLP.0 chunk c
+            auto finish_e = [&](float *ee, int c) {
+#pragma unroll
+                for (int k = 0; k < CW; k += 4) {
+                    const int j0 = c * kKC + kb + k;                 // < D16: constants are zero-padded
+                    const float4 bb = lds4(cstE + eb + j0), w0 = lds4(cstE + L.e_wi + j0), w1 = lds4(cstE + L.e_wi + L.D16 + j0), w2 = lds4(cstE + L.e_wi + 2 * L.D16 + j0);
+                    ee[k] = fmaf(w2.x, pi.ei2, fmaf(w1.x, pi.ei1, fmaf(w0.x, pi.ei0, ee[k] + bb.x)));
+                    ee[k + 1] = fmaf(w2.y, pi.ei2, fmaf(w1.y, pi.ei1, fmaf(w0.y, pi.ei0, ee[k + 1] + bb.y)));
+                    ee[k + 2] = fmaf(w2.z, pi.ei2, fmaf(w1.z, pi.ei1, fmaf(w0.z, pi.ei0, ee[k + 2] + bb.z)));
+                    ee[k + 3] = fmaf(w2.w, pi.ei2, fmaf(w1.w, pi.ei1, fmaf(w0.w, pi.ei0, ee[k + 3] + bb.w)));
+                }
+            };
+            if (drain) {
+                // E leaves TMEM: every thread parks the columns it will consume in the MLP.0 rounds in its own rows of the CTA's E scratch
+                // (L2; written and read back by the same thread), then Zs | Zt take over the columns
+#pragma unroll 1
+                for (int c = 0; c < nG; ++c) {
+                    if (kb < min(kKC, L.g0.K8 - c * kKC)) {
+                        float ee[CW];
+                        tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, ee);
+                        finish_e(ee, c);
+                        float *ec = Es + c * kSlabFloats + (kb >> 2) * 512 + row * 4;
+#pragma unroll
+                        for (int g = 0; g < CW / 4; ++g) __stcg(reinterpret_cast<float4 *>(ec + g * 512), make_float4(ee[4 * g], ee[4 * g + 1], ee[4 * g + 2], ee[4 * g + 3]));
+                    }
+                }
+                tc::fence_before_sync();
+                __syncthreads();
+                tc::fence_after_sync();
+            }
             for (int c = 0; c < nG; ++c) {
                 const int kcols = min(kKC, L.g0.K8 - c * kKC);
                 if (stage_nodes) { tc::mbar_wait(bars + 2, n_phase); n_phase ^= 1; }          // chunk c of the rows has landed
@@ -586,16 +621,8 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                         }
                         sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
                     }
-                    tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, ee);
-#pragma unroll
-                    for (int k = 0; k < CW; k += 4) {
-                        const int j0 = c * kKC + kb + k;                 // < D16: constants are zero-padded
-                        const float4 bb = lds4(cstE + eb + j0), w0 = lds4(cstE + L.e_wi + j0), w1 = lds4(cstE + L.e_wi + L.D16 + j0), w2 = lds4(cstE + L.e_wi + 2 * L.D16 + j0);
-                        ee[k] = fmaf(w2.x, pi.ei2, fmaf(w1.x, pi.ei1, fmaf(w0.x, pi.ei0, ee[k] + bb.x)));
-                        ee[k + 1] = fmaf(w2.y, pi.ei2, fmaf(w1.y, pi.ei1, fmaf(w0.y, pi.ei0, ee[k + 1] + bb.y)));
-                        ee[k + 2] = fmaf(w2.z, pi.ei2, fmaf(w1.z, pi.ei1, fmaf(w0.z, pi.ei0, ee[k + 2] + bb.z)));
-                        ee[k + 3] = fmaf(w2.w, pi.ei2, fmaf(w1.w, pi.ei1, fmaf(w0.w, pi.ei0, ee[k + 3] + bb.w)));
-                    }
+                    if (drain) ldw(Es + c * kSlabFloats, ee);
+                    else { tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, ee); finish_e(ee, c); }
                 };
                 auto put_z = [&](int o, bool second) {              // orientation o: p + relu(q + event)
 #pragma unroll
@@ -898,9 +925,13 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     // event passes with two A buffers (pairs of lin_event chunks, both MLP.0 orientations per round): TS mode, at most the first
     // lin_event chunk holds edge columns (one staged edge chunk per round)
     const bool dual = ts && !getenv("TEMPME_TC_NO_DUAL");
-    const bool dual_e = dual && L.nch_edge <= 1;             // pairs of lin_event chunks: one staged edge chunk per round at most
+    // drain mode (node_dim > 32, where E cannot alias Zt): lin_event's output leaves TMEM through an L2 scratch before the MLP.0 rounds, so E
+    // [0, D16) and Zs | Zt [0, 2H) share columns and the tile needs 256 columns instead of 512 -- two tiles per SM instead of one
+    const bool drain = ts && dual && !alias_e && L.D16 + 2 * kKC <= 256 && 2 * H + 4 * kKC <= 256 && !getenv("TEMPME_TC_NO_DRAIN");
+    const bool dual_e = dual && L.nch_edge <= 1 && !drain;   // pairs of lin_event chunks: one staged edge chunk per round at most; drain mode has one A buffer beside E
     // motif rounds: U | Y + one A buffer; event passes: Zs | Zt (| E) + one or two A buffers (the A buffers are the top columns)
-    while ((int)cols < std::max(3 * H + (ts ? 2 * kKC : 0), (alias_e ? 2 * H : 2 * H + L.D16) + (ts ? (dual ? 4 : 2) * kKC : 0))) cols <<= 1;
+    const int ev_cols = drain ? std::max(2 * H + 4 * kKC, L.D16 + 2 * kKC) : (alias_e ? 2 * H : 2 * H + L.D16) + (ts ? (dual ? 4 : 2) * kKC : 0);
+    while ((int)cols < std::max(3 * H + (ts ? 2 * kKC : 0), ev_cols)) cols <<= 1;
     if (cols > 512) { set_error("tc_encode_score: node_dim too large for the TMEM layout"); return TM_ERR_UNSUPPORTED; }
     int64_t bb = 0;
     for (const TcLin *l : {&L.evt, &L.g0, &L.sp, &L.q, &L.r, &L.m3}) bb = std::max(bb, chunk_floats(*l) * 4);
@@ -970,8 +1001,9 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     const int64_t tiles = (a.n_motifs + 127) / 128, cap = (int64_t)sms * ctas;
     const unsigned grid = (unsigned)std::min(tiles, cap);
     a.tile_counter = reinterpret_cast<unsigned long long *>(F + (int64_t)grid * 3 * (2 * H / kKC) * kSlabFloats);          // behind the h scratch (the workspace holds twice as much)
+    a.Es = drain ? F + 2 * tc_slab_motifs(device) * 3 * 2 * H + 64 : nullptr;                                             // behind both (tm_encoder_workspace_floats)
     TM_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), st));
-    if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] score kernel: %u CTAs (%d per SM), smem %zu B (needs %zu), %u TMEM columns, %lld tiles\n", grid, ctas, smem, need, cols, (long long)tiles);
+    if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] score kernel: %u CTAs (%d per SM), smem %zu B (needs %zu), %u TMEM columns, %lld tiles%s\n", grid, ctas, smem, need, cols, (long long)tiles, drain ? ", E drained through L2" : "");
     cudaEvent_t *pe = nullptr;
     if (g_prof && g_prof_used + 2 <= g_prof_ev.size()) {        // pool is created by tm_encoder_profile(1); when exhausted, stop recording
         pe = &g_prof_ev[g_prof_used]; g_prof_used += 2;

@@ -222,6 +222,11 @@ class TempME(nn.Module):
         mods = [self.event_conv, att.W1, att.W2, att.MLP, self.MLP, self.time_encoder]
         return [p for mod in mods for p in mod.parameters()]
 
+    def _dropout_active(self):
+        """train() mode with at least one live Dropout (the attention module keeps its own default p = 0.1 whatever dropout_p is,
+        explainer.py:121): the fused kernel has no dropout, so such calls take the layer-by-layer route."""
+        return self.training and any(isinstance(mod, nn.Dropout) and mod.p > 0 for mod in self.modules())
+
     def _wants_grad(self):
         """Build an autograd graph?  In train() mode whenever gradients are enabled and a scorer parameter requires them.  In eval()
         mode the reference's own evaluation loops run with gradients enabled and never call backward (temp_exp_main.py:300-330), so
@@ -239,7 +244,7 @@ class TempME(nn.Module):
         eid = self._t(edge_identify, torch.float32)                       # .float(), explainer.py:177
         if self._wants_grad():                                            # training loop (temp_exp_main.py:605-632): scores with an autograd graph
             return _tr.score_autograd(self, nodes, eidx, t, cat, cut, eid)
-        if self.training and self.dropout_p > 0:                          # train() under no_grad: dropout is part of the value
+        if self._dropout_active():                                        # train() under no_grad: dropout is part of the value
             return _tr.scores_layerwise(self, nodes.long(), eidx.long(), t, cat, cut, eid)
         return self.score_device(nodes, eidx, t, cat, cut, eid).view(B, W, 1)
 
@@ -268,7 +273,7 @@ class TempME(nn.Module):
         nodes, eidx, t, cat, cut, eid = self._walk_tensors(walks, cut_time_l, edge_identify)
         B, W = nodes.shape[0], nodes.shape[1]
         group = int(self.batch_group or max(B, 1))
-        if self._wants_grad() or (self.training and self.dropout_p > 0):      # enhance_main.py:321-357 trains through the walk embeddings
+        if self._wants_grad() or self._dropout_active():                      # enhance_main.py:321-357 trains through the walk embeddings
             y = _tr.attention_layerwise(self, nodes.long(), eidx.long(), t, cut, eid)
             w = self.compute_walk_importance(t, nodes, cut, group=group)     # a function of timestamps and degrees only: no parameters
             emb = (y * w.unsqueeze(-1)).sum(1)
@@ -362,7 +367,7 @@ class TempME(nn.Module):
         h_nodes = [self._t(node_record[0], torch.int32), self._t(node_record[1], torch.int32)]
         h_eidx = [self._t(eidx_record[0], torch.int32), self._t(eidx_record[1], torch.int32)]
         g_imp = graphlet_imp if isinstance(graphlet_imp, torch.Tensor) else self._t(graphlet_imp, torch.float32)
-        gate_dropout = self.training and self.use_dependency_aware_sampling and self.dropout_p > 0
+        gate_dropout = self.use_dependency_aware_sampling and self._dropout_active()
         want = (self.training or self.autograd_in_eval) and torch.is_grad_enabled() and (
             g_imp.requires_grad or (self.use_dependency_aware_sampling and any(p.requires_grad for p in self.edge_dependency_gcn.parameters())))
         if want or gate_dropout:

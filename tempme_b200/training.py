@@ -85,7 +85,7 @@ class FusedScore(torch.autograd.Function):
 def score_autograd(m, nodes, eidx, t, cat, cut, eid):
     """Scores with an autograd graph.  Active dropout (training mode, p > 0): the layer-by-layer evaluation end to end; otherwise
     the fused kernel's values with the recompute backward."""
-    if m.training and m.dropout_p > 0:
+    if m._dropout_active():
         return scores_layerwise(m, nodes.long(), eidx.long(), t, cat, cut, eid)
     return FusedScore.apply(m, nodes, eidx, t, cat, cut, eid, *m.scorer_parameters())
 

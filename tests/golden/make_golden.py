@@ -422,7 +422,7 @@ def gen_kl_all():
 
 def gen_train_step(tag, walks5, edge_identity, cut_time, subgraph, n_nodes, n_edges, D, Ed, seed, hid=64, prior="empirical", use_temporal=True):
     """forward -> retrieve_edge_imp_node(training=False: Beta mean, deterministic) -> kl_loss -> backward on the unmodified reference
-    module in train() mode with dropout_p = 0, as temp_exp_main.py:605-632 does per root type.  loss = sum(w0 imp0) + sum(w1 imp1) + 0.5 kl."""
+    module in train() mode with every Dropout probability set to 0, as temp_exp_main.py:605-632 does per root type.  loss = sum(w0 imp0) + sum(w1 imp1) + 0.5 kl."""
     import torch
     import models.explainer as rexp
     rs = np.random.RandomState(seed)
@@ -442,6 +442,9 @@ def gen_train_step(tag, walks5, edge_identity, cut_time, subgraph, n_nodes, n_ed
     with torch.no_grad():
         m.time_encoder.phase.copy_(0.1 * torch.randn(D))
     m.train()
+    for mod in m.modules():       # dropout_p does not reach the attention module (it keeps its default 0.1, explainer.py:121): zero every Dropout
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
     score = m(walks5, cut_time, edge_identity)
     imp0, imp1 = m.retrieve_edge_imp_node(subgraph, score, walks5, training=False)
     kl = m.kl_loss(score, walks5, target=0.3)

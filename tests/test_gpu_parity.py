@@ -447,8 +447,9 @@ def test_edge_importance_golden(tm, golden, tag, D):
         i0, i1 = m.retrieve_edge_imp_node(sub, z[f"{key}_score"], walks, training=False)
         np.testing.assert_allclose(i0.cpu().numpy(), z[f"{key}_imp0"], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(i1.cpu().numpy(), z[f"{key}_imp1"], rtol=1e-5, atol=1e-7)
-    with pytest.raises(NotImplementedError):
-        m.retrieve_edge_imp_node(sub, z["dep_score"], walks, training=True)
+    s0, s1 = m.retrieve_edge_imp_node(sub, z["nodep_score"], walks, training=True)       # Beta draws (tests/test_gpu_train.py checks their law)
+    live = torch.as_tensor(z["h0_node"]).cuda() != 0
+    assert s0.shape == i0.shape and bool((s0[~live] == 0).all()) and bool(((s0[live] > 0) & (s0[live] < 1)).all())
 
 
 def test_edge_importance_vs_oracle_larger(tm, orc):
@@ -556,7 +557,8 @@ def test_enhance_path_golden(tm, golden, tag):
     for pre in ws:
         emb = m.enhance_predict_walks(ws[pre], z["cut_time"], z[f"{pre}_ei"])
         np.testing.assert_allclose(emb.cpu().numpy(), z[f"emb_{pre}"], rtol=2e-5, atol=2e-5)
-    pos, neg = m.enhance_predict_agg(z["cut_time"], ws["src"], ws["tgt"], ws["src"], (z["src_ei"], z["tgt_ei"], z["src_ei"]), z["src_gat"], z["tgt_gat"], z["bgd_gat"])
+    with torch.no_grad():
+        pos, neg = m.enhance_predict_agg(z["cut_time"], ws["src"], ws["tgt"], ws["src"], (z["src_ei"], z["tgt_ei"], z["src_ei"]), z["src_gat"], z["tgt_gat"], z["bgd_gat"])
     np.testing.assert_allclose(pos.cpu().numpy(), z["pos"], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(neg.cpu().numpy(), z["neg"], rtol=1e-4, atol=1e-4)
 
