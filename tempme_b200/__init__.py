@@ -5,7 +5,7 @@ from .graph import NeighborFinder, class_hist_device, edge_identity_device, new_
 from .null_model import RandEdgeSampler, degree_dict, get_null_distribution, load_data_shuffle, pre_processing, statistic  # noqa: F401
 from .explainer import TempME, TimeEncode  # noqa: F401
 from .pipeline import MotifPipeline  # noqa: F401
-from .pack import build_pack, save_pack  # noqa: F401
+from .pack import build_pack, load_pack, save_pack  # noqa: F401
 
 __all__ = ["NeighborFinder", "TempME", "TimeEncode", "MotifPipeline", "get_null_distribution", "RandEdgeSampler",
-           "new_edge_info", "class_hist_device", "edge_identity_device", "launch_count", "build_pack", "save_pack"]
+           "new_edge_info", "class_hist_device", "edge_identity_device", "launch_count", "build_pack", "save_pack", "load_pack"]

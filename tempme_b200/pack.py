@@ -3,8 +3,8 @@
 The reference loops over the query events one by one (six sampler calls per event) and writes ``{data}_{MODE}.h5``, then
 ``{data}_{MODE}_cat.h5`` (walks with class id + dataset-wide class frequency) and ``{data}_{MODE}_edge.npy``.  ``build_pack`` makes the
 same arrays with one batched call per root type; ``utils/batch_loader.load_subgraph_margin(args, file)`` (:120-201) only does
-``file[name][:]``, so the returned dict (or the ``.npz`` written by ``save_pack``) can be passed to it directly.  HDF5 files are
-written when ``h5py`` is importable.
+``file[name][:]``, so the returned dict can be passed to it directly.  ``save_pack`` writes the HDF5 container the reference opens
+(through h5py when importable, else through the spec-level writer tempme_b200.h5min).
 """
 from __future__ import annotations
 
@@ -51,18 +51,32 @@ def build_pack(finder, src, dst, ts, e_idx, dst_fake, n_degree, num_neighbors=3,
 
 
 def save_pack(pack, edge_load, directory, data, mode):
-    """Writes ``{data}_{mode}_cat.h5`` (h5py importable) or ``{data}_{mode}_cat.npz``, and ``{data}_{mode}_edge.npy``; returns the paths."""
+    """Writes ``{data}_{mode}_cat.h5`` and ``{data}_{mode}_edge.npy`` (the two files temp_exp_main.py:705-714 opens); returns the paths.
+    The HDF5 file comes from h5py when it is importable, otherwise from tempme_b200.h5min (same container subset: version-0 superblock,
+    one old-style root group, contiguous datasets), so a loadable ``_cat.h5`` is produced either way."""
     os.makedirs(directory, exist_ok=True)
     edge_path = os.path.join(directory, f"{data}_{mode}_edge.npy")
     np.save(edge_path, edge_load)
+    path = os.path.join(directory, f"{data}_{mode}_cat.h5")
     try:
         import h5py
     except ImportError:
-        path = os.path.join(directory, f"{data}_{mode}_cat.npz")
-        np.savez(path, **pack)
+        from . import h5min
+        h5min.write(path, {k: np.asarray(pack[k]) for k in PACK_KEYS})
         return path, edge_path
-    path = os.path.join(directory, f"{data}_{mode}_cat.h5")
     with h5py.File(path, "w") as hf:
         for k in PACK_KEYS:
             hf.create_dataset(k, data=pack[k])
     return path, edge_path
+
+
+def load_pack(path):
+    """``{name: array}`` of a ``_cat.h5`` pack: what ``h5py.File(path)`` gives utils/batch_loader.load_subgraph_margin (:120-201), which only
+    does ``file[name][:]``.  Uses h5py when importable, else the spec-following reader of tempme_b200.h5min."""
+    try:
+        import h5py
+    except ImportError:
+        from . import h5min
+        return h5min.read(path)
+    with h5py.File(path, "r") as hf:
+        return {k: hf[k][:] for k in hf.keys()}

@@ -613,12 +613,15 @@ def test_build_pack_matches_oracle(tm, orc, tmp_path):
         cat = orc.class_ids_prep(oa)[0]
         ref = np.concatenate([on.astype(np.float64), oe.astype(np.float64), ot.astype(np.float64), cat[..., None].astype(np.float64), freq[cat][..., None]], axis=-1)
         assert (pack[f"walks_{name}_new"] == ref).all()
-    # the reference loader's slicing (utils/batch_loader.py:120-201) applies to the dict / npz as is
+    # the files temp_exp_main.py:705-714 opens: {data}_{mode}_cat.h5 (HDF5) and {data}_{mode}_edge.npy; the reference loader's slicing
+    # (utils/batch_loader.py:120-201: file[name][:]) on what comes back
     path, edge_path = tm.save_pack(pack, edge, str(tmp_path), "unit", "test")
-    z = np.load(path) if path.endswith(".npz") else None
-    if z is not None:
-        x0 = z["subgraph_src_0"][:]
-        assert x0[:, 0:n].shape == (len(q), n) and (z["walks_src_new"][:][:, :, 12:13].astype(int) == orc.class_ids_prep(walks["src"][3])[0][..., None]).all()
+    assert path.endswith("unit_test_cat.h5")
+    z = tm.load_pack(path)
+    for k in pack:
+        assert np.array_equal(z[k][:], pack[k]) and z[k].dtype == np.asarray(pack[k]).dtype, k
+    x0 = z["subgraph_src_0"][:]
+    assert x0[:, 0:n].shape == (len(q), n) and (z["walks_src_new"][:][:, :, 12:13].astype(int) == orc.class_ids_prep(walks["src"][3])[0][..., None]).all()
     assert np.load(edge_path).shape == edge.shape
 
 

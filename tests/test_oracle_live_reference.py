@@ -1,6 +1,8 @@
 """CPU, build container only: differential test of the oracle against the LIVE reference
 (imported from /root/reference, randomness replaced by the draw contract via tests/refshim.py)
 on freshly generated random multigraphs.  Skipped where the reference is absent (the GPU box)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -50,3 +52,35 @@ def test_random_graph_matches_reference(rg, seed, N, E, tmax, n, N2, lo):
             for x, y in zip(walks, owalks):
                 assert x.shape == y.shape and (x == y).all()
             assert walks[2].dtype == owalks[2].dtype == np.float32
+
+
+def test_pack_container_and_loader_match_the_reference_loader(tmp_path):
+    """A pack written by tempme_b200.h5min and opened with its reader, pushed through the REFERENCE's own
+    utils/batch_loader.load_subgraph_margin / get_item, equals compat.load_subgraph_margin on the same file."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("ref_batch_loader", os.path.join(refshim.REF, "utils", "batch_loader.py"))
+    bl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bl)
+    from tempme_b200 import compat, h5min
+    rng = np.random.default_rng(0)
+    n, Q, W = 5, 9, 15
+    arrays = {f"subgraph_{r}_{l}": rng.integers(0, 50, (Q, 3 * n ** (l + 1))).astype(np.float64) for r in ("src", "tgt", "bgd") for l in (0, 1)}
+    arrays.update({f"walks_{r}_new": rng.integers(0, 9, (Q, W, 14)).astype(np.float64) for r in ("src", "tgt", "bgd")})
+    arrays["dst_fake"] = rng.integers(1, 50, Q).astype(np.int64)
+    path = str(tmp_path / "unit_test_cat.h5")
+    h5min.write(path, dict(arrays))
+    f = h5min.read(path)
+    args = types.SimpleNamespace(n_degree=n)
+    ref = bl.load_subgraph_margin(args, f)
+    ours = compat.load_subgraph_margin(args, f)
+
+    def same(a, b):
+        if isinstance(a, (tuple, list)):
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                same(x, y)
+        else:
+            assert a.dtype == b.dtype and a.shape == b.shape and (a == b).all()
+    same(ref, ours)
+    same(bl.get_item(ref, np.arange(2, 6)), bl.get_item(ours, np.arange(2, 6)))
