@@ -55,6 +55,8 @@ const char *tm_last_error(void);
 
 /* ------------------------------------------------------------------------------------------
  * Graph: replaces NeighborFinder.__init__ / init_off_set / get_ts2idx (utils/graph.py:13-101).
+ * The build runs on the device (upload, stable radix sorts by timestamp and node, scan, per-edge table, secondary index); inputs with
+ * a (node, edge id) pair twice in one list or negative timestamps take the literal host pass instead (TEMPME_GRAPH_BUILD=host forces it).
  * Input is the flattened adj_list: entry j belongs to the list of node h_entry_node[j]; entries
  * of one node appear in insertion order.  Per node the entries are stably sorted by timestamp
  * (graph.py:48) into a device-resident CSR; nodeedge2idx is materialised as a per-edge table.
@@ -72,6 +74,9 @@ int tm_graph_sizes(const tm_graph *g, int64_t *n_nodes, int64_t *n_entries, int6
 int tm_graph_export(const tm_graph *g, int64_t *h_off, int32_t *h_nbr, int32_t *h_eidx, double *h_ts);
 /* nodeedge2idx as a table: h_tab[e] = {node_a, node_b, cut_a, cut_b} (-1 = absent), e in [0, max_eidx] */
 int tm_graph_export_edge_table(const tm_graph *g, int32_t *h_tab);
+/* The secondary index of the neighbour-id filter (get_final_step, utils/graph.py:358-371): per node the keys (neighbour << 32 | position)
+ * in ascending order, h_skey [n_entries].  For tests of the build (device sort passes == host pass). */
+int tm_graph_export_skey(const tm_graph *g, uint64_t *h_skey);
 
 /* find_before (utils/graph.py:103-146) for R rows: window = [d_start[i], d_start[i] + d_cut[i]).
  * d_cut_time may be NULL when every row carries an e_idx; d_eidx may be NULL (all rows cut by time). */

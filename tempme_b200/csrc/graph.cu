@@ -81,6 +81,65 @@ extern "C" int tm_version(void) { return 100; }
 extern "C" const char *tm_last_error(void) { return tmb::t_err.c_str(); }
 extern "C" uint64_t tm_launch_count(void) { return tmb::g_launches.load(); }
 
+
+static void free_graph(tm_graph *g) {
+    cudaFree((void *)g->v.off); cudaFree((void *)g->v.entry); cudaFree((void *)g->v.skey); cudaFree((void *)g->v.etab); cudaFree((void *)g->v.htab);
+    delete g;
+}
+
+// run directory (node, neighbour) -> run of skey, built on the device; load factor <= 1/2
+static int build_run_directory(tm_graph *g) {
+    const int64_t n_entries = g->v.n_entries;
+    cudaError_t ce = cudaSuccess;
+    if (n_entries > 0 && !getenv("TEMPME_NO_RUN_DIRECTORY")) {
+        unsigned long long *d_cnt = nullptr, runs = 0;
+        uint4 *d_h = nullptr;
+        ce = cudaMalloc(&d_cnt, sizeof *d_cnt);
+        if (ce == cudaSuccess) ce = cudaMemset(d_cnt, 0, sizeof *d_cnt);
+        if (ce == cudaSuccess) {
+            run_directory_kernel<<<148 * 8, 256>>>(g->v, nullptr, 0, d_cnt);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ce = cudaMemcpy(&runs, d_cnt, sizeof runs, cudaMemcpyDeviceToHost);
+        }
+        uint64_t slots = 1024;
+        while (slots < 2 * runs) slots <<= 1;
+        if (ce == cudaSuccess) ce = cudaMalloc(&d_h, sizeof(uint4) * slots);
+        if (ce == cudaSuccess) ce = cudaMemset(d_h, 0xff, sizeof(uint4) * slots);
+        if (ce == cudaSuccess) {
+            run_directory_kernel<<<148 * 8, 256>>>(g->v, d_h, slots - 1, nullptr);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ce = cudaDeviceSynchronize();
+        }
+        cudaFree(d_cnt);
+        if (ce != cudaSuccess) {
+            set_error("run directory build failed: %s", cudaGetErrorString(ce));
+            cudaFree(d_h);
+            return ce == cudaErrorMemoryAllocation ? TM_ERR_NOMEM : TM_ERR_CUDA;
+        }
+        g->v.htab = d_h; g->v.hmask = slots - 1;
+        g->device_bytes += (int64_t)(sizeof(uint4) * slots);
+    }
+    return TM_OK;
+}
+
+// device build (graph_build.cu): TM_OK, 1 = this input needs the literal host pass, < 0 = error
+namespace tmb {
+int device_graph_build(int64_t n_nodes, int64_t n, const int32_t *d_node, const int32_t *d_nbr, const int32_t *d_eidx, const double *d_ts,
+                       GraphView *view, int64_t *device_bytes);
+int device_graph_build_from_events(int64_t n_nodes, int64_t m, const int32_t *h_src, const int32_t *h_dst, const int32_t *h_eidx, const double *h_ts,
+                                   GraphView *view, int64_t *device_bytes);
+}
+
+static bool use_device_build() { const char *e = getenv("TEMPME_GRAPH_BUILD"); return !(e && strcmp(e, "host") == 0); }
+
+static int finish_device_graph(int rc, tm_graph *g, tm_graph **out) {
+    if (rc != TM_OK) { delete g; return rc; }
+    const int rd = build_run_directory(g);
+    if (rd != TM_OK) { free_graph(g); return rd; }
+    *out = g;
+    return TM_OK;
+}
+
 static inline int32_t slice_len(int64_t c, int64_t len) {  // python a[:c] on a list of length len
     if (c < 0) { c += len; if (c < 0) c = 0; }
     if (c > len) c = len;
@@ -94,6 +153,39 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
         return TM_ERR_ARG;
     }
     if (n_entries >= (int64_t)INT32_MAX) { set_error("tm_graph_create: more than 2^31-1 entries"); return TM_ERR_UNSUPPORTED; }
+    {   // argument errors are reported from the host arrays, before any device work: first bad entry, same text on either build path
+        int64_t bad_node = n_entries, bad_edge = n_entries;
+#pragma omp parallel for schedule(static) reduction(min : bad_node, bad_edge)
+        for (int64_t j = 0; j < n_entries; ++j) {
+            if (h_node[j] < 0 || h_node[j] >= n_nodes) bad_node = std::min(bad_node, j);
+            if (h_eidx[j] < 0) bad_edge = std::min(bad_edge, j);
+        }
+        if (bad_node < n_entries) { set_error("entry %lld: node %d outside [0, %lld)", (long long)bad_node, h_node[bad_node], (long long)n_nodes); return TM_ERR_NODE_RANGE; }
+        if (bad_edge < n_entries) { set_error("entry %lld: negative edge id %d", (long long)bad_edge, h_eidx[bad_edge]); return TM_ERR_EDGE_TABLE; }
+    }
+    if (use_device_build() && n_entries > 0) {
+        // K1 on the device: upload the entries, sort / scan / table build there (graph_build.cu).  Inputs that the literal get_ts2idx emulation
+        // treats specially (a (node, edge id) pair twice in one list, negative timestamps) come back with rc 1 and take the host pass below.
+        TM_DEVICE(device);
+        void *dn = nullptr, *db = nullptr, *de = nullptr, *dt = nullptr;
+        cudaError_t ce = cudaMalloc(&dn, 4 * n_entries);
+        if (ce == cudaSuccess) ce = cudaMalloc(&db, 4 * n_entries);
+        if (ce == cudaSuccess) ce = cudaMalloc(&de, 4 * n_entries);
+        if (ce == cudaSuccess) ce = cudaMalloc(&dt, 8 * n_entries);
+        if (ce == cudaSuccess) ce = cudaMemcpy(dn, h_node, 4 * n_entries, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(db, h_nbr, 4 * n_entries, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(de, h_eidx, 4 * n_entries, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(dt, h_ts, 8 * n_entries, cudaMemcpyHostToDevice);
+        int rc = TM_ERR_CUDA;
+        tm_graph *g = new tm_graph();
+        g->device = device; g->device_bytes = 0;
+        memset(&g->v, 0, sizeof g->v);
+        if (ce == cudaSuccess) rc = device_graph_build(n_nodes, n_entries, (const int32_t *)dn, (const int32_t *)db, (const int32_t *)de, (const double *)dt, &g->v, &g->device_bytes);
+        else set_error("graph upload failed: %s", cudaGetErrorString(ce));
+        cudaFree(dn); cudaFree(db); cudaFree(de); cudaFree(dt);
+        if (rc != 1) return finish_device_graph(rc, g, out);
+        delete g;
+    }
     std::vector<int64_t> off(n_nodes + 1, 0);
     int64_t max_e = -1;
     for (int64_t j = 0; j < n_entries; ++j) {
@@ -182,36 +274,8 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
     g->v.off = (const int64_t *)d_off; g->v.entry = (const Entry *)d_ent; g->v.skey = (const uint64_t *)d_nbr; g->v.etab = (const int4 *)d_tab;
     g->v.htab = nullptr; g->v.hmask = 0;
     g->device_bytes = (int64_t)(b_off + b_ent + b_nbr + b_tab);
-    // run directory (node, neighbour) -> run of skey, built on the device; load factor <= 1/2
-    if (n_entries > 0 && !getenv("TEMPME_NO_RUN_DIRECTORY")) {
-        unsigned long long *d_cnt = nullptr, runs = 0;
-        uint4 *d_h = nullptr;
-        ce = cudaMalloc(&d_cnt, sizeof *d_cnt);
-        if (ce == cudaSuccess) ce = cudaMemset(d_cnt, 0, sizeof *d_cnt);
-        if (ce == cudaSuccess) {
-            run_directory_kernel<<<148 * 8, 256>>>(g->v, nullptr, 0, d_cnt);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            ce = cudaMemcpy(&runs, d_cnt, sizeof runs, cudaMemcpyDeviceToHost);
-        }
-        uint64_t slots = 1024;
-        while (slots < 2 * runs) slots <<= 1;
-        if (ce == cudaSuccess) ce = cudaMalloc(&d_h, sizeof(uint4) * slots);
-        if (ce == cudaSuccess) ce = cudaMemset(d_h, 0xff, sizeof(uint4) * slots);
-        if (ce == cudaSuccess) {
-            run_directory_kernel<<<148 * 8, 256>>>(g->v, d_h, slots - 1, nullptr);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            ce = cudaDeviceSynchronize();
-        }
-        cudaFree(d_cnt);
-        if (ce != cudaSuccess) {
-            set_error("run directory build failed: %s", cudaGetErrorString(ce));
-            cudaFree(d_h); cudaFree(d_off); cudaFree(d_ent); cudaFree(d_nbr); cudaFree(d_tab);
-            delete g;
-            return ce == cudaErrorMemoryAllocation ? TM_ERR_NOMEM : TM_ERR_CUDA;
-        }
-        g->v.htab = d_h; g->v.hmask = slots - 1;
-        g->device_bytes += (int64_t)(sizeof(uint4) * slots);
-    }
+    const int rc_dir = build_run_directory(g);
+    if (rc_dir != TM_OK) { free_graph(g); return rc_dir; }
     *out = g;
     return TM_OK;
 }
@@ -219,6 +283,27 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
 extern "C" int tm_graph_create_from_events(int64_t n_nodes, int64_t n_events, const int32_t *h_src, const int32_t *h_dst,
                                            const int32_t *h_eidx, const double *h_ts, int device, tm_graph **out) {
     if (n_events < 0 || (n_events > 0 && (!h_src || !h_dst || !h_eidx || !h_ts))) { set_error("tm_graph_create_from_events: bad argument"); return TM_ERR_ARG; }
+    if (!out || n_nodes < 0) { set_error("tm_graph_create_from_events: bad argument"); return TM_ERR_ARG; }
+    if (2 * n_events >= (int64_t)INT32_MAX) { set_error("tm_graph_create_from_events: more than 2^31-1 entries"); return TM_ERR_UNSUPPORTED; }
+    {
+        int64_t bad_node = n_events, bad_edge = n_events;
+#pragma omp parallel for schedule(static) reduction(min : bad_node, bad_edge)
+        for (int64_t k = 0; k < n_events; ++k) {
+            if (h_src[k] < 0 || h_src[k] >= n_nodes || h_dst[k] < 0 || h_dst[k] >= n_nodes) bad_node = std::min(bad_node, k);
+            if (h_eidx[k] < 0) bad_edge = std::min(bad_edge, k);
+        }
+        if (bad_node < n_events) { set_error("event %lld: endpoint (%d, %d) outside [0, %lld)", (long long)bad_node, h_src[bad_node], h_dst[bad_node], (long long)n_nodes); return TM_ERR_NODE_RANGE; }
+        if (bad_edge < n_events) { set_error("event %lld: negative edge id %d", (long long)bad_edge, h_eidx[bad_edge]); return TM_ERR_EDGE_TABLE; }
+    }
+    if (use_device_build() && n_events > 0) {
+        TM_DEVICE(device);
+        tm_graph *g = new tm_graph();
+        g->device = device; g->device_bytes = 0;
+        memset(&g->v, 0, sizeof g->v);
+        const int rc = device_graph_build_from_events(n_nodes, n_events, h_src, h_dst, h_eidx, h_ts, &g->v, &g->device_bytes);
+        if (rc != 1) return finish_device_graph(rc, g, out);
+        delete g;
+    }
     std::vector<int32_t> node(2 * n_events), nbr(2 * n_events), e(2 * n_events);
     std::vector<double> t(2 * n_events);
 #pragma omp parallel for schedule(static)
@@ -267,6 +352,13 @@ extern "C" int tm_graph_export_edge_table(const tm_graph *g, int32_t *h_tab) {
     if (!g || !h_tab) { set_error("tm_graph_export_edge_table: bad argument"); return TM_ERR_ARG; }
     TM_DEVICE(g->device);
     if (g->v.max_eidx >= 0) TM_CUDA(cudaMemcpy(h_tab, g->v.etab, sizeof(int4) * (g->v.max_eidx + 1), cudaMemcpyDeviceToHost));
+    return TM_OK;
+}
+
+extern "C" int tm_graph_export_skey(const tm_graph *g, uint64_t *h_skey) {
+    if (!g || !h_skey) { set_error("tm_graph_export_skey: bad argument"); return TM_ERR_ARG; }
+    TM_DEVICE(g->device);
+    if (g->v.n_entries) TM_CUDA(cudaMemcpy(h_skey, g->v.skey, sizeof(uint64_t) * g->v.n_entries, cudaMemcpyDeviceToHost));
     return TM_OK;
 }
 

@@ -42,7 +42,7 @@ def _flatten_adj_list(adj_list):
 
 class NeighborFinder:
     def __init__(self, adj_list, bias=0, ts_precision=PRECISION, use_cache=False, sample_method='multinomial',
-                 device=None, seed=None, _entries=None):
+                 device=None, seed=None, _entries=None, _events=None):
         if not math.isclose(bias, 0) or sample_method != 'multinomial':
             # the reference's callers never leave the defaults; those branches are not built
             raise NotImplementedError("tempme_b200.NeighborFinder supports bias=0, sample_method='multinomial' only")
@@ -59,13 +59,19 @@ class NeighborFinder:
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
-        n_nodes, (node, nbr, eidx, ts) = (len(adj_list), _flatten_adj_list(adj_list)) if _entries is None else _entries
         h = C.c_void_p()
-        check(lib().tm_graph_create(n_nodes, len(node), ptr(node), ptr(nbr), ptr(eidx), ptr(ts), dev.index, C.byref(h)),
-              "tm_graph_create")
+        if _events is not None:        # event list: expanded to the two adjacency entries per event on the device
+            n_nodes, (src, dst, eidx, ts) = _events
+            check(lib().tm_graph_create_from_events(n_nodes, len(src), ptr(src), ptr(dst), ptr(eidx), ptr(ts), dev.index, C.byref(h)),
+                  "tm_graph_create_from_events")
+            self.n_entries = 2 * len(src)
+        else:
+            n_nodes, (node, nbr, eidx, ts) = (len(adj_list), _flatten_adj_list(adj_list)) if _entries is None else _entries
+            check(lib().tm_graph_create(n_nodes, len(node), ptr(node), ptr(nbr), ptr(eidx), ptr(ts), dev.index, C.byref(h)),
+                  "tm_graph_create")
+            self.n_entries = len(node)
         self._h = h
         self.n_nodes = n_nodes
-        self.n_entries = len(node)
         self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
         self.calls = 0
         self._host = None
@@ -77,13 +83,8 @@ class NeighborFinder:
     def from_events(cls, n_nodes, src, dst, eidx, ts, device=None, seed=None):
         """Graph of an event list; equals NeighborFinder(adj_list) for the adj_list the reference's
         callers build (each event appended to both endpoints, temp_exp_main.py:135-144)."""
-        src = np.asarray(src); dst = np.asarray(dst)
-        m = len(src)
-        node = np.empty(2 * m, np.int32); nbr = np.empty(2 * m, np.int32)
-        node[0::2] = src; node[1::2] = dst; nbr[0::2] = dst; nbr[1::2] = src
-        e = np.repeat(np.asarray(eidx).astype(np.int32), 2)
-        t = np.repeat(np.asarray(ts).astype(np.float64), 2)
-        return cls(None, device=device, seed=seed, _entries=(int(n_nodes), (node, nbr, e, t)))
+        c = lambda a, dt: np.ascontiguousarray(np.asarray(a), dtype=dt)
+        return cls(None, device=device, seed=seed, _events=(int(n_nodes), (c(src, np.int32), c(dst, np.int32), c(eidx, np.int32), c(ts, np.float64))))
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -135,6 +136,12 @@ class NeighborFinder:
         tab = np.full((v[2].value + 1, 4), -1, np.int32)
         check(lib().tm_graph_export_edge_table(self._h, ptr(tab)), "tm_graph_export_edge_table")
         return tab
+
+    def secondary_index(self):
+        """Per node the sorted keys (neighbour << 32 | position) of the id filter of step 3 (uint64 [n_entries]); for tests of the build."""
+        k = np.zeros(self.n_entries, np.uint64)
+        check(lib().tm_graph_export_skey(self._h, ptr(k)), "tm_graph_export_skey")
+        return k
 
     @property
     def nodeedge2idx(self):

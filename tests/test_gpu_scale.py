@@ -131,3 +131,46 @@ def test_time_cut_on_a_million_entry_window(tm, orc):
     osub = og.find_k_hop(1, np.full(64, hub), np.full(64, 1e300), 30, None, seed=9)
     for a, b in zip(sub, osub):
         assert (a[0] == b[0]).all()
+
+
+def _rand_events(seed, N, E, tmax, lo=1, loops=0):
+    rng = np.random.default_rng(seed)
+    p = 1.0 / np.arange(1, N - lo + 1) ** 1.1
+    p /= p.sum()
+    src = rng.choice(np.arange(lo, N), E, p=p); dst = rng.choice(np.arange(lo, N), E, p=p)
+    if loops:
+        k = rng.choice(E, loops, replace=False)
+        dst[k] = src[k]
+    ts = np.sort(rng.integers(0, tmax, E)).astype(np.float64)
+    return src, dst, np.arange(1, E + 1), ts
+
+
+@pytest.mark.parametrize("case", ["ties", "no_ties", "self_loops", "unsorted_input", "node0", "cfg5_5pct"])
+def test_device_build_equals_host_build(tm, monkeypatch, case):
+    """K1 on the device (radix sorts, scan, per-edge table, secondary index) == the literal host pass, array for array."""
+    from tempme_b200 import synth
+    if case == "cfg5_5pct":
+        g = synth.make_graph("cfg5", 0.05)
+        N, (src, dst, eidx, ts) = g["n_nodes"], (g["src"], g["dst"], g["eidx"], g["ts"])
+    else:
+        N = 400
+        src, dst, eidx, ts = _rand_events(11, N, 60000, {"ties": 300, "no_ties": 10 ** 9}.get(case, 5000), lo=0 if case == "node0" else 1,
+                                          loops=50 if case == "self_loops" else 0)
+        if case == "unsorted_input":                        # the API does not require chronological input: the sort must do the work
+            perm = np.random.default_rng(5).permutation(len(src))
+            src, dst, eidx, ts = src[perm], dst[perm], eidx[perm], ts[perm]
+    monkeypatch.delenv("TEMPME_GRAPH_BUILD", raising=False)
+    dev = tm.NeighborFinder.from_events(N, src, dst, eidx, ts)
+    monkeypatch.setenv("TEMPME_GRAPH_BUILD", "host")
+    host = tm.NeighborFinder.from_events(N, src, dst, eidx, ts)
+    monkeypatch.delenv("TEMPME_GRAPH_BUILD")
+    assert (dev.off_set_l == host.off_set_l).all() and (dev.node_idx_l == host.node_idx_l).all()
+    assert (dev.edge_idx_l == host.edge_idx_l).all() and (dev.node_ts_l == host.node_ts_l).all()
+    assert (dev.edge_table() == host.edge_table()).all()
+    assert (dev.secondary_index() == host.secondary_index()).all()
+    # the adj_list entry point takes the same route
+    if case in ("ties", "self_loops"):
+        node = np.empty(2 * len(src), np.int32); nbr = np.empty_like(node)
+        node[0::2] = src; node[1::2] = dst; nbr[0::2] = dst; nbr[1::2] = src
+        ent = tm.NeighborFinder(None, _entries=(N, (node, nbr, np.repeat(eidx.astype(np.int32), 2), np.repeat(ts, 2))))
+        assert (ent.off_set_l == host.off_set_l).all() and (ent.edge_table() == host.edge_table()).all() and (ent.secondary_index() == host.secondary_index()).all()
