@@ -121,6 +121,12 @@ int tm_walk_final_step(const tm_graph *g, int64_t R, const int32_t *d_src1, cons
                        const float *d_t1, const int32_t *d_step2, const float *d_t2, uint64_t seed, uint64_t row_offset,
                        const uint32_t *d_inject3, int32_t *d_o_nodes, int32_t *d_o_eidx, float *d_o_t, int32_t *d_o_anony,
                        tm_stream stream);
+/* get_next_step with e_idx_l = None (utils/graph.py:308-333; find_before_walk's bisect branch :170-171): row i draws N2 second events from
+ * the prefixes of [d_source[i], d_nbr[i]] cut by TIME at d_cut_time[i] (strict lower bound, float64).  Outputs [R, N2].  Draw contract:
+ * stage TM_STAGE_STEP2, row = row_offset + i (the e_idx form inside tm_sample_walks uses the same rows). */
+int tm_walk_next_step_time(const tm_graph *g, int64_t R, int N2, const int32_t *d_source, const int32_t *d_nbr, const double *d_cut_time,
+                           uint64_t seed, uint64_t row_offset, const uint32_t *d_inject, int32_t *d_o_src, int32_t *d_o_tgt, int32_t *d_o_eidx,
+                           float *d_o_ts, int32_t *d_err, tm_stream stream);
 
 /* statistic (utils/null_model.py:75-82) / marginal (processed/data_preprocess.py:148-208) on
  * anonymised rows [count, 3]: accumulates both 12-bin histograms, optionally writes category ids.

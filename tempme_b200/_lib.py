@@ -56,6 +56,7 @@ SIGNATURES = {
     "tm_sample_walks": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, _p, _p, _p, _u64, _u64, _p, _p,
                                   _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "tm_walk_final_step": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _u64, _u64, _p, _p, _p, _p, _p, _p]),
+    "tm_walk_next_step_time": (C.c_int, [_p, _i64, C.c_int, _p, _p, _p, _u64, _u64, _p, _p, _p, _p, _p, _p, _p]),
     "tm_class_hist": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p]),
     "tm_edge_identity": (C.c_int, [_i64, _i64, _p, _p, _p]),
     "tm_encoder_blob_floats": (_i64, [C.POINTER(EncoderDesc)]),

@@ -83,6 +83,23 @@ struct __align__(16) Entry {
     double ts;
 };
 
+// nodeedge2idx as a table: one 32-byte row (= one DRAM sector) per edge id with, for each of the (at most two) nodes whose list holds the
+// edge, the cut (effective prefix length) AND the start of the node's window, so a lookup by (node, e_idx) needs no access to off[].
+struct __align__(32) EdgeSlot {
+    int32_t node_a, node_b;   // -1 = absent; node_a < node_b when both are present
+    int32_t cut_a, cut_b;
+    int64_t start_a, start_b;
+};
+
+// One row (= one DRAM sector) of the run directory: the run of the secondary index that belongs to (node, neighbour), with the run's first
+// four positions inline -- most (node, neighbour) pairs of a temporal multigraph share one to four events, and for those the id filter of
+// step 3 never touches skey.
+struct __align__(32) RunSlot {
+    uint64_t key;             // node << 32 | neighbour; ~0 = empty
+    uint32_t start, len;      // run = skey[start .. start + len)
+    uint32_t pos[4];          // positions (inside the node's window) of the run's first min(len, 4) entries, ascending
+};
+
 // Device view of the graph (all pointers device memory, immutable after build).
 struct GraphView {
     int64_t n_nodes;
@@ -91,9 +108,9 @@ struct GraphView {
     const int64_t *off;   // [n_nodes + 1]
     const Entry *entry;   // [n_entries]  time-sorted per node
     const uint64_t *skey; // [n_entries]  per node: (nbr << 32 | position) sorted -- secondary index for the id filter of step 3
-    const int4 *etab;     // [max_eidx + 1] {node_a, node_b, cut_a, cut_b}: nodeedge2idx as a table
-    const uint4 *htab;    // open-addressing directory of the runs of skey: {key lo, key hi, start, len}, key = node << 32 | nbr,
-                          //   skey[start .. start+len) = the positions of neighbour nbr in node's list; nullptr: search skey instead
+    const EdgeSlot *etab; // [max_eidx + 1] nodeedge2idx as a table (see EdgeSlot)
+    const RunSlot *htab;  // open-addressing directory of the runs of skey, key = node << 32 | nbr: skey[start .. start+len) = the positions of
+                          //   neighbour nbr in node's list (the first four inline); nullptr: search skey instead
     uint64_t hmask;       // slots - 1 (power of two)
 };
 
@@ -155,12 +172,23 @@ __device__ __forceinline__ Entry load_entry(const Entry *p) {
     return e;
 }
 
-// nodeedge2idx[node].get(e): -1 when absent (None)
-__device__ __forceinline__ int64_t dict_get(const GraphView &g, int64_t node, int32_t e) {
-    if (e < 0 || (int64_t)e > g.max_eidx) return -1;
-    const int4 t = __ldg(g.etab + e);
-    if (node == t.x) return t.z;
-    if (node == t.y) return t.w;
+__device__ __forceinline__ EdgeSlot load_slot(const EdgeSlot *p) {       // two 128-bit loads of one sector
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(p)), b = __ldg(reinterpret_cast<const int4 *>(p) + 1);
+    EdgeSlot t;
+    t.node_a = a.x; t.node_b = a.y; t.cut_a = a.z; t.cut_b = a.w;
+    t.start_a = ((long long)(uint32_t)b.y << 32) | (uint32_t)b.x; t.start_b = ((long long)(uint32_t)b.w << 32) | (uint32_t)b.z;
+    return t;
+}
+__device__ __forceinline__ EdgeSlot empty_slot() { EdgeSlot t; t.node_a = t.node_b = t.cut_a = t.cut_b = -1; t.start_a = t.start_b = 0; return t; }
+// the row of edge id e (absent ids give an empty row)
+__device__ __forceinline__ EdgeSlot edge_slot(const GraphView &g, int32_t e) {
+    return (e >= 0 && (int64_t)e <= g.max_eidx) ? load_slot(g.etab + e) : empty_slot();
+}
+// nodeedge2idx[node].get(e): -1 when absent (None); *start receives the node's window start when present
+__device__ __forceinline__ int64_t dict_get(const GraphView &g, int64_t node, int32_t e, int64_t *start = nullptr) {
+    const EdgeSlot t = edge_slot(g, e);
+    if (node == t.node_a) { if (start) *start = t.start_a; return t.cut_a; }
+    if (node == t.node_b) { if (start) *start = t.start_b; return t.cut_b; }
     return -1;
 }
 

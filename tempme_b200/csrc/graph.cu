@@ -38,20 +38,22 @@ __global__ void find_before_kernel(GraphView g, int64_t R, const int32_t *__rest
         if (lane == 0) { o_start[row] = 0; o_cut[row] = 0; report_row_error(err, row); }
         return;
     }
-    const int64_t s = __ldg(g.off + v), len = __ldg(g.off + v + 1) - s;
     const int32_t e = eidx ? eidx[row] : TM_EIDX_NONE;
-    int64_t c;
-    if (e == TM_EIDX_NONE) c = warp_lower_bound(g.entry + s, len, cut_time ? cut_time[row] : 0.0, lane);   // graph.py:129
-    else if (v > 0) {                                                                       // graph.py:133
-        c = dict_get(g, v, e);
+    int64_t c, s = -1;
+    if (e == TM_EIDX_NONE) {
+        s = __ldg(g.off + v);
+        c = warp_lower_bound(g.entry + s, __ldg(g.off + v + 1) - s, cut_time ? cut_time[row] : 0.0, lane);   // graph.py:129
+    } else if (v > 0) {                                                                     // graph.py:133
+        c = dict_get(g, v, e, &s);
         if (c < 0) { c = 0; if (lane == 0) report_row_error(err, row); }   // IndexError, graph.py:134-135
     } else c = 0;
+    if (s < 0) s = __ldg(g.off + v);
     if (lane == 0) { o_start[row] = s; o_cut[row] = (int32_t)c; }
 }
 
 // Directory of the neighbour runs of skey (one warp per node, lanes stride over the node's window): a run starts where the
 // neighbour id changes; its end is the lower bound of the next id.  count != nullptr: only count the runs.
-__global__ void run_directory_kernel(GraphView g, uint4 *tab, uint64_t mask, unsigned long long *count) {
+__global__ void run_directory_kernel(GraphView g, RunSlot *tab, uint64_t mask, unsigned long long *count) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long local = 0;
@@ -65,9 +67,10 @@ __global__ void run_directory_kernel(GraphView g, uint4 *tab, uint64_t mask, uns
             while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((uint32_t)(g.skey[mid] >> 32) <= nb) lo = mid + 1; else hi = mid; }
             const uint64_t key = (uint64_t)v << 32 | nb;
             uint64_t slot = mix64(key) & mask;
-            unsigned long long *words = reinterpret_cast<unsigned long long *>(tab);
-            while (atomicCAS(words + 2 * slot, ~0ull, (unsigned long long)key) != ~0ull) slot = (slot + 1) & mask;
-            words[2 * slot + 1] = (unsigned long long)(uint32_t)i | (unsigned long long)(uint32_t)(lo - i) << 32;
+            while (atomicCAS(reinterpret_cast<unsigned long long *>(&tab[slot].key), ~0ull, (unsigned long long)key) != ~0ull) slot = (slot + 1) & mask;
+            RunSlot &r = tab[slot];
+            r.start = (uint32_t)i; r.len = (uint32_t)(lo - i);
+            for (int j = 0; j < 4; ++j) r.pos[j] = i + j < lo ? (uint32_t)g.skey[i + j] : 0xffffffffu;
         }
     }
     if (count && local) atomicAdd(count, local);
@@ -93,7 +96,7 @@ static int build_run_directory(tm_graph *g) {
     cudaError_t ce = cudaSuccess;
     if (n_entries > 0 && !getenv("TEMPME_NO_RUN_DIRECTORY")) {
         unsigned long long *d_cnt = nullptr, runs = 0;
-        uint4 *d_h = nullptr;
+        RunSlot *d_h = nullptr;
         ce = cudaMalloc(&d_cnt, sizeof *d_cnt);
         if (ce == cudaSuccess) ce = cudaMemset(d_cnt, 0, sizeof *d_cnt);
         if (ce == cudaSuccess) {
@@ -103,8 +106,8 @@ static int build_run_directory(tm_graph *g) {
         }
         uint64_t slots = 1024;
         while (slots < 2 * runs) slots <<= 1;
-        if (ce == cudaSuccess) ce = cudaMalloc(&d_h, sizeof(uint4) * slots);
-        if (ce == cudaSuccess) ce = cudaMemset(d_h, 0xff, sizeof(uint4) * slots);
+        if (ce == cudaSuccess) ce = cudaMalloc(&d_h, sizeof(RunSlot) * slots);
+        if (ce == cudaSuccess) ce = cudaMemset(d_h, 0xff, sizeof(RunSlot) * slots);
         if (ce == cudaSuccess) {
             run_directory_kernel<<<148 * 8, 256>>>(g->v, d_h, slots - 1, nullptr);
             g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -117,7 +120,7 @@ static int build_run_directory(tm_graph *g) {
             return ce == cudaErrorMemoryAllocation ? TM_ERR_NOMEM : TM_ERR_CUDA;
         }
         g->v.htab = d_h; g->v.hmask = slots - 1;
-        g->device_bytes += (int64_t)(sizeof(uint4) * slots);
+        g->device_bytes += (int64_t)(sizeof(RunSlot) * slots);
     }
     return TM_OK;
 }
@@ -213,20 +216,20 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
         if (!std::is_sorted(b, e, lt)) std::stable_sort(b, e, lt);
     }
     // nodeedge2idx as a table: claim the (edge, node) slots (sequential: two nodes share one row)
-    std::vector<int4> etab(max_e + 1, make_int4(-1, -1, -1, -1));
+    std::vector<EdgeSlot> etab(max_e + 1, EdgeSlot{-1, -1, -1, -1, 0, 0});
     for (int64_t v = 0; v < n_nodes; ++v)
         for (int64_t p = off[v]; p < off[v + 1]; ++p) {
-            int4 &t = etab[ent[p].eidx];
-            if (t.x == (int32_t)v || t.y == (int32_t)v) continue;
-            if (t.x == -1) t.x = (int32_t)v;
-            else if (t.y == -1) t.y = (int32_t)v;
+            EdgeSlot &t = etab[ent[p].eidx];
+            if (t.node_a == (int32_t)v || t.node_b == (int32_t)v) continue;
+            if (t.node_a == -1) { t.node_a = (int32_t)v; t.start_a = off[v]; }
+            else if (t.node_b == -1) { t.node_b = (int32_t)v; t.start_b = off[v]; }
             else { set_error("edge id %d occurs in the lists of more than two nodes", ent[p].eidx); return TM_ERR_EDGE_TABLE; }
         }
     // get_ts2idx, graph.py:77-101, emulated literally; each node only touches its own table words
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t v = 0; v < n_nodes; ++v) {
         const int64_t s = off[v], len = off[v + 1] - s;
-        auto slot = [&](int32_t e) -> int32_t & { int4 &t = etab[e]; return t.x == (int32_t)v ? t.z : t.w; };
+        auto slot = [&](int32_t e) -> int32_t & { EdgeSlot &t = etab[e]; return t.node_a == (int32_t)v ? t.cut_a : t.cut_b; };
         int64_t tie_lo = -1, tie_n = 0;
         double last_ts = -1.0;                                                    // :82
         for (int64_t i = 0; i < len; ++i) {
@@ -255,7 +258,7 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
     g->device = device;
     void *d_off = nullptr, *d_ent = nullptr, *d_nbr = nullptr, *d_tab = nullptr;
     const size_t b_off = sizeof(int64_t) * (n_nodes + 1), b_ent = sizeof(Entry) * std::max<int64_t>(n_entries, 1),
-                 b_nbr = sizeof(uint64_t) * std::max<int64_t>(n_entries, 1), b_tab = sizeof(int4) * std::max<int64_t>(max_e + 1, 1);
+                 b_nbr = sizeof(uint64_t) * std::max<int64_t>(n_entries, 1), b_tab = sizeof(EdgeSlot) * std::max<int64_t>(max_e + 1, 1);
     cudaError_t ce = cudaMalloc(&d_off, b_off);
     if (ce == cudaSuccess) ce = cudaMalloc(&d_ent, b_ent);
     if (ce == cudaSuccess) ce = cudaMalloc(&d_nbr, b_nbr);
@@ -263,7 +266,7 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
     if (ce == cudaSuccess) ce = cudaMemcpy(d_off, off.data(), b_off, cudaMemcpyHostToDevice);
     if (ce == cudaSuccess && n_entries) ce = cudaMemcpy(d_ent, ent.data(), sizeof(Entry) * n_entries, cudaMemcpyHostToDevice);
     if (ce == cudaSuccess && n_entries) ce = cudaMemcpy(d_nbr, skey.data(), sizeof(uint64_t) * n_entries, cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess && max_e >= 0) ce = cudaMemcpy(d_tab, etab.data(), sizeof(int4) * (max_e + 1), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && max_e >= 0) ce = cudaMemcpy(d_tab, etab.data(), sizeof(EdgeSlot) * (max_e + 1), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) {
         set_error("graph upload failed: %s", cudaGetErrorString(ce));
         cudaFree(d_off); cudaFree(d_ent); cudaFree(d_nbr); cudaFree(d_tab);
@@ -271,7 +274,7 @@ extern "C" int tm_graph_create(int64_t n_nodes, int64_t n_entries, const int32_t
         return ce == cudaErrorMemoryAllocation ? TM_ERR_NOMEM : TM_ERR_CUDA;
     }
     g->v.n_nodes = n_nodes; g->v.n_entries = n_entries; g->v.max_eidx = max_e;
-    g->v.off = (const int64_t *)d_off; g->v.entry = (const Entry *)d_ent; g->v.skey = (const uint64_t *)d_nbr; g->v.etab = (const int4 *)d_tab;
+    g->v.off = (const int64_t *)d_off; g->v.entry = (const Entry *)d_ent; g->v.skey = (const uint64_t *)d_nbr; g->v.etab = (const EdgeSlot *)d_tab;
     g->v.htab = nullptr; g->v.hmask = 0;
     g->device_bytes = (int64_t)(b_off + b_ent + b_nbr + b_tab);
     const int rc_dir = build_run_directory(g);
@@ -351,7 +354,11 @@ extern "C" int tm_graph_export(const tm_graph *g, int64_t *h_off, int32_t *h_nbr
 extern "C" int tm_graph_export_edge_table(const tm_graph *g, int32_t *h_tab) {
     if (!g || !h_tab) { set_error("tm_graph_export_edge_table: bad argument"); return TM_ERR_ARG; }
     TM_DEVICE(g->device);
-    if (g->v.max_eidx >= 0) TM_CUDA(cudaMemcpy(h_tab, g->v.etab, sizeof(int4) * (g->v.max_eidx + 1), cudaMemcpyDeviceToHost));
+    if (g->v.max_eidx >= 0) {
+        std::vector<EdgeSlot> tab(g->v.max_eidx + 1);
+        TM_CUDA(cudaMemcpy(tab.data(), g->v.etab, sizeof(EdgeSlot) * tab.size(), cudaMemcpyDeviceToHost));
+        for (size_t e = 0; e < tab.size(); ++e) { h_tab[4 * e] = tab[e].node_a; h_tab[4 * e + 1] = tab[e].node_b; h_tab[4 * e + 2] = tab[e].cut_a; h_tab[4 * e + 3] = tab[e].cut_b; }
+    }
     return TM_OK;
 }
 

@@ -78,7 +78,7 @@ __global__ void build_entries_kernel(int64_t n, const uint32_t *__restrict__ per
 }
 
 // nodeedge2idx: claim the (edge, node) slot, store the cut (see the header comment, step 3)
-__global__ void edge_table_kernel(int64_t n, const uint32_t *__restrict__ snode, const int64_t *__restrict__ off, const Entry *__restrict__ ent, int4 *etab, int *flags) {
+__global__ void edge_table_kernel(int64_t n, const uint32_t *__restrict__ snode, const int64_t *__restrict__ off, const Entry *__restrict__ ent, EdgeSlot *etab, int *flags) {
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
         const int32_t v = (int32_t)snode[p];
         const int64_t s = off[v], len = off[v + 1] - s, i = p - s;
@@ -89,20 +89,24 @@ __global__ void edge_table_kernel(int64_t n, const uint32_t *__restrict__ snode,
         lo = i + 1; hi = len;                                     // one past its last slot
         while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (ent[s + mid].ts <= t) lo = mid + 1; else hi = mid; }
         const int32_t cut = (int32_t)(lo < len ? first : i);      // flushed only when a later, different timestamp exists (:93-98)
-        int *w = reinterpret_cast<int *>(etab + ent[p].eidx);
+        EdgeSlot *row = etab + ent[p].eidx;
+        int *w = reinterpret_cast<int *>(row);                   // {node_a, node_b, cut_a, cut_b}, then the two window starts
         int prev = atomicCAS(w, -1, v);
-        if (prev == -1) { w[2] = cut; continue; }
+        if (prev == -1) { w[2] = cut; row->start_a = s; continue; }
         if (prev == v) { atomicOr(flags, kFlagDupPair); continue; }
         prev = atomicCAS(w + 1, -1, v);
-        if (prev == -1) { w[3] = cut; continue; }
+        if (prev == -1) { w[3] = cut; row->start_b = s; continue; }
         atomicOr(flags, prev == v ? kFlagDupPair : kFlagThreeNodes);
     }
 }
 // the host pass hands slot x to the smaller node id (it walks the nodes in ascending order): same convention here
-__global__ void order_slots_kernel(int64_t n, int4 *etab) {
+__global__ void order_slots_kernel(int64_t n, EdgeSlot *etab) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        const int4 t = etab[e];
-        if (t.y != -1 && t.y < t.x) etab[e] = make_int4(t.y, t.x, t.w, t.z);
+        EdgeSlot t = etab[e];
+        if (t.node_a == -1) { t.start_a = 0; t.start_b = 0; etab[e] = t; continue; }      // the 0xff fill also covered the starts
+        if (t.node_b == -1) t.start_b = 0;
+        else if (t.node_b < t.node_a) t = EdgeSlot{t.node_b, t.node_a, t.cut_b, t.cut_a, t.start_b, t.start_a};
+        etab[e] = t;
     }
 }
 
@@ -198,10 +202,10 @@ int device_graph_build(int64_t n_nodes, int64_t n, const int32_t *d_node, const 
     build_entries_kernel<<<blocks_for(n), kT>>>(n, perm, d_nbr, d_eidx, d_ts, ent.as<Entry>());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     // ---- 3. nodeedge2idx
-    TRY(etab.alloc(sizeof(int4) * (max_e + 1)));
-    TRY(cudaMemset(etab.p, 0xff, sizeof(int4) * std::max<int64_t>(max_e + 1, 1)));
-    edge_table_kernel<<<blocks_for(n), kT>>>(n, snode, off.as<int64_t>(), ent.as<Entry>(), etab.as<int4>(), flags.as<int>());
-    order_slots_kernel<<<blocks_for(max_e + 1), kT>>>(max_e + 1, etab.as<int4>());
+    TRY(etab.alloc(sizeof(EdgeSlot) * (max_e + 1)));
+    TRY(cudaMemset(etab.p, 0xff, sizeof(EdgeSlot) * std::max<int64_t>(max_e + 1, 1)));
+    edge_table_kernel<<<blocks_for(n), kT>>>(n, snode, off.as<int64_t>(), ent.as<Entry>(), etab.as<EdgeSlot>(), flags.as<int>());
+    order_slots_kernel<<<blocks_for(max_e + 1), kT>>>(max_e + 1, etab.as<EdgeSlot>());
     g_launches.fetch_add(2, std::memory_order_relaxed);
     TRY(cudaMemcpy(h, flags.p, sizeof h, cudaMemcpyDeviceToHost));
     if (h[0] & kFlagThreeNodes) { set_error("an edge id occurs in the lists of more than two nodes"); return TM_ERR_EDGE_TABLE; }
@@ -229,9 +233,9 @@ int device_graph_build(int64_t n_nodes, int64_t n, const int32_t *d_node, const 
     }
     TRY(cudaGetLastError());
     view->n_nodes = n_nodes; view->n_entries = n; view->max_eidx = max_e;
-    *device_bytes = (int64_t)(sizeof(int64_t) * (n_nodes + 1) + sizeof(Entry) * n + sizeof(unsigned long long) * n + sizeof(int4) * (max_e + 1));
+    *device_bytes = (int64_t)(sizeof(int64_t) * (n_nodes + 1) + sizeof(Entry) * n + sizeof(unsigned long long) * n + sizeof(EdgeSlot) * (max_e + 1));
     view->off = static_cast<const int64_t *>(off.release()); view->entry = static_cast<const Entry *>(ent.release());
-    view->skey = static_cast<const uint64_t *>(skey.release()); view->etab = static_cast<const int4 *>(etab.release());
+    view->skey = static_cast<const uint64_t *>(skey.release()); view->etab = static_cast<const EdgeSlot *>(etab.release());
     view->htab = nullptr; view->hmask = 0;
     return TM_OK;
 }

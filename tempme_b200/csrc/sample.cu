@@ -39,12 +39,12 @@ sample_hop_kernel(GraphView g, int64_t R, const int32_t *__restrict__ node, cons
     if (v < 0 || v >= g.n_nodes) {
         if (lane == 0) report_row_error(err, row);
     } else {
-        s = __ldg(g.off + v);
-        const int64_t len = __ldg(g.off + v + 1) - s;
         const int32_t e = eidx ? eidx[row] : TM_EIDX_NONE;
-        if (e == TM_EIDX_NONE) c = warp_lower_bound(g.entry + s, len, cut_time ? cut_time[row] : 0.0, lane);
-        else if (v > 0) {
-            c = dict_get(g, v, e);
+        if (e == TM_EIDX_NONE) {
+            s = __ldg(g.off + v);
+            c = warp_lower_bound(g.entry + s, __ldg(g.off + v + 1) - s, cut_time ? cut_time[row] : 0.0, lane);
+        } else if (v > 0) {                     // window start and cut from the edge's row: no access to off[]
+            c = dict_get(g, v, e, &s);
             if (c < 0) { c = 0; if (lane == 0) report_row_error(err, row); }
         }
     }
@@ -83,22 +83,41 @@ __device__ __forceinline__ int64_t key_lower_bound(const uint64_t *__restrict__ 
     }
     return lo;
 }
-struct IdRange { int64_t base, cnt; };   // skey[base .. base+cnt) = positions (< cut) of neighbour x, ascending
-// k = skey of the node's window (length len).  With the run directory the run of x costs one or two 16-byte probes instead of a
-// lower bound over the whole window; the cut inside the run is a lower bound over the run only.
+struct IdRange {              // positions (< cut) of neighbour x in the node's window, ascending: skey[base .. base+cnt), or the first cnt of pos[] (inl)
+    int64_t base, cnt;
+    uint32_t pos[4];
+    bool inl;
+};
+__device__ __forceinline__ uint32_t range_pos(const uint64_t *__restrict__ k, const IdRange &r, int64_t i) {
+    if (r.inl) return i == 0 ? r.pos[0] : i == 1 ? r.pos[1] : i == 2 ? r.pos[2] : r.pos[3];
+    return (uint32_t)__ldg(k + r.base + i);
+}
+// k = skey of the node's window (length len).  With the run directory the run of x costs one or two 32-byte probes instead of a
+// lower bound over the whole window; runs of up to four entries are answered from the probe itself, longer ones by a lower bound over
+// the run only.
 __device__ __forceinline__ IdRange id_prefix(const GraphView &g, int64_t node, const uint64_t *__restrict__ k, int64_t win, int64_t len, int64_t cut, int32_t x) {
     IdRange r;
+    r.inl = false; r.base = 0; r.cnt = 0;
+    r.pos[0] = r.pos[1] = r.pos[2] = r.pos[3] = 0xffffffffu;
     const uint64_t hi_key = (uint64_t)(uint32_t)x << 32;
     if (g.htab) {
         const uint64_t key = (uint64_t)node << 32 | (uint32_t)x;
         uint64_t slot = mix64(key) & g.hmask;
-        r.base = 0; r.cnt = 0;
         for (;;) {
-            const uint4 q = __ldg(g.htab + slot);
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(g.htab + slot));
             const uint64_t kk = (uint64_t)q.y << 32 | q.x;
             if (kk == key) {
-                r.base = (int64_t)q.z - win;
-                r.cnt = cut > 0 ? key_lower_bound(k, r.base, r.base + (int64_t)q.w, hi_key | (uint64_t)cut) - r.base : 0;
+                if (cut <= 0) break;
+                if (q.w <= 4u) {                             // the whole run is inline; positions are ascending, absent ones are 0xffffffff
+                    const uint4 pp = __ldg(reinterpret_cast<const uint4 *>(g.htab + slot) + 1);
+                    r.inl = true;
+                    r.pos[0] = pp.x; r.pos[1] = pp.y; r.pos[2] = pp.z; r.pos[3] = pp.w;
+                    const uint64_t c = (uint64_t)cut;
+                    r.cnt = (int64_t)(pp.x < c) + (pp.y < c) + (pp.z < c) + (pp.w < c);
+                } else {
+                    r.base = (int64_t)q.z - win;
+                    r.cnt = key_lower_bound(k, r.base, r.base + (int64_t)q.w, hi_key | (uint64_t)cut) - r.base;
+                }
                 break;
             }
             if (kk == ~0ull) break;
@@ -111,14 +130,14 @@ __device__ __forceinline__ IdRange id_prefix(const GraphView &g, int64_t node, c
     return r;
 }
 // position of the element of merged rank kk in the union of two ascending position lists (all positions distinct)
-__device__ __forceinline__ int64_t select_union(const uint64_t *__restrict__ k, IdRange a, IdRange b, int64_t kk) {
+__device__ __forceinline__ int64_t select_union(const uint64_t *__restrict__ k, const IdRange &a, const IdRange &b, int64_t kk) {
     int64_t lo = max((int64_t)0, kk - b.cnt), hi = min(kk, a.cnt);
     while (lo < hi) {   // lo = how many of the kk smaller elements come from a
         const int64_t mid = (lo + hi) >> 1;
-        if ((uint32_t)__ldg(k + a.base + mid) < (uint32_t)__ldg(k + b.base + (kk - mid - 1))) lo = mid + 1; else hi = mid;
+        if (range_pos(k, a, mid) < range_pos(k, b, kk - mid - 1)) lo = mid + 1; else hi = mid;
     }
-    const uint32_t pa = lo < a.cnt ? (uint32_t)__ldg(k + a.base + lo) : 0xffffffffu;
-    const uint32_t pb = kk - lo < b.cnt ? (uint32_t)__ldg(k + b.base + (kk - lo)) : 0xffffffffu;
+    const uint32_t pa = lo < a.cnt ? range_pos(k, a, lo) : 0xffffffffu;
+    const uint32_t pb = kk - lo < b.cnt ? range_pos(k, b, kk - lo) : 0xffffffffu;
     return (int64_t)min(pa, pb);
 }
 
@@ -136,9 +155,10 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
                     const float *__restrict__ pre2_t,
                     int32_t *__restrict__ o_nodes, int32_t *__restrict__ o_eidx, float *__restrict__ o_t,
                     int32_t *__restrict__ o_anony, uint8_t *__restrict__ o_cat,
-                    unsigned long long *hist_null, unsigned long long *hist_prep, unsigned long long *scanned) {
+                    unsigned long long *hist_null, unsigned long long *hist_prep, unsigned long long *scanned, int staged) {
     __shared__ unsigned int sh_hist[12];
     __shared__ unsigned long long sh_scan;
+    extern __shared__ __align__(16) int32_t stage[];   // staged: nodes [256 N2][6] | eidx [256 N2][3] | t [256 N2][3] of the block's walks
     if (threadIdx.x < 12) sh_hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) sh_scan = 0;
     __syncthreads();
@@ -153,10 +173,9 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
         // ---- step 2: find_before_walk([root, nbr], e_idx=e1): node 0 -> 0, missing key -> 0 (graph.py:174-176)
         int64_t c_a = 0, c_b = 0, s_a = 0, s_b = 0;
         {
-            int4 t = make_int4(-1, -1, -1, -1);
-            if (e1 >= 0 && (int64_t)e1 <= g.max_eidx) t = __ldg(g.etab + e1);
-            if (s1 > 0 && in_range(s1)) { s_a = __ldg(g.off + s1); c_a = s1 == t.x ? t.z : (s1 == t.y ? t.w : 0); }
-            if (t1n > 0 && in_range(t1n)) { s_b = __ldg(g.off + t1n); c_b = t1n == t.x ? t.z : (t1n == t.y ? t.w : 0); }
+            const EdgeSlot t = edge_slot(g, e1);            // one sector: both nodes' cuts and window starts
+            if (s1 > 0) { if (s1 == t.node_a) { c_a = t.cut_a; s_a = t.start_a; } else if (s1 == t.node_b) { c_a = t.cut_b; s_a = t.start_b; } }
+            if (t1n > 0) { if (t1n == t.node_a) { c_b = t.cut_a; s_b = t.start_a; } else if (t1n == t.node_b) { c_b = t.cut_b; s_b = t.start_b; } }
         }
         const int64_t L = pre2 ? 0 : c_a + c_b;
         uint64_t d[CAP];
@@ -191,15 +210,22 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
             else if (t1n == s2 && s1 != t2n) { A = t1n; Bn = t2n; fa1 = (int32_t)s1; fa2 = (int32_t)t2n; fb = (int32_t)s1; code = 3; }  // :395
             else { A = t1n; Bn = t2n; fa1 = fa2 = fb = -1; code = 1; }                                                                     // :436
             // cut = nodeedge2idx[x].get(e2) if x > 0 else 0; None -> whole list (graph.py:357-358)
-            int64_t cA = 0, cB = 0, sA = 0, sB = 0, lenA = 0, lenB = 0;
+            int64_t cA = 0, cB = 0, sA = 0, sB = 0, lenA = -1, lenB = -1;       // len < 0: not loaded (only the directory-less filter and the None case need it)
             {
-                int4 t = make_int4(-1, -1, -1, -1);
-                if (e2 >= 0 && (int64_t)e2 <= g.max_eidx) t = __ldg(g.etab + e2);
-                if (A > 0 && in_range(A)) { sA = __ldg(g.off + A); lenA = __ldg(g.off + A + 1) - sA; cA = A == t.x ? t.z : (A == t.y ? t.w : lenA); }
-                if (Bn > 0 && in_range(Bn)) { sB = __ldg(g.off + Bn); lenB = __ldg(g.off + Bn + 1) - sB; cB = Bn == t.x ? t.z : (Bn == t.y ? t.w : lenB); }
+                const EdgeSlot t = edge_slot(g, e2);
+                auto window = [&](int64_t v, int64_t &c, int64_t &st, int64_t &len) {
+                    if (v <= 0 || !in_range(v)) return;
+                    if (v == t.node_a) { c = t.cut_a; st = t.start_a; }
+                    else if (v == t.node_b) { c = t.cut_b; st = t.start_b; }
+                    else { st = __ldg(g.off + v); len = __ldg(g.off + v + 1) - st; c = len; }    // dict.get -> None -> [:None] = the whole list
+                    if (!g.htab && len < 0) len = __ldg(g.off + v + 1) - st;
+                };
+                window(A, cA, sA, lenA);
+                window(Bn, cB, sB, lenB);
             }
             int64_t nA, nB;
-            IdRange ra1 = {0, 0}, ra2 = {0, 0}, rb = {0, 0};
+            IdRange ra1, ra2, rb;
+            ra1.cnt = ra2.cnt = rb.cnt = 0; ra1.base = ra2.base = rb.base = 0; ra1.inl = ra2.inl = rb.inl = false;
             if (code == 1) { nA = cA; nB = cB; }
             else {
                 ra1 = id_prefix(g, A, g.skey + sA, sA, lenA, cA, fa1);
@@ -215,19 +241,28 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
                                  : (int64_t)draw_index(seed, TM_STAGE_STEP3, row_offset * W + w, 0, (uint64_t)(nA + nB));
                 int64_t p;
                 if (k < nA) { src3 = A; p = sA + (code == 1 ? k : select_union(g.skey + sA, ra1, ra2, k)); }
-                else { k -= nA; src3 = Bn; p = sB + (code == 1 ? k : (int64_t)(uint32_t)__ldg(g.skey + sB + rb.base + k)); }
+                else { k -= nA; src3 = Bn; p = sB + (code == 1 ? k : (int64_t)range_pos(g.skey + sB, rb, k)); }
                 const Entry en = load_entry(g.entry + p);
                 tgt3 = en.nbr; e3 = en.eidx; t3 = (float)en.ts;
                 if (code == 2) tc = (src3 == s1 && tgt3 == t1n) ? 1 : (src3 == s1 && tgt3 == t2n) ? 2 : (src3 == t1n && tgt3 == t2n) ? 3 : 0;      // :386-393
                 else if (code == 3) tc = (src3 == t1n && tgt3 == s1) ? 1 : (src3 == t1n && tgt3 == t2n) ? 3 : (src3 == t2n && tgt3 == s1) ? 2 : 0; // :427-434
                 else tc = (src3 == s1 && tgt3 != t1n) ? 3 : (src3 == t1n && tgt3 != s1) ? 2 : (src3 == s1 && tgt3 == t1n) ? 1 : (src3 == t1n && tgt3 == s1) ? 1 : 0;  // :464-473
             }
-            int2 *on = reinterpret_cast<int2 *>(o_nodes + w * 6);   // [src3,tgt3,src2,tgt2,src1,tgt1], graph.py:303
-            on[0] = make_int2((int32_t)src3, (int32_t)tgt3);
-            on[1] = make_int2((int32_t)s2, (int32_t)t2n);
-            on[2] = make_int2((int32_t)s1, (int32_t)t1n);
-            o_eidx[w * 3 + 0] = e3; o_eidx[w * 3 + 1] = e2; o_eidx[w * 3 + 2] = e1;     // :304
-            o_t[w * 3 + 0] = t3; o_t[w * 3 + 1] = t2; o_t[w * 3 + 2] = t1;               // :305
+            if (staged) {       // the block's walks are contiguous in every output array: park them in shared memory, write them out coalesced below
+                const int lw = (int)threadIdx.x * N2 + jj;
+                int32_t *sn = stage + lw * 6, *se = stage + 256 * N2 * 6 + lw * 3;
+                float *st_ = reinterpret_cast<float *>(stage + 256 * N2 * 9) + lw * 3;
+                sn[0] = (int32_t)src3; sn[1] = (int32_t)tgt3; sn[2] = (int32_t)s2; sn[3] = (int32_t)t2n; sn[4] = (int32_t)s1; sn[5] = (int32_t)t1n;
+                se[0] = e3; se[1] = e2; se[2] = e1;
+                st_[0] = t3; st_[1] = t2; st_[2] = t1;
+            } else {
+                int2 *on = reinterpret_cast<int2 *>(o_nodes + w * 6);   // [src3,tgt3,src2,tgt2,src1,tgt1], graph.py:303
+                on[0] = make_int2((int32_t)src3, (int32_t)tgt3);
+                on[1] = make_int2((int32_t)s2, (int32_t)t2n);
+                on[2] = make_int2((int32_t)s1, (int32_t)t1n);
+                o_eidx[w * 3 + 0] = e3; o_eidx[w * 3 + 1] = e2; o_eidx[w * 3 + 2] = e1;     // :304
+                o_t[w * 3 + 0] = t3; o_t[w * 3 + 1] = t2; o_t[w * 3 + 2] = t1;               // :305
+            }
             if (o_anony) { o_anony[w * 3 + 0] = 1; o_anony[w * 3 + 1] = code; o_anony[w * 3 + 2] = tc; }
             const int cls = class_prep(code, tc);
             if (o_cat) o_cat[w] = (uint8_t)cls;
@@ -236,6 +271,19 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
         if (scanned && scan_acc) atomicAdd(&sh_scan, scan_acc);
     }
     __syncthreads();
+    if (staged) {           // 16-byte stores of the block's contiguous output ranges (a thread's own stores would touch one sector per value)
+        const int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
+        const int64_t live = min((int64_t)blockDim.x, B * n - row0) * N2;                  // walks of this block
+        auto flush = [&](const int32_t *src, int32_t *dst, int per_walk) {
+            const int64_t words = live * per_walk;                                         // multiple of 4 except in the last block
+            dst += row0 * N2 * per_walk;
+            for (int64_t i = 4 * (int64_t)threadIdx.x; i + 3 < words; i += 4 * blockDim.x) *reinterpret_cast<int4 *>(dst + i) = *reinterpret_cast<const int4 *>(src + i);
+            for (int64_t i = (words & ~(int64_t)3) + threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+        };
+        flush(stage, o_nodes, 6);
+        flush(stage + 256 * N2 * 6, o_eidx, 3);
+        flush(stage + 256 * N2 * 9, reinterpret_cast<int32_t *>(o_t), 3);
+    }
     if (threadIdx.x < 12 && sh_hist[threadIdx.x]) {
         if (hist_prep) atomicAdd(hist_prep + threadIdx.x, (unsigned long long)sh_hist[threadIdx.x]);
         if (hist_null) atomicAdd(hist_null + kPrepToNull[threadIdx.x], (unsigned long long)sh_hist[threadIdx.x]);
@@ -308,6 +356,46 @@ edge_identity_kernel(int64_t B, int W, int slots_mask, const int32_t *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// get_next_step with e_idx_l = None (utils/graph.py:308-333 through find_before_walk's bisect branch, :170-171): the two prefixes of
+// row i, [source_i, nbr_i], are cut by TIME (strict lower bound on the float64 timestamps; no node-0 special case on this branch).
+// find_k_walks never takes this branch (it always passes e_idx); it exists for callers of get_next_step itself.  One thread per row.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t thread_lower_bound(const Entry *__restrict__ base, int64_t len, double x) {
+    int64_t lo = 0, hi = len;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(&base[mid].ts) < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__global__ void __launch_bounds__(256)
+next_step_time_kernel(GraphView g, int64_t R, int N2, const int32_t *__restrict__ source, const int32_t *__restrict__ nbr, const double *__restrict__ cut_time,
+                      uint64_t seed, uint64_t row_offset, const uint32_t *__restrict__ inj, int32_t *__restrict__ o_src, int32_t *__restrict__ o_tgt,
+                      int32_t *__restrict__ o_e, float *__restrict__ o_t, int32_t *err) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const int64_t a = source[i], b = nbr[i];
+    for (int j = 0; j < N2; ++j) { o_src[i * N2 + j] = 0; o_tgt[i * N2 + j] = 0; o_e[i * N2 + j] = 0; o_t[i * N2 + j] = 0.f; }
+    if (a < 0 || a >= g.n_nodes || b < 0 || b >= g.n_nodes) { report_row_error(err, i); return; }
+    const int64_t s_a = __ldg(g.off + a), s_b = __ldg(g.off + b);
+    const int64_t c_a = thread_lower_bound(g.entry + s_a, __ldg(g.off + a + 1) - s_a, cut_time[i]);
+    const int64_t c_b = thread_lower_bound(g.entry + s_b, __ldg(g.off + b + 1) - s_b, cut_time[i]);
+    const int64_t L = c_a + c_b;
+    if (L == 0) return;
+    uint64_t d[TM_MAX_STEP2_FANOUT];
+    for (int j = 0; j < N2; ++j) d[j] = inj ? min((uint64_t)inj[i * N2 + j], (uint64_t)L - 1) : draw_index(seed, TM_STAGE_STEP2, row_offset + i, j, (uint64_t)L);
+    for (int x = 1; x < N2; ++x) {            // np.sort (graph.py:328)
+        const uint64_t v = d[x];
+        int y = x - 1;
+        while (y >= 0 && d[y] > v) { d[y + 1] = d[y]; --y; }
+        d[y + 1] = v;
+    }
+    for (int j = 0; j < N2; ++j) {
+        const int64_t sd = (int64_t)d[j];
+        const bool from_a = sd < c_a;
+        const Entry en = load_entry(g.entry + (from_a ? s_a + sd : s_b + (sd - c_a)));
+        o_src[i * N2 + j] = (int32_t)(from_a ? a : b); o_tgt[i * N2 + j] = en.nbr; o_e[i * N2 + j] = en.eidx; o_t[i * N2 + j] = (float)en.ts;
+    }
+}
+
 }  // namespace tm
 
 using namespace tmb;
@@ -346,9 +434,14 @@ static int walks_impl(const tm_graph *g, int64_t B, int n, int N2, const int32_t
     if (B == 0) return TM_OK;
     TM_DEVICE(g->device);
     const int64_t rows = B * n, blocks = (rows + 255) / 256;
-#define TM_WALKS(CAP) sample_walks_kernel<CAP><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                           \
+    // outputs staged in shared memory and written coalesced when a block's walks fit 48 KB (N2 <= 4 at 48 bytes per walk); the base
+    // addresses of the block ranges are 16-byte aligned when the arrays are (256 N2 walks x 12 / 24 bytes)
+    const size_t stage_bytes = (size_t)256 * N2 * 48;
+    const bool staged = stage_bytes <= 48 * 1024 && !getenv("TEMPME_WALKS_NO_STAGING") && ((uintptr_t)d_o_nodes % 16 == 0) && ((uintptr_t)d_o_eidx % 16 == 0) &&
+                        ((uintptr_t)d_o_t % 16 == 0);
+#define TM_WALKS(CAP) sample_walks_kernel<CAP><<<(unsigned)blocks, 256, staged ? stage_bytes : 0, (cudaStream_t)stream>>>(    \
         g->v, B, n, N2, d_root, d_h1_node, d_h1_eidx, d_h1_ts, seed, row_offset, d_inject2, d_inject3, d_pre2, d_pre2_t,     \
-        d_o_nodes, d_o_eidx, d_o_t, d_o_anony, d_o_cat, d_hist_null, d_hist_prep, d_scanned)
+        d_o_nodes, d_o_eidx, d_o_t, d_o_anony, d_o_cat, d_hist_null, d_hist_prep, d_scanned, staged ? 1 : 0)
     if (N2 == 1) TM_WALKS(1); else if (N2 <= 4) TM_WALKS(4); else if (N2 <= 8) TM_WALKS(8); else TM_WALKS(TM_MAX_STEP2_FANOUT);
 #undef TM_WALKS
     TM_LAUNCH_CHECK();
@@ -373,6 +466,22 @@ extern "C" int tm_walk_final_step(const tm_graph *g, int64_t R, const int32_t *d
     // one root per walk (n = N2 = 1): row i of get_final_step is walk i
     return walks_impl(g, R, 1, 1, d_src1, d_tgt1, d_e1, d_t1, seed, row_offset, nullptr, d_inject3, d_step2, d_t2,
                       d_o_nodes, d_o_eidx, d_o_t, d_o_anony, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int tm_walk_next_step_time(const tm_graph *g, int64_t R, int N2, const int32_t *d_source, const int32_t *d_nbr, const double *d_cut_time,
+                                      uint64_t seed, uint64_t row_offset, const uint32_t *d_inject, int32_t *d_o_src, int32_t *d_o_tgt, int32_t *d_o_eidx,
+                                      float *d_o_ts, int32_t *d_err, tm_stream stream) {
+    if (!g || R < 0 || N2 <= 0 || (R > 0 && (!d_source || !d_nbr || !d_cut_time || !d_o_src || !d_o_tgt || !d_o_eidx || !d_o_ts))) {
+        set_error("tm_walk_next_step_time: bad argument");
+        return TM_ERR_ARG;
+    }
+    if (N2 > TM_MAX_STEP2_FANOUT) { set_error("tm_walk_next_step_time: fan-out %d > %d", N2, TM_MAX_STEP2_FANOUT); return TM_ERR_UNSUPPORTED; }
+    if (R == 0) return TM_OK;
+    TM_DEVICE(g->device);
+    next_step_time_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g->v, R, N2, d_source, d_nbr, d_cut_time, seed, row_offset, d_inject,
+                                                                                          d_o_src, d_o_tgt, d_o_eidx, d_o_ts, d_err);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
 }
 
 extern "C" int tm_class_hist(int64_t count, const int32_t *d_anony, unsigned long long *d_hist_null,

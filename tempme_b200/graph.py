@@ -340,9 +340,20 @@ class NeighborFinder:
 
     def get_next_step(self, src_idx_l, cut_time_l, num_neighbor, degree, e_idx_l=None, source_id=None, seed=None, row_offset=0):
         """graph.py:308-333 -> (src2, tgt2, e2, t2), each [B*degree, num_neighbor]."""
-        if e_idx_l is None:
-            raise NotImplementedError("get_next_step without e_idx_l (time cut) is not built: find_k_walks always passes e_idx")
         assert len(src_idx_l) == len(cut_time_l) == len(source_id) * degree
+        if e_idx_l is None:        # prefixes cut by time (find_before_walk's bisect branch, :170-171)
+            s = self._next_seed(seed)
+            R = len(src_idx_l)
+            source = self._dev(np.repeat(np.asarray(source_id), degree), torch.int32)
+            nbr = self._dev(src_idx_l, torch.int32); ct = self._dev(np.asarray(cut_time_l, dtype=np.float64), torch.float64)
+            o = [torch.empty((R, num_neighbor), dtype=torch.int32, device=self.device) for _ in range(3)]
+            o_t = torch.empty((R, num_neighbor), dtype=torch.float32, device=self.device)
+            self._clear_err()
+            check(lib().tm_walk_next_step_time(self._h, R, int(num_neighbor), ptr(source), ptr(nbr), ptr(ct), s, row_offset * degree, None,
+                                               ptr(o[0]), ptr(o[1]), ptr(o[2]), ptr(o_t), ptr(self._err), self._stream()), "tm_walk_next_step_time")
+            out = (o[0].cpu().numpy(), o[1].cpu().numpy(), o[2].cpu().numpy(), o_t.cpu().numpy())
+            self._raise_if_err("get_next_step")
+            return out
         B = len(source_id)
         sub = ([np.asarray(src_idx_l).reshape(B, degree)], [np.asarray(e_idx_l).reshape(B, degree)],
                [np.asarray(cut_time_l, dtype=np.float32).reshape(B, degree)])

@@ -17,6 +17,7 @@ Fixtures:
   edgeimp_*.npz    retrieve_edge_imp_node (eval mode) on those scores: `python tests/golden/make_golden.py edgeimp`
   enhance_*.npz    enhance_predict_walks / compute_walk_importance / enhance_predict_agg (eval): `python tests/golden/make_golden.py enhance`
   kl_loss.npz      TempME.kl_loss on fixed scores / classes, both priors: `python tests/golden/make_golden.py kl`
+  nextstep_time.npz  get_next_step(e_idx_l=None): second events drawn from time-cut prefixes: `python tests/golden/make_golden.py nextstep`
   trainstep_*.npz  one temp_exp_main.py:605-632-shaped step in train() mode with dropout_p = 0 (deterministic): scores, edge importances,
                    kl_loss, the loss and d loss / d parameter for every explainer parameter: `python tests/golden/make_golden.py train`
 """
@@ -487,6 +488,24 @@ def gen_train_all():
                    int(us["n_nodes"]), len(eidx) + 1, 172, 1, seed=23)
 
 
+def gen_next_step_time():
+    """get_next_step with e_idx_l = None (utils/graph.py:308-333, the bisect branch of find_before_walk) on the rand_small graph, run on
+    the unmodified reference under the draw contract (stage 16, row = i)."""
+    z = dict(np.load(os.path.join(HERE, "rand_small.npz")))
+    n_nodes = int(z["n_nodes"])
+    nf = rg.NeighborFinder(refshim.adj_list_from_events(n_nodes, z["src"], z["dst"], z["eidx"], z["ts"]))
+    roots = z["src"][z["q"]].astype(np.int64)
+    degree, N2 = int(z["n"]), 3
+    nbr = z["src_hop0_node"].reshape(-1).astype(np.int64)            # first-hop neighbours [B * degree] and their (float32) times
+    cut = z["src_hop0_ts"].reshape(-1).astype(np.float32)
+    shim = refshim.DrawShim(base_seed=31)
+    with shim.patched(rg):
+        shim.seed = 31
+        s2, t2, e2, ts2 = nf.get_next_step(nbr, cut, N2, degree, e_idx_l=None, source_id=roots)
+    np.savez_compressed(os.path.join(HERE, "nextstep_time.npz"), roots=roots, nbr=nbr, cut=cut, degree=degree, N2=N2, seed=31,
+                        o_src=s2, o_tgt=t2, o_eidx=e2, o_ts=ts2)
+
+
 def gen_edge_imp_all():
     """Fixtures of the motif -> edge aggregation; reads the committed walk fixtures (does not regenerate them)."""
     us = dict(np.load(os.path.join(HERE, "uslegis.npz")))
@@ -519,6 +538,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "kl":
         gen_kl_all()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "nextstep":
+        gen_next_step_time()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         gen_train_all()

@@ -675,3 +675,13 @@ def test_score_gather_peer_stores_single_gpu(tm):
         assert torch.isnan(b[[r for r in range(world) if r != rank]]).all()
     with pytest.raises(Exception):
         m.score_device(nodes, eidx, t, cat, cut, eid, group=B, peer_ptrs=[bufs[0].data_ptr()] * 8)
+
+
+def test_get_next_step_time_cut_golden(tm, golden):
+    """get_next_step(e_idx_l=None) (utils/graph.py:308-333): prefixes of [root, neighbour] cut by time, against the unmodified reference."""
+    g, z = golden("rand_small"), golden("nextstep_time")
+    f = finder_of(tm, g)
+    out = f.get_next_step(z["nbr"], z["cut"], int(z["N2"]), int(z["degree"]), e_idx_l=None, source_id=z["roots"], seed=int(z["seed"]))
+    for a, name in zip(out, ("o_src", "o_tgt", "o_eidx", "o_ts")):
+        ref = z[name]
+        assert a.shape == ref.shape and a.dtype == ref.dtype and (a == ref).all(), name
