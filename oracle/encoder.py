@@ -22,8 +22,14 @@ def _lin(x, p, name, dt):
     return x @ p[name + ".weight"].astype(dt).T + p[name + ".bias"].astype(dt)
 
 
-def time_encode(ts, p, dt):
-    """TimeEncode.forward, explainer.py:51-59: cos(ts * basis_freq + phase)."""
+def time_encode(ts, p, dt, arg32=False):
+    """TimeEncode.forward, explainer.py:51-59: cos(ts * basis_freq + phase).  arg32 (with dt = float64): the ARGUMENT is formed in fp32 as
+    the reference does -- at |argument| ~ 1e8 its fp32 rounding is part of the function's definition -- and only the cosine and
+    everything downstream run in float64: the arbiter for "which fp32 result is closer to the exact value of the reference's formula"."""
+    if arg32:
+        m = ts.astype(np.float32)[..., None] * p["time_encoder.basis_freq"].astype(np.float32)
+        m = (m + p["time_encoder.phase"].astype(np.float32)).astype(dt)
+        return np.cos(m)
     m = ts[..., None] * p["time_encoder.basis_freq"].astype(dt)
     m = m + p["time_encoder.phase"].astype(dt)
     return np.cos(m)
@@ -61,7 +67,7 @@ def temporal_attention(feat, time_idx, cut_time, p, dt, use_temporal=True):
 
 
 def forward(p, node_feat, edge_feat, walks, cut_time, edge_identify, dtype=np.float32,
-            use_temporal=True, if_cat=True, return_hidden=False, attention_only=False):
+            use_temporal=True, if_cat=True, return_hidden=False, attention_only=False, arg32=False):
     """TempME.forward, explainer.py:174-201.
 
     walks = (node_idx [B,W,6], edge_idx [B,W,3], time_idx [B,W,3], cat_feat [B,W,1] or [B,W], _)
@@ -76,7 +82,7 @@ def forward(p, node_feat, edge_feat, walks, cut_time, edge_identify, dtype=np.fl
     edge_count = np.asarray(edge_identify).astype(np.float32).astype(dt)        # :177
     delta = (t32[:, :, 2:3] - t32)                                               # :326 (fp32 subtraction)
     B, W = delta.shape[:2]
-    time_features = time_encode(delta.astype(dt), p, dt)                         # :328-329
+    time_features = time_encode(delta.astype(dt), p, dt, arg32)                  # :328-329
     ev = np.concatenate([edge_features, edge_count, time_features], axis=-1)    # :179
     nid = np.asarray(node_idx).astype(np.int64)
     srcf = node_feat[nid[:, :, [0, 2, 4]]]                                       # :348-351
@@ -160,11 +166,12 @@ def walk_importance(time_idx, node_idx, cut_time, node_degree, dtype=np.float32)
     return (imp / (imp.sum(-1, keepdims=True) / dt(W) + dt(1e-6))).astype(dt)             # :301
 
 
-def enhance_predict_walks(p, node_feat, edge_feat, walks, cut_time, edge_identify, node_degree, dtype=np.float32, use_temporal=True, if_cat=True):
+def enhance_predict_walks(p, node_feat, edge_feat, walks, cut_time, edge_identify, node_degree, dtype=np.float32, use_temporal=True, if_cat=True,
+                          arg32=False):
     """TempME.enhance_predict_walks, explainer.py:222-255: attention output per walk, weighted by walk_importance, summed over the
     walks; with if_cat the per-root class counts are appended (:307-313)."""
     dt = dtype
-    h = forward(p, node_feat, edge_feat, walks, cut_time, edge_identify, dtype=dt, use_temporal=use_temporal, if_cat=if_cat, attention_only=True)
+    h = forward(p, node_feat, edge_feat, walks, cut_time, edge_identify, dtype=dt, use_temporal=use_temporal, if_cat=if_cat, attention_only=True, arg32=arg32)
     w = walk_importance(walks[2], walks[0], cut_time, node_degree, dt)
     out = (h * w[..., None]).sum(1)                                                       # :245-249
     if if_cat:

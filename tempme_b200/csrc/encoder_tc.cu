@@ -396,7 +396,7 @@ template <> __device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, float *
 template <> __device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, float *v) { tc::tmem_ld8(taddr, v); }
 
 // CW = columns of a K chunk per thread: 16 -> 256 threads, 8 -> 512 threads; TS = A operand in TMEM (else shared memory)
-template <int CW, bool TS>
+template <int CW, bool TS, bool DRAIN>
 __global__ void __launch_bounds__(128 * (kKC / CW), 2)
 score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a, const __grid_constant__ CUtensorMap tm_node,
                 const __grid_constant__ CUtensorMap tm_edge) {
@@ -423,7 +423,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC; x.a_col2 = x.a_col - 2 * kKC;
     AFill<CW, TS> af;
     const int H = L.H, H2 = 2 * L.H, D = L.D, Ed = L.Ed, nG = L.g0.nch, nchS = L.sp.nch;
-    const bool drain = a.Es != nullptr;
+    constexpr bool drain = DRAIN;                          // host: a.Es != nullptr exactly for the DRAIN instantiations
     const int colZ = 0, colE = drain ? 0 : (nG == 1 && L.D16 <= H) ? H : H2;
     const bool dq = a.dual != 0, de = (a.dual & 2) != 0;   // dual rounds (bit 0: MLP.0 orientations, Q, R; bit 1: lin_event chunk pairs).  Q and R rounds in pairs: second A buffer = columns [0, 64) (U is dead by then)
     // m3one: MLP.3 in one round -- its two or three K chunks from A, A2 and a third buffer behind M0; M1 then lands over M0's first
@@ -514,6 +514,20 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 if (k < D) return live ? cos_accurate(__fadd_rn(__fmul_rn(pi.dt, cstE[L.e_freq + k]), cstE[L.e_phase + k]), ctab) : 0.f;
                 return 0.f;
             };
+            // this thread's columns of chunk cc are all TimeEncode columns (straight-line code, the cosines interleave)
+            auto time_chunk = [&](int cc) {
+                const int j0 = cc * kKC + kb;
+                return j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + L.D16 && kb + CW <= min(kKC, L.evt.K8 - cc * kKC);
+            };
+            auto cos_chunk = [&](int cc, float *w) {
+                const int j0 = cc * kKC + kb;
+#pragma unroll
+                for (int g = 0; g < CW / 4; ++g) {
+                    const float4 fq = lds4(cstE + L.e_freq + (j0 - Ed) + 4 * g), ph = lds4(cstE + L.e_phase + (j0 - Ed) + 4 * g);      // zero-padded to D16
+                    w[4 * g] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.x), ph.x), ctab); w[4 * g + 1] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.y), ph.y), ctab);
+                    w[4 * g + 2] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.z), ph.z), ctab); w[4 * g + 3] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.w), ph.w), ctab);
+                }
+            };
             // ---- lin_event (:93) -> E.  fill_evt(cc, second): this thread's columns of chunk cc of [edge | TimeEncode] into an A buffer
             auto fill_evt = [&](int cc, bool second) {
                 const int kcols = min(kKC, L.evt.K8 - cc * kKC);
@@ -523,14 +537,9 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                     for (int g = 0; g < CW / 4; ++g)
                         af.put4(x, row, kb, 4 * g, !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stage_piece(stg_e, row, kb + 4 * g)) : ldg4(ef + j0 + 4 * g));
                     af.commit(x, lane_base, kb, second);
-                } else if (j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + L.D16 && kb + CW <= kcols) {      // all TimeEncode: straight-line code, the cosines interleave
+                } else if (time_chunk(cc)) {                        // all TimeEncode
                     float w[CW];
-#pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) {
-                        const float4 fq = lds4(cstE + L.e_freq + (j0 - Ed) + 4 * g), ph = lds4(cstE + L.e_phase + (j0 - Ed) + 4 * g);      // zero-padded to D16
-                        w[4 * g] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.x), ph.x), ctab); w[4 * g + 1] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.y), ph.y), ctab);
-                        w[4 * g + 2] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.z), ph.z), ctab); w[4 * g + 3] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.w), ph.w), ctab);
-                    }
+                    cos_chunk(cc, w);
                     // no masks: columns >= D have zero frequency / phase (cos = 1) and zero weights; rows past the last motif are never stored
 #pragma unroll
                     for (int g = 0; g < CW / 4; ++g) af.put4(x, row, kb, 4 * g, make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]));
@@ -562,9 +571,10 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 tc_mma_round<TS>(x, L.D16, kc0, colE, c != 0, left > 0 ? L.evt.w + (int64_t)(c + cnt) * chunk_floats(L.evt) : L.g0.w,
                                  left > 0 ? min(cpr, left) * bytes_e : bytes_g,
                                  [&]() {                            // the staged chunk has been consumed: the next one lands behind the MMAs
-                                     if (!has_edge) return;
-                                     if (c + 1 < L.nch_edge) request_edges(pi, c + 1);
-                                     else if (pos < 2) request_edges(pnext, 0);
+                                     if (has_edge) {
+                                         if (c + 1 < L.nch_edge) request_edges(pi, c + 1);
+                                         else if (pos < 2) request_edges(pnext, 0);
+                                     }
                                  }, Dual{cnt == 2 ? kDualK : kSingle, kc1, 0, 0, 0});
             }
             // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
@@ -954,7 +964,8 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     const size_t need = a_bytes + (size_t)bb + (size_t)(L.n_cstE + L.n_cstM) * 4 + 152 * 8;
     if (need > 220 * 1024) { set_error("tc_encode_score: feature dims too large for one weight chunk in shared memory"); return TM_ERR_UNSUPPORTED; }
     using ScoreK = void (*)(const TcLayout, const float *, const TcArgs, const CUtensorMap, const CUtensorMap);
-    static const ScoreK kern[4] = {score_tc_kernel<8, false>, score_tc_kernel<16, false>, score_tc_kernel<8, true>, score_tc_kernel<16, true>};
+    static const ScoreK kern[5] = {score_tc_kernel<8, false, false>, score_tc_kernel<16, false, false>, score_tc_kernel<8, true, false>, score_tc_kernel<16, true, false>,
+                                   score_tc_kernel<16, true, true>};
     static bool attr_set[64] = {false};
     if (!attr_set[device]) {
         for (ScoreK k : kern) {
@@ -966,11 +977,11 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const char *cw_env = getenv("TEMPME_TC_CW");                 // columns per thread per K chunk: 16 (256 threads, default) or 8 (512 threads)
-    const int cw = cw_env && atoi(cw_env) == 8 && H == 64 ? 8 : 16;
-    const int kv = (cw == 16) + 2 * ts;
-    static size_t static_smem[4] = {0, 0, 0, 0};
+    const int cw = cw_env && atoi(cw_env) == 8 && H == 64 && !drain ? 8 : 16;
+    const int kv = drain ? 4 : (cw == 16) + 2 * ts;         // drain mode has its own instantiation (CW = 16, A operand in TMEM)
+    static size_t static_smem[5] = {0, 0, 0, 0, 0};
     if (!static_smem[0])
-        for (int v = 0; v < 4; ++v) { cudaFuncAttributes fa; TM_CUDA(cudaFuncGetAttributes(&fa, kern[v])); static_smem[v] = fa.sharedSizeBytes; }
+        for (int v = 0; v < 5; ++v) { cudaFuncAttributes fa; TM_CUDA(cudaFuncGetAttributes(&fa, kern[v])); static_smem[v] = fa.sharedSizeBytes; }
     // resident CTAs per SM: TMEM columns and shared memory (registers: __launch_bounds__(threads, 2))
     const int ctas = std::max(1, std::min<int>(2, std::min<int>(512 / cols, (int)((228 * 1024) / (need + 1024 + static_smem[kv])))));
     // dynamic shared memory padded so that no more than `ctas` CTAs fit an SM (TMEM columns are not part of the occupancy

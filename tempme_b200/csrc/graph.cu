@@ -133,10 +133,20 @@ int device_graph_build_from_events(int64_t n_nodes, int64_t m, const int32_t *h_
                                    GraphView *view, int64_t *device_bytes);
 }
 
+// L2 fetch granularity: the lookups of this library are random 16-32 byte reads (one sector); with the default 64-byte granularity every
+// miss fetches a neighbouring sector it never uses.  TEMPME_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity when a graph is created.
+static void apply_l2_fetch_hint() {
+    const char *e = getenv("TEMPME_L2_FETCH");
+    if (!e) return;
+    const int v = atoi(e);
+    if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+}
+
 static bool use_device_build() { const char *e = getenv("TEMPME_GRAPH_BUILD"); return !(e && strcmp(e, "host") == 0); }
 
 static int finish_device_graph(int rc, tm_graph *g, tm_graph **out) {
     if (rc != TM_OK) { delete g; return rc; }
+    apply_l2_fetch_hint();
     const int rd = build_run_directory(g);
     if (rd != TM_OK) { free_graph(g); return rd; }
     *out = g;
