@@ -146,6 +146,8 @@ typedef struct {
     int32_t hid_dim;      /* H: 64 or 32 (temp_exp_main.py:40, enhance_main.py:66)   explainer.py:111 */
     int32_t use_temporal; /* TemporalAwareAttention (1) or Attention (0) explainer.py:121 */
     int32_t if_cat;       /* one-hot category features                 explainer.py:116,195-197 */
+    int32_t edge_projected; /* 0: d_edge_feat is the base model's edge feature table [rows, Ed].  1: d_edge_feat is the table made by
+                             * tm_encoder_project_edges, [rows, D]: lin_event's edge columns already applied per edge id */
 } tm_encoder_desc;
 
 /* Host pointers to the reference's parameters (nn.Linear layout: weight [out, in] row-major). */
@@ -167,6 +169,11 @@ typedef struct {
  * uploads it once and keeps it resident). */
 int64_t tm_encoder_blob_floats(const tm_encoder_desc *desc);
 int tm_encoder_pack(const tm_encoder_desc *desc, const tm_encoder_params *params, float *h_blob);
+/* Edge projection: d_out[e][n] = sum_j lin_event.weight[n][j] * d_edge_feat[e][j] (j < Ed), i.e. the part of event_conv.lin_event
+ * (explainer.py:93) that depends on the edge id alone, as a table [n_edge_rows, D] in place of one Ed x D product per walk event.  Rebuild it
+ * whenever the weights (d_blob) or the feature table change; pass it as d_edge_feat with desc->edge_projected = 1. */
+int tm_encoder_project_edges(const tm_encoder_desc *desc, const float *d_blob, const float *d_edge_feat, int64_t n_edge_rows, float *d_out,
+                             int device, tm_stream stream);
 /* Workspace (floats) tm_encode_score needs for B roots in groups of `group` roots. */
 int64_t tm_encoder_workspace_floats(const tm_encoder_desc *desc, int64_t B, int64_t W, int64_t group);
 

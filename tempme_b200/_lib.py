@@ -20,7 +20,7 @@ _u64 = C.c_uint64
 
 class EncoderDesc(C.Structure):
     _fields_ = [("node_dim", C.c_int32), ("edge_dim", C.c_int32), ("hid_dim", C.c_int32),
-                ("use_temporal", C.c_int32), ("if_cat", C.c_int32)]
+                ("use_temporal", C.c_int32), ("if_cat", C.c_int32), ("edge_projected", C.c_int32)]
 
 
 PARAM_FIELDS = ["lin_event_w", "lin_event_b", "gcn0_w", "gcn0_b", "gcn2_w", "gcn2_b", "att_w1_w", "att_w1_b",
@@ -61,6 +61,7 @@ SIGNATURES = {
     "tm_edge_identity": (C.c_int, [_i64, _i64, _p, _p, _p]),
     "tm_encoder_blob_floats": (_i64, [C.POINTER(EncoderDesc)]),
     "tm_encoder_pack": (C.c_int, [C.POINTER(EncoderDesc), C.POINTER(EncoderParams), _p]),
+    "tm_encoder_project_edges": (C.c_int, [C.POINTER(EncoderDesc), _p, _p, _i64, _p, C.c_int, _p]),
     "tm_encoder_workspace_floats": (_i64, [C.POINTER(EncoderDesc), _i64, _i64, _i64]),
     "tm_encoder_profile": (C.c_int, [C.c_int]),
     "tm_encoder_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),

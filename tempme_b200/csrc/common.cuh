@@ -67,6 +67,8 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
                     int64_t n_node_rows, const float *edge_feat, int64_t n_edge_rows, const float *std_, float *F, float *scores,
                     float *y_out, float *const *peer_scores, int n_peers, int device, cudaStream_t st);
 
+int tc_project_edges(const tm_encoder_desc &d, const float *d_blob_tc, const float *edge_feat, int64_t n_edge_rows, float *P, cudaStream_t st);
+
 // tensor map for tile::gather4 row gathers (encoder_tc.cu)
 bool make_gather_map(CUtensorMap *map, const float *table, int64_t rows, int dim, int swizzle128);
 

@@ -281,6 +281,14 @@ extern "C" int64_t tm_encoder_workspace_floats(const tm_encoder_desc *desc, int6
     return n_std + 2 * (n_g > 1 ? full : slab) * 3 * 2 * desc->hid_dim + (n_g > 1 ? 64 + full / 128 * n_g * 4096 : 0);
 }
 
+extern "C" int tm_encoder_project_edges(const tm_encoder_desc *desc, const float *d_blob, const float *d_edge_feat, int64_t n_edge_rows, float *d_out,
+                                        int device, tm_stream stream) {
+    if (!desc || !d_blob || n_edge_rows < 0 || (n_edge_rows > 0 && (!d_edge_feat || !d_out))) { set_error("tm_encoder_project_edges: bad argument"); return TM_ERR_ARG; }
+    if (desc->node_dim < 1 || desc->node_dim > 256 || desc->edge_dim < 1 || desc->edge_dim > 1024) { set_error("tm_encoder_project_edges: node_dim must be in [1,256], edge_dim in [1,1024]"); return TM_ERR_UNSUPPORTED; }
+    TM_DEVICE(device);
+    return tc_project_edges(*desc, d_blob + make_layout(*desc).total, d_edge_feat, n_edge_rows, d_out, (cudaStream_t)stream);
+}
+
 extern "C" int tm_encoder_pack(const tm_encoder_desc *desc, const tm_encoder_params *p, float *h_blob) {
     if (!desc || !p || !h_blob) { set_error("tm_encoder_pack: bad argument"); return TM_ERR_ARG; }
     const EncLayout L = make_layout(*desc);
@@ -348,7 +356,7 @@ static int encode_score_impl(const tm_encoder_desc *desc, const float *d_blob, i
         TM_LAUNCH_CHECK();
     }
     const char *which = getenv("TEMPME_ENCODER");     // "ffma" selects the fp32 CUDA-core kernel (A/B validation); default: tcgen05
-    if (d_y || n_peers > 0 || desc->hid_dim != 64 || !which || strcmp(which, "ffma") != 0) {
+    if (desc->edge_projected || d_y || n_peers > 0 || desc->hid_dim != 64 || !which || strcmp(which, "ffma") != 0) {
         const int64_t n_std = (std::max<int64_t>(32, n_groups) + 31) & ~(int64_t)31;
         return tc_encode_score(*desc, d_blob + L.total, B, W, group, d_nodes, d_eidx, d_t, d_cat, d_cut_time, d_edge_identity, d_node_feat,
                                n_node_rows, d_edge_feat, n_edge_rows, d_workspace, d_workspace + n_std, d_scores, d_y, peer_scores, n_peers, device, st);

@@ -44,7 +44,10 @@ struct TcLayout {
     int D, Ed, H, M, use_temporal, if_cat, D16, M16;
     int nch_edge;                                        // lin_event chunks that hold an edge-feature column
     TcLin evt, g0, sp, q, r, m3;
-    int e_b, e_b2, e_wi, e_g0b, e_freq, e_phase, n_cstE; // event-kernel constants (offsets inside cstE)
+    TcLin evtT;                                          // lin_event restricted to its TimeEncode columns (edge-projection mode: the edge columns
+                                                         //   are applied once per edge id by tc_project_edges, not once per walk event)
+    int64_t we;                                          // lin_event's edge columns, plain fp32 [D][Ed] (operand of the projection kernel)
+    int e_b, e_b2, e_b2p, e_wi, e_g0b, e_freq, e_phase, n_cstE; // event-kernel constants (offsets inside cstE)
     int m_cu, m_d, m_e, m_cy, m_m3b, m_w5, m_b5, n_cstM; // motif-kernel constants (offsets inside cstM)
     int64_t cstE, cstM, cm, total;                       // cm: [12][M16] per-category bias of the folded MLP.0 (global, read through L1)
 };
@@ -69,8 +72,10 @@ TcLayout make_tc_layout(const tm_encoder_desc &d) {
     const int H = L.H;
     L.evt = lin(L.Ed + L.D, L.D); L.g0 = lin(L.D, H);
     L.sp = lin(2 * H, 3 * H); L.q = lin(2 * H, H); L.r = lin(H, L.M); L.m3 = lin(L.M, H);
+    L.evtT = lin(L.D, L.D);
+    L.we = o; o += ((int64_t)L.D * L.Ed + 31) & ~(int64_t)31;
     int c = 0;
-    L.e_b = c; c += L.D16; L.e_b2 = c; c += L.D16; L.e_wi = c; c += 3 * L.D16; L.e_g0b = c; c += r16(H);
+    L.e_b = c; c += L.D16; L.e_b2 = c; c += L.D16; L.e_b2p = c; c += L.D16; L.e_wi = c; c += 3 * L.D16; L.e_g0b = c; c += r16(H);
     L.e_freq = c; c += L.D16; L.e_phase = c; c += L.D16; L.n_cstE = c;
     c = 0;
     L.m_cu = c; c += 2 * H; L.m_d = c; c += 2 * H; L.m_e = c; c += 16; L.m_cy = c; c += H; L.m_m3b = c; c += H;
@@ -131,9 +136,20 @@ int tc_pack(const tm_encoder_desc &d, const tm_encoder_params &p, float *blob) {
             for (int t = 0; t < D; ++t) W[(size_t)n * (Ed + D) + Ed + t] = p.lin_event_w[(size_t)n * ev + Ed + 3 + t];
         }
         pack_tc_lin(L.evt, Ed + D, D, W.data(), blob);
+        {   // edge-projection mode: TimeEncode columns only on the tensor cores, edge columns as a plain matrix for tc_project_edges
+            Mat Wt((size_t)D * D);
+            for (int n = 0; n < D; ++n) {
+                for (int t = 0; t < D; ++t) Wt[(size_t)n * D + t] = p.lin_event_w[(size_t)n * ev + Ed + 3 + t];
+                for (int j = 0; j < Ed; ++j) blob[L.we + (int64_t)n * Ed + j] = p.lin_event_w[(size_t)n * ev + j];
+            }
+            pack_tc_lin(L.evtT, D, D, Wt.data(), blob);
+        }
         float *c = blob + L.cstE;
         for (int n = 0; n < D; ++n) {
             c[L.e_b + n] = p.lin_event_b[n];
+            double b2p = p.lin_event_b[n];            // position-2 rows in edge-projection mode: every TimeEncode column is cos(phase)
+            for (int t = 0; t < D; ++t) b2p += (double)p.lin_event_w[(size_t)n * ev + Ed + 3 + t] * cos((double)p.phase[t]);
+            c[L.e_b2p + n] = (float)b2p;
             double b2 = p.lin_event_b[n];             // position-2 rows: dt = 0, TimeEncode = cos(phase) in the chunks they skip
             for (int t = 0; t < D; ++t)
                 if (Ed + t >= L.nch_edge * kKC) b2 += (double)p.lin_event_w[(size_t)n * ev + Ed + 3 + t] * cos((double)p.phase[t]);
@@ -367,6 +383,8 @@ struct TcArgs {
     int stage_off;                           // byte offset of the node-feature staging (src rows, then tgt rows); 0: gather with plain loads
     int stage_edge_off;                      // byte offset of the edge-feature staging; 0: gather with plain loads
     unsigned long long *tile_counter;        // dynamic tile scheduler: CTA b takes tile b first, then gridDim.x + atomicAdd(counter, 1)
+    int proj;                                // edge-projection mode: edge_feat is the table P = lin_event[:, :Ed] . edge features [n_edge_rows][D] (tc_project_edges);
+                                             //   lin_event runs over its TimeEncode columns only and P's rows are gathered like a third node-feature table
     int discard;                             // discard.global.L2 on the h slabs once a tile has consumed them (no write-back of the scratch)
     int dual;                                // two A buffers: bit 0 both orientations of MLP.0 per round + Q / R chunk pairs, bit 1 lin_event chunk pairs, bit 2 MLP.3 in one round
     long long *dbg;                          // TEMPME_TC_TIMING: 128 x 5 clock stamps of CTA 0
@@ -433,9 +451,11 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     const int colU = 0, colY = H2, colM0 = dq ? max(H, 2 * kKC) : 0, colM1 = m3one ? colM0 : dq ? 0 : H2, colA3 = colM0 + L.M16;
     const int nsl = H2 / kKC;                              // h slabs per walk position
     const int64_t n_m = a.n_motifs, n_tiles = (n_m + 127) / 128;
-    const int bytes_e = (int)chunk_floats(L.evt) * 4, bytes_g = (int)chunk_floats(L.g0) * 4;
+    const bool proj = a.proj != 0;
+    const TcLin EV = proj ? L.evtT : L.evt;                // lin_event operand chunks in use
+    const int bytes_e = (int)chunk_floats(EV) * 4, bytes_g = (int)chunk_floats(L.g0) * 4;
     const int bytes_sp = (int)chunk_floats(L.sp) * 4, bytes_q = (int)chunk_floats(L.q) * 4, bytes_r = (int)chunk_floats(L.r) * 4, bytes_m3 = (int)chunk_floats(L.m3) * 4;
-    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, L.evt.w, min(de ? 2 : 1, L.evt.nch) * bytes_e);
+    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, EV.w, min(de ? 2 : 1, EV.nch) * bytes_e);
     const bool ed_vec = (Ed & 3) == 0, d_vec = (D & 3) == 0;
     float *Fs = a.F + (int64_t)blockIdx.x * 3 * nsl * kSlabFloats;      // this CTA's h slabs: [position][column chunk][piece k/4][128 rows][4]
     const float *F0 = Fs, *F1 = Fs + nsl * kSlabFloats, *F2 = Fs + 2 * nsl * kSlabFloats;
@@ -484,6 +504,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         if (!stage_edges) return;
         request_rows(bars + 3, prt == 0, &tm_edge, (q.e >= 0 && q.e < a.n_edge_rows) ? q.e : 0, stg_e, c * kKC);
     };
+    const int jofs = proj ? Ed : 0;                        // edge-projection mode: chunk cc of lin_event starts at TimeEncode column cc * kKC
     PassIdx pcur, pnext;
     {
         const int64_t g0_ = (int64_t)blockIdx.x * 128 + row;
@@ -503,7 +524,9 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         x.a_col2 = x.a_col - 2 * kKC;
 #pragma unroll 1
         for (int pos = 0; pos < 3; ++pos) {
-            const int nE = pos == 2 ? L.nch_edge : L.evt.nch;          // position 2: dt = 0, the pure TimeEncode chunks are in the bias
+            // position 2: dt = 0, the pure TimeEncode chunks are in the bias (edge-projection mode: no lin_event round at all)
+            const int nE = proj ? (pos == 2 ? 0 : EV.nch) : (pos == 2 ? L.nch_edge : L.evt.nch);
+            const bool have_E = nE > 0;
             const PassIdx pi = pcur;
             if (pos < 2) pnext = load_idx(gm, live, pos + 1);
             const bool e_ok = pi.e >= 0 && pi.e < a.n_edge_rows, s_ok = pi.ns >= 0 && pi.ns < a.n_node_rows, t_ok = pi.nt >= 0 && pi.nt < a.n_node_rows;
@@ -516,11 +539,11 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             };
             // this thread's columns of chunk cc are all TimeEncode columns (straight-line code, the cosines interleave)
             auto time_chunk = [&](int cc) {
-                const int j0 = cc * kKC + kb;
-                return j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + L.D16 && kb + CW <= min(kKC, L.evt.K8 - cc * kKC);
+                const int j0 = cc * kKC + kb + jofs;
+                return j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + L.D16 && kb + CW <= min(kKC, EV.K8 - cc * kKC);
             };
             auto cos_chunk = [&](int cc, float *w) {
-                const int j0 = cc * kKC + kb;
+                const int j0 = cc * kKC + kb + jofs;
 #pragma unroll
                 for (int g = 0; g < CW / 4; ++g) {
                     const float4 fq = lds4(cstE + L.e_freq + (j0 - Ed) + 4 * g), ph = lds4(cstE + L.e_phase + (j0 - Ed) + 4 * g);      // zero-padded to D16
@@ -530,8 +553,8 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             };
             // ---- lin_event (:93) -> E.  fill_evt(cc, second): this thread's columns of chunk cc of [edge | TimeEncode] into an A buffer
             auto fill_evt = [&](int cc, bool second) {
-                const int kcols = min(kKC, L.evt.K8 - cc * kKC);
-                const int j0 = cc * kKC + kb;                       // this thread's columns [j0, j0 + CW)
+                const int kcols = min(kKC, EV.K8 - cc * kKC);
+                const int j0 = cc * kKC + kb + jofs;                // this thread's columns [j0, j0 + CW) of [edge | TimeEncode]
                 if (ed_vec && j0 + CW <= Ed) {                      // all edge features (warp-uniform)
 #pragma unroll
                     for (int g = 0; g < CW / 4; ++g)
@@ -547,7 +570,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 } else {                                            // mixed columns
 #pragma unroll
                     for (int g = 0; g < CW / 4; ++g) {
-                        const int k = kb + 4 * g, j = cc * kKC + k;
+                        const int k = kb + 4 * g, j = cc * kKC + k + jofs;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (k < kcols) {
                             if (ed_vec && j + 3 < Ed) v = !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stage_piece(stg_e, row, k)) : ldg4(ef + j);
@@ -559,16 +582,16 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 }
             };
             const int cpr = de ? 2 : 1;                             // lin_event chunks per round
-            const int nE_next = pos == 1 ? L.nch_edge : L.evt.nch;  // chunks of the next pass (position 2 skips the pure TimeEncode chunks)
+            const int nE_next = proj ? (pos == 1 ? 0 : EV.nch) : (pos == 1 ? L.nch_edge : L.evt.nch);  // chunks of the next pass (position 2 skips the pure TimeEncode chunks)
             for (int c = 0; c < nE; c += cpr) {
                 const int cnt = min(cpr, nE - c);
-                const bool has_edge = c < L.nch_edge;               // pairs are only formed when at most the first chunk holds edge columns
+                const bool has_edge = !proj && c < L.nch_edge;      // pairs are only formed when at most the first chunk holds edge columns
                 if (stage_edges && has_edge) { tc::mbar_wait(bars + 3, e_phase); e_phase ^= 1; }        // chunk c of the edge rows has landed
                 fill_evt(c, false);
                 if (cnt == 2) fill_evt(c + 1, true);
-                const int kc0 = min(kKC, L.evt.K8 - c * kKC), kc1 = cnt == 2 ? min(kKC, L.evt.K8 - (c + 1) * kKC) : 0;
+                const int kc0 = min(kKC, EV.K8 - c * kKC), kc1 = cnt == 2 ? min(kKC, EV.K8 - (c + 1) * kKC) : 0;
                 const int left = nE - c - cnt;
-                tc_mma_round<TS>(x, L.D16, kc0, colE, c != 0, left > 0 ? L.evt.w + (int64_t)(c + cnt) * chunk_floats(L.evt) : L.g0.w,
+                tc_mma_round<TS>(x, L.D16, kc0, colE, c != 0, left > 0 ? EV.w + (int64_t)(c + cnt) * chunk_floats(EV) : L.g0.w,
                                  left > 0 ? min(cpr, left) * bytes_e : bytes_g,
                                  [&]() {                            // the staged chunk has been consumed: the next one lands behind the MMAs
                                      if (has_edge) {
@@ -578,7 +601,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                                  }, Dual{cnt == 2 ? kDualK : kSingle, kc1, 0, 0, 0});
             }
             // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
-            const int eb = pos == 2 ? L.e_b2 : L.e_b;
+            const int eb = pos == 2 ? (proj ? L.e_b2p : L.e_b2) : L.e_b;
             // lin_event's bias and the three edge-identity columns (applied on the CUDA cores) for this thread's columns of MLP.0 chunk c
             auto finish_e = [&](float *ee, int c) {
 #pragma unroll
@@ -591,7 +614,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                     ee[k + 3] = fmaf(w2.w, pi.ei2, fmaf(w1.w, pi.ei1, fmaf(w0.w, pi.ei0, ee[k + 3] + bb.w)));
                 }
             };
-            if (drain) {
+            if (drain && have_E) {
                 // E leaves TMEM: every thread parks the columns it will consume in the MLP.0 rounds in its own rows of the CTA's E scratch
                 // (L2; written and read back by the same thread), then Zs | Zt take over the columns
 #pragma unroll 1
@@ -612,6 +635,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             for (int c = 0; c < nG; ++c) {
                 const int kcols = min(kKC, L.g0.K8 - c * kKC);
                 if (stage_nodes) { tc::mbar_wait(bars + 2, n_phase); n_phase ^= 1; }          // chunk c of the rows has landed
+                if (proj && stage_edges) { tc::mbar_wait(bars + 3, e_phase); e_phase ^= 1; }  // and chunk c of the projected edge rows
                 float sv[CW], gv[CW], ee[CW];                       // endpoints' features and lin_event output + bias + edge-identity terms
                 auto load_g = [&]() {
 #pragma unroll
@@ -631,8 +655,23 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                         }
                         sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
                     }
-                    if (drain) ldw(Es + c * kSlabFloats, ee);
+                    if (!have_E) {
+#pragma unroll
+                        for (int i = 0; i < CW; ++i) ee[i] = 0.f;
+                        finish_e(ee, c);
+                    } else if (drain) ldw(Es + c * kSlabFloats, ee);
                     else { tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, ee); finish_e(ee, c); }
+                    if (proj && e_ok) {                             // + lin_event[:, :Ed] . edge features, precomputed per edge id
+#pragma unroll
+                        for (int k = 0; k < CW; k += 4) {
+                            const int j = c * kKC + kb + k;
+                            float4 p4;
+                            if (stage_edges) p4 = lds4(stage_piece(stg_e, row, kb + k));       // columns past D arrive as zeros (tensor-map bounds)
+                            else if (d_vec && j + 3 < D) p4 = ldg4(a.edge_feat + (int64_t)pi.e * D + j);
+                            else { const float *pr = a.edge_feat + (int64_t)pi.e * D; p4 = make_float4(j < D ? __ldg(pr + j) : 0.f, j + 1 < D ? __ldg(pr + j + 1) : 0.f, j + 2 < D ? __ldg(pr + j + 2) : 0.f, j + 3 < D ? __ldg(pr + j + 3) : 0.f); }
+                            ee[k] += p4.x; ee[k + 1] += p4.y; ee[k + 2] += p4.z; ee[k + 3] += p4.w;
+                        }
+                    }
                 };
                 auto put_z = [&](int o, bool second) {              // orientation o: p + relu(q + event)
 #pragma unroll
@@ -649,12 +688,13 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 };
                 const bool last = c + 1 == nG;
                 auto next_nodes = [&]() {                           // the staged chunk has been consumed
-                    if (c + 1 < nG) request_nodes(pi, c + 1);
-                    else if (pos < 2) request_nodes(pnext, 0);
+                    if (c + 1 < nG) { request_nodes(pi, c + 1); if (proj) request_edges(pi, c + 1); }
+                    else if (pos < 2) { request_nodes(pnext, 0); if (proj) request_edges(pnext, 0); }
                 };
                 int64_t noff; int nbytes;                           // weights after this chunk's last round
                 if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
-                else if (pos < 2) { noff = L.evt.w; nbytes = min(cpr, nE_next) * bytes_e; }
+                else if (pos < 2 && nE_next > 0) { noff = EV.w; nbytes = min(cpr, nE_next) * bytes_e; }
+                else if (pos < 2) { noff = L.g0.w; nbytes = bytes_g; }         // edge-projection mode: position 2 starts with MLP.0
                 else { noff = L.sp.w; nbytes = bytes_sp; }
                 if (a.dual) {                                       // both orientations in one round: Zs from the first A buffer, Zt from the second
                     if (kb < kcols) { load_g(); put_z(0, false); put_z(1, true); }
@@ -842,7 +882,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             fill_m3(0, x.a_col);
             if (nc > 1) fill_m3(1, x.a_col2);
             if (nc > 2) fill_m3(2, (uint32_t)colA3);
-            tc_mma_round<TS>(x, H, min(kKC, L.m3.K8), colM1, false, L.evt.w, more ? min(de ? 2 : 1, L.evt.nch) * bytes_e : 0,
+            tc_mma_round<TS>(x, H, min(kKC, L.m3.K8), colM1, false, EV.w, more ? min(de ? 2 : 1, EV.nch) * bytes_e : 0,
                              [&]() { if (more) { request_nodes(pcur, 0); request_edges(pcur, 0); } },
                              Dual{nc > 1 ? kDualK : kSingle, nc > 1 ? min(kKC, L.m3.K8 - kKC) : 0, 0, nc > 2 ? L.m3.K8 - 2 * kKC : 0, colA3});
         } else
@@ -851,7 +891,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             fill_m3(c, x.a_col);
             const bool last = c + 1 == L.m3.nch;
             // the staging overlaps the weight buffer of the larger motif-round chunks; MLP.3's are small and R's MMAs have completed
-            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? L.evt.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? min(de ? 2 : 1, L.evt.nch) * bytes_e : 0) : bytes_m3,
+            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? EV.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? min(de ? 2 : 1, EV.nch) * bytes_e : 0) : bytes_m3,
                              [&]() { if (c == 0 && more) { request_nodes(pcur, 0); request_edges(pcur, 0); } });
         }
         // ---- MLP.5 + sigmoid (:199-200)
@@ -918,6 +958,54 @@ bool make_gather_map(CUtensorMap *map, const float *table, int64_t rows, int dim
                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Edge projection: P[e][n] = sum_j lin_event.weight[n][j] * edge_feat[e][j], j < Ed -- the part of event_conv.lin_event (explainer.py:93)
+// that depends on the edge id alone.  The reference recomputes it for every walk event; here it is a table, rebuilt whenever the
+// explainer's weights change (one pass over the edge table: n_edge_rows * Ed * D multiply-adds in fp32 FMA, then the scorer gathers P's
+// rows where it used to gather the raw feature rows).  Tile of 64 edges per block: features and results staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+edge_project_kernel(const float *__restrict__ We, const float *__restrict__ efeat, int64_t rows, int Ed, int D, float *__restrict__ P) {
+    extern __shared__ float xs[];                    // X [64][Ed + 1] | Y [64][D + 1]
+    float *ys = xs + 64 * (Ed + 1);
+    const int64_t r0 = (int64_t)blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 64 * Ed; i += 256) {
+        const int r = i / Ed, j = i - r * Ed;
+        xs[r * (Ed + 1) + j] = r0 + r < rows ? __ldg(efeat + (r0 + r) * Ed + j) : 0.f;
+    }
+    __syncthreads();
+    const int r = threadIdx.x & 63;
+    const float *x = xs + r * (Ed + 1);
+    for (int n = threadIdx.x >> 6; n < D; n += 4) {  // the lanes of a warp share n (broadcast weight loads) and own consecutive rows
+        const float *w = We + (int64_t)n * Ed;
+        float acc = 0.f;
+        for (int j = 0; j < Ed; ++j) acc = fmaf(__ldg(w + j), x[j], acc);
+        ys[r * (D + 1) + n] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * D; i += 256) {
+        const int rr = i / D, n = i - rr * D;
+        if (r0 + rr < rows) P[(r0 + rr) * D + n] = ys[rr * (D + 1) + n];
+    }
+}
+
+int tc_project_edges(const tm_encoder_desc &d, const float *d_blob_tc, const float *edge_feat, int64_t n_edge_rows, float *P, cudaStream_t st) {
+    const TcLayout L = make_tc_layout(d);
+    const size_t smem = sizeof(float) * 64 * ((size_t)L.Ed + 1 + L.D + 1);
+    if (smem > 200 * 1024) { set_error("tm_encoder_project_edges: edge_dim + node_dim too large for one tile in shared memory"); return TM_ERR_UNSUPPORTED; }
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    TM_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        TM_CUDA(cudaFuncSetAttribute(edge_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[dev] = true;
+    }
+    if (n_edge_rows <= 0) return TM_OK;
+    edge_project_kernel<<<(unsigned)((n_edge_rows + 63) / 64), 256, smem, st>>>(d_blob_tc + L.we, edge_feat, n_edge_rows, L.Ed, L.D, P);
+    TM_LAUNCH_CHECK();
+    return TM_OK;
+}
+
 // std_ = per-batch std (already computed); F = scratch for the h slabs of the resident CTAs
 int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B, int64_t W, int64_t group, const int32_t *nodes,
                     const int32_t *eidx, const float *t, const uint8_t *cat, const float *cut, const float *eid, const float *node_feat,
@@ -938,14 +1026,16 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     // drain mode (node_dim > 32, where E cannot alias Zt): lin_event's output leaves TMEM through an L2 scratch before the MLP.0 rounds, so E
     // [0, D16) and Zs | Zt [0, 2H) share columns and the tile needs 256 columns instead of 512 -- two tiles per SM instead of one
     const bool drain = ts && dual && !alias_e && L.D16 + 2 * kKC <= 256 && 2 * H + 4 * kKC <= 256 && !getenv("TEMPME_TC_NO_DRAIN");
-    const bool dual_e = dual && L.nch_edge <= 1 && !drain;   // pairs of lin_event chunks: one staged edge chunk per round at most; drain mode has one A buffer beside E
+    const bool proj = d.edge_projected != 0;                 // d_edge_feat is the projected table [n_edge_rows][D] (tc_project_edges)
+    const TcLin &EV = proj ? L.evtT : L.evt;
+    const bool dual_e = dual && (proj || L.nch_edge <= 1) && !drain;   // pairs of lin_event chunks: one staged edge chunk per round at most; drain mode has one A buffer beside E
     // motif rounds: U | Y + one A buffer; event passes: Zs | Zt (| E) + one or two A buffers (the A buffers are the top columns)
     const int ev_cols = drain ? std::max(2 * H + 4 * kKC, L.D16 + 2 * kKC) : (alias_e ? 2 * H : 2 * H + L.D16) + (ts ? (dual ? 4 : 2) * kKC : 0);
     while ((int)cols < std::max(3 * H + (ts ? 2 * kKC : 0), ev_cols)) cols <<= 1;
     if (cols > 512) { set_error("tc_encode_score: node_dim too large for the TMEM layout"); return TM_ERR_UNSUPPORTED; }
     int64_t bb = 0;
-    for (const TcLin *l : {&L.evt, &L.g0, &L.sp, &L.q, &L.r, &L.m3}) bb = std::max(bb, chunk_floats(*l) * 4);
-    if (dual_e) bb = std::max(bb, (int64_t)std::min(2, L.evt.nch) * chunk_floats(L.evt) * 4);        // lin_event chunks arrive in pairs
+    for (const TcLin *l : {&EV, &L.g0, &L.sp, &L.q, &L.r, &L.m3}) bb = std::max(bb, chunk_floats(*l) * 4);
+    if (dual_e) bb = std::max(bb, (int64_t)std::min(2, EV.nch) * chunk_floats(EV) * 4);              // lin_event chunks arrive in pairs
     if (dual) bb = std::max(bb, 2 * std::max(chunk_floats(L.q), chunk_floats(L.r)) * 4);             // so do Q's and R's
     // MLP.3 in one round: all of its (two or three) K chunks in the weight buffer; the third A buffer sits between M0 and the A buffers
     const bool m3one = dual && !getenv("TEMPME_TC_NO_M3ONE") && L.m3.nch <= 3 && (L.m3.nch < 3 || (L.m3.K8 - 2 * kKC <= 16 && H == 64 && H + L.M16 + 3 * kKC / 2 <= 3 * H));
@@ -955,9 +1045,10 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     CUtensorMap tm_node, tm_edge;
     memset(&tm_node, 0, sizeof tm_node); memset(&tm_edge, 0, sizeof tm_edge);
     const bool stage_nodes = L.D % 4 == 0 && ((uintptr_t)node_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && make_gather_map(&tm_node, node_feat, n_node_rows, L.D, 1);
-    const bool stage_edges = L.Ed % 4 == 0 && ((uintptr_t)edge_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && !getenv("TEMPME_TC_NO_EDGE_STAGING") &&
-                             make_gather_map(&tm_edge, edge_feat, n_edge_rows, L.Ed, 1);
-    const int64_t stage_rel = (std::max(std::max((dual_e ? std::min(2, L.evt.nch) : 1) * chunk_floats(L.evt), chunk_floats(L.g0)), (m3one ? L.m3.nch : 1) * chunk_floats(L.m3)) * 4 + 1023) & ~(int64_t)1023;
+    const int edge_cols = proj ? L.D : L.Ed;                 // row length of the table behind d_edge_feat
+    const bool stage_edges = edge_cols % 4 == 0 && ((uintptr_t)edge_feat & 15) == 0 && !getenv("TEMPME_TC_NO_STAGING") && !getenv("TEMPME_TC_NO_EDGE_STAGING") &&
+                             make_gather_map(&tm_edge, edge_feat, n_edge_rows, edge_cols, 1);
+    const int64_t stage_rel = (std::max(std::max((dual_e ? std::min(2, EV.nch) : 1) * chunk_floats(EV), chunk_floats(L.g0)), (m3one ? L.m3.nch : 1) * chunk_floats(L.m3)) * 4 + 1023) & ~(int64_t)1023;
     const int64_t stage_edge_rel = stage_rel + (stage_nodes ? (int64_t)2 * kStageTable * 4 : 0);
     bb = std::max(bb, stage_edge_rel + (stage_edges ? (int64_t)kStageTable * 4 : 0));
     const size_t a_bytes = ts ? 0 : (size_t)2 * kATile;
@@ -997,6 +1088,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.stage_off = stage_nodes ? (int)(a_bytes + stage_rel) : 0;
     a.stage_edge_off = stage_edges ? (int)(a_bytes + stage_edge_rel) : 0;
     a.dual = (dual ? 1 : 0) | (dual_e ? 2 : 0) | (m3one ? 4 : 0);
+    a.proj = proj ? 1 : 0;
     a.discard = getenv("TEMPME_TC_DISCARD") ? 1 : 0;          // A/B knob, off: the discards removed the scratch write-back but cost 2.6 % of kernel time (profiles/README.md r02b)
     static long long *dbg_buf = nullptr;
 #ifdef TM_TC_TIMING
@@ -1014,7 +1106,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.tile_counter = reinterpret_cast<unsigned long long *>(F + (int64_t)grid * 3 * (2 * H / kKC) * kSlabFloats);          // behind the h scratch (the workspace holds twice as much)
     a.Es = drain ? F + 2 * tc_slab_motifs(device) * 3 * 2 * H + 64 : nullptr;                                             // behind both (tm_encoder_workspace_floats)
     TM_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), st));
-    if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] score kernel: %u CTAs (%d per SM), smem %zu B (needs %zu), %u TMEM columns, %lld tiles%s\n", grid, ctas, smem, need, cols, (long long)tiles, drain ? ", E drained through L2" : "");
+    if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] score kernel: %u CTAs (%d per SM), smem %zu B (needs %zu), %u TMEM columns, %lld tiles%s\n", grid, ctas, smem, need, cols, (long long)tiles, drain ? (proj ? ", E drained through L2, projected edge table" : ", E drained through L2") : (proj ? ", projected edge table" : ""));
     cudaEvent_t *pe = nullptr;
     if (g_prof && g_prof_used + 2 <= g_prof_ev.size()) {        // pool is created by tm_encoder_profile(1); when exhausted, stop recording
         pe = &g_prof_ev[g_prof_used]; g_prof_used += 2;

@@ -65,24 +65,27 @@ __global__ void walk_importance_kernel(int64_t B, int W, int64_t group, const fl
     }
 }
 
-// One block of H threads per root: weighted sum of the walks' hidden vectors, attention.MLP.3 once, class counts (:245-253)
+// One block of H threads per root: weighted sum of the walks' hidden vectors, attention.MLP.3 once, class counts (:245-253).
+// The sum over the W walks and the 64-term dot products accumulate in double: the result is a signed sum whose fp32 evaluation order
+// would otherwise decide its last digits (the reference's own order -- Linear per walk, then a pairwise torch.sum -- is a different one);
+// against the float64 arbiter this keeps the embedding closer to the exact value than the reference's fp32 evaluation is.
 __global__ void enhance_reduce_kernel(int64_t B, int W, int H, const float *__restrict__ y, const float *__restrict__ weights,
                                       const float *__restrict__ a3_w, const float *__restrict__ a3_b, const uint8_t *__restrict__ cat,
                                       int out_dim, float *__restrict__ out) {
-    extern __shared__ float acc[];             // [H]
+    extern __shared__ double acc[];            // [H]
     const int64_t b = blockIdx.x;
     const int j = threadIdx.x;
-    float s = 0.f, sw = 0.f;
+    double s = 0.0, sw = 0.0;
     for (int w = 0; w < W; ++w) {
-        const float wt = weights[b * W + w];
-        s = fmaf(wt, y[(b * W + w) * H + j], s);
+        const double wt = (double)weights[b * W + w];
+        s += wt * (double)y[(b * W + w) * H + j];
         sw += wt;
     }
     acc[j] = s;
     __syncthreads();
-    float o = a3_b[j] * sw;
-    for (int i = 0; i < H; ++i) o = fmaf(a3_w[j * H + i], acc[i], o);
-    out[b * out_dim + j] = o;
+    double o = (double)a3_b[j] * sw;
+    for (int i = 0; i < H; ++i) o += (double)a3_w[j * H + i] * acc[i];
+    out[b * out_dim + j] = (float)o;
     if (cat && j < 12) {
         int c = 0;
         for (int w = 0; w < W; ++w) c += cat[b * W + w] == j;
@@ -117,7 +120,7 @@ extern "C" int tm_enhance_reduce(int64_t B, int64_t W, int hid_dim, const float 
     if (B == 0) return TM_OK;
     TM_DEVICE(device_of(d_out));
     const int out_dim = hid_dim + (d_cat_or_null ? 12 : 0);
-    enhance_reduce_kernel<<<(unsigned)B, hid_dim, sizeof(float) * hid_dim, (cudaStream_t)stream>>>(B, (int)W, hid_dim, d_y, d_weights, d_att_mlp3_w,
+    enhance_reduce_kernel<<<(unsigned)B, hid_dim, sizeof(double) * hid_dim, (cudaStream_t)stream>>>(B, (int)W, hid_dim, d_y, d_weights, d_att_mlp3_w,
                                                                                                    d_att_mlp3_b, d_cat_or_null, out_dim, d_out);
     TM_LAUNCH_CHECK();
     return TM_OK;

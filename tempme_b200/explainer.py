@@ -11,6 +11,7 @@ and ``kl_loss`` kernels with their own backward), so ``temp_exp_main.py``'s trai
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -129,7 +130,14 @@ class TempME(nn.Module):
             self.gumbel_anneal_rate = 0.003
         # ---- device-side state of the fused scorer
         self.batch_group = batch_group          # roots per reference batch; None = the whole call is one batch
-        self._desc = EncoderDesc(self.node_dim, self.edge_dim, self.hid_dim, int(bool(use_temporal_guidance)), int(bool(self.if_cat)))
+        self._desc = EncoderDesc(self.node_dim, self.edge_dim, self.hid_dim, int(bool(use_temporal_guidance)), int(bool(self.if_cat)), 0)
+        # edge-projection mode of the scorer: lin_event's edge columns applied once per edge id (a [rows, node_dim] table next to the
+        # feature table, rebuilt when the weights change) instead of once per walk event.  TEMPME_EDGE_PROJECTION=0 disables it.
+        self._desc_proj = EncoderDesc(self.node_dim, self.edge_dim, self.hid_dim, int(bool(use_temporal_guidance)), int(bool(self.if_cat)), 1)
+        self.edge_projection = os.environ.get("TEMPME_EDGE_PROJECTION", "1") != "0" and self.edge_dim <= 256
+        self._proj = None
+        self._proj_key = None
+        self.projection_ms = None
         self._blob = None
         self._blob_key = None
         self.autograd_in_eval = False           # see _wants_grad
@@ -171,6 +179,29 @@ class TempME(nn.Module):
             ef = ef.detach().to(self.device, torch.float32).contiguous()
         return nf, ef
 
+    def _edge_table(self, blob, ef):
+        """(desc, table) the scorer reads edge rows from: the projected table P = edge_feat @ lin_event.weight[:, :Ed]^T (cached per
+        weights version and feature table; tm_encoder_project_edges) or, with the projection off, the raw feature table."""
+        if not self.edge_projection or os.environ.get("TEMPME_ENCODER") == "ffma":
+            return self._desc, ef
+        key = (self._blob_key, ef.data_ptr(), tuple(ef.shape))
+        if self._proj is None or key != self._proj_key:
+            if self._proj is not None:
+                self._ws_retired.append(self._proj)          # a captured graph may still gather from it
+            P = torch.empty((ef.shape[0], self.node_dim), dtype=torch.float32, device=self.device)
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            capturing = torch.cuda.is_current_stream_capturing()
+            if not capturing:
+                t0.record()
+            check(lib().tm_encoder_project_edges(C.byref(self._desc), ptr(blob), ptr(ef), ef.shape[0], ptr(P), self.device.index, st),
+                  "tm_encoder_project_edges")
+            if not capturing:
+                t1.record(); t1.synchronize()
+                self.projection_ms = t0.elapsed_time(t1)
+            self._proj, self._proj_key = P, key
+        return self._desc_proj, self._proj
+
     def _workspace(self, B, W, group):
         """Scratch of the scorer (per-batch std + the resident CTAs' h slabs).  It only grows, and a replaced buffer stays alive:
         a captured CUDA graph (MotifPipeline) may still hold its address."""
@@ -197,6 +228,7 @@ class TempME(nn.Module):
         group = int(group or self.batch_group or max(B, 1))
         blob = self.packed_weights()
         nf, ef = self._tables()
+        desc, ef = self._edge_table(blob, ef)
         self._workspace(B, W, group)
         if out is None:
             scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
@@ -207,11 +239,11 @@ class TempME(nn.Module):
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         if peer_ptrs:
             arr = (C.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
-            check(lib().tm_encode_score_gather(C.byref(self._desc), ptr(blob), B, W, group, ptr(nodes), ptr(eidx), ptr(t), ptr(cat),
+            check(lib().tm_encode_score_gather(C.byref(desc), ptr(blob), B, W, group, ptr(nodes), ptr(eidx), ptr(t), ptr(cat),
                                                ptr(cut_time), ptr(edge_identity), ptr(nf), nf.shape[0], ptr(ef), ef.shape[0],
                                                ptr(self._ws), ptr(scores), arr, len(peer_ptrs), self.device.index, st), "tm_encode_score_gather")
             return scores
-        check(lib().tm_encode_score(C.byref(self._desc), ptr(blob), B, W, group, ptr(nodes), ptr(eidx), ptr(t), ptr(cat),
+        check(lib().tm_encode_score(C.byref(desc), ptr(blob), B, W, group, ptr(nodes), ptr(eidx), ptr(t), ptr(cat),
                                     ptr(cut_time), ptr(edge_identity), ptr(nf), nf.shape[0], ptr(ef), ef.shape[0],
                                     ptr(self._ws), ptr(scores), self.device.index, st), "tm_encode_score")
         return scores
@@ -282,11 +314,12 @@ class TempME(nn.Module):
             return emb
         blob = self.packed_weights()
         nf, ef = self._tables()
+        desc, ef = self._edge_table(blob, ef)
         self._workspace(B, W, group)
         scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
         y = torch.empty((B, W, self.hid_dim), dtype=torch.float32, device=self.device)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        check(lib().tm_encode_attention(C.byref(self._desc), ptr(blob), B, W, group, ptr(nodes), ptr(eidx), ptr(t), ptr(cat), ptr(cut), ptr(eid),
+        check(lib().tm_encode_attention(C.byref(desc), ptr(blob), B, W, group, ptr(nodes), ptr(eidx), ptr(t), ptr(cat), ptr(cut), ptr(eid),
                                         ptr(nf), nf.shape[0], ptr(ef), ef.shape[0], ptr(self._ws), ptr(scores), ptr(y), self.device.index, st),
               "tm_encode_attention")
         w = self.compute_walk_importance(t, nodes, cut, group=group)
