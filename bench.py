@@ -533,7 +533,10 @@ def run_ours(args):
     value = world * motifs_step * args.steps / (t_ms * 1e-3)
     hist_ok = int(pipe.hist_null.sum().item()) == args.steps * motifs_step
     setup = {"graph_generate_or_map_s": graph_s, "graph_build_s": wl.build_s, "graph_device_bytes": wl.finder.device_bytes(),
-             "feature_table_bytes": int(wl.nfeat.numel() * 4 + wl.efeat.numel() * 4)}
+             "feature_table_bytes": int(wl.nfeat.numel() * 4 + wl.efeat.numel() * 4),
+             # model state rebuilt when the explainer's weights change: lin_event's edge columns applied once per edge id
+             "edge_projection": bool(wl.model.edge_projection), "edge_projection_ms": wl.model.projection_ms,
+             "edge_projection_bytes": int(wl.model._proj.numel() * 4) if wl.model._proj is not None else 0}
 
     # ---- roofline of the dominant kernel (stage durations from CUDA events inside the timed region)
     S_total = int(pipe.scanned.item())

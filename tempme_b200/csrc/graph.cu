@@ -51,29 +51,31 @@ __global__ void find_before_kernel(GraphView g, int64_t R, const int32_t *__rest
     if (lane == 0) { o_start[row] = s; o_cut[row] = (int32_t)c; }
 }
 
-// Directory of the neighbour runs of skey (one warp per node, lanes stride over the node's window): a run starts where the
-// neighbour id changes; its end is the lower bound of the next id.  count != nullptr: only count the runs.
+// Directory of the neighbour runs of skey.  One THREAD per CSR entry (hub windows of millions of entries would serialise a warp-per-node
+// walk): the thread finds its node by bisection over off[] (L2 resident), and if its entry starts a run of one neighbour id it finds the
+// run's end by bisection and inserts the run.  count != nullptr: only count the runs.
 __global__ void run_directory_kernel(GraphView g, RunSlot *tab, uint64_t mask, unsigned long long *count) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long local = 0;
-    for (int64_t v = warp0; v < g.n_nodes; v += n_warps) {
-        const int64_t s = g.off[v], e = g.off[v + 1];
-        for (int64_t i = s + lane; i < e; i += 32) {
-            const uint32_t nb = (uint32_t)(g.skey[i] >> 32);
-            if (i > s && (uint32_t)(g.skey[i - 1] >> 32) == nb) continue;
-            if (count) { ++local; continue; }
-            int64_t lo = i + 1, hi = e;                      // first index whose neighbour id is larger
-            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((uint32_t)(g.skey[mid] >> 32) <= nb) lo = mid + 1; else hi = mid; }
-            const uint64_t key = (uint64_t)v << 32 | nb;
-            uint64_t slot = mix64(key) & mask;
-            while (atomicCAS(reinterpret_cast<unsigned long long *>(&tab[slot].key), ~0ull, (unsigned long long)key) != ~0ull) slot = (slot + 1) & mask;
-            RunSlot &r = tab[slot];
-            r.start = (uint32_t)i; r.len = (uint32_t)(lo - i);
-            for (int j = 0; j < 4; ++j) r.pos[j] = i + j < lo ? (uint32_t)g.skey[i + j] : 0xffffffffu;
-        }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < g.n_entries; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t nb = (uint32_t)(g.skey[i] >> 32);
+        int64_t lo = 0, hi = g.n_nodes;                      // node v with off[v] <= i < off[v + 1]
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(g.off + mid + 1) <= i) lo = mid + 1; else hi = mid; }
+        const int64_t v = lo, s = __ldg(g.off + v), e = __ldg(g.off + v + 1);
+        if (i > s && (uint32_t)(g.skey[i - 1] >> 32) == nb) continue;
+        if (count) { ++local; continue; }
+        lo = i + 1; hi = e;                                  // first index whose neighbour id is larger
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((uint32_t)(g.skey[mid] >> 32) <= nb) lo = mid + 1; else hi = mid; }
+        const uint64_t key = (uint64_t)v << 32 | nb;
+        uint64_t slot = mix64(key) & mask;
+        while (atomicCAS(reinterpret_cast<unsigned long long *>(&tab[slot].key), ~0ull, (unsigned long long)key) != ~0ull) slot = (slot + 1) & mask;
+        RunSlot &r = tab[slot];
+        r.start = (uint32_t)i; r.len = (uint32_t)(lo - i);
+        for (int j = 0; j < 4; ++j) r.pos[j] = i + j < lo ? (uint32_t)g.skey[i + j] : 0xffffffffu;
     }
-    if (count && local) atomicAdd(count, local);
+    if (count) {
+        for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+    }
 }
 
 }  // namespace tm
@@ -100,7 +102,7 @@ static int build_run_directory(tm_graph *g) {
         ce = cudaMalloc(&d_cnt, sizeof *d_cnt);
         if (ce == cudaSuccess) ce = cudaMemset(d_cnt, 0, sizeof *d_cnt);
         if (ce == cudaSuccess) {
-            run_directory_kernel<<<148 * 8, 256>>>(g->v, nullptr, 0, d_cnt);
+            run_directory_kernel<<<148 * 16, 256>>>(g->v, nullptr, 0, d_cnt);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ce = cudaMemcpy(&runs, d_cnt, sizeof runs, cudaMemcpyDeviceToHost);
         }
@@ -109,7 +111,7 @@ static int build_run_directory(tm_graph *g) {
         if (ce == cudaSuccess) ce = cudaMalloc(&d_h, sizeof(RunSlot) * slots);
         if (ce == cudaSuccess) ce = cudaMemset(d_h, 0xff, sizeof(RunSlot) * slots);
         if (ce == cudaSuccess) {
-            run_directory_kernel<<<148 * 8, 256>>>(g->v, d_h, slots - 1, nullptr);
+            run_directory_kernel<<<148 * 16, 256>>>(g->v, d_h, slots - 1, nullptr);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ce = cudaDeviceSynchronize();
         }
