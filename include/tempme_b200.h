@@ -266,6 +266,12 @@ int tm_beta_sample(int64_t n, const float *d_prob, const int32_t *d_node_or_null
 int tm_kl_loss_backward(int64_t B, int64_t W, const float *d_prob, const uint8_t *d_cat, const float *d_null_values, int n_cat, float target,
                         int empirical, const float *d_grad_out_or_null, float *d_grad_prob, tm_stream stream);
 
+/* fp32-accurate GEMM on the tensor cores (tcgen05, 3xTF32 split, TMEM accumulators): C[M,N] (+)= A[M,K] . B[N,K]^T (+ bias[N]), row-major
+ * with leading dimensions.  The forward / dgrad / wgrad products of the explainer's nn.Linear layers when gradients are requested
+ * (models/explainer.py:174-201 under temp_exp_main.py:605-632's loss.backward()); tempme_b200/training.py: TcLinear. */
+int tm_gemm_tf32x3(int64_t M, int64_t N, int64_t K, const float *d_A, int64_t lda, const float *d_B, int64_t ldb, float *d_C, int64_t ldc,
+                   const float *d_bias_or_null, int accumulate, tm_stream stream);
+
 /* Hardware self-test of the tcgen05/TMEM conventions the scorer relies on: C[128,N] = A[128,K] * B[N,K]^T on the
  * tensor cores (mode 0: one TF32 pass, mode 1: 3xTF32 split accumulation).  K % 8 == 0, N % 16 == 0, N <= 256. */
 int tm_selftest_gemm(const float *d_A, const float *d_B, float *d_C, int K, int N, int mode, tm_stream stream);

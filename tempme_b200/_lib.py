@@ -65,6 +65,7 @@ SIGNATURES = {
     "tm_encoder_workspace_floats": (_i64, [C.POINTER(EncoderDesc), _i64, _i64, _i64]),
     "tm_encoder_profile": (C.c_int, [C.c_int]),
     "tm_encoder_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "tm_gemm_tf32x3": (C.c_int, [_i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, C.c_int, _p]),
     "tm_selftest_gemm": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p]),
     "tm_selftest_cos": (C.c_int, [_p, _p, _i64, _p]),
     "tm_selftest_gather4": (C.c_int, [_p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p]),

@@ -16,7 +16,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["graph.cu", "graph_build.cu", "sample.cu", "encoder.cu", "encoder_tc.cu", "tc_selftest.cu", "edge_imp.cu", "enhance.cu", "kl.cu", "train.cu"]
+SOURCES = ["graph.cu", "graph_build.cu", "sample.cu", "encoder.cu", "encoder_tc.cu", "tc_selftest.cu", "edge_imp.cu", "enhance.cu", "kl.cu", "train.cu", "gemm_tc.cu"]
 HEADERS = ["common.cuh", "tc.cuh", "timeenc.cuh", "beta.cuh", os.path.join("..", "..", "include", "tempme_b200.h")]
 LIB = os.path.join(CSRC, "libtempme_b200.so")
 STAMP = LIB + ".stamp"

@@ -6,7 +6,8 @@ Division of labour
   * forward values without dropout (eval mode, ``dropout_p == 0``, or no parameter requires grad) always come from the fused
     sm_100a scorer; ``FusedScore`` attaches a backward that recomputes the layers from the saved walk tensors;
   * the layer-by-layer differentiable evaluation below (``scores_layerwise``) is the recompute of that backward and the
-    training-mode forward (dropout masks must be shared by forward and backward); its GEMMs are plain library GEMMs;
+    training-mode forward (dropout masks must be shared by forward and backward); every nn.Linear in it goes through ``TcLinear``:
+    forward, dgrad and wgrad products on the library's tcgen05 3xTF32 GEMM (``tm_gemm_tf32x3``), the elementwise glue is torch;
   * hand-written kernels with their own backward: the Beta sampler (``tm_beta_sample``: Philox + Marsaglia-Tsang gammas, pathwise
     gradient through the two gammas) and ``kl_loss`` (``tm_kl_loss`` / ``tm_kl_loss_backward``).
 """
@@ -24,6 +25,58 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+# ---------------------------------------------------------------------------------------------------- Linear on the tcgen05 GEMM
+def gemm(a, b, bias=None, out=None, accumulate=False):
+    """out[M, N] (+)= a[M, K] @ b[N, K]^T (+ bias[N]) on tm_gemm_tf32x3 (fp32 in / out, 3xTF32 on the tensor cores)."""
+    a = a.contiguous(); b = b.contiguous()
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and a.dtype == torch.float32 and b.dtype == torch.float32
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    bs = bias.contiguous() if bias is not None else None
+    with torch.cuda.device(a.device):
+        check(lib().tm_gemm_tf32x3(M, N, K, ptr(a), K, ptr(b), K, ptr(out), out.stride(0), ptr(bs), int(bool(accumulate)), _stream(a.device)), "tm_gemm_tf32x3")
+    return out
+
+
+class TcLinear(torch.autograd.Function):
+    """y = x W^T + b with forward, dgrad (dx = dy W) and wgrad (dW = dy^T x) on the tensor cores."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1]).to(torch.float32)
+        ctx.save_for_backward(x2, weight)
+        ctx.shape = x.shape
+        ctx.has_bias = bias is not None
+        y = gemm(x2, weight.detach(), bias.detach() if bias is not None else None)
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1]).to(torch.float32).contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm(g2, weight.detach().t().contiguous()).view(ctx.shape)            # dX = dY W: B operand = W^T [K, N]
+        if ctx.needs_input_grad[1]:
+            gw = gemm(g2.t().contiguous(), x2.t().contiguous())                        # dW = dY^T X: reduction over the rows
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gx, gw, gb
+
+
+def _linear(mod, x):
+    return TcLinear.apply(x, mod.weight, mod.bias)
+
+
+def _seq(seq, x):
+    """nn.Sequential of Linear / ReLU / Dropout with the Linears on TcLinear."""
+    for layer in seq:
+        x = _linear(layer, x) if isinstance(layer, torch.nn.Linear) else layer(x)
+    return x
+
+
 # ---------------------------------------------------------------------------------------------------- layer-by-layer scorer
 def _time_encode(m, dt):
     """TimeEncode (explainer.py:51-59): cos(dt * basis_freq + phase), dt [...]. -> [..., D]"""
@@ -36,11 +89,11 @@ def attention_layerwise(m, nodes, eidx, t, cut, eid):
     nodes i64 [B,W,6] (src3,tgt3,src2,tgt2,src1,tgt1), eidx i64 [B,W,3], t f32 [B,W,3], cut f32 [B], eid f32 [B,W,3,3]."""
     ec, att = m.event_conv, m.attention
     x = torch.cat([m.edge_raw_embed(eidx), eid, _time_encode(m, t[..., 2:3] - t)], dim=-1)       # [B,W,3,ev] (:176-179, :326)
-    ev = ec.lin_event(x)
+    ev = _linear(ec.lin_event, x)
     a, b = m.node_raw_embed(nodes[..., 0::2]), m.node_raw_embed(nodes[..., 1::2])                # the events' two endpoints (:348-351)
-    h = torch.cat([ec.MLP(a + torch.relu(b + ev)), ec.MLP(b + torch.relu(a + ev))], dim=-1)      # both orientations (:182-186)
+    h = torch.cat([_seq(ec.MLP, a + torch.relu(b + ev)), _seq(ec.MLP, b + torch.relu(a + ev))], dim=-1)      # both orientations (:182-186)
     q, k = h[:, :, 2], h[:, :, :2]                                                               # the event next to the root queries the other two
-    wp, wq = att.W1(q), att.W2(k)                                                                # [B,W,2H], [B,W,2,2H]
+    wp, wq = _linear(att.W1, q), _linear(att.W2, k)                                              # [B,W,2H], [B,W,2,2H]
     s = (wq * wp.unsqueeze(2)).sum(-1)                                                           # [B,W,2]
     if m.use_temporal_guidance:
         td = (cut.view(-1, 1, 1) - t[..., :2]).abs()
@@ -48,7 +101,7 @@ def attention_layerwise(m, nodes, eidx, t, cut, eid):
     alpha = torch.softmax(s, dim=-1)
     if m.use_temporal_guidance:
         alpha = att.dropout(alpha)
-    return att.MLP(q + (alpha.unsqueeze(-1) * wq).sum(2))                                        # (:841-843)
+    return _seq(att.MLP, q + (alpha.unsqueeze(-1) * wq).sum(2))                                  # (:841-843)
 
 
 def scores_layerwise(m, nodes, eidx, t, cat, cut, eid):
@@ -56,7 +109,7 @@ def scores_layerwise(m, nodes, eidx, t, cat, cut, eid):
     y = attention_layerwise(m, nodes, eidx, t, cut, eid)
     if m.if_cat:
         y = torch.cat([y, F.one_hot(cat.long(), 12).to(y.dtype)], dim=-1)
-    return torch.sigmoid(m.MLP(y))
+    return torch.sigmoid(_seq(m.MLP, y))
 
 
 class FusedScore(torch.autograd.Function):
@@ -136,7 +189,7 @@ def edge_importance_autograd(m, scores, eidx_w, t_w, h_nodes, h_eidx, training):
     imp = scores.reshape(B, W, 1).expand(B, W, 3).reshape(B, 3 * W)                               # graphlet_imp.repeat(1,1,3) (:363)
     if m.use_dependency_aware_sampling:
         feat = torch.cat([m.edge_raw_embed(e), _time_encode(m, t_w.reshape(B, 3 * W))], dim=-1)  # raw timestamps (:371-375)
-        gate = torch.sigmoid(m.edge_dependency_gcn(feat).squeeze(-1))
+        gate = torch.sigmoid(_seq(m.edge_dependency_gcn, feat).squeeze(-1))
         imp = imp * (0.5 + 0.5 * gate)                                                           # (:383-386)
     stride = int(max(int(e.max()), max(int(x.max()) for x in h_eidx))) + 1
     row = torch.arange(B, device=e.device).view(B, 1) * stride

@@ -181,3 +181,26 @@ def test_kl_loss_backward_matches_autograd_of_the_formula(tm, golden, prior):
                 ref = (x * torch.log(x / target + 1e-6) + (1 - x) * torch.log((1 - x) / (1 - target + 1e-6) + 1e-6)).mean()
             ref.backward()
             np.testing.assert_allclose(p.grad.cpu().numpy(), q.grad.float().cpu().numpy(), rtol=2e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (300, 172, 347), (27000, 64, 172), (1, 1, 64), (77, 76, 76), (257, 130, 9), (5, 300, 40)])
+def test_tcgen05_gemm_of_the_training_path(tm, M, N, K):
+    """tm_gemm_tf32x3: C = A B^T + bias (and the accumulate form) against float64; TcLinear's three products against autograd of F.linear."""
+    from tempme_b200.training import TcLinear, gemm
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn((M, K), generator=g, device="cuda"); b = torch.randn((N, K), generator=g, device="cuda"); bias = torch.randn(N, generator=g, device="cuda")
+    ref = (a.double() @ b.double().t() + bias.double())
+    scale = (a.double().abs() @ b.double().abs().t()).clamp(min=1.0)
+    out = gemm(a, b, bias)
+    assert float(((out.double() - ref).abs() / scale).max()) < 2e-6           # 3xTF32: ~1e-6 of the sum of magnitudes (fp32: ~1e-7)
+    out2 = gemm(a, b, None, out=out.clone(), accumulate=True)
+    assert float(((out2.double() - (2 * ref - bias.double())).abs() / scale).max()) < 4e-6
+    x = a.clone().requires_grad_(True); w = b.clone().requires_grad_(True); bb = bias.clone().requires_grad_(True)
+    y = TcLinear.apply(x.view(1, M, K), w, bb)
+    gy = torch.randn((1, M, N), generator=g, device="cuda")
+    y.backward(gy)
+    x64, w64, b64 = (t.detach().double().requires_grad_(True) for t in (a, b, bias))
+    torch.nn.functional.linear(x64.view(1, M, K), w64, b64).backward(gy.double())
+    for got, want in ((x.grad, x64.grad), (w.grad, w64.grad), (bb.grad, b64.grad)):
+        s_ = max(float(want.abs().max()), 1e-12)
+        assert float((got.double() - want).abs().max()) <= 3e-5 * s_ * max(1.0, (M * 1.0) ** 0.5 / 16), (M, N, K)
