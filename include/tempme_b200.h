@@ -97,6 +97,12 @@ int tm_sample_hop(const tm_graph *g, int64_t R, const int32_t *d_node, const dou
                   const int32_t *d_eidx, int n, uint64_t seed, uint32_t stage, uint64_t row_offset,
                   const uint32_t *d_inject, int32_t *d_o_node, int32_t *d_o_eidx, float *d_o_ts,
                   int32_t *d_err, tm_stream stream);
+/* find_k_hop (utils/graph.py:233-262) as one call: hop 0 on the roots, hop l >= 1 on the flattened records of hop l - 1 looked up by e_idx
+ * (:247-250).  h_o_node / h_o_eidx / h_o_ts are HOST arrays of k device pointers; hop l has shape [B, n^(l+1)].  Stage l draws use
+ * row = row_offset * n^l + i, as k separate tm_sample_hop calls would. */
+int tm_sample_khop(const tm_graph *g, int64_t B, int k, int n, const int32_t *d_root, const double *d_cut_time, const int32_t *d_eidx,
+                   uint64_t seed, uint64_t row_offset, int32_t *const *h_o_node, int32_t *const *h_o_eidx, float *const *h_o_ts,
+                   int32_t *d_err, tm_stream stream);
 
 /* find_k_walks = get_next_step + get_final_step (utils/graph.py:265-476).
  * d_root [B]; d_h1_* [B, n] (first-hop record).  W = n * N2 walks per root, walk w = i1 * N2 + j.

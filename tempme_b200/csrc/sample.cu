@@ -419,6 +419,26 @@ extern "C" int tm_sample_hop(const tm_graph *g, int64_t R, const int32_t *d_node
     return TM_OK;
 }
 
+// find_k_hop (utils/graph.py:233-262) as one call: hop 0 on the roots (window by e_idx where d_eidx has one, else by time), hop l >= 1 on
+// the flattened records of hop l - 1, looked up by e_idx (:247-250).  h_o_node / h_o_eidx / h_o_ts: HOST arrays of k device pointers, hop l
+// = [B, n^(l+1)].  Draw contract: stage l, row = row_offset * n^l + i (so shards and chunks reproduce the single call).
+extern "C" int tm_sample_khop(const tm_graph *g, int64_t B, int k, int n, const int32_t *d_root, const double *d_cut_time, const int32_t *d_eidx,
+                              uint64_t seed, uint64_t row_offset, int32_t *const *h_o_node, int32_t *const *h_o_eidx, float *const *h_o_ts,
+                              int32_t *d_err, tm_stream stream) {
+    if (!g || B < 0 || k < 0 || n <= 0 || (k > 0 && (!h_o_node || !h_o_eidx || !h_o_ts))) { set_error("tm_sample_khop: bad argument"); return TM_ERR_ARG; }
+    int64_t rows = B;
+    uint64_t off = row_offset;
+    for (int l = 0; l < k; ++l) {
+        if (!h_o_node[l] || !h_o_eidx[l] || !h_o_ts[l]) { set_error("tm_sample_khop: null output for hop %d", l); return TM_ERR_ARG; }
+        const int rc = l == 0 ? tm_sample_hop(g, rows, d_root, d_cut_time, d_eidx, n, seed, 0, off, nullptr, h_o_node[0], h_o_eidx[0], h_o_ts[0], d_err, stream)
+                              : tm_sample_hop(g, rows, h_o_node[l - 1], nullptr, h_o_eidx[l - 1], n, seed, (uint32_t)l, off, nullptr, h_o_node[l], h_o_eidx[l],
+                                              h_o_ts[l], d_err, stream);
+        if (rc != TM_OK) return rc;
+        rows *= n; off *= (uint64_t)n;
+    }
+    return TM_OK;
+}
+
 static int walks_impl(const tm_graph *g, int64_t B, int n, int N2, const int32_t *d_root,
                       const int32_t *d_h1_node, const int32_t *d_h1_eidx, const float *d_h1_ts,
                       uint64_t seed, uint64_t row_offset, const uint32_t *d_inject2, const uint32_t *d_inject3,

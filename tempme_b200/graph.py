@@ -269,15 +269,28 @@ class NeighborFinder:
         n = int(num_neighbors)
         B = len(src_idx_l)
         ct = None if e_idx_l is not None else cut_time_l
-        x, y, z = self.sample_hop_device(src_idx_l, ct, n, e_idx_l, s, 0, row_offset, inject[0] if inject else None)
-        recs = ([x], [y], [z])
-        for layer in range(1, k):
-            pn, pe = recs[0][-1].reshape(-1), recs[1][-1].reshape(-1)
-            # deeper hops look the window up by e_idx; the (float32) time is unused (graph.py:247-250)
-            x, y, z = self.sample_hop_device(pn, None, n, pe, s, layer, row_offset * (n ** layer),
-                                             inject[layer] if inject else None)
-            for r, v in zip(recs, (x, y, z)):
-                r.append(v.view(B, n ** (layer + 1)))
+        if inject:                      # replaying recorded indices: hop by hop
+            x, y, z = self.sample_hop_device(src_idx_l, ct, n, e_idx_l, s, 0, row_offset, inject[0])
+            recs = ([x], [y], [z])
+            for layer in range(1, k):
+                pn, pe = recs[0][-1].reshape(-1), recs[1][-1].reshape(-1)
+                # deeper hops look the window up by e_idx; the (float32) time is unused (graph.py:247-250)
+                x, y, z = self.sample_hop_device(pn, None, n, pe, s, layer, row_offset * (n ** layer), inject[layer])
+                for r, v in zip(recs, (x, y, z)):
+                    r.append(v.view(B, n ** (layer + 1)))
+            return recs
+        root = self._dev(src_idx_l, torch.int32)
+        ctd = self._dev(ct, torch.float64) if ct is not None else None
+        ed = self._dev(e_idx_l, torch.int32)
+        recs = ([], [], [])
+        for layer in range(k):
+            w = n ** (layer + 1)
+            recs[0].append(torch.empty((B, w), dtype=torch.int32, device=self.device))
+            recs[1].append(torch.empty((B, w), dtype=torch.int32, device=self.device))
+            recs[2].append(torch.empty((B, w), dtype=torch.float32, device=self.device))
+        arr = lambda ts: (C.c_void_p * k)(*[t.data_ptr() for t in ts])
+        check(lib().tm_sample_khop(self._h, B, int(k), n, ptr(root), ptr(ctd), ptr(ed), s, row_offset, arr(recs[0]), arr(recs[1]), arr(recs[2]),
+                                   ptr(self._err), self._stream()), "tm_sample_khop")
         return recs
 
     def find_k_hop(self, k, src_idx_l, cut_time_l, num_neighbors, e_idx_l=None, seed=None, row_offset=0, inject=None):
