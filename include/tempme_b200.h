@@ -154,6 +154,10 @@ typedef struct {
     int32_t if_cat;       /* one-hot category features                 explainer.py:116,195-197 */
     int32_t edge_projected; /* 0: d_edge_feat is the base model's edge feature table [rows, Ed].  1: d_edge_feat is the table made by
                              * tm_encoder_project_edges, [rows, D]: lin_event's edge columns already applied per edge id */
+    int32_t walk_fanout;  /* layout hint, 0 / 1 = none: find_k_walks numbers the walks of a root w = i1 * N2 + j (utils/graph.py:290-300), so
+                           * walk_fanout = N2 consecutive walks share the event next to the root.  The scorer then evaluates that event's
+                           * layers (and the products that depend on it alone) once per group; every tile of groups checks the premise
+                           * on its own operands and repeats the work per walk where it does not hold, so any value gives the same scores */
 } tm_encoder_desc;
 
 /* Host pointers to the reference's parameters (nn.Linear layout: weight [out, in] row-major). */

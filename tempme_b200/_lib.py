@@ -20,7 +20,7 @@ _u64 = C.c_uint64
 
 class EncoderDesc(C.Structure):
     _fields_ = [("node_dim", C.c_int32), ("edge_dim", C.c_int32), ("hid_dim", C.c_int32),
-                ("use_temporal", C.c_int32), ("if_cat", C.c_int32), ("edge_projected", C.c_int32)]
+                ("use_temporal", C.c_int32), ("if_cat", C.c_int32), ("edge_projected", C.c_int32), ("walk_fanout", C.c_int32)]
 
 
 PARAM_FIELDS = ["lin_event_w", "lin_event_b", "gcn0_w", "gcn0_b", "gcn2_w", "gcn2_b", "att_w1_w", "att_w1_b",

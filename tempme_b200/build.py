@@ -33,7 +33,8 @@ def nvcc_path():
 
 def _extra_flags():
     # diagnostic build: per-round clock stamps in the scorer (TEMPME_TC_TIMING=1 at run time)
-    return ["-DTM_TC_TIMING"] if os.environ.get("TEMPME_BUILD_TIMING") else []
+    # TEMPME_BUILD_DEFS: extra -D switches of A/B experiments (space separated)
+    return (["-DTM_TC_TIMING"] if os.environ.get("TEMPME_BUILD_TIMING") else []) + os.environ.get("TEMPME_BUILD_DEFS", "").split()
 
 
 def source_hash() -> str:

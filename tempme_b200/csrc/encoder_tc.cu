@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -363,7 +364,18 @@ __device__ __forceinline__ void tma_gather4(void *dst_smem, const CUtensorMap *m
 }
 
 constexpr int kMaxPeers = 7;
+// Launch constants derived from the layout on the host: the kernel reads them from the parameter bank where it needs them instead of
+// deriving them in its prologue and carrying them in registers through every round
+struct TcDer {
+    int H2, nG, nchS, colE, colY, colM0, colM1, colA3, nsl, dq, de, m3one, cpr, ed_vec, d_vec, jofs;
+    int ev_K8, ev_nch, ne01, ne2;            // lin_event operand in use (edge-projection mode: its TimeEncode columns only): padded K, chunks, rounds at positions 0 / 1 and 2
+    int bytes_e, bytes_g, bytes_sp, bytes_q, bytes_r, bytes_m3;
+    int fw01_bytes, fw2_bytes;               // first weight request of a pass at positions 0 / 1 and at position 2
+    int64_t ev_w, ev_chunk, fw01_off, fw2_off;
+    int64_t n_rows, n_tiles;                 // tile rows (motifs, or first-hop slots of walk groups) and tiles of 128 rows
+};
 struct TcArgs {
+    TcDer k;
     int64_t n_motifs, W, group;              // B * W motifs; W walks per root; roots per reference batch (index of std_)
     const int32_t *nodes, *eidx;
     const float *t;
@@ -386,6 +398,9 @@ struct TcArgs {
     int proj;                                // edge-projection mode: edge_feat is the table P = lin_event[:, :Ed] . edge features [n_edge_rows][D] (tc_project_edges);
                                              //   lin_event runs over its TimeEncode columns only and P's rows are gathered like a third node-feature table
     int discard;                             // discard.global.L2 on the h slabs once a tile has consumed them (no write-back of the scratch)
+    int share;                               // SHARE instantiations: consecutive walks per first-hop slot (find_k_walks: w = i1 * N2 + j, share = N2 >= 2, divides n_motifs)
+    float *Ys;                               // SHARE: per CTA H / 32 slabs that hold P h_2 + cy of the tile's slots between the sub-tiles
+    int sp_stage_safe;                       // the row staging lies behind the [S; P] weight chunk: staged rows may be in flight during the [S; P] rounds
     int dual;                                // two A buffers: bit 0 both orientations of MLP.0 per round + Q / R chunk pairs, bit 1 lin_event chunk pairs, bit 2 MLP.3 in one round
     long long *dbg;                          // TEMPME_TC_TIMING: 128 x 5 clock stamps of CTA 0
 };
@@ -414,7 +429,12 @@ template <> __device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, float *
 template <> __device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, float *v) { tc::tmem_ld8(taddr, v); }
 
 // CW = columns of a K chunk per thread: 16 -> 256 threads, 8 -> 512 threads; TS = A operand in TMEM (else shared memory)
-template <int CW, bool TS, bool DRAIN>
+// SHARE: walk groups.  The s = a.share walks of a first-hop slot are consecutive (find_k_walks: w = i1 * N2 + j, utils/graph.py:290-300) and
+// carry the same event next to the root: same edge id, endpoints and edge-identity counts, dt = 0.  A tile is then 128 SLOTS: the
+// position-2 pass and the [S; P] rounds run once per slot, U + cu and P h_2 + cy leave TMEM for the CTA's L2 scratch (U over the dead h_2
+// slabs), and s sub-tiles (motif = slot * s + j) follow with the passes of positions 0 / 1 and the motif rounds.  Every tile verifies the
+// premise on its own operands (a CTA-wide vote); where it does not hold the position-2 work is simply repeated per sub-tile.
+template <int CW, bool TS, bool DRAIN, bool SHARE>
 __global__ void __launch_bounds__(128 * (kKC / CW), 2)
 score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a, const __grid_constant__ CUtensorMap tm_node,
                 const __grid_constant__ CUtensorMap tm_edge) {
@@ -440,26 +460,52 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     const uint32_t tmem = tmem_slot, lane_base = (uint32_t)((warp & 3) * 32) << 16;
     x.tmem = tmem; x.a_col = a.tmem_cols - 2 * kKC; x.a_col2 = x.a_col - 2 * kKC;
     AFill<CW, TS> af;
-    const int H = L.H, H2 = 2 * L.H, D = L.D, Ed = L.Ed, nG = L.g0.nch, nchS = L.sp.nch;
+    const int H = L.H, D = L.D, Ed = L.Ed;
     constexpr bool drain = DRAIN;                          // host: a.Es != nullptr exactly for the DRAIN instantiations
-    const int colZ = 0, colE = drain ? 0 : (nG == 1 && L.D16 <= H) ? H : H2;
-    const bool dq = a.dual != 0, de = (a.dual & 2) != 0;   // dual rounds (bit 0: MLP.0 orientations, Q, R; bit 1: lin_event chunk pairs).  Q and R rounds in pairs: second A buffer = columns [0, 64) (U is dead by then)
-    // m3one: MLP.3 in one round -- its two or three K chunks from A, A2 and a third buffer behind M0; M1 then lands over M0's first
-    // chunks (they have been read into the A buffers before the MMAs are issued)
-    const bool m3one = (a.dual & 4) != 0;
+    // Launch constants (TcDer, filled by tc_encode_score): read from the parameter bank at their uses.
+    // colE: E aliases Zt when MLP.0 has a single K chunk; dq / de: dual rounds (MLP.0 orientations, Q, R chunk pairs / lin_event chunk pairs);
+    // m3one: MLP.3 in one round -- its two or three K chunks from A, A2 and a third buffer behind M0; M1 then lands over M0's first chunks
     // (hid_dim 32: U [0,64) | Y [64,96); M0 then starts at column 64, clear of the second A buffer [0,64))
-    const int colU = 0, colY = H2, colM0 = dq ? max(H, 2 * kKC) : 0, colM1 = m3one ? colM0 : dq ? 0 : H2, colA3 = colM0 + L.M16;
-    const int nsl = H2 / kKC;                              // h slabs per walk position
-    const int64_t n_m = a.n_motifs, n_tiles = (n_m + 127) / 128;
+#define H2 (a.k.H2)
+#define nG (a.k.nG)
+#define nchS (a.k.nchS)
+#define colE (a.k.colE)
+#define colY (a.k.colY)
+#define colM0 (a.k.colM0)
+#define colM1 (a.k.colM1)
+#define colA3 (a.k.colA3)
+#define nsl (a.k.nsl)
+#define dq (a.k.dq != 0)
+#define de (a.k.de != 0)
+#define m3one (a.k.m3one != 0)
+#define cpr (a.k.cpr)
+#define ed_vec (a.k.ed_vec != 0)
+#define d_vec (a.k.d_vec != 0)
+#define jofs (a.k.jofs)
+#define bytes_e (a.k.bytes_e)
+#define bytes_g (a.k.bytes_g)
+#define bytes_sp (a.k.bytes_sp)
+#define bytes_q (a.k.bytes_q)
+#define bytes_r (a.k.bytes_r)
+#define bytes_m3 (a.k.bytes_m3)
+#define n_rows (a.k.n_rows)
+#define n_tiles (a.k.n_tiles)
+    constexpr int colZ = 0, colU = 0;
+    const int sh = SHARE ? a.share : 1;                    // sub-tiles per tile
     const bool proj = a.proj != 0;
-    const TcLin EV = proj ? L.evtT : L.evt;                // lin_event operand chunks in use
-    const int bytes_e = (int)chunk_floats(EV) * 4, bytes_g = (int)chunk_floats(L.g0) * 4;
-    const int bytes_sp = (int)chunk_floats(L.sp) * 4, bytes_q = (int)chunk_floats(L.q) * 4, bytes_r = (int)chunk_floats(L.r) * 4, bytes_m3 = (int)chunk_floats(L.m3) * 4;
-    if (t == 0 && blockIdx.x < n_tiles) tc_request_b(x, EV.w, min(de ? 2 : 1, EV.nch) * bytes_e);
-    const bool ed_vec = (Ed & 3) == 0, d_vec = (D & 3) == 0;
+    // lin_event rounds of the pass at position pos (position 2: dt = 0, the pure TimeEncode chunks are in the bias; edge-projection mode: no round
+    // at all), and the weights of a pass's first round
+    auto n_evt_rounds = [&](int pos) { return pos == 2 ? a.k.ne2 : a.k.ne01; };
+    auto first_w = [&](int pos, int64_t &off, int &bytes) {
+        if (pos == 2) { off = a.k.fw2_off; bytes = a.k.fw2_bytes; } else { off = a.k.fw01_off; bytes = a.k.fw01_bytes; }
+    };
+    constexpr int kFirstPos = SHARE ? 2 : 0;               // a tile starts with this position's pass
+    if (t == 0 && blockIdx.x < n_tiles) { int64_t o_; int b_; first_w(kFirstPos, o_, b_); tc_request_b(x, o_, b_); }
     float *Fs = a.F + (int64_t)blockIdx.x * 3 * nsl * kSlabFloats;      // this CTA's h slabs: [position][column chunk][piece k/4][128 rows][4]
     const float *F0 = Fs, *F1 = Fs + nsl * kSlabFloats, *F2 = Fs + 2 * nsl * kSlabFloats;
     float *Es = drain ? a.Es + (int64_t)blockIdx.x * nG * kSlabFloats : nullptr;
+    float *Us = Fs + 2 * nsl * kSlabFloats;                // SHARE: U + cu over the h_2 slabs (same thread-to-address map as their reader's), P h_2 + cy behind
+    float *Ys = SHARE ? a.Ys + (int64_t)blockIdx.x * (H / kKC) * kSlabFloats : nullptr;
     // this thread's CW columns [kb, kb+CW) of row `row` of a [128 x 32] slab (coalesced 16-byte pieces)
     auto ldw = [&](const float *slab, float *v) {
 #pragma unroll
@@ -504,253 +550,356 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         if (!stage_edges) return;
         request_rows(bars + 3, prt == 0, &tm_edge, (q.e >= 0 && q.e < a.n_edge_rows) ? q.e : 0, stg_e, c * kKC);
     };
-    const int jofs = proj ? Ed : 0;                        // edge-projection mode: chunk cc of lin_event starts at TimeEncode column cc * kKC
     PassIdx pcur, pnext;
     {
-        const int64_t g0_ = (int64_t)blockIdx.x * 128 + row;
-        const bool lv = blockIdx.x < n_tiles && g0_ < n_m;
-        pcur = load_idx(lv ? g0_ : 0, lv, 0);
+        const int64_t r0_ = (int64_t)blockIdx.x * 128 + row;
+        const bool lv = blockIdx.x < n_tiles && r0_ < n_rows;
+        pcur = load_idx(lv ? r0_ * sh : 0, lv, kFirstPos);
         pnext = pcur;
         if (blockIdx.x < n_tiles) { request_nodes(pcur, 0); request_edges(pcur, 0); }
     }
-
-    for (int64_t tile = blockIdx.x; tile < n_tiles;) {
-        const int64_t gm_ = tile * 128 + row;
-        const bool live = gm_ < n_m;
-        const int64_t gm = live ? gm_ : 0;
-        // the CTA's next tile (dynamic: SMs that run a single CTA, or faster ones, take more tiles); read after the event passes' barriers
-        if (t == 0) s_next_tile = (long long)gridDim.x + (long long)atomicAdd(a.tile_counter, 1ull);
-        // =========================== event passes ===========================
-        x.a_col2 = x.a_col - 2 * kKC;
+    // SHARE: do the sh walks of this thread's slot (first motif g0_, walk 0's position-2 operands in p0) carry the same event next to the root?
+    // Thread part 0 compares the ids, part 1 the edge-identity counts; the loads of up to four walks are in flight together.
+    auto group_eq = [&](const int64_t g0_, const PassIdx &p0) -> int {
+        int eq = 1;
+        if (prt == 0) {
 #pragma unroll 1
-        for (int pos = 0; pos < 3; ++pos) {
-            // position 2: dt = 0, the pure TimeEncode chunks are in the bias (edge-projection mode: no lin_event round at all)
-            const int nE = proj ? (pos == 2 ? 0 : EV.nch) : (pos == 2 ? L.nch_edge : L.evt.nch);
-            const bool have_E = nE > 0;
-            const PassIdx pi = pcur;
-            if (pos < 2) pnext = load_idx(gm, live, pos + 1);
-            const bool e_ok = pi.e >= 0 && pi.e < a.n_edge_rows, s_ok = pi.ns >= 0 && pi.ns < a.n_node_rows, t_ok = pi.nt >= 0 && pi.nt < a.n_node_rows;
-            const float *ef = a.edge_feat + (int64_t)max(pi.e, 0) * Ed, *sf = a.node_feat + (int64_t)max(pi.ns, 0) * D, *tf = a.node_feat + (int64_t)max(pi.nt, 0) * D;
-            auto xval = [&](int j) -> float {                                              // [edge features | TimeEncode] column j (:179, :55-58)
-                if (j < Ed) return e_ok ? __ldg(ef + j) : 0.f;
-                const int k = j - Ed;
-                if (k < D) return live ? cos_accurate(__fadd_rn(__fmul_rn(pi.dt, cstE[L.e_freq + k]), cstE[L.e_phase + k]), ctab) : 0.f;
-                return 0.f;
-            };
-            // this thread's columns of chunk cc are all TimeEncode columns (straight-line code, the cosines interleave)
-            auto time_chunk = [&](int cc) {
-                const int j0 = cc * kKC + kb + jofs;
-                return j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + L.D16 && kb + CW <= min(kKC, EV.K8 - cc * kKC);
-            };
-            auto cos_chunk = [&](int cc, float *w) {
-                const int j0 = cc * kKC + kb + jofs;
+            for (int j = 1; j < sh; j += 4) {
+                int32_t e_[4], s_[4], t_[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t g = g0_ + min(j + i, sh - 1);
+                    e_[i] = a.eidx[g * 3 + 2]; s_[i] = a.nodes[g * 6 + 4]; t_[i] = a.nodes[g * 6 + 5];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) eq &= (int)(e_[i] == p0.e) & (int)(s_[i] == p0.ns) & (int)(t_[i] == p0.nt);
+            }
+        } else if (prt == 1 && a.eid) {
+#pragma unroll 1
+            for (int j = 1; j < sh; j += 4) {
+                float c_[4][3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float *ei = a.eid + (g0_ + min(j + i, sh - 1)) * 9 + 6;
+                    c_[i][0] = __ldg(ei); c_[i][1] = __ldg(ei + 1); c_[i][2] = __ldg(ei + 2);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) eq &= (int)(c_[i][0] == p0.ei0) & (int)(c_[i][1] == p0.ei1) & (int)(c_[i][2] == p0.ei2);
+            }
+        }
+        return eq;
+    };
+    int eq = 1;                                 // this row's verdict for the tile that starts next (voted at the closing barrier of its position-2 pass)
+    if (SHARE) {
+        const int64_t r0_ = (int64_t)blockIdx.x * 128 + row;
+        if (blockIdx.x < n_tiles && r0_ < n_rows) eq = group_eq(r0_ * sh, pcur);
+    }
+    float sk0 = 0.f, sk1 = 0.f;                 // SHARE: this thread's share of h_0 . (U + cu) and h_1 . (U + cu), accumulated by the passes' epilogues
+
+    // =========================== event pass ===========================
+    // One walk position of the tile's rows: lin_event -> E, MLP.0 for both orientations -> Zs, Zt, h_pos = relu(. + bias) -> the CTA's h slabs.
+    // pi: the rows' operands (their first staged chunks are in flight); has_next: another event pass follows directly -- its operands are in
+    // pnext and its first chunks are requested behind this pass's last rounds; (after_off, after_bytes): weights of the round that follows the
+    // pass.  Returns the CTA-wide AND of pred, taken at the pass's closing barrier.
+    auto event_pass = [&](const int pos, const PassIdx pi, const bool live, const bool has_next, const int64_t after_off, const int after_bytes, const int pred) -> int {
+        x.a_col2 = x.a_col - 2 * kKC;
+        const int nE = n_evt_rounds(pos);
+        const bool have_E = nE > 0;
+        const bool e_ok = pi.e >= 0 && pi.e < a.n_edge_rows, s_ok = pi.ns >= 0 && pi.ns < a.n_node_rows, t_ok = pi.nt >= 0 && pi.nt < a.n_node_rows;
+        const float *ef = a.edge_feat + (int64_t)max(pi.e, 0) * Ed, *sf = a.node_feat + (int64_t)max(pi.ns, 0) * D, *tf = a.node_feat + (int64_t)max(pi.nt, 0) * D;
+        auto xval = [&](int j) -> float {                                              // [edge features | TimeEncode] column j (:179, :55-58)
+            if (j < Ed) return e_ok ? __ldg(ef + j) : 0.f;
+            const int k = j - Ed;
+            if (k < D) return live ? cos_accurate(__fadd_rn(__fmul_rn(pi.dt, cstE[L.e_freq + k]), cstE[L.e_phase + k]), ctab) : 0.f;
+            return 0.f;
+        };
+        // this thread's columns of chunk cc are all TimeEncode columns (straight-line code, the cosines interleave)
+        auto time_chunk = [&](int cc) {
+            const int j0 = cc * kKC + kb + jofs;
+            return j0 >= Ed && ((j0 - Ed) & 3) == 0 && j0 + CW <= Ed + L.D16 && kb + CW <= min(kKC, a.k.ev_K8 - cc * kKC);
+        };
+        auto cos_chunk = [&](int cc, float *w) {
+            const int j0 = cc * kKC + kb + jofs;
+#pragma unroll
+            for (int g = 0; g < CW / 4; ++g) {
+                const float4 fq = lds4(cstE + L.e_freq + (j0 - Ed) + 4 * g), ph = lds4(cstE + L.e_phase + (j0 - Ed) + 4 * g);      // zero-padded to D16
+                w[4 * g] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.x), ph.x), ctab); w[4 * g + 1] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.y), ph.y), ctab);
+                w[4 * g + 2] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.z), ph.z), ctab); w[4 * g + 3] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.w), ph.w), ctab);
+            }
+        };
+        // ---- lin_event (:93) -> E.  fill_evt(cc, second): this thread's columns of chunk cc of [edge | TimeEncode] into an A buffer
+        auto fill_evt = [&](int cc, bool second) {
+            const int kcols = min(kKC, a.k.ev_K8 - cc * kKC);
+            const int j0 = cc * kKC + kb + jofs;                // this thread's columns [j0, j0 + CW) of [edge | TimeEncode]
+            if (ed_vec && j0 + CW <= Ed) {                      // all edge features (warp-uniform)
+#pragma unroll
+                for (int g = 0; g < CW / 4; ++g)
+                    af.put4(x, row, kb, 4 * g, !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stage_piece(stg_e, row, kb + 4 * g)) : ldg4(ef + j0 + 4 * g));
+                af.commit(x, lane_base, kb, second);
+            } else if (time_chunk(cc)) {                        // all TimeEncode
+                float w[CW];
+                cos_chunk(cc, w);
+                // no masks: columns >= D have zero frequency / phase (cos = 1) and zero weights; rows past the last motif are never stored
+#pragma unroll
+                for (int g = 0; g < CW / 4; ++g) af.put4(x, row, kb, 4 * g, make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]));
+                af.commit(x, lane_base, kb, second);
+            } else {                                            // mixed columns
 #pragma unroll
                 for (int g = 0; g < CW / 4; ++g) {
-                    const float4 fq = lds4(cstE + L.e_freq + (j0 - Ed) + 4 * g), ph = lds4(cstE + L.e_phase + (j0 - Ed) + 4 * g);      // zero-padded to D16
-                    w[4 * g] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.x), ph.x), ctab); w[4 * g + 1] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.y), ph.y), ctab);
-                    w[4 * g + 2] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.z), ph.z), ctab); w[4 * g + 3] = cos_accurate(__fadd_rn(__fmul_rn(pi.dt, fq.w), ph.w), ctab);
-                }
-            };
-            // ---- lin_event (:93) -> E.  fill_evt(cc, second): this thread's columns of chunk cc of [edge | TimeEncode] into an A buffer
-            auto fill_evt = [&](int cc, bool second) {
-                const int kcols = min(kKC, EV.K8 - cc * kKC);
-                const int j0 = cc * kKC + kb + jofs;                // this thread's columns [j0, j0 + CW) of [edge | TimeEncode]
-                if (ed_vec && j0 + CW <= Ed) {                      // all edge features (warp-uniform)
-#pragma unroll
-                    for (int g = 0; g < CW / 4; ++g)
-                        af.put4(x, row, kb, 4 * g, !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stage_piece(stg_e, row, kb + 4 * g)) : ldg4(ef + j0 + 4 * g));
-                    af.commit(x, lane_base, kb, second);
-                } else if (time_chunk(cc)) {                        // all TimeEncode
-                    float w[CW];
-                    cos_chunk(cc, w);
-                    // no masks: columns >= D have zero frequency / phase (cos = 1) and zero weights; rows past the last motif are never stored
-#pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) af.put4(x, row, kb, 4 * g, make_float4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]));
-                    af.commit(x, lane_base, kb, second);
-                } else {                                            // mixed columns
-#pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) {
-                        const int k = kb + 4 * g, j = cc * kKC + k + jofs;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (k < kcols) {
-                            if (ed_vec && j + 3 < Ed) v = !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stage_piece(stg_e, row, k)) : ldg4(ef + j);
-                            else v = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
-                        }
-                        if (TS || k < kcols) af.put4(x, row, kb, 4 * g, v);
+                    const int k = kb + 4 * g, j = cc * kKC + k + jofs;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (k < kcols) {
+                        if (ed_vec && j + 3 < Ed) v = !e_ok ? make_float4(0.f, 0.f, 0.f, 0.f) : stage_edges ? lds4(stage_piece(stg_e, row, k)) : ldg4(ef + j);
+                        else v = make_float4(xval(j), xval(j + 1), xval(j + 2), xval(j + 3));
                     }
-                    if (kb < kcols) af.commit(x, lane_base, kb, second);
+                    if (TS || k < kcols) af.put4(x, row, kb, 4 * g, v);
                 }
-            };
-            const int cpr = de ? 2 : 1;                             // lin_event chunks per round
-            const int nE_next = proj ? (pos == 1 ? 0 : EV.nch) : (pos == 1 ? L.nch_edge : L.evt.nch);  // chunks of the next pass (position 2 skips the pure TimeEncode chunks)
-            for (int c = 0; c < nE; c += cpr) {
-                const int cnt = min(cpr, nE - c);
-                const bool has_edge = !proj && c < L.nch_edge;      // pairs are only formed when at most the first chunk holds edge columns
-                if (stage_edges && has_edge) { tc::mbar_wait(bars + 3, e_phase); e_phase ^= 1; }        // chunk c of the edge rows has landed
-                fill_evt(c, false);
-                if (cnt == 2) fill_evt(c + 1, true);
-                const int kc0 = min(kKC, EV.K8 - c * kKC), kc1 = cnt == 2 ? min(kKC, EV.K8 - (c + 1) * kKC) : 0;
-                const int left = nE - c - cnt;
-                tc_mma_round<TS>(x, L.D16, kc0, colE, c != 0, left > 0 ? EV.w + (int64_t)(c + cnt) * chunk_floats(EV) : L.g0.w,
-                                 left > 0 ? min(cpr, left) * bytes_e : bytes_g,
-                                 [&]() {                            // the staged chunk has been consumed: the next one lands behind the MMAs
-                                     if (has_edge) {
-                                         if (c + 1 < L.nch_edge) request_edges(pi, c + 1);
-                                         else if (pos < 2) request_edges(pnext, 0);
-                                     }
-                                 }, Dual{cnt == 2 ? kDualK : kSingle, kc1, 0, 0, 0});
+                if (kb < kcols) af.commit(x, lane_base, kb, second);
             }
-            // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
-            const int eb = pos == 2 ? (proj ? L.e_b2p : L.e_b2) : L.e_b;
-            // lin_event's bias and the three edge-identity columns (applied on the CUDA cores) for this thread's columns of MLP.0 chunk c
-            auto finish_e = [&](float *ee, int c) {
+        };
+        for (int c = 0; c < nE; c += cpr) {
+            const int cnt = min(cpr, nE - c);
+            const bool has_edge = !proj && c < L.nch_edge;      // pairs are only formed when at most the first chunk holds edge columns
+            if (stage_edges && has_edge) { tc::mbar_wait(bars + 3, e_phase); e_phase ^= 1; }        // chunk c of the edge rows has landed
+            fill_evt(c, false);
+            if (cnt == 2) fill_evt(c + 1, true);
+            const int kc0 = min(kKC, a.k.ev_K8 - c * kKC), kc1 = cnt == 2 ? min(kKC, a.k.ev_K8 - (c + 1) * kKC) : 0;
+            const int left = nE - c - cnt;
+            tc_mma_round<TS>(x, L.D16, kc0, colE, c != 0, left > 0 ? a.k.ev_w + (int64_t)(c + cnt) * a.k.ev_chunk : L.g0.w,
+                             left > 0 ? min(cpr, left) * bytes_e : bytes_g,
+                             [&]() {                            // the staged chunk has been consumed: the next one lands behind the MMAs
+                                 if (has_edge) {
+                                     if (c + 1 < L.nch_edge) request_edges(pi, c + 1);
+                                     else if (has_next) request_edges(pnext, 0);
+                                 }
+                             }, Dual{cnt == 2 ? kDualK : kSingle, kc1, 0, 0, 0});
+        }
+        // ---- event_conv.MLP.0 on src + relu(tgt + event) (o = 0) and tgt + relu(src + event) (o = 1) (:94-95, :182-184) -> Zs, Zt
+        const int eb = pos == 2 ? (proj ? L.e_b2p : L.e_b2) : L.e_b;
+        // lin_event's bias and the three edge-identity columns (applied on the CUDA cores) for this thread's columns of MLP.0 chunk c
+        auto finish_e = [&](float *ee, int c) {
 #pragma unroll
-                for (int k = 0; k < CW; k += 4) {
-                    const int j0 = c * kKC + kb + k;                 // < D16: constants are zero-padded
-                    const float4 bb = lds4(cstE + eb + j0), w0 = lds4(cstE + L.e_wi + j0), w1 = lds4(cstE + L.e_wi + L.D16 + j0), w2 = lds4(cstE + L.e_wi + 2 * L.D16 + j0);
-                    ee[k] = fmaf(w2.x, pi.ei2, fmaf(w1.x, pi.ei1, fmaf(w0.x, pi.ei0, ee[k] + bb.x)));
-                    ee[k + 1] = fmaf(w2.y, pi.ei2, fmaf(w1.y, pi.ei1, fmaf(w0.y, pi.ei0, ee[k + 1] + bb.y)));
-                    ee[k + 2] = fmaf(w2.z, pi.ei2, fmaf(w1.z, pi.ei1, fmaf(w0.z, pi.ei0, ee[k + 2] + bb.z)));
-                    ee[k + 3] = fmaf(w2.w, pi.ei2, fmaf(w1.w, pi.ei1, fmaf(w0.w, pi.ei0, ee[k + 3] + bb.w)));
-                }
-            };
-            if (drain && have_E) {
-                // E leaves TMEM: every thread parks the columns it will consume in the MLP.0 rounds in its own rows of the CTA's E scratch
-                // (L2; written and read back by the same thread), then Zs | Zt take over the columns
+            for (int k = 0; k < CW; k += 4) {
+                const int j0 = c * kKC + kb + k;                 // < D16: constants are zero-padded
+                const float4 bb = lds4(cstE + eb + j0), w0 = lds4(cstE + L.e_wi + j0), w1 = lds4(cstE + L.e_wi + L.D16 + j0), w2 = lds4(cstE + L.e_wi + 2 * L.D16 + j0);
+                ee[k] = fmaf(w2.x, pi.ei2, fmaf(w1.x, pi.ei1, fmaf(w0.x, pi.ei0, ee[k] + bb.x)));
+                ee[k + 1] = fmaf(w2.y, pi.ei2, fmaf(w1.y, pi.ei1, fmaf(w0.y, pi.ei0, ee[k + 1] + bb.y)));
+                ee[k + 2] = fmaf(w2.z, pi.ei2, fmaf(w1.z, pi.ei1, fmaf(w0.z, pi.ei0, ee[k + 2] + bb.z)));
+                ee[k + 3] = fmaf(w2.w, pi.ei2, fmaf(w1.w, pi.ei1, fmaf(w0.w, pi.ei0, ee[k + 3] + bb.w)));
+            }
+        };
+        if (drain && have_E) {
+            // E leaves TMEM: every thread parks the columns it will consume in the MLP.0 rounds in its own rows of the CTA's E scratch
+            // (L2; written and read back by the same thread), then Zs | Zt take over the columns
 #pragma unroll 1
-                for (int c = 0; c < nG; ++c) {
-                    if (kb < min(kKC, L.g0.K8 - c * kKC)) {
-                        float ee[CW];
-                        tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, ee);
-                        finish_e(ee, c);
-                        float *ec = Es + c * kSlabFloats + (kb >> 2) * 512 + row * 4;
-#pragma unroll
-                        for (int g = 0; g < CW / 4; ++g) __stcg(reinterpret_cast<float4 *>(ec + g * 512), make_float4(ee[4 * g], ee[4 * g + 1], ee[4 * g + 2], ee[4 * g + 3]));
-                    }
-                }
-                tc::fence_before_sync();
-                __syncthreads();
-                tc::fence_after_sync();
-            }
             for (int c = 0; c < nG; ++c) {
-                const int kcols = min(kKC, L.g0.K8 - c * kKC);
-                if (stage_nodes) { tc::mbar_wait(bars + 2, n_phase); n_phase ^= 1; }          // chunk c of the rows has landed
-                if (proj && stage_edges) { tc::mbar_wait(bars + 3, e_phase); e_phase ^= 1; }  // and chunk c of the projected edge rows
-                float sv[CW], gv[CW], ee[CW];                       // endpoints' features and lin_event output + bias + edge-identity terms
-                auto load_g = [&]() {
+                if (kb < min(kKC, L.g0.K8 - c * kKC)) {
+                    float ee[CW];
+                    tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, ee);
+                    finish_e(ee, c);
+                    float *ec = Es + c * kSlabFloats + (kb >> 2) * 512 + row * 4;
 #pragma unroll
-                    for (int k = 0; k < CW; k += 4) {
-                        const int j = c * kKC + kb + k;
-                        float4 s4, g4;
-                        if (stage_nodes) {
-                            s4 = s_ok ? lds4(stage_piece(stg, row, kb + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            g4 = t_ok ? lds4(stage_piece(stg + kStageTable, row, kb + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        } else if (d_vec && j + 3 < D) {
-                            s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f); g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        } else {
-                            float w[8];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) { w[i] = (j + i < D && s_ok) ? __ldg(sf + j + i) : 0.f; w[4 + i] = (j + i < D && t_ok) ? __ldg(tf + j + i) : 0.f; }
-                            s4 = make_float4(w[0], w[1], w[2], w[3]); g4 = make_float4(w[4], w[5], w[6], w[7]);
-                        }
-                        sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
-                    }
-                    if (!have_E) {
-#pragma unroll
-                        for (int i = 0; i < CW; ++i) ee[i] = 0.f;
-                        finish_e(ee, c);
-                    } else if (drain) ldw(Es + c * kSlabFloats, ee);
-                    else { tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, ee); finish_e(ee, c); }
-                    if (proj && e_ok) {                             // + lin_event[:, :Ed] . edge features, precomputed per edge id
-#pragma unroll
-                        for (int k = 0; k < CW; k += 4) {
-                            const int j = c * kKC + kb + k;
-                            float4 p4;
-                            if (stage_edges) p4 = lds4(stage_piece(stg_e, row, kb + k));       // columns past D arrive as zeros (tensor-map bounds)
-                            else if (d_vec && j + 3 < D) p4 = ldg4(a.edge_feat + (int64_t)pi.e * D + j);
-                            else { const float *pr = a.edge_feat + (int64_t)pi.e * D; p4 = make_float4(j < D ? __ldg(pr + j) : 0.f, j + 1 < D ? __ldg(pr + j + 1) : 0.f, j + 2 < D ? __ldg(pr + j + 2) : 0.f, j + 3 < D ? __ldg(pr + j + 3) : 0.f); }
-                            ee[k] += p4.x; ee[k + 1] += p4.y; ee[k + 2] += p4.z; ee[k + 3] += p4.w;
-                        }
-                    }
-                };
-                auto put_z = [&](int o, bool second) {              // orientation o: p + relu(q + event)
-#pragma unroll
-                    for (int k = 0; k < CW; k += 4) {
-                        float z[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float p_ = o ? gv[k + i] : sv[k + i], q_ = o ? sv[k + i] : gv[k + i];
-                            z[i] = p_ + fmaxf(q_ + ee[k + i], 0.f);     // columns >= D: features, lin_event output and constants are all zero (padding)
-                        }
-                        af.put4(x, row, kb, k, make_float4(z[0], z[1], z[2], z[3]));
-                    }
-                    af.commit(x, lane_base, kb, second);
-                };
-                const bool last = c + 1 == nG;
-                auto next_nodes = [&]() {                           // the staged chunk has been consumed
-                    if (c + 1 < nG) { request_nodes(pi, c + 1); if (proj) request_edges(pi, c + 1); }
-                    else if (pos < 2) { request_nodes(pnext, 0); if (proj) request_edges(pnext, 0); }
-                };
-                int64_t noff; int nbytes;                           // weights after this chunk's last round
-                if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
-                else if (pos < 2 && nE_next > 0) { noff = EV.w; nbytes = min(cpr, nE_next) * bytes_e; }
-                else if (pos < 2) { noff = L.g0.w; nbytes = bytes_g; }         // edge-projection mode: position 2 starts with MLP.0
-                else { noff = L.sp.w; nbytes = bytes_sp; }
-                if (a.dual) {                                       // both orientations in one round: Zs from the first A buffer, Zt from the second
-                    if (kb < kcols) { load_g(); put_z(0, false); put_z(1, true); }
-                    tc_mma_round<TS>(x, H, kcols, colZ, c != 0, noff, nbytes, next_nodes, Dual{kDualM, 0, colZ + H, 0, 0});
-                } else {
-#pragma unroll 1
-                    for (int o = 0; o < 2; ++o) {
-                        if (kb < kcols) { load_g(); put_z(o, false); }
-                        if (o == 0) tc_mma_round<TS>(x, H, kcols, colZ, c != 0, L.g0.w + (int64_t)c * chunk_floats(L.g0), bytes_g);
-                        else tc_mma_round<TS>(x, H, kcols, colZ + H, c != 0, noff, nbytes, next_nodes);
-                    }
-                }
-            }
-            // ---- h_pos = relu(MLP.0 + bias): thread part p owns columns [4 CW p, 4 CW (p + 1)) of [Zs | Zt]
-            for (int c0 = (H2 / kParts) * prt; c0 < (H2 / kParts) * (prt + 1); c0 += 16) {
-                float v[16];
-                tc::tmem_ld16(tmem + lane_base + colZ + c0, v);
-                float *fc = Fs + (pos * nsl + (c0 >> 5)) * kSlabFloats + ((c0 & 31) >> 2) * 512 + row * 4;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 bb = lds4(cstE + L.e_g0b + (c0 & (H - 1)) + i);
-                    __stcg(reinterpret_cast<float4 *>(fc + (i >> 2) * 512),
-                           make_float4(fmaxf(v[i] + bb.x, 0.f), fmaxf(v[i + 1] + bb.y, 0.f), fmaxf(v[i + 2] + bb.z, 0.f), fmaxf(v[i + 3] + bb.w, 0.f)));
+                    for (int g = 0; g < CW / 4; ++g) __stcg(reinterpret_cast<float4 *>(ec + g * 512), make_float4(ee[4 * g], ee[4 * g + 1], ee[4 * g + 2], ee[4 * g + 3]));
                 }
             }
             tc::fence_before_sync();
-            __syncthreads();            // TMEM reads done before the next pass overwrites E / Z; the h slabs are visible to the CTA
+            __syncthreads();
             tc::fence_after_sync();
-            if (pos < 2) pcur = pnext;
         }
-        // =========================== motif rounds ===========================
-        // ---- [U | Y] = [S; P] h_2 ; r = d . h_2
-        float rp = 0.f;
-        {
-            float nxt[CW];
-            ldw(F2, nxt);
-            for (int c = 0; c < nchS; ++c) {
-                float cur[CW];
+        const bool with_u = SHARE && pos < 2;
+        float4 ua[4], ub[4];                                    // SHARE: U + cu of the epilogue's first two column groups
 #pragma unroll
-                for (int i = 0; i < CW; ++i) cur[i] = nxt[i];
-                if (c + 1 < nchS) ldw(F2 + (c + 1) * kSlabFloats, nxt);
+        for (int i = 0; i < 4; ++i) ua[i] = ub[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_u = [&](const int g, float4 *u) {
+            const int c0 = (H2 / kParts) * prt + g * 16;
+            const float *uc = Us + (c0 >> 5) * kSlabFloats + ((c0 & 31) >> 2) * 512 + row * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u[i] = ldcg4(uc + i * 512);
+        };
+        // one K chunk of MLP.0; in SHARE kernels the last one is a call site of its own (PRE) so that the preload is not live across the loop
+        auto g0_chunk = [&](const int c, const bool last, const bool PRE) __attribute__((always_inline)) {
+            const int kcols = min(kKC, L.g0.K8 - c * kKC);
+            if (stage_nodes) { tc::mbar_wait(bars + 2, n_phase); n_phase ^= 1; }          // chunk c of the rows has landed
+            if (proj && stage_edges) { tc::mbar_wait(bars + 3, e_phase); e_phase ^= 1; }  // and chunk c of the projected edge rows
+            float sv[CW], gv[CW], ee[CW];                       // endpoints' features and lin_event output + bias + edge-identity terms
+            auto load_g = [&]() {
 #pragma unroll
                 for (int k = 0; k < CW; k += 4) {
-                    const float4 dd = lds4(cstM + L.m_d + c * kKC + kb + k);
-                    rp = fmaf(dd.x, cur[k], rp); rp = fmaf(dd.y, cur[k + 1], rp); rp = fmaf(dd.z, cur[k + 2], rp); rp = fmaf(dd.w, cur[k + 3], rp);
-                    af.put4(x, row, kb, k, make_float4(cur[k], cur[k + 1], cur[k + 2], cur[k + 3]));
+                    const int j = c * kKC + kb + k;
+                    float4 s4, g4;
+                    if (stage_nodes) {
+                        s4 = s_ok ? lds4(stage_piece(stg, row, kb + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        g4 = t_ok ? lds4(stage_piece(stg + kStageTable, row, kb + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else if (d_vec && j + 3 < D) {
+                        s4 = s_ok ? ldg4(sf + j) : make_float4(0.f, 0.f, 0.f, 0.f); g4 = t_ok ? ldg4(tf + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else {
+                        float w[8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { w[i] = (j + i < D && s_ok) ? __ldg(sf + j + i) : 0.f; w[4 + i] = (j + i < D && t_ok) ? __ldg(tf + j + i) : 0.f; }
+                        s4 = make_float4(w[0], w[1], w[2], w[3]); g4 = make_float4(w[4], w[5], w[6], w[7]);
+                    }
+                    sv[k] = s4.x; sv[k + 1] = s4.y; sv[k + 2] = s4.z; sv[k + 3] = s4.w; gv[k] = g4.x; gv[k + 1] = g4.y; gv[k + 2] = g4.z; gv[k + 3] = g4.w;
                 }
-                af.commit(x, lane_base, kb);
-                const bool last = c + 1 == nchS;
-                tc_mma_round<TS>(x, 3 * H, kKC, colU, c != 0, last ? L.q.w : L.sp.w + (int64_t)(c + 1) * chunk_floats(L.sp), last ? (dq ? 2 : 1) * bytes_q : bytes_sp);
+                if (!have_E) {
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) ee[i] = 0.f;
+                    finish_e(ee, c);
+                } else if (drain) ldw(Es + c * kSlabFloats, ee);
+                else { tmem_ldw<CW>(tmem + lane_base + colE + c * kKC + kb, ee); finish_e(ee, c); }
+                if (proj && e_ok) {                             // + lin_event[:, :Ed] . edge features, precomputed per edge id
+#pragma unroll
+                    for (int k = 0; k < CW; k += 4) {
+                        const int j = c * kKC + kb + k;
+                        float4 p4;
+                        if (stage_edges) p4 = lds4(stage_piece(stg_e, row, kb + k));       // columns past D arrive as zeros (tensor-map bounds)
+                        else if (d_vec && j + 3 < D) p4 = ldg4(a.edge_feat + (int64_t)pi.e * D + j);
+                        else { const float *pr = a.edge_feat + (int64_t)pi.e * D; p4 = make_float4(j < D ? __ldg(pr + j) : 0.f, j + 1 < D ? __ldg(pr + j + 1) : 0.f, j + 2 < D ? __ldg(pr + j + 2) : 0.f, j + 3 < D ? __ldg(pr + j + 3) : 0.f); }
+                        ee[k] += p4.x; ee[k + 1] += p4.y; ee[k + 2] += p4.z; ee[k + 3] += p4.w;
+                    }
+                }
+            };
+            auto put_z = [&](int o, bool second) {              // orientation o: p + relu(q + event)
+#pragma unroll
+                for (int k = 0; k < CW; k += 4) {
+                    float z[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float p_ = o ? gv[k + i] : sv[k + i], q_ = o ? sv[k + i] : gv[k + i];
+                        z[i] = p_ + fmaxf(q_ + ee[k + i], 0.f);     // columns >= D: features, lin_event output and constants are all zero (padding)
+                    }
+                    af.put4(x, row, kb, k, make_float4(z[0], z[1], z[2], z[3]));
+                }
+                af.commit(x, lane_base, kb, second);
+            };
+            auto next_nodes = [&]() {                           // the staged chunk has been consumed
+                if (c + 1 < nG) { request_nodes(pi, c + 1); if (proj) request_edges(pi, c + 1); }
+                else if (has_next) { request_nodes(pnext, 0); if (proj) request_edges(pnext, 0); }
+#ifdef TM_SHARE_PRELOAD
+                if (PRE && with_u) { load_u(0, ua); load_u(1, ub); }       // in flight behind the MMAs
+#endif
+            };
+            int64_t noff; int nbytes;                           // weights after this chunk's last round
+            if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
+            else { noff = after_off; nbytes = after_bytes; }
+            if (a.dual) {                                       // both orientations in one round: Zs from the first A buffer, Zt from the second
+                if (kb < kcols) { load_g(); put_z(0, false); put_z(1, true); }
+                tc_mma_round<TS>(x, H, kcols, colZ, c != 0, noff, nbytes, next_nodes, Dual{kDualM, 0, colZ + H, 0, 0});
+            } else {
+#pragma unroll 1
+                for (int o = 0; o < 2; ++o) {
+                    if (kb < kcols) { load_g(); put_z(o, false); }
+                    if (o == 0) tc_mma_round<TS>(x, H, kcols, colZ, c != 0, L.g0.w + (int64_t)c * chunk_floats(L.g0), bytes_g);
+                    else tc_mma_round<TS>(x, H, kcols, colZ + H, c != 0, noff, nbytes, next_nodes);
+                }
+            }
+        };
+        if (SHARE) {
+#pragma unroll 1
+            for (int c = 0; c + 1 < nG; ++c) g0_chunk(c, false, false);
+            g0_chunk(nG - 1, true, true);
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < nG; ++c) g0_chunk(c, c + 1 == nG, false);
+        }
+        // ---- h_pos = relu(MLP.0 + bias): thread part p owns columns [4 CW p, 4 CW (p + 1)) of [Zs | Zt]
+        // (SHARE, positions 0 / 1: U + cu is known already, so s_pos = h_pos . (U + cu) is taken here and the motif rounds do not read h back for
+        // it.  U comes from the L2 scratch 32 columns at a time; groups beyond the first two exist at hid_dim 64 only -- one uniform branch
+        // around their loads and uses, so that the values stay in registers.)
+        float sk = 0.f;
+        auto ep_group = [&](const int g, const float4 *u) __attribute__((always_inline)) {
+            const int c0 = (H2 / kParts) * prt + g * 16;
+            float v[16];
+            tc::tmem_ld16(tmem + lane_base + colZ + c0, v);
+            float *fc = Fs + (pos * nsl + (c0 >> 5)) * kSlabFloats + ((c0 & 31) >> 2) * 512 + row * 4;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 bb = lds4(cstE + L.e_g0b + (c0 & (H - 1)) + i);
+                const float4 hv = make_float4(fmaxf(v[i] + bb.x, 0.f), fmaxf(v[i + 1] + bb.y, 0.f), fmaxf(v[i + 2] + bb.z, 0.f), fmaxf(v[i + 3] + bb.w, 0.f));
+                __stcg(reinterpret_cast<float4 *>(fc + (i >> 2) * 512), hv);
+                if (SHARE) {
+                    const float4 uu = u[i >> 2];
+                    sk = fmaf(hv.x, uu.x, sk); sk = fmaf(hv.y, uu.y, sk); sk = fmaf(hv.z, uu.z, sk); sk = fmaf(hv.w, uu.w, sk);
+                }
+            }
+        };
+        {
+#ifndef TM_SHARE_PRELOAD
+            if (with_u) { load_u(0, ua); load_u(1, ub); }
+#endif
+            ep_group(0, ua); ep_group(1, ub);
+            if (H2 / kParts > 32) {
+                if (with_u) { load_u(2, ua); load_u(3, ub); }
+                ep_group(2, ua); ep_group(3, ub);
             }
         }
-        // ---- s_k = h_k . (U + cu) + r  (:806-808 after folding)
-        float s0 = 0.f, s1 = 0.f;
+        if (SHARE) { if (pos == 0) sk0 = sk; else if (pos == 1) sk1 = sk; }
+        tc::fence_before_sync();
+        const int vote = __syncthreads_and(pred);   // TMEM reads done before the next rounds overwrite E / Z; the h slabs are visible to the CTA
+        tc::fence_after_sync();
+        return vote;
+    };
+
+    // =========================== [U | Y] = [S; P] h_2 ; returns this thread's share of r = d . h_2 ===========================
+    auto sp_rounds = [&](const int64_t after_off, const int after_bytes) -> float {
+        float rp = 0.f;
+        float nxt[CW];
+        ldw(F2, nxt);
+        for (int c = 0; c < nchS; ++c) {
+            float cur[CW];
+#pragma unroll
+            for (int i = 0; i < CW; ++i) cur[i] = nxt[i];
+            if (c + 1 < nchS) ldw(F2 + (c + 1) * kSlabFloats, nxt);
+#pragma unroll
+            for (int k = 0; k < CW; k += 4) {
+                const float4 dd = lds4(cstM + L.m_d + c * kKC + kb + k);
+                rp = fmaf(dd.x, cur[k], rp); rp = fmaf(dd.y, cur[k + 1], rp); rp = fmaf(dd.z, cur[k + 2], rp); rp = fmaf(dd.w, cur[k + 3], rp);
+                af.put4(x, row, kb, k, make_float4(cur[k], cur[k + 1], cur[k + 2], cur[k + 3]));
+            }
+            af.commit(x, lane_base, kb);
+            const bool last = c + 1 == nchS;
+            tc_mma_round<TS>(x, 3 * H, kKC, colU, c != 0, last ? after_off : L.sp.w + (int64_t)(c + 1) * chunk_floats(L.sp), last ? after_bytes : bytes_sp);
+        }
+        return rp;
+    };
+    // SHARE: U + cu and P h_2 + cy leave TMEM (every thread parks the columns it will read back itself: no barrier on the scratch)
+    // U: the columns whose h the thread finishes in the event passes' epilogues (part p: [2H / parts * p, ...)), at the addresses of the same
+    // (row, column) of the h_2 slabs; Y: the columns of the thread's A-fills (put_y).
+    auto spill_uy = [&]() {
 #pragma unroll 1
-        for (int c = 0; c < nchS; c += 2) {
+        for (int c0 = (H2 / kParts) * prt; c0 < (H2 / kParts) * (prt + 1); c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(tmem + lane_base + colU + c0, v);
+            float *dst = Us + (c0 >> 5) * kSlabFloats + ((c0 & 31) >> 2) * 512 + row * 4;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 bb = lds4(cstM + L.m_cu + c0 + i);
+                __stcg(reinterpret_cast<float4 *>(dst + (i >> 2) * 512), make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w));
+            }
+        }
+#pragma unroll 1
+        for (int c = 0; c < H / kKC; ++c) {
+            float v[CW];
+            tmem_ldw<CW>(tmem + lane_base + colY + c * kKC + kb, v);
+            float *dst = Ys + c * kSlabFloats + (kb >> 2) * 512 + row * 4;
+#pragma unroll
+            for (int g = 0; g < CW / 4; ++g) {
+                const float4 bb = lds4(cstM + L.m_cy + c * kKC + kb + 4 * g);
+                __stcg(reinterpret_cast<float4 *>(dst + g * 512), make_float4(v[4 * g] + bb.x, v[4 * g + 1] + bb.y, v[4 * g + 2] + bb.z, v[4 * g + 3] + bb.w));
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();                 // TMEM reads done before the next pass's MMAs overwrite U | Y
+        tc::fence_after_sync();
+    };
+
+    // =========================== motif rounds of one (sub-)tile ===========================
+    // scores -> temporal weights, softmax -> Q mix -> R -> MLP.3 -> MLP.5 + sigmoid.  (nxt_g, nxt_live, nxt_pos): the rows of the event pass
+    // that follows (has_next); their operands are loaded into pcur behind the Q rounds and their first staged chunks requested behind MLP.3.
+    auto motif_rounds = [&](const int64_t gm, const bool live, const float rp, const bool has_next, const int64_t nxt_g, const bool nxt_live, const int nxt_pos, const bool new_tile) {
+        // ---- s_k = h_k . (U + cu) + r  (:806-808 after folding)
+        float s0 = SHARE ? sk0 : 0.f, s1 = SHARE ? sk1 : 0.f;       // SHARE: taken by the event passes' epilogues
+#pragma unroll 1
+        for (int c = 0; c < (SHARE ? 0 : nchS); c += 2) {
             float p0[2][CW], p1[2][CW];
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) { ldw(F0 + (c + cc) * kSlabFloats, p0[cc]); ldw(F1 + (c + cc) * kSlabFloats, p1[cc]); }
@@ -788,7 +937,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         }
         const float mx = fmaxf(s0, s1), e0 = expf(s0 - mx), e1 = expf(s1 - mx);
         const float al0 = e0 / (e0 + e1), al1 = e1 / (e0 + e1);
-        // ---- Y += Q (alpha_0 h_0 + alpha_1 h_1)   (:841-843 after folding)
+        // ---- Y (+)= Q (alpha_0 h_0 + alpha_1 h_1)   (:841-843 after folding; SHARE: P h_2 + cy is added from the scratch afterwards)
         auto put_mix = [&](const float *c0, const float *c1, bool second) {
 #pragma unroll
             for (int k = 0; k < CW; k += 4)
@@ -796,18 +945,30 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                                                    fmaf(al0, c0[k + 2], al1 * c1[k + 2]), fmaf(al0, c0[k + 3], al1 * c1[k + 3])));
             af.commit(x, lane_base, kb, second);
         };
-        if (dq) {                                               // two K chunks per round
+        float yb[2][CW];                                        // SHARE: P h_2 + cy of this thread's put_y columns, in flight across the last Q round
+        auto load_yb = [&]() {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) ldw(Ys + min(c, H / kKC - 1) * kSlabFloats, yb[c]);     // hid_dim 32: one chunk (the copy in yb[1] is not read)
+        };
+        if (dq) {                                               // two K chunks per round; the last round is a call site of its own (see g0_chunk)
             x.a_col2 = colU;
-            for (int c = 0; c < nchS; c += 2) {
+            auto q_round = [&](const int c, const bool LAST) __attribute__((always_inline)) {
                 float m0[CW], m1[CW];
                 ldw(F0 + (c + 1) * kSlabFloats, m0); ldw(F1 + (c + 1) * kSlabFloats, m1);
                 put_mix(n0, n1, false);
-                if (c + 2 < nchS) { ldw(F0 + (c + 2) * kSlabFloats, n0); ldw(F1 + (c + 2) * kSlabFloats, n1); }
+                if (!LAST) { ldw(F0 + (c + 2) * kSlabFloats, n0); ldw(F1 + (c + 2) * kSlabFloats, n1); }
                 put_mix(m0, m1, true);
-                const bool last = c + 2 >= nchS;
-                tc_mma_round<TS>(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 2) * chunk_floats(L.q), last ? min(2, L.r.nch) * bytes_r : 2 * bytes_q, NoMid(),
+                tc_mma_round<TS>(x, H, kKC, colY, !SHARE || c != 0, LAST ? L.r.w : L.q.w + (int64_t)(c + 2) * chunk_floats(L.q), LAST ? min(2, L.r.nch) * bytes_r : 2 * bytes_q,
+#ifdef TM_SHARE_PRELOAD
+                                 [&]() { if (SHARE && LAST) load_yb(); },
+#else
+                                 NoMid(),
+#endif
                                  Dual{kDualK, kKC, 0, 0, 0});
-            }
+            };
+#pragma unroll 1
+            for (int c = 0; c + 2 < nchS; c += 2) q_round(c, false);
+            q_round(nchS - 2, true);
         } else {
             for (int c = 0; c < nchS; ++c) {
                 float c0[CW], c1[CW];
@@ -816,33 +977,32 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 if (c + 1 < nchS) { ldw(F0 + (c + 1) * kSlabFloats, n0); ldw(F1 + (c + 1) * kSlabFloats, n1); }
                 put_mix(c0, c1, false);
                 const bool last = c + 1 == nchS;
-                tc_mma_round<TS>(x, H, kKC, colY, true, last ? L.r.w : L.q.w + (int64_t)(c + 1) * chunk_floats(L.q), last ? bytes_r : bytes_q);
+                tc_mma_round<TS>(x, H, kKC, colY, !SHARE || c != 0, last ? L.r.w : L.q.w + (int64_t)(c + 1) * chunk_floats(L.q), last ? bytes_r : bytes_q);
             }
         }
         // The tile's h slabs have been consumed (their last readers were the Q rounds' fills, completed before the rounds' barriers):
         // drop the dirty L2 lines instead of letting them be written back to HBM.  A 128-byte line = 8 rows x one 16-byte piece, read
-        // only by this warp; the lane of row 8j discards it.
+        // only by this warp; the lane of row 8j discards it.  (SHARE: the slabs of position 2 hold U for the sub-tiles to come.)
         if (a.discard && (t & 7) == 0) {
 #pragma unroll 1
-            for (int sI = 0; sI < 3 * nsl; ++sI)
+            for (int sI = 0; sI < (SHARE ? 2 : 3) * nsl; ++sI)
 #pragma unroll
                 for (int g = 0; g < CW / 4; ++g)
                     asm volatile("discard.global.L2 [%0], 128;\n" :: "l"(Fs + sI * kSlabFloats + ((kb >> 2) + g) * 512 + row * 4) : "memory");
         }
-        // ---- M0 = R relu(Y + cy)   (attention.MLP.3 and MLP.0 folded); the next tile's first-pass indices start to arrive
-        const int64_t next_tile = s_next_tile;
-        const bool more = next_tile < n_tiles;
-        {
-            const int64_t gn = next_tile * 128 + row;
-            const bool lv = more && gn < n_m;
-            pcur = load_idx(lv ? gn : 0, lv, 0);
-        }
-        auto put_y = [&](int c, bool second) {
+        // ---- M0 = R relu(Y + cy)   (attention.MLP.3 and MLP.0 folded); the next pass's operands start to arrive
+        pcur = load_idx(nxt_live ? nxt_g : 0, nxt_live, nxt_pos);
+#ifndef TM_SHARE_PRELOAD
+        if (SHARE) load_yb();
+#endif
+        auto put_y = [&](const int c, bool second) {           // c: 0 or 1 (hid_dim <= 64)
             float z[CW];
             tmem_ldw<CW>(tmem + lane_base + colY + c * kKC + kb, z);
 #pragma unroll
             for (int k = 0; k < CW; k += 4) {
-                const float4 bb = lds4(cstM + L.m_cy + c * kKC + kb + k);
+                float4 bb;
+                if (SHARE) bb = c == 0 ? make_float4(yb[0][k], yb[0][k + 1], yb[0][k + 2], yb[0][k + 3]) : make_float4(yb[1][k], yb[1][k + 1], yb[1][k + 2], yb[1][k + 3]);
+                else bb = lds4(cstM + L.m_cy + c * kKC + kb + k);
                 const float4 yv = make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f));
                 af.put4(x, row, kb, k, yv);
                 if (a.y_out && live) *reinterpret_cast<float4 *>(a.y_out + gm * H + c * kKC + kb + k) = yv;
@@ -862,6 +1022,8 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             }
         }
         // ---- M1 = MLP.3 relu(M0 + cm[category])   (:199)
+        int64_t noff = 0; int nbytes = 0;                       // weights of the pass that follows
+        if (has_next) first_w(nxt_pos, noff, nbytes);
         const float *cmr = blob + L.cm + (int64_t)((L.if_cat && live && a.cat) ? min((int)a.cat[gm], 11) : 0) * L.M16;
         auto fill_m3 = [&](int c, uint32_t col) {
             const int kcols = min(kKC, L.m3.K8 - c * kKC);
@@ -882,8 +1044,11 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             fill_m3(0, x.a_col);
             if (nc > 1) fill_m3(1, x.a_col2);
             if (nc > 2) fill_m3(2, (uint32_t)colA3);
-            tc_mma_round<TS>(x, H, min(kKC, L.m3.K8), colM1, false, EV.w, more ? min(de ? 2 : 1, EV.nch) * bytes_e : 0,
-                             [&]() { if (more) { request_nodes(pcur, 0); request_edges(pcur, 0); } },
+            tc_mma_round<TS>(x, H, min(kKC, L.m3.K8), colM1, false, noff, nbytes,
+                             [&]() {
+                                 if (has_next) { request_nodes(pcur, 0); request_edges(pcur, 0); }
+                                 if (SHARE && new_tile) eq = nxt_live ? group_eq(nxt_g, pcur) : 1;       // the next tile's verdict, behind the MMAs
+                             },
                              Dual{nc > 1 ? kDualK : kSingle, nc > 1 ? min(kKC, L.m3.K8 - kKC) : 0, 0, nc > 2 ? L.m3.K8 - 2 * kKC : 0, colA3});
         } else
         for (int c = 0; c < L.m3.nch; ++c) {
@@ -891,8 +1056,11 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             fill_m3(c, x.a_col);
             const bool last = c + 1 == L.m3.nch;
             // the staging overlaps the weight buffer of the larger motif-round chunks; MLP.3's are small and R's MMAs have completed
-            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? EV.w : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? (more ? min(de ? 2 : 1, EV.nch) * bytes_e : 0) : bytes_m3,
-                             [&]() { if (c == 0 && more) { request_nodes(pcur, 0); request_edges(pcur, 0); } });
+            tc_mma_round<TS>(x, H, kcols, colM1, c != 0, last ? noff : L.m3.w + (int64_t)(c + 1) * chunk_floats(L.m3), last ? nbytes : bytes_m3,
+                             [&]() {
+                                 if (c == 0 && has_next) { request_nodes(pcur, 0); request_edges(pcur, 0); }
+                                 if (SHARE && new_tile && c == 0) eq = nxt_live ? group_eq(nxt_g, pcur) : 1;
+                             });
         }
         // ---- MLP.5 + sigmoid (:199-200)
         float z5 = 0.f;
@@ -904,7 +1072,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         }
         part[prt][0][row] = z5;         // the score reduction's reads of part[] ended before the Q rounds' barriers
         tc::fence_before_sync();
-        __syncthreads();                 // also: all TMEM reads of this tile done before the next tile's MMAs overwrite it
+        __syncthreads();                 // also: all TMEM reads of this (sub-)tile done before the next MMAs overwrite it
         tc::fence_after_sync();
         if (live && prt == 0) {
             float zz = cstM[L.m_b5];
@@ -912,14 +1080,84 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             for (int q = 0; q < kParts; ++q) zz += part[q][0][row];
             const float sc = 1.f / (1.f + expf(-zz));
             a.scores[gm] = sc;
-            for (int p = 0; p < a.n_peer; ++p) a.peer[p][gm] = sc;       // 128-byte warp stores over NVLink; visible to the peers at kernel end
+            for (int p = 0; p < a.n_peer; ++p) a.peer[p][gm] = sc;       // warp stores over NVLink; visible to the peers at kernel end
+        }
+        // the next write to part[] comes after the barriers of the next rounds
+    };
+
+    float rp = 0.f;
+    for (int64_t tile = blockIdx.x; tile < n_tiles;) {
+        const int64_t gr = tile * 128 + row;        // tile row: a motif, or (SHARE) a first-hop slot with its sh consecutive motifs
+        const bool live = gr < n_rows;
+        // the CTA's next tile (dynamic: SMs that run a single CTA, or faster ones, take more tiles); read after the event passes' barriers
+        if (t == 0) s_next_tile = (long long)gridDim.x + (long long)atomicAdd(a.tile_counter, 1ull);
+        bool shared = false;
+        int64_t next_tile = 0;
+#pragma unroll 1
+        for (int j = 0; j < sh; ++j) {
+            const int64_t gm = live ? gr * sh + j : 0;
+            // passes of this (sub-)tile: positions 0, 1, 2, then the [S; P] rounds -- or (SHARE) position 2 and the [S; P] rounds, once per slot
+            // where the vote allows, then positions 0 and 1
+#pragma unroll 1
+            for (int k = (SHARE && j > 0 && shared) ? 1 : 0; k < 3; ++k) {
+                const int pos = SHARE ? (k == 0 ? 2 : k - 1) : k;
+                if (k < 2) pnext = load_idx(gm, live, SHARE ? k : k + 1);
+                int64_t aoff; int abytes;
+                if (SHARE ? k == 0 : k == 2) { aoff = L.sp.w; abytes = bytes_sp; }
+                else if (SHARE && k == 2) { aoff = L.q.w; abytes = (dq ? 2 : 1) * bytes_q; }
+                else first_w(SHARE ? 1 : k + 1, aoff, abytes);
+                // SHARE, k == 0: position 0's rows are requested behind the pass's last round where the staging lies clear of the [S; P] weights
+                const int vote = event_pass(pos, pcur, live, SHARE ? (k == 1 || (k == 0 && a.sp_stage_safe)) : k < 2, aoff, abytes, (SHARE && j == 0 && k == 0) ? eq : 1);
+                if (SHARE && k == 0) {
+                    if (j == 0) shared = vote != 0;
+                    first_w(0, aoff, abytes);
+                    rp = sp_rounds(aoff, abytes);
+                    pcur = pnext;
+                    if (!a.sp_stage_safe) { request_nodes(pcur, 0); request_edges(pcur, 0); }       // otherwise nothing was in flight during the [S; P] rounds
+                    spill_uy();
+                } else if (k < 2) pcur = pnext;
+            }
+            if (!SHARE) rp = sp_rounds(L.q.w, (dq ? 2 : 1) * bytes_q);
+            bool has_next, nxt_live; int64_t nxt_g; int nxt_pos;
+            const bool new_tile = !(SHARE && j + 1 < sh);
+            if (!new_tile) { has_next = true; nxt_live = live; nxt_g = gr * sh + j + 1; nxt_pos = shared ? 0 : 2; }
+            else {
+                next_tile = s_next_tile;
+                has_next = next_tile < n_tiles;
+                const int64_t rn = next_tile * 128 + row;
+                nxt_live = has_next && rn < n_rows; nxt_g = rn * sh; nxt_pos = kFirstPos;
+            }
+            motif_rounds(gm, live, rp, has_next, nxt_g, nxt_live, nxt_pos, new_tile);
         }
         tile = next_tile;
-        // the next write to part[] comes after the barriers of the next tile's rounds
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, a.tmem_cols);
+#undef H2
+#undef nG
+#undef nchS
+#undef colE
+#undef colY
+#undef colM0
+#undef colM1
+#undef colA3
+#undef nsl
+#undef dq
+#undef de
+#undef m3one
+#undef cpr
+#undef ed_vec
+#undef d_vec
+#undef jofs
+#undef bytes_e
+#undef bytes_g
+#undef bytes_sp
+#undef bytes_q
+#undef bytes_r
+#undef bytes_m3
+#undef n_rows
+#undef n_tiles
 }
 
 // Motifs whose h rows the workspace holds: two resident CTAs per SM x 128 motifs (tm_encoder_workspace_floats)
@@ -1055,8 +1293,10 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     const size_t need = a_bytes + (size_t)bb + (size_t)(L.n_cstE + L.n_cstM) * 4 + 152 * 8;
     if (need > 220 * 1024) { set_error("tc_encode_score: feature dims too large for one weight chunk in shared memory"); return TM_ERR_UNSUPPORTED; }
     using ScoreK = void (*)(const TcLayout, const float *, const TcArgs, const CUtensorMap, const CUtensorMap);
-    static const ScoreK kern[5] = {score_tc_kernel<8, false, false>, score_tc_kernel<16, false, false>, score_tc_kernel<8, true, false>, score_tc_kernel<16, true, false>,
-                                   score_tc_kernel<16, true, true>};
+    constexpr int kKernels = 7;
+    static const ScoreK kern[kKernels] = {score_tc_kernel<8, false, false, false>, score_tc_kernel<16, false, false, false>, score_tc_kernel<8, true, false, false>,
+                                          score_tc_kernel<16, true, false, false>, score_tc_kernel<16, true, true, false>,
+                                          score_tc_kernel<16, true, false, true>, score_tc_kernel<16, true, true, true>};      // [5], [6]: walk groups (SHARE)
     static bool attr_set[64] = {false};
     if (!attr_set[device]) {
         for (ScoreK k : kern) {
@@ -1069,10 +1309,13 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const char *cw_env = getenv("TEMPME_TC_CW");                 // columns per thread per K chunk: 16 (256 threads, default) or 8 (512 threads)
     const int cw = cw_env && atoi(cw_env) == 8 && H == 64 && !drain ? 8 : 16;
-    const int kv = drain ? 4 : (cw == 16) + 2 * ts;         // drain mode has its own instantiation (CW = 16, A operand in TMEM)
-    static size_t static_smem[5] = {0, 0, 0, 0, 0};
+    // walk groups: d.walk_fanout consecutive walks share their first-hop event (verified per tile by the kernel); needs the default
+    // operand path (A in TMEM, 256 threads) and whole groups
+    const int share = (d.walk_fanout >= 2 && d.walk_fanout <= 64 && ts && dual && cw == 16 && W % d.walk_fanout == 0 && !getenv("TEMPME_TC_NO_SHARE")) ? d.walk_fanout : 1;
+    const int kv = share > 1 ? (drain ? 6 : 5) : drain ? 4 : (cw == 16) + 2 * ts;         // drain mode has its own instantiations (CW = 16, A operand in TMEM)
+    static size_t static_smem[kKernels] = {0};
     if (!static_smem[0])
-        for (int v = 0; v < 5; ++v) { cudaFuncAttributes fa; TM_CUDA(cudaFuncGetAttributes(&fa, kern[v])); static_smem[v] = fa.sharedSizeBytes; }
+        for (int v = 0; v < kKernels; ++v) { cudaFuncAttributes fa; TM_CUDA(cudaFuncGetAttributes(&fa, kern[v])); static_smem[v] = fa.sharedSizeBytes; }
     // resident CTAs per SM: TMEM columns and shared memory (registers: __launch_bounds__(threads, 2))
     const int ctas = std::max(1, std::min<int>(2, std::min<int>(512 / cols, (int)((228 * 1024) / (need + 1024 + static_smem[kv])))));
     // dynamic shared memory padded so that no more than `ctas` CTAs fit an SM (TMEM columns are not part of the occupancy
@@ -1101,18 +1344,69 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
         TM_CUDA(cudaMemsetAsync(dbg_buf, 0, 128 * 5 * sizeof(long long), st));
         a.dbg = dbg_buf;
     }
-    const int64_t tiles = (a.n_motifs + 127) / 128, cap = (int64_t)sms * ctas;
+    a.share = share;
+    {
+        TcDer &k = a.k;
+        const bool dq_ = dual, de_ = dual_e;
+        k.H2 = 2 * H; k.nG = L.g0.nch; k.nchS = L.sp.nch;
+        k.colE = drain ? 0 : (L.g0.nch == 1 && L.D16 <= H) ? H : 2 * H;
+        k.colY = 2 * H; k.colM0 = dq_ ? std::max(H, 2 * kKC) : 0; k.colM1 = m3one ? k.colM0 : dq_ ? 0 : 2 * H; k.colA3 = k.colM0 + L.M16;
+        k.nsl = 2 * H / kKC; k.dq = dq_; k.de = de_; k.m3one = m3one; k.cpr = de_ ? 2 : 1;
+        k.ed_vec = (L.Ed & 3) == 0; k.d_vec = (L.D & 3) == 0; k.jofs = proj ? L.Ed : 0;
+        k.ev_K8 = EV.K8; k.ev_nch = EV.nch; k.ev_w = EV.w; k.ev_chunk = chunk_floats(EV);
+        k.ne01 = proj ? EV.nch : L.evt.nch; k.ne2 = proj ? 0 : L.nch_edge;
+        k.bytes_e = (int)chunk_floats(EV) * 4; k.bytes_g = (int)chunk_floats(L.g0) * 4; k.bytes_sp = (int)chunk_floats(L.sp) * 4;
+        k.bytes_q = (int)chunk_floats(L.q) * 4; k.bytes_r = (int)chunk_floats(L.r) * 4; k.bytes_m3 = (int)chunk_floats(L.m3) * 4;
+        auto fw = [&](int ne, int64_t &off, int &bytes) { if (ne > 0) { off = EV.w; bytes = std::min(k.cpr, ne) * k.bytes_e; } else { off = L.g0.w; bytes = k.bytes_g; } };
+        fw(k.ne01, k.fw01_off, k.fw01_bytes); fw(k.ne2, k.fw2_off, k.fw2_bytes);
+        k.n_rows = a.n_motifs / share; k.n_tiles = (k.n_rows + 127) / 128;
+    }
+    a.sp_stage_safe = stage_rel >= chunk_floats(L.sp) * 4 ? 1 : 0;
+    const int64_t tiles = (a.n_motifs / share + 127) / 128, cap = (int64_t)sms * ctas;
     const unsigned grid = (unsigned)std::min(tiles, cap);
     a.tile_counter = reinterpret_cast<unsigned long long *>(F + (int64_t)grid * 3 * (2 * H / kKC) * kSlabFloats);          // behind the h scratch (the workspace holds twice as much)
-    a.Es = drain ? F + 2 * tc_slab_motifs(device) * 3 * 2 * H + 64 : nullptr;                                             // behind both (tm_encoder_workspace_floats)
+    a.Ys = F + (int64_t)grid * 3 * (2 * H / kKC) * kSlabFloats + 64;                                                      // SHARE: H / 32 slabs per CTA, a sixth of the h scratch
+    a.Es = drain ? a.Ys + (int64_t)grid * (H / kKC) * kSlabFloats : nullptr;                                              // drain mode: nG slabs per CTA behind both
+    const size_t scratch_bytes = (size_t)((drain ? a.Es + (int64_t)grid * L.g0.nch * kSlabFloats : a.Ys + (int64_t)grid * (H / kKC) * kSlabFloats) - F) * sizeof(float);
     TM_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), st));
-    if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] score kernel: %u CTAs (%d per SM), smem %zu B (needs %zu), %u TMEM columns, %lld tiles%s\n", grid, ctas, smem, need, cols, (long long)tiles, drain ? (proj ? ", E drained through L2, projected edge table" : ", E drained through L2") : (proj ? ", projected edge table" : ""));
+    if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] score kernel: %u CTAs (%d per SM), smem %zu B (needs %zu), %u TMEM columns, %lld tiles%s%s\n", grid, ctas, smem, need, cols, (long long)tiles, share > 1 ? " of walk groups" : "", drain ? (proj ? ", E drained through L2, projected edge table" : ", E drained through L2") : (proj ? ", projected edge table" : ""));
     cudaEvent_t *pe = nullptr;
     if (g_prof && g_prof_used + 2 <= g_prof_ev.size()) {        // pool is created by tm_encoder_profile(1); when exhausted, stop recording
         pe = &g_prof_ev[g_prof_used]; g_prof_used += 2;
         cudaEventRecord(pe[0], st);
     }
-    kern[kv]<<<grid, 128 * (kKC / cw), smem, st>>>(L, d_blob_tc, a, tm_node, tm_edge);
+    // The CTAs' scratch (h slabs, U / Y, drained E) is written and read back within microseconds, but streams of feature rows and walk tensors
+    // pass through L2 in between: TEMPME_TC_L2_PERSIST_MB=<n> sets n MB of L2 aside for persisting lines and marks the scratch as such
+    // (access policy window on this launch), so that its reads hit and its dirty lines are not written back to HBM.
+    static int persist_mb[64];
+    static bool persist_init[64] = {false};
+    if (!persist_init[device]) {
+        const char *pm = getenv("TEMPME_TC_L2_PERSIST_MB");
+        int want = pm ? atoi(pm) : 0, max_persist = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        want = std::min(want, max_persist >> 20);
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want << 20) != cudaSuccess) { cudaGetLastError(); want = 0; }
+        persist_mb[device] = want;
+        persist_init[device] = true;
+        if (getenv("TEMPME_TC_DEBUG")) fprintf(stderr, "[tc] L2 set-aside %d MB (device maximum %d MB)\n", want, max_persist >> 20);
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128 * (kKC / cw)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (persist_mb[device] > 0) {
+        int max_win = 0;
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        const size_t win = std::min(scratch_bytes, (size_t)max_win);
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = F;
+        attr[0].val.accessPolicyWindow.num_bytes = win;
+        attr[0].val.accessPolicyWindow.hitRatio = std::min(1.0f, (float)((double)((size_t)persist_mb[device] << 20) / (double)std::max<size_t>(win, 1)));
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    TM_CUDA(cudaLaunchKernelEx(&cfg, kern[kv], L, d_blob_tc, a, tm_node, tm_edge));
     TM_LAUNCH_CHECK();
     if (pe) cudaEventRecord(pe[1], st);
     if (tim_env) {

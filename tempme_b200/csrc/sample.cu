@@ -459,6 +459,15 @@ static int walks_impl(const tm_graph *g, int64_t B, int n, int N2, const int32_t
     const size_t stage_bytes = (size_t)256 * N2 * 48;
     const bool staged = stage_bytes <= 48 * 1024 && !getenv("TEMPME_WALKS_NO_STAGING") && ((uintptr_t)d_o_nodes % 16 == 0) && ((uintptr_t)d_o_eidx % 16 == 0) &&
                         ((uintptr_t)d_o_t % 16 == 0);
+    // 48 KB of staging (N2 = 4) plus the kernel's static shared memory is above the default 48 KB limit: opt in once per device
+    static bool attr_set[64] = {false};
+    if (g->device >= 0 && g->device < 64 && !attr_set[g->device]) {
+        TM_CUDA(cudaFuncSetAttribute(sample_walks_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        TM_CUDA(cudaFuncSetAttribute(sample_walks_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        TM_CUDA(cudaFuncSetAttribute(sample_walks_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        TM_CUDA(cudaFuncSetAttribute(sample_walks_kernel<TM_MAX_STEP2_FANOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set[g->device] = true;
+    }
 #define TM_WALKS(CAP) sample_walks_kernel<CAP><<<(unsigned)blocks, 256, staged ? stage_bytes : 0, (cudaStream_t)stream>>>(    \
         g->v, B, n, N2, d_root, d_h1_node, d_h1_eidx, d_h1_ts, seed, row_offset, d_inject2, d_inject3, d_pre2, d_pre2_t,     \
         d_o_nodes, d_o_eidx, d_o_t, d_o_anony, d_o_cat, d_hist_null, d_hist_prep, d_scanned, staged ? 1 : 0)

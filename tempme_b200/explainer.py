@@ -137,6 +137,7 @@ class TempME(nn.Module):
         self.edge_projection = os.environ.get("TEMPME_EDGE_PROJECTION", "1") != "0" and self.edge_dim <= 256
         self._proj = None
         self._proj_key = None
+        self._desc_fanout = {}
         self.projection_ms = None
         self._blob = None
         self._blob_key = None
@@ -219,16 +220,43 @@ class TempME(nn.Module):
         return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(self.device, non_blocking=True)
 
     # ------------------------------------------------------------------ forward (explainer.py:174-201)
-    def score_device(self, nodes, eidx, t, cat, cut_time, edge_identity, group=None, out=None, peer_ptrs=None):
+    def _with_fanout(self, desc, fanout):
+        """The descriptor with the walk-layout hint set (tm_encoder_desc.walk_fanout)."""
+        fanout = int(fanout or 0)
+        if fanout < 2:
+            return desc
+        key = (desc.edge_projected, fanout)
+        if key not in self._desc_fanout:
+            self._desc_fanout[key] = EncoderDesc(desc.node_dim, desc.edge_dim, desc.hid_dim, desc.use_temporal, desc.if_cat, desc.edge_projected, fanout)
+        return self._desc_fanout[key]
+
+    @staticmethod
+    def detect_fanout(eidx, nodes):
+        """Largest c <= 10 dividing W such that every c consecutive walks have the same event next to the root -- find_k_walks' layout
+        w = i1 * N2 + j (utils/graph.py:290-300) gives c = N2.  Only a hint: the scorer verifies it tile by tile."""
+        B, W = eidx.shape[0], eidx.shape[1]
+        if B == 0:
+            return 1
+        key = torch.stack([eidx[:, :, 2], nodes[:, :, 4], nodes[:, :, 5]], dim=-1)
+        for c in range(min(10, W), 1, -1):
+            if W % c == 0:
+                g = key.view(B, W // c, c, 3)
+                if bool((g == g[:, :, :1]).all()):
+                    return c
+        return 1
+
+    def score_device(self, nodes, eidx, t, cat, cut_time, edge_identity, group=None, out=None, peer_ptrs=None, fanout=None):
         """All arguments CUDA tensors: nodes i32 [B,W,6], eidx i32 [B,W,3], t f32 [B,W,3], cat u8 [B,W],
         cut_time f32 [B], edge_identity f32 [B,W,3,3] -> scores f32 [B,W].  out: preallocated [B,W] result (e.g. this rank's segment of a
         gathered buffer); peer_ptrs: device addresses of the same segment on up to 7 peer GPUs -- the kernel stores every score there too
-        (tm_encode_score_gather; tempme_b200.dist.ScoreExchange)."""
+        (tm_encode_score_gather; tempme_b200.dist.ScoreExchange).  fanout: N2 when the walks come from find_k_walks (w = i1 * N2 + j): the
+        event next to the root is then evaluated once per N2 walks (verified by the kernel; the scores do not depend on the hint)."""
         B, W = nodes.shape[0], nodes.shape[1]
         group = int(group or self.batch_group or max(B, 1))
         blob = self.packed_weights()
         nf, ef = self._tables()
         desc, ef = self._edge_table(blob, ef)
+        desc = self._with_fanout(desc, fanout)
         self._workspace(B, W, group)
         if out is None:
             scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
@@ -278,7 +306,7 @@ class TempME(nn.Module):
             return _tr.score_autograd(self, nodes, eidx, t, cat, cut, eid)
         if self._dropout_active():                                        # train() under no_grad: dropout is part of the value
             return _tr.scores_layerwise(self, nodes.long(), eidx.long(), t, cat, cut, eid)
-        return self.score_device(nodes, eidx, t, cat, cut, eid).view(B, W, 1)
+        return self.score_device(nodes, eidx, t, cat, cut, eid, fanout=self.detect_fanout(eidx, nodes)).view(B, W, 1)
 
     # ------------------------------------------------------------------ enhance path (explainer.py:203-306), eval mode
     def _walk_tensors(self, walks, cut_time_l, edge_identify):
@@ -315,6 +343,7 @@ class TempME(nn.Module):
         blob = self.packed_weights()
         nf, ef = self._tables()
         desc, ef = self._edge_table(blob, ef)
+        desc = self._with_fanout(desc, self.detect_fanout(eidx, nodes))
         self._workspace(B, W, group)
         scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
         y = torch.empty((B, W, self.hid_dim), dtype=torch.float32, device=self.device)

@@ -137,7 +137,7 @@ class MotifPipeline:
             eid = edge_identity_device(eidx, out=ws["eid"] if full is None else full[4][sl])
             mark("edge_identity")
             pp = [int(p) + c0 * W * 4 for p in peer_ptrs] if peer_ptrs else None
-            self.explainer.score_device(nodes, eidx, t, cat, cut32[sl], eid, group=max(g, 1), out=out2[sl], peer_ptrs=pp)
+            self.explainer.score_device(nodes, eidx, t, cat, cut32[sl], eid, group=max(g, 1), out=out2[sl], peer_ptrs=pp, fanout=N2)
             mark("encode")
         return (out2, full) if want_walks else out2
 
@@ -156,7 +156,7 @@ class MotifPipeline:
                                                        row_offset=row_offset, want_anony=False, want_cat=True,
                                                        hist_null=self.hist_null, hist_prep=self.hist_prep, scanned=self.scanned)
         eid = edge_identity_device(eidx)
-        scores = self.explainer.score_device(nodes, eidx, t, cat, cut64.to(torch.float32), eid, group=max(g, 1))
+        scores = self.explainer.score_device(nodes, eidx, t, cat, cut64.to(torch.float32), eid, group=max(g, 1), fanout=N2)
         imp0, imp1 = self.explainer.edge_importance_device(scores, eidx, t, sub[0][0].view(R, n), sub[1][0].view(R, n),
                                                            sub[0][1].view(R, n * n), sub[1][1].view(R, n * n))
         return scores, imp0, imp1, sub

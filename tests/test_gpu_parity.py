@@ -745,3 +745,76 @@ def test_edge_projection_mode_equals_plain_mode(tm, D, Ed):
     d = m.score_device(nodes, we, wt, cat, cut, eid, group=100).clone()
     assert float((c - a).abs().max()) > 1e-4
     np.testing.assert_allclose(c.cpu().numpy(), d.cpu().numpy(), rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("D,Ed,hid,proj,N2", [(32, 32, 64, True, 3), (32, 32, 64, False, 3), (172, 172, 64, True, 5), (172, 172, 64, False, 2),
+                                              (100, 7, 32, True, 3), (32, 32, 32, True, 4), (64, 32, 64, True, 3)])
+def test_walk_group_mode_equals_plain_mode_and_oracle(tm, orc, D, Ed, hid, proj, N2):
+    """tm_encoder_desc.walk_fanout: the N2 walks of a first-hop slot share their event next to the root, evaluated once per group.  Same
+    scores as the per-walk evaluation (fp32 round-off of one reassociated sum) and as the oracle; the hint is only a hint: with the
+    walks of every root shuffled (groups no longer uniform, or only by chance) every tile falls back and the scores do not change."""
+    from oracle import encoder as orc_enc
+    rng = np.random.default_rng(D + Ed + N2)
+    src, dst, eidx, ts = synth_graph(23, 300, 20000, 10 ** 6)
+    f = tm.NeighborFinder.from_events(300, src, dst, eidx, ts)
+    q = np.arange(15000, 15450)                       # 450 roots x 10 x N2 walks: the last tile of slots is ragged
+    n = 10
+    sub = f.find_k_hop_device(1, src[q], ts[q], n, eidx[q], seed=3)
+    nodes, we, wt, anony, cat = f.find_k_walks_device(n, src[q], N2, sub, seed=4)
+    eid = tm.edge_identity_device(we)
+    nfeat = rng.standard_normal((300, D)).astype(np.float32); efeat = rng.standard_normal((20001, Ed)).astype(np.float32)
+    nfeat[0] = 0; efeat[0] = 0
+    torch.manual_seed(2)
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, hid, device="cuda", null_model={}).cuda().eval()
+    m.edge_projection = proj
+    cut = torch.as_tensor(ts[q].astype(np.float32)).cuda()
+    assert m.detect_fanout(we, nodes) % N2 == 0
+    plain = m.score_device(nodes, we, wt, cat, cut, eid, group=100).clone()
+    grouped = m.score_device(nodes, we, wt, cat, cut, eid, group=100, fanout=N2).clone()
+    np.testing.assert_allclose(grouped.cpu().numpy(), plain.cpu().numpy(), rtol=2e-6, atol=0)
+    p = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    for s in range(0, len(q), 100):
+        sl = slice(s, s + 100)
+        walks = (nodes[sl].cpu().numpy(), we[sl].cpu().numpy(), wt[sl].cpu().numpy(), cat[sl].cpu().numpy(), None)
+        ref = orc_enc.forward(p, nfeat, efeat, walks, ts[q][sl], eid[sl].cpu().numpy())
+        np.testing.assert_allclose(grouped[sl].cpu().numpy(), ref[..., 0], rtol=1e-5, atol=0)
+    # a wrong hint: shuffle the walks of every root (the same permutation for all per-walk tensors)
+    W = n * N2
+    perm = torch.stack([torch.randperm(W, generator=torch.Generator().manual_seed(i)) for i in range(len(q))]).cuda()
+    take = lambda x: torch.gather(x, 1, perm.view(len(q), W, *([1] * (x.dim() - 2))).expand_as(x)).contiguous()
+    nodes2, we2, wt2, cat2, eid2 = take(nodes), take(we), take(wt), take(cat), take(eid)
+    plain2 = m.score_device(nodes2, we2, wt2, cat2, cut, eid2, group=100).clone()
+    hinted2 = m.score_device(nodes2, we2, wt2, cat2, cut, eid2, group=100, fanout=N2).clone()
+    np.testing.assert_allclose(plain2.cpu().numpy(), take(plain).cpu().numpy(), rtol=2e-6, atol=0)
+    assert torch.equal(hinted2, plain2) or np.allclose(hinted2.cpu().numpy(), plain2.cpu().numpy(), rtol=2e-6, atol=0)
+    # half of the roots shuffled: shared and repeated tiles in one launch
+    half = len(q) // 2
+    mix = lambda a, b: torch.cat([a[:half], b[half:]]).contiguous()
+    mixed = m.score_device(mix(nodes, nodes2), mix(we, we2), mix(wt, wt2), mix(cat, cat2), cut, mix(eid, eid2), group=100, fanout=N2)
+    np.testing.assert_allclose(mixed.cpu().numpy(), mix(plain, plain2).cpu().numpy(), rtol=2e-6, atol=0)
+    # the enhance path's hidden-vector output goes through the same kernel
+    emb_a = m.enhance_predict_walks((nodes, we, wt, cat, None), ts[q], eid)
+    m._with_fanout = lambda desc, fanout: desc           # per-walk evaluation
+    emb_b = m.enhance_predict_walks((nodes, we, wt, cat, None), ts[q], eid)
+    scale = float(emb_b.abs().max())
+    assert float((emb_a - emb_b).abs().max()) <= 2e-6 * scale
+
+
+def test_walk_group_mode_many_tiles_per_cta(tm):
+    """More tiles of walk groups than resident CTAs (the next tile's first pass is prefetched behind the last sub-tile's rounds)."""
+    rng = np.random.default_rng(5)
+    src, dst, eidx, ts = synth_graph(29, 500, 40000, 10 ** 6)
+    f = tm.NeighborFinder.from_events(500, src, dst, eidx, ts)
+    q = rng.integers(20000, 40000, 4000)
+    q.sort()
+    n, N2 = 20, 3
+    sub = f.find_k_hop_device(1, src[q], ts[q], n, eidx[q], seed=3)
+    nodes, we, wt, anony, cat = f.find_k_walks_device(n, src[q], N2, sub, seed=4)      # 240,000 motifs = 80,000 slots = 625 tiles
+    eid = tm.edge_identity_device(we)
+    nfeat = rng.standard_normal((500, 32)).astype(np.float32); efeat = rng.standard_normal((40001, 32)).astype(np.float32)
+    torch.manual_seed(3)
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, 64, device="cuda", null_model={}).cuda().eval()
+    cut = torch.as_tensor(ts[q].astype(np.float32)).cuda()
+    plain = m.score_device(nodes, we, wt, cat, cut, eid, group=100).clone()
+    grouped = m.score_device(nodes, we, wt, cat, cut, eid, group=100, fanout=N2).clone()
+    np.testing.assert_allclose(grouped.cpu().numpy(), plain.cpu().numpy(), rtol=2e-6, atol=0)
