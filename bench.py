@@ -64,13 +64,15 @@ def encoder_flops(D, Ed, H=HID):
     return 3 * 2 * ev * D + 6 * 2 * (D * H + H * H) + 3 * 2 * (2 * H) ** 2 + 2 * (2 * H * H + H * H) + 2 * (M * M + M * H + H)
 
 
-def executed_flops(D, Ed, H=HID, projected=True):
+def executed_flops(D, Ed, H=HID, projected=True, fanout=1):
     """FLOPs per motif of the chain the kernel executes on the tensor cores: lin_event over [edge | TimeEncode] at positions
     0 / 1 and over the edge columns at position 2 (dt = 0: the TimeEncode part is a bias) -- or, in edge-projection mode, over the TimeEncode
-    columns of positions 0 / 1 only; MLP.0 for both orientations of the three events; the host-folded motif rounds."""
+    columns of positions 0 / 1 only; MLP.0 for both orientations of the three events; the host-folded motif rounds.  Walk groups (fanout = N2
+    walks per first-hop slot): the position-2 event and the [S; P] product once per slot."""
     M = H + 12
-    lin_event = 4 * D * D if projected else 2 * D * (3 * Ed + 2 * D)
-    return lin_event + 6 * 2 * D * H + 2 * (2 * H * 3 * H + 2 * H * H + H * M + M * H + H)
+    once = 1.0 / max(int(fanout), 1)
+    lin_event = 4 * D * D if projected else 2 * D * (2 * (Ed + D) + Ed * once)
+    return lin_event + (4 + 2 * once) * 2 * D * H + 2 * (2 * H * 3 * H * once + 2 * H * H + H * M + M * H + H)
 
 
 # events per GPU per step: sized so that the default --steps 20 run keeps the GPU busy for >= 1 s (sustained clocks)
@@ -560,7 +562,7 @@ def run_ours(args):
     }
     flops = {"encode": M * float(encoder_flops(D, Ed)), "score_tc": M * float(encoder_flops(D, Ed))}
     pk = peaks()
-    ex_flops = executed_flops(D, Ed, projected=bool(wl.model.edge_projection))
+    ex_flops = executed_flops(D, Ed, projected=bool(wl.model.edge_projection), fanout=1 if os.environ.get("TEMPME_TC_NO_SHARE") else N2)
     top = max(stage_ms, key=stage_ms.get)
     launches_top = args.steps * n_chunks
     dur_s = stage_ms[top] / launches_top * 1e-3                    # average duration of ONE launch of the dominant kernel
@@ -583,7 +585,7 @@ def run_ours(args):
                     executed_flops_per_motif=ex_flops, algorithmic_flops_per_motif=encoder_flops(D, Ed),
                     note="achieved = algorithmic FLOPs of the reference formulation per launch / the kernel's average launch duration; peak = measured "
                          "bf16 dense.  The scorer needs fp32 accuracy (rtol 1e-5): every product is 3 TF32 MMAs at half the bf16 rate, so the ceiling per "
-                         "executed FLOP is peak/6; the kernel executes the host-folded chain, with lin_event's edge columns applied once per edge id (executed_flops_per_motif)")
+                         "executed FLOP is peak/6; the kernel executes the host-folded chain, with lin_event's edge columns applied once per edge id and the event next to the root once per first-hop slot (executed_flops_per_motif)")
     else:
         ach = alg_bytes[top] / n_chunks / dur_s / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic}

@@ -426,6 +426,7 @@ extern "C" int tm_sample_khop(const tm_graph *g, int64_t B, int k, int n, const 
                               uint64_t seed, uint64_t row_offset, int32_t *const *h_o_node, int32_t *const *h_o_eidx, float *const *h_o_ts,
                               int32_t *d_err, tm_stream stream) {
     if (!g || B < 0 || k < 0 || n <= 0 || (k > 0 && (!h_o_node || !h_o_eidx || !h_o_ts))) { set_error("tm_sample_khop: bad argument"); return TM_ERR_ARG; }
+    if (B == 0) return TM_OK;                        // empty batch: nothing to write (the outputs may be null)
     int64_t rows = B;
     uint64_t off = row_offset;
     for (int l = 0; l < k; ++l) {
