@@ -716,8 +716,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll
             for (int i = 0; i < 4; ++i) u[i] = ldcg4(uc + i * 512);
         };
-        // one K chunk of MLP.0; in SHARE kernels the last one is a call site of its own (PRE) so that the preload is not live across the loop
-        auto g0_chunk = [&](const int c, const bool last, const bool PRE) __attribute__((always_inline)) {
+        auto g0_chunk = [&](const int c, const bool last) __attribute__((always_inline)) {      // one K chunk of MLP.0
             const int kcols = min(kKC, L.g0.K8 - c * kKC);
             if (stage_nodes) { tc::mbar_wait(bars + 2, n_phase); n_phase ^= 1; }          // chunk c of the rows has landed
             if (proj && stage_edges) { tc::mbar_wait(bars + 3, e_phase); e_phase ^= 1; }  // and chunk c of the projected edge rows
@@ -774,9 +773,6 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             auto next_nodes = [&]() {                           // the staged chunk has been consumed
                 if (c + 1 < nG) { request_nodes(pi, c + 1); if (proj) request_edges(pi, c + 1); }
                 else if (has_next) { request_nodes(pnext, 0); if (proj) request_edges(pnext, 0); }
-#ifdef TM_SHARE_PRELOAD
-                if (PRE && with_u) { load_u(0, ua); load_u(1, ub); }       // in flight behind the MMAs
-#endif
             };
             int64_t noff; int nbytes;                           // weights after this chunk's last round
             if (!last) { noff = L.g0.w + (int64_t)(c + 1) * chunk_floats(L.g0); nbytes = bytes_g; }
@@ -793,14 +789,8 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 }
             }
         };
-        if (SHARE) {
 #pragma unroll 1
-            for (int c = 0; c + 1 < nG; ++c) g0_chunk(c, false, false);
-            g0_chunk(nG - 1, true, true);
-        } else {
-#pragma unroll 1
-            for (int c = 0; c < nG; ++c) g0_chunk(c, c + 1 == nG, false);
-        }
+        for (int c = 0; c < nG; ++c) g0_chunk(c, c + 1 == nG);
         // ---- h_pos = relu(MLP.0 + bias): thread part p owns columns [4 CW p, 4 CW (p + 1)) of [Zs | Zt]
         // (SHARE, positions 0 / 1: U + cu is known already, so s_pos = h_pos . (U + cu) is taken here and the motif rounds do not read h back for
         // it.  U comes from the L2 scratch 32 columns at a time; groups beyond the first two exist at hid_dim 64 only -- one uniform branch
@@ -823,9 +813,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             }
         };
         {
-#ifndef TM_SHARE_PRELOAD
             if (with_u) { load_u(0, ua); load_u(1, ub); }
-#endif
             ep_group(0, ua); ep_group(1, ub);
             if (H2 / kParts > 32) {
                 if (with_u) { load_u(2, ua); load_u(3, ub); }
@@ -950,7 +938,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll
             for (int c = 0; c < 2; ++c) ldw(Ys + min(c, H / kKC - 1) * kSlabFloats, yb[c]);     // hid_dim 32: one chunk (the copy in yb[1] is not read)
         };
-        if (dq) {                                               // two K chunks per round; the last round is a call site of its own (see g0_chunk)
+        if (dq) {                                               // two K chunks per round
             x.a_col2 = colU;
             auto q_round = [&](const int c, const bool LAST) __attribute__((always_inline)) {
                 float m0[CW], m1[CW];
@@ -959,16 +947,10 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 if (!LAST) { ldw(F0 + (c + 2) * kSlabFloats, n0); ldw(F1 + (c + 2) * kSlabFloats, n1); }
                 put_mix(m0, m1, true);
                 tc_mma_round<TS>(x, H, kKC, colY, !SHARE || c != 0, LAST ? L.r.w : L.q.w + (int64_t)(c + 2) * chunk_floats(L.q), LAST ? min(2, L.r.nch) * bytes_r : 2 * bytes_q,
-#ifdef TM_SHARE_PRELOAD
-                                 [&]() { if (SHARE && LAST) load_yb(); },
-#else
-                                 NoMid(),
-#endif
-                                 Dual{kDualK, kKC, 0, 0, 0});
+                                 NoMid(), Dual{kDualK, kKC, 0, 0, 0});
             };
 #pragma unroll 1
-            for (int c = 0; c + 2 < nchS; c += 2) q_round(c, false);
-            q_round(nchS - 2, true);
+            for (int c = 0; c < nchS; c += 2) q_round(c, c + 2 >= nchS);
         } else {
             for (int c = 0; c < nchS; ++c) {
                 float c0[CW], c1[CW];
@@ -992,9 +974,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         }
         // ---- M0 = R relu(Y + cy)   (attention.MLP.3 and MLP.0 folded); the next pass's operands start to arrive
         pcur = load_idx(nxt_live ? nxt_g : 0, nxt_live, nxt_pos);
-#ifndef TM_SHARE_PRELOAD
         if (SHARE) load_yb();
-#endif
         auto put_y = [&](const int c, bool second) {           // c: 0 or 1 (hid_dim <= 64)
             float z[CW];
             tmem_ldw<CW>(tmem + lane_base + colY + c * kKC + kb, z);
