@@ -423,6 +423,28 @@ __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cas
 // Tiles are handed out dynamically (CTA b starts with tile b, then takes gridDim.x + atomicAdd(counter)).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+// The CTA's L2 scratch (h slabs, U / Y, drained E): written and read back within microseconds while feature rows and walk tensors stream
+// through L2.  Its lines carry the evict_last priority (createpolicy), so that the streams push each other out first (-11 % DRAM writes at
+// cfg5, same kernel time; TM_SCRATCH_PLAIN restores plain .cg accesses).
+#ifndef TM_SCRATCH_PLAIN
+__device__ __forceinline__ uint64_t scratch_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 scr_ld4(const float *p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void scr_st4(float *p, float4 v, uint64_t pol) {
+    asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+#else
+__device__ __forceinline__ uint64_t scratch_policy() { return 0; }
+__device__ __forceinline__ float4 scr_ld4(const float *p, uint64_t) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void scr_st4(float *p, float4 v, uint64_t) { __stcg(reinterpret_cast<float4 *>(p), v); }
+#endif
 
 template <int CW> __device__ __forceinline__ void tmem_ldw(uint32_t taddr, float *v);
 template <> __device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, float *v) { tc::tmem_ld16(taddr, v); }
@@ -506,10 +528,11 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     float *Es = drain ? a.Es + (int64_t)blockIdx.x * nG * kSlabFloats : nullptr;
     float *Us = Fs + 2 * nsl * kSlabFloats;                // SHARE: U + cu over the h_2 slabs (same thread-to-address map as their reader's), P h_2 + cy behind
     float *Ys = SHARE ? a.Ys + (int64_t)blockIdx.x * (H / kKC) * kSlabFloats : nullptr;
+    const uint64_t spol = scratch_policy();
     // this thread's CW columns [kb, kb+CW) of row `row` of a [128 x 32] slab (coalesced 16-byte pieces)
     auto ldw = [&](const float *slab, float *v) {
 #pragma unroll
-        for (int g = 0; g < CW / 4; ++g) { const float4 f = ldcg4(slab + ((kb >> 2) + g) * 512 + row * 4); v[4 * g] = f.x; v[4 * g + 1] = f.y; v[4 * g + 2] = f.z; v[4 * g + 3] = f.w; }
+        for (int g = 0; g < CW / 4; ++g) { const float4 f = scr_ld4(slab + ((kb >> 2) + g) * 512 + row * 4, spol); v[4 * g] = f.x; v[4 * g + 1] = f.y; v[4 * g + 2] = f.z; v[4 * g + 3] = f.w; }
     };
 
     // Per-pass operands of this thread's row are fetched one pass ahead: the indices, dt and the edge-identity counts with
@@ -699,7 +722,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                     finish_e(ee, c);
                     float *ec = Es + c * kSlabFloats + (kb >> 2) * 512 + row * 4;
 #pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) __stcg(reinterpret_cast<float4 *>(ec + g * 512), make_float4(ee[4 * g], ee[4 * g + 1], ee[4 * g + 2], ee[4 * g + 3]));
+                    for (int g = 0; g < CW / 4; ++g) scr_st4(ec + g * 512, make_float4(ee[4 * g], ee[4 * g + 1], ee[4 * g + 2], ee[4 * g + 3]), spol);
                 }
             }
             tc::fence_before_sync();
@@ -714,7 +737,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             const int c0 = (H2 / kParts) * prt + g * 16;
             const float *uc = Us + (c0 >> 5) * kSlabFloats + ((c0 & 31) >> 2) * 512 + row * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) u[i] = ldcg4(uc + i * 512);
+            for (int i = 0; i < 4; ++i) u[i] = scr_ld4(uc + i * 512, spol);
         };
         auto g0_chunk = [&](const int c, const bool last) __attribute__((always_inline)) {      // one K chunk of MLP.0
             const int kcols = min(kKC, L.g0.K8 - c * kKC);
@@ -805,7 +828,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             for (int i = 0; i < 16; i += 4) {
                 const float4 bb = lds4(cstE + L.e_g0b + (c0 & (H - 1)) + i);
                 const float4 hv = make_float4(fmaxf(v[i] + bb.x, 0.f), fmaxf(v[i + 1] + bb.y, 0.f), fmaxf(v[i + 2] + bb.z, 0.f), fmaxf(v[i + 3] + bb.w, 0.f));
-                __stcg(reinterpret_cast<float4 *>(fc + (i >> 2) * 512), hv);
+                scr_st4(fc + (i >> 2) * 512, hv, spol);
                 if (SHARE) {
                     const float4 uu = u[i >> 2];
                     sk = fmaf(hv.x, uu.x, sk); sk = fmaf(hv.y, uu.y, sk); sk = fmaf(hv.z, uu.z, sk); sk = fmaf(hv.w, uu.w, sk);
@@ -861,7 +884,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 bb = lds4(cstM + L.m_cu + c0 + i);
-                __stcg(reinterpret_cast<float4 *>(dst + (i >> 2) * 512), make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w));
+                scr_st4(dst + (i >> 2) * 512, make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w), spol);
             }
         }
 #pragma unroll 1
@@ -872,7 +895,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll
             for (int g = 0; g < CW / 4; ++g) {
                 const float4 bb = lds4(cstM + L.m_cy + c * kKC + kb + 4 * g);
-                __stcg(reinterpret_cast<float4 *>(dst + g * 512), make_float4(v[4 * g] + bb.x, v[4 * g + 1] + bb.y, v[4 * g + 2] + bb.z, v[4 * g + 3] + bb.w));
+                scr_st4(dst + g * 512, make_float4(v[4 * g] + bb.x, v[4 * g + 1] + bb.y, v[4 * g + 2] + bb.z, v[4 * g + 3] + bb.w), spol);
             }
         }
         tc::fence_before_sync();
