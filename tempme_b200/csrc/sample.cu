@@ -250,8 +250,8 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
             }
             if (staged) {       // the block's walks are contiguous in every output array: park them in shared memory, write them out coalesced below
                 const int lw = (int)threadIdx.x * N2 + jj;
-                int32_t *sn = stage + lw * 6, *se = stage + 256 * N2 * 6 + lw * 3;
-                float *st_ = reinterpret_cast<float *>(stage + 256 * N2 * 9) + lw * 3;
+                int32_t *sn = stage + lw * 6, *se = stage + (int)blockDim.x * N2 * 6 + lw * 3;
+                float *st_ = reinterpret_cast<float *>(stage + (int)blockDim.x * N2 * 9) + lw * 3;
                 sn[0] = (int32_t)src3; sn[1] = (int32_t)tgt3; sn[2] = (int32_t)s2; sn[3] = (int32_t)t2n; sn[4] = (int32_t)s1; sn[5] = (int32_t)t1n;
                 se[0] = e3; se[1] = e2; se[2] = e1;
                 st_[0] = t3; st_[1] = t2; st_[2] = t1;
@@ -281,8 +281,8 @@ sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__rest
             for (int64_t i = (words & ~(int64_t)3) + threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
         };
         flush(stage, o_nodes, 6);
-        flush(stage + 256 * N2 * 6, o_eidx, 3);
-        flush(stage + 256 * N2 * 9, reinterpret_cast<int32_t *>(o_t), 3);
+        flush(stage + (int)blockDim.x * N2 * 6, o_eidx, 3);
+        flush(stage + (int)blockDim.x * N2 * 9, reinterpret_cast<int32_t *>(o_t), 3);
     }
     if (threadIdx.x < 12 && sh_hist[threadIdx.x]) {
         if (hist_prep) atomicAdd(hist_prep + threadIdx.x, (unsigned long long)sh_hist[threadIdx.x]);
@@ -454,11 +454,16 @@ static int walks_impl(const tm_graph *g, int64_t B, int n, int N2, const int32_t
     if (N2 > TM_MAX_STEP2_FANOUT) { set_error("tm_sample_walks: step-2 fan-out %d > %d", N2, TM_MAX_STEP2_FANOUT); return TM_ERR_UNSUPPORTED; }
     if (B == 0) return TM_OK;
     TM_DEVICE(g->device);
-    const int64_t rows = B * n, blocks = (rows + 255) / 256;
+    // threads per block: the block's slots finish together (staged outputs), so smaller blocks wait less for their slowest walk -- 64 at N2 = 1
+    // (cfg2: 4.41 -> 3.47 ms per step), 128 at N2 <= 4 (cfg5: 8.95 -> 8.70 ms); wider walks are written directly from 256-thread blocks (staging
+    // 30 KB per 128 slots at N2 = 5 costs more occupancy than the coalesced stores return: cfg4 1.33 vs 1.80 ms).  TEMPME_WALKS_BLOCK overrides.
+    static const int wb_env = []() { const char *e = getenv("TEMPME_WALKS_BLOCK"); const int v = e ? atoi(e) : 0; return v == 64 || v == 128 || v == 256 ? v : 0; }();
+    const int wb = wb_env ? wb_env : N2 == 1 ? 64 : N2 <= 4 ? 128 : 256;
+    const int64_t rows = B * n, blocks = (rows + wb - 1) / wb;
     // outputs staged in shared memory and written coalesced when a block's walks fit 48 KB (N2 <= 4 at 48 bytes per walk); the base
     // addresses of the block ranges are 16-byte aligned when the arrays are (256 N2 walks x 12 / 24 bytes)
-    const size_t stage_bytes = (size_t)256 * N2 * 48;
-    const bool staged = stage_bytes <= 48 * 1024 && !getenv("TEMPME_WALKS_NO_STAGING") && ((uintptr_t)d_o_nodes % 16 == 0) && ((uintptr_t)d_o_eidx % 16 == 0) &&
+    const size_t stage_bytes = (size_t)wb * N2 * 48;
+    const bool staged = N2 <= 4 && stage_bytes <= 48 * 1024 && !getenv("TEMPME_WALKS_NO_STAGING") && ((uintptr_t)d_o_nodes % 16 == 0) && ((uintptr_t)d_o_eidx % 16 == 0) &&
                         ((uintptr_t)d_o_t % 16 == 0);
     // 48 KB of staging (N2 = 4) plus the kernel's static shared memory is above the default 48 KB limit: opt in once per device
     static bool attr_set[64] = {false};
@@ -469,7 +474,7 @@ static int walks_impl(const tm_graph *g, int64_t B, int n, int N2, const int32_t
         TM_CUDA(cudaFuncSetAttribute(sample_walks_kernel<TM_MAX_STEP2_FANOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set[g->device] = true;
     }
-#define TM_WALKS(CAP) sample_walks_kernel<CAP><<<(unsigned)blocks, 256, staged ? stage_bytes : 0, (cudaStream_t)stream>>>(    \
+#define TM_WALKS(CAP) sample_walks_kernel<CAP><<<(unsigned)blocks, wb, staged ? stage_bytes : 0, (cudaStream_t)stream>>>(    \
         g->v, B, n, N2, d_root, d_h1_node, d_h1_eidx, d_h1_ts, seed, row_offset, d_inject2, d_inject3, d_pre2, d_pre2_t,     \
         d_o_nodes, d_o_eidx, d_o_t, d_o_anony, d_o_cat, d_hist_null, d_hist_prep, d_scanned, staged ? 1 : 0)
     if (N2 == 1) TM_WALKS(1); else if (N2 <= 4) TM_WALKS(4); else if (N2 <= 8) TM_WALKS(8); else TM_WALKS(TM_MAX_STEP2_FANOUT);

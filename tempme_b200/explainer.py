@@ -230,19 +230,30 @@ class TempME(nn.Module):
             self._desc_fanout[key] = EncoderDesc(desc.node_dim, desc.edge_dim, desc.hid_dim, desc.use_temporal, desc.if_cat, desc.edge_projected, fanout)
         return self._desc_fanout[key]
 
-    @staticmethod
-    def detect_fanout(eidx, nodes):
+    _fanout_seen = {}               # W -> fan-out found last time (tried first)
+
+    @classmethod
+    def detect_fanout(cls, eidx, nodes, min_motifs=0):
         """Largest c <= 10 dividing W such that every c consecutive walks have the same event next to the root -- find_k_walks' layout
-        w = i1 * N2 + j (utils/graph.py:290-300) gives c = N2.  Only a hint: the scorer verifies it tile by tile."""
+        w = i1 * N2 + j (utils/graph.py:290-300) gives c = N2.  Only a hint: the scorer verifies it tile by tile.  Calls below
+        ``min_motifs`` walks skip the test (each candidate costs a small reduction and a synchronisation)."""
         B, W = eidx.shape[0], eidx.shape[1]
-        if B == 0:
+        if B == 0 or B * W < min_motifs:
             return 1
         key = torch.stack([eidx[:, :, 2], nodes[:, :, 4], nodes[:, :, 5]], dim=-1)
-        for c in range(min(10, W), 1, -1):
-            if W % c == 0:
-                g = key.view(B, W // c, c, 3)
-                if bool((g == g[:, :, :1]).all()):
-                    return c
+
+        def uniform(c):
+            g = key.view(B, W // c, c, 3)
+            return bool((g == g[:, :, :1]).all())
+        last = cls._fanout_seen.get(W)
+        cands = [c for c in range(min(10, W), 1, -1) if W % c == 0]
+        if last in cands and uniform(last) and not any(uniform(c) for c in cands if c > last and c % last == 0):
+            return last
+        for c in cands:
+            if uniform(c):
+                cls._fanout_seen[W] = c
+                return c
+        cls._fanout_seen[W] = 1
         return 1
 
     def score_device(self, nodes, eidx, t, cat, cut_time, edge_identity, group=None, out=None, peer_ptrs=None, fanout=None):
@@ -306,7 +317,7 @@ class TempME(nn.Module):
             return _tr.score_autograd(self, nodes, eidx, t, cat, cut, eid)
         if self._dropout_active():                                        # train() under no_grad: dropout is part of the value
             return _tr.scores_layerwise(self, nodes.long(), eidx.long(), t, cat, cut, eid)
-        return self.score_device(nodes, eidx, t, cat, cut, eid, fanout=self.detect_fanout(eidx, nodes)).view(B, W, 1)
+        return self.score_device(nodes, eidx, t, cat, cut, eid, fanout=self.detect_fanout(eidx, nodes, min_motifs=8192)).view(B, W, 1)
 
     # ------------------------------------------------------------------ enhance path (explainer.py:203-306), eval mode
     def _walk_tensors(self, walks, cut_time_l, edge_identify):
@@ -343,7 +354,7 @@ class TempME(nn.Module):
         blob = self.packed_weights()
         nf, ef = self._tables()
         desc, ef = self._edge_table(blob, ef)
-        desc = self._with_fanout(desc, self.detect_fanout(eidx, nodes))
+        desc = self._with_fanout(desc, self.detect_fanout(eidx, nodes, min_motifs=8192))
         self._workspace(B, W, group)
         scores = torch.empty((B, W), dtype=torch.float32, device=self.device)
         y = torch.empty((B, W, self.hid_dim), dtype=torch.float32, device=self.device)
