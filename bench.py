@@ -77,7 +77,9 @@ def executed_flops(D, Ed, H=HID, projected=True, fanout=1):
 
 # events per GPU per step: sized so that the default --steps 20 run keeps the GPU busy for >= 1 s (sustained clocks)
 DEFAULT_EVENTS = {"cfg1": 16000, "cfg2": 256000, "cfg3": 32000, "cfg4": 24000, "cfg5": 256000}
-DEFAULT_CHUNK = {"cfg1": 2000, "cfg2": 32000, "cfg3": 4000, "cfg4": 4000, "cfg5": 32000}
+# query events per kernel train: measured per workload (profiles/README.md r02b) -- the persistent scorer's last wave of tiles and the per-launch
+# costs weigh less on longer launches; cfg5 levels off at 64,000 (46 M motifs per step in four launches of 11.5 M)
+DEFAULT_CHUNK = {"cfg1": 16000, "cfg2": 128000, "cfg3": 32000, "cfg4": 24000, "cfg5": 64000}
 
 
 def workload_config(args, world=1):

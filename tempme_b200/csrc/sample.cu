@@ -147,7 +147,10 @@ __device__ __forceinline__ int64_t select_union(const uint64_t *__restrict__ k, 
 // 16-byte loads, so the latency is hidden by thread-level parallelism (>100k slots in flight).
 // ---------------------------------------------------------------------------------------------
 template <int CAP>
-__global__ void __launch_bounds__(256, 4)
+#ifndef TM_WALKS_MINBLOCKS
+#define TM_WALKS_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, TM_WALKS_MINBLOCKS)
 sample_walks_kernel(GraphView g, int64_t B, int n, int N2, const int32_t *__restrict__ root,
                     const int32_t *__restrict__ h1_node, const int32_t *__restrict__ h1_eidx, const float *__restrict__ h1_ts,
                     uint64_t seed, uint64_t row_offset, const uint32_t *__restrict__ inj2, const uint32_t *__restrict__ inj3,

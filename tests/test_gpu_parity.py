@@ -748,7 +748,8 @@ def test_edge_projection_mode_equals_plain_mode(tm, D, Ed):
 
 
 @pytest.mark.parametrize("D,Ed,hid,proj,N2", [(32, 32, 64, True, 3), (32, 32, 64, False, 3), (172, 172, 64, True, 5), (172, 172, 64, False, 2),
-                                              (100, 7, 32, True, 3), (32, 32, 32, True, 4), (64, 32, 64, True, 3)])
+                                              (100, 7, 32, True, 3), (32, 32, 32, True, 4), (64, 32, 64, True, 3),
+                                              (30, 6, 64, True, 3), (33, 5, 64, False, 3)])     # row sizes that are not multiples of 16 bytes: plain-load gathers
 def test_walk_group_mode_equals_plain_mode_and_oracle(tm, orc, D, Ed, hid, proj, N2):
     """tm_encoder_desc.walk_fanout: the N2 walks of a first-hop slot share their event next to the root, evaluated once per group.  Same
     scores as the per-walk evaluation (fp32 round-off of one reassociated sum) and as the oracle; the hint is only a hint: with the
