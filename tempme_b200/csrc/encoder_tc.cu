@@ -513,6 +513,13 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #define n_rows (a.k.n_rows)
 #define n_tiles (a.k.n_tiles)
     constexpr int colZ = 0, colU = 0;
+    // SPILL: the [S; P] rounds run once per slot too and U / Y wait in the scratch; TM_SHARE_SP_PER_WALK (A/B) shares the position-2 pass only and
+    // keeps the motif rounds of the per-walk evaluation ([S; P] from the h_2 slabs for every sub-tile, U and Y in TMEM)
+#ifdef TM_SHARE_SP_PER_WALK
+    constexpr bool SPILL = false;
+#else
+    constexpr bool SPILL = SHARE;
+#endif
     const int sh = SHARE ? a.share : 1;                    // sub-tiles per tile
     const bool proj = a.proj != 0;
     // lin_event rounds of the pass at position pos (position 2: dt = 0, the pure TimeEncode chunks are in the bias; edge-projection mode: no round
@@ -729,7 +736,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
             __syncthreads();
             tc::fence_after_sync();
         }
-        const bool with_u = SHARE && pos < 2;
+        const bool with_u = SPILL && pos < 2;
         float4 ua[4], ub[4];                                    // SHARE: U + cu of the epilogue's first two column groups
 #pragma unroll
         for (int i = 0; i < 4; ++i) ua[i] = ub[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -829,7 +836,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 const float4 bb = lds4(cstE + L.e_g0b + (c0 & (H - 1)) + i);
                 const float4 hv = make_float4(fmaxf(v[i] + bb.x, 0.f), fmaxf(v[i + 1] + bb.y, 0.f), fmaxf(v[i + 2] + bb.z, 0.f), fmaxf(v[i + 3] + bb.w, 0.f));
                 scr_st4(fc + (i >> 2) * 512, hv, spol);
-                if (SHARE) {
+                if (SPILL) {
                     const float4 uu = u[i >> 2];
                     sk = fmaf(hv.x, uu.x, sk); sk = fmaf(hv.y, uu.y, sk); sk = fmaf(hv.z, uu.z, sk); sk = fmaf(hv.w, uu.w, sk);
                 }
@@ -843,7 +850,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 ep_group(2, ua); ep_group(3, ub);
             }
         }
-        if (SHARE) { if (pos == 0) sk0 = sk; else if (pos == 1) sk1 = sk; }
+        if (SPILL) { if (pos == 0) sk0 = sk; else if (pos == 1) sk1 = sk; }
         tc::fence_before_sync();
         const int vote = __syncthreads_and(pred);   // TMEM reads done before the next rounds overwrite E / Z; the h slabs are visible to the CTA
         tc::fence_after_sync();
@@ -908,9 +915,9 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     // that follows (has_next); their operands are loaded into pcur behind the Q rounds and their first staged chunks requested behind MLP.3.
     auto motif_rounds = [&](const int64_t gm, const bool live, const float rp, const bool has_next, const int64_t nxt_g, const bool nxt_live, const int nxt_pos, const bool new_tile) {
         // ---- s_k = h_k . (U + cu) + r  (:806-808 after folding)
-        float s0 = SHARE ? sk0 : 0.f, s1 = SHARE ? sk1 : 0.f;       // SHARE: taken by the event passes' epilogues
+        float s0 = SPILL ? sk0 : 0.f, s1 = SPILL ? sk1 : 0.f;       // SHARE: taken by the event passes' epilogues
 #pragma unroll 1
-        for (int c = 0; c < (SHARE ? 0 : nchS); c += 2) {
+        for (int c = 0; c < (SPILL ? 0 : nchS); c += 2) {
             float p0[2][CW], p1[2][CW];
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) { ldw(F0 + (c + cc) * kSlabFloats, p0[cc]); ldw(F1 + (c + cc) * kSlabFloats, p1[cc]); }
@@ -969,7 +976,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 put_mix(n0, n1, false);
                 if (!LAST) { ldw(F0 + (c + 2) * kSlabFloats, n0); ldw(F1 + (c + 2) * kSlabFloats, n1); }
                 put_mix(m0, m1, true);
-                tc_mma_round<TS>(x, H, kKC, colY, !SHARE || c != 0, LAST ? L.r.w : L.q.w + (int64_t)(c + 2) * chunk_floats(L.q), LAST ? min(2, L.r.nch) * bytes_r : 2 * bytes_q,
+                tc_mma_round<TS>(x, H, kKC, colY, !SPILL || c != 0, LAST ? L.r.w : L.q.w + (int64_t)(c + 2) * chunk_floats(L.q), LAST ? min(2, L.r.nch) * bytes_r : 2 * bytes_q,
                                  NoMid(), Dual{kDualK, kKC, 0, 0, 0});
             };
 #pragma unroll 1
@@ -982,7 +989,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 if (c + 1 < nchS) { ldw(F0 + (c + 1) * kSlabFloats, n0); ldw(F1 + (c + 1) * kSlabFloats, n1); }
                 put_mix(c0, c1, false);
                 const bool last = c + 1 == nchS;
-                tc_mma_round<TS>(x, H, kKC, colY, !SHARE || c != 0, last ? L.r.w : L.q.w + (int64_t)(c + 1) * chunk_floats(L.q), last ? bytes_r : bytes_q);
+                tc_mma_round<TS>(x, H, kKC, colY, !SPILL || c != 0, last ? L.r.w : L.q.w + (int64_t)(c + 1) * chunk_floats(L.q), last ? bytes_r : bytes_q);
             }
         }
         // The tile's h slabs have been consumed (their last readers were the Q rounds' fills, completed before the rounds' barriers):
@@ -997,14 +1004,14 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         }
         // ---- M0 = R relu(Y + cy)   (attention.MLP.3 and MLP.0 folded); the next pass's operands start to arrive
         pcur = load_idx(nxt_live ? nxt_g : 0, nxt_live, nxt_pos);
-        if (SHARE) load_yb();
+        if (SPILL) load_yb();
         auto put_y = [&](const int c, bool second) {           // c: 0 or 1 (hid_dim <= 64)
             float z[CW];
             tmem_ldw<CW>(tmem + lane_base + colY + c * kKC + kb, z);
 #pragma unroll
             for (int k = 0; k < CW; k += 4) {
                 float4 bb;
-                if (SHARE) bb = c == 0 ? make_float4(yb[0][k], yb[0][k + 1], yb[0][k + 2], yb[0][k + 3]) : make_float4(yb[1][k], yb[1][k + 1], yb[1][k + 2], yb[1][k + 3]);
+                if (SPILL) bb = c == 0 ? make_float4(yb[0][k], yb[0][k + 1], yb[0][k + 2], yb[0][k + 3]) : make_float4(yb[1][k], yb[1][k + 1], yb[1][k + 2], yb[1][k + 3]);
                 else bb = lds4(cstM + L.m_cy + c * kKC + kb + k);
                 const float4 yv = make_float4(fmaxf(z[k] + bb.x, 0.f), fmaxf(z[k + 1] + bb.y, 0.f), fmaxf(z[k + 2] + bb.z, 0.f), fmaxf(z[k + 3] + bb.w, 0.f));
                 af.put4(x, row, kb, k, yv);
@@ -1106,13 +1113,13 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 const int pos = SHARE ? (k == 0 ? 2 : k - 1) : k;
                 if (k < 2) pnext = load_idx(gm, live, SHARE ? k : k + 1);
                 int64_t aoff; int abytes;
-                if (SHARE ? k == 0 : k == 2) { aoff = L.sp.w; abytes = bytes_sp; }
-                else if (SHARE && k == 2) { aoff = L.q.w; abytes = (dq ? 2 : 1) * bytes_q; }
-                else first_w(SHARE ? 1 : k + 1, aoff, abytes);
+                if (SPILL ? k == 0 : k == 2) { aoff = L.sp.w; abytes = bytes_sp; }
+                else if (SPILL && k == 2) { aoff = L.q.w; abytes = (dq ? 2 : 1) * bytes_q; }
+                else first_w(SHARE ? k : k + 1, aoff, abytes);
                 // SHARE, k == 0: position 0's rows are requested behind the pass's last round where the staging lies clear of the [S; P] weights
-                const int vote = event_pass(pos, pcur, live, SHARE ? (k == 1 || (k == 0 && a.sp_stage_safe)) : k < 2, aoff, abytes, (SHARE && j == 0 && k == 0) ? eq : 1);
-                if (SHARE && k == 0) {
-                    if (j == 0) shared = vote != 0;
+                const int vote = event_pass(pos, pcur, live, SPILL ? (k == 1 || (k == 0 && a.sp_stage_safe)) : k < 2, aoff, abytes, (SHARE && j == 0 && k == 0) ? eq : 1);
+                if (SHARE && j == 0 && k == 0) shared = vote != 0;
+                if (SPILL && k == 0) {
                     first_w(0, aoff, abytes);
                     rp = sp_rounds(aoff, abytes);
                     pcur = pnext;
@@ -1120,7 +1127,7 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                     spill_uy();
                 } else if (k < 2) pcur = pnext;
             }
-            if (!SHARE) rp = sp_rounds(L.q.w, (dq ? 2 : 1) * bytes_q);
+            if (!SPILL) rp = sp_rounds(L.q.w, (dq ? 2 : 1) * bytes_q);
             bool has_next, nxt_live; int64_t nxt_g; int nxt_pos;
             const bool new_tile = !(SHARE && j + 1 < sh);
             if (!new_tile) { has_next = true; nxt_live = live; nxt_g = gr * sh + j + 1; nxt_pos = shared ? 0 : 2; }

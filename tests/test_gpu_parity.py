@@ -819,3 +819,29 @@ def test_walk_group_mode_many_tiles_per_cta(tm):
     plain = m.score_device(nodes, we, wt, cat, cut, eid, group=100).clone()
     grouped = m.score_device(nodes, we, wt, cat, cut, eid, group=100, fanout=N2).clone()
     np.testing.assert_allclose(grouped.cpu().numpy(), plain.cpu().numpy(), rtol=2e-6, atol=0)
+
+
+def test_three_hops_one_call_vs_oracle_and_hop_by_hop(tm, orc):
+    """find_k_hop(3) through tm_sample_khop (one C call) equals the oracle and the hop-by-hop route (tm_sample_hop per level), with a shard
+    offset and both cut modes; an empty batch returns empty records."""
+    src, dst, eidx, ts = synth_graph(31, 200, 8000, 10 ** 5)
+    f = tm.NeighborFinder.from_events(200, src, dst, eidx, ts)
+    og = orc.OracleGraph.from_events(200, src, dst, eidx, ts)
+    q = np.arange(6000, 6040)
+    n = 4
+    for ee in (eidx[q], None):
+        sub = f.find_k_hop(3, src[q], ts[q], n, ee, seed=5, row_offset=11)
+        osub = og.find_k_hop(3, src[q], ts[q], n, ee, seed=5, row_offset=11)
+        for a, b in zip(sub, osub):
+            assert len(a) == 3
+            for x, y in zip(a, b):
+                assert x.shape == y.shape and (x == y).all()
+        # hop by hop: the same draws (stage = level, row = row_offset * n^level + i)
+        x0 = f.sample_hop_device(src[q], None if ee is not None else ts[q], n, ee, seed=5, stage=0, row_offset=11)
+        x1 = f.sample_hop_device(x0[0].reshape(-1), None, n, x0[1].reshape(-1), seed=5, stage=1, row_offset=11 * n)
+        x2 = f.sample_hop_device(x1[0].reshape(-1), None, n, x1[1].reshape(-1), seed=5, stage=2, row_offset=11 * n * n)
+        for lvl, x in enumerate((x0, x1, x2)):
+            for arr, ref in zip(x, (sub[0][lvl], sub[1][lvl], sub[2][lvl])):
+                assert (arr.cpu().numpy().reshape(ref.shape) == ref).all()
+    empty = f.find_k_hop(2, np.zeros(0, np.int64), np.zeros(0), n, None)
+    assert all(len(r) == 2 and r[0].shape == (0, n) and r[1].shape == (0, n * n) for r in empty)
