@@ -276,8 +276,8 @@ extern "C" int64_t tm_encoder_workspace_floats(const tm_encoder_desc *desc, int6
     const int64_t slab = std::min<int64_t>(tc_slab_motifs(), (std::max<int64_t>(B * W, 1) + 127) / 128 * 128);   // whole tiles of 128 motifs
     const int64_t full = tc_slab_motifs();
     const int64_t n_g = ((desc->node_dim + 7) / 8 * 8 + 31) / 32;           // MLP.0 K chunks: the E scratch of the drain mode (node_dim > 32) holds n_g slabs per CTA
-    // h scratch of the resident CTAs (192 KB each) + the tile counter behind it; for small calls the scratch is still sized for a full grid
-    // when the E scratch follows it (its offset does not depend on the call)
+    // h scratch of the resident CTAs (192 KB each) + the tile counter, the Y slabs of the walk groups (32 KB each) and, at node_dim > 32, the E scratch
+    // (n_g slabs each) behind it: the factor 2 on the h scratch covers the Y slabs; with an E scratch the whole is sized for a full grid
     return n_std + 2 * (n_g > 1 ? full : slab) * 3 * 2 * desc->hid_dim + (n_g > 1 ? 64 + full / 128 * n_g * 4096 : 0);
 }
 
