@@ -20,7 +20,7 @@ _u64 = C.c_uint64
 
 class EncoderDesc(C.Structure):
     _fields_ = [("node_dim", C.c_int32), ("edge_dim", C.c_int32), ("hid_dim", C.c_int32),
-                ("use_temporal", C.c_int32), ("if_cat", C.c_int32), ("edge_projected", C.c_int32), ("walk_fanout", C.c_int32)]
+                ("use_temporal", C.c_int32), ("if_cat", C.c_int32), ("edge_projected", C.c_int32), ("walk_fanout", C.c_int32), ("edge_identity_u8", C.c_int32)]
 
 
 PARAM_FIELDS = ["lin_event_w", "lin_event_b", "gcn0_w", "gcn0_b", "gcn2_w", "gcn2_b", "att_w1_w", "att_w1_b",
@@ -60,6 +60,7 @@ SIGNATURES = {
     "tm_walk_next_step_time": (C.c_int, [_p, _i64, C.c_int, _p, _p, _p, _u64, _u64, _p, _p, _p, _p, _p, _p, _p]),
     "tm_class_hist": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p]),
     "tm_edge_identity": (C.c_int, [_i64, _i64, _p, _p, _p]),
+    "tm_edge_identity_u8": (C.c_int, [_i64, _i64, _p, _p, _p]),
     "tm_encoder_blob_floats": (_i64, [C.POINTER(EncoderDesc)]),
     "tm_encoder_pack": (C.c_int, [C.POINTER(EncoderDesc), C.POINTER(EncoderParams), _p]),
     "tm_encoder_project_edges": (C.c_int, [C.POINTER(EncoderDesc), _p, _p, _i64, _p, C.c_int, _p]),

@@ -356,7 +356,7 @@ static int encode_score_impl(const tm_encoder_desc *desc, const float *d_blob, i
         TM_LAUNCH_CHECK();
     }
     const char *which = getenv("TEMPME_ENCODER");     // "ffma" selects the fp32 CUDA-core kernel (A/B validation); default: tcgen05
-    if (desc->edge_projected || d_y || n_peers > 0 || desc->hid_dim != 64 || !which || strcmp(which, "ffma") != 0) {
+    if (desc->edge_projected || desc->edge_identity_u8 || d_y || n_peers > 0 || desc->hid_dim != 64 || !which || strcmp(which, "ffma") != 0) {
         const int64_t n_std = (std::max<int64_t>(32, n_groups) + 31) & ~(int64_t)31;
         return tc_encode_score(*desc, d_blob + L.total, B, W, group, d_nodes, d_eidx, d_t, d_cat, d_cut_time, d_edge_identity, d_node_feat,
                                n_node_rows, d_edge_feat, n_edge_rows, d_workspace, d_workspace + n_std, d_scores, d_y, peer_scores, n_peers, device, st);

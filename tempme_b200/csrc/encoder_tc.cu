@@ -397,6 +397,7 @@ struct TcArgs {
     unsigned long long *tile_counter;        // dynamic tile scheduler: CTA b takes tile b first, then gridDim.x + atomicAdd(counter, 1)
     int proj;                                // edge-projection mode: edge_feat is the table P = lin_event[:, :Ed] . edge features [n_edge_rows][D] (tc_project_edges);
                                              //   lin_event runs over its TimeEncode columns only and P's rows are gathered like a third node-feature table
+    int eid_u8;                              // eid points to byte counts (tm_edge_identity_u8) instead of floats
     int discard;                             // discard.global.L2 on the h slabs once a tile has consumed them (no write-back of the scratch)
     int share;                               // SHARE instantiations: consecutive walks per first-hop slot (find_k_walks: w = i1 * N2 + j, share = N2 >= 2, divides n_motifs)
     float *Ys;                               // SHARE: per CTA H / 32 slabs that hold P h_2 + cy of the tile's slots between the sub-tiles
@@ -551,7 +552,10 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
         if (lv) {
             q.e = a.eidx[g * 3 + pos]; q.ns = a.nodes[g * 6 + 2 * pos]; q.nt = a.nodes[g * 6 + 2 * pos + 1];
             q.dt = __fsub_rn(a.t[g * 3 + 2], a.t[g * 3 + pos]);                          // explainer.py:326
-            if (a.eid) { const float *ei = a.eid + g * 9 + pos * 3; q.ei0 = __ldg(ei); q.ei1 = __ldg(ei + 1); q.ei2 = __ldg(ei + 2); }
+            if (a.eid) {
+                if (a.eid_u8) { const uint8_t *ei = reinterpret_cast<const uint8_t *>(a.eid) + g * 9 + pos * 3; q.ei0 = (float)__ldg(ei); q.ei1 = (float)__ldg(ei + 1); q.ei2 = (float)__ldg(ei + 2); }
+                else { const float *ei = a.eid + g * 9 + pos * 3; q.ei0 = __ldg(ei); q.ei1 = __ldg(ei + 1); q.ei2 = __ldg(ei + 2); }
+            }
         }
         return q;
     };
@@ -610,8 +614,9 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 float c_[4][3];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float *ei = a.eid + (g0_ + min(j + i, sh - 1)) * 9 + 6;
-                    c_[i][0] = __ldg(ei); c_[i][1] = __ldg(ei + 1); c_[i][2] = __ldg(ei + 2);
+                    const int64_t o = (g0_ + min(j + i, sh - 1)) * 9 + 6;
+                    if (a.eid_u8) { const uint8_t *ei = reinterpret_cast<const uint8_t *>(a.eid) + o; c_[i][0] = (float)__ldg(ei); c_[i][1] = (float)__ldg(ei + 1); c_[i][2] = (float)__ldg(ei + 2); }
+                    else { const float *ei = a.eid + o; c_[i][0] = __ldg(ei); c_[i][1] = __ldg(ei + 1); c_[i][2] = __ldg(ei + 2); }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) eq &= (int)(c_[i][0] == p0.ei0) & (int)(c_[i][1] == p0.ei1) & (int)(c_[i][2] == p0.ei2);
@@ -1342,6 +1347,7 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.stage_edge_off = stage_edges ? (int)(a_bytes + stage_edge_rel) : 0;
     a.dual = (dual ? 1 : 0) | (dual_e ? 2 : 0) | (m3one ? 4 : 0);
     a.proj = proj ? 1 : 0;
+    a.eid_u8 = d.edge_identity_u8 != 0 ? 1 : 0;
     a.discard = getenv("TEMPME_TC_DISCARD") ? 1 : 0;          // A/B knob, off: the discards removed the scratch write-back but cost 2.6 % of kernel time (profiles/README.md r02b)
     static long long *dbg_buf = nullptr;
 #ifdef TM_TC_TIMING

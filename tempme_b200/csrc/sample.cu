@@ -327,8 +327,9 @@ class_hist_kernel(int64_t count, const int32_t *__restrict__ anony, unsigned lon
 // again: O(3W) table operations per root instead of the (3W)^2 comparisons of the all-pairs form.
 // ---------------------------------------------------------------------------------------------
 constexpr int kEidWarps = 8;
+template <typename OutT>      // float (the reference's dtype) or uint8_t (the pipeline's compact form: counts <= W <= 255)
 __global__ void __launch_bounds__(kEidWarps * 32)
-edge_identity_kernel(int64_t B, int W, int slots_mask, const int32_t *__restrict__ eidx, float *__restrict__ out) {
+edge_identity_kernel(int64_t B, int W, int slots_mask, const int32_t *__restrict__ eidx, OutT *__restrict__ out) {
     extern __shared__ int32_t sh_tab[];         // per warp: keys [slots], counters [slots]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slots = slots_mask + 1;
     int32_t *keys = sh_tab + (size_t)warp * 2 * slots;
@@ -354,8 +355,8 @@ edge_identity_kernel(int64_t B, int W, int slots_mask, const int32_t *__restrict
         int slot = hash(id);
         while (keys[slot] != id) slot = (slot + 1) & slots_mask;
         const unsigned c = cnt[slot];
-        float *o = out + (b * n3 + i) * 3;
-        o[0] = (float)(c & 1023u); o[1] = (float)((c >> 10) & 1023u); o[2] = (float)((c >> 20) & 1023u);
+        OutT *o = out + (b * n3 + i) * 3;
+        o[0] = (OutT)(c & 1023u); o[1] = (OutT)((c >> 10) & 1023u); o[2] = (OutT)((c >> 20) & 1023u);
     }
 }
 
@@ -533,9 +534,11 @@ extern "C" int tm_class_hist(int64_t count, const int32_t *d_anony, unsigned lon
     return TM_OK;
 }
 
-extern "C" int tm_edge_identity(int64_t B, int64_t W, const int32_t *d_eidx, float *d_out, tm_stream stream) {
+template <typename OutT>
+static int edge_identity_impl(int64_t B, int64_t W, const int32_t *d_eidx, OutT *d_out, tm_stream stream) {
     if (B < 0 || W <= 0 || (B > 0 && (!d_eidx || !d_out))) { set_error("tm_edge_identity: bad argument"); return TM_ERR_ARG; }
     if (W > 1023) { set_error("tm_edge_identity: %lld walks per root exceed the 10-bit position counters", (long long)W); return TM_ERR_UNSUPPORTED; }
+    if (sizeof(OutT) == 1 && W > 255) { set_error("tm_edge_identity_u8: %lld walks per root do not fit a byte count", (long long)W); return TM_ERR_UNSUPPORTED; }
     int slots = 64;
     while (slots < 6 * W) slots <<= 1;                       // load factor <= 1/2
     const size_t smem = sizeof(int32_t) * 2 * (size_t)slots * kEidWarps;
@@ -545,11 +548,19 @@ extern "C" int tm_edge_identity(int64_t B, int64_t W, const int32_t *d_eidx, flo
     int dev = 0;
     TM_CUDA(cudaGetDevice(&dev));
     if (smem > 48 * 1024 && dev < 64 && !attr_set[dev]) {
-        TM_CUDA(cudaFuncSetAttribute(edge_identity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TM_CUDA(cudaFuncSetAttribute(edge_identity_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[dev] = true;
     }
     if (smem > 200 * 1024) { set_error("tm_edge_identity: %lld walks per root exceed the shared-memory window", (long long)W); return TM_ERR_UNSUPPORTED; }
-    edge_identity_kernel<<<(unsigned)((B + kEidWarps - 1) / kEidWarps), kEidWarps * 32, smem, (cudaStream_t)stream>>>(B, (int)W, slots - 1, d_eidx, d_out);
+    edge_identity_kernel<OutT><<<(unsigned)((B + kEidWarps - 1) / kEidWarps), kEidWarps * 32, smem, (cudaStream_t)stream>>>(B, (int)W, slots - 1, d_eidx, d_out);
     TM_LAUNCH_CHECK();
     return TM_OK;
+}
+
+extern "C" int tm_edge_identity(int64_t B, int64_t W, const int32_t *d_eidx, float *d_out, tm_stream stream) {
+    return edge_identity_impl<float>(B, W, d_eidx, d_out, stream);
+}
+
+extern "C" int tm_edge_identity_u8(int64_t B, int64_t W, const int32_t *d_eidx, uint8_t *d_out, tm_stream stream) {
+    return edge_identity_impl<uint8_t>(B, W, d_eidx, d_out, stream);
 }

@@ -220,14 +220,15 @@ class TempME(nn.Module):
         return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(self.device, non_blocking=True)
 
     # ------------------------------------------------------------------ forward (explainer.py:174-201)
-    def _with_fanout(self, desc, fanout):
-        """The descriptor with the walk-layout hint set (tm_encoder_desc.walk_fanout)."""
+    def _with_fanout(self, desc, fanout, eid_u8=False):
+        """The descriptor with the walk-layout hint (tm_encoder_desc.walk_fanout) and the edge-identity dtype flag set."""
         fanout = int(fanout or 0)
-        if fanout < 2:
+        if fanout < 2 and not eid_u8:
             return desc
-        key = (desc.edge_projected, fanout)
+        key = (desc.edge_projected, max(fanout, 0), bool(eid_u8))
         if key not in self._desc_fanout:
-            self._desc_fanout[key] = EncoderDesc(desc.node_dim, desc.edge_dim, desc.hid_dim, desc.use_temporal, desc.if_cat, desc.edge_projected, fanout)
+            self._desc_fanout[key] = EncoderDesc(desc.node_dim, desc.edge_dim, desc.hid_dim, desc.use_temporal, desc.if_cat, desc.edge_projected,
+                                                 fanout if fanout >= 2 else 0, int(bool(eid_u8)))
         return self._desc_fanout[key]
 
     _fanout_seen = {}               # W -> fan-out found last time (tried first)
@@ -258,7 +259,7 @@ class TempME(nn.Module):
 
     def score_device(self, nodes, eidx, t, cat, cut_time, edge_identity, group=None, out=None, peer_ptrs=None, fanout=None):
         """All arguments CUDA tensors: nodes i32 [B,W,6], eidx i32 [B,W,3], t f32 [B,W,3], cat u8 [B,W],
-        cut_time f32 [B], edge_identity f32 [B,W,3,3] -> scores f32 [B,W].  out: preallocated [B,W] result (e.g. this rank's segment of a
+        cut_time f32 [B], edge_identity f32 (or the byte counts of edge_identity_device(u8=True)) [B,W,3,3] -> scores f32 [B,W].  out: preallocated [B,W] result (e.g. this rank's segment of a
         gathered buffer); peer_ptrs: device addresses of the same segment on up to 7 peer GPUs -- the kernel stores every score there too
         (tm_encode_score_gather; tempme_b200.dist.ScoreExchange).  fanout: N2 when the walks come from find_k_walks (w = i1 * N2 + j): the
         event next to the root is then evaluated once per N2 walks (verified by the kernel; the scores do not depend on the hint)."""
@@ -267,7 +268,9 @@ class TempME(nn.Module):
         blob = self.packed_weights()
         nf, ef = self._tables()
         desc, ef = self._edge_table(blob, ef)
-        desc = self._with_fanout(desc, fanout)
+        if edge_identity.dtype not in (torch.float32, torch.uint8):
+            raise ValueError("score_device: edge_identity must be float32 (tm_edge_identity) or uint8 (tm_edge_identity_u8)")
+        desc = self._with_fanout(desc, fanout, eid_u8=edge_identity.dtype == torch.uint8)
         self._workspace(B, W, group)
         if out is None:
             scores = torch.empty((B, W), dtype=torch.float32, device=self.device)

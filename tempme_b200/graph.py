@@ -405,15 +405,22 @@ def class_hist_device(anony, want_cat=True):
     return hn, hp, (cat.view(anony.shape[:-1]) if want_cat else None), err
 
 
-def edge_identity_device(eidx, out=None):
-    """new_edge_info (processed/data_preprocess.py:327-343): [B, W, 3] int32 -> [B, W, 3, 3] float32."""
+def edge_identity_device(eidx, out=None, u8=False):
+    """new_edge_info (processed/data_preprocess.py:327-343): [B, W, 3] int32 -> [B, W, 3, 3] float32 (the reference's values), or with
+    ``u8`` the same counts as bytes (W <= 255): the compact form MotifPipeline hands to the scorer."""
     e = eidx.contiguous()
     B, W, _ = e.shape
+    dt = torch.uint8 if u8 else torch.float32
     if out is None:
-        out = torch.empty((B, W, 3, 3), dtype=torch.float32, device=e.device)
+        out = torch.empty((B, W, 3, 3), dtype=dt, device=e.device)
+    elif out.dtype != dt:
+        raise ValueError("edge_identity_device: out must be %s" % dt)
     st = C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream)
     with torch.cuda.device(e.device):
-        check(lib().tm_edge_identity(B, W, ptr(e), ptr(out), st), "tm_edge_identity")
+        if u8:
+            check(lib().tm_edge_identity_u8(B, W, ptr(e), ptr(out), st), "tm_edge_identity_u8")
+        else:
+            check(lib().tm_edge_identity(B, W, ptr(e), ptr(out), st), "tm_edge_identity")
     return out
 
 

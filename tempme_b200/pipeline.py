@@ -89,7 +89,8 @@ class MotifPipeline:
             ws = dict(h1=(torch.empty((R, n), dtype=i32, device=dev), torch.empty((R, n), dtype=i32, device=dev), torch.empty((R, n), dtype=f32, device=dev)),
                       walks=(torch.empty((R, W, 6), dtype=i32, device=dev), torch.empty((R, W, 3), dtype=i32, device=dev),
                              torch.empty((R, W, 3), dtype=f32, device=dev), torch.empty((R, W), dtype=torch.uint8, device=dev)),
-                      eid=torch.empty((R, W, 3, 3), dtype=f32, device=dev))
+                      # edge-identity counts in their compact form (bytes, W <= 255) when the walks stay inside the pipeline
+                      eid=torch.empty((R, W, 3, 3), dtype=torch.uint8 if W <= 255 else f32, device=dev))
             self._ws[R] = ws
         return ws
 
@@ -134,7 +135,7 @@ class MotifPipeline:
                                                            row_offset=row_offset + c0, want_anony=False, want_cat=True,
                                                            hist_null=self.hist_null, hist_prep=self.hist_prep, scanned=self.scanned, out=wout)
             mark("sample_walks")
-            eid = edge_identity_device(eidx, out=ws["eid"] if full is None else full[4][sl])
+            eid = edge_identity_device(eidx, out=ws["eid"], u8=ws["eid"].dtype == torch.uint8) if full is None else edge_identity_device(eidx, out=full[4][sl])
             mark("edge_identity")
             pp = [int(p) + c0 * W * 4 for p in peer_ptrs] if peer_ptrs else None
             self.explainer.score_device(nodes, eidx, t, cat, cut32[sl], eid, group=max(g, 1), out=out2[sl], peer_ptrs=pp, fanout=N2)

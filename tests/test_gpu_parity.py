@@ -845,3 +845,27 @@ def test_three_hops_one_call_vs_oracle_and_hop_by_hop(tm, orc):
                 assert (arr.cpu().numpy().reshape(ref.shape) == ref).all()
     empty = f.find_k_hop(2, np.zeros(0, np.int64), np.zeros(0), n, None)
     assert all(len(r) == 2 and r[0].shape == (0, n) and r[1].shape == (0, n * n) for r in empty)
+
+
+def test_edge_identity_bytes_equal_floats_and_score_alike(tm):
+    """tm_edge_identity_u8: the same counts as bytes; the scorer reads either form (tm_encoder_desc.edge_identity_u8) -- bit-identical scores,
+    with and without walk groups."""
+    rng = np.random.default_rng(9)
+    src, dst, eidx, ts = synth_graph(37, 300, 20000, 10 ** 6)
+    f = tm.NeighborFinder.from_events(300, src, dst, eidx, ts)
+    q = np.arange(15000, 15300)
+    sub = f.find_k_hop_device(1, src[q], ts[q], 10, eidx[q], seed=3)
+    nodes, we, wt, anony, cat = f.find_k_walks_device(10, src[q], 3, sub, seed=4)
+    eid_f = tm.edge_identity_device(we)
+    eid_b = tm.edge_identity_device(we, u8=True)
+    assert eid_b.dtype == torch.uint8 and torch.equal(eid_b.float(), eid_f)
+    nfeat = rng.standard_normal((300, 32)).astype(np.float32); efeat = rng.standard_normal((20001, 32)).astype(np.float32)
+    torch.manual_seed(4)
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, 64, device="cuda", null_model={}).cuda().eval()
+    cut = torch.as_tensor(ts[q].astype(np.float32)).cuda()
+    for fan in (None, 3):
+        a = m.score_device(nodes, we, wt, cat, cut, eid_f, group=100, fanout=fan).clone()
+        b = m.score_device(nodes, we, wt, cat, cut, eid_b, group=100, fanout=fan).clone()
+        assert torch.equal(a, b)
+    with pytest.raises(NotImplementedError):
+        tm.edge_identity_device(torch.zeros((1, 256, 3), dtype=torch.int32, device="cuda"), u8=True)
