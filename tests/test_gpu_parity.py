@@ -869,3 +869,25 @@ def test_edge_identity_bytes_equal_floats_and_score_alike(tm):
         assert torch.equal(a, b)
     with pytest.raises(NotImplementedError):
         tm.edge_identity_device(torch.zeros((1, 256, 3), dtype=torch.int32, device="cuda"), u8=True)
+
+
+@pytest.mark.parametrize("B,n,N2", [(1, 2, 3), (3, 5, 2), (7, 20, 5)])
+def test_walk_group_mode_tiny_batches(tm, B, n, N2):
+    """A handful of roots (one partial tile of slots) through the walk-group kernel == the per-walk evaluation."""
+    rng = np.random.default_rng(B)
+    src, dst, eidx, ts = synth_graph(41, 120, 6000, 10 ** 5)
+    f = tm.NeighborFinder.from_events(120, src, dst, eidx, ts)
+    q = np.arange(5000, 5000 + B)
+    sub = f.find_k_hop_device(1, src[q], ts[q], n, eidx[q], seed=3)
+    nodes, we, wt, anony, cat = f.find_k_walks_device(n, src[q], N2, sub, seed=4)
+    eid = tm.edge_identity_device(we)
+    nfeat = rng.standard_normal((120, 32)).astype(np.float32); efeat = rng.standard_normal((6001, 32)).astype(np.float32)
+    torch.manual_seed(6)
+    m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, 64, device="cuda", null_model={}).cuda().eval()
+    cut = torch.as_tensor(ts[q].astype(np.float32)).cuda()
+    plain = m.score_device(nodes, we, wt, cat, cut, eid, group=100).clone()
+    grouped = m.score_device(nodes, we, wt, cat, cut, eid, group=100, fanout=N2).clone()
+    np.testing.assert_allclose(grouped.cpu().numpy(), plain.cpu().numpy(), rtol=2e-6, atol=0)
+    # a hint that does not divide W is ignored
+    odd = m.score_device(nodes, we, wt, cat, cut, eid, group=100, fanout=7 if (n * N2) % 7 else 9).clone()
+    assert torch.equal(odd, plain)
