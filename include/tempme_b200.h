@@ -142,8 +142,8 @@ int tm_class_hist(int64_t count, const int32_t *d_anony, unsigned long long *d_h
 
 /* new_edge_info (processed/data_preprocess.py:327-343): d_eidx [B, W, 3] -> d_out [B, W, 3, 3] (f32) */
 int tm_edge_identity(int64_t B, int64_t W, const int32_t *d_eidx, float *d_out, tm_stream stream);
-/* The same counts as bytes, [B, W, 3, 3] u8 (W <= 255): the compact form the device pipeline hands to the scorer
- * (tm_encoder_desc.edge_identity_u8); a quarter of the bytes written and read back per walk. */
+/* The same counts as bytes (W <= 255), d_out [B, W, 3, 4] u8 = three counts and a pad byte per walk event: the compact form the device
+ * pipeline hands to the scorer (tm_encoder_desc.edge_identity_u8) -- a third of the bytes, one 4-byte store / load per event. */
 int tm_edge_identity_u8(int64_t B, int64_t W, const int32_t *d_eidx, uint8_t *d_out, tm_stream stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -161,7 +161,7 @@ typedef struct {
                            * walk_fanout = N2 consecutive walks share the event next to the root.  The scorer then evaluates that event's
                            * layers (and the products that depend on it alone) once per group; every tile of groups checks the premise
                            * on its own operands and repeats the work per walk where it does not hold, so any value gives the same scores */
-    int32_t edge_identity_u8; /* 1: d_edge_identity points to the byte counts of tm_edge_identity_u8 instead of floats */
+    int32_t edge_identity_u8; /* 1: d_edge_identity points to the byte counts of tm_edge_identity_u8 ([B, W, 3, 4] u8) instead of floats */
 } tm_encoder_desc;
 
 /* Host pointers to the reference's parameters (nn.Linear layout: weight [out, in] row-major). */

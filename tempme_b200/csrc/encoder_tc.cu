@@ -397,6 +397,7 @@ struct TcArgs {
     unsigned long long *tile_counter;        // dynamic tile scheduler: CTA b takes tile b first, then gridDim.x + atomicAdd(counter, 1)
     int proj;                                // edge-projection mode: edge_feat is the table P = lin_event[:, :Ed] . edge features [n_edge_rows][D] (tc_project_edges);
                                              //   lin_event runs over its TimeEncode columns only and P's rows are gathered like a third node-feature table
+    int nodes_vec;                           // nodes is 8-byte aligned: both endpoints of an event with one load
     int eid_u8;                              // eid points to byte counts (tm_edge_identity_u8) instead of floats
     int discard;                             // discard.global.L2 on the h slabs once a tile has consumed them (no write-back of the scratch)
     int share;                               // SHARE instantiations: consecutive walks per first-hop slot (find_k_walks: w = i1 * N2 + j, share = N2 >= 2, divides n_motifs)
@@ -550,10 +551,15 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
     auto load_idx = [&](int64_t g, bool lv, int pos) {
         PassIdx q; q.e = -1; q.ns = -1; q.nt = -1; q.dt = 0.f; q.ei0 = q.ei1 = q.ei2 = 0.f;
         if (lv) {
-            q.e = a.eidx[g * 3 + pos]; q.ns = a.nodes[g * 6 + 2 * pos]; q.nt = a.nodes[g * 6 + 2 * pos + 1];
+            q.e = a.eidx[g * 3 + pos];
+            if (a.nodes_vec) { const int2 nd = *reinterpret_cast<const int2 *>(a.nodes + g * 6 + 2 * pos); q.ns = nd.x; q.nt = nd.y; }      // both endpoints: one 8-byte load
+            else { q.ns = a.nodes[g * 6 + 2 * pos]; q.nt = a.nodes[g * 6 + 2 * pos + 1]; }
             q.dt = __fsub_rn(a.t[g * 3 + 2], a.t[g * 3 + pos]);                          // explainer.py:326
             if (a.eid) {
-                if (a.eid_u8) { const uint8_t *ei = reinterpret_cast<const uint8_t *>(a.eid) + g * 9 + pos * 3; q.ei0 = (float)__ldg(ei); q.ei1 = (float)__ldg(ei + 1); q.ei2 = (float)__ldg(ei + 2); }
+                if (a.eid_u8) {                   // [motif][position][4] bytes: three counts and a pad byte, one 4-byte load
+                    const uchar4 c4 = __ldg(reinterpret_cast<const uchar4 *>(a.eid) + g * 3 + pos);
+                    q.ei0 = (float)c4.x; q.ei1 = (float)c4.y; q.ei2 = (float)c4.z;
+                }
                 else { const float *ei = a.eid + g * 9 + pos * 3; q.ei0 = __ldg(ei); q.ei1 = __ldg(ei + 1); q.ei2 = __ldg(ei + 2); }
             }
         }
@@ -603,7 +609,8 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int64_t g = g0_ + min(j + i, sh - 1);
-                    e_[i] = a.eidx[g * 3 + 2]; s_[i] = a.nodes[g * 6 + 4]; t_[i] = a.nodes[g * 6 + 5];
+                    e_[i] = a.eidx[g * 3 + 2];
+                    s_[i] = a.nodes[g * 6 + 4]; t_[i] = a.nodes[g * 6 + 5];
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) eq &= (int)(e_[i] == p0.e) & (int)(s_[i] == p0.ns) & (int)(t_[i] == p0.nt);
@@ -614,9 +621,9 @@ score_tc_kernel(const TcLayout L, const float *__restrict__ blob, const TcArgs a
                 float c_[4][3];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int64_t o = (g0_ + min(j + i, sh - 1)) * 9 + 6;
-                    if (a.eid_u8) { const uint8_t *ei = reinterpret_cast<const uint8_t *>(a.eid) + o; c_[i][0] = (float)__ldg(ei); c_[i][1] = (float)__ldg(ei + 1); c_[i][2] = (float)__ldg(ei + 2); }
-                    else { const float *ei = a.eid + o; c_[i][0] = __ldg(ei); c_[i][1] = __ldg(ei + 1); c_[i][2] = __ldg(ei + 2); }
+                    const int64_t gg = g0_ + min(j + i, sh - 1);
+                    if (a.eid_u8) { const uchar4 c4 = __ldg(reinterpret_cast<const uchar4 *>(a.eid) + gg * 3 + 2); c_[i][0] = (float)c4.x; c_[i][1] = (float)c4.y; c_[i][2] = (float)c4.z; }
+                    else { const float *ei = a.eid + gg * 9 + 6; c_[i][0] = __ldg(ei); c_[i][1] = __ldg(ei + 1); c_[i][2] = __ldg(ei + 2); }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) eq &= (int)(c_[i][0] == p0.ei0) & (int)(c_[i][1] == p0.ei1) & (int)(c_[i][2] == p0.ei2);
@@ -1348,6 +1355,8 @@ int tc_encode_score(const tm_encoder_desc &d, const float *d_blob_tc, int64_t B,
     a.dual = (dual ? 1 : 0) | (dual_e ? 2 : 0) | (m3one ? 4 : 0);
     a.proj = proj ? 1 : 0;
     a.eid_u8 = d.edge_identity_u8 != 0 ? 1 : 0;
+    a.nodes_vec = ((uintptr_t)nodes & 7) == 0 ? 1 : 0;
+    if (a.eid_u8 && ((uintptr_t)eid & 3) != 0) { set_error("tc_encode_score: byte edge-identity counts must be 4-byte aligned"); return TM_ERR_ARG; }
     a.discard = getenv("TEMPME_TC_DISCARD") ? 1 : 0;          // A/B knob, off: the discards removed the scratch write-back but cost 2.6 % of kernel time (profiles/README.md r02b)
     static long long *dbg_buf = nullptr;
 #ifdef TM_TC_TIMING

@@ -355,8 +355,12 @@ edge_identity_kernel(int64_t B, int W, int slots_mask, const int32_t *__restrict
         int slot = hash(id);
         while (keys[slot] != id) slot = (slot + 1) & slots_mask;
         const unsigned c = cnt[slot];
-        OutT *o = out + (b * n3 + i) * 3;
-        o[0] = (OutT)(c & 1023u); o[1] = (OutT)((c >> 10) & 1023u); o[2] = (OutT)((c >> 20) & 1023u);
+        if (sizeof(OutT) == 1) {            // bytes: [walk][position][4] = three counts and a pad byte, one 4-byte store (and one 4-byte load in the scorer)
+            reinterpret_cast<uchar4 *>(out)[b * n3 + i] = make_uchar4((unsigned char)(c & 1023u), (unsigned char)((c >> 10) & 1023u), (unsigned char)((c >> 20) & 1023u), 0);
+        } else {
+            OutT *o = out + (b * n3 + i) * 3;
+            o[0] = (OutT)(c & 1023u); o[1] = (OutT)((c >> 10) & 1023u); o[2] = (OutT)((c >> 20) & 1023u);
+        }
     }
 }
 

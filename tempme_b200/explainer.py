@@ -259,7 +259,7 @@ class TempME(nn.Module):
 
     def score_device(self, nodes, eidx, t, cat, cut_time, edge_identity, group=None, out=None, peer_ptrs=None, fanout=None):
         """All arguments CUDA tensors: nodes i32 [B,W,6], eidx i32 [B,W,3], t f32 [B,W,3], cat u8 [B,W],
-        cut_time f32 [B], edge_identity f32 (or the byte counts of edge_identity_device(u8=True)) [B,W,3,3] -> scores f32 [B,W].  out: preallocated [B,W] result (e.g. this rank's segment of a
+        cut_time f32 [B], edge_identity f32 [B,W,3,3] (or the byte counts of edge_identity_device(u8=True), [B,W,3,4]) -> scores f32 [B,W].  out: preallocated [B,W] result (e.g. this rank's segment of a
         gathered buffer); peer_ptrs: device addresses of the same segment on up to 7 peer GPUs -- the kernel stores every score there too
         (tm_encode_score_gather; tempme_b200.dist.ScoreExchange).  fanout: N2 when the walks come from find_k_walks (w = i1 * N2 + j): the
         event next to the root is then evaluated once per N2 walks (verified by the kernel; the scores do not depend on the hint)."""

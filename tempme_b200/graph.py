@@ -407,14 +407,15 @@ def class_hist_device(anony, want_cat=True):
 
 def edge_identity_device(eidx, out=None, u8=False):
     """new_edge_info (processed/data_preprocess.py:327-343): [B, W, 3] int32 -> [B, W, 3, 3] float32 (the reference's values), or with
-    ``u8`` the same counts as bytes (W <= 255): the compact form MotifPipeline hands to the scorer."""
+    ``u8`` the same counts as bytes, [B, W, 3, 4] = three counts and a pad byte (W <= 255): the compact form MotifPipeline hands to the scorer."""
     e = eidx.contiguous()
     B, W, _ = e.shape
     dt = torch.uint8 if u8 else torch.float32
+    shape = (B, W, 3, 4) if u8 else (B, W, 3, 3)        # bytes: three counts and a pad byte per walk event
     if out is None:
-        out = torch.empty((B, W, 3, 3), dtype=dt, device=e.device)
-    elif out.dtype != dt:
-        raise ValueError("edge_identity_device: out must be %s" % dt)
+        out = torch.empty(shape, dtype=dt, device=e.device)
+    elif out.dtype != dt or tuple(out.shape) != shape:
+        raise ValueError("edge_identity_device: out must be %s %s" % (dt, shape))
     st = C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream)
     with torch.cuda.device(e.device):
         if u8:

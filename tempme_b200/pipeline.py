@@ -90,7 +90,7 @@ class MotifPipeline:
                       walks=(torch.empty((R, W, 6), dtype=i32, device=dev), torch.empty((R, W, 3), dtype=i32, device=dev),
                              torch.empty((R, W, 3), dtype=f32, device=dev), torch.empty((R, W), dtype=torch.uint8, device=dev)),
                       # edge-identity counts in their compact form (bytes, W <= 255) when the walks stay inside the pipeline
-                      eid=torch.empty((R, W, 3, 3), dtype=torch.uint8 if W <= 255 else f32, device=dev))
+                      eid=torch.empty((R, W, 3, 4), dtype=torch.uint8, device=dev) if W <= 255 else torch.empty((R, W, 3, 3), dtype=f32, device=dev))
             self._ws[R] = ws
         return ws
 

@@ -858,7 +858,7 @@ def test_edge_identity_bytes_equal_floats_and_score_alike(tm):
     nodes, we, wt, anony, cat = f.find_k_walks_device(10, src[q], 3, sub, seed=4)
     eid_f = tm.edge_identity_device(we)
     eid_b = tm.edge_identity_device(we, u8=True)
-    assert eid_b.dtype == torch.uint8 and torch.equal(eid_b.float(), eid_f)
+    assert eid_b.dtype == torch.uint8 and tuple(eid_b.shape) == (300, 30, 3, 4) and torch.equal(eid_b[..., :3].float(), eid_f) and int(eid_b[..., 3].max()) == 0
     nfeat = rng.standard_normal((300, 32)).astype(np.float32); efeat = rng.standard_normal((20001, 32)).astype(np.float32)
     torch.manual_seed(4)
     m = tm.TempME(_Base(nfeat, efeat), "tgn", "unit", 40, 64, device="cuda", null_model={}).cuda().eval()
