@@ -71,3 +71,39 @@ def test_product_does_not_import_oracle():
                 s = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M), f
                 assert "tempme_oracle" not in s, f
+
+
+def test_detect_fanout_host_logic():
+    """TempME.detect_fanout (the walk-layout hint of tm_encoder_desc.walk_fanout) on CPU tensors: find_k_walks' layout w = i1 * N2 + j gives N2;
+    shuffled walks give 1; small calls are skipped."""
+    import torch
+    from tempme_b200.explainer import TempME
+    B, n = 4, 5
+    for N2 in (1, 2, 3, 5):
+        W = n * N2
+        first = torch.arange(B * n, dtype=torch.int32).view(B, n)              # one distinct first-hop event per slot
+        e = torch.zeros((B, W, 3), dtype=torch.int32); nodes = torch.zeros((B, W, 6), dtype=torch.int32)
+        e[:, :, 2] = first.repeat_interleave(N2, dim=1)
+        nodes[:, :, 4] = 7; nodes[:, :, 5] = first.repeat_interleave(N2, dim=1) + 100
+        e[:, :, 1] = torch.arange(W, dtype=torch.int32)                         # the other positions differ per walk
+        TempME._fanout_seen.clear()
+        assert TempME.detect_fanout(e, nodes) == N2
+        assert TempME.detect_fanout(e, nodes) == N2                             # cached candidate first
+        assert TempME.detect_fanout(e, nodes, min_motifs=10 ** 6) == 1          # below the threshold: no test
+        if N2 > 1:
+            perm = torch.randperm(W, generator=torch.Generator().manual_seed(N2))
+            if not torch.equal(e[:, perm, 2].view(B, W // N2, N2), e[:, perm, 2].view(B, W // N2, N2)[:, :, :1].expand(B, W // N2, N2)):
+                assert TempME.detect_fanout(e[:, perm].contiguous(), nodes[:, perm].contiguous()) < N2 or N2 == 1
+    TempME._fanout_seen.clear()
+
+
+def test_executed_flops_accounting():
+    """bench.executed_flops: the position-2 event and the [S; P] product once per first-hop slot (walk groups)."""
+    import bench
+    D, H = 32, 64
+    M = H + 12
+    full = bench.executed_flops(D, D)
+    assert full == 4 * D * D + 12 * D * H + 2 * (2 * H * 3 * H + 2 * H * H + H * M + M * H + H)
+    g3 = bench.executed_flops(D, D, fanout=3)
+    assert abs((full - g3) - (2.0 / 3.0) * (4 * D * H + 2 * 2 * H * 3 * H)) < 1e-6
+    assert bench.executed_flops(D, D, fanout=1) == full
