@@ -423,6 +423,9 @@ __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cas
 // Motif rounds: U [0,2H) | Y [2H,3H) (one N = 3H accumulator of the [S; P] rounds) | A; then A2 = [0,64) over the dead U,
 // M0 [H, H + M16) and M1 [0,H) (single-buffer mode: M0 [0,M16), M1 [2H,3H)).
 // Tiles are handed out dynamically (CTA b starts with tile b, then takes gridDim.x + atomicAdd(counter)).
+// Walk groups (SHARE instantiations, see the template's comment): a tile is 128 first-hop slots; order per tile = position-2 pass, [S; P] rounds,
+// U + cu / P h_2 + cy parked in the CTA's scratch, then per sub-tile the passes of positions 0 and 1 (s_k taken in their epilogues) and the motif
+// rounds with Y = Q mix + the parked P h_2 + cy.  The TMEM layouts of the phases are the ones above.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 // The CTA's L2 scratch (h slabs, U / Y, drained E): written and read back within microseconds while feature rows and walk tensors stream
